@@ -1,0 +1,233 @@
+/*
+ * meshtok.h - C ABI of libmeshtok.so: the B200 (sm_100a) mesh-tokenization hot path of
+ * lucidrains/meshgpt-pytorch (MeshAutoencoder.tokenize / encode / quantize and
+ * derive_face_edges_from_faces).
+ *
+ * The reference has no FFI for this path (it is pure Python on torch eager ops); every entry point
+ * below names the reference code it replaces (paths relative to the reference repo root) and
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *  - All data pointers are DEVICE pointers borrowed for the duration of the call; the caller owns
+ *    every byte, including the workspace (size from the matching *_workspace_bytes query).
+ *  - Nothing allocates, nothing synchronises: work is enqueued on `stream` (a cudaStream_t) and
+ *    the call returns immediately.  Data-dependent sizes (number of valid faces, edges, referenced
+ *    vertices) stay on the device; grids are sized for the worst case and trimmed on the device.
+ *  - Return value: 0 on success, a negative meshtok_status otherwise; meshtok_last_error_string()
+ *    gives the thread-local reason.  Data errors that can only be seen on the device (vertex id out
+ *    of range, edge buffer too small) set bits in the int32 status word at the start of the
+ *    workspace (MESHTOK_WS_STATUS_*); the host wrapper reads it when it next synchronises.
+ *  - Integer tensors are int64 at this surface (what torch.randint / the reference produce) and
+ *    int32 inside; activations are fp32 row-major; there is no CPU implementation.
+ */
+#ifndef MESHTOK_H_
+#define MESHTOK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MESHTOK_ABI_VERSION 1
+
+typedef void* meshtok_stream_t; /* cudaStream_t */
+
+enum meshtok_status {
+  MESHTOK_OK = 0,
+  MESHTOK_ERR_INVALID_ARGUMENT = -1,
+  MESHTOK_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were built for */
+  MESHTOK_ERR_CUDA = -3,        /* a CUDA runtime call failed (see last_error_string) */
+  MESHTOK_ERR_WORKSPACE = -4    /* workspace too small / misaligned */
+};
+
+/* bits of the device-side status word (int32 at workspace offset 0) */
+#define MESHTOK_WS_STATUS_VERTEX_RANGE 1 /* a non-pad face references a vertex id outside [0, V) */
+#define MESHTOK_WS_STATUS_EDGE_OVERFLOW 2 /* more edges than edge_capacity */
+#define MESHTOK_WS_STATUS_EDGE_RANGE 4    /* a user-supplied edge references a face row outside the batch */
+
+int meshtok_version(void);
+const char* meshtok_last_error_string(void);
+
+/* Number of kernels this library has launched since it was loaded (process wide). */
+int64_t meshtok_kernel_launch_count(void);
+
+/* Optional device-side section timing: when enabled, the pipeline brackets each group of kernels with
+ * cudaEvents on the caller's stream.  meshtok_profile_collect synchronises on those events, ADDS the elapsed
+ * milliseconds and launch counts of each section into the caller's arrays (length >= meshtok_profile_sections())
+ * and forgets them.  Section names: meshtok_profile_section_name(i). */
+int meshtok_profile_enable(int on);
+int meshtok_profile_sections(void);
+const char* meshtok_profile_section_name(int section);
+int meshtok_profile_collect(float* ms_per_section, int32_t* events_per_section, int n);
+
+/* ------------------------------------------------------------------------------------------
+ * Model description: dimensions + device pointers to the weights, laid out as the reference's
+ * state_dict holds them (row-major fp32, nn.Linear weight = (out, in)) plus the tensors the host
+ * wrapper derives once at load time (folded embedding tables, fp16 codebook image).
+ * Replaces: the nn.Module attribute tree built in meshgpt_pytorch/meshgpt_pytorch.py:431-602.
+ * ------------------------------------------------------------------------------------------ */
+#define MESHTOK_MAX_SAGE_LAYERS 8
+
+typedef struct meshtok_sage_layer {
+  int32_t dim_in, dim_out;
+  const float* lin_w;   /* (dim_in, dim_in)  SAGEConv.lin.weight   */
+  const float* lin_b;   /* (dim_in)          SAGEConv.lin.bias     */
+  const float* cat_w;   /* (dim_out, 2*dim_in) = [lin_l.weight | lin_r.weight] concatenated along K */
+  const float* lin_l_b; /* (dim_out)         SAGEConv.lin_l.bias   */
+  const void* lin_w_img; /* split-bf16 UMMA images of lin_w / cat_w (meshtok_linear_build_image); may be NULL */
+  const void* cat_w_img; /* when the caller only uses gemm_simt */
+} meshtok_sage_layer;
+
+typedef struct meshtok_model {
+  int32_t abi_version;   /* MESHTOK_ABI_VERSION */
+  int32_t nvf;           /* 3 triangles, 4 quads            (meshgpt_pytorch.py:495-497) */
+  int32_t dim_codebook;  /* 192                              (:452) */
+  int32_t num_quantizers;/* 2                                (:453) */
+  int32_t codebook_size; /* 16384                            (:454) */
+  int32_t use_lfq;       /* 1 ResidualLFQ, 0 ResidualVQ      (:455) */
+  int32_t num_sage_layers;        /* 5 = init_sage_conv + 4 encoders (:442-444, 543-560) */
+  int32_t num_discrete_coors, num_discrete_angle, num_discrete_area, num_discrete_normals; /* :433-440 */
+  float coor_lo, coor_hi;         /* coor_continuous_range (:434) */
+  /* folded tables: slot s of the concatenated embedding (coords nvf*3, angles nvf, area 1, normals 3)
+   * -> table[s][bin][dim_codebook] = Embedding.weight[bin] @ project_in.weight[:, cols(s)]^T.
+   * slot_bins[s] = number of bins of slot s; slot_offset[s] = first table row of slot s. */
+  int32_t num_slots;
+  const float* folded_tables;     /* (sum_s bins_s, dim_codebook) */
+  const float* project_in_bias;   /* (dim_codebook) */
+  meshtok_sage_layer sage[MESHTOK_MAX_SAGE_LAYERS];
+  const float* ln_gamma;          /* init_encoder_act_and_norm.1.weight (dims[0]) */
+  const float* ln_beta;           /* init_encoder_act_and_norm.1.bias */
+  const float* pdc_w;             /* project_dim_codebook.weight (nvf*dim_codebook, dims[-1]) */
+  const float* pdc_b;             /* project_dim_codebook.bias */
+  const void* pdc_w_img;          /* split-bf16 UMMA image of pdc_w */
+  /* ResidualVQ (use_lfq == 0) */
+  const float* codebook;          /* (codebook_size, dim_codebook) fp32 */
+  const float* codebook_sqnorm;   /* (codebook_size) fp32  sum_d e^2 */
+  const void* codebook_f16_tiles; /* UMMA-canonical fp16 image of codebook * codebook_image_scale,
+                                     see meshtok_rvq_codebook_image_bytes / _build_codebook_image */
+  float codebook_image_scale;     /* power of two bringing max |e_jd| into [0.5, 1) */
+  float codebook_max_norm;        /* max_j |e_j|_2 (bounds the fp16 screening error) */
+  /* ResidualLFQ (use_lfq == 1) */
+  const float* lfq_in_w;          /* quantizer.project_in.weight (log2 K, dim_codebook) */
+  const float* lfq_in_b;          /* quantizer.project_in.bias */
+  const float* lfq_out_w;         /* quantizer.project_out.weight (dim_codebook, log2 K) (quantize() only) */
+  const float* lfq_out_b;
+} meshtok_model;
+
+/* ------------------------------------------------------------------------------------------
+ * K1  face adjacency.        Replaces derive_face_edges_from_faces, meshgpt_pytorch/data.py:297-340
+ * One CTA per mesh: vertex->(face,slot) incidence by counting sort in shared memory, per-face
+ * neighbour bitmaps, popc/prefix compaction.  Vertex ids must lie in [0, V); pad faces are faces
+ * with ANY slot == pad_id.  threshold = 2 (1 when neighbor_if_share_one_vertex), include_self as in
+ * the reference (pairs with exactly 3 shared slots dropped when 0).
+ *
+ * Two-phase dense API (the output length is data dependent):
+ *   count: edge_counts[b] = number of directed edges of mesh b     (int32, device)
+ *   fill : out (B, emax, 2) int64, rows sorted (i, then j), tail padded with pad_id
+ * ------------------------------------------------------------------------------------------ */
+int meshtok_topology_workspace_bytes(int B, int F, int nvf, int V, int E_user, size_t* bytes);
+
+int meshtok_face_edges_count(const int64_t* faces, int B, int F, int nvf, int V, int64_t pad_id,
+                             int threshold, int include_self, void* workspace, size_t workspace_bytes,
+                             int32_t* edge_counts, meshtok_stream_t stream);
+
+int meshtok_face_edges_fill(const int64_t* faces, int B, int F, int nvf, int V, int64_t pad_id,
+                            int threshold, int include_self, void* workspace, size_t workspace_bytes,
+                            int emax, int64_t* out_edges, meshtok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole pipeline.  Replaces MeshAutoencoder.forward(return_codes=True) / tokenize,
+ * meshgpt_pytorch/meshgpt_pytorch.py:949-1019 (encode :686-785, quantize :787-870).
+ *
+ *  vertices (B,V,3) fp32; faces (B,F,nvf) int64 padded with pad_id; face_edges (B,E,2) int64 or NULL
+ *  (NULL => derived on the device, never materialised as a dense list).
+ *  codes_out (B, F*nvf, Q) int64: codes, pad_id on padded tokens.
+ *  Optional outputs (NULL to skip):
+ *    encoded_out      (B,F,dims[-1]) fp32, zero on padded faces         (encode()'s first result)
+ *    face_coords_out  (B,F,nvf*3) int64 discretised coordinates          (encode()'s second result)
+ *    quantized_out    (B,F,nvf*dim_codebook) fp32                        (quantize()'s first result)
+ *    histogram        (Q, codebook_size) int64, ACCUMULATED (+=) over non-pad tokens
+ *  encoded_in (B,F,dims[-1]) fp32 or NULL: when given the encoder is skipped and quantize() runs on
+ *  it (this is MeshAutoencoder.quantize as a stand-alone call).
+ *  edge_capacity: number of int32 edge slots reserved in the workspace (derived or user edges).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct meshtok_tokenize_args {
+  const float* vertices;
+  const int64_t* faces;
+  const int64_t* face_edges;
+  const float* encoded_in;
+  int32_t B, F, V, E;
+  int64_t pad_id;
+  int64_t edge_capacity;
+  int64_t* codes_out;
+  float* encoded_out;
+  int64_t* face_coords_out;
+  float* quantized_out;
+  int64_t* histogram;
+  int32_t stop_after_encode; /* 1: encode() only (codes_out may be NULL) */
+  int32_t rvq_exact;         /* 1: fp32 SIMT search instead of the tcgen05 screening + re-score */
+  int32_t gemm_simt;         /* 1: fp32 SIMT linears instead of the tcgen05 split-bf16 GEMM */
+} meshtok_tokenize_args;
+
+int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E,
+                                     int64_t edge_capacity, size_t* bytes);
+
+int meshtok_tokenize(const meshtok_model* model, const meshtok_tokenize_args* args, void* workspace,
+                     size_t workspace_bytes, meshtok_stream_t stream);
+
+/* Debug / parity taps: after meshtok_tokenize, describes where the intermediate tensors live inside
+ * the workspace (byte offsets) so tests can compare them stage by stage with the oracle. */
+typedef struct meshtok_taps {
+  int64_t status;          /* int32 status word */
+  int64_t counts;          /* int32[4]: n_faces (valid), n_vertex_rows, n_edges, reserved */
+  int64_t face_row;        /* int32 (B*F): packed row of each face or -1 */
+  int64_t vert_row;        /* int32 (B*V): quantizer row of each vertex or -1 */
+  int64_t indptr;          /* int32 (B*F+1): CSR by target face row */
+  int64_t src;             /* int32 (edge_capacity): source face rows */
+  int64_t x0;              /* fp32 (B*F, dim_codebook): project_in output, packed rows */
+  int64_t layer_out[MESHTOK_MAX_SAGE_LAYERS]; /* fp32 (B*F, dim_out): output of each SAGE layer (layer 0: after act+norm) */
+  int64_t averaged;        /* fp32 (B*V, dim_codebook): scatter-mean rows (vert_row order) */
+  int64_t vertex_codes;    /* int32 (B*V, Q) */
+} meshtok_taps;
+
+int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                          meshtok_taps* taps);
+
+/* ------------------------------------------------------------------------------------------
+ * Stage entry points used by the parity tests with oracle-injected inputs.
+ * ------------------------------------------------------------------------------------------ */
+
+/* K8b residual LFQ on given rows.  Replaces vector_quantize_pytorch.ResidualLFQ.forward (eval),
+ * called at meshgpt_pytorch.py:842.  rows (R, dim) fp32 -> codes (R, Q) int32. */
+int meshtok_lfq_codes(const meshtok_model* model, const float* rows, int R, int32_t* codes,
+                      meshtok_stream_t stream);
+
+/* K8a residual VQ on given rows.  Replaces vector_quantize_pytorch.ResidualVQ.forward (eval, shared
+ * codebook), called at meshgpt_pytorch.py:842.  rows (R, dim) fp32 -> codes (R, Q) int32.
+ * exact != 0: fp32 SIMT search; 0: tcgen05 fp16 screening + fp32 re-score. */
+int meshtok_rvq_workspace_bytes(const meshtok_model* model, int R, size_t* bytes);
+int meshtok_rvq_codes(const meshtok_model* model, const float* rows, int R, int exact, int32_t* codes,
+                      float* residual_out /* (R, dim) or NULL */, void* workspace, size_t workspace_bytes,
+                      meshtok_stream_t stream);
+
+/* Size / builder of the UMMA-canonical fp16 codebook image (codebook * scale, scale a power of two)
+ * consumed by the tcgen05 search. */
+int meshtok_rvq_codebook_image_bytes(int codebook_size, int dim, size_t* bytes);
+int meshtok_rvq_build_codebook_image(const float* codebook, int codebook_size, int dim, float scale, void* image,
+                                     meshtok_stream_t stream);
+
+/* Dense linear C = act(A W^T + b).  Replaces torch.nn.functional.linear at meshgpt_pytorch.py:741, 803 and
+ * inside SAGEConv.  A (M, K) fp32; W (N, K) fp32; C (M, N) fp32.  relu: 0/1.
+ * simt != 0: fp32 SIMT kernel reading W.  simt == 0: tcgen05 split-bf16 kernel reading w_image, the
+ * (N*K*4 byte) hi/lo bf16 UMMA image of W built once by meshtok_linear_build_image. */
+int meshtok_linear_image_bytes(int N, int K, size_t* bytes);
+int meshtok_linear_build_image(const float* W, int N, int K, void* image, meshtok_stream_t stream);
+int meshtok_linear(const float* A, const float* W, const void* w_image, const float* bias, float* C, int M, int N,
+                   int K, int relu, int simt, meshtok_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MESHTOK_H_ */

@@ -1,0 +1,12 @@
+"""meshgpt_pytorch_b200 - B200-native (sm_100a) mesh tokenization: the hot path of
+lucidrains/meshgpt-pytorch's MeshAutoencoder.tokenize / encode / quantize and
+derive_face_edges_from_faces behind the reference's own Python signatures.
+
+Importing the package loads libmeshtok.so (hand-written CUDA kernels behind a C ABI, include/meshtok.h);
+it raises ImportError if the library has not been built - there is no CPU or PyTorch fallback.
+"""
+from ._lib import LIB_PATH, MeshtokError  # noqa: F401  (loads the shared library)
+from .autoencoder import MeshAutoencoder, ResidualLFQ, ResidualVQ, SAGEConv  # noqa: F401
+from .data import derive_face_edges_from_faces  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,469 @@
+"""Host-side mirror of the tokenization half of meshgpt_pytorch.MeshAutoencoder.
+
+Same constructor keywords, same state-dict key names, same method signatures and tensor contracts as the
+reference (meshgpt_pytorch/meshgpt_pytorch.py:428-1019) for
+    tokenize / forward(return_codes=True) / encode / quantize,
+but every FLOP runs in libmeshtok's sm_100a CUDA kernels through the C ABI (include/meshtok.h).  PyTorch is
+used for parameter storage, device memory and streams only.  There is no CPU path: inputs must be CUDA
+tensors, and importing this module fails if the library has not been built.
+
+Out of scope: the decoder (decode, decode_from_codes_to_faces, the reconstruction loss),
+the optional encoder attention blocks (attn_encoder_depth must be 0) and training.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import MeshtokError, Model, Taps, TokenizeArgs, check, lib, ptr, stream_ptr
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers with the reference's key names
+# ---------------------------------------------------------------------------------------------------
+
+
+class SAGEConv(nn.Module):
+    """Parameters of torch_geometric.nn.SAGEConv(in, out, normalize=True, project=True): lin (in->in, bias),
+    lin_l (in->out, bias), lin_r (in->out, no bias).  Compute lives in the CUDA kernels."""
+
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.lin = nn.Linear(dim_in, dim_in, bias=True)
+        self.lin_l = nn.Linear(dim_in, dim_out, bias=True)
+        self.lin_r = nn.Linear(dim_in, dim_out, bias=False)
+
+
+class ResidualLFQ(nn.Module):
+    """Parameters of vector_quantize_pytorch.ResidualLFQ that tokenization touches: project_in
+    (dim -> log2 K) and project_out (log2 K -> dim)."""
+
+    def __init__(self, dim: int, num_quantizers: int, codebook_size: int):
+        super().__init__()
+        bits = int(round(math.log2(codebook_size)))
+        assert 2 ** bits == codebook_size, "ResidualLFQ needs a power-of-two codebook_size"
+        self.project_in = nn.Linear(dim, bits)
+        self.project_out = nn.Linear(bits, dim)
+
+
+class _EuclideanCodebook(nn.Module):
+    def __init__(self, codebook_size: int, dim: int, init_std: float):
+        super().__init__()
+        self.register_buffer("embed", torch.randn(1, codebook_size, dim) * init_std)
+        self.register_buffer("embed_avg", self.embed.clone())
+        self.register_buffer("cluster_size", torch.zeros(1, codebook_size))
+        self.register_buffer("initted", torch.tensor([True]))
+
+
+class _VectorQuantize(nn.Module):
+    def __init__(self, codebook: _EuclideanCodebook):
+        super().__init__()
+        self._codebook = codebook
+
+
+class ResidualVQ(nn.Module):
+    """Buffers of vector_quantize_pytorch.ResidualVQ(shared_codebook=True): layers.{l}._codebook.embed
+    (1, K, D), aliased across levels.  The reference k-means-initialises the codebook on the first batch;
+    here it is an explicit tensor (random normal * init_std until a state dict is loaded) with initted=True."""
+
+    def __init__(self, dim: int, num_quantizers: int, codebook_size: int, init_std: float = 0.05):
+        super().__init__()
+        shared = _EuclideanCodebook(codebook_size, dim, init_std)
+        self.layers = nn.ModuleList([_VectorQuantize(shared) for _ in range(num_quantizers)])
+
+    @property
+    def codebook(self) -> Tensor:
+        return self.layers[0]._codebook.embed[0]
+
+
+# ---------------------------------------------------------------------------------------------------
+
+
+class MeshAutoencoder(nn.Module):
+    def __init__(
+        self,
+        num_discrete_coors=128,
+        coor_continuous_range: Tuple[float, float] = (-1.0, 1.0),
+        dim_coor_embed=64,
+        num_discrete_area=128,
+        dim_area_embed=16,
+        num_discrete_normals=128,
+        dim_normal_embed=64,
+        num_discrete_angle=128,
+        dim_angle_embed=16,
+        encoder_dims_through_depth: Tuple[int, ...] = (64, 128, 256, 256, 576),
+        dim_codebook=192,
+        num_quantizers=2,
+        codebook_size=16384,
+        use_residual_lfq=True,
+        sageconv_kwargs: dict = dict(normalize=True, project=True),
+        attn_encoder_depth=0,
+        pad_id=-1,
+        quads=False,
+        rvq_codebook_init_std=0.05,
+        **decoder_and_training_kwargs,   # accepted for signature compatibility, unused by tokenization
+    ):
+        super().__init__()
+        if attn_encoder_depth != 0:
+            raise NotImplementedError("attn_encoder_depth > 0 is out of scope for the B200 tokenization path")
+        if dict(sageconv_kwargs) != dict(normalize=True, project=True):
+            raise NotImplementedError("only SAGEConv(normalize=True, project=True) is implemented")
+        if len(encoder_dims_through_depth) > _lib.MAX_SAGE_LAYERS:
+            raise NotImplementedError(f"at most {_lib.MAX_SAGE_LAYERS} SAGE layers")
+        self.num_vertices_per_face = 4 if quads else 3
+        nvf = self.num_vertices_per_face
+        self.num_discrete_coors = num_discrete_coors
+        self.num_discrete_area = num_discrete_area
+        self.num_discrete_normals = num_discrete_normals
+        self.num_discrete_angle = num_discrete_angle
+        self.coor_continuous_range = tuple(float(x) for x in coor_continuous_range)
+        self.dim_codebook = dim_codebook
+        self.num_quantizers = num_quantizers
+        self.codebook_size = codebook_size
+        self.use_residual_lfq = use_residual_lfq
+        self.encoder_dims = tuple(encoder_dims_through_depth)
+        self.pad_id = pad_id
+
+        self.coor_embed = nn.Embedding(num_discrete_coors, dim_coor_embed)
+        self.angle_embed = nn.Embedding(num_discrete_angle, dim_angle_embed)
+        self.area_embed = nn.Embedding(num_discrete_area, dim_area_embed)
+        self.normal_embed = nn.Embedding(num_discrete_normals, dim_normal_embed)
+        init_dim = dim_coor_embed * 3 * nvf + dim_angle_embed * nvf + dim_normal_embed * 3 + dim_area_embed
+        self.project_in = nn.Linear(init_dim, dim_codebook)
+
+        first, *rest = encoder_dims_through_depth
+        self.init_sage_conv = SAGEConv(dim_codebook, first)
+        self.init_encoder_act_and_norm = nn.Sequential(nn.SiLU(), nn.LayerNorm(first))
+        self.encoders = nn.ModuleList()
+        cur = first
+        for d in rest:
+            self.encoders.append(SAGEConv(cur, d))
+            cur = d
+        self.project_dim_codebook = nn.Linear(cur, dim_codebook * nvf)
+        if use_residual_lfq:
+            self.quantizer = ResidualLFQ(dim_codebook, num_quantizers, codebook_size)
+        else:
+            self.quantizer = ResidualVQ(dim_codebook, num_quantizers, codebook_size, rvq_codebook_init_std)
+
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._prep: Optional[dict] = None
+        self._prep_key = None
+        self._ws_cache: Dict[tuple, Tensor] = {}
+        self.force_gemm_simt = False      # parity tests: fp32 SIMT linears instead of tcgen05 split-bf16
+        self.force_rvq_exact = False      # parity tests: fp32 SIMT nearest-code scan instead of tcgen05 screening
+        self.edge_slots_per_face = 8      # initial CSR capacity; grown automatically on overflow
+        self.last_workspace: Optional[Tensor] = None
+        self.last_shape: Optional[tuple] = None
+
+    # ---- weights ----------------------------------------------------------------------------------
+    def load_reference_state_dict(self, state_dict: Dict[str, Tensor]):
+        """Loads a reference MeshAutoencoder.state_dict(); decoder / loss keys are ignored, every key of the
+        tokenization half must be present."""
+        own = self.state_dict()
+        missing = [k for k in own if k not in state_dict]
+        if missing:
+            raise KeyError(f"state dict lacks tokenization keys: {missing[:8]}{'...' if len(missing) > 8 else ''}")
+        self.load_state_dict({k: state_dict[k] for k in own}, strict=True)
+        self._prep = None
+        return [k for k in state_dict if k not in own]
+
+    @property
+    def device(self):
+        return self.project_in.weight.device
+
+    def _weights_key(self):
+        return tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+
+    def _sage_layers(self):
+        return [self.init_sage_conv, *self.encoders]
+
+    def _prepare(self) -> dict:
+        key = self._weights_key()
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        dev = self.device
+        if dev.type != "cuda":
+            raise RuntimeError("MeshAutoencoder must live on a CUDA device (call .cuda()); there is no CPU path")
+        keep = {}
+        nvf, D = self.num_vertices_per_face, self.dim_codebook
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        # fold Embedding -> project_in into one (bins, D) table per slot of the concat (meshgpt_pytorch.py:735-741)
+        W = self.project_in.weight.detach().double()
+        tables, col = [], 0
+        for emb, reps in ((self.coor_embed, nvf * 3), (self.angle_embed, nvf), (self.area_embed, 1), (self.normal_embed, 3)):
+            E = emb.weight.detach().double()
+            d = E.shape[1]
+            for _ in range(reps):
+                tables.append(E @ W[:, col:col + d].t())
+                col += d
+        assert col == W.shape[1]
+        keep["tables"] = torch.cat(tables, 0).to(**f32).contiguous()
+        keep["pin_b"] = self.project_in.bias.detach().to(**f32).contiguous()
+
+        m = Model()
+        m.abi_version = _lib.ABI_VERSION
+        m.nvf, m.dim_codebook, m.num_quantizers, m.codebook_size = nvf, D, self.num_quantizers, self.codebook_size
+        m.use_lfq = int(self.use_residual_lfq)
+        m.num_discrete_coors, m.num_discrete_angle = self.num_discrete_coors, self.num_discrete_angle
+        m.num_discrete_area, m.num_discrete_normals = self.num_discrete_area, self.num_discrete_normals
+        m.coor_lo, m.coor_hi = self.coor_continuous_range
+        m.num_slots = nvf * 4 + 4
+        m.folded_tables, m.project_in_bias = ptr(keep["tables"]), ptr(keep["pin_b"])
+
+        def image_of(w: Tensor, name: str):
+            n, k = w.shape
+            nbytes = C.c_size_t()
+            if lib.meshtok_linear_image_bytes(n, k, C.byref(nbytes)) != 0:
+                return 0                       # shape not covered by the tcgen05 kernel -> SIMT for this model
+            img = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            check(lib.meshtok_linear_build_image(ptr(w), n, k, ptr(img), stream_ptr()))
+            keep[name] = img
+            return ptr(img)
+
+        layers = self._sage_layers()
+        m.num_sage_layers = len(layers)
+        all_images = True
+        with torch.cuda.device(dev):
+            for i, conv in enumerate(layers):
+                lw = conv.lin.weight.detach().to(**f32).contiguous()
+                lb = conv.lin.bias.detach().to(**f32).contiguous()
+                cw = torch.cat([conv.lin_l.weight.detach(), conv.lin_r.weight.detach()], dim=1).to(**f32).contiguous()
+                cb = conv.lin_l.bias.detach().to(**f32).contiguous()
+                keep[f"sage{i}"] = (lw, lb, cw, cb)
+                s = m.sage[i]
+                s.dim_in, s.dim_out = lw.shape[0], cw.shape[0]
+                s.lin_w, s.lin_b, s.cat_w, s.lin_l_b = ptr(lw), ptr(lb), ptr(cw), ptr(cb)
+                s.lin_w_img = image_of(lw, f"sage{i}_lin_img")
+                s.cat_w_img = image_of(cw, f"sage{i}_cat_img")
+                all_images &= bool(s.lin_w_img) and bool(s.cat_w_img)
+            ln = self.init_encoder_act_and_norm[1]
+            keep["ln"] = (ln.weight.detach().to(**f32).contiguous(), ln.bias.detach().to(**f32).contiguous())
+            m.ln_gamma, m.ln_beta = ptr(keep["ln"][0]), ptr(keep["ln"][1])
+            keep["pdc"] = (self.project_dim_codebook.weight.detach().to(**f32).contiguous(),
+                           self.project_dim_codebook.bias.detach().to(**f32).contiguous())
+            m.pdc_w, m.pdc_b = ptr(keep["pdc"][0]), ptr(keep["pdc"][1])
+            m.pdc_w_img = image_of(keep["pdc"][0], "pdc_img")
+            all_images &= bool(m.pdc_w_img)
+
+            rvq_tc_ok = False
+            if self.use_residual_lfq:
+                q = self.quantizer
+                keep["lfq"] = tuple(t.detach().to(**f32).contiguous() for t in
+                                    (q.project_in.weight, q.project_in.bias, q.project_out.weight, q.project_out.bias))
+                m.lfq_in_w, m.lfq_in_b, m.lfq_out_w, m.lfq_out_b = (ptr(t) for t in keep["lfq"])
+            else:
+                cb = self.quantizer.codebook.detach().to(**f32).contiguous()
+                e2 = (cb * cb).sum(dim=-1).contiguous()
+                keep["cb"] = (cb, e2)
+                m.codebook, m.codebook_sqnorm = ptr(cb), ptr(e2)
+                m.codebook_max_norm = float(e2.max().sqrt()) * (1 + 1e-6)
+                amax = float(cb.abs().max())
+                scale = 1.0 if not (amax > 0 and math.isfinite(amax)) else 2.0 ** (-math.frexp(amax)[1])
+                m.codebook_image_scale = scale
+                nbytes = C.c_size_t()
+                K, Dd = cb.shape
+                if K % 128 == 0 and Dd in (64, 128, 192):
+                    check(lib.meshtok_rvq_codebook_image_bytes(K, Dd, C.byref(nbytes)))
+                    img = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                    check(lib.meshtok_rvq_build_codebook_image(ptr(cb), K, Dd, scale, ptr(img), stream_ptr()))
+                    keep["cb_img"] = img
+                    m.codebook_f16_tiles = ptr(img)
+                    rvq_tc_ok = True
+        self._prep = dict(model=m, keep=keep, tc_gemm=all_images, tc_rvq=rvq_tc_ok, device=dev)
+        self._prep_key = key
+        self._ws_cache.clear()
+        return self._prep
+
+    # ---- the pipeline call ------------------------------------------------------------------------
+    def _workspace(self, prep, B, F, V, E, cap) -> Tensor:
+        key = (B, F, V, E, cap)
+        ws = self._ws_cache.get(key)
+        if ws is None:
+            nbytes = C.c_size_t()
+            check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, E, cap, C.byref(nbytes)))
+            if len(self._ws_cache) > 4:
+                self._ws_cache.clear()
+            ws = torch.empty(nbytes.value, dtype=torch.uint8, device=prep["device"])
+            self._ws_cache[key] = ws
+        return ws
+
+    def _run(self, *, vertices, faces, face_edges=None, encoded_in=None, want_codes=True, want_encoded=False,
+             want_face_coords=False, want_quantized=False, histogram=None, check_status=True):
+        prep = self._prepare()
+        dev = prep["device"]
+        if not faces.is_cuda:
+            raise RuntimeError("inputs must be CUDA tensors (no CPU path)")
+        nvf, D, Q = self.num_vertices_per_face, self.dim_codebook, self.num_quantizers
+        B, F, nv = faces.shape
+        assert nv == nvf, f"faces must have {nvf} vertices per face"          # meshgpt_pytorch.py:707-709
+        faces64 = faces.to(torch.int64).contiguous()
+        if vertices is not None:
+            vertices = vertices.to(torch.float32).contiguous()
+            V = vertices.shape[1]
+        else:
+            V = int(faces64.amax().item()) + 1                                     # quantize(): meshgpt_pytorch.py:800-801
+            V = max(V, 1)
+        E = 0
+        if face_edges is not None:
+            face_edges = face_edges.to(torch.int64).contiguous()
+            if face_edges.shape[1] == 0:
+                face_edges = torch.full((B, 1, 2), self.pad_id, dtype=torch.int64, device=dev)
+            E = face_edges.shape[1]
+        enc_dim = self.encoder_dims[-1]
+        if encoded_in is not None:
+            encoded_in = encoded_in.to(torch.float32).contiguous()
+            assert encoded_in.shape == (B, F, enc_dim)
+
+        out = {}
+        if want_codes:
+            out["codes"] = torch.empty((B, F * nvf, Q), dtype=torch.int64, device=dev)
+        if want_encoded:
+            out["encoded"] = torch.empty((B, F, enc_dim), dtype=torch.float32, device=dev)
+        if want_face_coords:
+            out["face_coords"] = torch.empty((B, F, nvf * 3), dtype=torch.int64, device=dev)
+        if want_quantized:
+            out["quantized"] = torch.empty((B, F, nvf * D), dtype=torch.float32, device=dev)
+
+        cap = max(1024, self.edge_slots_per_face * B * F, (B * E if E else 0))
+        with torch.cuda.device(dev):
+            while True:
+                ws = self._workspace(prep, B, F, V, E, cap)
+                a = TokenizeArgs()
+                a.vertices, a.faces, a.face_edges, a.encoded_in = ptr(vertices), ptr(faces64), ptr(face_edges), ptr(encoded_in)
+                a.B, a.F, a.V, a.E = B, F, V, E
+                a.pad_id, a.edge_capacity = int(self.pad_id), cap
+                a.codes_out = ptr(out.get("codes"))
+                a.encoded_out = ptr(out.get("encoded"))
+                a.face_coords_out = ptr(out.get("face_coords"))
+                a.quantized_out = ptr(out.get("quantized"))
+                a.histogram = ptr(histogram)
+                a.stop_after_encode = int(not want_codes and not want_quantized)
+                a.rvq_exact = int(self.force_rvq_exact or not prep["tc_rvq"])
+                a.gemm_simt = int(self.force_gemm_simt or not prep["tc_gemm"])
+                check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
+                self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
+                if not check_status:
+                    break
+                status = int(ws[:4].view(torch.int32).item())
+                if status & _lib.WS_STATUS_EDGE_OVERFLOW and face_edges is None:
+                    cap *= 4                       # rare: very high-valence meshes; rerun with a larger edge buffer
+                    self.edge_slots_per_face *= 4
+                    if histogram is not None:
+                        raise MeshtokError("edge buffer overflow while accumulating a histogram; raise edge_slots_per_face")
+                    continue
+                self._raise_on_status(status)
+                break
+        return out
+
+    @staticmethod
+    def _raise_on_status(status: int):
+        if status & _lib.WS_STATUS_VERTEX_RANGE:
+            raise IndexError("faces reference a vertex index outside [0, num_vertices) (the reference's gather would fail too)")
+        if status & _lib.WS_STATUS_EDGE_RANGE:
+            raise IndexError("face_edges reference a face outside the batch")
+        if status & _lib.WS_STATUS_EDGE_OVERFLOW:
+            raise MeshtokError("edge buffer overflow")
+
+    def check_last_status(self):
+        """Deferred form of the data-error check for callers that ran with check_status=False."""
+        if self.last_workspace is not None:
+            self._raise_on_status(int(self.last_workspace[:4].view(torch.int32).item()))
+
+    def taps(self) -> Dict[str, Tensor]:
+        """Views of the intermediate tensors of the last call (stage-wise parity tests)."""
+        prep = self._prepare()
+        B, F, V, E, cap = self.last_shape
+        t = Taps()
+        check(lib.meshtok_tokenize_taps(C.byref(prep["model"]), B, F, V, E, cap, C.byref(t)))
+        ws = self.last_workspace
+
+        def view(off, n, dtype):
+            size = torch.empty((), dtype=dtype).element_size()
+            return ws[off: off + n * size].view(dtype)
+
+        counts = view(t.counts, 4, torch.int32).tolist()
+        nf, nvr, ne = counts[0], counts[1], counts[2]
+        D, Q = self.dim_codebook, self.num_quantizers
+        res = dict(n_faces=nf, n_vrows=nvr, n_edges=ne,
+                   face_row=view(t.face_row, B * F, torch.int32).view(B, F),
+                   vert_row=view(t.vert_row, B * V, torch.int32).view(B, V),
+                   indptr=view(t.indptr, nf + 1, torch.int32),
+                   src=view(t.src, min(ne, cap), torch.int32),
+                   x0=view(t.x0, nf * D, torch.float32).view(nf, D),
+                   averaged=view(t.averaged, nvr * D, torch.float32).view(nvr, D),
+                   vertex_codes=view(t.vertex_codes, nvr * Q, torch.int32).view(nvr, Q))
+        for i, d in enumerate(self.encoder_dims):
+            res[f"layer{i}"] = view(t.layer_out[i], nf * d, torch.float32).view(nf, d)
+        return res
+
+    # ---- reference API ----------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, *, vertices, faces, face_edges, face_mask, face_edges_mask, return_face_coordinates=False):
+        """meshgpt_pytorch.py:686-785.  -> (b, nf, dims[-1]) fp32 [, (b, nf, nvf*3) int64]."""
+        faces = faces.masked_fill(~face_mask[:, :, None], self.pad_id)
+        face_edges = face_edges.masked_fill(~face_edges_mask[:, :, None], self.pad_id)
+        out = self._run(vertices=vertices, faces=faces, face_edges=face_edges, want_codes=False, want_encoded=True,
+                        want_face_coords=return_face_coordinates)
+        if not return_face_coordinates:
+            return out["encoded"]
+        return out["encoded"], out["face_coords"]
+
+    @torch.no_grad()
+    def quantize(self, *, faces, face_mask, face_embed, pad_id=None, rvq_sample_codebook_temp=1.0):
+        """meshgpt_pytorch.py:787-870.  -> (face_embed_output (b, nf, nvf*dim), codes (b, nf*nvf, q) int64,
+        commit_loss).  Eval semantics: no codebook sampling noise, commit loss is zero."""
+        faces = faces.masked_fill(~face_mask[:, :, None], self.pad_id)
+        out = self._run(vertices=None, faces=faces, encoded_in=face_embed, want_codes=True, want_quantized=True)
+        commit_loss = torch.zeros(self.num_quantizers, device=faces.device)
+        return out["quantized"], out["codes"], commit_loss
+
+    @torch.no_grad()
+    def forward(self, *, vertices, faces, face_edges=None, return_codes=False, histogram=None, check_status=True, **kwargs):
+        """meshgpt_pytorch.py:978-1019 with return_codes=True (the tokenization branch).  The training /
+        reconstruction branches are out of scope."""
+        if not return_codes:
+            raise NotImplementedError("only forward(return_codes=True) (tokenization) is implemented on this path")
+        if kwargs.get("return_recon_faces"):
+            raise AssertionError("cannot return reconstructed faces when just returning raw codes")
+        return self._run(vertices=vertices, faces=faces, face_edges=face_edges, histogram=histogram,
+                         check_status=check_status)["codes"]
+
+    @torch.no_grad()
+    def tokenize(self, vertices, faces, face_edges=None, **kwargs):
+        """meshgpt_pytorch.py:949-976.  vertices (b, nv, 3), faces (b, nf, nvf) padded with pad_id, optional
+        face_edges (b, e, 2) -> codes (b, nf*nvf, num_quantizers) int64 (batch-less inputs allowed)."""
+        assert "return_codes" not in kwargs
+        given = [t for t in (vertices, faces, face_edges) if t is not None]
+        ndims = {t.ndim for t in given}
+        assert len(ndims) == 1
+        batch_less = ndims.pop() == 2
+        if batch_less:
+            vertices, faces = vertices[None], faces[None]
+            face_edges = None if face_edges is None else face_edges[None]
+        self.eval()
+        codes = self.forward(vertices=vertices, faces=faces, face_edges=face_edges, return_codes=True, **kwargs)
+        return codes[0] if batch_less else codes
+
+    # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
+    @torch.no_grad()
+    def tokenize_host(self, vertices: Tensor, faces: Tensor, face_edges: Optional[Tensor] = None, pinned_out: Optional[Tensor] = None):
+        """Host tensors in, host tensor out: H2D copies, the device pipeline and the D2H copy of the codes,
+        all on the current stream; returns after the codes have landed."""
+        dev = self.device
+        v = vertices.to(dev, non_blocking=True)
+        f = faces.to(dev, non_blocking=True)
+        e = None if face_edges is None else face_edges.to(dev, non_blocking=True)
+        codes = self.forward(vertices=v, faces=f, face_edges=e, return_codes=True, check_status=False)
+        if pinned_out is None:
+            pinned_out = torch.empty(codes.shape, dtype=codes.dtype, pin_memory=True)
+        pinned_out.copy_(codes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.check_last_status()
+        return pinned_out

@@ -1,0 +1,534 @@
+// extern "C" surface of libmeshtok.so (see include/meshtok.h) and the per-batch pipeline driver.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "topology.cuh"
+
+namespace meshtok {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+// Bump allocator over the caller's workspace; with base == nullptr it only measures.
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <class T>
+  T* take(size_t n, int64_t* tap = nullptr) {
+    off = align_up(off, 256);
+    if (tap) *tap = (int64_t)off;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct Workspace {
+  int* status;
+  Counts* counts;
+  int* mesh_counts;
+  int* offs;
+  int *deg_out, *deg_in, *face_row, *row_face, *vert_row, *vptr, *vinc, *indptr, *src;
+  int *ecount, *cursor, *etmp;
+  float* x0;
+  float *xp, *agg;
+  float* layer_out[MESHTOK_MAX_SAGE_LAYERS];
+  float* y;
+  float* avg;
+  float* resid;
+  float* rscale;
+  float* qrows;
+  float* pad_qrow;
+  float* zero_row;
+  int32_t* vcodes;
+  int32_t* best;
+  int* amb_list;
+  int* amb_count;
+  float4* partial;
+  size_t total;
+};
+
+int check_model(const meshtok_model* m) {
+  MT_CHECK_ARG(m != nullptr, "model is null");
+  MT_CHECK_ARG(m->abi_version == MESHTOK_ABI_VERSION, "model.abi_version %d != library %d", m->abi_version, MESHTOK_ABI_VERSION);
+  MT_CHECK_ARG(m->nvf == 3 || m->nvf == 4, "model.nvf must be 3 or 4");
+  MT_CHECK_ARG(m->num_sage_layers >= 1 && m->num_sage_layers <= MESHTOK_MAX_SAGE_LAYERS, "model.num_sage_layers out of range");
+  MT_CHECK_ARG(m->num_quantizers >= 1 && m->num_quantizers <= 8, "model.num_quantizers out of range");
+  MT_CHECK_ARG(m->dim_codebook >= 16 && m->dim_codebook % 16 == 0 && m->dim_codebook <= 512,
+               "model.dim_codebook must be a multiple of 16 in [16, 512]");
+  MT_CHECK_ARG(m->num_slots == m->nvf * 4 + 4, "model.num_slots must be nvf*4+4");
+  MT_CHECK_ARG(m->sage[0].dim_in == m->dim_codebook, "first SAGE layer must take dim_codebook inputs");
+  for (int l = 0; l < m->num_sage_layers; ++l) {
+    MT_CHECK_ARG(m->sage[l].dim_in % 16 == 0 && m->sage[l].dim_out % 4 == 0 && m->sage[l].dim_in <= 1024 && m->sage[l].dim_out <= 1024,
+                 "SAGE layer %d: dims (%d -> %d) must be multiples of 16 / 4 and <= 1024", l, m->sage[l].dim_in, m->sage[l].dim_out);
+    if (l) MT_CHECK_ARG(m->sage[l].dim_in == m->sage[l - 1].dim_out, "SAGE layer %d input width mismatch", l);
+  }
+  return MESHTOK_OK;
+}
+
+int enc_dim(const meshtok_model* m) { return m->sage[m->num_sage_layers - 1].dim_out; }
+
+void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E, int64_t cap, meshtok_taps* taps) {
+  meshtok_taps dummy;
+  meshtok_taps* t = taps ? taps : &dummy;
+  const size_t BF = (size_t)B * F, BV = (size_t)B * V;
+  w->status = c.take<int>(16, &t->status);
+  w->counts = reinterpret_cast<Counts*>(w->status ? w->status + 8 : nullptr);
+  t->counts = t->status + 32;
+  w->mesh_counts = c.take<int>((size_t)B * 4);
+  w->offs = c.take<int>(3 * (size_t)(B + 1));
+  w->deg_out = c.take<int>(BF);
+  w->deg_in = c.take<int>(BF);
+  w->face_row = c.take<int>(BF, &t->face_row);
+  w->row_face = c.take<int>(BF);
+  w->vert_row = c.take<int>(BV, &t->vert_row);
+  w->vptr = c.take<int>(BV + 1);
+  w->vinc = c.take<int>(BF * nvf);
+  w->indptr = c.take<int>(BF + 1, &t->indptr);
+  w->src = c.take<int>((size_t)cap, &t->src);
+  if (E > 0) {
+    w->ecount = c.take<int>(BF);
+    w->cursor = c.take<int>(BF);
+    w->etmp = c.take<int>((size_t)cap);
+  } else {
+    w->ecount = w->cursor = w->etmp = nullptr;
+  }
+}
+
+int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, void* base, Workspace* w, meshtok_taps* taps) {
+  meshtok_taps dummy;
+  meshtok_taps* t = taps ? taps : &dummy;
+  memset(t, 0, sizeof(*t));
+  Carver c(base);
+  carve_topology(c, w, B, F, m->nvf, V, E, cap, t);
+  const size_t BF = (size_t)B * F, BV = (size_t)B * V;
+  const int D = m->dim_codebook, Q = m->num_quantizers;
+  int max_in = 0;
+  for (int l = 0; l < m->num_sage_layers; ++l) max_in = max(max_in, m->sage[l].dim_in);
+  w->x0 = c.take<float>(BF * D, &t->x0);
+  w->xp = c.take<float>(BF * max_in);
+  w->agg = c.take<float>(BF * max_in);
+  for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
+  w->y = c.take<float>(BF * m->nvf * D);
+  w->avg = c.take<float>(BV * D, &t->averaged);
+  w->resid = c.take<float>(BV * D);
+  w->rscale = c.take<float>(BV);
+  w->qrows = c.take<float>(BV * D);
+  w->pad_qrow = c.take<float>(D);
+  w->zero_row = c.take<float>(D);
+  w->vcodes = c.take<int32_t>(BV * Q, &t->vertex_codes);
+  w->best = c.take<int32_t>(BV);
+  w->amb_list = c.take<int>(BV);
+  w->amb_count = c.take<int>(4);
+  w->partial = nullptr;
+  if (!m->use_lfq) {
+    RvqTcPlan plan;
+    int rc = rvq_tc_plan((int)BV, m->codebook_size, D, &plan);
+    if (rc != MESHTOK_OK) return rc;
+    w->partial = c.take<float4>(plan.partial_bytes / sizeof(float4));
+  }
+  w->total = align_up(c.off, 256);
+  return MESHTOK_OK;
+}
+
+__global__ void sub_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int D,
+                                const int* n_dev, long long max_elems) {
+  const long long n = min((long long)(*n_dev) * D, max_elems);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i] - b[i];
+}
+
+__global__ void copy_rows_kernel(const float4* __restrict__ a, float4* __restrict__ out, int d4, const int* n_dev,
+                                 long long max_elems4) {
+  const long long n = min((long long)(*n_dev) * d4, max_elems4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = a[i];
+}
+
+int linear(bool simt, const float* A1, int K1, const float* A2, int K2, const float* W, const void* w_img, const float* bias,
+           float* C, int N, const int* m_dev, int m_max, bool relu, cudaStream_t s) {
+  if (simt) return launch_linear_simt(A1, K1, A2, K2, W, bias, C, N, m_dev, m_max, relu, s);
+  MT_CHECK_ARG(w_img != nullptr, "tcgen05 linear requested but the model carries no weight image (set gemm_simt or build images)");
+  return launch_linear_tc(A1, K1, A2, K2, w_img, bias, C, N, m_dev, m_max, relu, s);
+}
+
+// One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the final residual in
+// `resid` and the codes in vcodes (R x Q).
+int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes, int32_t* best,
+            int* amb_list, int* amb_count, float4* partial, const int* n_dev, int max_rows, bool exact, cudaStream_t s) {
+  const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
+  if (max_rows == 0) return MESHTOK_OK;
+  int rc;
+  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, n_dev, max_rows, s); }
+  if (rc != MESHTOK_OK) return rc;
+  RvqTcPlan plan;
+  if (!exact) {
+    MT_CHECK_ARG(m->codebook_f16_tiles != nullptr && m->codebook_image_scale > 0.f,
+                 "model.codebook_f16_tiles / codebook_image_scale not set (needed by the tcgen05 search)");
+    rc = rvq_tc_plan(max_rows, K, D, &plan);
+    if (rc != MESHTOK_OK) return rc;
+  }
+  for (int level = 0; level < Q; ++level) {
+    if (exact) {
+      { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, best, s); }
+      if (rc != MESHTOK_OK) return rc;
+    } else {
+      MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
+      { ProfScope ps(PROF_RVQ_SEARCH, s);
+        rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
+                                  n_dev, max_rows, plan, partial, s); }
+      if (rc != MESHTOK_OK) return rc;
+      { ProfScope ps(PROF_RVQ_RESCORE, s);
+        rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, m->codebook_max_norm,
+                                m->codebook_image_scale, partial, plan.n_splits, n_dev, max_rows, best, amb_list, amb_count, s); }
+      if (rc != MESHTOK_OK) return rc;
+      { ProfScope ps(PROF_RVQ_EXACT, s);
+        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, best, s); }
+      if (rc != MESHTOK_OK) return rc;
+    }
+    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_update(resid, D, m->codebook, best, vcodes, Q, level, rscale, n_dev, max_rows, s); }
+    if (rc != MESHTOK_OK) return rc;
+  }
+  return MESHTOK_OK;
+}
+
+}  // namespace
+}  // namespace meshtok
+
+using namespace meshtok;
+
+extern "C" {
+
+int meshtok_version(void) { return MESHTOK_ABI_VERSION; }
+
+const char* meshtok_last_error_string(void) { return g_error; }
+
+int meshtok_topology_workspace_bytes(int B, int F, int nvf, int V, int E_user, size_t* bytes) {
+  MT_CHECK_ARG(bytes != nullptr, "bytes is null");
+  int rc = topo_check_shape(B, F, nvf, V);
+  if (rc != MESHTOK_OK) return rc;
+  Carver c(nullptr);
+  Workspace w;
+  carve_topology(c, &w, B, F, nvf, V, E_user, 16, nullptr);
+  *bytes = align_up(c.off, 256);
+  return MESHTOK_OK;
+}
+
+static int face_edges_common(const int64_t* faces, int B, int F, int nvf, int V, int64_t pad_id, int threshold,
+                             int include_self, void* workspace, size_t workspace_bytes, TopoParams* p, Workspace* w) {
+  MT_CHECK_ARG(faces != nullptr && workspace != nullptr, "faces / workspace is null");
+  MT_CHECK_ARG(threshold == 1 || threshold == 2, "threshold must be 1 or 2");
+  int rc = topo_check_shape(B, F, nvf, V);
+  if (rc != MESHTOK_OK) return rc;
+  Carver c(workspace);
+  carve_topology(c, w, B, F, nvf, V, 0, 16, nullptr);
+  if (c.off > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", c.off, workspace_bytes);
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  memset(p, 0, sizeof(*p));
+  p->faces = faces; p->B = B; p->F = F; p->nvf = nvf; p->V = V; p->pad_id = pad_id;
+  p->threshold = threshold; p->include_self = include_self; p->do_adjacency = 1;
+  p->status = w->status; p->mesh_counts = w->mesh_counts; p->deg_out = w->deg_out; p->deg_in = w->deg_in;
+  return MESHTOK_OK;
+}
+
+int meshtok_face_edges_count(const int64_t* faces, int B, int F, int nvf, int V, int64_t pad_id, int threshold,
+                             int include_self, void* workspace, size_t workspace_bytes, int32_t* edge_counts,
+                             meshtok_stream_t stream) {
+  TopoParams p;
+  Workspace w;
+  int rc = face_edges_common(faces, B, F, nvf, V, pad_id, threshold, include_self, workspace, workspace_bytes, &p, &w);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(edge_counts != nullptr, "edge_counts is null");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  MT_CHECK_CUDA(cudaMemsetAsync(w.status, 0, 64, s));
+  p.edge_counts_out = edge_counts;
+  return topo_count(p, s);
+}
+
+int meshtok_face_edges_fill(const int64_t* faces, int B, int F, int nvf, int V, int64_t pad_id, int threshold,
+                            int include_self, void* workspace, size_t workspace_bytes, int emax, int64_t* out_edges,
+                            meshtok_stream_t stream) {
+  TopoParams p;
+  Workspace w;
+  int rc = face_edges_common(faces, B, F, nvf, V, pad_id, threshold, include_self, workspace, workspace_bytes, &p, &w);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(emax >= 0 && (emax == 0 || out_edges != nullptr), "bad emax / out_edges");
+  p.emax = emax;
+  p.dense_out = out_edges;
+  return topo_fill_dense(p, static_cast<cudaStream_t>(stream));
+}
+
+int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                                     size_t* bytes) {
+  MT_CHECK_ARG(bytes != nullptr, "bytes is null");
+  int rc = check_model(model);
+  if (rc != MESHTOK_OK) return rc;
+  rc = topo_check_shape(B, F, model->nvf, V);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(edge_capacity > 0 && edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
+  Workspace w;
+  rc = carve_all(model, B, F, V, E, edge_capacity, nullptr, &w, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  *bytes = w.total;
+  return MESHTOK_OK;
+}
+
+int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                          meshtok_taps* taps) {
+  MT_CHECK_ARG(taps != nullptr, "taps is null");
+  int rc = check_model(model);
+  if (rc != MESHTOK_OK) return rc;
+  Workspace w;
+  return carve_all(model, B, F, V, E, edge_capacity, nullptr, &w, taps);
+}
+
+int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, void* workspace, size_t workspace_bytes,
+                     meshtok_stream_t stream) {
+  int rc = check_model(m);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a != nullptr && workspace != nullptr, "args / workspace is null");
+  MT_CHECK_ARG(a->faces != nullptr, "faces is null");
+  MT_CHECK_ARG(a->vertices != nullptr || a->encoded_in != nullptr, "vertices is null");
+  MT_CHECK_ARG(a->stop_after_encode || a->codes_out != nullptr, "codes_out is null");
+  MT_CHECK_ARG(a->face_edges == nullptr || a->E > 0, "face_edges given but E <= 0 (pass one all-pad edge for an empty list)");
+  const int B = a->B, F = a->F, V = a->V, nvf = m->nvf, D = m->dim_codebook, Q = m->num_quantizers;
+  const int E = a->face_edges ? a->E : 0;
+  rc = topo_check_shape(B, F, nvf, V);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a->edge_capacity > 0 && a->edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
+  Workspace w;
+  rc = carve_all(m, B, F, V, E, a->edge_capacity, workspace, &w, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  if (w.total > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", w.total, workspace_bytes);
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int max_rows = B * F, max_vrows = B * V;
+  const bool simt = a->gemm_simt != 0;
+
+  // ---- topology -------------------------------------------------------------------------------
+  MT_CHECK_CUDA(cudaMemsetAsync(w.status, 0, 64, s));
+  TopoParams p;
+  memset(&p, 0, sizeof(p));
+  p.faces = a->faces; p.B = B; p.F = F; p.nvf = nvf; p.V = V; p.pad_id = a->pad_id;
+  p.threshold = 2; p.include_self = 1; p.do_adjacency = a->face_edges ? 0 : 1;
+  p.status = w.status; p.mesh_counts = w.mesh_counts; p.deg_out = w.deg_out; p.deg_in = w.deg_in;
+  p.face_off = w.offs; p.vert_off = w.offs + (B + 1); p.edge_off = w.offs + 2 * (size_t)(B + 1);
+  p.face_row = w.face_row; p.row_face = w.row_face; p.vert_row = w.vert_row; p.vptr = w.vptr; p.vinc = w.vinc;
+  p.indptr = w.indptr; p.src = w.src; p.edge_capacity = a->edge_capacity;
+  prof_begin(PROF_TOPOLOGY, s);
+  if ((rc = topo_count(p, s)) != MESHTOK_OK) return rc;
+  if ((rc = topo_offsets(w.mesh_counts, w.offs, B, w.counts, s)) != MESHTOK_OK) return rc;
+  if ((rc = topo_fill_csr(p, s)) != MESHTOK_OK) return rc;
+  if (a->face_edges) {
+    rc = topo_user_edges(a->face_edges, B, E, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
+                         w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
+    if (rc != MESHTOK_OK) return rc;
+  }
+  prof_end(PROF_TOPOLOGY, s);
+  const int* n_faces_dev = &w.counts->n_faces;
+  const int* n_vrows_dev = &w.counts->n_vrows;
+
+  // ---- encoder --------------------------------------------------------------------------------
+  const int L = m->num_sage_layers;
+  const float* enc = nullptr;
+  if (a->encoded_in == nullptr) {
+    FeatParams fp;
+    memset(&fp, 0, sizeof(fp));
+    fp.vertices = a->vertices; fp.faces = a->faces; fp.row_face = w.row_face; fp.counts = w.counts;
+    fp.F = F; fp.V = V; fp.nvf = nvf; fp.D = D;
+    fp.coor_lo = m->coor_lo;
+    fp.coor_den = (float)((double)m->coor_hi - (double)m->coor_lo);
+    fp.angle_den = (float)3.141592653589793;
+    fp.area_den = (float)(((double)m->coor_hi - (double)m->coor_lo) * ((double)m->coor_hi - (double)m->coor_lo));
+    fp.clip_lo = (float)(-1.0 + 1e-5); fp.clip_hi = (float)(1.0 - 1e-5);
+    fp.n_coor = m->num_discrete_coors; fp.n_angle = m->num_discrete_angle; fp.n_area = m->num_discrete_area;
+    fp.n_normal = m->num_discrete_normals;
+    fp.tables = m->folded_tables; fp.bias = m->project_in_bias;
+    {
+      int off = 0, s_i = 0;
+      for (int k = 0; k < nvf * 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_coors; }
+      for (int k = 0; k < nvf; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_angle; }
+      fp.slot_off[s_i++] = off; off += m->num_discrete_area;
+      for (int k = 0; k < 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_normals; }
+    }
+    fp.x0 = w.x0; fp.face_coords_out = a->face_coords_out;
+    if (a->face_coords_out)
+      MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)max_rows * nvf * 3, s));
+    { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }
+
+    const float* x = w.x0;
+    for (int l = 0; l < L; ++l) {
+      const meshtok_sage_layer& ly = m->sage[l];
+      // xp = relu(lin(x))
+      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, ly.dim_in, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, w.agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      // out = lin_l(agg) + lin_r(x)
+      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, ly.dim_in, x, ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_NORM, s);
+        if ((rc = launch_row_norm(w.layer_out[l], ly.dim_out, l == 0 ? m->ln_gamma : nullptr, l == 0 ? m->ln_beta : nullptr,
+                                  w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      x = w.layer_out[l];
+    }
+    enc = x;
+  } else {
+    if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc;
+    enc = w.layer_out[L - 1];
+  }
+  if (a->encoded_out)
+    if ((rc = launch_unpack_rows(enc, w.face_row, max_rows, enc_dim(m), a->encoded_out, s)) != MESHTOK_OK) return rc;
+  if (a->stop_after_encode) return MESHTOK_OK;
+
+  // ---- quantize -------------------------------------------------------------------------------
+  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, enc_dim(m), nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+  { ProfScope ps(PROF_SCATTER_MEAN, s); if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, s)) != MESHTOK_OK) return rc; }
+  const float* pad_row = nullptr;
+  if (m->use_lfq) {
+    int bits = 0;
+    while ((1 << bits) < m->codebook_size) ++bits;
+    MT_CHECK_ARG((1 << bits) == m->codebook_size, "LFQ needs a power-of-two codebook_size");
+    MT_CHECK_ARG(m->lfq_in_w && m->lfq_in_b, "model.lfq_in_* is null");
+    float* qrows = a->quantized_out ? w.qrows : nullptr;
+    if (qrows) MT_CHECK_ARG(m->lfq_out_w && m->lfq_out_b, "model.lfq_out_* is null (needed for quantized_out)");
+    { ProfScope ps(PROF_LFQ, s);
+      if ((rc = launch_lfq(w.avg, D, m->lfq_in_w, m->lfq_in_b, bits, Q, m->lfq_out_w, m->lfq_out_b, w.vcodes, qrows,
+                           n_vrows_dev, max_vrows, s)) != MESHTOK_OK) return rc; }
+    if (qrows) {  // the reference also quantises its all-zero pad-vertex row; padded faces gather that
+      MT_CHECK_CUDA(cudaMemsetAsync(w.zero_row, 0, sizeof(float) * D, s));
+      if ((rc = launch_lfq(w.zero_row, D, m->lfq_in_w, m->lfq_in_b, bits, Q, m->lfq_out_w, m->lfq_out_b, w.best, w.pad_qrow,
+                           nullptr, 1, s)) != MESHTOK_OK) return rc;
+      pad_row = w.pad_qrow;
+    }
+  } else {
+    MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
+    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.best, w.amb_list, w.amb_count, w.partial, n_vrows_dev, max_vrows,
+                      a->rvq_exact != 0, s)) != MESHTOK_OK) return rc;
+    if (a->quantized_out) {
+      const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
+      sub_rows_kernel<<<blocks, 256, 0, s>>>(w.avg, w.resid, w.qrows, D, n_vrows_dev, (long long)max_vrows * D);
+      MT_CHECK_LAUNCH();
+    }
+  }
+  { ProfScope ps(PROF_GATHER_CODES, s);
+    if ((rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out,
+                                  reinterpret_cast<unsigned long long*>(a->histogram), m->codebook_size, s)) != MESHTOK_OK) return rc; }
+  if (a->quantized_out)
+    if ((rc = launch_gather_quantized(a->faces, w.face_row, w.vert_row, w.qrows, B, F, nvf, V, D, pad_row, a->quantized_out, s)) != MESHTOK_OK) return rc;
+  return MESHTOK_OK;
+}
+
+int meshtok_lfq_codes(const meshtok_model* m, const float* rows, int R, int32_t* codes, meshtok_stream_t stream) {
+  int rc = check_model(m);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(rows && codes && R >= 0, "rows / codes is null");
+  int bits = 0;
+  while ((1 << bits) < m->codebook_size) ++bits;
+  MT_CHECK_ARG((1 << bits) == m->codebook_size, "LFQ needs a power-of-two codebook_size");
+  MT_CHECK_ARG(m->lfq_in_w && m->lfq_in_b, "model.lfq_in_* is null");
+  return launch_lfq(rows, m->dim_codebook, m->lfq_in_w, m->lfq_in_b, bits, m->num_quantizers, nullptr, nullptr, codes,
+                    nullptr, nullptr, R, static_cast<cudaStream_t>(stream));
+}
+
+int meshtok_rvq_workspace_bytes(const meshtok_model* m, int R, size_t* bytes) {
+  int rc = check_model(m);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(bytes && R >= 0, "bad arguments");
+  RvqTcPlan plan;
+  if ((rc = rvq_tc_plan(R, m->codebook_size, m->dim_codebook, &plan)) != MESHTOK_OK) return rc;
+  Carver c(nullptr);
+  c.take<float>((size_t)R * m->dim_codebook);
+  c.take<float>(R);
+  c.take<int32_t>(R);
+  c.take<int>(R);
+  c.take<int>(4);
+  c.take<int>(4);
+  c.take<float4>(plan.partial_bytes / sizeof(float4));
+  *bytes = align_up(c.off, 256);
+  return MESHTOK_OK;
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exact, int32_t* codes, float* residual_out,
+                      void* workspace, size_t workspace_bytes, meshtok_stream_t stream) {
+  int rc = check_model(m);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(rows && codes && workspace && R >= 0, "rows / codes / workspace is null");
+  MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
+  RvqTcPlan plan;
+  if ((rc = rvq_tc_plan(R, m->codebook_size, m->dim_codebook, &plan)) != MESHTOK_OK) return rc;
+  Carver c(workspace);
+  float* resid = c.take<float>((size_t)R * m->dim_codebook);
+  float* rscale = c.take<float>(R);
+  int32_t* best = c.take<int32_t>(R);
+  int* amb_list = c.take<int>(R);
+  int* amb_count = c.take<int>(4);
+  int* n_dev = c.take<int>(4);
+  float4* partial = c.take<float4>(plan.partial_bytes / sizeof(float4));
+  if (align_up(c.off, 256) > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", align_up(c.off, 256), workspace_bytes);
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
+  MT_CHECK_LAUNCH();
+  rc = run_rvq(m, rows, resid, rscale, codes, best, amb_list, amb_count, partial, n_dev, R, exact != 0, s);
+  if (rc != MESHTOK_OK) return rc;
+  if (residual_out && R > 0)
+    MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));
+  return MESHTOK_OK;
+}
+
+int meshtok_rvq_codebook_image_bytes(int codebook_size, int dim, size_t* bytes) {
+  MT_CHECK_ARG(bytes && codebook_size > 0 && dim > 0, "bad arguments");
+  *bytes = rvq_codebook_image_bytes(codebook_size, dim);
+  return MESHTOK_OK;
+}
+
+int meshtok_rvq_build_codebook_image(const float* codebook, int codebook_size, int dim, float scale, void* image,
+                                     meshtok_stream_t stream) {
+  MT_CHECK_ARG(codebook && image, "codebook / image is null");
+  MT_CHECK_ARG(scale > 0.f, "scale must be a positive power of two");
+  return launch_rvq_build_image(codebook, codebook_size, dim, scale, image, static_cast<cudaStream_t>(stream));
+}
+
+int meshtok_linear_image_bytes(int N, int K, size_t* bytes) {
+  MT_CHECK_ARG(bytes && N > 0 && K > 0, "bad arguments");
+  int passes, NT;
+  int rc = linear_tc_plan(N, K, 0, &passes, &NT);
+  if (rc != MESHTOK_OK) return rc;
+  *bytes = linear_tc_image_bytes(N, K);
+  return MESHTOK_OK;
+}
+
+int meshtok_linear_build_image(const float* W, int N, int K, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(W && image, "W / image is null");
+  return launch_linear_tc_build_image(W, N, K, image, static_cast<cudaStream_t>(stream));
+}
+
+int meshtok_linear(const float* A, const float* W, const void* w_image, const float* bias, float* C, int M, int N, int K,
+                   int relu, int simt, meshtok_stream_t stream) {
+  MT_CHECK_ARG(A && C && M >= 0 && N > 0 && K > 0, "bad arguments");
+  MT_CHECK_ARG(simt ? W != nullptr : w_image != nullptr, "W (simt) / w_image (tcgen05) is null");
+  return linear(simt != 0, A, K, nullptr, 0, W, w_image, bias, C, N, nullptr, M, relu != 0, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+// Shared helpers for libmeshtok (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/meshtok.h"
+
+namespace meshtok {
+
+void set_error(const char* fmt, ...);
+
+#define MT_CHECK_ARG(cond, ...)                       \
+  do {                                                \
+    if (!(cond)) {                                    \
+      ::meshtok::set_error(__VA_ARGS__);              \
+      return MESHTOK_ERR_INVALID_ARGUMENT;            \
+    }                                                 \
+  } while (0)
+
+#define MT_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      ::meshtok::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return MESHTOK_ERR_CUDA;                                                                \
+    }                                                                                         \
+  } while (0)
+
+extern long long g_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define MT_CHECK_LAUNCH()                  \
+  do {                                     \
+    ++::meshtok::g_launch_count;           \
+    MT_CHECK_CUDA(cudaGetLastError());     \
+  } while (0)
+
+// Optional per-section device timing (cudaEvent pairs on the caller's stream); off by default.
+enum ProfSection {
+  PROF_TOPOLOGY = 0, PROF_FACE_EMBED, PROF_SAGE_LINEAR, PROF_SAGE_GATHER, PROF_SAGE_NORM, PROF_PDC_LINEAR,
+  PROF_SCATTER_MEAN, PROF_LFQ, PROF_RVQ_PREP_UPDATE, PROF_RVQ_SEARCH, PROF_RVQ_RESCORE, PROF_RVQ_EXACT,
+  PROF_GATHER_CODES, PROF_OTHER, PROF_NUM_SECTIONS
+};
+void prof_begin(int section, cudaStream_t s);
+void prof_end(int section, cudaStream_t s);
+struct ProfScope {
+  int sec; cudaStream_t s;
+  ProfScope(int section, cudaStream_t st) : sec(section), s(st) { prof_begin(sec, s); }
+  ~ProfScope() { prof_end(sec, s); }
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+constexpr int kWarp = 32;
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_min_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ int warp_max_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// inclusive prefix sum over the warp
+__device__ __forceinline__ int warp_inclusive_scan(int v) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane_id() >= o) v += n;
+  }
+  return v;
+}
+
+// In-place exclusive scan of data[0..n) held in shared memory by the whole block.
+// scratch: >= 33 ints of shared memory.  Returns the total in every thread.
+__device__ __forceinline__ int block_exclusive_scan(int* data, int n, int* scratch) {
+  const int nt = blockDim.x;
+  const int per = (n + nt - 1) / nt;
+  const int beg = min(n, (int)threadIdx.x * per);
+  const int end = min(n, beg + per);
+  int local = 0;
+  for (int i = beg; i < end; ++i) local += data[i];
+  int inc = warp_inclusive_scan(local);
+  if (lane_id() == 31) scratch[warp_id()] = inc;
+  __syncthreads();
+  if (warp_id() == 0) {
+    int nw = (nt + 31) >> 5;
+    int w = lane_id() < nw ? scratch[lane_id()] : 0;
+    int winc = warp_inclusive_scan(w);
+    scratch[lane_id()] = winc - w;
+    if (lane_id() == 31) scratch[32] = winc;
+  }
+  __syncthreads();
+  int run = scratch[warp_id()] + inc - local;
+  const int total = scratch[32];
+  for (int i = beg; i < end; ++i) {
+    int v = data[i];
+    data[i] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+// workspace layout shared by the pipeline kernels -------------------------------------------------
+struct Counts {  // device resident, int32[8]
+  int n_faces;   // valid faces in the batch  (packed rows)
+  int n_vrows;   // referenced (mesh, vertex) pairs = quantizer rows
+  int n_edges;   // directed edges
+  int pad[5];
+};
+
+}  // namespace meshtok

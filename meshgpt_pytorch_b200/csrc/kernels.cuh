@@ -1,0 +1,93 @@
+// Launch wrappers of the pipeline kernels (host side declarations).
+#pragma once
+#include "common.cuh"
+
+namespace meshtok {
+
+// ---- K2 ------------------------------------------------------------------------------------------
+struct FeatParams {
+  const float* vertices;    // (B,V,3)
+  const int64_t* faces;     // (B,F,nvf)
+  const int* row_face;      // packed row -> b*F+f
+  const Counts* counts;
+  int F, V, nvf, D;
+  float coor_lo, coor_den, angle_den, area_den, clip_lo, clip_hi;
+  int n_coor, n_angle, n_area, n_normal;
+  const float* tables;      // (sum bins, D)
+  const float* bias;        // (D)
+  int slot_off[20];
+  float* x0;                // (rows, D)
+  int64_t* face_coords_out; // (B,F,nvf*3) or null
+};
+int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
+
+// ---- K4 ------------------------------------------------------------------------------------------
+// agg[t] = mean over in-edges (s -> t) of x[s]; sum in ascending CSR order / max(count, 1).
+int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity,
+                       float* agg, const Counts* counts, int max_rows, cudaStream_t stream);
+// in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).
+int launch_row_norm(float* x, int d, const float* gamma, const float* beta, const Counts* counts, int max_rows,
+                    cudaStream_t stream);
+
+// C[m, :] = act([A1 | A2][m, :] . W^T + bias), fp32 SIMT.  m < *m_dev (<= m_max).
+int launch_linear_simt(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
+                       int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream);
+
+// ---- K6/K7/K8b/K9 --------------------------------------------------------------------------------
+// avg[vrow] = (sum over incidence entries e of y[e*D .. ]) / count      (scatter_mean, meshgpt_pytorch.py:243-257)
+int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc, float* avg, const Counts* counts,
+                        int max_vrows, cudaStream_t stream);
+// residual LFQ codes of rows (R x D): codes (R x Q) int32; optional quantized_out (R x D) = project_out(sum q).
+int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, int bits, int Q, const float* w_out,
+               const float* b_out, int32_t* codes, float* quantized_out, const int* n_rows_dev, int max_rows,
+               cudaStream_t stream);
+// codes_out[b, f*nvf+c, q] = vcodes[vert_row[b, faces[b,f,c]], q] (pad_id on padded faces) + histogram.
+int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, unsigned long long* hist,
+                        int K, cudaStream_t stream);
+// quantized_out[b, f, c*D:(c+1)*D] = qrows[vert_row[b, faces[b,f,c]]]; padded faces get the pad-vertex row,
+// which the reference leaves at zero for LFQ / at the (zero) input for RVQ.
+int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
+                            int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream);
+// encoded_out (B*F, d) <- packed rows, zeros on padded faces.
+int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, cudaStream_t stream);
+// packed rows <- (B*F, d) padded layout.
+int launch_pack_rows(const float* padded, const int* row_face, int d, float* packed, const Counts* counts, int max_rows,
+                     cudaStream_t stream);
+
+// ---- K8a -----------------------------------------------------------------------------------------
+// exact fp32 nearest-code search: best[r] = argmin_j sqrt(max(|x|^2 + |e_j|^2 - 2 x.e_j, 0)), lowest index on ties.
+// row_list == null: rows 0..*n_rows_dev-1; else rows row_list[0..*n_list_dev-1].
+int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
+                     const int* n_dev, int max_rows, int32_t* best, cudaStream_t stream);
+// r <- r - e[idx]; codes[r*Q + level] = idx; rscale[r] = power of two that brings max|r_d| into [0.5, 1).
+int launch_rvq_update(float* rows, int D, const float* codebook, const int32_t* best, int32_t* codes, int Q, int level,
+                      float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
+// resid <- rows_in (copy) and rscale as above.
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, const int* n_rows_dev, int max_rows,
+                    cudaStream_t stream);
+
+// tcgen05 screening search (rvq_tc.cu).  Produces per (row, split) the two best fp16-screened scores + indices.
+struct RvqTcPlan {
+  int m_tiles, n_splits, tiles_per_split, units, grid;
+  size_t partial_bytes;
+};
+int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan);
+int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+                         int K, const int* n_rows_dev, int max_rows, const RvqTcPlan& plan, float4* partial, cudaStream_t stream);
+// re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
+// flag rows whose candidate list may be incomplete (-> exact scan).
+int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
+                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows, int32_t* best,
+                       int* amb_list, int* amb_count, cudaStream_t stream);
+size_t rvq_codebook_image_bytes(int K, int D);
+int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream);
+
+// tcgen05 split-bf16 linear (linear_tc.cu); w_image from launch_linear_tc_build_image
+int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT);
+size_t linear_tc_image_bytes(int N, int K);
+int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cudaStream_t stream);
+int launch_linear_tc(const float* A1, int K1, const float* A2, int K2, const void* w_image, const float* bias, float* C,
+                     int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream);
+
+}  // namespace meshtok

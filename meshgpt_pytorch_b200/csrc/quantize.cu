@@ -1,0 +1,246 @@
+// K7 scatter-mean faces -> vertices, K8b residual LFQ, K9 gather codes back per face-vertex.
+//
+// Replaces MeshAutoencoder.quantize (meshgpt_pytorch.py:787-870): the padding-aware scatter_mean
+// (:243-257, :807-824) becomes a segmented sum over the vertex incidence CSR built by the topology
+// kernel (one warp per referenced vertex, entries in the reference's (face, slot) order, no atomics,
+// no (b, nf*nvf, d) int64 index tensor); ResidualLFQ (vector_quantize_pytorch, called at :842) becomes
+// log2(K) dot products + sign tests per vertex; the two get_at gathers and masked_fills (:856-866,
+// :1018) become one kernel that writes the final int64 codes and the codebook-usage histogram.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace meshtok {
+
+namespace {
+
+template <int PER2>  // float2 per lane: D <= 64 * PER2
+__global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restrict__ y, int D, const int* __restrict__ vptr,
+                                                           const int* __restrict__ vinc, float* __restrict__ avg,
+                                                           const Counts* counts) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const int n = counts->n_vrows;
+  const int d2 = D >> 1;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
+    const int s = vptr[row], e = vptr[row + 1];
+    float2 acc[PER2];
+#pragma unroll
+    for (int i = 0; i < PER2; ++i) acc[i] = make_float2(0.f, 0.f);
+    for (int q = s; q < e; ++q) {
+      const float2* yr = reinterpret_cast<const float2*>(y + (size_t)vinc[q] * D);
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d2) {
+          const float2 v = __ldg(yr + c);
+          acc[i].x += v.x;
+          acc[i].y += v.y;
+        }
+      }
+    }
+    const float cnt = fmaxf((float)(e - s), 1e-5f);  // den.clamp(min = eps)
+    float2* out = reinterpret_cast<float2*>(avg + (size_t)row * D);
+#pragma unroll
+    for (int i = 0; i < PER2; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d2) out[c] = make_float2(__fdiv_rn(acc[i].x, cnt), __fdiv_rn(acc[i].y, cnt));
+    }
+  }
+}
+
+// Residual LFQ (eval).  x = W_in v + b; level l: bit_d = r_d > 0, q_d = +-2^-l, r <- r - q;
+// code = sum_d bit_d << (bits-1-d)  (dimension 0 is the most significant bit).
+// The soft clamp tanh(r/c)*c of the upstream module preserves the sign and is therefore skipped.
+template <int PER>
+__global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows, int D, const float* __restrict__ w_in,
+                                                  const float* __restrict__ b_in, int bits, int Q,
+                                                  const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                                  int32_t* __restrict__ codes, float* __restrict__ quantized_out,
+                                                  const int* __restrict__ n_rows_dev, int max_rows) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const int n = n_rows_dev ? min(*n_rows_dev, max_rows) : max_rows;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < D ? rows[(size_t)row * D + c] : 0.f;
+    }
+    float x_mine = 0.f;  // lane d keeps projected dimension d
+    for (int dd = 0; dd < bits; ++dd) {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        if (c < D) part = fmaf(v[i], __ldg(w_in + (size_t)dd * D + c), part);
+      }
+      part = warp_sum(part) + b_in[dd];
+      if (lane == dd) x_mine = part;
+    }
+    float r = x_mine, qsum = 0.f;
+    for (int l = 0; l < Q; ++l) {
+      const float scale = exp2f(-(float)l);
+      const bool bit = (lane < bits) && (r > 0.f);
+      const unsigned m = __ballot_sync(0xffffffffu, bit);
+      // lane d holds bit (bits-1-d) of the code: reverse the low `bits` bits of the ballot
+      const unsigned code = __brev(m) >> (32 - bits);
+      if (lane == 0) codes[(size_t)row * Q + l] = (int32_t)code;
+      const float q = bit ? scale : -scale;
+      r -= q;
+      qsum += q;
+    }
+    if (quantized_out != nullptr) {
+      // project_out: (D x bits) . qsum + b_out
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        float o = 0.f;
+        for (int dd = 0; dd < bits; ++dd) {
+          const float qd = __shfl_sync(0xffffffffu, qsum, dd);
+          if (c < D) o = fmaf(qd, __ldg(w_out + (size_t)c * bits + dd), o);
+        }
+        if (c < D) quantized_out[(size_t)row * D + c] = o + b_out[c];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
+                                                           const int* __restrict__ vert_row, const int32_t* __restrict__ vcodes,
+                                                           int BF, int F, int nvf, int V, int Q, int64_t pad_id,
+                                                           int64_t* __restrict__ codes_out, unsigned long long* __restrict__ hist,
+                                                           int K) {
+  const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= (long long)BF * nvf) return;
+  const int pf = (int)(tok / nvf);
+  int64_t* dst = codes_out + tok * Q;
+  if (face_row[pf] < 0) {
+    for (int q = 0; q < Q; ++q) dst[q] = pad_id;
+    return;
+  }
+  const int b = pf / F;
+  const long long v = faces[tok];
+  const int vr = vert_row[(size_t)b * V + v];
+  for (int q = 0; q < Q; ++q) {
+    const int c = vcodes[(size_t)vr * Q + q];
+    dst[q] = c;
+    if (hist != nullptr && c >= 0 && c < K) atomicAdd(hist + (size_t)q * K + c, 1ull);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_quantized_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
+                                                               const int* __restrict__ vert_row, const float* __restrict__ qrows,
+                                                               int BF, int F, int nvf, int V, int D,
+                                                               const float* __restrict__ pad_row, float* __restrict__ out) {
+  const int wpb = blockDim.x >> 5;
+  const long long tok = (long long)blockIdx.x * wpb + warp_id();
+  if (tok >= (long long)BF * nvf) return;
+  const int pf = (int)(tok / nvf);
+  const float* srcp;
+  if (face_row[pf] < 0) srcp = pad_row;
+  else {
+    const int b = pf / F;
+    srcp = qrows + (size_t)vert_row[(size_t)b * V + faces[tok]] * D;
+  }
+  for (int c = lane_id(); c < D; c += 32) out[tok * D + c] = srcp ? srcp[c] : 0.f;
+}
+
+__global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ packed, const int* __restrict__ face_row,
+                                                          int BF, int d4, float4* __restrict__ out) {
+  const int wpb = blockDim.x >> 5;
+  for (long long pf = (long long)blockIdx.x * wpb + warp_id(); pf < BF; pf += (long long)gridDim.x * wpb) {
+    const int row = face_row[pf];
+    const float4* s = reinterpret_cast<const float4*>(packed) + (size_t)(row < 0 ? 0 : row) * d4;
+    for (int c = lane_id(); c < d4; c += 32) out[pf * d4 + c] = row < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : s[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float4* __restrict__ padded, const int* __restrict__ row_face,
+                                                        int d4, float4* __restrict__ packed, const Counts* counts) {
+  const int wpb = blockDim.x >> 5;
+  const int n = counts->n_faces;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
+    const float4* s = padded + (size_t)row_face[row] * d4;
+    for (int c = lane_id(); c < d4; c += 32) packed[(size_t)row * d4 + c] = s[c];
+  }
+}
+
+}  // namespace
+
+int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc, float* avg, const Counts* counts,
+                        int max_vrows, cudaStream_t stream) {
+  MT_CHECK_ARG(D % 2 == 0 && D <= 512, "scatter_mean: dim %d must be even and <= 512", D);
+  const int blocks = max(1, min(ceil_div(max_vrows, 8), 148 * 16));
+  const int per2 = ceil_div(D / 2, 32);
+#define SM(P) scatter_mean_kernel<P><<<blocks, 256, 0, stream>>>(y, D, vptr, vinc, avg, counts)
+  if (per2 <= 1) SM(1);
+  else if (per2 <= 2) SM(2);
+  else if (per2 <= 3) SM(3);
+  else if (per2 <= 4) SM(4);
+  else SM(8);
+#undef SM
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, int bits, int Q, const float* w_out,
+               const float* b_out, int32_t* codes, float* quantized_out, const int* n_rows_dev, int max_rows,
+               cudaStream_t stream) {
+  MT_CHECK_ARG(bits >= 1 && bits <= 30, "lfq: codebook_size must be 2^1..2^30 (bits=%d)", bits);
+  MT_CHECK_ARG(D >= 1 && D <= 512, "lfq: dim %d must be <= 512", D);
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  const int per = ceil_div(D, 32);
+#define LQ(P) lfq_kernel<P><<<blocks, 256, 0, stream>>>(rows, D, w_in, b_in, bits, Q, w_out, b_out, codes, quantized_out, n_rows_dev, max_rows)
+  if (per <= 2) LQ(2);
+  else if (per <= 6) LQ(6);
+  else if (per <= 8) LQ(8);
+  else LQ(16);
+#undef LQ
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, unsigned long long* hist,
+                        int K, cudaStream_t stream) {
+  const long long n = (long long)B * F * nvf;
+  if (n == 0) return MESHTOK_OK;
+  gather_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q,
+                                                                      pad_id, codes_out, hist, K);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
+                            int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream) {
+  const long long n = (long long)B * F * nvf;
+  if (n == 0) return MESHTOK_OK;
+  gather_quantized_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(faces, face_row, vert_row, qrows, B * F, F, nvf, V, D,
+                                                                      pad_row, out);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, cudaStream_t stream) {
+  MT_CHECK_ARG(d % 4 == 0, "unpack_rows: width %d must be a multiple of 4", d);
+  if (BF == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(BF, 8), 148 * 16));
+  unpack_rows_kernel<<<blocks, 256, 0, stream>>>(packed, face_row, BF, d / 4, reinterpret_cast<float4*>(out));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_pack_rows(const float* padded, const int* row_face, int d, float* packed, const Counts* counts, int max_rows,
+                     cudaStream_t stream) {
+  MT_CHECK_ARG(d % 4 == 0, "pack_rows: width %d must be a multiple of 4", d);
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  pack_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(padded), row_face, d / 4,
+                                               reinterpret_cast<float4*>(packed), counts);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // namespace meshtok

@@ -1,0 +1,189 @@
+// K8a (exact path): fp32 nearest-codebook search and the residual update of ResidualVQ (eval).
+//
+// Replaces vector_quantize_pytorch's EuclideanCodebook forward as called through ResidualVQ at
+// meshgpt_pytorch.py:842:   dist = -sqrt(clamp(|x|^2 + |e|^2 - 2 x.e, 0)); idx = argmax(dist)  (lowest
+// index on ties); r <- r - e[idx].  The reference materialises a (1, R, K) fp32 distance tensor and a
+// one-hot of the same size per level; here a 64x64 register-tiled sweep keeps a running (dist, idx) per
+// row.  This kernel is (a) the re-check of the rows the tcgen05 screening flags as ambiguous, and
+// (b) the exact checker the GPU tests compare the tensor-core path against.
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace meshtok {
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
+                                                        const float* __restrict__ e2, int K, const int* __restrict__ row_list,
+                                                        const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ best) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Es[BK][BN + 4];
+  __shared__ float x2s[BM];
+  __shared__ int rid[BM];
+  __shared__ float red_d[BM][17];
+  __shared__ int red_i[BM][17];
+  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  const int m0 = blockIdx.x * BM;
+  if (m0 >= n) return;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
+
+  if (tid < BM) {
+    const int m = m0 + tid;
+    rid[tid] = m < n ? (row_list ? row_list[m] : m) : -1;
+  }
+  __syncthreads();
+  {  // |x|^2, 4 threads per row
+    const int r = rid[lr];
+    float s = 0.f;
+    if (r >= 0)
+      for (int k = (tid & 3); k < D; k += 4) { const float v = rows[(size_t)r * D + k]; s = fmaf(v, v, s); }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if ((tid & 3) == 0) x2s[lr] = s;
+  }
+  __syncthreads();
+
+  float bd[4];
+  int bi[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
+
+  for (int n0 = 0; n0 < K; n0 += BN) {
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < D; k0 += BK) {
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r = rid[lr];
+      if (r >= 0) av = *reinterpret_cast<const float4*>(rows + (size_t)r * D + k0 + lk);
+      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + lr < K) ev = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(n0 + lr) * D + k0 + lk));
+      As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
+      Es[lk + 0][lr] = ev.x; Es[lk + 1][lr] = ev.y; Es[lk + 2][lr] = ev.z; Es[lk + 3][lr] = ev.w;
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+        const float4 w = *reinterpret_cast<const float4*>(&Es[kk][tx * 4]);
+        const float ar[4] = {a.x, a.y, a.z, a.w};
+        const float wr[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], wr[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int code = n0 + tx * 4 + j;
+      if (code >= K) continue;
+      const float y2 = __ldg(e2 + code);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float d2 = __fadd_rn(__fadd_rn(x2s[ty * 4 + i], y2), __fmul_rn(acc[i][j], -2.f));
+        const float dist = sqrtf(fmaxf(d2, 0.f));
+        if (dist < bd[i] || (dist == bd[i] && code < bi[i])) { bd[i] = dist; bi[i] = code; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { red_d[ty * 4 + i][tx] = bd[i]; red_i[ty * 4 + i][tx] = bi[i]; }
+  __syncthreads();
+  if (tid < BM && rid[tid] >= 0) {
+    float d = red_d[tid][0];
+    int ix = red_i[tid][0];
+    for (int t = 1; t < 16; ++t) {
+      const float dt = red_d[tid][t];
+      const int it = red_i[tid][t];
+      if (dt < d || (dt == d && it < ix)) { d = dt; ix = it; }
+    }
+    best[rid[tid]] = ix;
+  }
+}
+
+// power of two s such that max|v| * s lies in [0.5, 1)  (1 for an all-zero row)
+__device__ __forceinline__ float pow2_scale(float vmax) {
+  if (!(vmax > 0.f) || !(vmax < INFINITY)) return 1.f;
+  int e;
+  frexpf(vmax, &e);  // vmax = m * 2^e, m in [0.5, 1)
+  e = max(-100, min(100, e));
+  return ldexpf(1.f, -e);
+}
+
+template <int PER, bool UPDATE>
+__global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict__ rows_in, float* __restrict__ rows, int D,
+                                                         const float* __restrict__ cb, const int32_t* __restrict__ best,
+                                                         int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
+                                                         const int* __restrict__ n_dev, int max_rows) {
+  const int wpb = blockDim.x >> 5;
+  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
+    int idx = 0;
+    if (UPDATE) {
+      idx = best[row];
+      if (lane_id() == 0) codes[(size_t)row * Q + level] = idx;
+    }
+    float vmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane_id() + 32 * i;
+      if (c < D) {
+        float v = rows_in[(size_t)row * D + c];
+        if (UPDATE) v = __fsub_rn(v, __ldg(cb + (size_t)idx * D + c));
+        rows[(size_t)row * D + c] = v;
+        vmax = fmaxf(vmax, fabsf(v));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if (lane_id() == 0 && rscale) rscale[row] = pow2_scale(vmax);
+  }
+}
+
+}  // namespace
+
+int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
+                     const int* n_dev, int max_rows, int32_t* best, cudaStream_t stream) {
+  MT_CHECK_ARG(D % BK == 0, "rvq: dim %d must be a multiple of %d", D, BK);
+  if (max_rows == 0) return MESHTOK_OK;
+  rvq_exact_kernel<<<ceil_div(max_rows, BM), 256, 0, stream>>>(rows, D, codebook, e2, K, row_list, n_dev, max_rows, best);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_rvq_update(float* rows, int D, const float* codebook, const int32_t* best, int32_t* codes, int Q, int level,
+                      float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
+  MT_CHECK_ARG(D <= 512, "rvq: dim %d must be <= 512", D);
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  const int per = ceil_div(D, 32);
+#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, best, codes, Q, level, rscale, n_rows_dev, max_rows)
+  if (per <= 6) RU(6);
+  else RU(16);
+#undef RU
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, const int* n_rows_dev, int max_rows,
+                    cudaStream_t stream) {
+  MT_CHECK_ARG(D <= 512, "rvq: dim %d must be <= 512", D);
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  const int per = ceil_div(D, 32);
+#define RP(P) rvq_update_kernel<P, false><<<blocks, 256, 0, stream>>>(rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, n_rows_dev, max_rows)
+  if (per <= 6) RP(6);
+  else RP(16);
+#undef RP
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // namespace meshtok

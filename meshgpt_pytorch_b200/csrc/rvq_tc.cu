@@ -1,0 +1,429 @@
+// K8a: residual-VQ nearest-codebook search on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// Replaces the EuclideanCodebook distance + argmax of vector_quantize_pytorch.ResidualVQ (eval) called
+// at meshgpt_pytorch.py:842 - a (R x K x D) = (28288 x 16384 x 192) contraction per level at the
+// MeshGPT shape, which the reference does as an fp32 cuBLAS GEMM into a materialised (R, K) tensor.
+//
+// Screening GEMM:   s~[r, j] = |e_j|^2 - 2 <fp16(r), fp16(e_j)>          (fp32 accumulate in TMEM)
+//   * operands are fp16, not bf16: tcgen05 kind::f16 runs both at the same rate, and fp16's 11-bit
+//     significand makes the screening error bound 8x tighter, which is what keeps the number of rows
+//     that need the exact re-scan negligible.  Rows are pre-scaled by a per-row power of two (max |r_d|
+//     -> [0.5, 1)) and the codebook by one global power of two, so nothing overflows and the scaling is
+//     undone exactly in the epilogue;
+//   * work unit = (256-row tile of residuals) x (one split of the codebook, <= 4096 codes);
+//   * the row tile lives in shared memory as fp16 in the canonical K-major UMMA layout (two M=128
+//     halves -> two accumulators), the codebook streams through a 6-stage ring of 16 KB stages
+//     (128 codes x 64 dims) filled by cp.async.bulk from a pre-tiled fp16 image of the codebook;
+//   * accumulators are double buffered in TMEM (2 buffers x 2 halves x 128 columns = all 512 columns) so
+//     the epilogue of tile t overlaps the MMAs of tile t+1;
+//   * epilogue warps (one TMEM lane = one row per thread) keep the two smallest s~ and their indices.
+// The exact fp32 decision is taken by rvq_rescore_kernel on the screened candidates, with the
+// reference's own formula; rows whose candidate list might be incomplete go to the exact fp32 scan.
+//
+// Warp roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
+// w4..w11 epilogue + row-tile loader (w4-7: rows 0-127, w8-11: rows 128-255; TMEM lane quarter = warp%4).
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+#include <cuda_fp16.h>
+
+namespace meshtok {
+
+namespace {
+
+using namespace tc;
+
+constexpr int M_TILE = 256;        // rows per unit (two UMMA M=128 halves)
+constexpr int N_TILE = 128;        // codes per accumulator tile (UMMA N)
+constexpr int KC = 64;             // K elements per pipeline stage
+constexpr int STAGES = 6;
+constexpr int STAGE_BYTES = N_TILE * KC * 2;   // 16 KB
+constexpr int MAX_SPLIT_CODES = 4096;          // e2 slice kept in shared memory per unit
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_THREADS = 256;
+constexpr uint32_t SBO_B = (KC / 8) * 128;     // 1024: next 8 codes inside a stage
+
+template <int D>
+struct Smem {
+  static constexpr uint32_t SBO_A = (D / 8) * 128;
+  static constexpr uint32_t HALF_BYTES = 128 * D * 2;
+  static constexpr uint32_t A_BYTES = 2 * HALF_BYTES;
+  static constexpr uint32_t B_OFF = A_BYTES;
+  static constexpr uint32_t E2_OFF = B_OFF + STAGES * STAGE_BYTES;
+  static constexpr uint32_t BAR_OFF = E2_OFF + MAX_SPLIT_CODES * 4;
+  static constexpr uint32_t TOTAL = BAR_OFF + 256;
+};
+
+struct SearchArgs {
+  const float* rows;       // (R, D) fp32 residuals
+  const uint8_t* image;    // fp16 codebook image: [K/128 tiles][D/64 chunks][16 KB canonical stage]
+  const float* e2;         // (K) |e_j|^2
+  const float* rscale;     // (R) power-of-two row scales
+  float escale;            // power-of-two codebook scale baked into the image
+  const int* n_rows_dev;
+  int max_rows, K, n_splits, tiles_per_split;
+  float4* partial;         // (R, n_splits): {best, idx_best, second, idx_second}
+};
+
+template <int D>
+__global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using L = Smem<D>;
+  constexpr int KCHUNKS = D / KC;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + L::B_OFF;
+  float* sE2 = reinterpret_cast<float*>(smem + L::E2_OFF);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* b_full = bars;                 // [STAGES]
+  uint64_t* b_empty = bars + STAGES;       // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint64_t* a_full = acc_empty + 2;
+  uint64_t* a_empty = a_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+  const int warp = warp_id(), lane = lane_id();
+  const int n_rows = min(*a.n_rows_dev, a.max_rows);
+  const int m_tiles = (n_rows + M_TILE - 1) / M_TILE;
+  const int units = m_tiles * a.n_splits;
+  // contiguous unit ranges so that consecutive units of one CTA share the row tile
+  const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
+  const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_THREADS / 32); }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: stream codebook stages =====
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int u = u0; u < u1; ++u) {
+        const int tile0 = (u % a.n_splits) * a.tiles_per_split;
+        for (int t = 0; t < a.tiles_per_split; ++t) {
+          const uint8_t* src = a.image + (size_t)(tile0 + t) * KCHUNKS * STAGE_BYTES;
+          for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&b_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES);
+            bulk_g2s(sB + s * STAGE_BYTES, src + (size_t)kc * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(128, N_TILE, /*bf16=*/false);
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      uint32_t it = 0, acc_it = 0, a_phase = 0;
+      int prev_m = -1;
+      for (int u = u0; u < u1; ++u) {
+        const int m_tile = u / a.n_splits;
+        if (m_tile != prev_m) {
+          mbar_wait(a_full, a_phase);
+          a_phase ^= 1;
+          prev_m = m_tile;
+          tcgen05_fence_after();
+        }
+        for (int t = 0; t < a.tiles_per_split; ++t, ++acc_it) {
+          const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+          mbar_wait(&acc_empty[buf], aph ^ 1);
+          tcgen05_fence_after();
+          for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
+            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+            mbar_wait(&b_full[s], ph);
+            tcgen05_fence_after();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+              for (int k16 = 0; k16 < KC / 16; ++k16) {
+                const uint64_t da = make_smem_desc(sA_addr + h * L::HALF_BYTES + (kc * (KC / 8) + k16 * 2) * 128, 128, L::SBO_A);
+                const uint64_t db = make_smem_desc(sB_addr + s * STAGE_BYTES + k16 * 2 * 128, 128, SBO_B);
+                umma_f16(tmem_base + (buf * 2 + h) * N_TILE, da, db, idesc, (kc | k16) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&b_empty[s]);
+          }
+          umma_commit(&acc_full[buf]);
+        }
+        const int next_m = (u + 1 < u1) ? (u + 1) / a.n_splits : -1;
+        if (next_m != m_tile) umma_commit(a_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== row-tile loader + epilogue =====
+    const int ew = warp - 4;                 // 0..7
+    const int et = threadIdx.x - 128;        // 0..255
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int h = ew >> 2;                   // row half
+    const int row_in_tile = h * 128 + q * 32 + lane;
+    uint32_t acc_it = 0, a_empty_phase = 0;
+    int prev_m = -1;
+    for (int u = u0; u < u1; ++u) {
+      const int m_tile = u / a.n_splits, split = u % a.n_splits;
+      const int tile0 = split * a.tiles_per_split;
+      named_bar_sync(1, EPI_THREADS);  // every epilogue thread is done with the previous unit's sE2
+      const bool new_tile = m_tile != prev_m;
+      if (new_tile) {
+        if (prev_m != -1) { mbar_wait(a_empty, a_empty_phase); a_empty_phase ^= 1; }
+        // fp32 rows -> bf16 canonical layout.  One warp-iteration = 8 rows x 4 k-chunks (16 B each):
+        // global reads are 8 x 128 contiguous bytes, shared writes 512 contiguous bytes.
+        constexpr int KQ = D / 32;
+        for (int item = ew; item < (M_TILE / 8) * KQ; item += EPI_THREADS / 32) {
+          const int g = item / KQ, kq = item % KQ;
+          const int r = g * 8 + (lane & 7);
+          const int k8 = kq * 4 + (lane >> 3);
+          const long long grow = (long long)m_tile * M_TILE + r;
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+          float sc = 1.f;
+          if (grow < n_rows) {
+            const float4* src = reinterpret_cast<const float4*>(a.rows + (size_t)grow * D + k8 * 8);
+            v0 = src[0];
+            v1 = src[1];
+            sc = __ldg(a.rscale + grow);
+          }
+          __half2 p0 = __floats2half2_rn(v0.x * sc, v0.y * sc), p1 = __floats2half2_rn(v0.z * sc, v0.w * sc);
+          __half2 p2 = __floats2half2_rn(v1.x * sc, v1.y * sc), p3 = __floats2half2_rn(v1.z * sc, v1.w * sc);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+          const uint32_t off = (r >> 7) * L::HALF_BYTES + canon_offset(r & 127, k8 * 8, L::SBO_A);
+          *reinterpret_cast<uint4*>(sA + off) = pk;
+        }
+        fence_proxy_async_smem();
+      }
+      for (int i = et; i < a.tiles_per_split * N_TILE; i += EPI_THREADS) sE2[i] = __ldg(a.e2 + (size_t)tile0 * N_TILE + i);
+      named_bar_sync(1, EPI_THREADS);
+      if (new_tile) {
+        if (et == 0) mbar_arrive(a_full);
+        prev_m = m_tile;
+      }
+
+      float b1 = INFINITY, b2 = INFINITY;
+      int i1 = 0, i2 = 0;
+      const long long my_row = (long long)m_tile * M_TILE + row_in_tile;
+      // acc = <r * rscale, e * escale>  ->  -2 <r, e> = acc * cmul
+      const float cmul = -2.f / ((my_row < n_rows ? __ldg(a.rscale + my_row) : 1.f) * a.escale);
+      for (int t = 0; t < a.tiles_per_split; ++t, ++acc_it) {
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(&acc_full[buf], aph);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + h) * N_TILE;
+        const int code0 = (tile0 + t) * N_TILE;
+        const float* e2t = sE2 + t * N_TILE;
+#pragma unroll 1
+        for (int c = 0; c < N_TILE / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 e = *reinterpret_cast<const float4*>(e2t + c * 32 + j);
+            const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              const float s = fmaf(__uint_as_float(v[j + jj]), cmul, ev[jj]);
+              if (s < b2) {
+                const int idx = code0 + c * 32 + j + jj;
+                if (s < b1) { b2 = b1; i2 = i1; b1 = s; i1 = idx; }
+                else { b2 = s; i2 = idx; }
+              }
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      }
+      const long long grow = (long long)m_tile * M_TILE + row_in_tile;
+      if (grow < n_rows)
+        a.partial[(size_t)grow * a.n_splits + split] = make_float4(b1, __int_as_float(i1), b2, __int_as_float(i2));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ---- re-score ---------------------------------------------------------------------------------------
+// One warp per row.  Screening error bound: both operands are rounded to fp16 (relative 2^-11 each, the
+// power-of-two scalings are exact) so |s~ - s| <= 2 ((1+2^-11)^2 - 1) sum_d |r_d e_jd| < 2^-9 * 1.01 * |r| max|e|,
+// plus 2^-25 absolute per element that falls into the fp16 subnormal range after scaling  =: delta  (fp32
+// accumulation error is orders of magnitude below).  Every code whose true score ties the minimum therefore has
+// s~ <= min s~ + 2 delta; if some split's SECOND best is inside that window a third one may hide behind it and the
+// row is sent to the exact scan.
+template <int PER>
+__global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
+                                                          const float* __restrict__ e2, float max_norm, float escale,
+                                                          const float* __restrict__ rscale,
+                                                          const float4* __restrict__ partial, int n_splits,
+                                                          const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ best,
+                                                          int* __restrict__ amb_list, int* __restrict__ amb_count) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const int n = min(*n_dev, max_rows);
+  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
+    float x[PER];
+    float x2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < D ? rows[(size_t)row * D + c] : 0.f;
+      x2 = fmaf(x[i], x[i], x2);
+    }
+    x2 = warp_sum(x2);
+    const float xn = sqrtf(x2);
+    const float delta = 0.001953125f * 1.01f * xn * max_norm +
+                        5.96e-8f * sqrtf((float)D) * (max_norm / rscale[row] + xn / escale) + 1e-7f * (x2 + max_norm * max_norm);
+    float smin = INFINITY;
+    for (int s = lane; s < n_splits; s += 32) smin = fminf(smin, partial[(size_t)row * n_splits + s].x);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    const float window = smin + 2.f * delta;
+    bool ambiguous = false;
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int s = 0; s < n_splits; ++s) {
+      const float4 p = partial[(size_t)row * n_splits + s];
+      if (p.z <= window) ambiguous = true;
+      if (p.x <= window) {
+        const int code = __float_as_int(p.y);
+        float dot = 0.f;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int c = lane + 32 * i;
+          if (c < D) dot = fmaf(x[i], __ldg(cb + (size_t)code * D + c), dot);
+        }
+        dot = warp_sum(dot);
+        const float d2 = __fadd_rn(__fadd_rn(x2, __ldg(e2 + code)), __fmul_rn(dot, -2.f));
+        const float dist = sqrtf(fmaxf(d2, 0.f));
+        if (dist < bd || (dist == bd && code < bi)) { bd = dist; bi = code; }
+      }
+    }
+    if (lane == 0) {
+      best[row] = bi;
+      if (ambiguous) amb_list[atomicAdd(amb_count, 1)] = row;
+    }
+  }
+}
+
+// fp32 codebook * escale -> fp16 image in stage order.
+__global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ cb, int K, int D, float escale, uint8_t* __restrict__ image) {
+  const long long total = (long long)K * (D / 8);  // 16-byte chunks
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int code = (int)(i / (D / 8));
+    const int k8 = (int)(i % (D / 8));
+    const float4* src = reinterpret_cast<const float4*>(cb + (size_t)code * D + k8 * 8);
+    const float4 v0 = src[0], v1 = src[1];
+    __half2 p0 = __floats2half2_rn(v0.x * escale, v0.y * escale), p1 = __floats2half2_rn(v0.z * escale, v0.w * escale);
+    __half2 p2 = __floats2half2_rn(v1.x * escale, v1.y * escale), p3 = __floats2half2_rn(v1.z * escale, v1.w * escale);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+    const int tile = code / N_TILE, r = code % N_TILE;
+    const int kc = (k8 * 8) / KC, kin = (k8 * 8) % KC;
+    const size_t off = ((size_t)tile * (D / KC) + kc) * STAGE_BYTES + tc::canon_offset(r, kin, SBO_B);
+    *reinterpret_cast<uint4*>(image + off) = pk;
+  }
+}
+
+template <int D>
+int launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc_search_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D>::TOTAL));
+    configured = true;
+  }
+  rvq_tc_search_kernel<D><<<grid, NUM_THREADS, Smem<D>::TOTAL, stream>>>(a);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // namespace
+
+int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan) {
+  memset(plan, 0, sizeof(*plan));
+  if (K % N_TILE != 0 || (D != 64 && D != 128 && D != 192)) {
+    set_error("tcgen05 RVQ search supports codebook_size %% 128 == 0 and dim in {64,128,192} (got K=%d, D=%d); "
+              "use the exact path (rvq_exact) for other shapes", K, D);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  const int tiles = K / N_TILE;
+  const int m_tiles = max(1, ceil_div(max_rows, M_TILE));
+  int best_ns = 0;
+  double best_eff = -1.0;
+  for (int ns = 1; ns <= tiles; ns *= 2) {
+    if (tiles % ns != 0) break;
+    if ((tiles / ns) * N_TILE > MAX_SPLIT_CODES) continue;
+    const long long units = (long long)m_tiles * ns;
+    const long long waves = (units + 147) / 148;
+    const double eff = (double)units / (double)(waves * 148);
+    if (eff > best_eff + 0.02) { best_eff = eff; best_ns = ns; }
+    if (units >= 148 * 4) break;
+  }
+  if (best_ns == 0) {
+    set_error("tcgen05 RVQ search: cannot split %d code tiles", tiles);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  plan->m_tiles = m_tiles;
+  plan->n_splits = best_ns;
+  plan->tiles_per_split = tiles / best_ns;
+  plan->units = m_tiles * best_ns;
+  plan->grid = min(plan->units, 148);
+  plan->partial_bytes = align_up((size_t)max(max_rows, 1) * best_ns * sizeof(float4), 256);
+  return MESHTOK_OK;
+}
+
+int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+                         int K, const int* n_rows_dev, int max_rows, const RvqTcPlan& plan, float4* partial, cudaStream_t stream) {
+  if (max_rows == 0) return MESHTOK_OK;
+  SearchArgs a;
+  a.rows = rows; a.rscale = rscale; a.escale = escale; a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.n_rows_dev = n_rows_dev;
+  a.max_rows = max_rows; a.K = K; a.n_splits = plan.n_splits; a.tiles_per_split = plan.tiles_per_split; a.partial = partial;
+  switch (D) {
+    case 64: return launch_search<64>(a, plan.grid, stream);
+    case 128: return launch_search<128>(a, plan.grid, stream);
+    case 192: return launch_search<192>(a, plan.grid, stream);
+  }
+  set_error("tcgen05 RVQ search: unsupported dim %d", D);
+  return MESHTOK_ERR_UNSUPPORTED;
+}
+
+int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
+                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows, int32_t* best,
+                       int* amb_list, int* amb_count, cudaStream_t stream) {
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, n_splits, n_rows_dev, max_rows, best,
+                                                    amb_list, amb_count);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+size_t rvq_codebook_image_bytes(int K, int D) { return (size_t)ceil_div(K, N_TILE) * N_TILE * D * 2; }
+
+int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream) {
+  MT_CHECK_ARG(K % N_TILE == 0 && D % KC == 0, "codebook image needs codebook_size %% 128 == 0 and dim %% 64 == 0 (got %d, %d)", K, D);
+  const long long total = (long long)K * (D / 8);
+  const long long want = (total + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  build_image_kernel<<<blocks, 256, 0, stream>>>(codebook, K, D, escale, static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // namespace meshtok

@@ -1,0 +1,144 @@
+// K4 (memory-bound half): SAGEConv mean aggregation over the face CSR and the row epilogues.
+//
+// Replaces the message passing of torch_geometric.nn.SAGEConv (scatter-add of x[edge_index[0]] onto
+// edge_index[1], divided by clamp(count, 1)) called at meshgpt_pytorch.py:764 and :769, the
+// F.normalize(p=2) that ends every SAGEConv (normalize=True, :471-474) and init_encoder_act_and_norm
+// (SiLU + LayerNorm, :545-548, applied at :766).  One warp per face row; neighbour rows are summed in
+// ascending source order, the order the reference's CPU scatter_add visits them in, so the result is
+// deterministic (the reference's GPU path uses atomics and is not).
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace meshtok {
+
+namespace {
+
+template <int CHUNKS>  // float4 chunks per lane (d = 128 * CHUNKS at most)
+__global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
+                                                          const int* __restrict__ src, long long cap,
+                                                          float* __restrict__ agg, const Counts* counts) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const int n_rows = counts->n_faces;
+  const int d4 = d >> 2;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n_rows; row += gridDim.x * wpb) {
+    const long long s = indptr[row];
+    const long long e_true = indptr[row + 1];
+    const long long e = e_true < cap ? e_true : cap;
+    float4 acc[CHUNKS];
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long q = s; q < e; ++q) {
+      const int srow = src[q];
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)srow * d);
+#pragma unroll
+      for (int c = 0; c < CHUNKS; ++c) {
+        const int i4 = lane + 32 * c;
+        if (i4 < d4) {
+          const float4 v = __ldg(xr + i4);
+          acc[c].x += v.x; acc[c].y += v.y; acc[c].z += v.z; acc[c].w += v.w;
+        }
+      }
+    }
+    const float cnt = fmaxf((float)(e_true - s), 1.f);
+    float4* out = reinterpret_cast<float4*>(agg + (size_t)row * d);
+#pragma unroll
+    for (int c = 0; c < CHUNKS; ++c) {
+      const int i4 = lane + 32 * c;
+      if (i4 < d4)
+        out[i4] = make_float4(__fdiv_rn(acc[c].x, cnt), __fdiv_rn(acc[c].y, cnt), __fdiv_rn(acc[c].z, cnt), __fdiv_rn(acc[c].w, cnt));
+    }
+  }
+}
+
+template <int PER>  // elements per lane (d <= 32 * PER)
+__global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, int d, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const Counts* counts) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const int n_rows = counts->n_faces;
+  for (int row = blockIdx.x * wpb + warp_id(); row < n_rows; row += gridDim.x * wpb) {
+    float* xr = x + (size_t)row * d;
+    float v[PER];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < d ? xr[c] : 0.f;
+      ss += v[i] * v[i];
+    }
+    ss = warp_sum(ss);
+    const float den = fmaxf(sqrtf(ss), 1e-12f);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = __fdiv_rn(v[i], den);
+    if (gamma != nullptr) {
+      // SiLU then LayerNorm (biased variance, eps 1e-5)
+      float mean = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        const float t = v[i];
+        v[i] = c < d ? __fdiv_rn(t, 1.f + expf(-t)) : 0.f;
+        mean += v[i];
+      }
+      mean = warp_sum(mean) / (float)d;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        const float t = c < d ? v[i] - mean : 0.f;
+        var += t * t;
+      }
+      var = warp_sum(var) / (float)d;
+      const float rstd = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d) v[i] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d) xr[c] = v[i];
+    }
+  }
+}
+
+}  // namespace
+
+int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity, float* agg,
+                       const Counts* counts, int max_rows, cudaStream_t stream) {
+  MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  const int chunks = ceil_div(d / 4, 32);
+#define GM(C) gather_mean_kernel<C><<<blocks, 256, 0, stream>>>(x, d, indptr, src, edge_capacity, agg, counts)
+  switch (chunks) {
+    case 1: GM(1); break;
+    case 2: GM(2); break;
+    case 3: GM(3); break;
+    case 4: GM(4); break;
+    default: GM(8); break;
+  }
+#undef GM
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_row_norm(float* x, int d, const float* gamma, const float* beta, const Counts* counts, int max_rows,
+                    cudaStream_t stream) {
+  MT_CHECK_ARG(d >= 1 && d <= 1024, "row_norm: feature width %d must be in [1, 1024]", d);
+  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  const int per = ceil_div(d, 32);
+#define RN(P) row_norm_kernel<P><<<blocks, 256, 0, stream>>>(x, d, gamma, beta, counts)
+  if (per <= 2) RN(2);
+  else if (per <= 4) RN(4);
+  else if (per <= 8) RN(8);
+  else if (per <= 18) RN(18);
+  else RN(32);
+#undef RN
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // namespace meshtok

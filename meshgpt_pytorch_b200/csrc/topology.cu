@@ -1,0 +1,510 @@
+// K1: face adjacency + batch topology (packed face rows, vertex incidence CSR, face CSR by target).
+//
+// Replaces derive_face_edges_from_faces (reference meshgpt_pytorch/data.py:297-340) and the
+// offset / boolean-index packing of MeshAutoencoder.encode (meshgpt_pytorch.py:748-760) and the
+// scatter index construction of quantize (meshgpt_pytorch.py:807-824).
+//
+// One CTA per mesh, everything in shared memory:
+//   1. faces -> int32, validity (a face is padding if ANY slot == pad_id, data.py:317), rank of
+//      each valid face among the valid faces (= its packed row inside the mesh);
+//   2. counting sort of (face,slot) by vertex id -> incidence lists, each list ascending in
+//      (face, slot) = the order in which the reference's scatter_add visits them on the CPU;
+//   3. per face i (one warp): candidates = union of the incidence lists of its slots; for each
+//      candidate k the exact slot counts n(i,k), n(k,i) of data.py:324-325 are recomputed from the
+//      two faces and turned into bits of an out- and an in-bitmap; popc gives the degrees, a
+//      prefix-popc walk emits the neighbours in ascending order (= the reference's row-major order).
+// The relation is NOT symmetric for degenerate faces (SURVEY hard part 1), hence two bitmaps.
+#include <limits.h>
+
+#include "common.cuh"
+#include "topology.cuh"
+
+namespace meshtok {
+
+namespace {
+
+constexpr int MODE_COUNT = 0;
+constexpr int MODE_FILL_DENSE = 1;
+constexpr int MODE_FILL_CSR = 2;
+
+// Walks the set bits of words[wlo..whi] in ascending order; fn(rank, bit_index).  Returns the count.
+template <class Fn>
+__device__ __forceinline__ int warp_emit_bits(const uint32_t* words, int wlo, int whi, Fn fn) {
+  int base = 0;
+  const int lane = lane_id();
+  for (int w0 = wlo; w0 <= whi; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t bits = (w <= whi) ? words[w] : 0u;
+    const int c = __popc(bits);
+    const int incl = warp_inclusive_scan(c);
+    int off = base + incl - c;
+    while (bits) {
+      const int bpos = __ffs(bits) - 1;
+      bits &= bits - 1;
+      fn(off++, w * 32 + bpos);
+    }
+    base += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  return base;
+}
+
+__device__ __forceinline__ int warp_count_bits(const uint32_t* words, int wlo, int whi) {
+  int c = 0;
+  for (int w = wlo + lane_id(); w <= whi; w += 32) c += __popc(words[w]);
+  return warp_sum_int(c);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
+  extern __shared__ int smem[];
+  const int b = blockIdx.x;
+  const int F = p.F, nvf = p.nvf, V = p.V;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = lane_id(), warp = warp_id(), nwarps = nt >> 5;
+  const int FN = F * nvf;
+
+  int* fv = smem;                 // [FN]   vertex id of (face,slot) or -1
+  int* frank = fv + FN;           // [F]    exclusive rank among valid faces
+  int* fptr = frank + F;          // [F]    exclusive prefix of the degrees (fill modes)
+  int* vstart = fptr + F;         // [V+1]  incidence list offsets
+  int* vcur = vstart + (V + 1);   // [V+1]  fill cursors, later vertex ranks
+  int* inc = vcur + (V + 1);      // [FN]   incidence entries face*nvf+slot
+  int* scratch = inc + FN;        // [48]
+  uint32_t* bits = reinterpret_cast<uint32_t*>(scratch + 48);  // [nwarps][p.words_per_warp]
+  const int Wf = (F + 31) >> 5;
+  const int Ww = p.words_per_warp;
+
+  // ---- 1. faces -------------------------------------------------------------------------------
+  int bad = 0;
+  const int64_t* fsrc = p.faces + (size_t)b * FN;
+  for (int idx = tid; idx < FN; idx += nt) {
+    const long long v = fsrc[idx];
+    int iv;
+    if (v == p.pad_id) iv = -1;
+    else if (v < 0 || v >= V) { iv = -1; bad = 1; }
+    else iv = (int)v;
+    fv[idx] = iv;
+  }
+  if (bad) atomicOr(p.status, MESHTOK_WS_STATUS_VERTEX_RANGE);
+  for (int i = tid; i < nwarps * Ww; i += nt) bits[i] = 0u;
+  for (int v = tid; v <= V; v += nt) vstart[v] = 0;
+  if (tid < 48) scratch[tid] = 0;
+  __syncthreads();
+
+  auto face_valid = [&](int f) {
+    bool ok = true;
+    for (int c = 0; c < nvf; ++c) ok &= fv[f * nvf + c] >= 0;
+    return ok;
+  };
+
+  for (int f = tid; f < F; f += nt) frank[f] = face_valid(f) ? 1 : 0;
+  __syncthreads();
+  const int nvalid = block_exclusive_scan(frank, F, scratch);
+
+  // ---- 2. incidence lists ---------------------------------------------------------------------
+  for (int idx = tid; idx < FN; idx += nt) {
+    const int f = idx / nvf;
+    if (face_valid(f)) atomicAdd(&vstart[fv[idx]], 1);
+  }
+  __syncthreads();
+  {
+    int local = 0;
+    for (int v = tid; v < V; v += nt) local += vstart[v] > 0;
+    local = warp_sum_int(local);
+    if (lane == 0 && local) atomicAdd(&scratch[40], local);
+  }
+  __syncthreads();
+  const int nref = scratch[40];
+  block_exclusive_scan(vstart, V + 1, scratch);
+  for (int v = tid; v <= V; v += nt) vcur[v] = vstart[v];
+  __syncthreads();
+  for (int idx = tid; idx < FN; idx += nt) {
+    const int f = idx / nvf;
+    if (face_valid(f)) {
+      const int pos = atomicAdd(&vcur[fv[idx]], 1);
+      inc[pos] = idx;
+    }
+  }
+  __syncthreads();
+  // short lists: one thread each, insertion sort
+  for (int v = tid; v < V; v += nt) {
+    const int s = vstart[v], e = vstart[v + 1];
+    if (e - s > 1 && e - s <= 32) {
+      for (int i = s + 1; i < e; ++i) {
+        const int key = inc[i];
+        int j = i - 1;
+        while (j >= s && inc[j] > key) { inc[j + 1] = inc[j]; --j; }
+        inc[j + 1] = key;
+      }
+    }
+  }
+  __syncthreads();
+  // long lists (high-valence vertices): one warp each, bitmap sort over the FN key space
+  {
+    uint32_t* wb = bits + warp * Ww;
+    const int Wk = (FN + 31) >> 5;
+    for (int v = warp; v < V; v += nwarps) {
+      const int s = vstart[v], e = vstart[v + 1];
+      if (e - s <= 32) continue;
+      for (int i = s + lane; i < e; i += 32) {
+        const int key = inc[i];
+        atomicOr(&wb[key >> 5], 1u << (key & 31));
+      }
+      __syncwarp();
+      warp_emit_bits(wb, 0, Wk - 1, [&](int r, int key) { inc[s + r] = key; });
+      __syncwarp();
+      for (int w = lane; w < Wk; w += 32) wb[w] = 0u;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- fill-mode prologue: local prefix of the degrees computed by the COUNT pass --------------
+  int mesh_total = 0;
+  if (MODE != MODE_COUNT && p.do_adjacency) {
+    const int* deg = (MODE == MODE_FILL_DENSE) ? p.deg_out : p.deg_in;
+    for (int f = tid; f < F; f += nt) fptr[f] = deg[(size_t)b * F + f];
+    __syncthreads();
+    mesh_total = block_exclusive_scan(fptr, F, scratch);
+  }
+  const int face_off = (MODE == MODE_FILL_CSR) ? p.face_off[b] : 0;
+  const int edge_off = (MODE == MODE_FILL_CSR) ? p.edge_off[b] : 0;
+
+  // ---- 3. adjacency ---------------------------------------------------------------------------
+  if (p.do_adjacency) {
+    uint32_t* obits = bits + warp * Ww;
+    uint32_t* ibits = obits + Wf;
+    const int thr = p.threshold;
+    const bool keep3 = p.include_self != 0;
+    for (int i = warp; i < F; i += nwarps) {
+      if (!face_valid(i)) {
+        if (MODE == MODE_COUNT && lane == 0) {
+          p.deg_out[(size_t)b * F + i] = 0;
+          p.deg_in[(size_t)b * F + i] = 0;
+        }
+        continue;
+      }
+      int mine[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) mine[c] = c < nvf ? fv[i * nvf + c] : -2 - c;
+      int wmin = INT_MAX, wmax = -1;
+      for (int c = 0; c < nvf; ++c) {
+        const int v = mine[c];
+        bool dup = false;
+        for (int c0 = 0; c0 < c; ++c0) dup |= mine[c0] == v;
+        if (dup) continue;  // same list again
+        const int s = vstart[v], e = vstart[v + 1];
+        for (int q = s + lane; q < e; q += 32) {
+          const int k = inc[q] / nvf;
+          int other[4];
+#pragma unroll
+          for (int d = 0; d < 4; ++d) other[d] = d < nvf ? fv[k * nvf + d] : -7 - d;
+          int n_ik = 0, n_ki = 0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            bool in_k = false, in_i = false;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+              in_k |= mine[a] == other[d];
+              in_i |= other[a] == mine[d];
+            }
+            n_ik += (a < nvf) && in_k;
+            n_ki += (a < nvf) && in_i;
+          }
+          const bool eo = n_ik >= thr && (keep3 || n_ik != 3);
+          const bool ei = n_ki >= thr && (keep3 || n_ki != 3);
+          if (eo) atomicOr(&obits[k >> 5], 1u << (k & 31));
+          if (ei) atomicOr(&ibits[k >> 5], 1u << (k & 31));
+          if (eo || ei) { wmin = min(wmin, k >> 5); wmax = max(wmax, k >> 5); }
+        }
+      }
+      wmin = warp_min_int(wmin);
+      wmax = warp_max_int(wmax);
+      __syncwarp();
+      if (wmax < 0) {
+        if (MODE == MODE_COUNT && lane == 0) {
+          p.deg_out[(size_t)b * F + i] = 0;
+          p.deg_in[(size_t)b * F + i] = 0;
+        }
+        continue;
+      }
+      if (MODE == MODE_COUNT) {
+        const int dout = warp_count_bits(obits, wmin, wmax);
+        const int din = warp_count_bits(ibits, wmin, wmax);
+        if (lane == 0) {
+          p.deg_out[(size_t)b * F + i] = dout;
+          p.deg_in[(size_t)b * F + i] = din;
+          atomicAdd(&scratch[41], dout);
+        }
+      } else if (MODE == MODE_FILL_DENSE) {
+        int64_t* dst = p.dense_out + ((size_t)b * p.emax + fptr[i]) * 2;
+        warp_emit_bits(obits, wmin, wmax, [&](int r, int k) {
+          dst[2 * r] = i;
+          dst[2 * r + 1] = k;
+        });
+      } else {
+        const int base = edge_off + fptr[i];
+        warp_emit_bits(ibits, wmin, wmax, [&](int r, int k) {
+          const long long pos = (long long)base + r;
+          if (pos < p.edge_capacity) p.src[pos] = face_off + frank[k];
+        });
+      }
+      __syncwarp();
+      for (int w = wmin + lane; w <= wmax; w += 32) { obits[w] = 0u; ibits[w] = 0u; }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+
+  // ---- 4. outputs -----------------------------------------------------------------------------
+  if (MODE == MODE_COUNT) {
+    if (tid == 0) {
+      int* mc = p.mesh_counts + 4 * b;
+      mc[0] = nvalid;
+      mc[1] = nref;
+      mc[2] = scratch[41];
+      mc[3] = 0;
+      if (p.edge_counts_out) p.edge_counts_out[b] = scratch[41];
+    }
+    return;
+  }
+  if (MODE == MODE_FILL_DENSE) {
+    int64_t* dst = p.dense_out + (size_t)b * p.emax * 2;
+    for (int t = mesh_total * 2 + tid; t < p.emax * 2; t += nt) dst[t] = p.pad_id;
+    return;
+  }
+  // MODE_FILL_CSR: maps + vertex CSR + face CSR row pointers
+  const int vert_off = p.vert_off[b];
+  for (int f = tid; f < F; f += nt) {
+    const bool ok = face_valid(f);
+    const int row = face_off + frank[f];
+    p.face_row[(size_t)b * F + f] = ok ? row : -1;
+    if (ok) {
+      p.row_face[row] = b * F + f;
+      if (p.do_adjacency) p.indptr[row] = edge_off + fptr[f];
+    }
+  }
+  if (p.do_adjacency && edge_off + mesh_total > p.edge_capacity && tid == 0)
+    atomicOr(p.status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
+  for (int v = tid; v < V; v += nt) vcur[v] = (vstart[v + 1] > vstart[v]) ? 1 : 0;
+  __syncthreads();
+  block_exclusive_scan(vcur, V, scratch);
+  for (int v = tid; v < V; v += nt) {
+    const bool ref = vstart[v + 1] > vstart[v];
+    const int vr = vert_off + vcur[v];
+    p.vert_row[(size_t)b * V + v] = ref ? vr : -1;
+    if (ref) p.vptr[vr] = face_off * nvf + vstart[v];
+  }
+  const int nent = vstart[V];
+  for (int e = tid; e < nent; e += nt) {
+    const int idx = inc[e];
+    const int f = idx / nvf, c = idx - f * nvf;
+    p.vinc[(size_t)face_off * nvf + e] = (face_off + frank[f]) * nvf + c;
+  }
+  if (b == gridDim.x - 1 && tid == 0) {
+    const int nf = p.face_off[gridDim.x], nv = p.vert_off[gridDim.x];
+    p.vptr[nv] = nf * nvf;
+    if (p.do_adjacency) p.indptr[nf] = p.edge_off[gridDim.x];
+  }
+}
+
+// exclusive prefix sums of the per-mesh counts -> face_off / vert_off / edge_off, and the totals.
+__global__ void __launch_bounds__(1024) mesh_offsets_kernel(const int* __restrict__ mesh_counts, int* __restrict__ offs,
+                                                            int B, Counts* counts) {
+  __shared__ int buf[4096];
+  __shared__ int scratch[40];
+  for (int q = 0; q < 3; ++q) {
+    int running = 0;
+    int* out = offs + (size_t)q * (B + 1);
+    for (int base = 0; base < B; base += 4096) {
+      const int n = min(4096, B - base);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = mesh_counts[4 * (base + i) + q];
+      __syncthreads();
+      const int total = block_exclusive_scan(buf, n, scratch);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) out[base + i] = running + buf[i];
+      running += total;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      out[B] = running;
+      if (q == 0) counts->n_faces = running;
+      if (q == 1) counts->n_vrows = running;
+      if (q == 2) counts->n_edges = running;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- user supplied face_edges -> CSR by target (meshgpt_pytorch.py:752-754) -----------------------
+// edges (B,E,2): row0 = first column = source i, row1 = second column = target j, both offset by the
+// number of valid faces of the preceding meshes; an edge is kept iff neither entry equals pad_id.
+__global__ void user_edges_count_kernel(const int64_t* __restrict__ edges, int B, int E, int64_t pad_id,
+                                        const int* __restrict__ face_off, int* __restrict__ ecount, int* status) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * E) return;
+  const long long i = edges[2 * idx], j = edges[2 * idx + 1];
+  if (i == pad_id || j == pad_id) return;
+  const int b = (int)(idx / E);
+  const long long n = face_off[B];
+  const long long s = face_off[b] + i, t = face_off[b] + j;
+  if (s < 0 || s >= n || t < 0 || t >= n) { atomicOr(status, MESHTOK_WS_STATUS_EDGE_RANGE); return; }
+  atomicAdd(&ecount[t], 1);
+}
+
+__global__ void __launch_bounds__(256) user_edges_mesh_sum_kernel(const int* __restrict__ ecount, const int* __restrict__ face_off,
+                                                                  int* __restrict__ mesh_counts) {
+  __shared__ int acc;
+  if (threadIdx.x == 0) acc = 0;
+  __syncthreads();
+  const int b = blockIdx.x;
+  int local = 0;
+  for (int r = face_off[b] + threadIdx.x; r < face_off[b + 1]; r += blockDim.x) local += ecount[r];
+  local = warp_sum_int(local);
+  if (lane_id() == 0 && local) atomicAdd(&acc, local);
+  __syncthreads();
+  if (threadIdx.x == 0) mesh_counts[4 * b + 2] = acc;
+}
+
+__global__ void __launch_bounds__(256) user_edges_indptr_kernel(const int* __restrict__ ecount, const int* __restrict__ face_off,
+                                                                const int* __restrict__ edge_off, int* __restrict__ indptr,
+                                                                int* __restrict__ cursor, int B) {
+  __shared__ int buf[2048];
+  __shared__ int scratch[40];
+  const int b = blockIdx.x;
+  int running = edge_off[b];
+  const int r0 = face_off[b], r1 = face_off[b + 1];
+  for (int base = r0; base < r1; base += 2048) {
+    const int n = min(2048, r1 - base);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) buf[i] = ecount[base + i];
+    __syncthreads();
+    const int total = block_exclusive_scan(buf, n, scratch);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      indptr[base + i] = running + buf[i];
+      cursor[base + i] = running + buf[i];
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (b == B - 1 && threadIdx.x == 0) indptr[face_off[B]] = edge_off[B];
+}
+
+__global__ void user_edges_fill_kernel(const int64_t* __restrict__ edges, int B, int E, int64_t pad_id,
+                                       const int* __restrict__ face_off, int* __restrict__ cursor, int* __restrict__ etmp,
+                                       long long capacity, int* status) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)B * E) return;
+  const long long i = edges[2 * idx], j = edges[2 * idx + 1];
+  if (i == pad_id || j == pad_id) return;
+  const int b = (int)(idx / E);
+  const long long n = face_off[B];
+  const long long s = face_off[b] + i, t = face_off[b] + j;
+  if (s < 0 || s >= n || t < 0 || t >= n) return;
+  const int pos = atomicAdd(&cursor[t], 1);
+  if (pos < capacity) etmp[pos] = (int)idx;
+  else atomicOr(status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
+}
+
+// per target row: order the incoming edges by their position in the user's list (the order in which
+// the reference's scatter_add visits them on the CPU), then replace edge ids by source rows.
+__global__ void user_edges_sort_kernel(const int64_t* __restrict__ edges, int E, const int* __restrict__ face_off,
+                                       const int* __restrict__ indptr, const int* __restrict__ etmp, int* __restrict__ src,
+                                       const Counts* counts, long long capacity) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= counts->n_faces) return;
+  const long long s = indptr[row], e = min((long long)indptr[row + 1], capacity);
+  for (long long i = s; i < e; ++i) {  // selection by rank: lists are short
+    const int key = etmp[i];
+    int rank = 0;
+    for (long long j = s; j < e; ++j) rank += etmp[j] < key;
+    const int b = key / E;
+    src[s + rank] = face_off[b] + (int)edges[2 * (long long)key];
+  }
+}
+
+size_t topo_smem_bytes(int F, int nvf, int V, int nthreads, int* words_per_warp) {
+  const int Wf = (F + 31) / 32;
+  const int Wk = (F * nvf + 31) / 32;
+  const int Ww = (2 * Wf > Wk ? 2 * Wf : Wk);
+  if (words_per_warp) *words_per_warp = Ww;
+  size_t ints = (size_t)F * nvf * 2 + (size_t)F * 2 + (size_t)(V + 1) * 2 + 48 + (size_t)(nthreads / 32) * Ww;
+  return ints * 4;
+}
+
+}  // namespace
+
+int topo_threads(int F) { return F >= 384 ? 1024 : (F >= 96 ? 512 : 256); }
+
+int topo_check_shape(int B, int F, int nvf, int V) {
+  if (B <= 0 || F <= 0 || V <= 0 || (nvf != 3 && nvf != 4)) {
+    set_error("topology: need B,F,V > 0 and nvf in {3,4} (got B=%d F=%d nvf=%d V=%d)", B, F, nvf, V);
+    return MESHTOK_ERR_INVALID_ARGUMENT;
+  }
+  if ((long long)B * F >= (1ll << 30) || (long long)B * V >= (1ll << 30) || (long long)B * F * nvf >= (1ll << 31)) {
+    set_error("topology: batch too large for int32 row ids (B*F=%lld, B*V=%lld)", (long long)B * F, (long long)B * V);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  int ww;
+  const size_t smem = topo_smem_bytes(F, nvf, V, topo_threads(F), &ww);
+  if (smem > 220 * 1024) {
+    set_error("topology: one mesh (F=%d, nvf=%d, V=%d) needs %zu B of shared memory, more than one SM has; "
+              "meshes this large are not supported by the per-mesh kernel", F, nvf, V, smem);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  return MESHTOK_OK;
+}
+
+template <int MODE>
+static int launch_topology(TopoParams p, cudaStream_t stream) {
+  const int nt = topo_threads(p.F);
+  int ww = 0;
+  const size_t smem = topo_smem_bytes(p.F, p.nvf, p.V, nt, &ww);
+  p.words_per_warp = ww;
+  static size_t configured[3] = {0, 0, 0};
+  if (smem > 48 * 1024 && smem > configured[MODE]) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(topology_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured[MODE] = 220 * 1024;
+  }
+  topology_kernel<MODE><<<p.B, nt, smem, stream>>>(p);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int topo_count(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_COUNT>(p, stream); }
+int topo_fill_dense(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_FILL_DENSE>(p, stream); }
+int topo_fill_csr(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_FILL_CSR>(p, stream); }
+
+int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream) {
+  mesh_offsets_kernel<<<1, 1024, 0, stream>>>(mesh_counts, offs, B, counts);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
+                    int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,
+                    int* status, cudaStream_t stream) {
+  const int* face_off = offs;
+  const int* edge_off = offs + 2 * (size_t)(B + 1);
+  MT_CHECK_CUDA(cudaMemsetAsync(ecount, 0, sizeof(int) * (size_t)max_rows, stream));
+  const long long ne = (long long)B * E;
+  if (ne > 0) {
+    const int blocks = (int)((ne + 255) / 256);
+    user_edges_count_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, pad_id, face_off, ecount, status);
+    MT_CHECK_LAUNCH();
+  }
+  user_edges_mesh_sum_kernel<<<B, 256, 0, stream>>>(ecount, face_off, mesh_counts);
+  MT_CHECK_LAUNCH();
+  mesh_offsets_kernel<<<1, 1024, 0, stream>>>(mesh_counts, offs, B, counts);
+  MT_CHECK_LAUNCH();
+  user_edges_indptr_kernel<<<B, 256, 0, stream>>>(ecount, face_off, edge_off, indptr, cursor, B);
+  MT_CHECK_LAUNCH();
+  if (ne > 0) {
+    const int blocks = (int)((ne + 255) / 256);
+    user_edges_fill_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, pad_id, face_off, cursor, etmp, capacity, status);
+    MT_CHECK_LAUNCH();
+    user_edges_sort_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(edges, E, face_off, indptr, etmp, src, counts, capacity);
+    MT_CHECK_LAUNCH();
+  }
+  return MESHTOK_OK;
+}
+
+}  // namespace meshtok

@@ -1,0 +1,46 @@
+#pragma once
+#include "common.cuh"
+
+namespace meshtok {
+
+struct TopoParams {
+  const int64_t* faces;   // (B,F,nvf)
+  int B, F, nvf, V;
+  int64_t pad_id;
+  int threshold;          // shared-slot threshold (2, or 1 for neighbor_if_share_one_vertex)
+  int include_self;
+  int do_adjacency;       // 0 when the caller supplies face_edges
+  int words_per_warp;     // filled by the launcher
+  int* status;
+  int* mesh_counts;       // [B][4] nvalid, nref, nedges, -
+  int* deg_out;           // [B*F]
+  int* deg_in;            // [B*F]
+  int32_t* edge_counts_out;  // [B] or null
+  // fill dense
+  int emax;
+  int64_t* dense_out;     // (B, emax, 2)
+  // fill csr
+  const int* face_off;    // [B+1]
+  const int* vert_off;    // [B+1]
+  const int* edge_off;    // [B+1]
+  int* face_row;          // [B*F]
+  int* row_face;          // [B*F]
+  int* vert_row;          // [B*V]
+  int* vptr;              // [B*V+1]
+  int* vinc;              // [B*F*nvf]
+  int* indptr;            // [B*F+1]
+  int* src;               // [edge_capacity]
+  long long edge_capacity;
+};
+
+int topo_threads(int F);
+int topo_check_shape(int B, int F, int nvf, int V);
+int topo_count(const TopoParams& p, cudaStream_t stream);
+int topo_fill_dense(const TopoParams& p, cudaStream_t stream);
+int topo_fill_csr(const TopoParams& p, cudaStream_t stream);
+int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream);
+int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
+                    int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,
+                    int* status, cudaStream_t stream);
+
+}  // namespace meshtok
