@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py - faces tokenized / second on B200 (BASELINE.json metric), one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c1|c4] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one tokenize() of one batch of synthetic meshes per rank (workload c2 = BASELINE configs[1]: 64 meshes x
+800 triangle faces, ResidualVQ 16384 x 192, 2 quantizers, random-init weights).  Meshes shard across ranks with no
+data-path collective (weak scaling: every rank tokenizes its own 64 meshes per step); the only exchange is the NCCL
+all-reduce of the codebook-usage histogram, inside the timed region.
+
+  value       device-timed (CUDA events around each step, inputs resident in HBM, L2 flushed between steps,
+              max over ranks) whole-job faces/s.
+  e2e         same metric through the host-buffer call MeshAutoencoder.tokenize_host: pinned host inputs ->
+              H2D -> pipeline -> D2H of the int64 codes, all inside the timed region.
+  roofline    the dominant kernel (tcgen05 RVQ search): 2*R*K*D flops per launch / its CUDA-event duration,
+              against MEASURED_PEAKS.json bf16_tflops_sustained (fp16 and bf16 share the kind::f16 tensor pipe).
+  cpu_baseline the oracle (CPU restatement of the reference path) on a bounded sample, all host threads.
+--impl reference times that oracle alone (the reference package itself cannot be imported: 13 of its
+dependencies are not installed and there is no network).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "faces tokenized/sec (device-timed, max over ranks)"
+UNIT = "faces/s"
+
+WORKLOADS = {
+    "c1": dict(kind="tri", nx=0, ny=0, batch=2, cfg=dict(num_discrete_coors=128), desc="README: batch 2 x 64 random tri faces, 121 vertices, default (LFQ)"),
+    "c2": dict(kind="tri", nx=20, ny=20, batch=64, cfg=dict(use_residual_lfq=False), desc="batch 64 x 800 tri faces (20x20 grid, 441 vertices), ResidualVQ 16384x192 x2"),
+    "c3": dict(kind="quad", nx=20, ny=40, batch=64, cfg=dict(quads=True), desc="batch 64 x 800 quad faces (20x40 grid, 861 vertices), residual LFQ"),
+    "c4": dict(kind="tri", nx=20, ny=20, batch=256, cfg=dict(use_residual_lfq=False), desc="batch 256, faces U[100,800] padded with -1, ResidualVQ"),
+}
+
+
+def make_inputs(name, first_seed, batch):
+    from meshgpt_pytorch_b200 import synth
+    w = WORKLOADS[name]
+    if name == "c1":
+        return synth.readme_batch(first_seed, batch=batch)
+    if name == "c4":
+        g = torch.Generator().manual_seed(1234 + first_seed)
+        nf = torch.randint(100, 801, (batch,), generator=g).tolist()
+        return synth.ragged_batch(w["kind"], w["nx"], w["ny"], nf, range(first_seed, first_seed + batch))
+    return synth.grid_batch(w["kind"], w["nx"], w["ny"], range(first_seed, first_seed + batch))
+
+
+def valid_faces(faces):
+    return int((faces != -1).all(-1).sum())
+
+
+def build_models(name, want_cuda):
+    """Oracle (CPU) with torch.manual_seed(42) init + explicit codebook; CUDA model loaded from its state dict."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    cfg = WORKLOADS[name]["cfg"]
+    oracle = helpers.make_oracle(seed=42, **cfg)
+    model = None
+    if want_cuda:
+        import meshgpt_pytorch_b200 as M
+        model = M.MeshAutoencoder(**cfg)
+        model.load_reference_state_dict(oracle.state_dict())
+        model = model.cuda().eval()
+    return oracle, model
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        busy = sorted(s for s in sm if s >= 0.5 * max(sm)) or sorted(sm)
+        return dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_time_oracle(oracle, name, n_meshes, repeats, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    v, f = make_inputs(name, 0, n_meshes)
+    times = []
+    for i in range(warmup + repeats):
+        t0 = time.perf_counter()
+        oracle.tokenize(v, f)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return valid_faces(f), times
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    oracle, _ = build_models(args.workload, want_cuda=False)
+    n = args.cpu_meshes
+    faces, times = cpu_time_oracle(oracle, args.workload, n, args.steps, args.warmup)
+    ms = 1e3 * sum(times) / len(times)
+    val = faces / (ms / 1e3)
+    line = dict(impl="reference", metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=args.workload + ": " + WORKLOADS[args.workload]["desc"],
+                            note="CPU oracle (restated reference path); the reference package is not importable here"),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=os.cpu_count(), kind="port",
+                                  sample=f"{n} of the workload's meshes per step ({faces} faces), mean of {args.steps} steps"),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from meshgpt_pytorch_b200 import _lib
+    lib = _lib.lib
+    w = WORKLOADS[args.workload]
+    oracle, model = build_models(args.workload, want_cuda=True)
+    batch = w["batch"]
+    v_cpu, f_cpu = make_inputs(args.workload, rank * batch, batch)
+    n_faces_rank = valid_faces(f_cpu)
+    v_dev, f_dev = v_cpu.cuda(), f_cpu.cuda()
+    v_pin, f_pin = v_cpu.pin_memory(), f_cpu.pin_memory()
+    Q, K = model.num_quantizers, model.codebook_size
+    hist = torch.zeros(Q, K, dtype=torch.int64, device="cuda")
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    nsec = lib.meshtok_profile_sections()
+    sec_names = [lib.meshtok_profile_section_name(i).decode() for i in range(nsec)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    step_hist = torch.zeros_like(hist)
+
+    def device_step():
+        step_hist.zero_()
+        model.forward(vertices=v_dev, faces=f_dev, return_codes=True, histogram=step_hist, check_status=False)
+        if world > 1:
+            dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
+        hist.add_(step_hist)
+
+    codes_pin = torch.empty((batch, f_cpu.shape[1] * f_cpu.shape[2], Q), dtype=torch.int64, pin_memory=True)
+
+    def host_step():
+        model.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
+
+    def timed(step_fn, steps, profile=False):
+        evs = []
+        if profile:
+            lib.meshtok_profile_enable(1)
+        barrier()
+        wall0 = time.perf_counter()
+        for _ in range(steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_fn()
+            b.record()
+            evs.append((a, b))
+        barrier()
+        wall = time.perf_counter() - wall0
+        sec_ms = (C.c_float * nsec)()
+        sec_n = (C.c_int32 * nsec)()
+        if profile:
+            lib.meshtok_profile_enable(0)
+            _lib.check(lib.meshtok_profile_collect(sec_ms, sec_n, nsec))
+        ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall, list(sec_ms), list(sec_n)
+
+    # warm-up (also sizes the workspace and the edge buffer)
+    for _ in range(args.warmup):
+        device_step()
+    model.check_last_status()
+    for _ in range(max(1, args.warmup // 2)):
+        host_step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = lib.meshtok_kernel_launch_count()
+    ms_dev, wall_dev, sec_ms, sec_n = timed(device_step, args.steps, profile=True)
+    launches = lib.meshtok_kernel_launch_count() - launches0
+    model.check_last_status()
+    ms_e2e, _, _, _ = timed(host_step, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    total_faces = torch.tensor([n_faces_rank], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_faces)
+    total_faces = int(total_faces.item())
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        t = model.taps()
+        R = t["n_vrows"]
+        D = model.dim_codebook
+        sec = {n: dict(ms_per_step=sec_ms[i] / args.steps, launches_per_step=sec_n[i] / args.steps) for i, n in enumerate(sec_names) if sec_n[i]}
+        roofline = None
+        if not model.use_residual_lfq and "rvq_search_tc" in sec:
+            per_launch_ms = sec_ms[sec_names.index("rvq_search_tc")] / max(1, sec_n[sec_names.index("rvq_search_tc")])
+            flops = 2.0 * R * K * D
+            achieved = flops / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks.get("bf16_tflops_sustained") or 1400.0
+            roofline = dict(kernel="rvq_tc_search_kernel", bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s",
+                            frac=achieved / peak, traffic=None, peak_source="measured" if peaks else "fallback",
+                            flops_per_launch=flops, ms_per_launch=per_launch_ms)
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            faces_s, times = cpu_time_oracle(oracle, args.workload, args.cpu_meshes, repeats=2, warmup=1)
+            cpu = dict(value=faces_s / min(times), unit=UNIT, cores=os.cpu_count(), kind="port",
+                       sample=f"oracle on {args.cpu_meshes} of the workload's {batch} meshes ({faces_s} faces), best of 2 after 1 warm-up")
+        h2d = v_pin.numel() * v_pin.element_size() + f_pin.numel() * f_pin.element_size()
+        d2h = codes_pin.numel() * codes_pin.element_size()
+        line = dict(metric=METRIC, value=total_faces / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms_dev, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32 activations (split-bf16 tcgen05 linears), f16 tcgen05 RVQ screening + f32 re-score",
+                    data="synthetic",
+                    config=dict(workload=args.workload + ": " + w["desc"], meshes_per_rank=batch, faces_per_step=total_faces,
+                                quantizer_rows_per_rank=R, l2="flushed between steps (512 MiB memset outside the timed events)",
+                                sharding="meshes by rank, weights replicated; NCCL all-reduce of the (Q,K) int64 histogram per step",
+                                wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps),
+                    e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
+                             ms_per_step=ms_e2e),
+                    gpu_launches=int(launches), sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads, exports every symbol include/meshtok.h declares, and its host-side argument
+checks answer without a GPU (no compute is launched here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from helpers import ROOT
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "meshtok.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(meshtok_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from meshgpt_pytorch_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 20
+    raw = C.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(raw, n), f"{n} declared in include/meshtok.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert _lib.lib.meshtok_version() == _lib.ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    from meshgpt_pytorch_b200 import _lib
+    # meshtok_sage_layer: 2 x int32 + 6 pointers; meshtok_model embeds 8 of them
+    assert C.sizeof(_lib.SageLayer) == 8 + 6 * 8
+    assert _lib.Model.sage.size == 8 * C.sizeof(_lib.SageLayer)
+    assert C.sizeof(_lib.TokenizeArgs) == 4 * 8 + 4 * 4 + 2 * 8 + 5 * 8 + 3 * 4 + 4
+    assert C.sizeof(_lib.Taps) == (7 + 8 + 2) * 8
+
+
+def test_host_side_argument_checks():
+    from meshgpt_pytorch_b200 import _lib
+    lib = _lib.lib
+    n = C.c_size_t()
+    assert lib.meshtok_topology_workspace_bytes(64, 800, 3, 441, 0, C.byref(n)) == 0 and n.value > 64 * 800 * 4
+    assert lib.meshtok_topology_workspace_bytes(2, 10, 5, 10, 0, C.byref(n)) == -1          # nvf must be 3 or 4
+    assert b"nvf" in lib.meshtok_last_error_string()
+    assert lib.meshtok_topology_workspace_bytes(1, 200000, 3, 100000, 0, C.byref(n)) == -2  # too large for one SM
+    assert lib.meshtok_linear_image_bytes(576, 512, C.byref(n)) == 0 and n.value == 576 * 512 * 4
+    assert lib.meshtok_linear_image_bytes(100, 30, C.byref(n)) == -2
+    assert lib.meshtok_rvq_codebook_image_bytes(16384, 192, C.byref(n)) == 0 and n.value == 16384 * 192 * 2
+    assert lib.meshtok_profile_sections() >= 10
+    assert lib.meshtok_profile_section_name(0) == b"topology"
+    m = _lib.Model()
+    assert lib.meshtok_tokenize_workspace_bytes(C.byref(m), 1, 1, 1, 0, 16, C.byref(n)) == -1  # abi_version 0
+    with pytest.raises(_lib.MeshtokError):
+        _lib.check(-1)

@@ -1,0 +1,107 @@
+"""CPU: host-side mirror of the reference interface - constructor contract, state-dict compatibility,
+synthetic inputs, sharding helpers, the no-CPU-fallback rule."""
+import pytest
+import torch
+
+import meshgpt_pytorch_b200 as M
+from helpers import SMALL_CFG, make_oracle
+from meshgpt_pytorch_b200 import sharding, synth
+from oracle import meshtok_oracle as O
+
+REFERENCE_KEYS_TRI_LFQ = {
+    "coor_embed.weight": (128, 64), "angle_embed.weight": (128, 16), "area_embed.weight": (128, 16),
+    "normal_embed.weight": (128, 64), "project_in.weight": (192, 832), "project_in.bias": (192,),
+    "init_sage_conv.lin.weight": (192, 192), "init_sage_conv.lin.bias": (192,), "init_sage_conv.lin_l.weight": (64, 192),
+    "init_sage_conv.lin_l.bias": (64,), "init_sage_conv.lin_r.weight": (64, 192),
+    "init_encoder_act_and_norm.1.weight": (64,), "init_encoder_act_and_norm.1.bias": (64,),
+    "encoders.0.lin_l.weight": (128, 64), "encoders.3.lin_l.weight": (576, 256), "encoders.3.lin_r.weight": (576, 256),
+    "project_dim_codebook.weight": (576, 576), "project_dim_codebook.bias": (576,),
+    "quantizer.project_in.weight": (14, 192), "quantizer.project_in.bias": (14,),
+    "quantizer.project_out.weight": (192, 14), "quantizer.project_out.bias": (192,),
+}
+
+
+def test_default_constructor_matches_reference_key_layout():
+    m = M.MeshAutoencoder(num_discrete_coors=128)            # README example: default => ResidualLFQ, triangles
+    sd = m.state_dict()
+    for k, shape in REFERENCE_KEYS_TRI_LFQ.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert "init_sage_conv.lin_r.bias" not in sd
+    q = M.MeshAutoencoder(quads=True)
+    assert q.project_in.weight.shape == (192, 1040) and q.project_dim_codebook.weight.shape == (768, 576)
+    r = M.MeshAutoencoder(use_residual_lfq=False)
+    sd = r.state_dict()
+    assert tuple(sd["quantizer.layers.0._codebook.embed"].shape) == (1, 16384, 192)
+    assert sd["quantizer.layers.1._codebook.embed"].data_ptr() == sd["quantizer.layers.0._codebook.embed"].data_ptr()
+    assert bool(sd["quantizer.layers.0._codebook.initted"])
+
+
+def test_state_dict_round_trip_with_oracle_and_extra_decoder_keys():
+    o = make_oracle(**SMALL_CFG)
+    m = M.MeshAutoencoder(**SMALL_CFG)
+    sd = dict(o.state_dict())
+    sd["decoders.0.block1.proj.weight"] = torch.zeros(3)       # a decoder key of a real checkpoint
+    ignored = m.load_reference_state_dict(sd)
+    assert ignored == ["decoders.0.block1.proj.weight"]
+    for k, v in o.state_dict().items():
+        assert torch.equal(m.state_dict()[k], v), k
+    del sd["project_in.bias"]
+    with pytest.raises(KeyError):
+        m.load_reference_state_dict(sd)
+
+
+def test_unsupported_configurations_are_refused():
+    with pytest.raises(NotImplementedError):
+        M.MeshAutoencoder(attn_encoder_depth=1)
+    with pytest.raises(NotImplementedError):
+        M.MeshAutoencoder(sageconv_kwargs=dict(normalize=False, project=True))
+    m = M.MeshAutoencoder(**SMALL_CFG)
+    v, f = synth.readme_batch()
+    with pytest.raises(NotImplementedError):
+        m.forward(vertices=v, faces=f)                         # training branch is out of scope
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.tokenize(v, f)                                       # CPU tensors / CPU module: no fallback
+    with pytest.raises(RuntimeError, match="CUDA"):
+        M.derive_face_edges_from_faces(f)
+    with pytest.raises(AssertionError):
+        m.tokenize(v, f, return_codes=True)                    # meshgpt_pytorch.py:951
+
+
+def test_product_never_imports_the_oracle():
+    import os
+    import re
+    root = os.path.dirname(M.__file__)
+    for dirpath, _, files in os.walk(root):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+
+
+def test_synthetic_meshes():
+    v, f = synth.grid_mesh("tri", 20, 20, 3)
+    assert v.shape == (441, 3) and f.shape == (800, 3) and float(v.abs().max()) < 1 and int(f.max()) == 440
+    v, f = synth.grid_mesh("quad", 20, 40, 3)
+    assert v.shape == (861, 3) and f.shape == (800, 4)
+    v1, _ = synth.grid_mesh("tri", 4, 4, 11)
+    v2, _ = synth.grid_mesh("tri", 4, 4, 11)
+    assert torch.equal(v1, v2)
+    vs, fs = synth.ragged_batch("tri", 20, 20, [100, 800, 333], [0, 1, 2])
+    assert fs.shape == (3, 800, 3) and (fs[0, 100:] == -1).all() and (fs[2, 333:] == -1).all() and (fs[1] >= 0).all()
+    assert vs.shape[1] == 441 and (vs[0, int(fs[0].max()) + 1:] == -1).all()
+
+
+def test_shard_ranges_and_balancing():
+    assert [sharding.shard_range(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert sharding.shard_range(3, 3, 4) == (3, 3)
+    counts = [800, 100, 100, 100, 700, 200, 300, 500]
+    cuts = sharding.balanced_contiguous_shards(counts, 3)
+    assert cuts[0][0] == 0 and cuts[-1][1] == len(counts) and all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+    loads = [sum(counts[a:b]) for a, b in cuts]
+    assert max(loads) <= 1.35 * sum(counts) / 3
+
+
+def test_histogram_definition():
+    codes = torch.tensor([[[3, 1], [3, 0], [-1, -1]], [[2, 1], [-1, -1], [-1, -1]]])
+    h = O.codebook_usage_histogram(codes, 2, 4)
+    assert h.tolist() == [[0, 0, 1, 2], [1, 2, 0, 0]]
