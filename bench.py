@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -196,7 +197,7 @@ def main():
 
     def device_step():
         step_hist.zero_()
-        model.forward(vertices=v_dev, faces=f_dev, return_codes=True, histogram=step_hist, check_status=False)
+        model.forward(vertices=v_dev, faces=f_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
         if world > 1:
             dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
         hist.add_(step_hist)
@@ -286,7 +287,8 @@ def main():
                     config=dict(workload=args.workload + ": " + w["desc"], meshes_per_rank=batch, faces_per_step=total_faces,
                                 quantizer_rows_per_rank=R, l2="flushed between steps (512 MiB memset outside the timed events)",
                                 sharding="meshes by rank, weights replicated; NCCL all-reduce of the (Q,K) int64 histogram per step",
-                                wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps),
+                                wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps,
+                                rvq_rows_rechecked_by_exact_scan=t.get("rvq_exact_rechecks")),
                     e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                              ms_per_step=ms_e2e),
                     gpu_launches=int(launches), sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)

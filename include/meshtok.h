@@ -190,6 +190,7 @@ typedef struct meshtok_taps {
   int64_t layer_out[MESHTOK_MAX_SAGE_LAYERS]; /* fp32 (B*F, dim_out): output of each SAGE layer (layer 0: after act+norm) */
   int64_t averaged;        /* fp32 (B*V, dim_codebook): scatter-mean rows (vert_row order) */
   int64_t vertex_codes;    /* int32 (B*V, Q) */
+  int64_t rvq_stats;       /* int32[4]: [1] = rows re-checked by the exact scan (summed over levels) in the last call */
 } meshtok_taps;
 
 int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
@@ -220,12 +221,17 @@ int meshtok_rvq_build_codebook_image(const float* codebook, int codebook_size, i
 
 /* Dense linear C = act(A W^T + b).  Replaces torch.nn.functional.linear at meshgpt_pytorch.py:741, 803 and
  * inside SAGEConv.  A (M, K) fp32; W (N, K) fp32; C (M, N) fp32.  relu: 0/1.
- * simt != 0: fp32 SIMT kernel reading W.  simt == 0: tcgen05 split-bf16 kernel reading w_image, the
- * (N*K*4 byte) hi/lo bf16 UMMA image of W built once by meshtok_linear_build_image. */
+ * simt != 0: fp32 SIMT kernel reading A and W.
+ * simt == 0: tcgen05 split-bf16 kernel reading two operand images: w_image, the (N*K*4 byte) hi/lo bf16 UMMA
+ * image of W built once by meshtok_linear_build_image, and a_image, the hi/lo bf16 image of the activation rows
+ * (inside the pipeline every producer kernel writes its output in this form; for a stand-alone call build it
+ * with meshtok_rows_build_image). */
 int meshtok_linear_image_bytes(int N, int K, size_t* bytes);
 int meshtok_linear_build_image(const float* W, int N, int K, void* image, meshtok_stream_t stream);
-int meshtok_linear(const float* A, const float* W, const void* w_image, const float* bias, float* C, int M, int N,
-                   int K, int relu, int simt, meshtok_stream_t stream);
+int meshtok_rows_image_bytes(int M, int K, size_t* bytes);
+int meshtok_rows_build_image(const float* A, int M, int K, void* image, meshtok_stream_t stream);
+int meshtok_linear(const float* A, const void* a_image, const float* W, const void* w_image, const float* bias,
+                   float* C, int M, int N, int K, int relu, int simt, meshtok_stream_t stream);
 
 #ifdef __cplusplus
 }

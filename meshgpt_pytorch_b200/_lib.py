@@ -58,6 +58,7 @@ class Taps(C.Structure):
         ("status", C.c_int64), ("counts", C.c_int64), ("face_row", C.c_int64), ("vert_row", C.c_int64),
         ("indptr", C.c_int64), ("src", C.c_int64), ("x0", C.c_int64),
         ("layer_out", C.c_int64 * MAX_SAGE_LAYERS), ("averaged", C.c_int64), ("vertex_codes", C.c_int64),
+        ("rvq_stats", C.c_int64),
     ]
 
 
@@ -87,8 +88,10 @@ SIGNATURES = {
     "meshtok_rvq_build_codebook_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
     "meshtok_linear_image_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "meshtok_linear_build_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
-    "meshtok_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                                 C.c_int, C.c_int, C.c_void_p]),
+    "meshtok_rows_image_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "meshtok_rows_build_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "meshtok_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 

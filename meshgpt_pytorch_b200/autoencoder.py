@@ -398,7 +398,8 @@ class MeshAutoencoder(nn.Module):
                    src=view(t.src, min(ne, cap), torch.int32),
                    x0=view(t.x0, nf * D, torch.float32).view(nf, D),
                    averaged=view(t.averaged, nvr * D, torch.float32).view(nvr, D),
-                   vertex_codes=view(t.vertex_codes, nvr * Q, torch.int32).view(nvr, Q))
+                   vertex_codes=view(t.vertex_codes, nvr * Q, torch.int32).view(nvr, Q),
+                   rvq_exact_rechecks=int(view(t.rvq_stats, 4, torch.int32)[1]))
         for i, d in enumerate(self.encoder_dims):
             res[f"layer{i}"] = view(t.layer_out[i], nf * d, torch.float32).view(nf, d)
         return res

@@ -43,6 +43,7 @@ struct Workspace {
   int *ecount, *cursor, *etmp;
   float* x0;
   float *xp, *agg;
+  uint8_t *img_x, *img_agg;   // split-bf16 activation images (tcgen05 linears); null when a width is not a multiple of 32
   float* layer_out[MESHTOK_MAX_SAGE_LAYERS];
   float* y;
   float* avg;
@@ -53,6 +54,7 @@ struct Workspace {
   float* zero_row;
   int32_t* vcodes;
   int32_t* best;
+  unsigned long long* packed;
   int* amb_list;
   int* amb_count;
   float4* partial;
@@ -116,9 +118,17 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   const int D = m->dim_codebook, Q = m->num_quantizers;
   int max_in = 0;
   for (int l = 0; l < m->num_sage_layers; ++l) max_in = max(max_in, m->sage[l].dim_in);
+  bool images = D % 32 == 0;
+  int max_w = D;
+  for (int l = 0; l < m->num_sage_layers; ++l) {
+    images = images && m->sage[l].dim_in % 32 == 0 && m->sage[l].dim_out % 32 == 0;
+    max_w = max(max_w, max(m->sage[l].dim_in, m->sage[l].dim_out));
+  }
   w->x0 = c.take<float>(BF * D, &t->x0);
   w->xp = c.take<float>(BF * max_in);
   w->agg = c.take<float>(BF * max_in);
+  w->img_x = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
+  w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
   w->avg = c.take<float>(BV * D, &t->averaged);
@@ -129,8 +139,9 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->zero_row = c.take<float>(D);
   w->vcodes = c.take<int32_t>(BV * Q, &t->vertex_codes);
   w->best = c.take<int32_t>(BV);
+  w->packed = c.take<unsigned long long>(BV);
   w->amb_list = c.take<int>(BV);
-  w->amb_count = c.take<int>(4);
+  w->amb_count = c.take<int>(4, &t->rvq_stats);
   w->partial = nullptr;
   if (!m->use_lfq) {
     RvqTcPlan plan;
@@ -156,22 +167,25 @@ __global__ void copy_rows_kernel(const float4* __restrict__ a, float4* __restric
     out[i] = a[i];
 }
 
-int linear(bool simt, const float* A1, int K1, const float* A2, int K2, const float* W, const void* w_img, const float* bias,
-           float* C, int N, const int* m_dev, int m_max, bool relu, cudaStream_t s) {
+// fp32 SIMT linear on fp32 rows, or the tcgen05 split-bf16 linear on activation images
+int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* A2, const void* A2_img, int K2, const float* W,
+           const void* w_img, const float* bias, float* C, int N, const int* m_dev, int m_max, bool relu, cudaStream_t s) {
   if (simt) return launch_linear_simt(A1, K1, A2, K2, W, bias, C, N, m_dev, m_max, relu, s);
   MT_CHECK_ARG(w_img != nullptr, "tcgen05 linear requested but the model carries no weight image (set gemm_simt or build images)");
-  return launch_linear_tc(A1, K1, A2, K2, w_img, bias, C, N, m_dev, m_max, relu, s);
+  MT_CHECK_ARG(A1_img != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
+  return launch_linear_tc(A1_img, K1, A2_img, K2, w_img, bias, C, N, m_dev, m_max, relu, s);
 }
 
 // One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the final residual in
 // `resid` and the codes in vcodes (R x Q).
 int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes, int32_t* best,
-            int* amb_list, int* amb_count, float4* partial, const int* n_dev, int max_rows, bool exact, cudaStream_t s) {
+            unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, const int* n_dev, int max_rows, bool exact, cudaStream_t s) {
   const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
   if (max_rows == 0) return MESHTOK_OK;
   int rc;
   { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, n_dev, max_rows, s); }
   if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
   RvqTcPlan plan;
   if (!exact) {
     MT_CHECK_ARG(m->codebook_f16_tiles != nullptr && m->codebook_image_scale > 0.f,
@@ -181,10 +195,10 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
   }
   for (int level = 0; level < Q; ++level) {
     if (exact) {
-      { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, best, s); }
+      { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, packed, best, s); }
       if (rc != MESHTOK_OK) return rc;
     } else {
-      MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
+      MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), s));  // [0] per level; [1] running total of the call
       { ProfScope ps(PROF_RVQ_SEARCH, s);
         rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
                                   n_dev, max_rows, plan, partial, s); }
@@ -194,7 +208,7 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
                                 m->codebook_image_scale, partial, plan.n_splits, n_dev, max_rows, best, amb_list, amb_count, s); }
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_EXACT, s);
-        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, best, s); }
+        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, best, s); }
       if (rc != MESHTOK_OK) return rc;
     }
     { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_update(resid, D, m->codebook, best, vcodes, Q, level, rscale, n_dev, max_rows, s); }
@@ -370,35 +384,41 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       fp.slot_off[s_i++] = off; off += m->num_discrete_area;
       for (int k = 0; k < 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_normals; }
     }
-    fp.x0 = w.x0; fp.face_coords_out = a->face_coords_out;
+    fp.x0 = w.x0; fp.x0_image = simt ? nullptr : w.img_x; fp.face_coords_out = a->face_coords_out;
     if (a->face_coords_out)
       MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)max_rows * nvf * 3, s));
     { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }
 
+    // tcgen05 path: every activation that feeds a linear also exists as a split-bf16 image (img_x: the layer input,
+    // img_agg: the aggregated neighbours), written by the kernel that produces it.
     const float* x = w.x0;
     for (int l = 0; l < L; ++l) {
       const meshtok_sage_layer& ly = m->sage[l];
       // xp = relu(lin(x))
-      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, ly.dim_in, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
-      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, w.agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x, ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
       // out = lin_l(agg) + lin_r(x)
-      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, ly.dim_in, x, ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, w.img_agg, ly.dim_in, x, w.img_x, ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
       { ProfScope ps(PROF_SAGE_NORM, s);
         if ((rc = launch_row_norm(w.layer_out[l], ly.dim_out, l == 0 ? m->ln_gamma : nullptr, l == 0 ? m->ln_beta : nullptr,
-                                  w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+                                  simt ? nullptr : w.img_x, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
       x = w.layer_out[l];
     }
     enc = x;
   } else {
     if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc;
     enc = w.layer_out[L - 1];
+    if (!simt && !a->stop_after_encode) {
+      MT_CHECK_ARG(w.img_x != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
+      if ((rc = launch_rows_to_image(enc, enc_dim(m), n_faces_dev, max_rows, w.img_x, s)) != MESHTOK_OK) return rc;
+    }
   }
   if (a->encoded_out)
     if ((rc = launch_unpack_rows(enc, w.face_row, max_rows, enc_dim(m), a->encoded_out, s)) != MESHTOK_OK) return rc;
   if (a->stop_after_encode) return MESHTOK_OK;
 
   // ---- quantize -------------------------------------------------------------------------------
-  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, enc_dim(m), nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, w.img_x, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
   { ProfScope ps(PROF_SCATTER_MEAN, s); if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, s)) != MESHTOK_OK) return rc; }
   const float* pad_row = nullptr;
   if (m->use_lfq) {
@@ -419,7 +439,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   } else {
     MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
-    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.best, w.amb_list, w.amb_count, w.partial, n_vrows_dev, max_vrows,
+    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.best, w.packed, w.amb_list, w.amb_count, w.partial, n_vrows_dev, max_vrows,
                       a->rvq_exact != 0, s)) != MESHTOK_OK) return rc;
     if (a->quantized_out) {
       const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
@@ -428,8 +448,10 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   }
   { ProfScope ps(PROF_GATHER_CODES, s);
-    if ((rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out,
-                                  reinterpret_cast<unsigned long long*>(a->histogram), m->codebook_size, s)) != MESHTOK_OK) return rc; }
+    if ((rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out, s)) != MESHTOK_OK) return rc;
+    if (a->histogram)
+      if ((rc = launch_histogram(w.vptr, w.vcodes, w.counts, max_vrows, Q, m->codebook_size,
+                                 reinterpret_cast<unsigned long long*>(a->histogram), s)) != MESHTOK_OK) return rc; }
   if (a->quantized_out)
     if ((rc = launch_gather_quantized(a->faces, w.face_row, w.vert_row, w.qrows, B, F, nvf, V, D, pad_row, a->quantized_out, s)) != MESHTOK_OK) return rc;
   return MESHTOK_OK;
@@ -457,6 +479,7 @@ int meshtok_rvq_workspace_bytes(const meshtok_model* m, int R, size_t* bytes) {
   c.take<float>((size_t)R * m->dim_codebook);
   c.take<float>(R);
   c.take<int32_t>(R);
+  c.take<unsigned long long>(R);
   c.take<int>(R);
   c.take<int>(4);
   c.take<int>(4);
@@ -479,6 +502,7 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   float* resid = c.take<float>((size_t)R * m->dim_codebook);
   float* rscale = c.take<float>(R);
   int32_t* best = c.take<int32_t>(R);
+  unsigned long long* packed = c.take<unsigned long long>(R);
   int* amb_list = c.take<int>(R);
   int* amb_count = c.take<int>(4);
   int* n_dev = c.take<int>(4);
@@ -490,7 +514,7 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
   MT_CHECK_LAUNCH();
-  rc = run_rvq(m, rows, resid, rscale, codes, best, amb_list, amb_count, partial, n_dev, R, exact != 0, s);
+  rc = run_rvq(m, rows, resid, rscale, codes, best, packed, amb_list, amb_count, partial, n_dev, R, exact != 0, s);
   if (rc != MESHTOK_OK) return rc;
   if (residual_out && R > 0)
     MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));
@@ -524,11 +548,23 @@ int meshtok_linear_build_image(const float* W, int N, int K, void* image, meshto
   return launch_linear_tc_build_image(W, N, K, image, static_cast<cudaStream_t>(stream));
 }
 
-int meshtok_linear(const float* A, const float* W, const void* w_image, const float* bias, float* C, int M, int N, int K,
-                   int relu, int simt, meshtok_stream_t stream) {
-  MT_CHECK_ARG(A && C && M >= 0 && N > 0 && K > 0, "bad arguments");
-  MT_CHECK_ARG(simt ? W != nullptr : w_image != nullptr, "W (simt) / w_image (tcgen05) is null");
-  return linear(simt != 0, A, K, nullptr, 0, W, w_image, bias, C, N, nullptr, M, relu != 0, static_cast<cudaStream_t>(stream));
+int meshtok_rows_image_bytes(int M, int K, size_t* bytes) {
+  MT_CHECK_ARG(bytes && M >= 0 && K > 0 && K % 32 == 0, "rows image: K must be a positive multiple of 32");
+  *bytes = rows_image_bytes(M, K);
+  return MESHTOK_OK;
+}
+
+int meshtok_rows_build_image(const float* A, int M, int K, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(A && image && M >= 0, "A / image is null");
+  return launch_rows_to_image(A, K, nullptr, M, image, static_cast<cudaStream_t>(stream));
+}
+
+int meshtok_linear(const float* A, const void* a_image, const float* W, const void* w_image, const float* bias, float* C, int M,
+                   int N, int K, int relu, int simt, meshtok_stream_t stream) {
+  MT_CHECK_ARG(C && M >= 0 && N > 0 && K > 0, "bad arguments");
+  MT_CHECK_ARG(simt ? (A != nullptr && W != nullptr) : (a_image != nullptr && w_image != nullptr),
+               "A, W (simt) / a_image, w_image (tcgen05) is null");
+  return linear(simt != 0, A, a_image, K, nullptr, nullptr, 0, W, w_image, bias, C, N, nullptr, M, relu != 0, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -10,6 +10,7 @@
 // reference's separate fp32 ops ((t-lo)/(hi-lo), *n, -0.5, round-half-even; meshgpt_pytorch.py:197-201).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace meshtok {
 
@@ -107,7 +108,8 @@ __global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
         acc.x += t.x;
         acc.y += t.y;
       }
-      *reinterpret_cast<float2*>(p.x0 + (size_t)row * D + c0) = acc;
+      if (p.x0) *reinterpret_cast<float2*>(p.x0 + (size_t)row * D + c0) = acc;
+      if (p.x0_image) tc::image_store2(p.x0_image, D, row, c0, acc.x, acc.y);
     }
   }
 }

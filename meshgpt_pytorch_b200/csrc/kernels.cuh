@@ -16,18 +16,21 @@ struct FeatParams {
   const float* tables;      // (sum bins, D)
   const float* bias;        // (D)
   int slot_off[20];
-  float* x0;                // (rows, D)
+  float* x0;                // (rows, D) fp32 or null
+  uint8_t* x0_image;        // split-bf16 activation image of x0 (tc_common.cuh) or null
   int64_t* face_coords_out; // (B,F,nvf*3) or null
 };
 int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
 
 // ---- K4 ------------------------------------------------------------------------------------------
 // agg[t] = mean over in-edges (s -> t) of x[s]; sum in ascending CSR order / max(count, 1).
+// agg (fp32 rows) and agg_image (split-bf16 activation image) are both optional outputs.
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity,
-                       float* agg, const Counts* counts, int max_rows, cudaStream_t stream);
+                       float* agg, void* agg_image, const Counts* counts, int max_rows, cudaStream_t stream);
 // in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).
-int launch_row_norm(float* x, int d, const float* gamma, const float* beta, const Counts* counts, int max_rows,
-                    cudaStream_t stream);
+// image_out (optional): the same rows as a split-bf16 activation image for the next tcgen05 linear.
+int launch_row_norm(float* x, int d, const float* gamma, const float* beta, void* image_out, const Counts* counts,
+                    int max_rows, cudaStream_t stream);
 
 // C[m, :] = act([A1 | A2][m, :] . W^T + bias), fp32 SIMT.  m < *m_dev (<= m_max).
 int launch_linear_simt(const float* A1, int K1, const float* A2, int K2, const float* W, const float* bias, float* C,
@@ -41,10 +44,12 @@ int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc,
 int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, int bits, int Q, const float* w_out,
                const float* b_out, int32_t* codes, float* quantized_out, const int* n_rows_dev, int max_rows,
                cudaStream_t stream);
-// codes_out[b, f*nvf+c, q] = vcodes[vert_row[b, faces[b,f,c]], q] (pad_id on padded faces) + histogram.
+// codes_out[b, f*nvf+c, q] = vcodes[vert_row[b, faces[b,f,c]], q] (pad_id on padded faces).
 int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
-                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, unsigned long long* hist,
-                        int K, cudaStream_t stream);
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream);
+// hist[q][code] += incidence count of every quantizer row (= non-pad output tokens carrying the code).
+int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* counts, int max_vrows, int Q, int K,
+                     unsigned long long* hist, cudaStream_t stream);
 // quantized_out[b, f, c*D:(c+1)*D] = qrows[vert_row[b, faces[b,f,c]]]; padded faces get the pad-vertex row,
 // which the reference leaves at zero for LFQ / at the (zero) input for RVQ.
 int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
@@ -58,8 +63,9 @@ int launch_pack_rows(const float* padded, const int* row_face, int d, float* pac
 // ---- K8a -----------------------------------------------------------------------------------------
 // exact fp32 nearest-code search: best[r] = argmin_j sqrt(max(|x|^2 + |e_j|^2 - 2 x.e_j, 0)), lowest index on ties.
 // row_list == null: rows 0..*n_rows_dev-1; else rows row_list[0..*n_list_dev-1].
+// packed: scratch of max(all row ids)+1 uint64 (distance bits << 32 | index, merged with atomicMin).
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
-                     const int* n_dev, int max_rows, int32_t* best, cudaStream_t stream);
+                     const int* n_dev, int max_rows, unsigned long long* packed, int32_t* best, cudaStream_t stream);
 // r <- r - e[idx]; codes[r*Q + level] = idx; rscale[r] = power of two that brings max|r_d| into [0.5, 1).
 int launch_rvq_update(float* rows, int D, const float* codebook, const int32_t* best, int32_t* codes, int Q, int level,
                       float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
@@ -87,7 +93,10 @@ int launch_rvq_build_image(const float* codebook, int K, int D, float escale, vo
 int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT);
 size_t linear_tc_image_bytes(int N, int K);
 int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cudaStream_t stream);
-int launch_linear_tc(const float* A1, int K1, const float* A2, int K2, const void* w_image, const float* bias, float* C,
+// a1_image / a2_image: split-bf16 activation images (tc_common.cuh) written by the producing kernels
+int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                      int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream);
+size_t rows_image_bytes(long long rows, int K);
+int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream);
 
 }  // namespace meshtok

@@ -2,22 +2,24 @@
 //
 // Replaces the cuBLAS SGEMMs behind torch.nn.functional.linear in SAGEConv.lin / lin_l / lin_r
 // (torch_geometric, called at meshgpt_pytorch.py:764, :769) and project_dim_codebook (:803).
-//   C = act([A1 | A2] W^T + bias),  A fp32 (M, K1+K2), W fp32 (N, K)
+//   C = act([A1 | A2] W^T + bias),  A (M, K1+K2), W (N, K), C fp32 (M, N)
 // Every fp32 operand x is split as x = hi + lo with hi = bf16(x), lo = bf16(x - hi) and the product is
-// accumulated in fp32 (TMEM) as  hi.hi + hi.lo + lo.hi  (the lo.lo term, relative 2^-16, is dropped), i.e.
+// accumulated in fp32 (TMEM) as  lo.hi + hi.lo + hi.hi  (the lo.lo term, relative 2^-16, is dropped), i.e.
 // three bf16 UMMAs per K step: relative error ~1e-5 instead of bf16's 4e-3, at 3/8 of the cost of an
 // fp32-exact 3xTF32 scheme.
 //
-//   * W is split and re-tiled ONCE at load time into the canonical K-major UMMA image (per pass, per
-//     32-wide K chunk: hi block then lo block), so the producer thread streams it with one cp.async.bulk
-//     per stage;
-//   * A is read as fp32 rows, split and written to shared memory in the same canonical layout by eight
-//     loader warps (8 rows x 4 sixteen-byte chunks per warp step: coalesced 128 B reads, conflict-free
-//     512 B writes);
-//   * unit of work = (128-row tile, pass of NT <= 256 output columns); accumulators are double buffered in
-//     TMEM so the epilogue (TMEM -> +bias -> ReLU -> global) of one unit overlaps the MMAs of the next.
-// Warp roles (512 threads): w0 W producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-7 epilogue,
-// w8-15 A loaders.
+// Both operands arrive as ready-made shared-memory images (tc_common.cuh): W is split and tiled once at load
+// time, the activations are written in image form by the kernels that produce them (face_embed, gather_mean,
+// row_norm), so a pipeline stage = two cp.async.bulk copies issued by one thread - no register staging, no
+// per-chunk conversion in this kernel.  (A first version converted fp32 rows in eight loader warps; it ran at a
+// fifth of the MMA-bound time because the loader warps, not the tensor pipe, set the pace.)
+//   * unit of work = (128-row tile, pass of NT <= 256 output columns), K walked in 32-wide chunks through a
+//     4-stage ring (16 KB of A + up to 32 KB of W per stage);
+//   * accumulators are double buffered in TMEM so the epilogue of one unit overlaps the MMAs of the next;
+//   * epilogue: TMEM -> registers -> per-warp shared-memory transpose -> +bias -> ReLU -> fp32 stores
+//     (8 rows x 64 B per instruction).
+// Warp roles (384 threads): w0 producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue
+// (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -28,22 +30,25 @@ namespace {
 
 using namespace tc;
 
-constexpr int M_TILE = 128;
-constexpr int KC = 32;
+constexpr int M_TILE = IMG_ROWS;   // 128
+constexpr int KC = IMG_KC;         // 32
 constexpr int STAGES = 4;
 constexpr int NT_MAX = 256;
-constexpr int NUM_THREADS = 512;
-constexpr int LOADER_WARPS = 8;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
 constexpr uint32_t SBO = (KC / 8) * 128;                   // 512
-constexpr uint32_t A_PART = M_TILE * KC * 2;               // 8 KB (hi or lo)
+constexpr uint32_t A_PART = IMG_PART;                      // 8 KB (hi or lo)
 constexpr uint32_t W_PART_MAX = NT_MAX * KC * 2;           // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_PART + 2 * W_PART_MAX;  // 48 KB
 constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
-constexpr uint32_t SMEM_TOTAL = BAR_OFF + 256;
+constexpr int EPI_LD = 20;                                 // padded row length (floats) of the 32 x 16 epilogue staging tiles
+constexpr uint32_t EPI_OFF = BAR_OFF + 256;
+constexpr uint32_t SMEM_TOTAL = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;
+static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct LinArgs {
-  const float* A1;
-  const float* A2;
+  const uint8_t* a1_image;
+  const uint8_t* a2_image;
   int K1, K2;
   const uint8_t* w_image;
   const float* bias;
@@ -64,18 +69,10 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-__device__ __forceinline__ void split_bf16(float x, float y, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
-  const float2 hf = __bfloat1622float2(h);
-  const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
 __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* full = bars;               // [STAGES]  producer tx + 8 loader warps
+  uint64_t* full = bars;               // [STAGES]  producer (expect_tx of both copies)
   uint64_t* empty = bars + STAGES;     // [STAGES]  MMA commit
   uint64_t* acc_full = empty + STAGES; // [2]
   uint64_t* acc_empty = acc_full + 2;  // [2]
@@ -85,13 +82,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   const int M = a.m_dev ? min(*a.m_dev, a.m_max) : a.m_max;
   const int m_tiles = (M + M_TILE - 1) / M_TILE;
   const int units = m_tiles * a.passes;
-  const int K = a.K1 + a.K2;
-  const int kchunks = K / KC;
+  const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
+  const int kchunks = kch1 + kch2;
   const uint32_t w_part = (uint32_t)a.NT * KC * 2;
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1 + LOADER_WARPS); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -101,17 +98,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== W producer =====
+    // ===== producer: one A block (16 KB) + one W block (2 * NT * 64 B) per stage =====
     if (lane == 0) {
       uint32_t it = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int pass = u % a.passes;
-        const uint8_t* src = a.w_image + (size_t)pass * kchunks * (2 * w_part);
+        const int m_tile = u / a.passes, pass = u % a.passes;
+        const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part);
+        const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
+        const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
         for (int kc = 0; kc < kchunks; ++kc, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], 2 * w_part);
-          bulk_g2s(smem + s * STAGE_BYTES + 2 * A_PART, src + (size_t)kc * (2 * w_part), 2 * w_part, &full[s]);
+          mbar_arrive_expect_tx(&full[s], IMG_BLOCK + 2 * w_part);
+          uint8_t* stage = smem + s * STAGE_BYTES;
+          const uint8_t* asrc = kc < kch1 ? a1src + (size_t)kc * IMG_BLOCK : a2src + (size_t)(kc - kch1) * IMG_BLOCK;
+          bulk_g2s(stage, asrc, IMG_BLOCK, &full[s]);
+          bulk_g2s(stage + 2 * A_PART, wsrc + (size_t)kc * (2 * w_part), 2 * w_part, &full[s]);
         }
       }
     }
@@ -146,81 +148,54 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
         umma_commit(&acc_full[buf]);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4) {
     // ===== epilogue =====
+    const int ew = warp - 4;
     const int q = warp & 3;
+    const int chalf = ew >> 2;   // which half of the NT columns this warp stores
+    float* stage = reinterpret_cast<float*>(smem + EPI_OFF) + ew * (32 * EPI_LD);
     uint32_t acc_it = 0;
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
       const int m_tile = u / a.passes, pass = u % a.passes;
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tcgen05_fence_after();
-      const int row = m_tile * M_TILE + q * 32 + lane;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT_MAX;
       const int n0 = pass * a.NT;
-      float* crow = a.C + (size_t)row * a.N + n0;
-      const float* brow = a.bias ? a.bias + n0 : nullptr;
-      for (int c = 0; c < a.NT; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
+      const int row0 = m_tile * M_TILE + q * 32;
+      // columns [c_lo, c_hi) of this pass in blocks of 16 (NT is a multiple of 16); TMEM loads are double buffered
+      const int half_cols = ((a.NT / 2 + 15) / 16) * 16;
+      const int c_lo = chalf * half_cols, c_hi = chalf ? a.NT : min(a.NT, half_cols);
+      const int c4 = (lane & 3) * 4, rsub = lane >> 2;
+      uint32_t va[16], vb[16];
+      if (c_lo < c_hi) tmem_ld16(taddr + c_lo, va);
+      int parity = 0;
+      for (int c = c_lo; c < c_hi; c += 16, parity ^= 1) {
         tmem_ld_wait();
-        if (row < M) {
+        uint32_t(&v)[16] = parity ? vb : va;
+        if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, parity ? va : vb);
+        float* mine = stage + lane * EPI_LD;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            float4 o;
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-            if (brow) { const float4 bb = __ldg(reinterpret_cast<const float4*>(brow + c + j)); b0 = bb.x; b1 = bb.y; b2 = bb.z; b3 = bb.w; }
-            o.x = __uint_as_float(v[j]) + b0; o.y = __uint_as_float(v[j + 1]) + b1;
-            o.z = __uint_as_float(v[j + 2]) + b2; o.w = __uint_as_float(v[j + 3]) + b3;
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(mine + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + c4));
+#pragma unroll
+        for (int it2 = 0; it2 < 4; ++it2) {
+          const int r = it2 * 8 + rsub;
+          if (row0 + r < M) {
+            float4 o = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
+            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
             if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(crow + c + j) = o;
+            *reinterpret_cast<float4*>(a.C + (size_t)(row0 + r) * a.N + n0 + c + c4) = o;
           }
         }
+        __syncwarp();
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
-    }
-  } else if (warp >= 8) {
-    // ===== A loaders: fp32 -> (hi, lo) bf16, canonical layout =====
-    const int lw = warp - 8;
-    uint32_t it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int m_tile = u / a.passes;
-      for (int kc = 0; kc < kchunks; ++kc, ++it) {
-        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* sAh = smem + s * STAGE_BYTES;
-        uint8_t* sAl = sAh + A_PART;
-        const int k0 = kc * KC;
-        const float* base;
-        int ld, kk;
-        if (k0 < a.K1) { base = a.A1; ld = a.K1; kk = k0; }
-        else { base = a.A2; ld = a.K2; kk = k0 - a.K1; }
-#pragma unroll
-        for (int g = lw; g < M_TILE / 8; g += LOADER_WARPS) {
-          const int r = g * 8 + (lane & 7);
-          const int k8 = lane >> 3;
-          const long long grow = (long long)m_tile * M_TILE + r;
-          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-          if (grow < M) {
-            const float4* src = reinterpret_cast<const float4*>(base + (size_t)grow * ld + kk + k8 * 8);
-            v0 = src[0];
-            v1 = src[1];
-          }
-          uint4 hi, lo;
-          split_bf16(v0.x, v0.y, hi.x, lo.x);
-          split_bf16(v0.z, v0.w, hi.y, lo.y);
-          split_bf16(v1.x, v1.y, hi.z, lo.z);
-          split_bf16(v1.z, v1.w, hi.w, lo.w);
-          const uint32_t off = canon_offset(r, k8 * 8, SBO);
-          *reinterpret_cast<uint4*>(sAh + off) = hi;
-          *reinterpret_cast<uint4*>(sAl + off) = lo;
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full[s]);
-      }
     }
   }
 
@@ -243,10 +218,10 @@ __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restr
     const float4* src = reinterpret_cast<const float4*>(W + (size_t)n * K + k8 * 8);
     const float4 v0 = src[0], v1 = src[1];
     uint4 hi, lo;
-    split_bf16(v0.x, v0.y, hi.x, lo.x);
-    split_bf16(v0.z, v0.w, hi.y, lo.y);
-    split_bf16(v1.x, v1.y, hi.z, lo.z);
-    split_bf16(v1.z, v1.w, hi.w, lo.w);
+    split2(v0.x, v0.y, hi.x, lo.x);
+    split2(v0.z, v0.w, hi.y, lo.y);
+    split2(v1.x, v1.y, hi.z, lo.z);
+    split2(v1.z, v1.w, hi.w, lo.w);
     const int pass = n / NT, r = n % NT;
     const int kc = (k8 * 8) / KC, kin = (k8 * 8) % KC;
     const size_t base = ((size_t)pass * kchunks + kc) * (2 * (size_t)w_part);
@@ -256,10 +231,21 @@ __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restr
   }
 }
 
+// fp32 rows (M, K) -> activation image (used for tensors that do not come from an image-writing kernel)
+__global__ void __launch_bounds__(256) rows_to_image_kernel(const float* __restrict__ A, int K, const int* __restrict__ m_dev, int m_max,
+                                                            uint8_t* __restrict__ image) {
+  const int M = m_dev ? min(*m_dev, m_max) : m_max;
+  const long long total = (long long)M * (K / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (K / 4);
+    const int col = (int)(i % (K / 4)) * 4;
+    image_store4(image, K, row, col, *reinterpret_cast<const float4*>(A + (size_t)row * K + col));
+  }
+}
+
 }  // namespace
 
 int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT) {
-  const int K = K1 + K2;
   if (N <= 0 || K1 <= 0 || K1 % KC != 0 || K2 % KC != 0) {
     set_error("tcgen05 linear: input widths must be multiples of %d (got %d, %d); use the SIMT path", KC, K1, K2);
     return MESHTOK_ERR_UNSUPPORTED;
@@ -269,13 +255,14 @@ int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT) {
     set_error("tcgen05 linear: output width %d does not split into %d passes of a multiple of 16 columns; use the SIMT path", N, p);
     return MESHTOK_ERR_UNSUPPORTED;
   }
-  (void)K;
   *passes = p;
   *NT = N / p;
   return MESHTOK_OK;
 }
 
 size_t linear_tc_image_bytes(int N, int K) { return (size_t)N * K * 4; }
+
+size_t rows_image_bytes(long long rows, int K) { return tc::image_bytes(rows, K); }
 
 int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cudaStream_t stream) {
   int passes, NT;
@@ -289,12 +276,23 @@ int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cuda
   return MESHTOK_OK;
 }
 
-int launch_linear_tc(const float* A1, int K1, const float* A2, int K2, const void* w_image, const float* bias, float* C, int N,
-                     const int* m_dev, int m_max, bool relu, cudaStream_t stream) {
+int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream) {
+  MT_CHECK_ARG(K % KC == 0, "rows_to_image: width %d must be a multiple of %d", K, KC);
   if (m_max == 0) return MESHTOK_OK;
-  MT_CHECK_ARG(w_image != nullptr, "tcgen05 linear: weight image is null");
+  const long long want = ((long long)m_max * (K / 4) + 255) / 256;
+  const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
+  rows_to_image_kernel<<<blocks, 256, 0, stream>>>(A, K, m_dev, m_max, static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
+                     int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream) {
+  if (m_max == 0) return MESHTOK_OK;
+  MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
   LinArgs a;
-  a.A1 = A1; a.A2 = A2; a.K1 = K1; a.K2 = K2; a.w_image = static_cast<const uint8_t*>(w_image); a.bias = bias; a.C = C;
+  a.a1_image = static_cast<const uint8_t*>(a1_image); a.a2_image = static_cast<const uint8_t*>(a2_image);
+  a.K1 = K1; a.K2 = K2; a.w_image = static_cast<const uint8_t*>(w_image); a.bias = bias; a.C = C;
   a.N = N; a.m_dev = m_dev; a.m_max = m_max; a.relu = relu ? 1 : 0;
   int rc = linear_tc_plan(N, K1, K2, &a.passes, &a.NT);
   if (rc != MESHTOK_OK) return rc;

@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows
 __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
                                                            const int* __restrict__ vert_row, const int32_t* __restrict__ vcodes,
                                                            int BF, int F, int nvf, int V, int Q, int64_t pad_id,
-                                                           int64_t* __restrict__ codes_out, unsigned long long* __restrict__ hist,
-                                                           int K) {
+                                                           int64_t* __restrict__ codes_out) {
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= (long long)BF * nvf) return;
   const int pf = (int)(tok / nvf);
@@ -123,9 +122,20 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
   const long long v = faces[tok];
   const int vr = vert_row[(size_t)b * V + v];
   for (int q = 0; q < Q; ++q) {
-    const int c = vcodes[(size_t)vr * Q + q];
-    dst[q] = c;
-    if (hist != nullptr && c >= 0 && c < K) atomicAdd(hist + (size_t)q * K + c, 1ull);
+    dst[q] = vcodes[(size_t)vr * Q + q];
+  }
+}
+
+// hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex
+// (one weighted atomic per vertex row and level instead of one per token).
+__global__ void __launch_bounds__(256) histogram_kernel(const int* __restrict__ vptr, const int32_t* __restrict__ vcodes,
+                                                        const Counts* counts, int Q, int K, unsigned long long* __restrict__ hist) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= counts->n_vrows) return;
+  const unsigned long long w = (unsigned long long)(vptr[row + 1] - vptr[row]);
+  for (int q = 0; q < Q; ++q) {
+    const int c = vcodes[(size_t)row * Q + q];
+    if (c >= 0 && c < K) atomicAdd(hist + (size_t)q * K + c, w);
   }
 }
 
@@ -203,12 +213,19 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
 }
 
 int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
-                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, unsigned long long* hist,
-                        int K, cudaStream_t stream) {
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream) {
   const long long n = (long long)B * F * nvf;
   if (n == 0) return MESHTOK_OK;
   gather_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q,
-                                                                      pad_id, codes_out, hist, K);
+                                                                      pad_id, codes_out);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* counts, int max_vrows, int Q, int K,
+                     unsigned long long* hist, cudaStream_t stream) {
+  if (max_vrows == 0) return MESHTOK_OK;
+  histogram_kernel<<<ceil_div(max_vrows, 256), 256, 0, stream>>>(vptr, vcodes, counts, Q, K, hist);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

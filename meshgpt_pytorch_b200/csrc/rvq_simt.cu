@@ -15,9 +15,13 @@ namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16;
 
+// grid = (row blocks of 64, code splits): every CTA scans `codes_per_split` codes for its 64 rows and merges its
+// (distance, index) into packed[row] with a 64-bit atomicMin - distance bits in the high word (non-negative floats
+// order like unsigned ints), index in the low word, so equal distances resolve to the lowest index.
 __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
-                                                        const float* __restrict__ e2, int K, const int* __restrict__ row_list,
-                                                        const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ best) {
+                                                        const float* __restrict__ e2, int K, int codes_per_split,
+                                                        const int* __restrict__ row_list, const int* __restrict__ n_dev, int max_rows,
+                                                        unsigned long long* __restrict__ packed) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Es[BK][BN + 4];
   __shared__ float x2s[BM];
@@ -25,9 +29,9 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
   __shared__ float red_d[BM][17];
   __shared__ int red_i[BM][17];
   const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
-  const int m0 = blockIdx.x * BM;
-  if (m0 >= n) return;
   const int tid = threadIdx.x;
+  for (int m0 = blockIdx.x * BM; m0 < n; m0 += gridDim.x * BM) {   // row blocks (grid.x may be capped in list mode)
+  __syncthreads();
   const int tx = tid & 15, ty = tid >> 4;
   const int lr = tid >> 2, lk = (tid & 3) * 4;
 
@@ -39,8 +43,16 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
   {  // |x|^2, 4 threads per row
     const int r = rid[lr];
     float s = 0.f;
-    if (r >= 0)
-      for (int k = (tid & 3); k < D; k += 4) { const float v = rows[(size_t)r * D + k]; s = fmaf(v, v, s); }
+    if (r >= 0) {   // independent 16-byte loads (D is a multiple of 16), 4 threads interleaved over the row
+      const float4* xr = reinterpret_cast<const float4*>(rows + (size_t)r * D);
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+      for (int k4 = (tid & 3); k4 < D / 4; k4 += 4) {
+        const float4 v = xr[k4];
+        s4[0] = fmaf(v.x, v.x, s4[0]); s4[1] = fmaf(v.y, v.y, s4[1]); s4[2] = fmaf(v.z, v.z, s4[2]); s4[3] = fmaf(v.w, v.w, s4[3]);
+      }
+      s = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if ((tid & 3) == 0) x2s[lr] = s;
@@ -52,18 +64,28 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 4; ++i) { bd[i] = INFINITY; bi[i] = 0x7fffffff; }
 
-  for (int n0 = 0; n0 < K; n0 += BN) {
+  const int c_begin = blockIdx.y * codes_per_split;
+  const int c_end = min(K, c_begin + codes_per_split);
+  for (int n0 = c_begin; n0 < c_end; n0 += BN) {
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    // software pipelined: the slice k0+BK is in flight (registers) while slice k0 is multiplied
+    const int r_ld = rid[lr];
+    const bool a_ok = r_ld >= 0, e_ok = n0 + lr < c_end;
+    const float4* a_src = reinterpret_cast<const float4*>(rows + (size_t)(a_ok ? r_ld : 0) * D + lk);
+    const float4* e_src = reinterpret_cast<const float4*>(cb + (size_t)(e_ok ? n0 + lr : 0) * D + lk);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 av_next = a_ok ? a_src[0] : zero4;
+    float4 ev_next = e_ok ? __ldg(e_src) : zero4;
     for (int k0 = 0; k0 < D; k0 += BK) {
-      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r = rid[lr];
-      if (r >= 0) av = *reinterpret_cast<const float4*>(rows + (size_t)r * D + k0 + lk);
-      float4 ev = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (n0 + lr < K) ev = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(n0 + lr) * D + k0 + lk));
+      const float4 av = av_next, ev = ev_next;
+      if (k0 + BK < D) {
+        av_next = a_ok ? a_src[(k0 + BK) / 4] : zero4;
+        ev_next = e_ok ? __ldg(e_src + (k0 + BK) / 4) : zero4;
+      }
       As[lk + 0][lr] = av.x; As[lk + 1][lr] = av.y; As[lk + 2][lr] = av.z; As[lk + 3][lr] = av.w;
       Es[lk + 0][lr] = ev.x; Es[lk + 1][lr] = ev.y; Es[lk + 2][lr] = ev.z; Es[lk + 3][lr] = ev.w;
       __syncthreads();
@@ -83,7 +105,7 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int code = n0 + tx * 4 + j;
-      if (code >= K) continue;
+      if (code >= c_end) continue;
       const float y2 = __ldg(e2 + code);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -104,7 +126,26 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
       const int it = red_i[tid][t];
       if (dt < d || (dt == d && it < ix)) { d = dt; ix = it; }
     }
-    best[rid[tid]] = ix;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)ix;
+    atomicMin(packed + rid[tid], key);
+  }
+  }
+}
+
+__global__ void rvq_exact_init_kernel(const int* __restrict__ row_list, const int* __restrict__ n_dev, int max_rows,
+                                      unsigned long long* __restrict__ packed) {
+  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) packed[row_list ? row_list[i] : i] = ~0ull;
+}
+
+__global__ void rvq_exact_finish_kernel(const int* __restrict__ row_list, const int* __restrict__ n_dev, int max_rows,
+                                        const unsigned long long* __restrict__ packed, int32_t* __restrict__ best) {
+  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const int row = row_list ? row_list[i] : i;
+    best[row] = (int32_t)(packed[row] & 0xffffffffull);
   }
 }
 
@@ -150,10 +191,22 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
 }  // namespace
 
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
-                     const int* n_dev, int max_rows, int32_t* best, cudaStream_t stream) {
+                     const int* n_dev, int max_rows, unsigned long long* packed, int32_t* best, cudaStream_t stream) {
   MT_CHECK_ARG(D % BK == 0, "rvq: dim %d must be a multiple of %d", D, BK);
   if (max_rows == 0) return MESHTOK_OK;
-  rvq_exact_kernel<<<ceil_div(max_rows, BM), 256, 0, stream>>>(rows, D, codebook, e2, K, row_list, n_dev, max_rows, best);
+  // few rows (the re-check of ambiguous rows): many code splits so the sweep is short; all rows: fewer, larger splits
+  // list mode: the number of rows is a device-side count that is small in practice; cap the grid and loop
+  const int row_blocks = row_list ? min(ceil_div(max_rows, BM), 16) : ceil_div(max_rows, BM);
+  int splits = row_list ? 1024 : 8;   // list mode is latency bound: one 64-code tile per CTA
+  while (splits > 1 && K / splits < BN) splits >>= 1;
+  const int codes_per_split = ceil_div(ceil_div(K, splits), BN) * BN;
+  splits = ceil_div(K, codes_per_split);
+  rvq_exact_init_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed);
+  MT_CHECK_LAUNCH();
+  rvq_exact_kernel<<<dim3(row_blocks, splits), 256, 0, stream>>>(rows, D, codebook, e2, K, codes_per_split, row_list, n_dev,
+                                                               max_rows, packed);
+  MT_CHECK_LAUNCH();
+  rvq_exact_finish_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed, best);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

@@ -16,8 +16,10 @@
 //     (128 codes x 64 dims) filled by cp.async.bulk from a pre-tiled fp16 image of the codebook;
 //   * accumulators are double buffered in TMEM (2 buffers x 2 halves x 128 columns = all 512 columns) so
 //     the epilogue of tile t overlaps the MMAs of tile t+1;
-//   * epilogue warps (one TMEM lane = one row per thread) keep the two smallest s~ and their indices.
-// The exact fp32 decision is taken by rvq_rescore_kernel on the screened candidates, with the
+//   * epilogue warps (one TMEM lane = one row per thread) reduce every 8-code chunk to its minimum s~ (one FFMA
+//     and one FMNMX per value - the epilogue, not the MMA, was the limiter with per-code bookkeeping) and keep the
+//     two best chunks per (row, split).
+// The exact fp32 decision is taken by rvq_rescore_kernel on every code of the screened chunks, with the
 // reference's own formula; rows whose candidate list might be incomplete go to the exact fp32 scan.
 //
 // Warp roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
@@ -38,6 +40,7 @@ constexpr int N_TILE = 128;        // codes per accumulator tile (UMMA N)
 constexpr int KC = 64;             // K elements per pipeline stage
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = N_TILE * KC * 2;   // 16 KB
+constexpr int CHUNK = 8;                       // screening granularity: codes per candidate chunk
 constexpr int MAX_SPLIT_CODES = 4096;          // e2 slice kept in shared memory per unit
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
@@ -62,7 +65,7 @@ struct SearchArgs {
   float escale;            // power-of-two codebook scale baked into the image
   const int* n_rows_dev;
   int max_rows, K, n_splits, tiles_per_split;
-  float4* partial;         // (R, n_splits): {best, idx_best, second, idx_second}
+  float4* partial;         // (R, n_splits): {best chunk minimum, its chunk id, second best, its chunk id}
 };
 
 template <int D>
@@ -219,25 +222,31 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
         mbar_wait(&acc_full[buf], aph);
         tcgen05_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (buf * 2 + h) * N_TILE;
-        const int code0 = (tile0 + t) * N_TILE;
+        const int chunk0 = (tile0 + t) * (N_TILE / CHUNK);
         const float* e2t = sE2 + t * N_TILE;
-#pragma unroll 1
+        // Per CHUNK (8) codes only the MINIMUM screened score is kept (one FFMA + one FMNMX per value, one
+        // compare + rarely-taken branch per chunk); the re-score kernel evaluates every code of the winning
+        // chunks exactly.  TMEM loads are double buffered: 32 columns are in flight while 32 are reduced.
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+#pragma unroll
         for (int c = 0; c < N_TILE / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c * 32, v);
           tmem_ld_wait();
+          uint32_t(&v)[32] = (c & 1) ? vb : va;
+          if (c + 1 < N_TILE / 32) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 e = *reinterpret_cast<const float4*>(e2t + c * 32 + j);
-            const float ev[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-              const float s = fmaf(__uint_as_float(v[j + jj]), cmul, ev[jj]);
-              if (s < b2) {
-                const int idx = code0 + c * 32 + j + jj;
-                if (s < b1) { b2 = b1; i2 = i1; b1 = s; i1 = idx; }
-                else { b2 = s; i2 = idx; }
-              }
+          for (int j = 0; j < 32; j += CHUNK) {
+            const float4 e0 = *reinterpret_cast<const float4*>(e2t + c * 32 + j);
+            const float4 e1 = *reinterpret_cast<const float4*>(e2t + c * 32 + j + 4);
+            const float m0 = fminf(fminf(fmaf(__uint_as_float(v[j + 0]), cmul, e0.x), fmaf(__uint_as_float(v[j + 1]), cmul, e0.y)),
+                                   fminf(fmaf(__uint_as_float(v[j + 2]), cmul, e0.z), fmaf(__uint_as_float(v[j + 3]), cmul, e0.w)));
+            const float m1 = fminf(fminf(fmaf(__uint_as_float(v[j + 4]), cmul, e1.x), fmaf(__uint_as_float(v[j + 5]), cmul, e1.y)),
+                                   fminf(fmaf(__uint_as_float(v[j + 6]), cmul, e1.z), fmaf(__uint_as_float(v[j + 7]), cmul, e1.w)));
+            const float m = fminf(m0, m1);
+            if (m < b2) {
+              const int idx = chunk0 + (c * 32 + j) / CHUNK;
+              if (m < b1) { b2 = b1; i2 = i1; b1 = m; i1 = idx; }
+              else { b2 = m; i2 = idx; }
             }
           }
         }
@@ -299,24 +308,38 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
     int bi = 0x7fffffff;
     for (int s = 0; s < n_splits; ++s) {
       const float4 p = partial[(size_t)row * n_splits + s];
-      if (p.z <= window) ambiguous = true;
-      if (p.x <= window) {
-        const int code = __float_as_int(p.y);
-        float dot = 0.f;
+      if (p.z <= window) ambiguous = true;   // both kept chunks are inside the window: a third may hide behind them
+#pragma unroll 1
+      for (int which = 0; which < 2; ++which) {
+        const float sc = which ? p.z : p.x;
+        if (!(sc <= window)) continue;
+        const int code0 = __float_as_int(which ? p.w : p.y) * CHUNK;
+        // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
+        float d[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) d[j] = 0.f;
 #pragma unroll
         for (int i = 0; i < PER; ++i) {
           const int c = lane + 32 * i;
-          if (c < D) dot = fmaf(x[i], __ldg(cb + (size_t)code * D + c), dot);
+          if (c < D) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) d[j] = fmaf(x[i], __ldg(cb + (size_t)(code0 + j) * D + c), d[j]);
+          }
         }
-        dot = warp_sum(dot);
-        const float d2 = __fadd_rn(__fadd_rn(x2, __ldg(e2 + code)), __fmul_rn(dot, -2.f));
-        const float dist = sqrtf(fmaxf(d2, 0.f));
-        if (dist < bd || (dist == bd && code < bi)) { bd = dist; bi = code; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) {
+          const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, __ldg(e2 + code0 + j)), __fmul_rn(d[j], -2.f)), 0.f));
+          if (q < bd || (q == bd && code0 + j < bi)) { bd = q; bi = code0 + j; }
+        }
       }
     }
     if (lane == 0) {
       best[row] = bi;
-      if (ambiguous) amb_list[atomicAdd(amb_count, 1)] = row;
+      if (ambiguous) { amb_list[atomicAdd(amb_count, 1)] = row; atomicAdd(amb_count + 1, 1); }
     }
   }
 }

@@ -8,6 +8,7 @@
 // deterministic (the reference's GPU path uses atomics and is not).
 #include "common.cuh"
 #include "kernels.cuh"
+#include "tc_common.cuh"
 
 namespace meshtok {
 
@@ -16,7 +17,8 @@ namespace {
 template <int CHUNKS>  // float4 chunks per lane (d = 128 * CHUNKS at most)
 __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                           const int* __restrict__ src, long long cap,
-                                                          float* __restrict__ agg, const Counts* counts) {
+                                                          float* __restrict__ agg, uint8_t* __restrict__ agg_image,
+                                                          const Counts* counts) {
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n_rows = counts->n_faces;
@@ -41,66 +43,77 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
       }
     }
     const float cnt = fmaxf((float)(e_true - s), 1.f);
-    float4* out = reinterpret_cast<float4*>(agg + (size_t)row * d);
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       const int i4 = lane + 32 * c;
-      if (i4 < d4)
-        out[i4] = make_float4(__fdiv_rn(acc[c].x, cnt), __fdiv_rn(acc[c].y, cnt), __fdiv_rn(acc[c].z, cnt), __fdiv_rn(acc[c].w, cnt));
+      if (i4 < d4) {
+        const float4 o = make_float4(__fdiv_rn(acc[c].x, cnt), __fdiv_rn(acc[c].y, cnt), __fdiv_rn(acc[c].z, cnt), __fdiv_rn(acc[c].w, cnt));
+        if (agg) reinterpret_cast<float4*>(agg + (size_t)row * d)[i4] = o;
+        if (agg_image) tc::image_store4(agg_image, d, row, i4 * 4, o);
+      }
     }
   }
 }
 
-template <int PER>  // elements per lane (d <= 32 * PER)
+template <int PER2>  // float2 pairs per lane (d <= 64 * PER2, d even)
 __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, int d, const float* __restrict__ gamma,
-                                                       const float* __restrict__ beta, const Counts* counts) {
+                                                       const float* __restrict__ beta, uint8_t* __restrict__ image,
+                                                       const Counts* counts) {
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n_rows = counts->n_faces;
+  const int d2 = d >> 1;
   for (int row = blockIdx.x * wpb + warp_id(); row < n_rows; row += gridDim.x * wpb) {
-    float* xr = x + (size_t)row * d;
-    float v[PER];
+    float2* xr = reinterpret_cast<float2*>(x + (size_t)row * d);
+    float2 v[PER2];
     float ss = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
+    for (int i = 0; i < PER2; ++i) {
       const int c = lane + 32 * i;
-      v[i] = c < d ? xr[c] : 0.f;
-      ss += v[i] * v[i];
+      v[i] = c < d2 ? xr[c] : make_float2(0.f, 0.f);
+      ss += v[i].x * v[i].x + v[i].y * v[i].y;
     }
     ss = warp_sum(ss);
     const float den = fmaxf(sqrtf(ss), 1e-12f);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) v[i] = __fdiv_rn(v[i], den);
+    for (int i = 0; i < PER2; ++i) { v[i].x = __fdiv_rn(v[i].x, den); v[i].y = __fdiv_rn(v[i].y, den); }
     if (gamma != nullptr) {
       // SiLU then LayerNorm (biased variance, eps 1e-5)
       float mean = 0.f;
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
+      for (int i = 0; i < PER2; ++i) {
         const int c = lane + 32 * i;
-        const float t = v[i];
-        v[i] = c < d ? __fdiv_rn(t, 1.f + expf(-t)) : 0.f;
-        mean += v[i];
+        const float2 t = v[i];
+        v[i] = c < d2 ? make_float2(__fdiv_rn(t.x, 1.f + expf(-t.x)), __fdiv_rn(t.y, 1.f + expf(-t.y))) : make_float2(0.f, 0.f);
+        mean += v[i].x + v[i].y;
       }
       mean = warp_sum(mean) / (float)d;
       float var = 0.f;
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
+      for (int i = 0; i < PER2; ++i) {
         const int c = lane + 32 * i;
-        const float t = c < d ? v[i] - mean : 0.f;
-        var += t * t;
+        const float tx = c < d2 ? v[i].x - mean : 0.f, ty = c < d2 ? v[i].y - mean : 0.f;
+        var += tx * tx + ty * ty;
       }
       var = warp_sum(var) / (float)d;
       const float rstd = 1.f / sqrtf(var + 1e-5f);
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
+      for (int i = 0; i < PER2; ++i) {
         const int c = lane + 32 * i;
-        if (c < d) v[i] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        if (c < d2) {
+          const float2 g = *reinterpret_cast<const float2*>(gamma + 2 * c), b = *reinterpret_cast<const float2*>(beta + 2 * c);
+          v[i].x = (v[i].x - mean) * rstd * g.x + b.x;
+          v[i].y = (v[i].y - mean) * rstd * g.y + b.y;
+        }
       }
     }
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
+    for (int i = 0; i < PER2; ++i) {
       const int c = lane + 32 * i;
-      if (c < d) xr[c] = v[i];
+      if (c < d2) {
+        xr[c] = v[i];
+        if (image) tc::image_store2(image, d, row, 2 * c, v[i].x, v[i].y);
+      }
     }
   }
 }
@@ -108,11 +121,11 @@ __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, in
 }  // namespace
 
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity, float* agg,
-                       const Counts* counts, int max_rows, cudaStream_t stream) {
+                       void* agg_image, const Counts* counts, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int chunks = ceil_div(d / 4, 32);
-#define GM(C) gather_mean_kernel<C><<<blocks, 256, 0, stream>>>(x, d, indptr, src, edge_capacity, agg, counts)
+#define GM(C) gather_mean_kernel<C><<<blocks, 256, 0, stream>>>(x, d, indptr, src, edge_capacity, agg, static_cast<uint8_t*>(agg_image), counts)
   switch (chunks) {
     case 1: GM(1); break;
     case 2: GM(2); break;
@@ -125,17 +138,18 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   return MESHTOK_OK;
 }
 
-int launch_row_norm(float* x, int d, const float* gamma, const float* beta, const Counts* counts, int max_rows,
+int launch_row_norm(float* x, int d, const float* gamma, const float* beta, void* image_out, const Counts* counts, int max_rows,
                     cudaStream_t stream) {
-  MT_CHECK_ARG(d >= 1 && d <= 1024, "row_norm: feature width %d must be in [1, 1024]", d);
+  MT_CHECK_ARG(d >= 2 && d % 2 == 0 && d <= 1024, "row_norm: feature width %d must be even and in [2, 1024]", d);
+  MT_CHECK_ARG(image_out == nullptr || d % tc::IMG_KC == 0, "row_norm: image output needs a width that is a multiple of %d", tc::IMG_KC);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  const int per = ceil_div(d, 32);
-#define RN(P) row_norm_kernel<P><<<blocks, 256, 0, stream>>>(x, d, gamma, beta, counts)
-  if (per <= 2) RN(2);
-  else if (per <= 4) RN(4);
-  else if (per <= 8) RN(8);
-  else if (per <= 18) RN(18);
-  else RN(32);
+  const int per2 = ceil_div(d / 2, 32);
+#define RN(P) row_norm_kernel<P><<<blocks, 256, 0, stream>>>(x, d, gamma, beta, static_cast<uint8_t*>(image_out), counts)
+  if (per2 <= 1) RN(1);
+  else if (per2 <= 2) RN(2);
+  else if (per2 <= 4) RN(4);
+  else if (per2 <= 9) RN(9);
+  else RN(16);
 #undef RN
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;

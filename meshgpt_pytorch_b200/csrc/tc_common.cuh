@@ -133,3 +133,53 @@ __host__ __device__ constexpr uint32_t canon_offset(int r, int k, uint32_t sbo) 
 
 }  // namespace tc
 }  // namespace meshtok
+
+// ---- split-bf16 activation images ---------------------------------------------------------------------
+// An (rows x K) fp32 activation is kept in global memory as the exact byte image the tcgen05 linear kernel
+// wants in shared memory: for every (128-row tile, 32-column chunk) a 16 KB block = 8 KB of hi = bf16(x) followed
+// by 8 KB of lo = bf16(x - hi), each in the canonical K-major layout (8-row groups 512 B apart).  A GEMM stage is
+// then one contiguous cp.async.bulk.  Rows are padded to a multiple of 128 (pad rows are never stored by the GEMM).
+namespace meshtok {
+namespace tc {
+
+constexpr int IMG_ROWS = 128;
+constexpr int IMG_KC = 32;
+constexpr uint32_t IMG_PART = IMG_ROWS * IMG_KC * 2;   // 8 KB
+constexpr uint32_t IMG_BLOCK = 2 * IMG_PART;           // 16 KB
+
+__host__ __device__ inline size_t image_bytes(long long rows, int K) {
+  return (size_t)((rows + IMG_ROWS - 1) / IMG_ROWS) * (size_t)(K / IMG_KC) * IMG_BLOCK;
+}
+// byte offset of the hi element (row, col); the lo element is IMG_PART bytes further
+__device__ __forceinline__ size_t image_offset(int K, long long row, int col) {
+  const long long m_tile = row >> 7;
+  const int r = (int)(row & 127), kc = col >> 5, kin = col & 31;
+  return ((size_t)m_tile * (K >> 5) + kc) * IMG_BLOCK + (size_t)((r >> 3) * 512 + (kin >> 3) * 128 + (r & 7) * 16 + (kin & 7) * 2);
+}
+__device__ __forceinline__ void split2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);
+  const float2 hf = __bfloat1622float2(h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// two adjacent columns (col even)
+__device__ __forceinline__ void image_store2(uint8_t* img, int K, long long row, int col, float x, float y) {
+  uint32_t hi, lo;
+  split2(x, y, hi, lo);
+  uint8_t* p = img + image_offset(K, row, col);
+  *reinterpret_cast<uint32_t*>(p) = hi;
+  *reinterpret_cast<uint32_t*>(p + IMG_PART) = lo;
+}
+// four adjacent columns (col % 4 == 0)
+__device__ __forceinline__ void image_store4(uint8_t* img, int K, long long row, int col, float4 v) {
+  uint2 hi, lo;
+  split2(v.x, v.y, hi.x, lo.x);
+  split2(v.z, v.w, hi.y, lo.y);
+  uint8_t* p = img + image_offset(K, row, col);
+  *reinterpret_cast<uint2*>(p) = hi;
+  *reinterpret_cast<uint2*>(p + IMG_PART) = lo;
+}
+
+}  // namespace tc
+}  // namespace meshtok

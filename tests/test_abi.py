@@ -32,7 +32,7 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.SageLayer) == 8 + 6 * 8
     assert _lib.Model.sage.size == 8 * C.sizeof(_lib.SageLayer)
     assert C.sizeof(_lib.TokenizeArgs) == 4 * 8 + 4 * 4 + 2 * 8 + 5 * 8 + 3 * 4 + 4
-    assert C.sizeof(_lib.Taps) == (7 + 8 + 2) * 8
+    assert C.sizeof(_lib.Taps) == (7 + 8 + 3) * 8
 
 
 def test_host_side_argument_checks():

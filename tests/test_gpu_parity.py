@@ -105,9 +105,12 @@ def test_linear_kernels(M_, N, K):
     check(lib.meshtok_linear_image_bytes(N, K, C.byref(nbytes)))
     img = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
     check(lib.meshtok_linear_build_image(ptr(W), N, K, ptr(img), stream_ptr()))
+    check(lib.meshtok_rows_image_bytes(M_, K, C.byref(nbytes)))
+    a_img = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    check(lib.meshtok_rows_build_image(ptr(A), M_, K, ptr(a_img), stream_ptr()))
     for simt, relu, tol in ((1, 0, 2e-6), (0, 0, 3e-5), (0, 1, 3e-5)):
         out = torch.full((M_, N), float("nan"), device="cuda")
-        check(lib.meshtok_linear(ptr(A), ptr(W), ptr(img), ptr(b), ptr(out), M_, N, K, relu, simt, stream_ptr()))
+        check(lib.meshtok_linear(ptr(A), ptr(a_img), ptr(W), ptr(img), ptr(b), ptr(out), M_, N, K, relu, simt, stream_ptr()))
         torch.cuda.synchronize()
         want = ref.clamp(min=0) if relu else ref
         err = float((out.double() - want).abs().max() / want.abs().max())
