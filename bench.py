@@ -41,6 +41,9 @@ WORKLOADS = {
     "c2": dict(kind="tri", nx=20, ny=20, batch=64, cfg=dict(use_residual_lfq=False), desc="batch 64 x 800 tri faces (20x20 grid, 441 vertices), ResidualVQ 16384x192 x2"),
     "c3": dict(kind="quad", nx=20, ny=40, batch=64, cfg=dict(quads=True), desc="batch 64 x 800 quad faces (20x40 grid, 861 vertices), residual LFQ"),
     "c4": dict(kind="tri", nx=20, ny=20, batch=256, cfg=dict(use_residual_lfq=False), desc="batch 256, faces U[100,800] padded with -1, ResidualVQ"),
+    # BASELINE configs[4] (100k meshes sharded over the GPUs) is run as a stream of launches of this size per rank:
+    # activations (14 GB) >> L2, the regime the HBM-roofline figures of the gather/scatter/feature kernels are quoted in.
+    "c5": dict(kind="tri", nx=20, ny=20, batch=1024, cfg=dict(use_residual_lfq=False), desc="batch 1024 x 800 tri faces per launch (the 100k-mesh sharded run's launch size), ResidualVQ 16384x192 x2"),
 }
 
 
@@ -116,6 +119,30 @@ class ClockSampler:
         return dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
 
 
+def section_work(model, n_faces, n_vrows, n_edges, batch, F, V):
+    """Algorithmic work of each pipeline section per step: bytes each tensor is read/written once
+    for the memory-bound kernels, flops for the tensor-core kernels."""
+    nvf, D, Q, K = model.num_vertices_per_face, model.dim_codebook, model.num_quantizers, model.codebook_size
+    dims_in = [D] + list(model.encoder_dims[:-1])
+    dims_out = list(model.encoder_dims)
+    N, R, E = n_faces, n_vrows, n_edges
+    faces_b = batch * F * nvf * 8
+    work = {
+        "topology": ("hbm", faces_b + 4 * (E + N + N * nvf + R + 2 * batch * F + batch * V)),
+        "face_embed": ("hbm", faces_b + batch * V * 12 + N * D * 4),
+        "sage_gather_mean": ("hbm", sum(2 * N * d * 4 for d in dims_in) + len(dims_in) * 4 * (E + N)),
+        "sage_row_norm": ("hbm", 3 * N * dims_out[-1] * 4),
+        "scatter_mean": ("hbm", N * nvf * D * 4 + R * D * 4 + 4 * (N * nvf + R)),
+        "gather_codes": ("hbm", faces_b + R * Q * 4 + batch * F * nvf * Q * 8),
+        "lfq": ("hbm", R * D * 4 + R * Q * 4),
+        # fp32-equivalent flops; the split-bf16 scheme issues 3 bf16 MMAs per product
+        "sage_linear": ("tensor", sum(2.0 * N * (di * di + 2 * di * do) for di, do in zip(dims_in, dims_out))),
+        "pdc_linear": ("tensor", 2.0 * N * dims_out[-1] * nvf * D),
+        "rvq_search_tc": ("tensor", 2.0 * R * K * D * Q),
+    }
+    return work
+
+
 def cpu_time_oracle(oracle, name, n_meshes, repeats, warmup):
     torch.set_num_threads(os.cpu_count() or 1)
     v, f = make_inputs(name, 0, n_meshes)
@@ -157,6 +184,9 @@ def main():
     ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
+    ap.add_argument("--ncu-window", type=int, default=0,
+                    help="profiling aid: after the warm-up run this many device steps between cudaProfilerStart/Stop and exit "
+                         "(use with ncu --profile-from-start off); prints no bench line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -241,10 +271,24 @@ def main():
         host_step()
     torch.cuda.synchronize()
 
+    if args.ncu_window:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        for _ in range(args.ncu_window):
+            flush.zero_()
+            device_step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps(dict(ncu_window_steps=args.ncu_window, workload=args.workload)), flush=True)
+        return
+
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.meshtok_kernel_launch_count()
-    ms_dev, wall_dev, sec_ms, sec_n = timed(device_step, args.steps, profile=True)
+    ms_dev, wall_dev, _, _ = timed(device_step, args.steps)
     launches = lib.meshtok_kernel_launch_count() - launches0
+    # second pass with cudaEvent pairs around every pipeline section (kept out of the headline timing)
+    prof_steps = min(args.steps, 10)
+    _, _, sec_ms, sec_n = timed(device_step, prof_steps, profile=True)
     model.check_last_status()
     ms_e2e, _, _, _ = timed(host_step, args.steps)
     clocks = sampler.stop() if sampler else None
@@ -263,7 +307,21 @@ def main():
         t = model.taps()
         R = t["n_vrows"]
         D = model.dim_codebook
-        sec = {n: dict(ms_per_step=sec_ms[i] / args.steps, launches_per_step=sec_n[i] / args.steps) for i, n in enumerate(sec_names) if sec_n[i]}
+        sec = {n: dict(ms_per_step=sec_ms[i] / prof_steps, launches_per_step=sec_n[i] / prof_steps) for i, n in enumerate(sec_names) if sec_n[i]}
+        hbm_peak = peaks.get("hbm_gbs") or 6650.0
+        tc_peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        work = section_work(model, t["n_faces"], R, t["n_edges"], batch, f_cpu.shape[1], v_cpu.shape[1])
+        for n, d in sec.items():
+            if n not in work or d["ms_per_step"] <= 0:
+                continue
+            bound, amount = work[n]
+            if bound == "hbm":
+                gbs = amount / (d["ms_per_step"] * 1e-3) / 1e9
+                d.update(bound="hbm", algorithmic_bytes=int(amount), achieved_gbs=gbs, frac_of_hbm_peak=gbs / hbm_peak)
+            else:
+                tf = amount / (d["ms_per_step"] * 1e-3) / 1e12
+                mult = 1.0 if n == "rvq_search_tc" else 3.0
+                d.update(bound="tensor", flops=amount, achieved_tflops=tf, tensor_pipe_tflops=tf * mult, frac_of_bf16_peak=tf * mult / tc_peak)
         roofline = None
         if not model.use_residual_lfq and "rvq_search_tc" in sec:
             per_launch_ms = sec_ms[sec_names.index("rvq_search_tc")] / max(1, sec_n[sec_names.index("rvq_search_tc")])
@@ -291,7 +349,7 @@ def main():
                                 rvq_rows_rechecked_by_exact_scan=t.get("rvq_exact_rechecks")),
                     e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                              ms_per_step=ms_e2e),
-                    gpu_launches=int(launches), sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
+                    gpu_launches=int(launches), gpu_launches_per_step=launches / args.steps, sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -169,6 +169,8 @@ typedef struct meshtok_tokenize_args {
   int32_t stop_after_encode; /* 1: encode() only (codes_out may be NULL) */
   int32_t rvq_exact;         /* 1: fp32 SIMT search instead of the tcgen05 screening + re-score */
   int32_t gemm_simt;         /* 1: fp32 SIMT linears instead of the tcgen05 split-bf16 GEMM */
+  int32_t keep_taps;         /* 1: also store the fp32 form of every intermediate activation (meshtok_tokenize_taps);
+                                0: activations that only feed tcgen05 linears exist as split-bf16 images only */
 } meshtok_tokenize_args;
 
 int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E,
@@ -177,8 +179,8 @@ int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, i
 int meshtok_tokenize(const meshtok_model* model, const meshtok_tokenize_args* args, void* workspace,
                      size_t workspace_bytes, meshtok_stream_t stream);
 
-/* Debug / parity taps: after meshtok_tokenize, describes where the intermediate tensors live inside
- * the workspace (byte offsets) so tests can compare them stage by stage with the oracle. */
+/* Debug / parity taps: after meshtok_tokenize with args.keep_taps = 1, describes where the intermediate tensors
+ * live inside the workspace (byte offsets) so tests can compare them stage by stage with the oracle. */
 typedef struct meshtok_taps {
   int64_t status;          /* int32 status word */
   int64_t counts;          /* int32[4]: n_faces (valid), n_vertex_rows, n_edges, reserved */

@@ -49,7 +49,7 @@ class TokenizeArgs(C.Structure):
         ("pad_id", C.c_int64), ("edge_capacity", C.c_int64),
         ("codes_out", C.c_void_p), ("encoded_out", C.c_void_p), ("face_coords_out", C.c_void_p),
         ("quantized_out", C.c_void_p), ("histogram", C.c_void_p),
-        ("stop_after_encode", C.c_int32), ("rvq_exact", C.c_int32), ("gemm_simt", C.c_int32),
+        ("stop_after_encode", C.c_int32), ("rvq_exact", C.c_int32), ("gemm_simt", C.c_int32), ("keep_taps", C.c_int32),
     ]
 
 

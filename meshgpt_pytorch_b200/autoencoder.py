@@ -157,6 +157,7 @@ class MeshAutoencoder(nn.Module):
         self._ws_cache: Dict[tuple, Tensor] = {}
         self.force_gemm_simt = False      # parity tests: fp32 SIMT linears instead of tcgen05 split-bf16
         self.force_rvq_exact = False      # parity tests: fp32 SIMT nearest-code scan instead of tcgen05 screening
+        self.keep_taps = False            # parity tests: also store every intermediate activation as fp32 rows (see taps())
         self.edge_slots_per_face = 8      # initial CSR capacity; grown automatically on overflow
         self.last_workspace: Optional[Tensor] = None
         self.last_shape: Optional[tuple] = None
@@ -347,6 +348,7 @@ class MeshAutoencoder(nn.Module):
                 a.stop_after_encode = int(not want_codes and not want_quantized)
                 a.rvq_exact = int(self.force_rvq_exact or not prep["tc_rvq"])
                 a.gemm_simt = int(self.force_gemm_simt or not prep["tc_gemm"])
+                a.keep_taps = int(self.keep_taps)
                 check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
                 self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
                 if not check_status:
@@ -377,7 +379,8 @@ class MeshAutoencoder(nn.Module):
             self._raise_on_status(int(self.last_workspace[:4].view(torch.int32).item()))
 
     def taps(self) -> Dict[str, Tensor]:
-        """Views of the intermediate tensors of the last call (stage-wise parity tests)."""
+        """Views of the intermediate tensors of the last call (stage-wise parity tests).  The fp32 activations
+        (x0, layer{i}) are only stored when the call ran with self.keep_taps = True."""
         prep = self._prepare()
         B, F, V, E, cap = self.last_shape
         t = Taps()

@@ -43,7 +43,8 @@ struct Workspace {
   int *ecount, *cursor, *etmp;
   float* x0;
   float *xp, *agg;
-  uint8_t *img_x, *img_agg;   // split-bf16 activation images (tcgen05 linears); null when a width is not a multiple of 32
+  uint8_t *img_x[2], *img_agg;   // split-bf16 activation images (tcgen05 linears; layer input ping-pong + aggregate);
+                                 // null when a width is not a multiple of 32
   float* layer_out[MESHTOK_MAX_SAGE_LAYERS];
   float* y;
   float* avg;
@@ -127,7 +128,8 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->x0 = c.take<float>(BF * D, &t->x0);
   w->xp = c.take<float>(BF * max_in);
   w->agg = c.take<float>(BF * max_in);
-  w->img_x = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
+  w->img_x[0] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
+  w->img_x[1] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
@@ -169,11 +171,12 @@ __global__ void copy_rows_kernel(const float4* __restrict__ a, float4* __restric
 
 // fp32 SIMT linear on fp32 rows, or the tcgen05 split-bf16 linear on activation images
 int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* A2, const void* A2_img, int K2, const float* W,
-           const void* w_img, const float* bias, float* C, int N, const int* m_dev, int m_max, bool relu, cudaStream_t s) {
+           const void* w_img, const float* bias, float* C, int N, const int* m_dev, int m_max, bool relu, cudaStream_t s,
+           const LinearRowEpilogue* epi = nullptr) {
   if (simt) return launch_linear_simt(A1, K1, A2, K2, W, bias, C, N, m_dev, m_max, relu, s);
   MT_CHECK_ARG(w_img != nullptr, "tcgen05 linear requested but the model carries no weight image (set gemm_simt or build images)");
   MT_CHECK_ARG(A1_img != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
-  return launch_linear_tc(A1_img, K1, A2_img, K2, w_img, bias, C, N, m_dev, m_max, relu, s);
+  return launch_linear_tc(A1_img, K1, A2_img, K2, w_img, bias, C, N, m_dev, m_max, relu, epi, s);
 }
 
 // One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the final residual in
@@ -364,6 +367,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   // ---- encoder --------------------------------------------------------------------------------
   const int L = m->num_sage_layers;
   const float* enc = nullptr;
+  const uint8_t* enc_img = w.img_x[0];
   if (a->encoded_in == nullptr) {
     FeatParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -384,33 +388,48 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       fp.slot_off[s_i++] = off; off += m->num_discrete_area;
       for (int k = 0; k < 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_normals; }
     }
-    fp.x0 = w.x0; fp.x0_image = simt ? nullptr : w.img_x; fp.face_coords_out = a->face_coords_out;
+    fp.x0 = (simt || a->keep_taps) ? w.x0 : nullptr; fp.x0_image = simt ? nullptr : w.img_x[0]; fp.face_coords_out = a->face_coords_out;
     if (a->face_coords_out)
       MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)max_rows * nvf * 3, s));
     { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }
 
-    // tcgen05 path: every activation that feeds a linear also exists as a split-bf16 image (img_x: the layer input,
-    // img_agg: the aggregated neighbours), written by the kernel that produces it.
+    // tcgen05 path: every activation that feeds a linear exists as a split-bf16 image, written by the kernel that
+    // produces it (img_x[cur]: the layer input, img_agg: the aggregated neighbours).  Where the layer is narrow enough
+    // for a single pass, the L2 normalisation (+ SiLU + LayerNorm after the first layer) runs in the epilogue of the
+    // second linear, which writes the next layer's image directly; fp32 rows are then only kept for the parity taps.
     const float* x = w.x0;
+    int cur = 0;
     for (int l = 0; l < L; ++l) {
       const meshtok_sage_layer& ly = m->sage[l];
+      const bool first = l == 0, last = l == L - 1;
+      const int mode = first ? 2 : 1;
+      const bool fused = !simt && !last && linear_tc_fused_norm_ok(ly.dim_out, mode) == MESHTOK_OK;
       // xp = relu(lin(x))
-      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x, ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
       { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
-      // out = lin_l(agg) + lin_r(x)
-      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, w.img_agg, ly.dim_in, x, w.img_x, ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
-      { ProfScope ps(PROF_SAGE_NORM, s);
-        if ((rc = launch_row_norm(w.layer_out[l], ly.dim_out, l == 0 ? m->ln_gamma : nullptr, l == 0 ? m->ln_beta : nullptr,
-                                  simt ? nullptr : w.img_x, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
+      if (fused) {
+        LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1]};
+        ProfScope ps(PROF_SAGE_LINEAR, s);
+        if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
+                         a->keep_taps ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;
+      } else {
+        { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, w.img_agg, ly.dim_in, x, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+        { ProfScope ps(PROF_SAGE_NORM, s);
+          if ((rc = launch_row_norm(w.layer_out[l], ly.dim_out, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr,
+                                    simt ? nullptr : w.img_x[cur ^ 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      }
+      cur ^= 1;
       x = w.layer_out[l];
     }
+    enc_img = w.img_x[cur];
     enc = x;
   } else {
     if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc;
     enc = w.layer_out[L - 1];
     if (!simt && !a->stop_after_encode) {
-      MT_CHECK_ARG(w.img_x != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
-      if ((rc = launch_rows_to_image(enc, enc_dim(m), n_faces_dev, max_rows, w.img_x, s)) != MESHTOK_OK) return rc;
+      MT_CHECK_ARG(w.img_x[0] != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
+      if ((rc = launch_rows_to_image(enc, enc_dim(m), n_faces_dev, max_rows, w.img_x[0], s)) != MESHTOK_OK) return rc;
     }
   }
   if (a->encoded_out)
@@ -418,7 +437,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   if (a->stop_after_encode) return MESHTOK_OK;
 
   // ---- quantize -------------------------------------------------------------------------------
-  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, w.img_x, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, enc_img, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
   { ProfScope ps(PROF_SCATTER_MEAN, s); if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, s)) != MESHTOK_OK) return rc; }
   const float* pad_row = nullptr;
   if (m->use_lfq) {

@@ -93,9 +93,18 @@ int launch_rvq_build_image(const float* codebook, int K, int D, float escale, vo
 int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT);
 size_t linear_tc_image_bytes(int N, int K);
 int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cudaStream_t stream);
-// a1_image / a2_image: split-bf16 activation images (tc_common.cuh) written by the producing kernels
+// a1_image / a2_image: split-bf16 activation images (tc_common.cuh) written by the producing kernels.
+// epi (optional): fused row epilogue - 1: x / max(|x|_2, 1e-12); 2: that + SiLU + LayerNorm(gamma, beta, eps 1e-5);
+// the result goes to C (fp32 rows, may be null) and / or out_image (activation image with K = N).
+struct LinearRowEpilogue {
+  int norm_mode;
+  const float* gamma;
+  const float* beta;
+  void* out_image;
+};
+int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
-                     int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream);
+                     int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream);
 size_t rows_image_bytes(long long rows, int K);
 int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream);
 

@@ -16,8 +16,12 @@
 //   * unit of work = (128-row tile, pass of NT <= 256 output columns), K walked in 32-wide chunks through a
 //     4-stage ring (16 KB of A + up to 32 KB of W per stage);
 //   * accumulators are double buffered in TMEM so the epilogue of one unit overlaps the MMAs of the next;
-//   * epilogue: TMEM -> registers -> per-warp shared-memory transpose -> +bias -> ReLU -> fp32 stores
-//     (8 rows x 64 B per instruction).
+//   * plain epilogue: TMEM -> registers -> per-warp shared-memory transpose -> +bias -> ReLU -> fp32 stores
+//     (8 rows x 64 B per instruction);
+//   * fused row epilogue (single pass, N <= 256): the F.normalize(p=2) that ends every SAGEConv - and for the first
+//     layer SiLU + LayerNorm (meshgpt_pytorch.py:545-548) - is done on the accumulator rows (one TMEM lane = one row per
+//     thread, the two column halves exchange their partial sums through shared memory) and the result is written
+//     straight into the NEXT linear's activation image: 16 B hi + 16 B lo per 8 columns, 8 lanes = 128 contiguous bytes.
 // Warp roles (384 threads): w0 producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue
 // (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).
 #include "common.cuh"
@@ -43,7 +47,8 @@ constexpr uint32_t STAGE_BYTES = 2 * A_PART + 2 * W_PART_MAX;  // 48 KB
 constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
 constexpr int EPI_LD = 20;                                 // padded row length (floats) of the 32 x 16 epilogue staging tiles
 constexpr uint32_t EPI_OFF = BAR_OFF + 256;
-constexpr uint32_t SMEM_TOTAL = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;
+constexpr uint32_t XCH_OFF = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;   // [2 unit parities][3 sums][2 halves][128 rows] floats
+constexpr uint32_t SMEM_TOTAL = XCH_OFF + 2 * 3 * 2 * 128 * 4;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct LinArgs {
@@ -57,6 +62,10 @@ struct LinArgs {
   const int* m_dev;
   int m_max;
   int relu;
+  int norm_mode;            // 0 plain, 1 row L2-normalise, 2 L2-normalise + SiLU + LayerNorm(gamma, beta)
+  const float* gamma;
+  const float* beta;
+  uint8_t* out_image;       // activation image of the output rows (K = N) or null
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -163,9 +172,113 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT_MAX;
       const int n0 = pass * a.NT;
       const int row0 = m_tile * M_TILE + q * 32;
-      // columns [c_lo, c_hi) of this pass in blocks of 16 (NT is a multiple of 16); TMEM loads are double buffered
       const int half_cols = ((a.NT / 2 + 15) / 16) * 16;
       const int c_lo = chalf * half_cols, c_hi = chalf ? a.NT : min(a.NT, half_cols);
+      if (a.norm_mode != 0) {
+        // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0) ----
+        float* xs = reinterpret_cast<float*>(smem + XCH_OFF) + (acc_it & 1) * (3 * 256);
+        const int rit = q * 32 + lane;
+        const long long grow = (long long)row0 + lane;
+        const bool live = grow < M;
+        auto put = [&](int c, const float (&o)[16]) {   // 16 consecutive columns of this thread's row
+          if (!live) return;
+          if (a.C) {
+            float4* dst = reinterpret_cast<float4*>(a.C + (size_t)grow * a.N + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          }
+          if (a.out_image) {
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+              uint4 hi, lo;
+              split2(o[8 * g + 0], o[8 * g + 1], hi.x, lo.x);
+              split2(o[8 * g + 2], o[8 * g + 3], hi.y, lo.y);
+              split2(o[8 * g + 4], o[8 * g + 5], hi.z, lo.z);
+              split2(o[8 * g + 6], o[8 * g + 7], hi.w, lo.w);
+              uint8_t* pimg = a.out_image + image_offset(a.N, grow, c + 8 * g);
+              *reinterpret_cast<uint4*>(pimg) = hi;
+              *reinterpret_cast<uint4*>(pimg + IMG_PART) = lo;
+            }
+          }
+        };
+        auto load16 = [&](int c, float (&o)[16]) {       // accumulator + bias
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + c + j));
+            o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+            o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+          }
+        };
+        if (a.norm_mode == 1) {
+          float ss = 0.f;
+          for (int c = c_lo; c < c_hi; c += 16) {
+            float o[16];
+            load16(c, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ss = fmaf(o[j], o[j], ss);
+          }
+          xs[chalf * 128 + rit] = ss;
+          named_bar_sync(2, EPI_WARPS * 32);
+          const float den = fmaxf(sqrtf(xs[rit] + xs[128 + rit]), 1e-12f);
+          for (int c = c_lo; c < c_hi; c += 16) {
+            float o[16];
+            load16(c, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j] = __fdiv_rn(o[j], den);
+            put(c, o);
+          }
+        } else {
+          // <= 32 columns per thread (host checks NT <= 64): the row stays in registers
+          float o0[16], o1[16];
+          const bool h0 = c_lo < c_hi, h1 = c_lo + 16 < c_hi;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { o0[j] = 0.f; o1[j] = 0.f; }
+          if (h0) load16(c_lo, o0);
+          if (h1) load16(c_lo + 16, o1);
+          float ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { ss = fmaf(o0[j], o0[j], ss); ss = fmaf(o1[j], o1[j], ss); }
+          xs[chalf * 128 + rit] = ss;
+          named_bar_sync(2, EPI_WARPS * 32);
+          const float den = fmaxf(sqrtf(xs[rit] + xs[128 + rit]), 1e-12f);
+          float sum = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float t0 = __fdiv_rn(o0[j], den), t1 = __fdiv_rn(o1[j], den);
+            o0[j] = h0 ? __fdiv_rn(t0, 1.f + expf(-t0)) : 0.f;
+            o1[j] = h1 ? __fdiv_rn(t1, 1.f + expf(-t1)) : 0.f;
+            sum += o0[j] + o1[j];
+          }
+          xs[256 + chalf * 128 + rit] = sum;
+          named_bar_sync(2, EPI_WARPS * 32);
+          const float mean = (xs[256 + rit] + xs[256 + 128 + rit]) / (float)a.N;
+          float var = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d0 = h0 ? o0[j] - mean : 0.f, d1 = h1 ? o1[j] - mean : 0.f;
+            var = fmaf(d0, d0, var);
+            var = fmaf(d1, d1, var);
+          }
+          xs[512 + chalf * 128 + rit] = var;
+          named_bar_sync(2, EPI_WARPS * 32);
+          const float rstd = 1.f / sqrtf((xs[512 + rit] + xs[512 + 128 + rit]) / (float)a.N + 1e-5f);
+          if (h0) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o0[j] = (o0[j] - mean) * rstd * __ldg(a.gamma + c_lo + j) + __ldg(a.beta + c_lo + j);
+            put(c_lo, o0);
+          }
+          if (h1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o1[j] = (o1[j] - mean) * rstd * __ldg(a.gamma + c_lo + 16 + j) + __ldg(a.beta + c_lo + 16 + j);
+            put(c_lo + 16, o1);
+          }
+        }
+      } else {
+      // columns [c_lo, c_hi) of this pass in blocks of 16 (NT is a multiple of 16); TMEM loads are double buffered
       const int c4 = (lane & 3) * 4, rsub = lane >> 2;
       uint32_t va[16], vb[16];
       if (c_lo < c_hi) tmem_ld16(taddr + c_lo, va);
@@ -192,6 +305,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           }
         }
         __syncwarp();
+      }
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -260,6 +374,14 @@ int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT) {
   return MESHTOK_OK;
 }
 
+int linear_tc_fused_norm_ok(int N, int norm_mode) {
+  if (N > NT_MAX || N % 16 != 0 || (norm_mode == 2 && N > 64)) {
+    set_error("tcgen05 linear: fused row epilogue needs N %% 16 == 0 and N <= %d (<= 64 with LayerNorm), got %d", NT_MAX, N);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  return MESHTOK_OK;
+}
+
 size_t linear_tc_image_bytes(int N, int K) { return (size_t)N * K * 4; }
 
 size_t rows_image_bytes(long long rows, int K) { return tc::image_bytes(rows, K); }
@@ -287,10 +409,22 @@ int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, voi
 }
 
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
-                     int N, const int* m_dev, int m_max, bool relu, cudaStream_t stream) {
+                     int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream) {
   if (m_max == 0) return MESHTOK_OK;
   MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
   LinArgs a;
+  a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
+  if (epi != nullptr && epi->norm_mode != 0) {
+    int rc0 = linear_tc_fused_norm_ok(N, epi->norm_mode);
+    if (rc0 != MESHTOK_OK) return rc0;
+    MT_CHECK_ARG(!relu, "tcgen05 linear: the fused row epilogue does not combine with ReLU");
+    MT_CHECK_ARG(epi->norm_mode == 1 || (epi->gamma && epi->beta), "tcgen05 linear: LayerNorm needs gamma and beta");
+    MT_CHECK_ARG(epi->out_image == nullptr || N % KC == 0, "tcgen05 linear: an output image needs N %% %d == 0 (got %d)", KC, N);
+    MT_CHECK_ARG(C != nullptr || epi->out_image != nullptr, "tcgen05 linear: no output given");
+    a.norm_mode = epi->norm_mode; a.gamma = epi->gamma; a.beta = epi->beta; a.out_image = static_cast<uint8_t*>(epi->out_image);
+  } else {
+    MT_CHECK_ARG(C != nullptr, "tcgen05 linear: C is null");
+  }
   a.a1_image = static_cast<const uint8_t*>(a1_image); a.a2_image = static_cast<const uint8_t*>(a2_image);
   a.K1 = K1; a.K2 = K2; a.w_image = static_cast<const uint8_t*>(w_image); a.bias = bias; a.C = C;
   a.N = N; a.m_dev = m_dev; a.m_max = m_max; a.relu = relu ? 1 : 0;

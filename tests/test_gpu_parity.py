@@ -195,7 +195,10 @@ def test_rvq_tc_small_codebooks_and_ragged_row_counts():
 
 def _encoder_stage_check(o, m, vertices, faces, label):
     codes, st = o.forward_codes(vertices=vertices, faces=faces, return_stages=True)
+    m.keep_taps = True
     got_codes = m.tokenize(*cuda(vertices, faces))
+    m.keep_taps = False
+    assert torch.equal(m.tokenize(*cuda(vertices, faces)), got_codes), label      # the taps do not change the result
     t = m.taps()
     n = st["project_in"].shape[0]
     assert t["n_faces"] == n, label
