@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
+    ap.add_argument("--no-graph", action="store_true", help="launch the pipeline kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profiling aid: after the warm-up run this many device steps between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -225,9 +226,26 @@ def main():
 
     step_hist = torch.zeros_like(hist)
 
-    def device_step():
+    def eager_step():
         step_hist.zero_()
         model.forward(vertices=v_dev, faces=f_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
+        if world > 1:
+            dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
+        hist.add_(step_hist)
+
+    # the whole pipeline of a batch as ONE CUDA graph (the C ABI never allocates or synchronises)
+    graphed = None
+    launches_per_graph = 0
+    if not args.no_graph:
+        l0 = lib.meshtok_kernel_launch_count()
+        graphed = model.graphed(v_dev, f_dev, histogram=None if args.no_hist else step_hist)
+        launches_per_graph = (lib.meshtok_kernel_launch_count() - l0) // 3      # eager check run + side-stream warm-up + capture
+
+    def device_step():
+        if graphed is None:
+            return eager_step()
+        step_hist.zero_()
+        graphed()
         if world > 1:
             dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
         hist.add_(step_hist)
@@ -235,7 +253,10 @@ def main():
     codes_pin = torch.empty((batch, f_cpu.shape[1] * f_cpu.shape[2], Q), dtype=torch.int64, pin_memory=True)
 
     def host_step():
-        model.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
+        if graphed is None:
+            model.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
+        else:
+            graphed.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
 
     def timed(step_fn, steps, profile=False):
         evs = []
@@ -276,7 +297,7 @@ def main():
         torch.cuda.profiler.start()
         for _ in range(args.ncu_window):
             flush.zero_()
-            device_step()
+            eager_step()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         print(json.dumps(dict(ncu_window_steps=args.ncu_window, workload=args.workload)), flush=True)
@@ -286,9 +307,13 @@ def main():
     launches0 = lib.meshtok_kernel_launch_count()
     ms_dev, wall_dev, _, _ = timed(device_step, args.steps)
     launches = lib.meshtok_kernel_launch_count() - launches0
-    # second pass with cudaEvent pairs around every pipeline section (kept out of the headline timing)
+    if graphed is not None:
+        launches = launches_per_graph * args.steps          # kernels inside the replayed graphs
+    # second pass, kernel by kernel, with cudaEvent pairs around every pipeline section (kept out of the headline timing)
     prof_steps = min(args.steps, 10)
-    _, _, sec_ms, sec_n = timed(device_step, prof_steps, profile=True)
+    for _ in range(2):
+        eager_step()
+    _, _, sec_ms, sec_n = timed(eager_step, prof_steps, profile=True)
     model.check_last_status()
     ms_e2e, _, _, _ = timed(host_step, args.steps)
     clocks = sampler.stop() if sampler else None
@@ -345,6 +370,7 @@ def main():
                     config=dict(workload=args.workload + ": " + w["desc"], meshes_per_rank=batch, faces_per_step=total_faces,
                                 quantizer_rows_per_rank=R, l2="flushed between steps (512 MiB memset outside the timed events)",
                                 sharding="meshes by rank, weights replicated; NCCL all-reduce of the (Q,K) int64 histogram per step",
+                                launch="one CUDA graph replay per step" if graphed is not None else "kernel by kernel",
                                 wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps,
                                 rvq_rows_rechecked_by_exact_scan=t.get("rvq_exact_rechecks")),
                     e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,

@@ -455,6 +455,13 @@ class MeshAutoencoder(nn.Module):
         codes = self.forward(vertices=vertices, faces=faces, face_edges=face_edges, return_codes=True, **kwargs)
         return codes[0] if batch_less else codes
 
+    # ---- CUDA-graph replay of the whole pipeline ----------------------------------------------------
+    def graphed(self, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None) -> "GraphedTokenizer":
+        """Captures tokenize() for this input shape into a CUDA graph (the C ABI never allocates or synchronises, so
+        the ~40 kernel launches of a batch replay as one graph launch).  The example inputs are validated by one eager
+        run first (status word, edge-buffer size).  See GraphedTokenizer."""
+        return GraphedTokenizer(self, vertices, faces, histogram)
+
     # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
     @torch.no_grad()
     def tokenize_host(self, vertices: Tensor, faces: Tensor, face_edges: Optional[Tensor] = None, pinned_out: Optional[Tensor] = None):
@@ -470,4 +477,55 @@ class MeshAutoencoder(nn.Module):
         pinned_out.copy_(codes, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         self.check_last_status()
+        return pinned_out
+
+
+class GraphedTokenizer:
+    """tokenize() for one input shape as a CUDA graph.
+
+        g = model.graphed(vertices, faces)            # CUDA tensors of the shape to be replayed
+        codes = g(vertices2, faces2)                  # copies into the static inputs, replays, returns g.codes
+        codes = g()                                   # replays on whatever g.vertices / g.faces hold now
+
+    g.codes is a static buffer that the next replay overwrites; clone it to keep it.  Data errors (vertex id out of
+    range, edge-buffer overflow) are reported by g.check() / model.check_last_status(), not by the replay itself."""
+
+    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None):
+        assert vertices.is_cuda and faces.is_cuda and vertices.ndim == 3 and faces.ndim == 3
+        self.model = model
+        self.vertices = vertices.to(torch.float32).clone()
+        self.faces = faces.to(torch.int64).clone()
+        self.histogram = histogram
+        model.eval()
+        # eager run: raises on bad data, grows the edge buffer if needed, allocates the workspace
+        model._run(vertices=self.vertices, faces=self.faces, check_status=True)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            model._run(vertices=self.vertices, faces=self.faces, check_status=False)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.codes = model._run(vertices=self.vertices, faces=self.faces, histogram=histogram, check_status=False)["codes"]
+        self._workspace = model.last_workspace
+
+    def __call__(self, vertices: Optional[Tensor] = None, faces: Optional[Tensor] = None) -> Tensor:
+        if vertices is not None:
+            self.vertices.copy_(vertices, non_blocking=True)
+        if faces is not None:
+            self.faces.copy_(faces, non_blocking=True)
+        self.graph.replay()
+        return self.codes
+
+    def check(self):
+        MeshAutoencoder._raise_on_status(int(self._workspace[:4].view(torch.int32).item()))
+
+    def tokenize_host(self, vertices: Tensor, faces: Tensor, pinned_out: Optional[Tensor] = None) -> Tensor:
+        """Host tensors in, host tensor out (H2D into the static inputs, one graph launch, D2H of the codes)."""
+        codes = self(vertices, faces)
+        if pinned_out is None:
+            pinned_out = torch.empty(codes.shape, dtype=codes.dtype, pin_memory=True)
+        pinned_out.copy_(codes, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        self.check()
         return pinned_out

@@ -89,7 +89,7 @@ void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E
   w->status = c.take<int>(16, &t->status);
   w->counts = reinterpret_cast<Counts*>(w->status ? w->status + 8 : nullptr);
   t->counts = t->status + 32;
-  w->mesh_counts = c.take<int>((size_t)B * 4);
+  w->mesh_counts = c.take<int>((size_t)B * 8 + 4);   // [B][4] aggregates, [B][4] inclusive prefixes, ticket (one memset)
   w->offs = c.take<int>(3 * (size_t)(B + 1));
   w->deg_out = c.take<int>(BF);
   w->deg_in = c.take<int>(BF);
@@ -198,7 +198,7 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
   }
   for (int level = 0; level < Q; ++level) {
     if (exact) {
-      { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, packed, best, s); }
+      { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, packed, s); }
       if (rc != MESHTOK_OK) return rc;
     } else {
       MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), s));  // [0] per level; [1] running total of the call
@@ -208,13 +208,13 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_RESCORE, s);
         rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, m->codebook_max_norm,
-                                m->codebook_image_scale, partial, plan.n_splits, n_dev, max_rows, best, amb_list, amb_count, s); }
+                                m->codebook_image_scale, partial, plan.n_splits, n_dev, max_rows, packed, amb_list, amb_count, s); }
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_EXACT, s);
-        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, best, s); }
+        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, s); }
       if (rc != MESHTOK_OK) return rc;
     }
-    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_update(resid, D, m->codebook, best, vcodes, Q, level, rscale, n_dev, max_rows, s); }
+    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, n_dev, max_rows, s); }
     if (rc != MESHTOK_OK) return rc;
   }
   return MESHTOK_OK;
@@ -348,13 +348,13 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   p.faces = a->faces; p.B = B; p.F = F; p.nvf = nvf; p.V = V; p.pad_id = a->pad_id;
   p.threshold = 2; p.include_self = 1; p.do_adjacency = a->face_edges ? 0 : 1;
   p.status = w.status; p.mesh_counts = w.mesh_counts; p.deg_out = w.deg_out; p.deg_in = w.deg_in;
+  p.mesh_prefix = w.mesh_counts + 4 * (size_t)B; p.ticket = w.mesh_counts + 8 * (size_t)B; p.counts = w.counts;
   p.face_off = w.offs; p.vert_off = w.offs + (B + 1); p.edge_off = w.offs + 2 * (size_t)(B + 1);
   p.face_row = w.face_row; p.row_face = w.row_face; p.vert_row = w.vert_row; p.vptr = w.vptr; p.vinc = w.vinc;
   p.indptr = w.indptr; p.src = w.src; p.edge_capacity = a->edge_capacity;
   prof_begin(PROF_TOPOLOGY, s);
-  if ((rc = topo_count(p, s)) != MESHTOK_OK) return rc;
-  if ((rc = topo_offsets(w.mesh_counts, w.offs, B, w.counts, s)) != MESHTOK_OK) return rc;
-  if ((rc = topo_fill_csr(p, s)) != MESHTOK_OK) return rc;
+  MT_CHECK_CUDA(cudaMemsetAsync(w.mesh_counts, 0, sizeof(int) * ((size_t)B * 8 + 4), s));
+  if ((rc = topo_csr(p, s)) != MESHTOK_OK) return rc;
   if (a->face_edges) {
     rc = topo_user_edges(a->face_edges, B, E, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);

@@ -63,11 +63,12 @@ int launch_pack_rows(const float* padded, const int* row_face, int d, float* pac
 // ---- K8a -----------------------------------------------------------------------------------------
 // exact fp32 nearest-code search: best[r] = argmin_j sqrt(max(|x|^2 + |e_j|^2 - 2 x.e_j, 0)), lowest index on ties.
 // row_list == null: rows 0..*n_rows_dev-1; else rows row_list[0..*n_list_dev-1].
-// packed: scratch of max(all row ids)+1 uint64 (distance bits << 32 | index, merged with atomicMin).
+// packed[row] = (distance bits << 32 | index), merged with a 64-bit atomicMin.  Full scan: initialised here; list mode:
+// merged into the values the re-score kernel left (its candidate is a valid code, so the minimum is the exact answer).
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
-                     const int* n_dev, int max_rows, unsigned long long* packed, int32_t* best, cudaStream_t stream);
+                     const int* n_dev, int max_rows, unsigned long long* packed, cudaStream_t stream);
 // r <- r - e[idx]; codes[r*Q + level] = idx; rscale[r] = power of two that brings max|r_d| into [0.5, 1).
-int launch_rvq_update(float* rows, int D, const float* codebook, const int32_t* best, int32_t* codes, int Q, int level,
+int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
                       float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
 // resid <- rows_in (copy) and rscale as above.
 int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, const int* n_rows_dev, int max_rows,
@@ -84,8 +85,8 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
 // re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
 // flag rows whose candidate list may be incomplete (-> exact scan).
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows, int32_t* best,
-                       int* amb_list, int* amb_count, cudaStream_t stream);
+                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows,
+                       unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream);
 size_t rvq_codebook_image_bytes(int K, int D);
 int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream);
 

@@ -126,16 +126,27 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
   }
 }
 
-// hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex
-// (one weighted atomic per vertex row and level instead of one per token).
+// hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex.
+// One weighted atomic per DISTINCT code per warp and level: the 32 rows of a warp are combined first (codebook usage
+// is skewed, so many rows of a warp share a code and un-aggregated atomics serialise on a few hot addresses).
 __global__ void __launch_bounds__(256) histogram_kernel(const int* __restrict__ vptr, const int32_t* __restrict__ vcodes,
                                                         const Counts* counts, int Q, int K, unsigned long long* __restrict__ hist) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= counts->n_vrows) return;
-  const unsigned long long w = (unsigned long long)(vptr[row + 1] - vptr[row]);
+  const bool live = row < counts->n_vrows;
+  const unsigned w = live ? (unsigned)(vptr[row + 1] - vptr[row]) : 0u;
+  const int lane = lane_id();
   for (int q = 0; q < Q; ++q) {
-    const int c = vcodes[(size_t)row * Q + q];
-    if (c >= 0 && c < K) atomicAdd(hist + (size_t)q * K + c, w);
+    int c = live ? vcodes[(size_t)row * Q + q] : -1;
+    if (c >= K) c = -1;
+    unsigned sum = 0;
+    int leader = 32;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const int cl = __shfl_sync(0xffffffffu, c, l);
+      const unsigned wl = __shfl_sync(0xffffffffu, w, l);
+      if (cl == c) { sum += wl; leader = min(leader, l); }
+    }
+    if (c >= 0 && leader == lane && sum) atomicAdd(hist + (size_t)q * K + c, (unsigned long long)sum);
   }
 }
 

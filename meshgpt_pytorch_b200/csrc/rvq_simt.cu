@@ -139,16 +139,6 @@ __global__ void rvq_exact_init_kernel(const int* __restrict__ row_list, const in
   if (i < n) packed[row_list ? row_list[i] : i] = ~0ull;
 }
 
-__global__ void rvq_exact_finish_kernel(const int* __restrict__ row_list, const int* __restrict__ n_dev, int max_rows,
-                                        const unsigned long long* __restrict__ packed, int32_t* __restrict__ best) {
-  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    const int row = row_list ? row_list[i] : i;
-    best[row] = (int32_t)(packed[row] & 0xffffffffull);
-  }
-}
-
 // power of two s such that max|v| * s lies in [0.5, 1)  (1 for an all-zero row)
 __device__ __forceinline__ float pow2_scale(float vmax) {
   if (!(vmax > 0.f) || !(vmax < INFINITY)) return 1.f;
@@ -160,7 +150,7 @@ __device__ __forceinline__ float pow2_scale(float vmax) {
 
 template <int PER, bool UPDATE>
 __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict__ rows_in, float* __restrict__ rows, int D,
-                                                         const float* __restrict__ cb, const int32_t* __restrict__ best,
+                                                         const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
                                                          int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
                                                          const int* __restrict__ n_dev, int max_rows) {
   const int wpb = blockDim.x >> 5;
@@ -168,7 +158,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
   for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
     int idx = 0;
     if (UPDATE) {
-      idx = best[row];
+      idx = (int)(unsigned int)(packed[row] & 0xffffffffull);   // low word of (distance bits, index)
       if (lane_id() == 0) codes[(size_t)row * Q + level] = idx;
     }
     float vmax = 0.f;
@@ -191,33 +181,33 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
 }  // namespace
 
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
-                     const int* n_dev, int max_rows, unsigned long long* packed, int32_t* best, cudaStream_t stream) {
+                     const int* n_dev, int max_rows, unsigned long long* packed, cudaStream_t stream) {
   MT_CHECK_ARG(D % BK == 0, "rvq: dim %d must be a multiple of %d", D, BK);
   if (max_rows == 0) return MESHTOK_OK;
   // few rows (the re-check of ambiguous rows): many code splits so the sweep is short; all rows: fewer, larger splits
   // list mode: the number of rows is a device-side count that is small in practice; cap the grid and loop
-  const int row_blocks = row_list ? min(ceil_div(max_rows, BM), 16) : ceil_div(max_rows, BM);
+  const int row_blocks = row_list ? min(ceil_div(max_rows, BM), 2) : ceil_div(max_rows, BM);
   int splits = row_list ? 1024 : 8;   // list mode is latency bound: one 64-code tile per CTA
   while (splits > 1 && K / splits < BN) splits >>= 1;
   const int codes_per_split = ceil_div(ceil_div(K, splits), BN) * BN;
   splits = ceil_div(K, codes_per_split);
-  rvq_exact_init_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed);
-  MT_CHECK_LAUNCH();
+  if (row_list == nullptr) {   // full scan: start from +inf; list mode merges into the re-score kernel's (distance, index)
+    rvq_exact_init_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed);
+    MT_CHECK_LAUNCH();
+  }
   rvq_exact_kernel<<<dim3(row_blocks, splits), 256, 0, stream>>>(rows, D, codebook, e2, K, codes_per_split, row_list, n_dev,
                                                                max_rows, packed);
-  MT_CHECK_LAUNCH();
-  rvq_exact_finish_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed, best);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int launch_rvq_update(float* rows, int D, const float* codebook, const int32_t* best, int32_t* codes, int Q, int level,
+int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
                       float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(D <= 512, "rvq: dim %d must be <= 512", D);
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per = ceil_div(D, 32);
-#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, best, codes, Q, level, rscale, n_rows_dev, max_rows)
+#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, packed, codes, Q, level, rscale, n_rows_dev, max_rows)
   if (per <= 6) RU(6);
   else RU(16);
 #undef RU

@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
                                                           const float* __restrict__ e2, float max_norm, float escale,
                                                           const float* __restrict__ rscale,
                                                           const float4* __restrict__ partial, int n_splits,
-                                                          const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ best,
+                                                          const int* __restrict__ n_dev, int max_rows,
+                                                          unsigned long long* __restrict__ packed,
                                                           int* __restrict__ amb_list, int* __restrict__ amb_count) {
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
@@ -338,7 +339,10 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
       }
     }
     if (lane == 0) {
-      best[row] = bi;
+      // (distance bits << 32 | index): non-negative floats order like unsigned ints, so the exact scan of an ambiguous
+      // row can merge into this with a 64-bit atomicMin and ties still resolve to the lowest index
+      if (bi == 0x7fffffff) { bi = 0; bd = INFINITY; }   // NaN row: no comparison succeeded
+      packed[row] = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)bi;
       if (ambiguous) { amb_list[atomicAdd(amb_count, 1)] = row; atomicAdd(amb_count + 1, 1); }
     }
   }
@@ -427,11 +431,11 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
 }
 
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows, int32_t* best,
-                       int* amb_list, int* amb_count, cudaStream_t stream) {
+                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows,
+                       unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, n_splits, n_rows_dev, max_rows, best,
+  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, n_splits, n_rows_dev, max_rows, packed,
                                                     amb_list, amb_count);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;

@@ -14,6 +14,13 @@
 //      two faces and turned into bits of an out- and an in-bitmap; popc gives the degrees, a
 //      prefix-popc walk emits the neighbours in ascending order (= the reference's row-major order).
 // The relation is NOT symmetric for degenerate faces (SURVEY hard part 1), hence two bitmaps.
+//
+// The pipeline uses ONE launch (MODE_CSR): each CTA takes a mesh by ticket, counts its in-degrees, obtains the
+// exclusive prefix of (valid faces, referenced vertices, edges) over the preceding meshes with a warp-wide decoupled
+// look-back over per-mesh descriptors in global memory (aggregate / inclusive-prefix flags, as in single-pass scans),
+// and then emits its slice of the batch-global CSR - no separate count launch, offsets kernel or host sync.  The
+// dense (B, emax, 2) list of the stand-alone derive_face_edges_from_faces drop-in keeps the count / fill pair
+// because its output length has to reach the host in between.
 #include <limits.h>
 
 #include "common.cuh"
@@ -25,7 +32,7 @@ namespace {
 
 constexpr int MODE_COUNT = 0;
 constexpr int MODE_FILL_DENSE = 1;
-constexpr int MODE_FILL_CSR = 2;
+constexpr int MODE_CSR = 2;
 
 // Walks the set bits of words[wlo..whi] in ascending order; fn(rank, bit_index).  Returns the count.
 template <class Fn>
@@ -55,11 +62,16 @@ __device__ __forceinline__ int warp_count_bits(const uint32_t* words, int wlo, i
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
+__global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   extern __shared__ int smem[];
-  const int b = blockIdx.x;
-  const int F = p.F, nvf = p.nvf, V = p.V;
+  __shared__ int s_ticket;
   const int tid = threadIdx.x, nt = blockDim.x;
+  if (MODE == MODE_CSR) {   // meshes are taken in ticket order so that every predecessor of the look-back is running or done
+    if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
+    __syncthreads();
+  }
+  const int b = (MODE == MODE_CSR) ? s_ticket : (int)blockIdx.x;
+  const int F = p.F, nvf = p.nvf, V = p.V;
   const int lane = lane_id(), warp = warp_id(), nwarps = nt >> 5;
   const int FN = F * nvf;
 
@@ -159,82 +171,77 @@ __global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
   }
   __syncthreads();
 
-  // ---- fill-mode prologue: local prefix of the degrees computed by the COUNT pass --------------
-  int mesh_total = 0;
-  if (MODE != MODE_COUNT && p.do_adjacency) {
-    const int* deg = (MODE == MODE_FILL_DENSE) ? p.deg_out : p.deg_in;
-    for (int f = tid; f < F; f += nt) fptr[f] = deg[(size_t)b * F + f];
-    __syncthreads();
-    mesh_total = block_exclusive_scan(fptr, F, scratch);
-  }
-  const int face_off = (MODE == MODE_FILL_CSR) ? p.face_off[b] : 0;
-  const int edge_off = (MODE == MODE_FILL_CSR) ? p.edge_off[b] : 0;
-
   // ---- 3. adjacency ---------------------------------------------------------------------------
-  if (p.do_adjacency) {
+  // counting: degrees only (MODE_COUNT: both, to global; MODE_CSR: in-degree into fptr[]);  else: emit the
+  // neighbours in ascending order at fptr[i] (dense list by source / CSR by target).
+  auto adjacency = [&](const bool counting, const int face_off, const int edge_off) {
     uint32_t* obits = bits + warp * Ww;
     uint32_t* ibits = obits + Wf;
     const int thr = p.threshold;
     const bool keep3 = p.include_self != 0;
     for (int i = warp; i < F; i += nwarps) {
-      if (!face_valid(i)) {
-        if (MODE == MODE_COUNT && lane == 0) {
-          p.deg_out[(size_t)b * F + i] = 0;
-          p.deg_in[(size_t)b * F + i] = 0;
-        }
-        continue;
-      }
-      int mine[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) mine[c] = c < nvf ? fv[i * nvf + c] : -2 - c;
       int wmin = INT_MAX, wmax = -1;
-      for (int c = 0; c < nvf; ++c) {
-        const int v = mine[c];
-        bool dup = false;
-        for (int c0 = 0; c0 < c; ++c0) dup |= mine[c0] == v;
-        if (dup) continue;  // same list again
-        const int s = vstart[v], e = vstart[v + 1];
-        for (int q = s + lane; q < e; q += 32) {
-          const int k = inc[q] / nvf;
-          int other[4];
+      if (face_valid(i)) {
+        int mine[4];
 #pragma unroll
-          for (int d = 0; d < 4; ++d) other[d] = d < nvf ? fv[k * nvf + d] : -7 - d;
-          int n_ik = 0, n_ki = 0;
+        for (int c = 0; c < 4; ++c) mine[c] = c < nvf ? fv[i * nvf + c] : -2 - c;
+        for (int c = 0; c < nvf; ++c) {
+          const int v = mine[c];
+          bool dup = false;
+          for (int c0 = 0; c0 < c; ++c0) dup |= mine[c0] == v;
+          if (dup) continue;  // same list again
+          const int s = vstart[v], e = vstart[v + 1];
+          for (int q = s + lane; q < e; q += 32) {
+            const int k = inc[q] / nvf;
+            int other[4];
 #pragma unroll
-          for (int a = 0; a < 4; ++a) {
-            bool in_k = false, in_i = false;
+            for (int d = 0; d < 4; ++d) other[d] = d < nvf ? fv[k * nvf + d] : -7 - d;
+            int n_ik = 0, n_ki = 0;
 #pragma unroll
-            for (int d = 0; d < 4; ++d) {
-              in_k |= mine[a] == other[d];
-              in_i |= other[a] == mine[d];
+            for (int a = 0; a < 4; ++a) {
+              bool in_k = false, in_i = false;
+#pragma unroll
+              for (int d = 0; d < 4; ++d) {
+                in_k |= mine[a] == other[d];
+                in_i |= other[a] == mine[d];
+              }
+              n_ik += (a < nvf) && in_k;
+              n_ki += (a < nvf) && in_i;
             }
-            n_ik += (a < nvf) && in_k;
-            n_ki += (a < nvf) && in_i;
+            const bool eo = (MODE != MODE_CSR) && n_ik >= thr && (keep3 || n_ik != 3);
+            const bool ei = (MODE != MODE_FILL_DENSE) && n_ki >= thr && (keep3 || n_ki != 3);
+            if (eo) atomicOr(&obits[k >> 5], 1u << (k & 31));
+            if (ei) atomicOr(&ibits[k >> 5], 1u << (k & 31));
+            if (eo || ei) { wmin = min(wmin, k >> 5); wmax = max(wmax, k >> 5); }
           }
-          const bool eo = n_ik >= thr && (keep3 || n_ik != 3);
-          const bool ei = n_ki >= thr && (keep3 || n_ki != 3);
-          if (eo) atomicOr(&obits[k >> 5], 1u << (k & 31));
-          if (ei) atomicOr(&ibits[k >> 5], 1u << (k & 31));
-          if (eo || ei) { wmin = min(wmin, k >> 5); wmax = max(wmax, k >> 5); }
         }
+        wmin = warp_min_int(wmin);
+        wmax = warp_max_int(wmax);
+        __syncwarp();
       }
-      wmin = warp_min_int(wmin);
-      wmax = warp_max_int(wmax);
-      __syncwarp();
-      if (wmax < 0) {
-        if (MODE == MODE_COUNT && lane == 0) {
-          p.deg_out[(size_t)b * F + i] = 0;
-          p.deg_in[(size_t)b * F + i] = 0;
+      if (wmax < 0) {   // padded face, or no neighbour at all
+        if (counting && lane == 0) {
+          if (MODE == MODE_COUNT) {
+            p.deg_out[(size_t)b * F + i] = 0;
+            p.deg_in[(size_t)b * F + i] = 0;
+          } else {
+            fptr[i] = 0;
+          }
         }
         continue;
       }
-      if (MODE == MODE_COUNT) {
-        const int dout = warp_count_bits(obits, wmin, wmax);
-        const int din = warp_count_bits(ibits, wmin, wmax);
-        if (lane == 0) {
-          p.deg_out[(size_t)b * F + i] = dout;
-          p.deg_in[(size_t)b * F + i] = din;
-          atomicAdd(&scratch[41], dout);
+      if (counting) {
+        if (MODE == MODE_COUNT) {
+          const int dout = warp_count_bits(obits, wmin, wmax);
+          const int din = warp_count_bits(ibits, wmin, wmax);
+          if (lane == 0) {
+            p.deg_out[(size_t)b * F + i] = dout;
+            p.deg_in[(size_t)b * F + i] = din;
+            atomicAdd(&scratch[41], dout);
+          }
+        } else {
+          const int din = warp_count_bits(ibits, wmin, wmax);
+          if (lane == 0) fptr[i] = din;
         }
       } else if (MODE == MODE_FILL_DENSE) {
         int64_t* dst = p.dense_out + ((size_t)b * p.emax + fptr[i]) * 2;
@@ -253,11 +260,11 @@ __global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
       for (int w = wmin + lane; w <= wmax; w += 32) { obits[w] = 0u; ibits[w] = 0u; }
       __syncwarp();
     }
-  }
-  __syncthreads();
+  };
 
-  // ---- 4. outputs -----------------------------------------------------------------------------
   if (MODE == MODE_COUNT) {
+    if (p.do_adjacency) adjacency(true, 0, 0);
+    __syncthreads();
     if (tid == 0) {
       int* mc = p.mesh_counts + 4 * b;
       mc[0] = nvalid;
@@ -269,12 +276,67 @@ __global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
     return;
   }
   if (MODE == MODE_FILL_DENSE) {
+    // local prefix of the out-degrees computed by the COUNT launch
+    for (int f = tid; f < F; f += nt) fptr[f] = p.deg_out[(size_t)b * F + f];
+    __syncthreads();
+    const int mesh_total = block_exclusive_scan(fptr, F, scratch);
+    adjacency(false, 0, 0);
     int64_t* dst = p.dense_out + (size_t)b * p.emax * 2;
     for (int t = mesh_total * 2 + tid; t < p.emax * 2; t += nt) dst[t] = p.pad_id;
     return;
   }
-  // MODE_FILL_CSR: maps + vertex CSR + face CSR row pointers
-  const int vert_off = p.vert_off[b];
+
+  // ---- MODE_CSR: degrees -> look-back over the preceding meshes -> emit -------------------------
+  int mesh_total = 0;
+  if (p.do_adjacency) {
+    adjacency(true, 0, 0);
+    __syncthreads();
+    mesh_total = block_exclusive_scan(fptr, F, scratch);
+  }
+  if (warp == 0) {
+    volatile int* agg = p.mesh_counts;   // [B][4]: nvalid, nref, nedges, ready flag
+    volatile int* pre = p.mesh_prefix;   // [B][4]: inclusive prefixes of the same, ready flag
+    if (lane == 0) {
+      agg[4 * b + 0] = nvalid; agg[4 * b + 1] = nref; agg[4 * b + 2] = mesh_total;
+      __threadfence();
+      agg[4 * b + 3] = 1;
+    }
+    int ex0 = 0, ex1 = 0, ex2 = 0;
+    for (int j = b - 1;; j -= 32) {          // 32 predecessors per step; lanes past mesh 0 act as a zero prefix
+      const int idx = j - lane;
+      bool is_prefix = true;
+      int v0 = 0, v1 = 0, v2 = 0;
+      if (idx >= 0) {
+        for (;;) {
+          if (pre[4 * idx + 3] != 0) { is_prefix = true; break; }
+          if (agg[4 * idx + 3] != 0) { is_prefix = false; break; }
+        }
+        __threadfence();
+        volatile int* src_d = is_prefix ? pre : agg;
+        v0 = src_d[4 * idx + 0]; v1 = src_d[4 * idx + 1]; v2 = src_d[4 * idx + 2];
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, is_prefix);
+      const int stop = m ? __ffs(m) - 1 : 32;   // lanes < stop: aggregates of nearer meshes; lane stop: a full prefix
+      if (lane > stop) { v0 = 0; v1 = 0; v2 = 0; }
+      ex0 += warp_sum_int(v0); ex1 += warp_sum_int(v1); ex2 += warp_sum_int(v2);
+      if (m) break;
+    }
+    if (lane == 0) {
+      pre[4 * b + 0] = ex0 + nvalid; pre[4 * b + 1] = ex1 + nref; pre[4 * b + 2] = ex2 + mesh_total;
+      __threadfence();
+      pre[4 * b + 3] = 1;
+      scratch[42] = ex0; scratch[43] = ex1; scratch[44] = ex2;
+    }
+  }
+  __syncthreads();
+  const int face_off = scratch[42], vert_off = scratch[43], edge_off = scratch[44];
+  if (p.do_adjacency) adjacency(false, face_off, edge_off);
+  __syncthreads();
+
+  // ---- 4. outputs: maps + vertex CSR + face CSR row pointers ------------------------------------
+  if (tid == 0) {
+    p.face_off[b] = face_off; p.vert_off[b] = vert_off; p.edge_off[b] = edge_off;
+  }
   for (int f = tid; f < F; f += nt) {
     const bool ok = face_valid(f);
     const int row = face_off + frank[f];
@@ -284,7 +346,7 @@ __global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
       if (p.do_adjacency) p.indptr[row] = edge_off + fptr[f];
     }
   }
-  if (p.do_adjacency && edge_off + mesh_total > p.edge_capacity && tid == 0)
+  if (p.do_adjacency && (long long)edge_off + mesh_total > p.edge_capacity && tid == 0)
     atomicOr(p.status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
   for (int v = tid; v < V; v += nt) vcur[v] = (vstart[v + 1] > vstart[v]) ? 1 : 0;
   __syncthreads();
@@ -301,10 +363,12 @@ __global__ void __launch_bounds__(1024) topology_kernel(TopoParams p) {
     const int f = idx / nvf, c = idx - f * nvf;
     p.vinc[(size_t)face_off * nvf + e] = (face_off + frank[f]) * nvf + c;
   }
-  if (b == gridDim.x - 1 && tid == 0) {
-    const int nf = p.face_off[gridDim.x], nv = p.vert_off[gridDim.x];
+  if (b == (int)gridDim.x - 1 && tid == 0) {   // the last mesh knows the batch totals
+    const int nf = face_off + nvalid, nv = vert_off + nref, ne = edge_off + mesh_total;
+    p.face_off[gridDim.x] = nf; p.vert_off[gridDim.x] = nv; p.edge_off[gridDim.x] = ne;
+    p.counts->n_faces = nf; p.counts->n_vrows = nv; p.counts->n_edges = ne;
     p.vptr[nv] = nf * nvf;
-    if (p.do_adjacency) p.indptr[nf] = p.edge_off[gridDim.x];
+    if (p.do_adjacency) p.indptr[nf] = ne;
   }
 }
 
@@ -471,7 +535,7 @@ static int launch_topology(TopoParams p, cudaStream_t stream) {
 
 int topo_count(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_COUNT>(p, stream); }
 int topo_fill_dense(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_FILL_DENSE>(p, stream); }
-int topo_fill_csr(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_FILL_CSR>(p, stream); }
+int topo_csr(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_CSR>(p, stream); }
 
 int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream) {
   mesh_offsets_kernel<<<1, 1024, 0, stream>>>(mesh_counts, offs, B, counts);

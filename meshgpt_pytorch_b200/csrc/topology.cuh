@@ -12,17 +12,20 @@ struct TopoParams {
   int do_adjacency;       // 0 when the caller supplies face_edges
   int words_per_warp;     // filled by the launcher
   int* status;
-  int* mesh_counts;       // [B][4] nvalid, nref, nedges, -
+  int* mesh_counts;       // [B][4] nvalid, nref, nedges, ready flag (MODE_CSR look-back descriptor)
+  int* mesh_prefix;       // [B][4] inclusive prefixes of the same + ready flag   (MODE_CSR)
+  int* ticket;            // mesh ticket counter                                  (MODE_CSR)
+  Counts* counts;         // batch totals, written by the CTA of the last mesh    (MODE_CSR)
   int* deg_out;           // [B*F]
   int* deg_in;            // [B*F]
   int32_t* edge_counts_out;  // [B] or null
   // fill dense
   int emax;
   int64_t* dense_out;     // (B, emax, 2)
-  // fill csr
-  const int* face_off;    // [B+1]
-  const int* vert_off;    // [B+1]
-  const int* edge_off;    // [B+1]
+  // csr (single launch): exclusive offsets per mesh, written by the kernel
+  int* face_off;          // [B+1]
+  int* vert_off;          // [B+1]
+  int* edge_off;          // [B+1]
   int* face_row;          // [B*F]
   int* row_face;          // [B*F]
   int* vert_row;          // [B*V]
@@ -37,7 +40,8 @@ int topo_threads(int F);
 int topo_check_shape(int B, int F, int nvf, int V);
 int topo_count(const TopoParams& p, cudaStream_t stream);
 int topo_fill_dense(const TopoParams& p, cudaStream_t stream);
-int topo_fill_csr(const TopoParams& p, cudaStream_t stream);
+// single-launch batch topology; the caller zeroes mesh_counts, mesh_prefix and ticket first
+int topo_csr(const TopoParams& p, cudaStream_t stream);
 int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream);
 int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
                     int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,

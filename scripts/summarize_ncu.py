@@ -30,9 +30,16 @@ KEY_METRICS = [
 
 
 def short(name: str) -> str:
-    name = re.sub(r"^void ", "", name)
-    name = re.sub(r"^.*(<unnamed>|\(anonymous namespace\))::", "", name)
-    name = re.sub(r"\(.*$", "", name)
+    name = re.sub(r"^void ", "", name.strip())
+    if name.endswith(")"):                     # drop the argument list (balanced from the end)
+        depth = 0
+        for i in range(len(name) - 1, -1, -1):
+            depth += name[i] == ")"
+            depth -= name[i] == "("
+            if depth == 0:
+                name = name[:i]
+                break
+    name = re.sub(r"^(\w+::)*(<unnamed>|\(anonymous namespace\))::", "", name)
     return name[:90]
 
 

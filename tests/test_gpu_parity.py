@@ -305,6 +305,12 @@ def test_tokenize_variants_agree():
     assert one.shape == (f.shape[1] * 3, 2) and torch.equal(one, base[1])
     host = m.tokenize_host(v, f)
     assert not host.is_cuda and torch.equal(host, base.cpu())
+    # CUDA-graph replay: same codes, also after new data has been copied into the static inputs
+    g = m.graphed(v.cuda(), f.cuda())
+    assert torch.equal(g(), base)
+    v2, f2 = synth.ragged_batch("tri", 8, 8, [77, 128, 9], [7, 8, 9])
+    assert torch.equal(g(v2.cuda(), f2.cuda()), m.tokenize(v2.cuda(), f2.cuda()))
+    assert torch.equal(g.tokenize_host(v, f), base.cpu())
     bad = f.clone()
     bad[0, 0, 0] = v.shape[1] + 5
     with pytest.raises(IndexError):
