@@ -1,5 +1,6 @@
 // extern "C" surface of libmeshtok.so (see include/meshtok.h) and the per-batch pipeline driver.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -59,8 +60,37 @@ struct Workspace {
   int* amb_list;
   int* amb_count;
   float4* partial;
+  uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
   size_t total;
 };
+
+// tcgen05 RVQ screening kernel: 2 = CTA-pair (cta_group::2, rvq_tc2.cu) whenever the codebook size allows it, 1 = single-CTA
+// (rvq_tc.cu).  MESHTOK_RVQ_TC=1 forces the single-CTA kernel (A/B measurements; at the MeshGPT shape the pair kernel
+// takes 171 us per level against 182 us).
+int rvq_tc_variant(int K) {
+  static int forced = -1;
+  if (forced < 0) {
+    const char* e = getenv("MESHTOK_RVQ_TC");
+    forced = (e && e[0] == '1') ? 1 : 0;
+  }
+  return (forced == 1 || K % 256 != 0) ? 1 : 2;
+}
+
+// workspace needs of the screening search for up to R rows: partial candidates (+ the row image of the pair kernel)
+int rvq_tc_sizes(int R, int K, int D, size_t* partial_bytes, size_t* rimg_bytes) {
+  *rimg_bytes = 0;
+  RvqTcPlan p1;
+  int rc = rvq_tc_plan(R, K, D, &p1);
+  if (rc != MESHTOK_OK) return rc;
+  *partial_bytes = p1.partial_bytes;
+  if (rvq_tc_variant(K) == 2) {
+    RvqTc2Plan p2;
+    if ((rc = rvq_tc2_plan(R, K, D, &p2)) != MESHTOK_OK) return rc;
+    *partial_bytes = p2.partial_bytes;
+    *rimg_bytes = p2.row_image_bytes;
+  }
+  return MESHTOK_OK;
+}
 
 int check_model(const meshtok_model* m) {
   MT_CHECK_ARG(m != nullptr, "model is null");
@@ -145,11 +175,13 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->amb_list = c.take<int>(BV);
   w->amb_count = c.take<int>(4, &t->rvq_stats);
   w->partial = nullptr;
-  if (!m->use_lfq) {
-    RvqTcPlan plan;
-    int rc = rvq_tc_plan((int)BV, m->codebook_size, D, &plan);
+  w->rimg = nullptr;
+  if (!m->use_lfq && m->codebook_f16_tiles != nullptr) {
+    size_t pb = 0, rb = 0;
+    int rc = rvq_tc_sizes((int)BV, m->codebook_size, D, &pb, &rb);
     if (rc != MESHTOK_OK) return rc;
-    w->partial = c.take<float4>(plan.partial_bytes / sizeof(float4));
+    w->partial = c.take<float4>(pb / sizeof(float4));
+    if (rb) w->rimg = c.take<uint8_t>(rb);
   }
   w->total = align_up(c.off, 256);
   return MESHTOK_OK;
@@ -181,21 +213,35 @@ int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* 
 
 // One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the final residual in
 // `resid` and the codes in vcodes (R x Q).
-int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes, int32_t* best,
-            unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, const int* n_dev, int max_rows, bool exact, cudaStream_t s) {
+int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes,
+            unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, uint8_t* rimg, const int* n_dev, int max_rows,
+            bool exact, cudaStream_t s) {
   const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
   if (max_rows == 0) return MESHTOK_OK;
   int rc;
-  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, n_dev, max_rows, s); }
-  if (rc != MESHTOK_OK) return rc;
-  MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
+  const int variant = exact ? 0 : rvq_tc_variant(K);
   RvqTcPlan plan;
+  RvqTc2Plan plan2;
+  RvqPartialLayout layout;
+  memset(&layout, 0, sizeof(layout));
   if (!exact) {
     MT_CHECK_ARG(m->codebook_f16_tiles != nullptr && m->codebook_image_scale > 0.f,
                  "model.codebook_f16_tiles / codebook_image_scale not set (needed by the tcgen05 search)");
-    rc = rvq_tc_plan(max_rows, K, D, &plan);
-    if (rc != MESHTOK_OK) return rc;
+    MT_CHECK_ARG(partial != nullptr, "no workspace for the tcgen05 search candidates");
+    if (variant == 2) {
+      MT_CHECK_ARG(rimg != nullptr, "no workspace for the residual row image");
+      if ((rc = rvq_tc2_plan(max_rows, K, D, &plan2)) != MESHTOK_OK) return rc;
+      layout = rvq_tc2_partial_layout(plan2, max_rows);
+    } else {
+      if ((rc = rvq_tc_plan(max_rows, K, D, &plan)) != MESHTOK_OK) return rc;
+      layout.mode = 1;
+      layout.stride = plan.n_splits;
+    }
   }
+  uint8_t* row_image = variant == 2 ? rimg : nullptr;
+  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, n_dev, max_rows, s); }
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
   for (int level = 0; level < Q; ++level) {
     if (exact) {
       { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, packed, s); }
@@ -203,18 +249,23 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
     } else {
       MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), s));  // [0] per level; [1] running total of the call
       { ProfScope ps(PROF_RVQ_SEARCH, s);
-        rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
-                                  n_dev, max_rows, plan, partial, s); }
+        if (variant == 2)
+          rc = launch_rvq_tc2_search(rimg, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, n_dev,
+                                     max_rows, plan2, partial, s);
+        else
+          rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
+                                    n_dev, max_rows, plan, partial, s); }
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_RESCORE, s);
         rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, m->codebook_max_norm,
-                                m->codebook_image_scale, partial, plan.n_splits, n_dev, max_rows, packed, amb_list, amb_count, s); }
+                                m->codebook_image_scale, partial, layout, n_dev, max_rows, packed, amb_list, amb_count, s); }
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_EXACT, s);
         rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, s); }
       if (rc != MESHTOK_OK) return rc;
     }
-    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, n_dev, max_rows, s); }
+    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
+      rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, n_dev, max_rows, s); }
     if (rc != MESHTOK_OK) return rc;
   }
   return MESHTOK_OK;
@@ -458,7 +509,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   } else {
     MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
-    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.best, w.packed, w.amb_list, w.amb_count, w.partial, n_vrows_dev, max_vrows,
+    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.packed, w.amb_list, w.amb_count, w.partial, w.rimg, n_vrows_dev, max_vrows,
                       a->rvq_exact != 0, s)) != MESHTOK_OK) return rc;
     if (a->quantized_out) {
       const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
@@ -488,23 +539,34 @@ int meshtok_lfq_codes(const meshtok_model* m, const float* rows, int R, int32_t*
                     nullptr, nullptr, R, static_cast<cudaStream_t>(stream));
 }
 
+// carves the stand-alone RVQ workspace; base == nullptr only measures
+static int carve_rvq(const meshtok_model* m, int R, void* base, float** resid, float** rscale, unsigned long long** packed,
+                     int** amb_list, int** amb_count, int** n_dev, float4** partial, uint8_t** rimg, size_t* total) {
+  size_t pb = 0, rb = 0;
+  const bool tc = m->codebook_f16_tiles != nullptr || base == nullptr;
+  if (tc) {
+    int rc = rvq_tc_sizes(R, m->codebook_size, m->dim_codebook, &pb, &rb);
+    if (rc != MESHTOK_OK) { if (base != nullptr) return rc; pb = rb = 0; }   // shapes only the exact path covers
+  }
+  Carver c(base);
+  *resid = c.take<float>((size_t)R * m->dim_codebook);
+  *rscale = c.take<float>(R);
+  *packed = c.take<unsigned long long>(R);
+  *amb_list = c.take<int>(R);
+  *amb_count = c.take<int>(4);
+  *n_dev = c.take<int>(4);
+  *partial = pb ? c.take<float4>(pb / sizeof(float4)) : nullptr;
+  *rimg = rb ? c.take<uint8_t>(rb) : nullptr;
+  *total = align_up(c.off, 256);
+  return MESHTOK_OK;
+}
+
 int meshtok_rvq_workspace_bytes(const meshtok_model* m, int R, size_t* bytes) {
   int rc = check_model(m);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(bytes && R >= 0, "bad arguments");
-  RvqTcPlan plan;
-  if ((rc = rvq_tc_plan(R, m->codebook_size, m->dim_codebook, &plan)) != MESHTOK_OK) return rc;
-  Carver c(nullptr);
-  c.take<float>((size_t)R * m->dim_codebook);
-  c.take<float>(R);
-  c.take<int32_t>(R);
-  c.take<unsigned long long>(R);
-  c.take<int>(R);
-  c.take<int>(4);
-  c.take<int>(4);
-  c.take<float4>(plan.partial_bytes / sizeof(float4));
-  *bytes = align_up(c.off, 256);
-  return MESHTOK_OK;
+  float *resid, *rscale; unsigned long long* packed; int *amb_list, *amb_count, *n_dev; float4* partial; uint8_t* rimg;
+  return carve_rvq(m, R, nullptr, &resid, &rscale, &packed, &amb_list, &amb_count, &n_dev, &partial, &rimg, bytes);
 }
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
@@ -515,25 +577,17 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(rows && codes && workspace && R >= 0, "rows / codes / workspace is null");
   MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
-  RvqTcPlan plan;
-  if ((rc = rvq_tc_plan(R, m->codebook_size, m->dim_codebook, &plan)) != MESHTOK_OK) return rc;
-  Carver c(workspace);
-  float* resid = c.take<float>((size_t)R * m->dim_codebook);
-  float* rscale = c.take<float>(R);
-  int32_t* best = c.take<int32_t>(R);
-  unsigned long long* packed = c.take<unsigned long long>(R);
-  int* amb_list = c.take<int>(R);
-  int* amb_count = c.take<int>(4);
-  int* n_dev = c.take<int>(4);
-  float4* partial = c.take<float4>(plan.partial_bytes / sizeof(float4));
-  if (align_up(c.off, 256) > workspace_bytes) {
-    set_error("workspace too small: need %zu bytes, got %zu", align_up(c.off, 256), workspace_bytes);
+  float *resid, *rscale; unsigned long long* packed; int *amb_list, *amb_count, *n_dev; float4* partial; uint8_t* rimg;
+  size_t total = 0;
+  if ((rc = carve_rvq(m, R, workspace, &resid, &rscale, &packed, &amb_list, &amb_count, &n_dev, &partial, &rimg, &total)) != MESHTOK_OK) return rc;
+  if (total > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", total, workspace_bytes);
     return MESHTOK_ERR_WORKSPACE;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
   MT_CHECK_LAUNCH();
-  rc = run_rvq(m, rows, resid, rscale, codes, best, packed, amb_list, amb_count, partial, n_dev, R, exact != 0, s);
+  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, s);
   if (rc != MESHTOK_OK) return rc;
   if (residual_out && R > 0)
     MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));

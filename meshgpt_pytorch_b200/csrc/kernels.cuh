@@ -68,10 +68,11 @@ int launch_pack_rows(const float* padded, const int* row_face, int d, float* pac
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
                      const int* n_dev, int max_rows, unsigned long long* packed, cudaStream_t stream);
 // r <- r - e[idx]; codes[r*Q + level] = idx; rscale[r] = power of two that brings max|r_d| into [0.5, 1).
+// row_image (optional): fp16(r * rscale) in the layout the CTA-pair search bulk-copies ([128-row tile] x canonical 128 x D).
 int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
-                      float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
-// resid <- rows_in (copy) and rscale as above.
-int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, const int* n_rows_dev, int max_rows,
+                      float* rscale, void* row_image, const int* n_rows_dev, int max_rows, cudaStream_t stream);
+// resid <- rows_in (copy), rscale and row_image as above.
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, const int* n_rows_dev, int max_rows,
                     cudaStream_t stream);
 
 // tcgen05 screening search (rvq_tc.cu).  Produces per (row, split) the two best fp16-screened scores + indices.
@@ -82,11 +83,27 @@ struct RvqTcPlan {
 int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan);
 int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
                          int K, const int* n_rows_dev, int max_rows, const RvqTcPlan& plan, float4* partial, cudaStream_t stream);
+// Where the screening kernels leave the candidates of a row: mode 1 (rvq_tc.cu): n_splits entries at
+// partial[row * n_splits ..]; mode 2 (rvq_tc2.cu): 2 entries (column halves) per cluster whose step range touched the
+// row's 256-row tile, at partial[row * stride + 2 * (cluster - first cluster of the tile) + half].
+struct RvqPartialLayout {
+  int mode, stride, T, n_clusters, w_min;
+};
 // re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
 // flag rows whose candidate list may be incomplete (-> exact scan).
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows,
+                       float escale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream);
+
+// CTA-pair (cta_group::2) screening search (rvq_tc2.cu)
+struct RvqTc2Plan {
+  int T, n_clusters, max_slots;
+  size_t partial_bytes, row_image_bytes;
+};
+int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan);
+RvqPartialLayout rvq_tc2_partial_layout(const RvqTc2Plan& plan, int max_rows);
+int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+                          const int* n_rows_dev, int max_rows, const RvqTc2Plan& plan, float4* partial, cudaStream_t stream);
 size_t rvq_codebook_image_bytes(int K, int D);
 int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream);
 

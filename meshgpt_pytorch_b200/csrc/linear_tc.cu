@@ -107,40 +107,41 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== producer: one A block (16 KB) + one W block (2 * NT * 64 B) per stage =====
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        const int m_tile = u / a.passes, pass = u % a.passes;
-        const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part);
-        const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
-        const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
-        for (int kc = 0; kc < kchunks; ++kc, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+    // ===== producer (warp-converged; one elected lane issues): one A block (16 KB) + one W block (2 * NT * 64 B) per stage =====
+    uint32_t it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      const int m_tile = u / a.passes, pass = u % a.passes;
+      const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part);
+      const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
+      const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], IMG_BLOCK + 2 * w_part);
           uint8_t* stage = smem + s * STAGE_BYTES;
           const uint8_t* asrc = kc < kch1 ? a1src + (size_t)kc * IMG_BLOCK : a2src + (size_t)(kc - kch1) * IMG_BLOCK;
           bulk_g2s(stage, asrc, IMG_BLOCK, &full[s]);
           bulk_g2s(stage + 2 * A_PART, wsrc + (size_t)kc * (2 * w_part), 2 * w_part, &full[s]);
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16_f32(M_TILE, a.NT, /*bf16=*/true);
-      const uint32_t s0 = smem_u32(smem);
-      uint32_t it = 0, acc_it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
-        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
-        mbar_wait(&acc_empty[buf], aph ^ 1);
+    // ===== MMA issuer (warp-converged; one elected lane issues) =====
+    const uint32_t idesc = make_idesc_f16_f32(M_TILE, a.NT, /*bf16=*/true);
+    const uint32_t s0 = smem_u32(smem);
+    uint32_t it = 0, acc_it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
+      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(&acc_empty[buf], aph ^ 1);
+      tcgen05_fence_after();
+      const uint32_t d = tmem_base + buf * NT_MAX;
+      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
         tcgen05_fence_after();
-        const uint32_t d = tmem_base + buf * NT_MAX;
-        for (int kc = 0; kc < kchunks; ++kc, ++it) {
-          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          tcgen05_fence_after();
+        if (elect_one()) {
           const uint32_t ah = s0 + s * STAGE_BYTES, al = ah + A_PART;
           const uint32_t wh = ah + 2 * A_PART, wl = wh + w_part;
 #pragma unroll
@@ -154,8 +155,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           }
           umma_commit(&empty[s]);
         }
-        umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
+      if (elect_one()) umma_commit(&acc_full[buf]);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ===== epilogue =====

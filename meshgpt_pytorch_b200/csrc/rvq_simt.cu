@@ -6,6 +6,8 @@
 // one-hot of the same size per level; here a 64x64 register-tiled sweep keeps a running (dist, idx) per
 // row.  This kernel is (a) the re-check of the rows the tcgen05 screening flags as ambiguous, and
 // (b) the exact checker the GPU tests compare the tensor-core path against.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -148,33 +150,60 @@ __device__ __forceinline__ float pow2_scale(float vmax) {
   return ldexpf(1.f, -e);
 }
 
-template <int PER, bool UPDATE>
+template <int PER2, bool UPDATE>   // float2 pairs per lane: D <= 64 * PER2
 __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict__ rows_in, float* __restrict__ rows, int D,
                                                          const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
                                                          int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
-                                                         const int* __restrict__ n_dev, int max_rows) {
+                                                         uint8_t* __restrict__ row_image, const int* __restrict__ n_dev, int max_rows) {
   const int wpb = blockDim.x >> 5;
+  const int lane = lane_id();
   const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  const int d2 = D >> 1;
   for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
     int idx = 0;
     if (UPDATE) {
       idx = (int)(unsigned int)(packed[row] & 0xffffffffull);   // low word of (distance bits, index)
-      if (lane_id() == 0) codes[(size_t)row * Q + level] = idx;
+      if (lane == 0) codes[(size_t)row * Q + level] = idx;
     }
+    float2 v[PER2];
     float vmax = 0.f;
+    const float2* src = reinterpret_cast<const float2*>(rows_in + (size_t)row * D);
+    const float2* code = reinterpret_cast<const float2*>(cb + (size_t)idx * D);
+    float2* dst = reinterpret_cast<float2*>(rows + (size_t)row * D);
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int c = lane_id() + 32 * i;
-      if (c < D) {
-        float v = rows_in[(size_t)row * D + c];
-        if (UPDATE) v = __fsub_rn(v, __ldg(cb + (size_t)idx * D + c));
-        rows[(size_t)row * D + c] = v;
-        vmax = fmaxf(vmax, fabsf(v));
+    for (int i = 0; i < PER2; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = make_float2(0.f, 0.f);
+      if (c < d2) {
+        v[i] = src[c];
+        if (UPDATE) {
+          const float2 e = __ldg(code + c);
+          v[i].x = __fsub_rn(v[i].x, e.x);
+          v[i].y = __fsub_rn(v[i].y, e.y);
+        }
+        dst[c] = v[i];
+        vmax = fmaxf(vmax, fmaxf(fabsf(v[i].x), fabsf(v[i].y)));
       }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    if (lane_id() == 0 && rscale) rscale[row] = pow2_scale(vmax);
+    const float sc = pow2_scale(vmax);
+    if (lane == 0 && rscale) rscale[row] = sc;
+    if (row_image) {
+      // fp16(r * scale) at [128-row tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B] (what rvq_tc2.cu bulk-copies)
+      uint8_t* tile = row_image + (size_t)(row >> 7) * ((size_t)128 * D * 2);
+      const int r = row & 127;
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d2) {
+          const int k = 2 * c;
+          const __half2 h = __floats2half2_rn(v[i].x * sc, v[i].y * sc);
+          const uint32_t off = (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)r * 128u + ((uint32_t)(((k >> 3) ^ r) & 7) << 4) + (uint32_t)(k & 7) * 2u;
+          *reinterpret_cast<__half2*>(tile + off) = h;
+        }
+      }
+    }
   }
 }
 
@@ -202,28 +231,30 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
 }
 
 int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
-                      float* rscale, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
-  MT_CHECK_ARG(D <= 512, "rvq: dim %d must be <= 512", D);
+                      float* rscale, void* row_image, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
+  MT_CHECK_ARG(D <= 512 && D % 2 == 0, "rvq: dim %d must be even and <= 512", D);
+  MT_CHECK_ARG(row_image == nullptr || D % 64 == 0, "rvq: a row image needs dim %% 64 == 0");
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  const int per = ceil_div(D, 32);
-#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, packed, codes, Q, level, rscale, n_rows_dev, max_rows)
-  if (per <= 6) RU(6);
-  else RU(16);
+  const int per2 = ceil_div(D / 2, 32);
+#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+  if (per2 <= 3) RU(3);
+  else RU(8);
 #undef RU
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, const int* n_rows_dev, int max_rows,
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, const int* n_rows_dev, int max_rows,
                     cudaStream_t stream) {
-  MT_CHECK_ARG(D <= 512, "rvq: dim %d must be <= 512", D);
+  MT_CHECK_ARG(D <= 512 && D % 2 == 0, "rvq: dim %d must be even and <= 512", D);
+  MT_CHECK_ARG(row_image == nullptr || D % 64 == 0, "rvq: a row image needs dim %% 64 == 0");
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  const int per = ceil_div(D, 32);
-#define RP(P) rvq_update_kernel<P, false><<<blocks, 256, 0, stream>>>(rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, n_rows_dev, max_rows)
-  if (per <= 6) RP(6);
-  else RP(16);
+  const int per2 = ceil_div(D / 2, 32);
+#define RP(P) rvq_update_kernel<P, false><<<blocks, 256, 0, stream>>>(rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+  if (per2 <= 3) RP(3);
+  else RP(8);
 #undef RP
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;

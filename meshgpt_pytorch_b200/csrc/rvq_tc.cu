@@ -24,8 +24,11 @@
 //
 // Warp roles (384 threads): w0 bulk-copy producer, w1 MMA issuer, w2 TMEM allocator, w3 idle,
 // w4..w11 epilogue + row-tile loader (w4-7: rows 0-127, w8-11: rows 128-255; TMEM lane quarter = warp%4).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rvq_screen.cuh"
 #include "tc_common.cuh"
 #include <cuda_fp16.h>
 
@@ -40,7 +43,7 @@ constexpr int N_TILE = 128;        // codes per accumulator tile (UMMA N)
 constexpr int KC = 64;             // K elements per pipeline stage
 constexpr int STAGES = 6;
 constexpr int STAGE_BYTES = N_TILE * KC * 2;   // 16 KB
-constexpr int CHUNK = 8;                       // screening granularity: codes per candidate chunk
+constexpr int CHUNK = RVQ_CHUNK;               // screening granularity: codes per candidate chunk
 constexpr int MAX_SPLIT_CODES = 4096;          // e2 slice kept in shared memory per unit
 constexpr int NUM_THREADS = 384;
 constexpr int EPI_THREADS = 256;
@@ -65,10 +68,12 @@ struct SearchArgs {
   float escale;            // power-of-two codebook scale baked into the image
   const int* n_rows_dev;
   int max_rows, K, n_splits, tiles_per_split;
-  float4* partial;         // (R, n_splits): {best chunk minimum, its chunk id, second best, its chunk id}
+  float4* partial;         // (R, n_splits) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
+  int debug;               // timing experiments only (MESHTOK_RVQ_DEBUG): 1 = epilogue skips the TMEM loads, 2 = loads but no
+                           // math, 3 = every CTA walks its code tiles from a different start (no lockstep reads of one tile)
 };
 
-template <int D>
+template <int D, int DBG>
 __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using L = Smem<D>;
@@ -107,60 +112,67 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===== producer: stream codebook stages =====
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int u = u0; u < u1; ++u) {
-        const int tile0 = (u % a.n_splits) * a.tiles_per_split;
-        for (int t = 0; t < a.tiles_per_split; ++t) {
-          const uint8_t* src = a.image + (size_t)(tile0 + t) * KCHUNKS * STAGE_BYTES;
-          for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
-            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(&b_empty[s], ph ^ 1);
+    // ===== producer (warp-converged; one elected lane issues): stream codebook stages =====
+    uint32_t it = 0;
+    for (int u = u0; u < u1; ++u) {
+      const int tile0 = (u % a.n_splits) * a.tiles_per_split;
+      for (int t0 = 0; t0 < a.tiles_per_split; ++t0) {
+        const int t = DBG == 3 ? (t0 + (int)blockIdx.x * 5) % a.tiles_per_split : t0;
+        const uint8_t* src = a.image + (size_t)(tile0 + t) * KCHUNKS * STAGE_BYTES;
+        for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&b_empty[s], ph ^ 1);
+          if (elect_one()) {
             mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES);
             bulk_g2s(sB + s * STAGE_BYTES, src + (size_t)kc * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16_f32(128, N_TILE, /*bf16=*/false);
-      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
-      uint32_t it = 0, acc_it = 0, a_phase = 0;
-      int prev_m = -1;
-      for (int u = u0; u < u1; ++u) {
-        const int m_tile = u / a.n_splits;
-        if (m_tile != prev_m) {
-          mbar_wait(a_full, a_phase);
-          a_phase ^= 1;
-          prev_m = m_tile;
+    // ===== MMA issuer (warp-converged; one elected lane issues) =====
+    constexpr uint32_t idesc = make_idesc_f16_f32(128, N_TILE, /*bf16=*/false);
+    const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+    uint32_t it = 0, acc_it = 0, a_phase = 0;
+    int prev_m = -1;
+    for (int u = u0; u < u1; ++u) {
+      const int m_tile = u / a.n_splits;
+      if (m_tile != prev_m) {
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        prev_m = m_tile;
+        tcgen05_fence_after();
+      }
+      for (int t = 0; t < a.tiles_per_split; ++t, ++acc_it) {
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        tcgen05_fence_after();
+        for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&b_full[s], ph);
           tcgen05_fence_after();
-        }
-        for (int t = 0; t < a.tiles_per_split; ++t, ++acc_it) {
-          const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
-          mbar_wait(&acc_empty[buf], aph ^ 1);
-          tcgen05_fence_after();
-          for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
-            const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-            mbar_wait(&b_full[s], ph);
-            tcgen05_fence_after();
+          if (elect_one()) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
 #pragma unroll
               for (int k16 = 0; k16 < KC / 16; ++k16) {
-                const uint64_t da = make_smem_desc(sA_addr + h * L::HALF_BYTES + (kc * (KC / 8) + k16 * 2) * 128, 128, L::SBO_A);
-                const uint64_t db = make_smem_desc(sB_addr + s * STAGE_BYTES + k16 * 2 * 128, 128, SBO_B);
+                const uint64_t da = make_smem_desc_sw128(sA_addr + (kc * 2 + h) * STAGE_BYTES + k16 * 32);
+                const uint64_t db = make_smem_desc_sw128(sB_addr + s * STAGE_BYTES + k16 * 32);
                 umma_f16(tmem_base + (buf * 2 + h) * N_TILE, da, db, idesc, (kc | k16) != 0 ? 1u : 0u);
               }
             }
             umma_commit(&b_empty[s]);
           }
-          umma_commit(&acc_full[buf]);
+          __syncwarp();
         }
-        const int next_m = (u + 1 < u1) ? (u + 1) / a.n_splits : -1;
-        if (next_m != m_tile) umma_commit(a_empty);
+        if (elect_one()) umma_commit(&acc_full[buf]);
+        __syncwarp();
+      }
+      const int next_m = (u + 1 < u1) ? (u + 1) / a.n_splits : -1;
+      if (next_m != m_tile) {
+        if (elect_one()) umma_commit(a_empty);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -200,7 +212,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
           uint4 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
           pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-          const uint32_t off = (r >> 7) * L::HALF_BYTES + canon_offset(r & 127, k8 * 8, L::SBO_A);
+          // [k chunk of 64][row half][128 rows x 128 B, SWIZZLE_128B]
+          const uint32_t off = (uint32_t)(((k8 >> 3) * 2 + (r >> 7)) * STAGE_BYTES) + sw128_offset(r & 127, (k8 & 7) * 8);
           *reinterpret_cast<uint4*>(sA + off) = pk;
         }
         fence_proxy_async_smem();
@@ -212,12 +225,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
         prev_m = m_tile;
       }
 
-      float b1 = INFINITY, b2 = INFINITY;
-      int i1 = 0, i2 = 0;
+      RvqTop top;
+      top.reset();
       const long long my_row = (long long)m_tile * M_TILE + row_in_tile;
       // acc = <r * rscale, e * escale>  ->  -2 <r, e> = acc * cmul
       const float cmul = -2.f / ((my_row < n_rows ? __ldg(a.rscale + my_row) : 1.f) * a.escale);
-      for (int t = 0; t < a.tiles_per_split; ++t, ++acc_it) {
+      for (int t0 = 0; t0 < a.tiles_per_split; ++t0, ++acc_it) {
+        const int t = DBG == 3 ? (t0 + (int)blockIdx.x * 5) % a.tiles_per_split : t0;
         const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
         mbar_wait(&acc_full[buf], aph);
         tcgen05_fence_after();
@@ -228,27 +242,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
         // compare + rarely-taken branch per chunk); the re-score kernel evaluates every code of the winning
         // chunks exactly.  TMEM loads are double buffered: 32 columns are in flight while 32 are reduced.
         uint32_t va[32], vb[32];
+        if (DBG == 1) {   // experiment: how fast is the MMA pipeline when nobody reads the accumulators
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+          continue;
+        }
         tmem_ld32(taddr, va);
 #pragma unroll
         for (int c = 0; c < N_TILE / 32; ++c) {
           tmem_ld_wait();
           uint32_t(&v)[32] = (c & 1) ? vb : va;
           if (c + 1 < N_TILE / 32) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
-#pragma unroll
-          for (int j = 0; j < 32; j += CHUNK) {
-            const float4 e0 = *reinterpret_cast<const float4*>(e2t + c * 32 + j);
-            const float4 e1 = *reinterpret_cast<const float4*>(e2t + c * 32 + j + 4);
-            const float m0 = fminf(fminf(fmaf(__uint_as_float(v[j + 0]), cmul, e0.x), fmaf(__uint_as_float(v[j + 1]), cmul, e0.y)),
-                                   fminf(fmaf(__uint_as_float(v[j + 2]), cmul, e0.z), fmaf(__uint_as_float(v[j + 3]), cmul, e0.w)));
-            const float m1 = fminf(fminf(fmaf(__uint_as_float(v[j + 4]), cmul, e1.x), fmaf(__uint_as_float(v[j + 5]), cmul, e1.y)),
-                                   fminf(fmaf(__uint_as_float(v[j + 6]), cmul, e1.z), fmaf(__uint_as_float(v[j + 7]), cmul, e1.w)));
-            const float m = fminf(m0, m1);
-            if (m < b2) {
-              const int idx = chunk0 + (c * 32 + j) / CHUNK;
-              if (m < b1) { b2 = b1; i2 = i1; b1 = m; i1 = idx; }
-              else { b2 = m; i2 = idx; }
-            }
+          if (DBG == 2) {   // experiment: TMEM loads without the reduction
+            if (__uint_as_float(v[lane & 31]) == 123.456f) top.insert(0.f, c);
+            continue;
           }
+          rvq_screen32(v, e2t + c * 32, cmul, chunk0 + (c * 32) / CHUNK, top);
         }
         tcgen05_fence_before();
         __syncwarp();
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
       }
       const long long grow = (long long)m_tile * M_TILE + row_in_tile;
       if (grow < n_rows)
-        a.partial[(size_t)grow * a.n_splits + split] = make_float4(b1, __int_as_float(i1), b2, __int_as_float(i2));
+        top.store(a.partial + ((size_t)grow * a.n_splits + split) * RVQ_SLOT_F4);
     }
   }
 
@@ -274,12 +284,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
 // plus 2^-25 absolute per element that falls into the fp16 subnormal range after scaling  =: delta  (fp32
 // accumulation error is orders of magnitude below).  Every code whose true score ties the minimum therefore has
 // s~ <= min s~ + 2 delta; if some split's SECOND best is inside that window a third one may hide behind it and the
-// row is sent to the exact scan.
+// row is sent to the exact scan (with RVQ_TOPK kept chunks per slot: if the LAST of them is inside the window).
 template <int PER>
 __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
                                                           const float* __restrict__ e2, float max_norm, float escale,
                                                           const float* __restrict__ rscale,
-                                                          const float4* __restrict__ partial, int n_splits,
+                                                          const float4* __restrict__ partial, RvqPartialLayout lay,
                                                           const int* __restrict__ n_dev, int max_rows,
                                                           unsigned long long* __restrict__ packed,
                                                           int* __restrict__ amb_list, int* __restrict__ amb_count) {
@@ -299,8 +309,18 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
     const float xn = sqrtf(x2);
     const float delta = 0.001953125f * 1.01f * xn * max_norm +
                         5.96e-8f * sqrtf((float)D) * (max_norm / rscale[row] + xn / escale) + 1e-7f * (x2 + max_norm * max_norm);
+    // this row's candidate entries (see RvqPartialLayout)
+    int n_splits = lay.stride;
+    if (lay.mode == 2) {
+      const long long g = row >> 8;                                    // 256-row tile
+      const long long S = (long long)((n + 255) >> 8) * lay.T;
+      long long W = (S + lay.n_clusters - 1) / lay.n_clusters;
+      if (W < lay.w_min) W = lay.w_min;
+      n_splits = 2 * (int)((g * lay.T + lay.T - 1) / W - (g * lay.T) / W + 1);
+    }
+    const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
     float smin = INFINITY;
-    for (int s = lane; s < n_splits; s += 32) smin = fminf(smin, partial[(size_t)row * n_splits + s].x);
+    for (int s = lane; s < n_splits; s += 32) smin = fminf(smin, prow[s * RVQ_SLOT_F4].x);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
     const float window = smin + 2.f * delta;
@@ -308,13 +328,13 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
     float bd = INFINITY;
     int bi = 0x7fffffff;
     for (int s = 0; s < n_splits; ++s) {
-      const float4 p = partial[(size_t)row * n_splits + s];
-      if (p.z <= window) ambiguous = true;   // both kept chunks are inside the window: a third may hide behind them
+      const float4 p0 = prow[s * RVQ_SLOT_F4], p1 = prow[s * RVQ_SLOT_F4 + 1];
+      if (p1.z <= window) ambiguous = true;   // every kept chunk is inside the window: a further one may hide behind them
 #pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        const float sc = which ? p.z : p.x;
-        if (!(sc <= window)) continue;
-        const int code0 = __float_as_int(which ? p.w : p.y) * CHUNK;
+      for (int which = 0; which < RVQ_TOPK; ++which) {
+        const float sc = which == 0 ? p0.x : which == 1 ? p0.z : which == 2 ? p1.x : p1.z;
+        if (!(sc <= window)) break;           // ascending list
+        const int code0 = __float_as_int(which == 0 ? p0.y : which == 1 ? p0.w : which == 2 ? p1.y : p1.w) * CHUNK;
         // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
         float d[CHUNK];
 #pragma unroll
@@ -348,7 +368,7 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
   }
 }
 
-// fp32 codebook * escale -> fp16 image in stage order.
+// fp32 codebook * escale -> fp16 image in stage order: [128-code tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B].
 __global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ cb, int K, int D, float escale, uint8_t* __restrict__ image) {
   const long long total = (long long)K * (D / 8);  // 16-byte chunks
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -363,19 +383,19 @@ __global__ void __launch_bounds__(256) build_image_kernel(const float* __restric
     pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
     const int tile = code / N_TILE, r = code % N_TILE;
     const int kc = (k8 * 8) / KC, kin = (k8 * 8) % KC;
-    const size_t off = ((size_t)tile * (D / KC) + kc) * STAGE_BYTES + tc::canon_offset(r, kin, SBO_B);
+    const size_t off = ((size_t)tile * (D / KC) + kc) * STAGE_BYTES + tc::sw128_offset(r, kin);
     *reinterpret_cast<uint4*>(image + off) = pk;
   }
 }
 
-template <int D>
+template <int D, int DBG>
 int launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc_search_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D>::TOTAL));
+    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D>::TOTAL));
     configured = true;
   }
-  rvq_tc_search_kernel<D><<<grid, NUM_THREADS, Smem<D>::TOTAL, stream>>>(a);
+  rvq_tc_search_kernel<D, DBG><<<grid, NUM_THREADS, Smem<D>::TOTAL, stream>>>(a);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
@@ -411,7 +431,7 @@ int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan) {
   plan->tiles_per_split = tiles / best_ns;
   plan->units = m_tiles * best_ns;
   plan->grid = min(plan->units, 148);
-  plan->partial_bytes = align_up((size_t)max(max_rows, 1) * best_ns * sizeof(float4), 256);
+  plan->partial_bytes = align_up((size_t)max(max_rows, 1) * best_ns * RVQ_SLOT_F4 * sizeof(float4), 256);
   return MESHTOK_OK;
 }
 
@@ -420,22 +440,31 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
   if (max_rows == 0) return MESHTOK_OK;
   SearchArgs a;
   a.rows = rows; a.rscale = rscale; a.escale = escale; a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.n_rows_dev = n_rows_dev;
+  static int debug = -1;
+  if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
+  a.debug = debug;
   a.max_rows = max_rows; a.K = K; a.n_splits = plan.n_splits; a.tiles_per_split = plan.tiles_per_split; a.partial = partial;
   switch (D) {
-    case 64: return launch_search<64>(a, plan.grid, stream);
-    case 128: return launch_search<128>(a, plan.grid, stream);
-    case 192: return launch_search<192>(a, plan.grid, stream);
+    case 64: return launch_search<64, 0>(a, plan.grid, stream);
+    case 128: return launch_search<128, 0>(a, plan.grid, stream);
+    case 192:
+      switch (a.debug) {   // timing experiments (MESHTOK_RVQ_DEBUG), D = 192 only
+        case 1: return launch_search<192, 1>(a, plan.grid, stream);
+        case 2: return launch_search<192, 2>(a, plan.grid, stream);
+        case 3: return launch_search<192, 3>(a, plan.grid, stream);
+      }
+      return launch_search<192, 0>(a, plan.grid, stream);
   }
   set_error("tcgen05 RVQ search: unsupported dim %d", D);
   return MESHTOK_ERR_UNSUPPORTED;
 }
 
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, int n_splits, const int* n_rows_dev, int max_rows,
+                       float escale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, n_splits, n_rows_dev, max_rows, packed,
+  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, layout, n_rows_dev, max_rows, packed,
                                                     amb_list, amb_count);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;

@@ -1,0 +1,377 @@
+// K8a, CTA-pair version: residual-VQ nearest-codebook screening with tcgen05.mma.cta_group::2.
+//
+// Same contract as rvq_tc.cu (fp16 screening GEMM  s~[r, j] = |e_j|^2 - 2 <fp16(r), fp16(e_j)>  with fp32 accumulation
+// in TMEM, two best 8-code chunks kept per (row, partial slot), exact fp32 decision by rvq_rescore_kernel), replacing
+// the EuclideanCodebook distance + argmax of vector_quantize_pytorch.ResidualVQ called at meshgpt_pytorch.py:842.
+//
+// Why a second version: ncu on the single-CTA kernel (profiles/r01d_*) showed the tensor pipe active only 48 % of the
+// time with neither the epilogue nor L2 the limiter - an M=128 x N=128 MMA needs 8 KB of shared-memory operands per 64
+// cycles, the full 128 B/cycle of one SM, before the bulk copies and the epilogue touch shared memory at all.  Here two
+// CTAs of a cluster (one TPC) issue ONE M=256 x N=256 MMA per K step: every CTA stages its own 128 residual rows and
+// its own 128 codes of the 256-code tile, i.e. 8 KB per 128 cycles = half the operand traffic per SM, while the
+// codebook bytes pulled from L2 per row stay the same as before.
+//   * row tile: 128 rows per CTA, fp16 pre-scaled image written by the residual prep / update kernels, one 48 KB bulk
+//     copy (no register staging, no conversion here);
+//   * codebook: 8-stage ring of 16 KB stages (128 codes x 64 dims) per CTA from the same image rvq_tc.cu uses
+//     (CTA rank r takes image tile 2t + r);
+//   * accumulators: 2 buffers x 256 columns of TMEM in each CTA (lanes = the CTA's 128 rows);
+//   * work split: the (row-pair-tile x code-pair-tile) steps of the whole problem are cut into equal contiguous ranges,
+//     one per cluster ("stream-K"), so the load is balanced to one step whatever the row count; a row tile cut by a
+//     range boundary simply produces one more partial slot;
+//   * synchronisation: the leader CTA (cluster rank 0) issues all MMAs.  Its full barriers count two arrivals: its own
+//     producer's expect_tx and a remote arrive forwarded by the peer CTA once the peer's copy has landed; stage /
+//     row-tile / accumulator releases are tcgen05.commit multicasts to both CTAs; the peer's epilogue warps release
+//     the accumulator with remote arrives.
+// Warp roles (384 threads per CTA): w0 producer, w1 MMA issuer (leader only), w2 TMEM allocator, w3 completion
+// forwarder (peer only), w4..w11 epilogue (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "rvq_screen.cuh"
+#include "tc_common.cuh"
+
+namespace meshtok {
+
+namespace {
+
+using namespace tc;
+
+constexpr int M_CTA = 128;         // residual rows per CTA
+constexpr int M_PAIR = 256;        // rows per cluster step
+constexpr int N_CTA = 128;         // codes staged per CTA and stage (one tile of the codebook image)
+constexpr int N_PAIR = 256;        // codes per MMA
+constexpr int KC = 64;             // K elements per pipeline stage
+constexpr int STAGES = 10;
+constexpr int STAGE_BYTES = N_CTA * KC * 2;    // 16 KB
+constexpr int CHUNK = RVQ_CHUNK;
+constexpr int NUM_THREADS = 384;
+constexpr int EPI_WARPS = 8;
+constexpr uint32_t SBO_B = (KC / 8) * 128;     // 1024
+constexpr int E2_RING = 8;        // |e|^2 slices in flight: > stages / stages-per-tile + 2 accumulators + 1
+constexpr int W_MIN = 16;          // fewest steps a cluster takes (bounds the partial slots per row)
+
+template <int D>
+struct Smem2 {
+  static constexpr uint32_t SBO_A = (D / 8) * 128;
+  static constexpr uint32_t A_BYTES = M_CTA * D * 2;
+  static constexpr uint32_t B_OFF = A_BYTES;
+  static constexpr uint32_t E2_OFF = B_OFF + STAGES * STAGE_BYTES;          // ring of E2_RING x 256 floats
+  static constexpr uint32_t BAR_OFF = E2_OFF + E2_RING * N_PAIR * 4;
+  static constexpr uint32_t TOTAL = BAR_OFF + 512;
+};
+
+struct Search2Args {
+  const uint8_t* rimg;     // fp16 image of the scaled residuals: [128-row tile] x canonical (128 x D), see rvq_row_image_*
+  const uint8_t* image;    // fp16 codebook image: [K/128 tiles][D/64 chunks][16 KB canonical stage]
+  const float* e2;         // (K) |e_j|^2
+  const float* rscale;     // (R) power-of-two row scales baked into rimg
+  float escale;            // power-of-two codebook scale baked into the image
+  const int* n_rows_dev;
+  int max_rows, T, max_slots;   // T = K / 256 code-pair-tiles
+  float4* partial;         // (R, 2 * max_slots) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
+};
+
+__device__ __forceinline__ int steps_per_cluster(long long S, int n_clusters) {
+  const long long w = (S + n_clusters - 1) / n_clusters;
+  return (int)(w < W_MIN ? W_MIN : w);
+}
+
+template <int D, int DBG>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_tc2_search_kernel(Search2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using L = Smem2<D>;
+  constexpr int KCH = D / KC;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + L::B_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* b_full = bars;                   // [STAGES]
+  uint64_t* b_empty = bars + STAGES;         // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;    // [2]
+  uint64_t* acc_empty = acc_full + 2;        // [2]  (the leader's are the ones waited on)
+  uint64_t* a_full = acc_empty + 2;
+  uint64_t* a_empty = a_full + 1;
+  uint64_t* e2_full = a_empty + 1;           // [E2_RING]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e2_full + E2_RING);
+  float* sE2 = reinterpret_cast<float*>(smem + L::E2_OFF);
+
+  const int warp = warp_id(), lane = lane_id();
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_rows = min(*a.n_rows_dev, a.max_rows);
+  const int G = (n_rows + M_PAIR - 1) / M_PAIR;
+  const int T = a.T;
+  const long long S = (long long)G * T;
+  const int n_clusters = gridDim.x >> 1;
+  const int cid = blockIdx.x >> 1;
+  const int W = steps_per_cluster(S, n_clusters);
+  const long long lo = min(S, (long long)cid * W), hi = min(S, lo + W);
+
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], leader ? 2 : 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
+    mbar_init(a_full, leader ? 2 : 1);
+    mbar_init(a_empty, 1);
+    for (int i = 0; i < E2_RING; ++i) mbar_init(&e2_full[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer (both CTAs; warp-converged, one elected lane issues): own row tile + own half of every stage =====
+    uint32_t it = 0, a_cnt = 0, tile_it = 0;
+    int prev_g = -1;
+    for (long long step = lo; step < hi; ++step, ++tile_it) {
+      const int g = (int)(step / T), t = (int)(step % T);
+      // |e|^2 of the tile's 256 codes for the epilogue.  The ring slot was last used E2_RING tiles ago; the stage ring (and
+      // behind it the accumulator ring) keeps this warp fewer tiles than that ahead of the epilogue, so the slot is free.
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&e2_full[tile_it % E2_RING], N_PAIR * 4);
+        bulk_g2s(sE2 + (tile_it % E2_RING) * N_PAIR, a.e2 + (size_t)t * N_PAIR, N_PAIR * 4, &e2_full[tile_it % E2_RING]);
+      }
+      __syncwarp();
+      if (g != prev_g) {
+        if (a_cnt > 0) mbar_wait(a_empty, (a_cnt - 1) & 1);   // MMAs on the previous row tile are complete
+        if (elect_one()) {
+          mbar_arrive_expect_tx(a_full, L::A_BYTES);
+          bulk_g2s(sA, a.rimg + (size_t)(2 * g + (int)rank) * L::A_BYTES, L::A_BYTES, a_full);
+        }
+        __syncwarp();
+        ++a_cnt;
+        prev_g = g;
+      }
+      const uint8_t* src = a.image + (size_t)(2 * t + (int)rank) * KCH * STAGE_BYTES;
+      for (int kc = 0; kc < KCH; ++kc, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(&b_empty[s], ph ^ 1);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES);
+          bulk_g2s(sB + s * STAGE_BYTES, src + (size_t)kc * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
+        }
+        __syncwarp();
+      }
+    }
+    // drain: every multicast commit aimed at this CTA has landed before the CTA may exit
+    const uint32_t pending = it < (uint32_t)STAGES ? it : (uint32_t)STAGES;
+    for (uint32_t i = 0; i < pending; ++i) {
+      const uint32_t j = it - 1 - i;
+      mbar_wait(&b_empty[j % STAGES], (j / STAGES) & 1);
+    }
+    if (a_cnt > 0) mbar_wait(a_empty, (a_cnt - 1) & 1);
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only; warp-converged, one elected lane issues): M=256 x N=256 x K=16 per MMA =====
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc_f16_f32(M_PAIR, N_PAIR, /*bf16=*/false);
+      const uint32_t sA_addr = smem_u32(sA), sB_addr = smem_u32(sB);
+      uint32_t it = 0, acc_it = 0, a_phase = 0;
+      int prev_g = -1;
+      for (long long step = lo; step < hi; ++step, ++acc_it) {
+        const int g = (int)(step / T);
+        if (g != prev_g) {
+          mbar_wait(a_full, a_phase);
+          a_phase ^= 1;
+          prev_g = g;
+          tcgen05_fence_after();
+        }
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
+        tcgen05_fence_after();
+        for (int kc = 0; kc < KCH; ++kc, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(&b_full[s], ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int k16 = 0; k16 < KC / 16; ++k16) {
+              const uint64_t da = make_smem_desc_sw128(sA_addr + kc * STAGE_BYTES + k16 * 32);
+              const uint64_t db = make_smem_desc_sw128(sB_addr + s * STAGE_BYTES + k16 * 32);
+              umma_f16_pair(tmem_base + buf * N_PAIR, da, db, idesc, (kc | k16) != 0 ? 1u : 0u);
+            }
+            umma_commit_pair_mc(&b_empty[s], 3);
+          }
+          __syncwarp();
+        }
+        const int next_g = (step + 1 < hi) ? (int)((step + 1) / T) : -1;
+        if (elect_one()) {
+          umma_commit_pair_mc(&acc_full[buf], 3);
+          if (next_g != g) umma_commit_pair_mc(a_empty, 3);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 3) {
+    // ===== completion forwarder (peer CTA only): tells the leader that this CTA's copies have landed.  Lane s follows
+    // stage s, lane STAGES follows the row tile, so the remote arrives of different stages overlap. =====
+    if (!leader) {
+      const uint32_t total_it = (uint32_t)(hi - lo) * KCH;
+      const uint32_t n_a = hi > lo ? (uint32_t)((hi - 1) / T - lo / T + 1) : 0u;
+      if (lane < STAGES) {
+        const uint32_t remote = mapa_shared(smem_u32(&b_full[lane]), 0);
+        uint32_t ph = 0;
+        for (uint32_t it = lane; it < total_it; it += STAGES, ph ^= 1) {
+          mbar_wait(&b_full[lane], ph);
+          mbar_arrive_cluster(remote);
+        }
+      } else if (lane == STAGES) {
+        const uint32_t remote = mapa_shared(smem_u32(a_full), 0);
+        for (uint32_t i = 0; i < n_a; ++i) {
+          mbar_wait(a_full, i & 1);
+          mbar_arrive_cluster(remote);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): running two best 8-code chunks per row and column half =====
+    const int ew = warp - 4;
+    const int q = warp & 3;                  // TMEM lane quarter this warp may read
+    const int chalf = ew >> 2;               // columns [chalf * 128, +128) of the 256-code tile
+    const int row_in_cta = q * 32 + lane;
+    const uint32_t acc_empty_remote0 = mapa_shared(smem_u32(&acc_empty[0]), 0);
+    const uint32_t acc_empty_remote1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
+    uint32_t acc_it = 0;
+    int prev_g = -1;
+    float cmul = 0.f;
+    RvqTop top;
+    top.reset();
+    long long my_row = 0;
+    auto flush = [&](int g) {
+      if (my_row < n_rows) {
+        const int slot = 2 * (cid - (int)(((long long)g * T) / W)) + chalf;
+        top.store(a.partial + ((size_t)my_row * (2 * a.max_slots) + slot) * RVQ_SLOT_F4);
+      }
+    };
+    for (long long step = lo; step < hi; ++step, ++acc_it) {
+      const int g = (int)(step / T), t = (int)(step % T);
+      if (g != prev_g) {
+        if (prev_g >= 0) flush(prev_g);
+        prev_g = g;
+        my_row = (long long)g * M_PAIR + (long long)rank * M_CTA + row_in_cta;
+        // acc = <r * rscale, e * escale>  ->  -2 <r, e> = acc * cmul
+        cmul = -2.f / ((my_row < n_rows ? __ldg(a.rscale + my_row) : 1.f) * a.escale);
+        top.reset();
+      }
+      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      mbar_wait(&acc_full[buf], aph);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * N_PAIR + chalf * 128;
+      const int code0 = t * N_PAIR + chalf * 128;
+      uint32_t va[32], vb[32];
+      if (DBG == 1) {   // timing experiment: nobody reads the accumulators
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[buf]);
+          else mbar_arrive_cluster_relaxed(buf ? acc_empty_remote1 : acc_empty_remote0);
+        }
+        continue;
+      }
+      tmem_ld32(taddr, va);
+      mbar_wait(&e2_full[acc_it % E2_RING], (acc_it / E2_RING) & 1);
+      const float* e2t = sE2 + (acc_it % E2_RING) * N_PAIR + chalf * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_ld_wait();
+        uint32_t(&v)[32] = (c & 1) ? vb : va;
+        if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
+        rvq_screen32(v, e2t + c * 32, cmul, (code0 + c * 32) / CHUNK, top);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) {   // the TMEM reads are complete (wait::ld); no data is handed over through memory, hence relaxed
+        if (leader) mbar_arrive(&acc_empty[buf]);
+        else mbar_arrive_cluster_relaxed(buf ? acc_empty_remote1 : acc_empty_remote0);
+      }
+    }
+    if (prev_g >= 0) flush(prev_g);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // nothing of the pair is still in flight towards either CTA
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+template <int D, int DBG>
+int launch_search2(const Search2Args& a, int grid, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc2_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2<D>::TOTAL));
+    configured = true;
+  }
+  rvq_tc2_search_kernel<D, DBG><<<grid, NUM_THREADS, Smem2<D>::TOTAL, stream>>>(a);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int sm_pairs() {
+  static int pairs = 0;
+  if (pairs == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 2) sms = 148;
+    pairs = sms / 2;
+  }
+  return pairs;
+}
+
+}  // namespace
+
+int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan) {
+  memset(plan, 0, sizeof(*plan));
+  if (K % N_PAIR != 0 || (D != 64 && D != 128 && D != 192)) {
+    set_error("tcgen05 CTA-pair RVQ search supports codebook_size %% 256 == 0 and dim in {64,128,192} (got K=%d, D=%d)", K, D);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  plan->T = K / N_PAIR;
+  plan->n_clusters = sm_pairs();
+  plan->max_slots = (plan->T - 1) / W_MIN + 2;
+  const size_t rows_padded = (size_t)ceil_div(max(max_rows, 1), M_PAIR) * M_PAIR;
+  plan->partial_bytes = align_up(rows_padded * 2 * plan->max_slots * RVQ_SLOT_F4 * sizeof(float4), 256);
+  plan->row_image_bytes = align_up(rows_padded * D * 2, 256);
+  return MESHTOK_OK;
+}
+
+int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+                          const int* n_rows_dev, int max_rows, const RvqTc2Plan& plan, float4* partial, cudaStream_t stream) {
+  if (max_rows == 0) return MESHTOK_OK;
+  Search2Args a;
+  a.rimg = static_cast<const uint8_t*>(row_image); a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.rscale = rscale;
+  a.escale = escale; a.n_rows_dev = n_rows_dev; a.max_rows = max_rows; a.T = plan.T; a.max_slots = plan.max_slots; a.partial = partial;
+  // enough clusters for the worst case, never more than the machine has SM pairs
+  const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
+  const int clusters = (int)min((long long)plan.n_clusters, (steps + W_MIN - 1) / W_MIN);
+  const int grid = 2 * max(1, clusters);
+  switch (D) {
+    case 64: return launch_search2<64, 0>(a, grid, stream);
+    case 128: return launch_search2<128, 0>(a, grid, stream);
+    case 192: {
+      static int debug = -1;
+      if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
+      return debug == 1 ? launch_search2<192, 1>(a, grid, stream) : launch_search2<192, 0>(a, grid, stream);
+    }
+  }
+  set_error("tcgen05 CTA-pair RVQ search: unsupported dim %d", D);
+  return MESHTOK_ERR_UNSUPPORTED;
+}
+
+// partial-slot enumeration shared with the re-score kernel (must mirror the kernel's work split)
+RvqPartialLayout rvq_tc2_partial_layout(const RvqTc2Plan& plan, int max_rows) {
+  RvqPartialLayout l;
+  l.mode = 2;
+  l.stride = 2 * plan.max_slots;
+  l.T = plan.T;
+  const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
+  l.n_clusters = max(1, (int)min((long long)plan.n_clusters, (steps + W_MIN - 1) / W_MIN));
+  l.w_min = W_MIN;
+  return l;
+}
+
+}  // namespace meshtok

@@ -52,6 +52,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a fully converged warp (the lowest).  Role loops run warp-converged and wrap only the single-thread
+// instructions (bulk copies, MMAs, commits) in `if (elect_one())`: issued from a diverged `if (lane == 0)` region the
+// compiler has to move every descriptor into uniform registers with an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence per
+// instruction, which made the MMA issue thread - not the tensor pipe - the limiter (profiles/r01d_stalls_rvq_tc_search.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / bulk copy -----------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -106,6 +120,77 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA pairs (cta_group::2): one MMA spans two SMs of a cluster ------------------------------------------
+// Each CTA stages its own 128 rows of A and its own half of B; the leader CTA (cluster rank 0) issues the MMA for the
+// pair, which halves the shared-memory operand traffic per SM compared with two independent M=128 MMAs.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` (a shared::cta address) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded like mbar_wait; acquire at cluster scope (the barrier is also arrived on by the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("meshtok: cluster mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {  // the same warp in BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A . B^T over the CTA pair (M = 256: 128 rows per CTA; N codes split across the CTAs' smem)
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier at this shared-memory offset in every CTA of `cta_mask` once all tcgen05 ops issued so far
+// by this thread have completed
+__device__ __forceinline__ void umma_commit_pair_mc(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // ---- descriptors -----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (sm_100 "version 1"), SWIZZLE_NONE, K-major.
 //   [0,14) start address >> 4   [16,30) LBO >> 4   [32,46) SBO >> 4   [46,48) version = 1
@@ -123,6 +208,25 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int M, int N, bool bf16) {
   return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---- SWIZZLE_128B K-major tiles (16-bit elements) ---------------------------------------------------------
+// A tile is [rows][64 elements] = rows of 128 bytes; the 16-byte chunk c of row r is stored at chunk c ^ (r & 7)
+// (Swizzle<3,4,3> on the byte address), 8-row groups are 1024 B apart, and the tile base must be 1024-byte aligned.
+// One MMA K step (16 elements) advances the descriptor start address by 32 bytes inside the 128-byte row.
+constexpr int SW128_K = 64;
+__host__ __device__ constexpr uint32_t sw128_offset(int r, int k) {
+  return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(((k >> 3) ^ r) & 7) << 4) + static_cast<uint32_t>(k & 7) * 2u;
+}
+//   [0,14) start address >> 4   [16,30) LBO >> 4 = 1 (unused)   [32,46) SBO >> 4 = 64   [46,48) version = 1   [61,64) = 2
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024u >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
 
 // byte offset of element (row r, column k) of a K-major canonical tile whose 8-row groups are `sbo` apart
