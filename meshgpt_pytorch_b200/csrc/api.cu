@@ -61,6 +61,7 @@ struct Workspace {
   int* amb_count;
   float4* partial;
   uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
+  float* ssq;        // (B*F, 8): parts of the squared row norms of the last SAGE layer (deferred normalisation)
   size_t total;
 };
 
@@ -161,6 +162,7 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->img_x[0] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_x[1] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
+  w->ssq = c.take<float>(BF * 8);
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
   w->avg = c.take<float>(BV * D, &t->averaged);
@@ -419,6 +421,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   const int L = m->num_sage_layers;
   const float* enc = nullptr;
   const uint8_t* enc_img = w.img_x[0];
+  const float* enc_ssq = nullptr;   // set when the encoder left its output rows un-normalised (deferred to project_dim_codebook)
+  int enc_ssq_parts = 0;
   if (a->encoded_in == nullptr) {
     FeatParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -454,16 +458,31 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       const meshtok_sage_layer& ly = m->sage[l];
       const bool first = l == 0, last = l == L - 1;
       const int mode = first ? 2 : 1;
-      const bool fused = !simt && !last && linear_tc_fused_norm_ok(ly.dim_out, mode) == MESHTOK_OK;
+      const bool fused = !simt && linear_tc_fused_norm_ok(ly.dim_out, mode) == MESHTOK_OK;
+      // a last layer too wide for the fused epilogue leaves its rows un-normalised (image + squared norms) and
+      // project_dim_codebook divides by the norm in ITS epilogue: W (x / |x|) + b = (W x) / |x| + b
+      const bool deferred = !simt && !fused && last && !first && linear_tc_ssq_parts(ly.dim_out) <= 8;
+      const bool need_fp32 = a->keep_taps || (last && (a->encoded_out != nullptr || a->stop_after_encode));
       // xp = relu(lin(x))
       { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
       { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {
-        LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1]};
+        LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1], nullptr, nullptr, 0};
         ProfScope ps(PROF_SAGE_LINEAR, s);
         if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
-                         a->keep_taps ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;
+                         need_fp32 ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;
+      } else if (deferred) {
+        LinearRowEpilogue epi{0, nullptr, nullptr, w.img_x[cur ^ 1], w.ssq, nullptr, 0};
+        { ProfScope ps(PROF_SAGE_LINEAR, s);
+          if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
+                           need_fp32 ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc; }
+        enc_ssq = w.ssq;
+        enc_ssq_parts = linear_tc_ssq_parts(ly.dim_out);
+        if (need_fp32) {   // encode() / the parity taps want the normalised fp32 rows
+          ProfScope ps(PROF_SAGE_NORM, s);
+          if ((rc = launch_row_norm(w.layer_out[l], ly.dim_out, nullptr, nullptr, nullptr, w.counts, max_rows, s)) != MESHTOK_OK) return rc;
+        }
       } else {
         { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, w.agg, w.img_agg, ly.dim_in, x, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, w.layer_out[l], ly.dim_out, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
         { ProfScope ps(PROF_SAGE_NORM, s);
@@ -488,7 +507,10 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   if (a->stop_after_encode) return MESHTOK_OK;
 
   // ---- quantize -------------------------------------------------------------------------------
-  { ProfScope ps(PROF_PDC_LINEAR, s); if ((rc = linear(simt, enc, enc_img, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s)) != MESHTOK_OK) return rc; }
+  { ProfScope ps(PROF_PDC_LINEAR, s);
+    LinearRowEpilogue epi{0, nullptr, nullptr, nullptr, nullptr, enc_ssq, enc_ssq_parts};
+    if ((rc = linear(simt, enc, enc_img, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s,
+                     enc_ssq ? &epi : nullptr)) != MESHTOK_OK) return rc; }
   { ProfScope ps(PROF_SCATTER_MEAN, s); if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, s)) != MESHTOK_OK) return rc; }
   const float* pad_row = nullptr;
   if (m->use_lfq) {

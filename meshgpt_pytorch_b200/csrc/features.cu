@@ -37,88 +37,118 @@ __device__ __forceinline__ void unit3(const float v[3], float out[3]) {
   out[2] = __fdiv_rn(v[2], d);
 }
 
+// Two phases per chunk of ROWS face rows (small chunks so that the grid-stride loop balances over the SMs):
+//   1. one THREAD per face: gather the corner positions, derive the features, discretise -> NSLOT bin ids in shared memory
+//      (no lane repeats another lane's acosf / sqrt / divide);
+//   2. one WARP per face, two faces in flight: x0[row] = bias + sum_s table_s[bin_s] in fixed slot order, 16 B per lane and
+//      table row (the tables are L2 resident; the kernel is bound by the latency of these reads, so a lane keeps
+//      2 faces x NSLOT independent 16-byte loads in flight).
 template <int NVF>
 __global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
-  const int lane = lane_id();
-  const int warps_per_block = blockDim.x >> 5;
-  const int n_rows = p.counts->n_faces;
   constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
-  for (int row = blockIdx.x * warps_per_block + warp_id(); row < n_rows; row += gridDim.x * warps_per_block) {
-    const int pf = p.row_face[row];
-    const int b = pf / p.F;
-    const int64_t* fptr = p.faces + (size_t)pf * NVF;
-    float pos[NVF][3];
+  constexpr int ROWS = 64;
+  constexpr int RPW = ROWS / 8;   // rows per warp in phase 2
+  __shared__ unsigned short sbins[ROWS][NSLOT];
+  __shared__ int spf[ROWS];
+  const int lane = lane_id(), warp = warp_id();
+  const int n_rows = p.counts->n_faces;
+  const int D = p.D, d4 = D >> 2;
+  for (int base = blockIdx.x * ROWS; base < n_rows; base += gridDim.x * ROWS) {
+    // ---- phase 1 ----
+    const int row = base + threadIdx.x;
+    if (threadIdx.x < ROWS && row < n_rows) {
+      const int pf = p.row_face[row];
+      const int b = pf / p.F;
+      const int64_t* fptr = p.faces + (size_t)pf * NVF;
+      float pos[NVF][3];
 #pragma unroll
-    for (int k = 0; k < NVF; ++k) {
-      const long long v = fptr[k];
-      const float* src = p.vertices + ((size_t)b * p.V + (size_t)v) * 3;
-      pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
-    }
-    int bins[NSLOT];
-    // coordinates: slot = vertex*3 + xyz (meshgpt_pytorch.py:732-733)
+      for (int k = 0; k < NVF; ++k) {
+        const long long v = fptr[k];
+        const float* src = p.vertices + ((size_t)b * p.V + (size_t)v) * 3;
+        pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
+      }
+      unsigned short* bins = sbins[threadIdx.x];
+      // coordinates: slot = vertex*3 + xyz (meshgpt_pytorch.py:732-733)
 #pragma unroll
-    for (int k = 0; k < NVF; ++k)
+      for (int k = 0; k < NVF; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          bins[k * 3 + c] = (unsigned short)discretize_rn(pos[k][c], p.coor_lo, p.coor_den, (float)p.n_coor, p.n_coor);
+      // angles between position vectors k and k-1 (meshgpt_pytorch.py:151-153, 164-166)
+      float un[NVF][3];
+#pragma unroll
+      for (int k = 0; k < NVF; ++k) unit3(pos[k], un[k]);
+#pragma unroll
+      for (int k = 0; k < NVF; ++k) {
+        const int km = (k + NVF - 1) % NVF;
+        float z = __fadd_rn(__fadd_rn(__fmul_rn(un[k][0], un[km][0]), __fmul_rn(un[k][1], un[km][1])), __fmul_rn(un[k][2], un[km][2]));
+        z = (z != z) ? z : fminf(fmaxf(z, p.clip_lo), p.clip_hi);  // torch.clamp propagates NaN
+        bins[NVF * 3 + k] = (unsigned short)discretize_rn(acosf(z), 0.f, p.angle_den, (float)p.n_angle, p.n_angle);
+      }
+      // edges: rows 0 and 1 of (p - prev); prev = one step back (tri) / two steps back (quad) (:168-172)
+      constexpr int SH = (NVF == 3) ? 1 : 2;
+      float e1[3], e2[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        e1[c] = __fsub_rn(pos[0][c], pos[(0 + NVF - SH) % NVF][c]);
+        e2[c] = __fsub_rn(pos[1][c], pos[(1 + NVF - SH) % NVF][c]);
+      }
+      float cr[3];
+      cr[0] = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
+      cr[1] = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
+      cr[2] = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
+      const float cn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cr[0], cr[0]), __fmul_rn(cr[1], cr[1])), __fmul_rn(cr[2], cr[2])));
+      bins[NVF * 4] = (unsigned short)discretize_rn(__fmul_rn(cn, 0.5f), 0.f, p.area_den, (float)p.n_area, p.n_area);
+      const float cd = fmaxf(cn, 1e-12f);
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        bins[k * 3 + c] = discretize_rn(pos[k][c], p.coor_lo, p.coor_den, (float)p.n_coor, p.n_coor);
-    // angles between position vectors k and k-1 (meshgpt_pytorch.py:151-153, 164-166)
-    float un[NVF][3];
+        bins[NVF * 4 + 1 + c] = (unsigned short)discretize_rn(__fdiv_rn(cr[c], cd), p.coor_lo, p.coor_den, (float)p.n_normal, p.n_normal);
+      spf[threadIdx.x] = pf;
+      if (p.face_coords_out) {
 #pragma unroll
-    for (int k = 0; k < NVF; ++k) unit3(pos[k], un[k]);
-#pragma unroll
-    for (int k = 0; k < NVF; ++k) {
-      const int km = (k + NVF - 1) % NVF;
-      float z = __fadd_rn(__fadd_rn(__fmul_rn(un[k][0], un[km][0]), __fmul_rn(un[k][1], un[km][1])), __fmul_rn(un[k][2], un[km][2]));
-      z = (z != z) ? z : fminf(fmaxf(z, p.clip_lo), p.clip_hi);  // torch.clamp propagates NaN
-      bins[NVF * 3 + k] = discretize_rn(acosf(z), 0.f, p.angle_den, (float)p.n_angle, p.n_angle);
-    }
-    // edges: rows 0 and 1 of (p - prev); prev = one step back (tri) / two steps back (quad) (:168-172)
-    constexpr int SH = (NVF == 3) ? 1 : 2;
-    float e1[3], e2[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      e1[c] = __fsub_rn(pos[0][c], pos[(0 + NVF - SH) % NVF][c]);
-      e2[c] = __fsub_rn(pos[1][c], pos[(1 + NVF - SH) % NVF][c]);
-    }
-    float cr[3];
-    cr[0] = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
-    cr[1] = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
-    cr[2] = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
-    const float cn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cr[0], cr[0]), __fmul_rn(cr[1], cr[1])), __fmul_rn(cr[2], cr[2])));
-    bins[NVF * 4] = discretize_rn(__fmul_rn(cn, 0.5f), 0.f, p.area_den, (float)p.n_area, p.n_area);
-    const float cd = fmaxf(cn, 1e-12f);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      bins[NVF * 4 + 1 + c] = discretize_rn(__fdiv_rn(cr[c], cd), p.coor_lo, p.coor_den, (float)p.n_normal, p.n_normal);
-
-    if (p.face_coords_out && lane < NVF * 3) {
-      int v = 0;
-#pragma unroll
-      for (int s = 0; s < NVF * 3; ++s) v = (s == lane) ? bins[s] : v;
-      p.face_coords_out[(size_t)pf * (NVF * 3) + lane] = v;
-    }
-
-    // x0[row] = bias + sum_s table_s[bin_s]   (fixed slot order; 2 columns per lane per 64-col group)
-    const int D = p.D;
-    for (int c0 = 2 * lane; c0 < D; c0 += 64) {
-      float2 acc = *reinterpret_cast<const float2*>(p.bias + c0);
-#pragma unroll
-      for (int s = 0; s < NSLOT; ++s) {
-        const float2 t = __ldg(reinterpret_cast<const float2*>(p.tables + ((size_t)(p.slot_off[s] + bins[s])) * D + c0));
-        acc.x += t.x;
-        acc.y += t.y;
+        for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[(size_t)pf * (NVF * 3) + s] = bins[s];
       }
-      if (p.x0) *reinterpret_cast<float2*>(p.x0 + (size_t)row * D + c0) = acc;
-      if (p.x0_image) tc::image_store2(p.x0_image, D, row, c0, acc.x, acc.y);
     }
+    __syncthreads();
+    // ---- phase 2 ----
+    const int rows_here = min(ROWS, n_rows - base);
+    for (int r0 = warp * RPW; r0 < min(rows_here, warp * RPW + RPW); r0 += 2) {
+      const bool two = r0 + 1 < rows_here;
+      const unsigned short* ba = sbins[r0];
+      const unsigned short* bb = sbins[two ? r0 + 1 : r0];
+      for (int i4 = lane; i4 < d4; i4 += 32) {
+        const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bias) + i4);
+        float4 acc_a = bias, acc_b = bias;
+        float4 ta[NSLOT], tb[NSLOT];
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          ta[s] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)(p.slot_off[s] + ba[s]) * D) + i4);
+          tb[s] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)(p.slot_off[s] + bb[s]) * D) + i4);
+        }
+#pragma unroll
+        for (int s = 0; s < NSLOT; ++s) {
+          acc_a.x += ta[s].x; acc_a.y += ta[s].y; acc_a.z += ta[s].z; acc_a.w += ta[s].w;
+          acc_b.x += tb[s].x; acc_b.y += tb[s].y; acc_b.z += tb[s].z; acc_b.w += tb[s].w;
+        }
+        const long long ra = base + r0;
+        if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)ra * D + i4 * 4) = acc_a;
+        if (p.x0_image) tc::image_store4(p.x0_image, D, ra, i4 * 4, acc_a);
+        if (two) {
+          if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)(ra + 1) * D + i4 * 4) = acc_b;
+          if (p.x0_image) tc::image_store4(p.x0_image, D, ra + 1, i4 * 4, acc_b);
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
 }  // namespace
 
 int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
-  MT_CHECK_ARG(p.D % 2 == 0, "face_embed: dim_codebook must be even (got %d)", p.D);
-  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 8));
+  MT_CHECK_ARG(p.D % 4 == 0, "face_embed: dim_codebook must be a multiple of 4 (got %d)", p.D);
+  MT_CHECK_ARG(max(max(p.n_coor, p.n_angle), max(p.n_area, p.n_normal)) <= 65535, "face_embed: at most 65535 bins per feature");
+  const int blocks = max(1, min(ceil_div(max_rows, 64), 148 * 2));
   if (p.nvf == 3) face_embed_kernel<3><<<blocks, 256, 0, stream>>>(p);
   else face_embed_kernel<4><<<blocks, 256, 0, stream>>>(p);
   MT_CHECK_LAUNCH();

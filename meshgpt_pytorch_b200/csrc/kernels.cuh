@@ -114,12 +114,19 @@ int launch_linear_tc_build_image(const float* W, int N, int K, void* image, cuda
 // a1_image / a2_image: split-bf16 activation images (tc_common.cuh) written by the producing kernels.
 // epi (optional): fused row epilogue - 1: x / max(|x|_2, 1e-12); 2: that + SiLU + LayerNorm(gamma, beta, eps 1e-5);
 // the result goes to C (fp32 rows, may be null) and / or out_image (activation image with K = N).
+// norm_mode 0 (plain epilogue) with extras, for output rows too wide for the fused normalisation: out_image = image of
+// the UN-normalised rows, ssq_out (M, 2 * passes) = parts of their squared norms; the consumer passes them as row_ssq
+// and gets C = acc / max(|x_row|, 1e-12) + bias, which equals the linear of the normalised rows.
 struct LinearRowEpilogue {
   int norm_mode;
   const float* gamma;
   const float* beta;
   void* out_image;
+  float* ssq_out;
+  const float* row_ssq;
+  int row_ssq_parts;
 };
+int linear_tc_ssq_parts(int N);   // 2 * passes of an N-wide tcgen05 linear
 int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                      int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream);

@@ -66,6 +66,10 @@ struct LinArgs {
   const float* gamma;
   const float* beta;
   uint8_t* out_image;       // activation image of the output rows (K = N) or null
+  // plain mode, deferred row normalisation (layers too wide for the fused epilogue):
+  float* ssq_out;           // (M, 2 * passes): sum of squares of this CTA's part of every output row, or null
+  const float* row_ssq;     // (M, row_ssq_parts): parts of |x_row|^2 of the INPUT rows; C = acc / max(|x|, 1e-12) + bias
+  int row_ssq_parts;
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -281,8 +285,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           }
         }
       } else {
-      // columns [c_lo, c_hi) of this pass in blocks of 16 (NT is a multiple of 16); TMEM loads are double buffered
+      // columns [c_lo, c_hi) of this pass in blocks of 16 (NT is a multiple of 16); TMEM loads are double buffered.
+      // Row phase (thread = row): scale, bias, ReLU, image chunks, sum of squares; then a per-warp shared-memory
+      // transpose for the fp32 row-major stores.
       const int c4 = (lane & 3) * 4, rsub = lane >> 2;
+      const long long grow = (long long)row0 + lane;
+      const bool live = grow < M;
+      float scale = 1.f;
+      if (a.row_ssq != nullptr && live) {   // the producer left its rows un-normalised: x / |x| commutes with the linear map
+        float t = 0.f;
+        for (int i = 0; i < a.row_ssq_parts; ++i) t += a.row_ssq[(size_t)grow * a.row_ssq_parts + i];
+        scale = 1.f / fmaxf(sqrtf(t), 1e-12f);
+      }
+      float ss = 0.f;
       uint32_t va[16], vb[16];
       if (c_lo < c_hi) tmem_ld16(taddr + c_lo, va);
       int parity = 0;
@@ -290,25 +305,50 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
         tmem_ld_wait();
         uint32_t(&v)[16] = parity ? vb : va;
         if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, parity ? va : vb);
-        float* mine = stage + lane * EPI_LD;
+        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<uint4*>(mine + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        __syncwarp();
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + c4));
+        for (int j = 0; j < 16; j += 4) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + j));
+          o[j] = fmaf(__uint_as_float(v[j]), scale, bb.x); o[j + 1] = fmaf(__uint_as_float(v[j + 1]), scale, bb.y);
+          o[j + 2] = fmaf(__uint_as_float(v[j + 2]), scale, bb.z); o[j + 3] = fmaf(__uint_as_float(v[j + 3]), scale, bb.w);
+        }
+        if (a.relu) {
 #pragma unroll
-        for (int it2 = 0; it2 < 4; ++it2) {
-          const int r = it2 * 8 + rsub;
-          if (row0 + r < M) {
-            float4 o = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            *reinterpret_cast<float4*>(a.C + (size_t)(row0 + r) * a.N + n0 + c + c4) = o;
+          for (int j = 0; j < 16; ++j) o[j] = fmaxf(o[j], 0.f);
+        }
+        if (a.ssq_out) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ss = fmaf(o[j], o[j], ss);
+        }
+        if (a.out_image && live) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 hi, lo;
+            split2(o[8 * g + 0], o[8 * g + 1], hi.x, lo.x);
+            split2(o[8 * g + 2], o[8 * g + 3], hi.y, lo.y);
+            split2(o[8 * g + 4], o[8 * g + 5], hi.z, lo.z);
+            split2(o[8 * g + 6], o[8 * g + 7], hi.w, lo.w);
+            uint8_t* pimg = a.out_image + image_offset(a.N, grow, n0 + c + 8 * g);
+            *reinterpret_cast<uint4*>(pimg) = hi;
+            *reinterpret_cast<uint4*>(pimg + IMG_PART) = lo;
           }
         }
-        __syncwarp();
+        if (a.C) {
+          float* mine = stage + lane * EPI_LD;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          __syncwarp();
+#pragma unroll
+          for (int it2 = 0; it2 < 4; ++it2) {
+            const int r = it2 * 8 + rsub;
+            if (row0 + r < M)
+              *reinterpret_cast<float4*>(a.C + (size_t)(row0 + r) * a.N + n0 + c + c4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
+          }
+          __syncwarp();
+        }
       }
+      if (a.ssq_out && live) a.ssq_out[(size_t)grow * (2 * a.passes) + 2 * pass + chalf] = ss;
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -385,6 +425,8 @@ int linear_tc_fused_norm_ok(int N, int norm_mode) {
   return MESHTOK_OK;
 }
 
+int linear_tc_ssq_parts(int N) { return 2 * ceil_div(N, NT_MAX); }
+
 size_t linear_tc_image_bytes(int N, int K) { return (size_t)N * K * 4; }
 
 size_t rows_image_bytes(long long rows, int K) { return tc::image_bytes(rows, K); }
@@ -417,7 +459,14 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
   MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
   LinArgs a;
   a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
-  if (epi != nullptr && epi->norm_mode != 0) {
+  a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
+  if (epi != nullptr && epi->norm_mode == 0) {
+    // plain epilogue with the deferred-normalisation extras
+    MT_CHECK_ARG(epi->out_image == nullptr || N % KC == 0, "tcgen05 linear: an output image needs N %% %d == 0 (got %d)", KC, N);
+    MT_CHECK_ARG(C != nullptr || epi->out_image != nullptr, "tcgen05 linear: no output given");
+    a.out_image = static_cast<uint8_t*>(epi->out_image);
+    a.ssq_out = epi->ssq_out; a.row_ssq = epi->row_ssq; a.row_ssq_parts = epi->row_ssq_parts;
+  } else if (epi != nullptr && epi->norm_mode != 0) {
     int rc0 = linear_tc_fused_norm_ok(N, epi->norm_mode);
     if (rc0 != MESHTOK_OK) return rc0;
     MT_CHECK_ARG(!relu, "tcgen05 linear: the fused row epilogue does not combine with ReLU");

@@ -61,7 +61,7 @@ __device__ __forceinline__ int warp_count_bits(const uint32_t* words, int wlo, i
   return warp_sum_int(c);
 }
 
-template <int MODE>
+template <int MODE, int NVF>   // NVF compile-time: the (face, slot) index arithmetic divides by it everywhere
 __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   extern __shared__ int smem[];
   __shared__ int s_ticket;
@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     __syncthreads();
   }
   const int b = (MODE == MODE_CSR) ? s_ticket : (int)blockIdx.x;
-  const int F = p.F, nvf = p.nvf, V = p.V;
+  const int F = p.F, V = p.V;
+  constexpr int nvf = NVF;
   const int lane = lane_id(), warp = warp_id(), nwarps = nt >> 5;
   const int FN = F * nvf;
 
@@ -517,20 +518,25 @@ int topo_check_shape(int B, int F, int nvf, int V) {
   return MESHTOK_OK;
 }
 
-template <int MODE>
-static int launch_topology(TopoParams p, cudaStream_t stream) {
+template <int MODE, int NVF>
+static int launch_topology_nvf(TopoParams p, cudaStream_t stream) {
   const int nt = topo_threads(p.F);
   int ww = 0;
   const size_t smem = topo_smem_bytes(p.F, p.nvf, p.V, nt, &ww);
   p.words_per_warp = ww;
-  static size_t configured[3] = {0, 0, 0};
-  if (smem > 48 * 1024 && smem > configured[MODE]) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(topology_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured[MODE] = 220 * 1024;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(topology_kernel<MODE, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    configured = 220 * 1024;
   }
-  topology_kernel<MODE><<<p.B, nt, smem, stream>>>(p);
+  topology_kernel<MODE, NVF><<<p.B, nt, smem, stream>>>(p);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
+}
+
+template <int MODE>
+static int launch_topology(const TopoParams& p, cudaStream_t stream) {
+  return p.nvf == 3 ? launch_topology_nvf<MODE, 3>(p, stream) : launch_topology_nvf<MODE, 4>(p, stream);
 }
 
 int topo_count(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_COUNT>(p, stream); }
