@@ -84,10 +84,10 @@ int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan);
 int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
                          int K, const int* n_rows_dev, int max_rows, const RvqTcPlan& plan, float4* partial, cudaStream_t stream);
 // Where the screening kernels leave the candidates of a row: mode 1 (rvq_tc.cu): n_splits entries at
-// partial[row * n_splits ..]; mode 2 (rvq_tc2.cu): 2 entries (column halves) per cluster whose step range touched the
-// row's 256-row tile, at partial[row * stride + 2 * (cluster - first cluster of the tile) + half].
+// partial[row * n_splits ..]; mode 2 (rvq_tc2.cu): `parts` entries (column parts of the 256-code tile) per cluster whose
+// step range touched the row's 256-row tile, at partial[row * stride + parts * (cluster - first cluster of the tile) + part].
 struct RvqPartialLayout {
-  int mode, stride, T, n_clusters, w_min;
+  int mode, stride, T, n_clusters, w_min, parts;
 };
 // re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
 // flag rows whose candidate list may be incomplete (-> exact scan).

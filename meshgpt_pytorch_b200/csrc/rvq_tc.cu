@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
       const long long S = (long long)((n + 255) >> 8) * lay.T;
       long long W = (S + lay.n_clusters - 1) / lay.n_clusters;
       if (W < lay.w_min) W = lay.w_min;
-      n_splits = 2 * (int)((g * lay.T + lay.T - 1) / W - (g * lay.T) / W + 1);
+      n_splits = lay.parts * (int)((g * lay.T + lay.T - 1) / W - (g * lay.T) / W + 1);
     }
     const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
     float smin = INFINITY;

@@ -46,8 +46,10 @@ constexpr int KC = 64;             // K elements per pipeline stage
 constexpr int STAGES = 10;
 constexpr int STAGE_BYTES = N_CTA * KC * 2;    // 16 KB
 constexpr int CHUNK = RVQ_CHUNK;
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
+constexpr int EPI_WARPS = 16;       // 4 per TMEM lane quarter, each takes COLS_PER_WARP of the 256 columns
+constexpr int NUM_THREADS = (4 + EPI_WARPS) * 32;
+constexpr int CSPLIT = EPI_WARPS / 4;  // column parts = partial entries per (row, cluster segment)
+constexpr int COLS_PER_WARP = N_PAIR / CSPLIT;
 constexpr uint32_t SBO_B = (KC / 8) * 128;     // 1024
 constexpr int E2_RING = 8;        // |e|^2 slices in flight: > stages / stages-per-tile + 2 accumulators + 1
 constexpr int W_MIN = 16;          // fewest steps a cluster takes (bounds the partial slots per row)
@@ -70,7 +72,7 @@ struct Search2Args {
   float escale;            // power-of-two codebook scale baked into the image
   const int* n_rows_dev;
   int max_rows, T, max_slots;   // T = K / 256 code-pair-tiles
-  float4* partial;         // (R, 2 * max_slots) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
+  float4* partial;         // (R, CSPLIT * max_slots) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
 };
 
 __device__ __forceinline__ int steps_per_cluster(long long S, int n_clusters) {
@@ -230,7 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     // ===== epilogue (both CTAs): running two best 8-code chunks per row and column half =====
     const int ew = warp - 4;
     const int q = warp & 3;                  // TMEM lane quarter this warp may read
-    const int chalf = ew >> 2;               // columns [chalf * 128, +128) of the 256-code tile
+    const int chalf = ew >> 2;               // column part: columns [chalf * COLS_PER_WARP, +COLS_PER_WARP) of the 256-code tile
     const int row_in_cta = q * 32 + lane;
     const uint32_t acc_empty_remote0 = mapa_shared(smem_u32(&acc_empty[0]), 0);
     const uint32_t acc_empty_remote1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
@@ -242,8 +244,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     long long my_row = 0;
     auto flush = [&](int g) {
       if (my_row < n_rows) {
-        const int slot = 2 * (cid - (int)(((long long)g * T) / W)) + chalf;
-        top.store(a.partial + ((size_t)my_row * (2 * a.max_slots) + slot) * RVQ_SLOT_F4);
+        const int slot = CSPLIT * (cid - (int)(((long long)g * T) / W)) + chalf;
+        top.store(a.partial + ((size_t)my_row * (CSPLIT * a.max_slots) + slot) * RVQ_SLOT_F4);
       }
     };
     for (long long step = lo; step < hi; ++step, ++acc_it) {
@@ -259,8 +261,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * N_PAIR + chalf * 128;
-      const int code0 = t * N_PAIR + chalf * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * N_PAIR + chalf * COLS_PER_WARP;
+      const int code0 = t * N_PAIR + chalf * COLS_PER_WARP;
       uint32_t va[32], vb[32];
       if (DBG == 1) {   // timing experiment: nobody reads the accumulators
         tcgen05_fence_before();
@@ -273,12 +275,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
       }
       tmem_ld32(taddr, va);
       mbar_wait(&e2_full[acc_it % E2_RING], (acc_it / E2_RING) & 1);
-      const float* e2t = sE2 + (acc_it % E2_RING) * N_PAIR + chalf * 128;
+      const float* e2t = sE2 + (acc_it % E2_RING) * N_PAIR + chalf * COLS_PER_WARP;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         tmem_ld_wait();
         uint32_t(&v)[32] = (c & 1) ? vb : va;
-        if (c + 1 < 4) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
+        if (c + 1 < COLS_PER_WARP / 32) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
         rvq_screen32(v, e2t + c * 32, cmul, (code0 + c * 32) / CHUNK, top);
       }
       tcgen05_fence_before();
@@ -334,7 +336,7 @@ int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan) {
   plan->n_clusters = sm_pairs();
   plan->max_slots = (plan->T - 1) / W_MIN + 2;
   const size_t rows_padded = (size_t)ceil_div(max(max_rows, 1), M_PAIR) * M_PAIR;
-  plan->partial_bytes = align_up(rows_padded * 2 * plan->max_slots * RVQ_SLOT_F4 * sizeof(float4), 256);
+  plan->partial_bytes = align_up(rows_padded * CSPLIT * plan->max_slots * RVQ_SLOT_F4 * sizeof(float4), 256);
   plan->row_image_bytes = align_up(rows_padded * D * 2, 256);
   return MESHTOK_OK;
 }
@@ -366,7 +368,8 @@ int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, con
 RvqPartialLayout rvq_tc2_partial_layout(const RvqTc2Plan& plan, int max_rows) {
   RvqPartialLayout l;
   l.mode = 2;
-  l.stride = 2 * plan.max_slots;
+  l.stride = CSPLIT * plan.max_slots;
+  l.parts = CSPLIT;
   l.T = plan.T;
   const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
   l.n_clusters = max(1, (int)min((long long)plan.n_clusters, (steps + W_MIN - 1) / W_MIN));
