@@ -65,6 +65,29 @@ struct Workspace {
   size_t total;
 };
 
+// Per host thread: a non-blocking side stream and the two events that fork it from / join it to the caller's stream.
+// Created on first use (the only allocation this library ever makes) and kept for the life of the thread.
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+SideStream* side_stream() {
+  static thread_local SideStream ss;
+  static thread_local int device = -1;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  if (ss.stream != nullptr && dev == device) return &ss;
+  if (ss.stream != nullptr) {   // the thread moved to another device: events and streams are per device
+    cudaStreamDestroy(ss.stream); cudaEventDestroy(ss.fork); cudaEventDestroy(ss.join);
+    ss = SideStream();
+  }
+  if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  device = dev;
+  return &ss;
+}
+
 // tcgen05 RVQ screening kernel: 2 = CTA-pair (cta_group::2, rvq_tc2.cu) whenever the codebook size allows it, 1 = single-CTA
 // (rvq_tc.cu).  MESHTOK_RVQ_TC=1 forces the single-CTA kernel (A/B measurements; at the MeshGPT shape the pair kernel
 // takes 171 us per level against 182 us).
@@ -120,7 +143,8 @@ void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E
   w->status = c.take<int>(16, &t->status);
   w->counts = reinterpret_cast<Counts*>(w->status ? w->status + 8 : nullptr);
   t->counts = t->status + 32;
-  w->mesh_counts = c.take<int>((size_t)B * 8 + 4);   // [B][4] aggregates, [B][4] inclusive prefixes, ticket (one memset)
+  w->mesh_counts = c.take<int>(2 * ((size_t)B * 8 + 4));   // two look-back blocks (maps launch, edges launch), each
+                                                            // [B][4] aggregates, [B][4] inclusive prefixes, ticket; one memset
   w->offs = c.take<int>(3 * (size_t)(B + 1));
   w->deg_out = c.take<int>(BF);
   w->deg_in = c.take<int>(BF);
@@ -406,13 +430,38 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   p.face_row = w.face_row; p.row_face = w.row_face; p.vert_row = w.vert_row; p.vptr = w.vptr; p.vinc = w.vinc;
   p.indptr = w.indptr; p.src = w.src; p.edge_capacity = a->edge_capacity;
   prof_begin(PROF_TOPOLOGY, s);
-  MT_CHECK_CUDA(cudaMemsetAsync(w.mesh_counts, 0, sizeof(int) * ((size_t)B * 8 + 4), s));
-  if ((rc = topo_csr(p, s)) != MESHTOK_OK) return rc;
+  // Two launches: the maps (packed face rows, vertex incidence CSR) are all the feature kernel and the first linear
+  // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
+  // side stream next to them and is joined before the first neighbour aggregation.  Inside a stream capture the side
+  // stream becomes a parallel branch of the graph.
+  MT_CHECK_CUDA(cudaMemsetAsync(w.mesh_counts, 0, sizeof(int) * 2 * ((size_t)B * 8 + 4), s));
+  if ((rc = topo_maps(p, s)) != MESHTOK_OK) return rc;
+  bool edges_pending = false;
+  SideStream* side = nullptr;
   if (a->face_edges) {
     rc = topo_user_edges(a->face_edges, B, E, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
     if (rc != MESHTOK_OK) return rc;
+  } else {
+    side = side_stream();
+    MT_CHECK_ARG(side != nullptr, "could not create the side stream for the adjacency kernel");
+    TopoParams pe = p;
+    pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
+    pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
+    pe.ticket = pe.mesh_counts + 8 * (size_t)B;
+    MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
+    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if ((rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
+    MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+    edges_pending = true;
   }
+  auto join_edges = [&]() -> int {
+    if (edges_pending) {
+      MT_CHECK_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+      edges_pending = false;
+    }
+    return MESHTOK_OK;
+  };
   prof_end(PROF_TOPOLOGY, s);
   const int* n_faces_dev = &w.counts->n_faces;
   const int* n_vrows_dev = &w.counts->n_vrows;
@@ -465,6 +514,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       const bool need_fp32 = a->keep_taps || (last && (a->encoded_out != nullptr || a->stop_after_encode));
       // xp = relu(lin(x))
       { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
+      if ((rc = join_edges()) != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {
@@ -495,6 +545,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     enc_img = w.img_x[cur];
     enc = x;
   } else {
+    if ((rc = join_edges()) != MESHTOK_OK) return rc;   // quantize(): no encoder, but the side stream must rejoin
     if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc;
     enc = w.layer_out[L - 1];
     if (!simt && !a->stop_after_encode) {

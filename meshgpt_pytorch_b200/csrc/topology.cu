@@ -32,7 +32,9 @@ namespace {
 
 constexpr int MODE_COUNT = 0;
 constexpr int MODE_FILL_DENSE = 1;
-constexpr int MODE_CSR = 2;
+constexpr int MODE_CSR = 2;     // maps + edges in one launch
+constexpr int MODE_MAPS = 3;    // packed face rows + vertex incidence CSR only (everything the feature kernel needs)
+constexpr int MODE_EDGES = 4;   // face CSR by target only; runs after MODE_MAPS, typically on a second stream
 
 // Walks the set bits of words[wlo..whi] in ascending order; fn(rank, bit_index).  Returns the count.
 template <class Fn>
@@ -66,11 +68,14 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   extern __shared__ int smem[];
   __shared__ int s_ticket;
   const int tid = threadIdx.x, nt = blockDim.x;
-  if (MODE == MODE_CSR) {   // meshes are taken in ticket order so that every predecessor of the look-back is running or done
+  constexpr bool kLookBack = MODE == MODE_CSR || MODE == MODE_MAPS || MODE == MODE_EDGES;
+  constexpr bool kMaps = MODE == MODE_CSR || MODE == MODE_MAPS;
+  constexpr bool kEdges = MODE == MODE_CSR || MODE == MODE_EDGES;
+  if (kLookBack) {   // meshes are taken in ticket order so that every predecessor of the look-back is running or done
     if (tid == 0) s_ticket = atomicAdd(p.ticket, 1);
     __syncthreads();
   }
-  const int b = (MODE == MODE_CSR) ? s_ticket : (int)blockIdx.x;
+  const int b = kLookBack ? s_ticket : (int)blockIdx.x;
   const int F = p.F, V = p.V;
   constexpr int nvf = NVF;
   const int lane = lane_id(), warp = warp_id(), nwarps = nt >> 5;
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
               n_ik += (a < nvf) && in_k;
               n_ki += (a < nvf) && in_i;
             }
-            const bool eo = (MODE != MODE_CSR) && n_ik >= thr && (keep3 || n_ik != 3);
+            const bool eo = !kLookBack && n_ik >= thr && (keep3 || n_ik != 3);
             const bool ei = (MODE != MODE_FILL_DENSE) && n_ki >= thr && (keep3 || n_ki != 3);
             if (eo) atomicOr(&obits[k >> 5], 1u << (k & 31));
             if (ei) atomicOr(&ibits[k >> 5], 1u << (k & 31));
@@ -287,9 +292,9 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     return;
   }
 
-  // ---- MODE_CSR: degrees -> look-back over the preceding meshes -> emit -------------------------
+  // ---- CSR modes: degrees -> look-back over the preceding meshes -> emit ------------------------
   int mesh_total = 0;
-  if (p.do_adjacency) {
+  if (kEdges && p.do_adjacency) {
     adjacency(true, 0, 0);
     __syncthreads();
     mesh_total = block_exclusive_scan(fptr, F, scratch);
@@ -331,24 +336,31 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   }
   __syncthreads();
   const int face_off = scratch[42], vert_off = scratch[43], edge_off = scratch[44];
-  if (p.do_adjacency) adjacency(false, face_off, edge_off);
+  if (kEdges && p.do_adjacency) adjacency(false, face_off, edge_off);
   __syncthreads();
 
   // ---- 4. outputs: maps + vertex CSR + face CSR row pointers ------------------------------------
-  if (tid == 0) {
-    p.face_off[b] = face_off; p.vert_off[b] = vert_off; p.edge_off[b] = edge_off;
+  const bool last_mesh = b == (int)gridDim.x - 1;   // the last mesh knows the batch totals
+  if (kEdges && p.do_adjacency) {
+    if (tid == 0) p.edge_off[b] = edge_off;
+    for (int f = tid; f < F; f += nt)
+      if (face_valid(f)) p.indptr[face_off + frank[f]] = edge_off + fptr[f];
+    if ((long long)edge_off + mesh_total > p.edge_capacity && tid == 0) atomicOr(p.status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
+    if (last_mesh && tid == 0) {
+      const int nf = face_off + nvalid, ne = edge_off + mesh_total;
+      p.edge_off[gridDim.x] = ne;
+      p.counts->n_edges = ne;
+      p.indptr[nf] = ne;
+    }
   }
+  if (!kMaps) return;
+  if (tid == 0) { p.face_off[b] = face_off; p.vert_off[b] = vert_off; }
   for (int f = tid; f < F; f += nt) {
     const bool ok = face_valid(f);
     const int row = face_off + frank[f];
     p.face_row[(size_t)b * F + f] = ok ? row : -1;
-    if (ok) {
-      p.row_face[row] = b * F + f;
-      if (p.do_adjacency) p.indptr[row] = edge_off + fptr[f];
-    }
+    if (ok) p.row_face[row] = b * F + f;
   }
-  if (p.do_adjacency && (long long)edge_off + mesh_total > p.edge_capacity && tid == 0)
-    atomicOr(p.status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
   for (int v = tid; v < V; v += nt) vcur[v] = (vstart[v + 1] > vstart[v]) ? 1 : 0;
   __syncthreads();
   block_exclusive_scan(vcur, V, scratch);
@@ -364,12 +376,14 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     const int f = idx / nvf, c = idx - f * nvf;
     p.vinc[(size_t)face_off * nvf + e] = (face_off + frank[f]) * nvf + c;
   }
-  if (b == (int)gridDim.x - 1 && tid == 0) {   // the last mesh knows the batch totals
-    const int nf = face_off + nvalid, nv = vert_off + nref, ne = edge_off + mesh_total;
-    p.face_off[gridDim.x] = nf; p.vert_off[gridDim.x] = nv; p.edge_off[gridDim.x] = ne;
-    p.counts->n_faces = nf; p.counts->n_vrows = nv; p.counts->n_edges = ne;
+  if (last_mesh && tid == 0) {
+    const int nf = face_off + nvalid, nv = vert_off + nref;
+    p.face_off[gridDim.x] = nf; p.vert_off[gridDim.x] = nv;
+    p.counts->n_faces = nf; p.counts->n_vrows = nv;
     p.vptr[nv] = nf * nvf;
-    if (p.do_adjacency) p.indptr[nf] = ne;
+    if (MODE == MODE_MAPS || !p.do_adjacency) {   // no edges (yet): keep the totals consistent until they are known
+      p.edge_off[gridDim.x] = 0;
+    }
   }
 }
 
@@ -542,6 +556,8 @@ static int launch_topology(const TopoParams& p, cudaStream_t stream) {
 int topo_count(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_COUNT>(p, stream); }
 int topo_fill_dense(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_FILL_DENSE>(p, stream); }
 int topo_csr(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_CSR>(p, stream); }
+int topo_maps(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_MAPS>(p, stream); }
+int topo_edges(const TopoParams& p, cudaStream_t stream) { return launch_topology<MODE_EDGES>(p, stream); }
 
 int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream) {
   mesh_offsets_kernel<<<1, 1024, 0, stream>>>(mesh_counts, offs, B, counts);

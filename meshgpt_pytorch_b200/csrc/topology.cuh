@@ -42,6 +42,10 @@ int topo_count(const TopoParams& p, cudaStream_t stream);
 int topo_fill_dense(const TopoParams& p, cudaStream_t stream);
 // single-launch batch topology; the caller zeroes mesh_counts, mesh_prefix and ticket first
 int topo_csr(const TopoParams& p, cudaStream_t stream);
+// the same in two launches: maps first (packed rows, vertex CSR, face / vertex totals), then the face CSR (edges), which
+// needs its own zeroed mesh_counts / mesh_prefix / ticket block and may run on another stream once the maps are done
+int topo_maps(const TopoParams& p, cudaStream_t stream);
+int topo_edges(const TopoParams& p, cudaStream_t stream);
 int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream);
 int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
                     int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,
