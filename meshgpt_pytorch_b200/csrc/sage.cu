@@ -14,6 +14,14 @@ namespace meshtok {
 
 namespace {
 
+// x / cnt for a small positive integer-valued cnt with rc = 1 / cnt: one FMA correction of the reciprocal product gives
+// the correctly rounded quotient for normal operands (what div.rn's fast path does) without its special-case scaffolding -
+// the IEEE divide was a third of this kernel's instructions.
+__device__ __forceinline__ float div_count(float x, float cnt, float rc) {
+  const float q = x * rc;
+  return fmaf(fmaf(-q, cnt, x), rc, q);
+}
+
 template <int CHUNKS>  // float4 chunks per lane (d = 128 * CHUNKS at most)
 __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                           const int* __restrict__ src, long long cap,
@@ -23,16 +31,19 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
   const int wpb = blockDim.x >> 5;
   const int n_rows = counts->n_faces;
   const int d4 = d >> 2;
+  // image offset of this lane's first float4 (columns 4*lane ..): chunk of 32 columns = lane >> 3, 8-column group inside
+  // it = (lane & 7) >> 1, element in the group = (lane & 1) * 4; every further 32 lanes' worth is 4 chunks on
+  const uint32_t img_lane = (uint32_t)(lane >> 3) * tc::IMG_BLOCK + (uint32_t)((lane & 7) >> 1) * 128u + (uint32_t)(lane & 1) * 8u;
+  const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
   for (int row = blockIdx.x * wpb + warp_id(); row < n_rows; row += gridDim.x * wpb) {
-    const long long s = indptr[row];
-    const long long e_true = indptr[row + 1];
-    const long long e = e_true < cap ? e_true : cap;
+    const int s = indptr[row];
+    const int e_true = indptr[row + 1];
+    const int e = (long long)e_true < cap ? e_true : (int)cap;
     float4 acc[CHUNKS];
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (long long q = s; q < e; ++q) {
-      const int srow = src[q];
-      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)srow * d);
+    for (int q = s; q < e; ++q) {
+      const float4* xr = reinterpret_cast<const float4*>(x + (size_t)__ldg(src + q) * d);
 #pragma unroll
       for (int c = 0; c < CHUNKS; ++c) {
         const int i4 = lane + 32 * c;
@@ -43,13 +54,24 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
       }
     }
     const float cnt = fmaxf((float)(e_true - s), 1.f);
+    const float rc = __frcp_rn(cnt);
+    uint8_t* img_row = agg_image ? agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_lane
+                                 : nullptr;
 #pragma unroll
     for (int c = 0; c < CHUNKS; ++c) {
       const int i4 = lane + 32 * c;
       if (i4 < d4) {
-        const float4 o = make_float4(__fdiv_rn(acc[c].x, cnt), __fdiv_rn(acc[c].y, cnt), __fdiv_rn(acc[c].z, cnt), __fdiv_rn(acc[c].w, cnt));
+        const float4 o = make_float4(div_count(acc[c].x, cnt, rc), div_count(acc[c].y, cnt, rc), div_count(acc[c].z, cnt, rc),
+                                     div_count(acc[c].w, cnt, rc));
         if (agg) reinterpret_cast<float4*>(agg + (size_t)row * d)[i4] = o;
-        if (agg_image) tc::image_store4(agg_image, d, row, i4 * 4, o);
+        if (agg_image) {
+          uint2 hi, lo;
+          tc::split2(o.x, o.y, hi.x, lo.x);
+          tc::split2(o.z, o.w, hi.y, lo.y);
+          uint8_t* pimg = img_row + (size_t)c * (4 * tc::IMG_BLOCK);
+          *reinterpret_cast<uint2*>(pimg) = hi;
+          *reinterpret_cast<uint2*>(pimg + tc::IMG_PART) = lo;
+        }
       }
     }
   }
