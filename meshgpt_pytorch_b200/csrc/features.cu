@@ -45,6 +45,7 @@ __device__ __forceinline__ void unit3(const float v[3], float out[3]) {
 //      2 faces x NSLOT independent 16-byte loads in flight).
 template <int NVF>
 __global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
+  pdl_wait();
   constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
   constexpr int ROWS = 64;
   constexpr int RPW = ROWS / 8;   // rows per warp in phase 2
@@ -141,6 +142,7 @@ __global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
     }
     __syncthreads();
   }
+  pdl_launch_dependents();
 }
 
 }  // namespace
@@ -149,9 +151,8 @@ int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(p.D % 4 == 0, "face_embed: dim_codebook must be a multiple of 4 (got %d)", p.D);
   MT_CHECK_ARG(max(max(p.n_coor, p.n_angle), max(p.n_area, p.n_normal)) <= 65535, "face_embed: at most 65535 bins per feature");
   const int blocks = max(1, min(ceil_div(max_rows, 64), 148 * 2));
-  if (p.nvf == 3) face_embed_kernel<3><<<blocks, 256, 0, stream>>>(p);
-  else face_embed_kernel<4><<<blocks, 256, 0, stream>>>(p);
-  MT_CHECK_LAUNCH();
+  if (p.nvf == 3) MT_LAUNCH_PDL(face_embed_kernel<3>, blocks, 256, 0, stream, p);
+  else MT_LAUNCH_PDL(face_embed_kernel<4>, blocks, 256, 0, stream, p);
   return MESHTOK_OK;
 }
 

@@ -92,9 +92,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = warp_id(), lane = lane_id();
-  const int M = a.m_dev ? min(*a.m_dev, a.m_max) : a.m_max;
-  const int m_tiles = (M + M_TILE - 1) / M_TILE;
-  const int units = m_tiles * a.passes;
   const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
   const int kchunks = kch1 + kch2;
   const uint32_t w_part = (uint32_t)a.NT * KC * 2;
@@ -109,6 +106,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of earlier kernels; from here on their results are read
+  pdl_wait();
+  const int M = a.m_dev ? min(*a.m_dev, a.m_max) : a.m_max;
+  const int m_tiles = (M + M_TILE - 1) / M_TILE;
+  const int units = m_tiles * a.passes;
 
   if (warp == 0) {
     // ===== producer (warp-converged; one elected lane issues): one A block (16 KB) + one W block (2 * NT * 64 B) per stage =====
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
     }
   }
 
+  pdl_launch_dependents();   // this CTA's work is done: let the next kernel's CTAs start their prologue
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -489,8 +492,7 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
   }
   const int units = ceil_div(m_max, M_TILE) * a.passes;
   const int grid = min(units, 148);
-  linear_tc_kernel<<<grid, NUM_THREADS, SMEM_TOTAL, stream>>>(a);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL(linear_tc_kernel, grid, NUM_THREADS, SMEM_TOTAL, stream, a);
   return MESHTOK_OK;
 }
 

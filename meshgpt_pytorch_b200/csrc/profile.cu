@@ -1,4 +1,6 @@
 // Launch counter + optional cudaEvent section timing (see meshtok_profile_* in include/meshtok.h).
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -7,6 +9,12 @@
 namespace meshtok {
 
 long long g_launch_count = 0;
+
+bool pdl_enabled() {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MESHTOK_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on == 1;
+}
 
 namespace {
 struct Rec { int section; cudaEvent_t a, b; };

@@ -17,6 +17,7 @@ template <int PER2>  // float2 per lane: D <= 64 * PER2
 __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restrict__ y, int D, const int* __restrict__ vptr,
                                                            const int* __restrict__ vinc, float* __restrict__ avg,
                                                            const Counts* counts) {
+  pdl_wait();
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n = counts->n_vrows;
@@ -46,6 +47,7 @@ __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restri
       if (c < d2) out[c] = make_float2(__fdiv_rn(acc[i].x, cnt), __fdiv_rn(acc[i].y, cnt));
     }
   }
+  pdl_launch_dependents();
 }
 
 // Residual LFQ (eval).  x = W_in v + b; level l: bit_d = r_d > 0, q_d = +-2^-l, r <- r - q;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
                                                            const int* __restrict__ vert_row, const int32_t* __restrict__ vcodes,
                                                            int BF, int F, int nvf, int V, int Q, int64_t pad_id,
                                                            int64_t* __restrict__ codes_out) {
+  pdl_wait();
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= (long long)BF * nvf) return;
   const int pf = (int)(tok / nvf);
@@ -131,6 +134,7 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
 // is skewed, so many rows of a warp share a code and un-aggregated atomics serialise on a few hot addresses).
 __global__ void __launch_bounds__(256) histogram_kernel(const int* __restrict__ vptr, const int32_t* __restrict__ vcodes,
                                                         const Counts* counts, int Q, int K, unsigned long long* __restrict__ hist) {
+  pdl_wait();
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = row < counts->n_vrows;
   const unsigned w = live ? (unsigned)(vptr[row + 1] - vptr[row]) : 0u;
@@ -194,14 +198,13 @@ int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc,
   MT_CHECK_ARG(D % 2 == 0 && D <= 512, "scatter_mean: dim %d must be even and <= 512", D);
   const int blocks = max(1, min(ceil_div(max_vrows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define SM(P) scatter_mean_kernel<P><<<blocks, 256, 0, stream>>>(y, D, vptr, vinc, avg, counts)
+#define SM(P) MT_LAUNCH_PDL(scatter_mean_kernel<P>, blocks, 256, 0, stream, y, D, vptr, vinc, avg, counts)
   if (per2 <= 1) SM(1);
   else if (per2 <= 2) SM(2);
   else if (per2 <= 3) SM(3);
   else if (per2 <= 4) SM(4);
   else SM(8);
 #undef SM
-  MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
@@ -227,17 +230,15 @@ int launch_gather_codes(const int64_t* faces, const int* face_row, const int* ve
                         int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream) {
   const long long n = (long long)B * F * nvf;
   if (n == 0) return MESHTOK_OK;
-  gather_codes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q,
-                                                                      pad_id, codes_out);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL(gather_codes_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q, pad_id,
+                codes_out);
   return MESHTOK_OK;
 }
 
 int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* counts, int max_vrows, int Q, int K,
                      unsigned long long* hist, cudaStream_t stream) {
   if (max_vrows == 0) return MESHTOK_OK;
-  histogram_kernel<<<ceil_div(max_vrows, 256), 256, 0, stream>>>(vptr, vcodes, counts, Q, K, hist);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL(histogram_kernel, ceil_div(max_vrows, 256), 256, 0, stream, vptr, vcodes, counts, Q, K, hist);
   return MESHTOK_OK;
 }
 

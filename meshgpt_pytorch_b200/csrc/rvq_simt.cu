@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
                                                         const float* __restrict__ e2, int K, int codes_per_split,
                                                         const int* __restrict__ row_list, const int* __restrict__ n_dev, int max_rows,
                                                         unsigned long long* __restrict__ packed) {
+  pdl_wait();
   __shared__ float As[BK][BM + 4];
   __shared__ float Es[BK][BN + 4];
   __shared__ float x2s[BM];
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
                                                          const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
                                                          int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
                                                          uint8_t* __restrict__ row_image, const int* __restrict__ n_dev, int max_rows) {
+  pdl_wait();
   const int wpb = blockDim.x >> 5;
   const int lane = lane_id();
   const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
@@ -205,6 +207,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
       }
     }
   }
+  pdl_launch_dependents();
 }
 
 }  // namespace
@@ -224,9 +227,8 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
     rvq_exact_init_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(row_list, n_dev, max_rows, packed);
     MT_CHECK_LAUNCH();
   }
-  rvq_exact_kernel<<<dim3(row_blocks, splits), 256, 0, stream>>>(rows, D, codebook, e2, K, codes_per_split, row_list, n_dev,
-                                                               max_rows, packed);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL(rvq_exact_kernel, dim3(row_blocks, splits), 256, 0, stream, rows, D, codebook, e2, K, codes_per_split, row_list, n_dev, max_rows,
+                packed);
   return MESHTOK_OK;
 }
 
@@ -237,11 +239,10 @@ int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned 
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RU(P) rvq_update_kernel<P, true><<<blocks, 256, 0, stream>>>(rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+#define RU(P) MT_LAUNCH_PDL((rvq_update_kernel<P, true>), blocks, 256, 0, stream, rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
   if (per2 <= 3) RU(3);
   else RU(8);
 #undef RU
-  MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
@@ -252,11 +253,10 @@ int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, vo
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RP(P) rvq_update_kernel<P, false><<<blocks, 256, 0, stream>>>(rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+#define RP(P) MT_LAUNCH_PDL((rvq_update_kernel<P, false>), blocks, 256, 0, stream, rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
   if (per2 <= 3) RP(3);
   else RP(8);
 #undef RP
-  MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 

@@ -91,12 +91,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
 
   const int warp = warp_id(), lane = lane_id();
-  const int n_rows = min(*a.n_rows_dev, a.max_rows);
-  const int m_tiles = (n_rows + M_TILE - 1) / M_TILE;
-  const int units = m_tiles * a.n_splits;
-  // contiguous unit ranges so that consecutive units of one CTA share the row tile
-  const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
-  const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
@@ -110,6 +104,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of earlier kernels; from here on their results are read
+  pdl_wait();
+  const int n_rows = min(*a.n_rows_dev, a.max_rows);
+  const int m_tiles = (n_rows + M_TILE - 1) / M_TILE;
+  const int units = m_tiles * a.n_splits;
+  // contiguous unit ranges so that consecutive units of one CTA share the row tile
+  const int u0 = (int)((long long)units * blockIdx.x / gridDim.x);
+  const int u1 = (int)((long long)units * (blockIdx.x + 1) / gridDim.x);
 
   if (warp == 0) {
     // ===== producer (warp-converged; one elected lane issues): stream codebook stages =====
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
     }
   }
 
+  pdl_launch_dependents();   // this CTA's work is done: let the next kernel's CTAs start their prologue
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -293,6 +296,7 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
                                                           const int* __restrict__ n_dev, int max_rows,
                                                           unsigned long long* __restrict__ packed,
                                                           int* __restrict__ amb_list, int* __restrict__ amb_count) {
+  pdl_wait();
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n = min(*n_dev, max_rows);
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
       if (ambiguous) { amb_list[atomicAdd(amb_count, 1)] = row; atomicAdd(amb_count + 1, 1); }
     }
   }
+  pdl_launch_dependents();
 }
 
 // fp32 codebook * escale -> fp16 image in stage order: [128-code tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B].
@@ -395,8 +400,7 @@ int launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
     MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D>::TOTAL));
     configured = true;
   }
-  rvq_tc_search_kernel<D, DBG><<<grid, NUM_THREADS, Smem<D>::TOTAL, stream>>>(a);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL((rvq_tc_search_kernel<D, DBG>), grid, NUM_THREADS, Smem<D>::TOTAL, stream, a);
   return MESHTOK_OK;
 }
 
@@ -464,9 +468,8 @@ int launch_rvq_rescore(const float* rows, const float* rscale, int D, const floa
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  rvq_rescore_kernel<6><<<blocks, 256, 0, stream>>>(rows, D, codebook, e2, max_norm, escale, rscale, partial, layout, n_rows_dev, max_rows, packed,
-                                                    amb_list, amb_count);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, rscale, partial, layout, n_rows_dev,
+                max_rows, packed, amb_list, amb_count);
   return MESHTOK_OK;
 }
 

@@ -101,15 +101,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int n_rows = min(*a.n_rows_dev, a.max_rows);
-  const int G = (n_rows + M_PAIR - 1) / M_PAIR;
-  const int T = a.T;
-  const long long S = (long long)G * T;
-  const int n_clusters = gridDim.x >> 1;
-  const int cid = blockIdx.x >> 1;
-  const int W = steps_per_cluster(S, n_clusters);
-  const long long lo = min(S, (long long)cid * W), hi = min(S, lo + W);
-
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], leader ? 2 : 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
@@ -124,6 +115,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is independent of earlier kernels; from here on their results are read
+  pdl_wait();
+  const int n_rows = min(*a.n_rows_dev, a.max_rows);
+  const int G = (n_rows + M_PAIR - 1) / M_PAIR;
+  const int T = a.T;
+  const long long S = (long long)G * T;
+  const int n_clusters = gridDim.x >> 1;
+  const int cid = blockIdx.x >> 1;
+  const int W = steps_per_cluster(S, n_clusters);
+  const long long lo = min(S, (long long)cid * W), hi = min(S, lo + W);
 
   if (warp == 0) {
     // ===== producer (both CTAs; warp-converged, one elected lane issues): own row tile + own half of every stage =====
@@ -293,6 +294,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     if (prev_g >= 0) flush(prev_g);
   }
 
+  pdl_launch_dependents();   // this CTA's work is done: let the next kernel's CTAs start their prologue
   tcgen05_fence_before();
   __syncthreads();
   cluster_sync_all();   // nothing of the pair is still in flight towards either CTA
@@ -309,8 +311,7 @@ int launch_search2(const Search2Args& a, int grid, cudaStream_t stream) {
     MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc2_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2<D>::TOTAL));
     configured = true;
   }
-  rvq_tc2_search_kernel<D, DBG><<<grid, NUM_THREADS, Smem2<D>::TOTAL, stream>>>(a);
-  MT_CHECK_LAUNCH();
+  MT_LAUNCH_PDL((rvq_tc2_search_kernel<D, DBG>), grid, NUM_THREADS, Smem2<D>::TOTAL, stream, a);
   return MESHTOK_OK;
 }
 

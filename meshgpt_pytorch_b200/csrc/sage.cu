@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
                                                           const int* __restrict__ src, long long cap,
                                                           float* __restrict__ agg, uint8_t* __restrict__ agg_image,
                                                           const Counts* counts) {
+  pdl_wait();
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n_rows = counts->n_faces;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
       }
     }
   }
+  pdl_launch_dependents();
 }
 
 template <int PER2>  // float2 pairs per lane (d <= 64 * PER2, d even)
@@ -147,7 +149,7 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int chunks = ceil_div(d / 4, 32);
-#define GM(C) gather_mean_kernel<C><<<blocks, 256, 0, stream>>>(x, d, indptr, src, edge_capacity, agg, static_cast<uint8_t*>(agg_image), counts)
+#define GM(C) MT_LAUNCH_PDL(gather_mean_kernel<C>, blocks, 256, 0, stream, x, d, indptr, src, edge_capacity, agg, static_cast<uint8_t*>(agg_image), counts)
   switch (chunks) {
     case 1: GM(1); break;
     case 2: GM(2); break;
@@ -156,7 +158,6 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     default: GM(8); break;
   }
 #undef GM
-  MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
