@@ -72,3 +72,58 @@ def derive_face_edges_from_faces(
             tail = torch.arange(emax, device=dev)[None, :] >= counts[:, None]
             out[tail] = pad_id
     return out[0] if one_mesh else out
+
+
+# ---------------------------------------------------------------------------------------------------
+# bulk producer of the reference's on-disk face-edge cache
+# ---------------------------------------------------------------------------------------------------
+
+FACE_EDGES_CACHE_FILE = "cache.face_edges_embed.memmap.npy"
+IS_CACHED_FILE = "cache.is_cached.memmap.npy"
+
+
+def write_face_edges_cache(cache_path, dataset_len: int, start: int, face_edges: Tensor, max_edges_len: int,
+                           pad_id: int = -1, assert_edge_len_lt_max: bool = True, memmap_file_mode: str = "r+"):
+    """Stores the edge lists of meshes [start, start + b) in the cache the reference's
+    `cache_face_edges_for_dataset` decorator reads (meshgpt_pytorch/data.py:158-257): `cache.face_edges_embed.memmap.npy`
+    (dataset_len, max_edges_len, 2) **float32** (the reference's dtype, data.py:191) and `cache.is_cached.memmap.npy`
+    (dataset_len,) bool.  face_edges: (b, e, 2) integer, rows padded with pad_id (what derive_face_edges_from_faces
+    returns); every mesh is padded or cut to max_edges_len rows like the reference's pad_or_slice_to (data.py:205-210)."""
+    import os
+    import numpy as np
+    from numpy.lib.format import open_memmap
+
+    os.makedirs(cache_path, exist_ok=True)
+    fe_file = os.path.join(cache_path, FACE_EDGES_CACHE_FILE)
+    ic_file = os.path.join(cache_path, IS_CACHED_FILE)
+    mode = memmap_file_mode if (os.path.isfile(fe_file) and os.path.isfile(ic_file)) else "w+"
+    if mode == "w+":
+        cache = open_memmap(fe_file, mode="w+", dtype="float32", shape=(dataset_len, max_edges_len, 2))
+        cached = open_memmap(ic_file, mode="w+", dtype="bool", shape=(dataset_len,))
+    else:
+        cache = open_memmap(fe_file, mode=mode)
+        cached = open_memmap(ic_file, mode=mode)
+        assert cache.shape == (dataset_len, max_edges_len, 2) and cached.shape == (dataset_len,), "cache shape mismatch"
+    fe = face_edges.detach().cpu()
+    b, e, _ = fe.shape
+    assert 0 <= start and start + b <= dataset_len
+    if assert_edge_len_lt_max:
+        edge_len = (fe != pad_id).all(-1).sum(-1)
+        worst = int(edge_len.max()) if b else 0
+        assert worst <= max_edges_len, f"a mesh has {worst} edges which exceeds the cache length of {max_edges_len}"
+    out = torch.full((b, max_edges_len, 2), float(pad_id), dtype=torch.float32)
+    keep = min(e, max_edges_len)
+    out[:, :keep] = fe[:, :keep].to(torch.float32)
+    cache[start:start + b] = out.numpy()
+    cached[start:start + b] = True
+    cache.flush()
+    cached.flush()
+    return fe_file, ic_file
+
+
+def cache_face_edges(faces: Tensor, cache_path, dataset_len: int, start: int, max_edges_len: int, pad_id: int = -1,
+                     assert_edge_len_lt_max: bool = True):
+    """derive_face_edges_from_faces on the GPU for a whole padded batch (b, nf, nvf) + write_face_edges_cache: fills the
+    reference's face-edge cache for meshes [start, start + b) in one go instead of one Python call per __getitem__."""
+    edges = derive_face_edges_from_faces(faces, pad_id=pad_id)
+    return write_face_edges_cache(cache_path, dataset_len, start, edges, max_edges_len, pad_id, assert_edge_len_lt_max)

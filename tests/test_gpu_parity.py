@@ -356,3 +356,17 @@ def test_full_size_properties_c2_and_c3():
         fpad[:, 500:] = -1
         c = m.tokenize(v, fpad)
         assert bool((c[:, 500 * nvf:] == -1).all()) and bool((c[:, :500 * nvf] >= 0).all())
+
+
+def test_face_edges_cache_bulk_fill(tmp_path):
+    """the GPU adjacency kernel fills the reference's on-disk face-edge cache for a whole batch."""
+    import numpy as np
+    import meshgpt_pytorch_b200 as M
+    _, faces = synth.ragged_batch("quad", 7, 9, [63, 40, 2, 63], [3, 4, 5, 6])
+    fe_file, ic_file = M.cache_face_edges(faces.cuda(), tmp_path, dataset_len=4, start=0, max_edges_len=400)
+    cache = np.load(fe_file, mmap_mode="r")
+    assert bool(np.load(ic_file, mmap_mode="r").all()) and cache.dtype == np.float32
+    for i in range(4):
+        row = torch.from_numpy(np.array(cache[i]))
+        want = O.derive_face_edges_from_faces(faces[i])
+        assert torch.equal(row[(row != -1).all(-1)].long(), want[(want != -1).all(-1)])

@@ -105,3 +105,31 @@ def test_histogram_definition():
     codes = torch.tensor([[[3, 1], [3, 0], [-1, -1]], [[2, 1], [-1, -1], [-1, -1]]])
     h = O.codebook_usage_histogram(codes, 2, 4)
     assert h.tolist() == [[0, 0, 1, 2], [1, 2, 0, 0]]
+
+
+def test_face_edges_cache_file_format(tmp_path):
+    """write_face_edges_cache produces what the reference's cache_face_edges_for_dataset decorator reads back
+    (meshgpt_pytorch/data.py:184-214): float32 (dataset_len, max_edges_len, 2) padded with pad_id + bool flags."""
+    import numpy as np
+    import meshgpt_pytorch_b200 as M
+    from meshgpt_pytorch_b200 import synth
+    from oracle import meshtok_oracle as O
+    _, faces = synth.ragged_batch("tri", 6, 6, [72, 30, 1], [0, 1, 2])
+    edges = O.derive_face_edges_from_faces(faces)                     # (3, e, 2) padded with -1
+    max_len = int((edges != -1).all(-1).sum(-1).max()) + 5
+    fe_file, ic_file = M.write_face_edges_cache(tmp_path, dataset_len=5, start=1, face_edges=edges, max_edges_len=max_len)
+    cache, cached = np.load(fe_file, mmap_mode="r"), np.load(ic_file, mmap_mode="r")
+    assert cache.dtype == np.float32 and cache.shape == (5, max_len, 2) and cached.dtype == np.bool_
+    assert cached.tolist() == [False, True, True, True, False]
+    for i in range(3):
+        # the reference's read path: rows with no pad entry are the mesh's edges, in order
+        row = torch.from_numpy(np.array(cache[1 + i]))
+        got = row[(row != -1).all(-1)].long()
+        want = O.derive_face_edges_from_faces(faces[i])
+        want = want[(want != -1).all(-1)]
+        assert torch.equal(got, want)
+    # a second batch goes into the same files; too-long meshes are refused like the reference's assert
+    M.write_face_edges_cache(tmp_path, 5, 4, edges[:1], max_len)
+    assert np.load(ic_file, mmap_mode="r").tolist() == [False, True, True, True, True]
+    with pytest.raises(AssertionError):
+        M.write_face_edges_cache(tmp_path / "small", 5, 0, edges, max_edges_len=3)
