@@ -315,7 +315,32 @@ def main():
         eager_step()
     _, _, sec_ms, sec_n = timed(eager_step, prof_steps, profile=True)
     model.check_last_status()
-    ms_e2e, _, _, _ = timed(host_step, args.steps)
+    ms_e2e_serial, _, _, _ = timed(host_step, args.steps)
+    ms_e2e = ms_e2e_serial
+    if graphed is not None:
+        # the public host-to-host API for a stream of batches: HostPipeline double-buffers, so the H2D copy of step i+1 and
+        # the D2H copy of step i-1 overlap the kernels of step i; every step's copies are inside the timed region
+        pipe = model.host_pipeline(v_dev, f_dev)
+        for _ in range(4):
+            pipe.submit(v_pin, f_pin)
+        pipe.drain()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for slot in pipe.slots:
+            slot["stream"].wait_event(ev0)
+        for _ in range(args.steps):
+            pipe.submit(v_pin, f_pin)
+        last = pipe.drain()
+        assert torch.equal(last[-1][1], codes_pin), "pipelined and single-call host paths disagree"
+        for slot in pipe.slots:
+            torch.cuda.current_stream().wait_stream(slot["stream"])
+        ev1.record()
+        ev1.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
     clocks = sampler.stop() if sampler else None
 
     total_faces = torch.tensor([n_faces_rank], dtype=torch.int64, device="cuda")
@@ -374,7 +399,8 @@ def main():
                                 wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps,
                                 rvq_rows_rechecked_by_exact_scan=t.get("rvq_exact_rechecks")),
                     e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
-                             ms_per_step=ms_e2e),
+                             ms_per_step=ms_e2e, api="HostPipeline.submit (double-buffered graph replays)" if graphed is not None else "tokenize_host",
+                             single_call_ms=ms_e2e_serial, single_call_value=total_faces / (ms_e2e_serial * 1e-3)),
                     gpu_launches=int(launches), gpu_launches_per_step=launches / args.steps, sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)
         print(json.dumps(line), flush=True)
     if world > 1:

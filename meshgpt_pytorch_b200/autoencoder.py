@@ -283,20 +283,20 @@ class MeshAutoencoder(nn.Module):
         return self._prep
 
     # ---- the pipeline call ------------------------------------------------------------------------
-    def _workspace(self, prep, B, F, V, E, cap) -> Tensor:
-        key = (B, F, V, E, cap)
+    def _workspace(self, prep, B, F, V, E, cap, tag=None) -> Tensor:
+        key = (B, F, V, E, cap, tag)          # tag: callers that run concurrently (two graphs in flight) keep apart
         ws = self._ws_cache.get(key)
         if ws is None:
             nbytes = C.c_size_t()
             check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, E, cap, C.byref(nbytes)))
-            if len(self._ws_cache) > 4:
+            if len(self._ws_cache) > 8:
                 self._ws_cache.clear()
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=prep["device"])
             self._ws_cache[key] = ws
         return ws
 
     def _run(self, *, vertices, faces, face_edges=None, encoded_in=None, want_codes=True, want_encoded=False,
-             want_face_coords=False, want_quantized=False, histogram=None, check_status=True):
+             want_face_coords=False, want_quantized=False, histogram=None, check_status=True, workspace_tag=None):
         prep = self._prepare()
         dev = prep["device"]
         if not faces.is_cuda:
@@ -335,7 +335,7 @@ class MeshAutoencoder(nn.Module):
         cap = max(1024, self.edge_slots_per_face * B * F, (B * E if E else 0))
         with torch.cuda.device(dev):
             while True:
-                ws = self._workspace(prep, B, F, V, E, cap)
+                ws = self._workspace(prep, B, F, V, E, cap, workspace_tag)
                 a = TokenizeArgs()
                 a.vertices, a.faces, a.face_edges, a.encoded_in = ptr(vertices), ptr(faces64), ptr(face_edges), ptr(encoded_in)
                 a.B, a.F, a.V, a.E = B, F, V, E
@@ -462,6 +462,10 @@ class MeshAutoencoder(nn.Module):
         run first (status word, edge-buffer size).  See GraphedTokenizer."""
         return GraphedTokenizer(self, vertices, faces, histogram)
 
+    def host_pipeline(self, vertices: Tensor, faces: Tensor) -> "HostPipeline":
+        """Double-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
+        return HostPipeline(self, vertices, faces)
+
     # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
     @torch.no_grad()
     def tokenize_host(self, vertices: Tensor, faces: Tensor, face_edges: Optional[Tensor] = None, pinned_out: Optional[Tensor] = None):
@@ -493,20 +497,22 @@ class GraphedTokenizer:
     def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None):
         assert vertices.is_cuda and faces.is_cuda and vertices.ndim == 3 and faces.ndim == 3
         self.model = model
+        tag = ("graph", id(self))             # its own workspace: several graphs of one model may be in flight
         self.vertices = vertices.to(torch.float32).clone()
         self.faces = faces.to(torch.int64).clone()
         self.histogram = histogram
         model.eval()
         # eager run: raises on bad data, grows the edge buffer if needed, allocates the workspace
-        model._run(vertices=self.vertices, faces=self.faces, check_status=True)
+        model._run(vertices=self.vertices, faces=self.faces, check_status=True, workspace_tag=tag)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            model._run(vertices=self.vertices, faces=self.faces, check_status=False)
+            model._run(vertices=self.vertices, faces=self.faces, check_status=False, workspace_tag=tag)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.codes = model._run(vertices=self.vertices, faces=self.faces, histogram=histogram, check_status=False)["codes"]
+            self.codes = model._run(vertices=self.vertices, faces=self.faces, histogram=histogram, check_status=False,
+                                    workspace_tag=tag)["codes"]
         self._workspace = model.last_workspace
 
     def __call__(self, vertices: Optional[Tensor] = None, faces: Optional[Tensor] = None) -> Tensor:
@@ -529,3 +535,49 @@ class GraphedTokenizer:
         torch.cuda.current_stream().synchronize()
         self.check()
         return pinned_out
+
+
+class HostPipeline:
+    """Host tensors in, host tensors out, with the copies of one batch overlapping the kernels of the other: two
+    GraphedTokenizers (own static inputs, workspace and pinned output each) alternate on two streams, so the H2D copy of
+    batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is on the SMs.
+
+        pipe = model.host_pipeline(example_vertices, example_faces)      # CUDA tensors of the batch shape
+        for v, f in batches:                                             # pinned host tensors
+            done = pipe.submit(v, f)        # -> (ticket, codes) of the batch submitted TWO calls ago, or None
+        for ticket, codes in pipe.drain(): ...
+
+    The returned codes tensor is the slot's pinned buffer: copy it before the slot is used again (two submits later)."""
+
+    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor):
+        self.slots = []
+        for _ in range(2):
+            stream = torch.cuda.Stream()
+            torch.cuda.current_stream().synchronize()
+            with torch.cuda.stream(stream):
+                g = GraphedTokenizer(model, vertices, faces)
+            stream.synchronize()
+            out = torch.empty(g.codes.shape, dtype=g.codes.dtype, pin_memory=True)
+            self.slots.append(dict(graph=g, stream=stream, out=out, done=torch.cuda.Event(), busy=False, ticket=-1))
+        self.n = 0
+
+    def _collect(self, slot):
+        slot["done"].synchronize()
+        slot["busy"] = False
+        slot["graph"].check()
+        return slot["ticket"], slot["out"]
+
+    def submit(self, vertices: Tensor, faces: Tensor):
+        slot = self.slots[self.n % 2]
+        finished = self._collect(slot) if slot["busy"] else None
+        with torch.cuda.stream(slot["stream"]):
+            codes = slot["graph"](vertices, faces)
+            slot["out"].copy_(codes, non_blocking=True)
+            slot["done"].record()
+        slot["busy"], slot["ticket"] = True, self.n
+        self.n += 1
+        return finished
+
+    def drain(self):
+        order = sorted((s for s in self.slots if s["busy"]), key=lambda s: s["ticket"])
+        return [self._collect(s) for s in order]

@@ -322,23 +322,31 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
       if (W < lay.w_min) W = lay.w_min;
       n_splits = lay.parts * (int)((g * lay.T + lay.T - 1) / W - (g * lay.T) / W + 1);
     }
+    // lane s holds entry s (n_splits <= 32 is checked by the launcher): one parallel load instead of a serial walk
     const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
-    float smin = INFINITY;
-    for (int s = lane; s < n_splits; s += 32) smin = fminf(smin, prow[s * RVQ_SLOT_F4].x);
+    float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
+    if (lane < n_splits) { p0 = prow[lane * RVQ_SLOT_F4]; p1 = prow[lane * RVQ_SLOT_F4 + 1]; }
+    float smin = p0.x;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
     const float window = smin + 2.f * delta;
-    bool ambiguous = false;
+    // chunks of this lane's entry inside the window (ascending list -> a prefix), and whether the list may be incomplete
+    const int mine = (p0.x <= window) + (p0.z <= window) + (p1.x <= window) + (p1.z <= window);
+    const bool ambiguous = __any_sync(0xffffffffu, p1.z <= window);
     float bd = INFINITY;
     int bi = 0x7fffffff;
-    for (int s = 0; s < n_splits; ++s) {
-      const float4 p0 = prow[s * RVQ_SLOT_F4], p1 = prow[s * RVQ_SLOT_F4 + 1];
-      if (p1.z <= window) ambiguous = true;   // every kept chunk is inside the window: a further one may hide behind them
+    // walk the candidates entry by entry (ascending entry = ascending code range within a cluster's slots is not
+    // guaranteed, so ties are resolved explicitly on the code index below)
+    unsigned live = __ballot_sync(0xffffffffu, mine > 0);
+    while (live) {
+      const int owner = __ffs(live) - 1;
+      live &= live - 1;
+      const int cnt = __shfl_sync(0xffffffffu, mine, owner);
+      const float y0 = __shfl_sync(0xffffffffu, p0.y, owner), y1 = __shfl_sync(0xffffffffu, p0.w, owner);
+      const float y2 = __shfl_sync(0xffffffffu, p1.y, owner), y3 = __shfl_sync(0xffffffffu, p1.w, owner);
 #pragma unroll 1
-      for (int which = 0; which < RVQ_TOPK; ++which) {
-        const float sc = which == 0 ? p0.x : which == 1 ? p0.z : which == 2 ? p1.x : p1.z;
-        if (!(sc <= window)) break;           // ascending list
-        const int code0 = __float_as_int(which == 0 ? p0.y : which == 1 ? p0.w : which == 2 ? p1.y : p1.w) * CHUNK;
+      for (int which = 0; which < cnt; ++which) {
+        const int code0 = __float_as_int(which == 0 ? y0 : which == 1 ? y1 : which == 2 ? y2 : y3) * CHUNK;
         // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
         float d[CHUNK];
 #pragma unroll
@@ -417,7 +425,7 @@ int rvq_tc_plan(int max_rows, int K, int D, RvqTcPlan* plan) {
   const int m_tiles = max(1, ceil_div(max_rows, M_TILE));
   int best_ns = 0;
   double best_eff = -1.0;
-  for (int ns = 1; ns <= tiles; ns *= 2) {
+  for (int ns = 1; ns <= tiles && ns <= 32; ns *= 2) {   // the re-score kernel reads one entry per lane
     if (tiles % ns != 0) break;
     if ((tiles / ns) * N_TILE > MAX_SPLIT_CODES) continue;
     const long long units = (long long)m_tiles * ns;
@@ -467,6 +475,7 @@ int launch_rvq_rescore(const float* rows, const float* rscale, int D, const floa
                        float escale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
+  MT_CHECK_ARG(layout.stride <= 32, "rvq re-score: at most 32 candidate entries per row (got %d)", layout.stride);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, rscale, partial, layout, n_rows_dev,
                 max_rows, packed, amb_list, amb_count);

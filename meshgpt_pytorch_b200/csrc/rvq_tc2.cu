@@ -52,7 +52,7 @@ constexpr int CSPLIT = EPI_WARPS / 4;  // column parts = partial entries per (ro
 constexpr int COLS_PER_WARP = N_PAIR / CSPLIT;
 constexpr uint32_t SBO_B = (KC / 8) * 128;     // 1024
 constexpr int E2_RING = 8;        // |e|^2 slices in flight: > stages / stages-per-tile + 2 accumulators + 1
-constexpr int W_MIN = 16;          // fewest steps a cluster takes (bounds the partial slots per row)
+constexpr int W_MIN = 16;          // fewest steps a cluster takes; max(W_MIN, T / 4) bounds the partial slots per row to 6
 
 template <int D>
 struct Smem2 {
@@ -71,13 +71,14 @@ struct Search2Args {
   const float* rscale;     // (R) power-of-two row scales baked into rimg
   float escale;            // power-of-two codebook scale baked into the image
   const int* n_rows_dev;
-  int max_rows, T, max_slots;   // T = K / 256 code-pair-tiles
+  int max_rows, T, max_slots, w_min;   // T = K / 256 code-pair-tiles
   float4* partial;         // (R, CSPLIT * max_slots) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
 };
 
-__device__ __forceinline__ int steps_per_cluster(long long S, int n_clusters) {
+__host__ __device__ __forceinline__ int w_min_of(int T) { return T / 4 > W_MIN ? T / 4 : W_MIN; }
+__device__ __forceinline__ int steps_per_cluster(long long S, int n_clusters, int w_min) {
   const long long w = (S + n_clusters - 1) / n_clusters;
-  return (int)(w < W_MIN ? W_MIN : w);
+  return (int)(w < w_min ? w_min : w);
 }
 
 template <int D, int DBG>
@@ -123,7 +124,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   const long long S = (long long)G * T;
   const int n_clusters = gridDim.x >> 1;
   const int cid = blockIdx.x >> 1;
-  const int W = steps_per_cluster(S, n_clusters);
+  const int W = steps_per_cluster(S, n_clusters, a.w_min);
   const long long lo = min(S, (long long)cid * W), hi = min(S, lo + W);
 
   if (warp == 0) {
@@ -335,7 +336,7 @@ int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan) {
   }
   plan->T = K / N_PAIR;
   plan->n_clusters = sm_pairs();
-  plan->max_slots = (plan->T - 1) / W_MIN + 2;
+  plan->max_slots = (plan->T - 1) / w_min_of(plan->T) + 2;
   const size_t rows_padded = (size_t)ceil_div(max(max_rows, 1), M_PAIR) * M_PAIR;
   plan->partial_bytes = align_up(rows_padded * CSPLIT * plan->max_slots * RVQ_SLOT_F4 * sizeof(float4), 256);
   plan->row_image_bytes = align_up(rows_padded * D * 2, 256);
@@ -347,10 +348,11 @@ int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, con
   if (max_rows == 0) return MESHTOK_OK;
   Search2Args a;
   a.rimg = static_cast<const uint8_t*>(row_image); a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.rscale = rscale;
-  a.escale = escale; a.n_rows_dev = n_rows_dev; a.max_rows = max_rows; a.T = plan.T; a.max_slots = plan.max_slots; a.partial = partial;
+  a.escale = escale; a.n_rows_dev = n_rows_dev; a.max_rows = max_rows; a.T = plan.T; a.max_slots = plan.max_slots; a.w_min = w_min_of(plan.T); a.partial = partial;
   // enough clusters for the worst case, never more than the machine has SM pairs
   const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
-  const int clusters = (int)min((long long)plan.n_clusters, (steps + W_MIN - 1) / W_MIN);
+  const int wm = w_min_of(plan.T);
+  const int clusters = (int)min((long long)plan.n_clusters, (steps + wm - 1) / wm);
   const int grid = 2 * max(1, clusters);
   switch (D) {
     case 64: return launch_search2<64, 0>(a, grid, stream);
@@ -373,8 +375,9 @@ RvqPartialLayout rvq_tc2_partial_layout(const RvqTc2Plan& plan, int max_rows) {
   l.parts = CSPLIT;
   l.T = plan.T;
   const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
-  l.n_clusters = max(1, (int)min((long long)plan.n_clusters, (steps + W_MIN - 1) / W_MIN));
-  l.w_min = W_MIN;
+  const int wm = w_min_of(plan.T);
+  l.n_clusters = max(1, (int)min((long long)plan.n_clusters, (steps + wm - 1) / wm));
+  l.w_min = wm;
   return l;
 }
 

@@ -370,3 +370,19 @@ def test_face_edges_cache_bulk_fill(tmp_path):
         row = torch.from_numpy(np.array(cache[i]))
         want = O.derive_face_edges_from_faces(faces[i])
         assert torch.equal(row[(row != -1).all(-1)].long(), want[(want != -1).all(-1)])
+
+
+def test_host_pipeline_matches_single_calls():
+    o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+    batches = [synth.ragged_batch("tri", 8, 8, [128, 50 + 9 * i, 1 + i], [i, i + 1, i + 2]) for i in range(5)]   # one padded shape
+    pipe = m.host_pipeline(batches[0][0].cuda(), batches[0][1].cuda())
+    got = {}
+    for v, f in batches:
+        done = pipe.submit(v.pin_memory(), f.pin_memory())
+        if done is not None:
+            got[done[0]] = done[1].clone()
+    for ticket, codes in pipe.drain():
+        got[ticket] = codes.clone()
+    assert sorted(got) == list(range(5))
+    for i, (v, f) in enumerate(batches):
+        assert torch.equal(got[i], m.tokenize(v.cuda(), f.cuda()).cpu()), i
