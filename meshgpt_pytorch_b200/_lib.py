@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmeshtok.so")
+LIB_PATH = os.environ.get("MESHTOK_LIBRARY") or os.path.join(HERE, "lib", "libmeshtok.so")   # override: A/B of two builds
 
 MAX_SAGE_LAYERS = 8
 ABI_VERSION = 1
