@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
+    ap.add_argument("--precomputed-edges", action="store_true",
+                    help="pass face_edges (derived once, outside the timed region) instead of deriving them inside tokenize (BASELINE config 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch the pipeline kernel by kernel instead of replaying its CUDA graph")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profiling aid: after the warm-up run this many device steps between cudaProfilerStart/Stop and exit "
@@ -212,6 +214,10 @@ def main():
     v_cpu, f_cpu = make_inputs(args.workload, rank * batch, batch)
     n_faces_rank = valid_faces(f_cpu)
     v_dev, f_dev = v_cpu.cuda(), f_cpu.cuda()
+    e_dev = None
+    if args.precomputed_edges:
+        import meshgpt_pytorch_b200 as M
+        e_dev = M.derive_face_edges_from_faces(f_dev)            # (b, emax, 2) int64, -1 padded: what a dataset cache holds
     v_pin, f_pin = v_cpu.pin_memory(), f_cpu.pin_memory()
     Q, K = model.num_quantizers, model.codebook_size
     hist = torch.zeros(Q, K, dtype=torch.int64, device="cuda")
@@ -228,7 +234,7 @@ def main():
 
     def eager_step():
         step_hist.zero_()
-        model.forward(vertices=v_dev, faces=f_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
+        model.forward(vertices=v_dev, faces=f_dev, face_edges=e_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
         if world > 1:
             dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
         hist.add_(step_hist)
@@ -238,7 +244,7 @@ def main():
     launches_per_graph = 0
     if not args.no_graph:
         l0 = lib.meshtok_kernel_launch_count()
-        graphed = model.graphed(v_dev, f_dev, histogram=None if args.no_hist else step_hist)
+        graphed = model.graphed(v_dev, f_dev, histogram=None if args.no_hist else step_hist, face_edges=e_dev)
         launches_per_graph = (lib.meshtok_kernel_launch_count() - l0) // 3      # eager check run + side-stream warm-up + capture
 
     def device_step():
@@ -253,6 +259,8 @@ def main():
     codes_pin = torch.empty((batch, f_cpu.shape[1] * f_cpu.shape[2], Q), dtype=torch.int64, pin_memory=True)
 
     def host_step():
+        if e_dev is not None:
+            return      # the host-buffer entries take vertices and faces only
         if graphed is None:
             model.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
         else:
@@ -317,7 +325,7 @@ def main():
     model.check_last_status()
     ms_e2e_serial, _, _, _ = timed(host_step, args.steps)
     ms_e2e = ms_e2e_serial
-    if graphed is not None:
+    if graphed is not None and e_dev is None:
         # the public host-to-host API for a stream of batches: HostPipeline double-buffers, so the H2D copy of step i+1 and
         # the D2H copy of step i-1 overlap the kernels of step i; every step's copies are inside the timed region
         pipe = model.host_pipeline(v_dev, f_dev)
@@ -396,9 +404,10 @@ def main():
                                 quantizer_rows_per_rank=R, l2="flushed between steps (512 MiB memset outside the timed events)",
                                 sharding="meshes by rank, weights replicated; NCCL all-reduce of the (Q,K) int64 histogram per step",
                                 launch="one CUDA graph replay per step" if graphed is not None else "kernel by kernel",
+                                face_edges="precomputed (user-supplied edge lists -> CSR by target on the device)" if e_dev is not None else "derived inside tokenize",
                                 wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps,
                                 rvq_rows_rechecked_by_exact_scan=t.get("rvq_exact_rechecks")),
-                    e2e=dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
+                    e2e=None if e_dev is not None else dict(value=total_faces / (ms_e2e * 1e-3), unit=UNIT, h2d_bytes_per_step=h2d * world, d2h_bytes_per_step=d2h * world,
                              ms_per_step=ms_e2e, api="HostPipeline.submit (double-buffered graph replays)" if graphed is not None else "tokenize_host",
                              single_call_ms=ms_e2e_serial, single_call_value=total_faces / (ms_e2e_serial * 1e-3)),
                     gpu_launches=int(launches), gpu_launches_per_step=launches / args.steps, sections=sec, roofline=roofline, cpu_baseline=cpu, clocks=clocks)

@@ -456,11 +456,12 @@ class MeshAutoencoder(nn.Module):
         return codes[0] if batch_less else codes
 
     # ---- CUDA-graph replay of the whole pipeline ----------------------------------------------------
-    def graphed(self, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None) -> "GraphedTokenizer":
+    def graphed(self, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None,
+                face_edges: Optional[Tensor] = None) -> "GraphedTokenizer":
         """Captures tokenize() for this input shape into a CUDA graph (the C ABI never allocates or synchronises, so
         the ~40 kernel launches of a batch replay as one graph launch).  The example inputs are validated by one eager
         run first (status word, edge-buffer size).  See GraphedTokenizer."""
-        return GraphedTokenizer(self, vertices, faces, histogram)
+        return GraphedTokenizer(self, vertices, faces, histogram, face_edges)
 
     def host_pipeline(self, vertices: Tensor, faces: Tensor) -> "HostPipeline":
         """Double-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
@@ -494,32 +495,38 @@ class GraphedTokenizer:
     g.codes is a static buffer that the next replay overwrites; clone it to keep it.  Data errors (vertex id out of
     range, edge-buffer overflow) are reported by g.check() / model.check_last_status(), not by the replay itself."""
 
-    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None):
+    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None,
+                 face_edges: Optional[Tensor] = None):
         assert vertices.is_cuda and faces.is_cuda and vertices.ndim == 3 and faces.ndim == 3
         self.model = model
+        # optional user-supplied (b, e, 2) edge lists (the reference's precomputed face_edges), a static input like the others
+        self.face_edges = None if face_edges is None else face_edges.to(torch.int64).clone()
         tag = ("graph", id(self))             # its own workspace: several graphs of one model may be in flight
         self.vertices = vertices.to(torch.float32).clone()
         self.faces = faces.to(torch.int64).clone()
         self.histogram = histogram
         model.eval()
         # eager run: raises on bad data, grows the edge buffer if needed, allocates the workspace
-        model._run(vertices=self.vertices, faces=self.faces, check_status=True, workspace_tag=tag)
+        model._run(vertices=self.vertices, faces=self.faces, face_edges=self.face_edges, check_status=True, workspace_tag=tag)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            model._run(vertices=self.vertices, faces=self.faces, check_status=False, workspace_tag=tag)
+            model._run(vertices=self.vertices, faces=self.faces, face_edges=self.face_edges, check_status=False, workspace_tag=tag)
         torch.cuda.current_stream().wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.codes = model._run(vertices=self.vertices, faces=self.faces, histogram=histogram, check_status=False,
-                                    workspace_tag=tag)["codes"]
+            self.codes = model._run(vertices=self.vertices, faces=self.faces, face_edges=self.face_edges, histogram=histogram,
+                                    check_status=False, workspace_tag=tag)["codes"]
         self._workspace = model.last_workspace
 
-    def __call__(self, vertices: Optional[Tensor] = None, faces: Optional[Tensor] = None) -> Tensor:
+    def __call__(self, vertices: Optional[Tensor] = None, faces: Optional[Tensor] = None, face_edges: Optional[Tensor] = None) -> Tensor:
         if vertices is not None:
             self.vertices.copy_(vertices, non_blocking=True)
         if faces is not None:
             self.faces.copy_(faces, non_blocking=True)
+        if face_edges is not None:
+            assert self.face_edges is not None and face_edges.shape == self.face_edges.shape, "captured without / with other face_edges"
+            self.face_edges.copy_(face_edges, non_blocking=True)
         self.graph.replay()
         return self.codes
 

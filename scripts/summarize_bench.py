@@ -4,7 +4,7 @@ import sys
 
 line = [l for l in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin) if l.startswith("{")][-1]
 d = json.loads(line)
-print(f"value {d['value']/1e6:.2f} M faces/s  ms/step {d['ms_per_step']:.3f}  e2e {d['e2e']['value']/1e6:.2f} M  launches {d.get('gpu_launches')}  n_gpus {d['n_gpus']}")
+print(f"value {d['value']/1e6:.2f} M faces/s  ms/step {d['ms_per_step']:.3f}  e2e {((d.get('e2e') or {}).get('value') or float('nan'))/1e6:.2f} M  launches {d.get('gpu_launches')}  n_gpus {d['n_gpus']}")
 for k, v in (d.get("sections") or {}).items():
     extra = ""
     if v.get("bound") == "hbm":

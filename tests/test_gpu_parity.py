@@ -386,3 +386,13 @@ def test_host_pipeline_matches_single_calls():
     assert sorted(got) == list(range(5))
     for i, (v, f) in enumerate(batches):
         assert torch.equal(got[i], m.tokenize(v.cuda(), f.cuda()).cpu()), i
+
+
+def test_graphed_with_precomputed_edges():
+    o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+    v, f = synth.ragged_batch("tri", 8, 8, [128, 50, 1], [0, 1, 2])
+    fe = O.derive_face_edges_from_faces(f)
+    g = m.graphed(v.cuda(), f.cuda(), face_edges=fe.cuda())
+    assert torch.equal(g(), m.tokenize(v.cuda(), f.cuda()))
+    perm = torch.randperm(fe.shape[1], generator=torch.Generator().manual_seed(1))
+    assert match_rate(g(face_edges=fe[:, perm].cuda()), m.tokenize(v.cuda(), f.cuda())) > 0.995
