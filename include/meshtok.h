@@ -215,11 +215,13 @@ int meshtok_rvq_codes(const meshtok_model* model, const float* rows, int R, int 
                       float* residual_out /* (R, dim) or NULL */, void* workspace, size_t workspace_bytes,
                       meshtok_stream_t stream);
 
-/* Size / builder of the UMMA-canonical fp16 codebook image (codebook * scale, scale a power of two)
- * consumed by the tcgen05 search. */
+/* Size / builder of the fp16 codebook image consumed by the tcgen05 search: codebook * scale (scale a power of two) in
+ * stage order, plus per 128-code tile a 4 KB K block carrying -kappa * |e_j|^2 as an fp16 pair (kappa = the power of two
+ * that brings max_norm^2 into [0.5, 1)), which the CTA-pair kernel folds into the MMA chain.  codebook_sqnorm and max_norm
+ * are the model's codebook_sqnorm / codebook_max_norm. */
 int meshtok_rvq_codebook_image_bytes(int codebook_size, int dim, size_t* bytes);
-int meshtok_rvq_build_codebook_image(const float* codebook, int codebook_size, int dim, float scale, void* image,
-                                     meshtok_stream_t stream);
+int meshtok_rvq_build_codebook_image(const float* codebook, const float* codebook_sqnorm, int codebook_size, int dim,
+                                     float scale, float max_norm, void* image, meshtok_stream_t stream);
 
 /* Dense linear C = act(A W^T + b).  Replaces torch.nn.functional.linear at meshgpt_pytorch.py:741, 803 and
  * inside SAGEConv.  A (M, K) fp32; W (N, K) fp32; C (M, N) fp32.  relu: 0/1.

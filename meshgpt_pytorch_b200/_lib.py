@@ -85,7 +85,7 @@ SIGNATURES = {
     "meshtok_rvq_codes": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
     "meshtok_rvq_codebook_image_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
-    "meshtok_rvq_build_codebook_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "meshtok_rvq_build_codebook_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "meshtok_linear_image_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "meshtok_linear_build_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_rows_image_bytes": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_size_t)]),

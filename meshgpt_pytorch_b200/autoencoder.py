@@ -273,7 +273,7 @@ class MeshAutoencoder(nn.Module):
                 if K % 128 == 0 and Dd in (64, 128, 192):
                     check(lib.meshtok_rvq_codebook_image_bytes(K, Dd, C.byref(nbytes)))
                     img = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
-                    check(lib.meshtok_rvq_build_codebook_image(ptr(cb), K, Dd, scale, ptr(img), stream_ptr()))
+                    check(lib.meshtok_rvq_build_codebook_image(ptr(cb), ptr(e2), K, Dd, scale, m.codebook_max_norm, ptr(img), stream_ptr()))
                     keep["cb_img"] = img
                     m.codebook_f16_tiles = ptr(img)
                     rvq_tc_ok = True

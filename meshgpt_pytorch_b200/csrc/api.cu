@@ -5,6 +5,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rvq_screen.cuh"
 #include "topology.cuh"
 
 namespace meshtok {
@@ -265,7 +266,8 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
     }
   }
   uint8_t* row_image = variant == 2 ? rimg : nullptr;
-  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, n_dev, max_rows, s); }
+  const float c_scale = m->codebook_image_scale / (2.f * rvq_e2_kappa(m->codebook_max_norm));   // powers of two: exact
+  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, c_scale, n_dev, max_rows, s); }
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
   for (int level = 0; level < Q; ++level) {
@@ -276,7 +278,7 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
       MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), s));  // [0] per level; [1] running total of the call
       { ProfScope ps(PROF_RVQ_SEARCH, s);
         if (variant == 2)
-          rc = launch_rvq_tc2_search(rimg, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, n_dev,
+          rc = launch_rvq_tc2_search(rimg, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, n_dev,
                                      max_rows, plan2, partial, s);
         else
           rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
@@ -284,14 +286,15 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_RESCORE, s);
         rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, m->codebook_max_norm,
-                                m->codebook_image_scale, partial, layout, n_dev, max_rows, packed, amb_list, amb_count, s); }
+                                m->codebook_image_scale, variant == 2 ? c_scale : 0.f, partial, layout, n_dev, max_rows, packed, amb_list,
+                                amb_count, s); }
       if (rc != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_RVQ_EXACT, s);
         rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, s); }
       if (rc != MESHTOK_OK) return rc;
     }
     { ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
-      rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, n_dev, max_rows, s); }
+      rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, c_scale, n_dev, max_rows, s); }
     if (rc != MESHTOK_OK) return rc;
   }
   return MESHTOK_OK;
@@ -673,11 +676,12 @@ int meshtok_rvq_codebook_image_bytes(int codebook_size, int dim, size_t* bytes) 
   return MESHTOK_OK;
 }
 
-int meshtok_rvq_build_codebook_image(const float* codebook, int codebook_size, int dim, float scale, void* image,
-                                     meshtok_stream_t stream) {
-  MT_CHECK_ARG(codebook && image, "codebook / image is null");
+int meshtok_rvq_build_codebook_image(const float* codebook, const float* codebook_sqnorm, int codebook_size, int dim, float scale,
+                                     float max_norm, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(codebook && codebook_sqnorm && image, "codebook / codebook_sqnorm / image is null");
   MT_CHECK_ARG(scale > 0.f, "scale must be a positive power of two");
-  return launch_rvq_build_image(codebook, codebook_size, dim, scale, image, static_cast<cudaStream_t>(stream));
+  MT_CHECK_ARG(max_norm >= 0.f, "max_norm must be max_j |e_j|");
+  return launch_rvq_build_image(codebook, codebook_sqnorm, codebook_size, dim, scale, max_norm, image, static_cast<cudaStream_t>(stream));
 }
 
 int meshtok_linear_image_bytes(int N, int K, size_t* bytes) {

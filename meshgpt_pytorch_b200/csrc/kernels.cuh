@@ -68,12 +68,14 @@ int launch_pack_rows(const float* padded, const int* row_face, int d, float* pac
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
                      const int* n_dev, int max_rows, unsigned long long* packed, cudaStream_t stream);
 // r <- r - e[idx]; codes[r*Q + level] = idx; rscale[r] = power of two that brings max|r_d| into [0.5, 1).
-// row_image (optional): fp16(r * rscale) in the layout the CTA-pair search bulk-copies ([128-row tile] x canonical 128 x D).
+// row_image (optional): fp16(r * rscale) in the layout the CTA-pair search bulk-copies, with the per-row constant
+// rscale * c_scale of the folded |e|^2 column (c_scale = codebook scale / (2 kappa), rvq_screen.cuh); rscale is then capped
+// so that this constant stays a finite fp16 power of two.
 int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
-                      float* rscale, void* row_image, const int* n_rows_dev, int max_rows, cudaStream_t stream);
+                      float* rscale, void* row_image, float c_scale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
 // resid <- rows_in (copy), rscale and row_image as above.
-int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, const int* n_rows_dev, int max_rows,
-                    cudaStream_t stream);
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, float c_scale, const int* n_rows_dev,
+                    int max_rows, cudaStream_t stream);
 
 // tcgen05 screening search (rvq_tc.cu).  Produces per (row, split) the two best fp16-screened scores + indices.
 struct RvqTcPlan {
@@ -91,8 +93,9 @@ struct RvqPartialLayout {
 };
 // re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
 // flag rows whose candidate list may be incomplete (-> exact scan).
+// c_scale: 0 for the single-CTA screening kernel, the folded-|e|^2 row constant factor for the CTA-pair kernel
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
+                       float escale, float c_scale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream);
 
 // CTA-pair (cta_group::2) screening search (rvq_tc2.cu)
@@ -102,10 +105,11 @@ struct RvqTc2Plan {
 };
 int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan);
 RvqPartialLayout rvq_tc2_partial_layout(const RvqTc2Plan& plan, int max_rows);
-int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale,
                           const int* n_rows_dev, int max_rows, const RvqTc2Plan& plan, float4* partial, cudaStream_t stream);
 size_t rvq_codebook_image_bytes(int K, int D);
-int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream);
+int launch_rvq_build_image(const float* codebook, const float* e2, int K, int D, float escale, float max_norm, void* image,
+                           cudaStream_t stream);
 
 // tcgen05 split-bf16 linear (linear_tc.cu); w_image from launch_linear_tc_build_image
 int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT);

@@ -7,12 +7,31 @@
 // re-score kernel is bound by those L2 reads, not by arithmetic - and TOPK = 4 makes the exact scan a rare event.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 
 namespace meshtok {
 
 constexpr int RVQ_CHUNK = 4;     // rvq_screen32 below is written for 4
 constexpr int RVQ_TOPK = 4;
-constexpr int RVQ_SLOT_F4 = 2;   // float4 per partial entry: {b0, i0, b1, i1}, {b2, i2, b3, i3}
+constexpr int RVQ_SLOT_F4 = 2;
+// Codebook image: per 128-code tile, D/64 stages of 16 KB (128 codes x 64 dims fp16, SWIZZLE_128B) followed by one 4 KB
+// "extra" K block (128 codes x 16 columns, canonical no-swizzle layout, 8-code groups 256 B apart) that carries
+// -kappa * |e_j|^2 as an fp16 pair (hi, lo) in columns 0 and 1.  The CTA-pair kernel multiplies it with a per-row constant
+// in the same MMA chain, so the accumulator already holds a multiple of the screened score and the epilogue needs no
+// per-value FMA and no |e|^2 loads; the single-CTA kernel skips the block.
+constexpr int RVQ_TILE_CODES = 128;
+constexpr int RVQ_EXTRA_BYTES = RVQ_TILE_CODES * 16 * 2;   // 4 KB
+constexpr unsigned RVQ_EXTRA_SBO = 256;
+__host__ __device__ inline size_t rvq_image_tile_bytes(int D) { return (size_t)RVQ_TILE_CODES * D * 2 + RVQ_EXTRA_BYTES; }
+// power of two kappa with kappa * max_norm^2 in [0.5, 1)
+inline float rvq_e2_kappa(float max_norm) {
+  const float m2 = max_norm * max_norm;
+  if (!(m2 > 0.f) || !(m2 < 3.0e38f)) return 1.f;
+  int e;
+  frexpf(m2, &e);
+  e = e > 100 ? 100 : (e < -100 ? -100 : e);
+  return ldexpf(1.f, -e);
+}   // float4 per partial entry: {b0, i0, b1, i1}, {b2, i2, b3, i3}
 
 struct RvqTop {   // scalars (not arrays) so that everything stays in registers
   float b0, b1, b2, b3;
@@ -52,6 +71,26 @@ __device__ __forceinline__ void rvq_screen32(const uint32_t (&v)[32], const floa
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (m[q] < top.worst()) top.insert(m[q], chunk_base + q);
+  }
+}
+
+// The same for accumulators that already hold a NEGATIVE multiple of the screened score (|e|^2 folded into the MMA chain):
+// s~ = cmul * acc with cmul < 0, so the best codes have the LARGEST acc.  thr = top.worst() / cmul is the accumulator value
+// a chunk maximum has to exceed to enter the list; the hot path is 31 FMNMX and one compare per 32 columns.
+__device__ __forceinline__ void rvq_screen32_max(const uint32_t (&v)[32], float cmul, float icm, int chunk_base, RvqTop& top, float& thr) {
+  float m[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    m[q] = fmaxf(fmaxf(__uint_as_float(v[4 * q + 0]), __uint_as_float(v[4 * q + 1])),
+                 fmaxf(__uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3])));
+  const float mm = fmaxf(fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3])), fmaxf(fmaxf(m[4], m[5]), fmaxf(m[6], m[7])));
+  if (mm > thr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (m[q] > thr) {
+        top.insert(cmul * m[q], chunk_base + q);
+        thr = top.worst() * icm;
+      }
   }
 }
 

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rvq_screen.cuh"
 
 namespace meshtok {
 
@@ -155,7 +156,8 @@ template <int PER2, bool UPDATE>   // float2 pairs per lane: D <= 64 * PER2
 __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict__ rows_in, float* __restrict__ rows, int D,
                                                          const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
                                                          int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
-                                                         uint8_t* __restrict__ row_image, const int* __restrict__ n_dev, int max_rows) {
+                                                         uint8_t* __restrict__ row_image, float c_scale, const int* __restrict__ n_dev,
+                                                         int max_rows) {
   pdl_wait();
   const int wpb = blockDim.x >> 5;
   const int lane = lane_id();
@@ -189,11 +191,15 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    const float sc = pow2_scale(vmax);
+    float sc = pow2_scale(vmax);
+    // the pair kernel multiplies the folded |e|^2 column by c = sc * c_scale, which must stay a finite fp16 power of two
+    if (row_image) sc = fminf(sc, 32768.f / c_scale);
     if (lane == 0 && rscale) rscale[row] = sc;
     if (row_image) {
-      // fp16(r * scale) at [128-row tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B] (what rvq_tc2.cu bulk-copies)
-      uint8_t* tile = row_image + (size_t)(row >> 7) * ((size_t)128 * D * 2);
+      // fp16(r * scale) at [128-row tile]{[64-dim chunk][128 rows x 128 B, SWIZZLE_128B], 4 KB extra K block} (what rvq_tc2.cu
+      // bulk-copies); the extra block holds c = scale * c_scale in columns 0 and 1 (times the codebook's (hi, lo) of
+      // -kappa |e|^2), zeros elsewhere
+      uint8_t* tile = row_image + (size_t)(row >> 7) * rvq_image_tile_bytes(D);
       const int r = row & 127;
 #pragma unroll
       for (int i = 0; i < PER2; ++i) {
@@ -204,6 +210,12 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
           const uint32_t off = (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)r * 128u + ((uint32_t)(((k >> 3) ^ r) & 7) << 4) + (uint32_t)(k & 7) * 2u;
           *reinterpret_cast<__half2*>(tile + off) = h;
         }
+      }
+      if (lane < 2) {
+        const __half ch = __float2half_rn(sc * c_scale);
+        const __half2 cc = __halves2half2(ch, ch);
+        uint8_t* ex = tile + (size_t)128 * D * 2 + (size_t)(r >> 3) * RVQ_EXTRA_SBO + (size_t)(r & 7) * 16 + (size_t)lane * 128;
+        *reinterpret_cast<uint4*>(ex) = lane == 0 ? make_uint4(*reinterpret_cast<const uint32_t*>(&cc), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
       }
     }
   }
@@ -233,27 +245,27 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
 }
 
 int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
-                      float* rscale, void* row_image, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
+                      float* rscale, void* row_image, float c_scale, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(D <= 512 && D % 2 == 0, "rvq: dim %d must be even and <= 512", D);
-  MT_CHECK_ARG(row_image == nullptr || D % 64 == 0, "rvq: a row image needs dim %% 64 == 0");
+  MT_CHECK_ARG(row_image == nullptr || (D % 64 == 0 && c_scale > 0.f), "rvq: a row image needs dim %% 64 == 0 and c_scale > 0");
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RU(P) MT_LAUNCH_PDL((rvq_update_kernel<P, true>), blocks, 256, 0, stream, rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+#define RU(P) MT_LAUNCH_PDL((rvq_update_kernel<P, true>), blocks, 256, 0, stream, rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows)
   if (per2 <= 3) RU(3);
   else RU(8);
 #undef RU
   return MESHTOK_OK;
 }
 
-int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, const int* n_rows_dev, int max_rows,
-                    cudaStream_t stream) {
+int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, float c_scale, const int* n_rows_dev,
+                    int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(D <= 512 && D % 2 == 0, "rvq: dim %d must be even and <= 512", D);
-  MT_CHECK_ARG(row_image == nullptr || D % 64 == 0, "rvq: a row image needs dim %% 64 == 0");
+  MT_CHECK_ARG(row_image == nullptr || (D % 64 == 0 && c_scale > 0.f), "rvq: a row image needs dim %% 64 == 0 and c_scale > 0");
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RP(P) MT_LAUNCH_PDL((rvq_update_kernel<P, false>), blocks, 256, 0, stream, rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), n_rows_dev, max_rows)
+#define RP(P) MT_LAUNCH_PDL((rvq_update_kernel<P, false>), blocks, 256, 0, stream, rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows)
   if (per2 <= 3) RP(3);
   else RP(8);
 #undef RP

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
       const int tile0 = (u % a.n_splits) * a.tiles_per_split;
       for (int t0 = 0; t0 < a.tiles_per_split; ++t0) {
         const int t = DBG == 3 ? (t0 + (int)blockIdx.x * 5) % a.tiles_per_split : t0;
-        const uint8_t* src = a.image + (size_t)(tile0 + t) * KCHUNKS * STAGE_BYTES;
+        const uint8_t* src = a.image + (size_t)(tile0 + t) * rvq_image_tile_bytes(D);   // (the 4 KB extra block is not used here)
         for (int kc = 0; kc < KCHUNKS; ++kc, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(&b_empty[s], ph ^ 1);
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
 // row is sent to the exact scan (with RVQ_TOPK kept chunks per slot: if the LAST of them is inside the window).
 template <int PER>
 __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
-                                                          const float* __restrict__ e2, float max_norm, float escale,
+                                                          const float* __restrict__ e2, float max_norm, float escale, float c_scale,
                                                           const float* __restrict__ rscale,
                                                           const float4* __restrict__ partial, RvqPartialLayout lay,
                                                           const int* __restrict__ n_dev, int max_rows,
@@ -311,8 +311,14 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
     }
     x2 = warp_sum(x2);
     const float xn = sqrtf(x2);
-    const float delta = 0.001953125f * 1.01f * xn * max_norm +
-                        5.96e-8f * sqrtf((float)D) * (max_norm / rscale[row] + xn / escale) + 1e-7f * (x2 + max_norm * max_norm);
+    float delta = 0.001953125f * 1.01f * xn * max_norm +
+                  5.96e-8f * sqrtf((float)D) * (max_norm / rscale[row] + xn / escale) + 1e-7f * (x2 + max_norm * max_norm);
+    if (c_scale > 0.f) {
+      // CTA-pair kernel: |e|^2 enters the MMA chain as an fp16 (hi, lo) pair (relative error 2^-21) times the row constant
+      // rscale * c_scale; should that constant underflow fp16 (astronomically large rows) the |e|^2 term is lost altogether
+      delta += 1e-6f * max_norm * max_norm;
+      if (rscale[row] * c_scale < 5.9604645e-8f) delta += max_norm * max_norm;
+    }
     // this row's candidate entries (see RvqPartialLayout)
     int n_splits = lay.stride;
     if (lay.mode == 2) {
@@ -382,7 +388,9 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
 }
 
 // fp32 codebook * escale -> fp16 image in stage order: [128-code tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B].
-__global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ cb, int K, int D, float escale, uint8_t* __restrict__ image) {
+__global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ cb, const float* __restrict__ e2, int K, int D, float escale,
+                                                          float kappa, uint8_t* __restrict__ image) {
+  const size_t tile_bytes = rvq_image_tile_bytes(D);
   const long long total = (long long)K * (D / 8);  // 16-byte chunks
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int code = (int)(i / (D / 8));
@@ -396,8 +404,19 @@ __global__ void __launch_bounds__(256) build_image_kernel(const float* __restric
     pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
     const int tile = code / N_TILE, r = code % N_TILE;
     const int kc = (k8 * 8) / KC, kin = (k8 * 8) % KC;
-    const size_t off = ((size_t)tile * (D / KC) + kc) * STAGE_BYTES + tc::sw128_offset(r, kin);
+    const size_t off = (size_t)tile * tile_bytes + (size_t)kc * STAGE_BYTES + tc::sw128_offset(r, kin);
     *reinterpret_cast<uint4*>(image + off) = pk;
+    if (k8 == 0) {
+      // extra K block: columns 0, 1 = fp16 pair (hi, lo) of -kappa * |e|^2, columns 2..15 zero
+      const float t = -kappa * e2[code];
+      const __half hi = __float2half_rn(t);
+      const __half lo = __float2half_rn(t - __half2float(hi));
+      const __half2 hl = __halves2half2(hi, lo);
+      uint4 first = make_uint4(*reinterpret_cast<const uint32_t*>(&hl), 0u, 0u, 0u);
+      uint8_t* ex = image + (size_t)tile * tile_bytes + (size_t)(D / KC) * STAGE_BYTES + (size_t)(r >> 3) * RVQ_EXTRA_SBO + (size_t)(r & 7) * 16;
+      *reinterpret_cast<uint4*>(ex) = first;                         // K core matrix 0 (columns 0..7)
+      *reinterpret_cast<uint4*>(ex + 128) = make_uint4(0u, 0u, 0u, 0u);  // K core matrix 1 (columns 8..15)
+    }
   }
 }
 
@@ -472,24 +491,24 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
 }
 
 int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
-                       float escale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
+                       float escale, float c_scale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   MT_CHECK_ARG(layout.stride <= 32, "rvq re-score: at most 32 candidate entries per row (got %d)", layout.stride);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, rscale, partial, layout, n_rows_dev,
+  MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, c_scale, rscale, partial, layout, n_rows_dev,
                 max_rows, packed, amb_list, amb_count);
   return MESHTOK_OK;
 }
 
-size_t rvq_codebook_image_bytes(int K, int D) { return (size_t)ceil_div(K, N_TILE) * N_TILE * D * 2; }
+size_t rvq_codebook_image_bytes(int K, int D) { return (size_t)ceil_div(K, N_TILE) * rvq_image_tile_bytes(D); }
 
-int launch_rvq_build_image(const float* codebook, int K, int D, float escale, void* image, cudaStream_t stream) {
+int launch_rvq_build_image(const float* codebook, const float* e2, int K, int D, float escale, float max_norm, void* image, cudaStream_t stream) {
   MT_CHECK_ARG(K % N_TILE == 0 && D % KC == 0, "codebook image needs codebook_size %% 128 == 0 and dim %% 64 == 0 (got %d, %d)", K, D);
   const long long total = (long long)K * (D / 8);
   const long long want = (total + 255) / 256;
   const unsigned blocks = (unsigned)(want < 148 * 16 ? want : 148 * 16);
-  build_image_kernel<<<blocks, 256, 0, stream>>>(codebook, K, D, escale, static_cast<uint8_t*>(image));
+  build_image_kernel<<<blocks, 256, 0, stream>>>(codebook, e2, K, D, escale, rvq_e2_kappa(max_norm), static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

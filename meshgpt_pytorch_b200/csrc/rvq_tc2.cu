@@ -43,7 +43,7 @@ constexpr int M_PAIR = 256;        // rows per cluster step
 constexpr int N_CTA = 128;         // codes staged per CTA and stage (one tile of the codebook image)
 constexpr int N_PAIR = 256;        // codes per MMA
 constexpr int KC = 64;             // K elements per pipeline stage
-constexpr int STAGES = 10;
+constexpr int STAGES = 9;
 constexpr int STAGE_BYTES = N_CTA * KC * 2;    // 16 KB
 constexpr int CHUNK = RVQ_CHUNK;
 constexpr int EPI_WARPS = 16;       // 4 per TMEM lane quarter, each takes COLS_PER_WARP of the 256 columns
@@ -51,23 +51,25 @@ constexpr int NUM_THREADS = (4 + EPI_WARPS) * 32;
 constexpr int CSPLIT = EPI_WARPS / 4;  // column parts = partial entries per (row, cluster segment)
 constexpr int COLS_PER_WARP = N_PAIR / CSPLIT;
 constexpr uint32_t SBO_B = (KC / 8) * 128;     // 1024
-constexpr int E2_RING = 8;        // |e|^2 slices in flight: > stages / stages-per-tile + 2 accumulators + 1
 constexpr int W_MIN = 16;          // fewest steps a cluster takes; max(W_MIN, T / 4) bounds the partial slots per row to 6
 
 template <int D>
 struct Smem2 {
-  static constexpr uint32_t SBO_A = (D / 8) * 128;
-  static constexpr uint32_t A_BYTES = M_CTA * D * 2;
+  static constexpr uint32_t A_MAIN = M_CTA * D * 2;                      // D/64 SWIZZLE_128B blocks of 16 KB
+  static constexpr uint32_t A_BYTES = A_MAIN + RVQ_EXTRA_BYTES;          // + the extra K block (per-row constant)
   static constexpr uint32_t B_OFF = A_BYTES;
-  static constexpr uint32_t E2_OFF = B_OFF + STAGES * STAGE_BYTES;          // ring of E2_RING x 256 floats
-  static constexpr uint32_t BAR_OFF = E2_OFF + E2_RING * N_PAIR * 4;
+  // extra K blocks (|e|^2 columns) in flight, one per code tile, released with the tile's last stage: the producer runs at
+  // most ceil(STAGES / stages per tile) tiles ahead of the MMAs, so that many + 1 slots are live; one more for margin
+  static constexpr int EX_RING = (STAGES + D / KC - 1) / (D / KC) + 2;
+  static constexpr uint32_t X_OFF = B_OFF + STAGES * STAGE_BYTES;         // ring of EX_RING extra K blocks of the codebook
+  static constexpr uint32_t BAR_OFF = X_OFF + EX_RING * RVQ_EXTRA_BYTES;
   static constexpr uint32_t TOTAL = BAR_OFF + 512;
 };
+static_assert(Smem2<192>::TOTAL <= 227 * 1024 && Smem2<128>::TOTAL <= 227 * 1024 && Smem2<64>::TOTAL <= 227 * 1024, "shared memory budget");
 
 struct Search2Args {
-  const uint8_t* rimg;     // fp16 image of the scaled residuals: [128-row tile] x canonical (128 x D), see rvq_row_image_*
-  const uint8_t* image;    // fp16 codebook image: [K/128 tiles][D/64 chunks][16 KB canonical stage]
-  const float* e2;         // (K) |e_j|^2
+  const uint8_t* rimg;     // fp16 image of the scaled residuals per 128-row tile (rvq_update_kernel): D/64 blocks + extra K block
+  const uint8_t* image;    // fp16 codebook image per 128-code tile: D/64 stages of 16 KB + extra K block (rvq_screen.cuh)
   const float* rscale;     // (R) power-of-two row scales baked into rimg
   float escale;            // power-of-two codebook scale baked into the image
   const int* n_rows_dev;
@@ -95,9 +97,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   uint64_t* acc_empty = acc_full + 2;        // [2]  (the leader's are the ones waited on)
   uint64_t* a_full = acc_empty + 2;
   uint64_t* a_empty = a_full + 1;
-  uint64_t* e2_full = a_empty + 1;           // [E2_RING]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(e2_full + E2_RING);
-  float* sE2 = reinterpret_cast<float*>(smem + L::E2_OFF);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+  uint8_t* sX = smem + L::X_OFF;
 
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = cluster_ctarank();
@@ -107,7 +108,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
     mbar_init(a_full, leader ? 2 : 1);
     mbar_init(a_empty, 1);
-    for (int i = 0; i < E2_RING; ++i) mbar_init(&e2_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair(tmem_slot, 512);
@@ -133,30 +133,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     int prev_g = -1;
     for (long long step = lo; step < hi; ++step, ++tile_it) {
       const int g = (int)(step / T), t = (int)(step % T);
-      // |e|^2 of the tile's 256 codes for the epilogue.  The ring slot was last used E2_RING tiles ago; the stage ring (and
-      // behind it the accumulator ring) keeps this warp fewer tiles than that ahead of the epilogue, so the slot is free.
-      if (elect_one()) {
-        mbar_arrive_expect_tx(&e2_full[tile_it % E2_RING], N_PAIR * 4);
-        bulk_g2s(sE2 + (tile_it % E2_RING) * N_PAIR, a.e2 + (size_t)t * N_PAIR, N_PAIR * 4, &e2_full[tile_it % E2_RING]);
-      }
-      __syncwarp();
       if (g != prev_g) {
         if (a_cnt > 0) mbar_wait(a_empty, (a_cnt - 1) & 1);   // MMAs on the previous row tile are complete
         if (elect_one()) {
           mbar_arrive_expect_tx(a_full, L::A_BYTES);
-          bulk_g2s(sA, a.rimg + (size_t)(2 * g + (int)rank) * L::A_BYTES, L::A_BYTES, a_full);
+          bulk_g2s(sA, a.rimg + (size_t)(2 * g + (int)rank) * rvq_image_tile_bytes(D), L::A_BYTES, a_full);
         }
         __syncwarp();
         ++a_cnt;
         prev_g = g;
       }
-      const uint8_t* src = a.image + (size_t)(2 * t + (int)rank) * KCH * STAGE_BYTES;
+      const uint8_t* src = a.image + (size_t)(2 * t + (int)rank) * rvq_image_tile_bytes(D);
       for (int kc = 0; kc < KCH; ++kc, ++it) {
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&b_empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES);
+          // the tile's last stage also brings its extra K block (|e|^2 columns).  Its ring slot was used EX_RING tiles ago (see Smem2),
+          // and this stage slot only became free after that tile's MMAs - the extra one included - had completed.
+          const bool last = kc == KCH - 1;
+          mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES + (last ? RVQ_EXTRA_BYTES : 0));
           bulk_g2s(sB + s * STAGE_BYTES, src + (size_t)kc * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
+          if (last) bulk_g2s(sX + (tile_it % L::EX_RING) * RVQ_EXTRA_BYTES, src + (size_t)KCH * STAGE_BYTES, RVQ_EXTRA_BYTES, &b_full[s]);
         }
         __syncwarp();
       }
@@ -196,6 +193,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
               const uint64_t da = make_smem_desc_sw128(sA_addr + kc * STAGE_BYTES + k16 * 32);
               const uint64_t db = make_smem_desc_sw128(sB_addr + s * STAGE_BYTES + k16 * 32);
               umma_f16_pair(tmem_base + buf * N_PAIR, da, db, idesc, (kc | k16) != 0 ? 1u : 0u);
+            }
+            if (kc == KCH - 1) {   // extra K block: + c_row * (hi, lo)(-kappa |e|^2)  ->  acc = -(rscale * escale / 2) * s~
+              const uint64_t da = make_smem_desc(sA_addr + L::A_MAIN, 128, RVQ_EXTRA_SBO);
+              const uint64_t db = make_smem_desc(smem_u32(sX) + (acc_it % L::EX_RING) * RVQ_EXTRA_BYTES, 128, RVQ_EXTRA_SBO);
+              umma_f16_pair(tmem_base + buf * N_PAIR, da, db, idesc, 1u);
             }
             umma_commit_pair_mc(&b_empty[s], 3);
           }
@@ -240,7 +242,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
     const uint32_t acc_empty_remote1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
     uint32_t acc_it = 0;
     int prev_g = -1;
-    float cmul = 0.f;
+    float cmul = 0.f, icm = 0.f, thr = -INFINITY;
     RvqTop top;
     top.reset();
     long long my_row = 0;
@@ -256,9 +258,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
         if (prev_g >= 0) flush(prev_g);
         prev_g = g;
         my_row = (long long)g * M_PAIR + (long long)rank * M_CTA + row_in_cta;
-        // acc = <r * rscale, e * escale>  ->  -2 <r, e> = acc * cmul
+        // acc = rscale * escale * (<r, e> - |e|^2 / 2)  ->  s~ = |e|^2 - 2 <r, e> = acc * cmul
         cmul = -2.f / ((my_row < n_rows ? __ldg(a.rscale + my_row) : 1.f) * a.escale);
+        icm = 1.f / cmul;
         top.reset();
+        thr = -INFINITY;
       }
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
@@ -276,14 +280,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
         continue;
       }
       tmem_ld32(taddr, va);
-      mbar_wait(&e2_full[acc_it % E2_RING], (acc_it / E2_RING) & 1);
-      const float* e2t = sE2 + (acc_it % E2_RING) * N_PAIR + chalf * COLS_PER_WARP;
 #pragma unroll
       for (int c = 0; c < COLS_PER_WARP / 32; ++c) {
         tmem_ld_wait();
         uint32_t(&v)[32] = (c & 1) ? vb : va;
         if (c + 1 < COLS_PER_WARP / 32) tmem_ld32(taddr + (c + 1) * 32, (c & 1) ? va : vb);
-        rvq_screen32(v, e2t + c * 32, cmul, (code0 + c * 32) / CHUNK, top);
+        rvq_screen32_max(v, cmul, icm, (code0 + c * 32) / CHUNK, top, thr);
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -339,15 +341,15 @@ int rvq_tc2_plan(int max_rows, int K, int D, RvqTc2Plan* plan) {
   plan->max_slots = (plan->T - 1) / w_min_of(plan->T) + 2;
   const size_t rows_padded = (size_t)ceil_div(max(max_rows, 1), M_PAIR) * M_PAIR;
   plan->partial_bytes = align_up(rows_padded * CSPLIT * plan->max_slots * RVQ_SLOT_F4 * sizeof(float4), 256);
-  plan->row_image_bytes = align_up(rows_padded * D * 2, 256);
+  plan->row_image_bytes = align_up(rows_padded / M_CTA * rvq_image_tile_bytes(D), 256);
   return MESHTOK_OK;
 }
 
-int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale, const float* e2,
+int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, const void* codebook_tiles, float escale,
                           const int* n_rows_dev, int max_rows, const RvqTc2Plan& plan, float4* partial, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   Search2Args a;
-  a.rimg = static_cast<const uint8_t*>(row_image); a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.rscale = rscale;
+  a.rimg = static_cast<const uint8_t*>(row_image); a.image = static_cast<const uint8_t*>(codebook_tiles); a.rscale = rscale;
   a.escale = escale; a.n_rows_dev = n_rows_dev; a.max_rows = max_rows; a.T = plan.T; a.max_slots = plan.max_slots; a.w_min = w_min_of(plan.T); a.partial = partial;
   // enough clusters for the worst case, never more than the machine has SM pairs
   const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;

@@ -45,7 +45,7 @@ def test_host_side_argument_checks():
     assert lib.meshtok_topology_workspace_bytes(1, 200000, 3, 100000, 0, C.byref(n)) == -2  # too large for one SM
     assert lib.meshtok_linear_image_bytes(576, 512, C.byref(n)) == 0 and n.value == 576 * 512 * 4
     assert lib.meshtok_linear_image_bytes(100, 30, C.byref(n)) == -2
-    assert lib.meshtok_rvq_codebook_image_bytes(16384, 192, C.byref(n)) == 0 and n.value == 16384 * 192 * 2
+    assert lib.meshtok_rvq_codebook_image_bytes(16384, 192, C.byref(n)) == 0 and n.value == 16384 * 192 * 2 + (16384 // 128) * 4096
     assert lib.meshtok_profile_sections() >= 10
     assert lib.meshtok_profile_section_name(0) == b"topology"
     m = _lib.Model()
