@@ -386,8 +386,16 @@ def main():
             flops = 2.0 * R * K * D
             achieved = flops / (per_launch_ms * 1e-3) / 1e12
             peak = peaks.get("bf16_tflops_sustained") or 1400.0
-            roofline = dict(kernel="rvq_tc_search_kernel", bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s",
-                            frac=achieved / peak, traffic=None, peak_source="measured" if peaks else "fallback",
+            # DRAM bytes per launch of this kernel from the committed ncu --set full capture (profiles/traffic.json), or null
+            traffic, kernel_name = None, "rvq_tc2_search_kernel (CTA pair) / rvq_tc_search_kernel"
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+                traffic = tj["rvq_search"]["dram_bytes_per_launch"]
+                kernel_name = tj["rvq_search"].get("kernel", kernel_name)
+            except Exception:
+                pass
+            roofline = dict(kernel=kernel_name, bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s",
+                            frac=achieved / peak, traffic=traffic, peak_source="measured" if peaks else "fallback",
                             flops_per_launch=flops, ms_per_launch=per_launch_ms)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
