@@ -48,7 +48,9 @@ constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
 constexpr int EPI_LD = 20;                                 // padded row length (floats) of the 32 x 16 epilogue staging tiles
 constexpr uint32_t EPI_OFF = BAR_OFF + 256;
 constexpr uint32_t XCH_OFF = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;   // [2 unit parities][3 sums][2 halves][128 rows] floats
-constexpr uint32_t SMEM_TOTAL = XCH_OFF + 2 * 3 * 2 * 128 * 4;
+constexpr uint32_t VEC_OFF = XCH_OFF + 2 * 3 * 2 * 128 * 4;          // bias (N <= 1024), gamma, beta (N <= 64) staged once per CTA
+constexpr int VEC_MAX_N = 1024;
+constexpr uint32_t SMEM_TOTAL = VEC_OFF + (VEC_MAX_N + 2 * 64) * 4;
 static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
 
 struct LinArgs {
@@ -102,6 +104,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
+  // bias / gamma / beta -> shared memory (the epilogue reads them per 16-column block; as global loads they sat on its
+  // critical path)
+  float* sbias = reinterpret_cast<float*>(smem + VEC_OFF);
+  float* sgamma = sbias + VEC_MAX_N;
+  float* sbeta = sgamma + 64;
+  for (int i = threadIdx.x; i < a.N; i += NUM_THREADS) {
+    sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+    if (a.norm_mode == 2) { sgamma[i] = __ldg(a.gamma + i); sbeta[i] = __ldg(a.beta + i); }
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -216,8 +227,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + c + j));
+            const float4 bb = *reinterpret_cast<const float4*>(sbias + c + j);
             o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
             o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
           }
@@ -277,12 +287,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           const float rstd = 1.f / sqrtf((xs[512 + rit] + xs[512 + 128 + rit]) / (float)a.N + 1e-5f);
           if (h0) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o0[j] = (o0[j] - mean) * rstd * __ldg(a.gamma + c_lo + j) + __ldg(a.beta + c_lo + j);
+            for (int j = 0; j < 16; ++j) o0[j] = (o0[j] - mean) * rstd * sgamma[c_lo + j] + sbeta[c_lo + j];
             put(c_lo, o0);
           }
           if (h1) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o1[j] = (o1[j] - mean) * rstd * __ldg(a.gamma + c_lo + 16 + j) + __ldg(a.beta + c_lo + 16 + j);
+            for (int j = 0; j < 16; ++j) o1[j] = (o1[j] - mean) * rstd * sgamma[c_lo + 16 + j] + sbeta[c_lo + 16 + j];
             put(c_lo + 16, o1);
           }
         }
@@ -310,8 +320,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (a.bias) bb = __ldg(reinterpret_cast<const float4*>(a.bias + n0 + c + j));
+          const float4 bb = *reinterpret_cast<const float4*>(sbias + n0 + c + j);
           o[j] = fmaf(__uint_as_float(v[j]), scale, bb.x); o[j + 1] = fmaf(__uint_as_float(v[j + 1]), scale, bb.y);
           o[j + 2] = fmaf(__uint_as_float(v[j + 2]), scale, bb.z); o[j + 3] = fmaf(__uint_as_float(v[j + 3]), scale, bb.w);
         }
@@ -406,6 +415,10 @@ __global__ void __launch_bounds__(256) rows_to_image_kernel(const float* __restr
 }  // namespace
 
 int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT) {
+  if (N > VEC_MAX_N) {
+    set_error("tcgen05 linear: output width %d is more than %d; use the SIMT path", N, VEC_MAX_N);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
   if (N <= 0 || K1 <= 0 || K1 % KC != 0 || K2 % KC != 0) {
     set_error("tcgen05 linear: input widths must be multiples of %d (got %d, %d); use the SIMT path", KC, K1, K2);
     return MESHTOK_ERR_UNSUPPORTED;
