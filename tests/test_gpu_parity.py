@@ -396,3 +396,24 @@ def test_graphed_with_precomputed_edges():
     assert torch.equal(g(), m.tokenize(v.cuda(), f.cuda()))
     perm = torch.randperm(fe.shape[1], generator=torch.Generator().manual_seed(1))
     assert match_rate(g(face_edges=fe[:, perm].cuda()), m.tokenize(v.cuda(), f.cuda())) > 0.995
+
+
+@pytest.mark.parametrize("cfg,kind,grid,counts", [
+    (dict(SMALL_CFG, use_residual_lfq=False, quads=True), "quad", (6, 7), [42, 17, 3]),              # quads + RVQ (CTA-pair search)
+    (dict(SMALL_CFG, use_residual_lfq=False, codebook_size=384), "tri", (8, 8), [128, 1]),          # K % 256 != 0 -> single-CTA search
+    (dict(SMALL_CFG, use_residual_lfq=False, codebook_size=200), "tri", (8, 8), [90, 60]),          # no tcgen05 image -> exact fp32 scan
+    (dict(SMALL_CFG, num_quantizers=3, codebook_size=512), "tri", (8, 8), [128, 128, 5, 77]),       # LFQ, 3 levels, 9 bits
+    (dict(dim_codebook=192, encoder_dims_through_depth=(64, 128), codebook_size=1024, use_residual_lfq=False), "tri", (10, 10), [200, 150]),
+])
+def test_config_matrix_end_to_end(cfg, kind, grid, counts):
+    """Other constructor configurations end to end against the oracle (token agreement; exact pad positions)."""
+    o, m = make_pair(**cfg)
+    v, f = synth.ragged_batch(kind, grid[0], grid[1], counts, list(range(len(counts))))
+    got = m.tokenize(v.cuda(), f.cuda()).cpu()
+    want = o.tokenize(v, f)
+    assert got.shape == want.shape and torch.equal(got == -1, want == -1)
+    assert match_rate(got, want) > 0.97, match_rate(got, want)
+    # vertices nobody references and a lone single-face mesh do not disturb anything
+    v2 = torch.cat([v, torch.rand(v.shape[0], 7, 3) * 2 - 1], dim=1)
+    assert torch.equal(m.tokenize(v2.cuda(), f.cuda()).cpu(), got)
+    assert torch.equal(m.tokenize(v[-1:].cuda(), f[-1:].cuda()).cpu(), got[-1:])
