@@ -63,6 +63,7 @@ struct Workspace {
   float4* partial;
   uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
   float* ssq;        // (B*F, 8): parts of the squared row norms of the last SAGE layer (deferred normalisation)
+  uint16_t* bins;    // (B*F, nvf*4+4): folded-table row ids of every packed row
   size_t total;
 };
 
@@ -188,6 +189,7 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->img_x[1] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
   w->ssq = c.take<float>(BF * 8);
+  w->bins = c.take<uint16_t>(BF * (size_t)(m->nvf * 4 + 4));
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
   w->avg = c.take<float>(BV * D, &t->averaged);
@@ -496,6 +498,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       for (int k = 0; k < 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_normals; }
     }
     fp.x0 = (simt || a->keep_taps) ? w.x0 : nullptr; fp.x0_image = simt ? nullptr : w.img_x[0]; fp.face_coords_out = a->face_coords_out;
+    fp.bins_out = w.bins;
     if (a->face_coords_out)
       MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)max_rows * nvf * 3, s));
     { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }

@@ -37,110 +37,119 @@ __device__ __forceinline__ void unit3(const float v[3], float out[3]) {
   out[2] = __fdiv_rn(v[2], d);
 }
 
-// Two phases per chunk of ROWS face rows (small chunks so that the grid-stride loop balances over the SMs):
-//   1. one THREAD per face: gather the corner positions, derive the features, discretise -> NSLOT bin ids in shared memory
-//      (no lane repeats another lane's acosf / sqrt / divide);
-//   2. one WARP per face, two faces in flight: x0[row] = bias + sum_s table_s[bin_s] in fixed slot order, 16 B per lane and
-//      table row (the tables are L2 resident; the kernel is bound by the latency of these reads, so a lane keeps
-//      2 faces x NSLOT independent 16-byte loads in flight).
+// Two kernels:
+//   face_bins_kernel: one THREAD per face - gather the corner positions, derive the features, discretise -> NSLOT bin ids
+//     (uint16) in global memory (no lane repeats another lane's acosf / sqrt / divide);
+//   face_sum_kernel: one WARP per pair of faces - x0[row] = bias + sum_s table_s[bin_s] in fixed slot order.  The 2 * D/4
+//     float4 columns of the pair are spread over the lanes so that all of them work; a lane keeps half of the table rows of
+//     its column in flight at a time.  The tables are L2 resident and the kernel is bound by the latency of those reads, so
+//     it is written for occupancy (<= 64 registers, no shared memory, no barriers).
 template <int NVF>
-__global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
+__global__ void __launch_bounds__(128) face_bins_kernel(FeatParams p) {
   pdl_wait();
   constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
-  constexpr int ROWS = 64;
-  constexpr int RPW = ROWS / 8;   // rows per warp in phase 2
-  __shared__ unsigned short sbins[ROWS][NSLOT];
-  __shared__ int spf[ROWS];
-  const int lane = lane_id(), warp = warp_id();
   const int n_rows = p.counts->n_faces;
-  const int D = p.D, d4 = D >> 2;
-  for (int base = blockIdx.x * ROWS; base < n_rows; base += gridDim.x * ROWS) {
-    // ---- phase 1 ----
-    const int row = base + threadIdx.x;
-    if (threadIdx.x < ROWS && row < n_rows) {
-      const int pf = p.row_face[row];
-      const int b = pf / p.F;
-      const int64_t* fptr = p.faces + (size_t)pf * NVF;
-      float pos[NVF][3];
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
+    const int pf = p.row_face[row];
+    const int b = pf / p.F;
+    const int64_t* fptr = p.faces + (size_t)pf * NVF;
+    float pos[NVF][3];
 #pragma unroll
-      for (int k = 0; k < NVF; ++k) {
-        const long long v = fptr[k];
-        const float* src = p.vertices + ((size_t)b * p.V + (size_t)v) * 3;
-        pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
-      }
-      unsigned short* bins = sbins[threadIdx.x];
-      // coordinates: slot = vertex*3 + xyz (meshgpt_pytorch.py:732-733)
+    for (int k = 0; k < NVF; ++k) {
+      const long long v = fptr[k];
+      const float* src = p.vertices + ((size_t)b * p.V + (size_t)v) * 3;
+      pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
+    }
+    unsigned short bins[NSLOT];
+    // coordinates: slot = vertex*3 + xyz (meshgpt_pytorch.py:732-733)
 #pragma unroll
-      for (int k = 0; k < NVF; ++k)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          bins[k * 3 + c] = (unsigned short)discretize_rn(pos[k][c], p.coor_lo, p.coor_den, (float)p.n_coor, p.n_coor);
-      // angles between position vectors k and k-1 (meshgpt_pytorch.py:151-153, 164-166)
-      float un[NVF][3];
-#pragma unroll
-      for (int k = 0; k < NVF; ++k) unit3(pos[k], un[k]);
-#pragma unroll
-      for (int k = 0; k < NVF; ++k) {
-        const int km = (k + NVF - 1) % NVF;
-        float z = __fadd_rn(__fadd_rn(__fmul_rn(un[k][0], un[km][0]), __fmul_rn(un[k][1], un[km][1])), __fmul_rn(un[k][2], un[km][2]));
-        z = (z != z) ? z : fminf(fmaxf(z, p.clip_lo), p.clip_hi);  // torch.clamp propagates NaN
-        bins[NVF * 3 + k] = (unsigned short)discretize_rn(acosf(z), 0.f, p.angle_den, (float)p.n_angle, p.n_angle);
-      }
-      // edges: rows 0 and 1 of (p - prev); prev = one step back (tri) / two steps back (quad) (:168-172)
-      constexpr int SH = (NVF == 3) ? 1 : 2;
-      float e1[3], e2[3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        e1[c] = __fsub_rn(pos[0][c], pos[(0 + NVF - SH) % NVF][c]);
-        e2[c] = __fsub_rn(pos[1][c], pos[(1 + NVF - SH) % NVF][c]);
-      }
-      float cr[3];
-      cr[0] = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
-      cr[1] = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
-      cr[2] = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
-      const float cn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cr[0], cr[0]), __fmul_rn(cr[1], cr[1])), __fmul_rn(cr[2], cr[2])));
-      bins[NVF * 4] = (unsigned short)discretize_rn(__fmul_rn(cn, 0.5f), 0.f, p.area_den, (float)p.n_area, p.n_area);
-      const float cd = fmaxf(cn, 1e-12f);
+    for (int k = 0; k < NVF; ++k)
 #pragma unroll
       for (int c = 0; c < 3; ++c)
-        bins[NVF * 4 + 1 + c] = (unsigned short)discretize_rn(__fdiv_rn(cr[c], cd), p.coor_lo, p.coor_den, (float)p.n_normal, p.n_normal);
-      spf[threadIdx.x] = pf;
-      if (p.face_coords_out) {
+        bins[k * 3 + c] = (unsigned short)discretize_rn(pos[k][c], p.coor_lo, p.coor_den, (float)p.n_coor, p.n_coor);
+    // angles between position vectors k and k-1 (meshgpt_pytorch.py:151-153, 164-166)
+    float un[NVF][3];
 #pragma unroll
-        for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[(size_t)pf * (NVF * 3) + s] = bins[s];
+    for (int k = 0; k < NVF; ++k) unit3(pos[k], un[k]);
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      const int km = (k + NVF - 1) % NVF;
+      float z = __fadd_rn(__fadd_rn(__fmul_rn(un[k][0], un[km][0]), __fmul_rn(un[k][1], un[km][1])), __fmul_rn(un[k][2], un[km][2]));
+      z = (z != z) ? z : fminf(fmaxf(z, p.clip_lo), p.clip_hi);  // torch.clamp propagates NaN
+      bins[NVF * 3 + k] = (unsigned short)discretize_rn(acosf(z), 0.f, p.angle_den, (float)p.n_angle, p.n_angle);
+    }
+    // edges: rows 0 and 1 of (p - prev); prev = one step back (tri) / two steps back (quad) (:168-172)
+    constexpr int SH = (NVF == 3) ? 1 : 2;
+    float e1[3], e2[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      e1[c] = __fsub_rn(pos[0][c], pos[(0 + NVF - SH) % NVF][c]);
+      e2[c] = __fsub_rn(pos[1][c], pos[(1 + NVF - SH) % NVF][c]);
+    }
+    float cr[3];
+    cr[0] = __fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1]));
+    cr[1] = __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2]));
+    cr[2] = __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0]));
+    const float cn = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(cr[0], cr[0]), __fmul_rn(cr[1], cr[1])), __fmul_rn(cr[2], cr[2])));
+    bins[NVF * 4] = (unsigned short)discretize_rn(__fmul_rn(cn, 0.5f), 0.f, p.area_den, (float)p.n_area, p.n_area);
+    const float cd = fmaxf(cn, 1e-12f);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      bins[NVF * 4 + 1 + c] = (unsigned short)discretize_rn(__fdiv_rn(cr[c], cd), p.coor_lo, p.coor_den, (float)p.n_normal, p.n_normal);
+    // table row ids (slot offset + bin), 2 per 32-bit store
+    uint32_t* dst = reinterpret_cast<uint32_t*>(p.bins_out + (size_t)row * NSLOT);
+#pragma unroll
+    for (int s = 0; s < NSLOT; s += 2)
+      dst[s / 2] = (uint32_t)(p.slot_off[s] + bins[s]) | ((uint32_t)(p.slot_off[s + 1] + bins[s + 1]) << 16);
+    if (p.face_coords_out) {
+#pragma unroll
+      for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[(size_t)pf * (NVF * 3) + s] = bins[s];
+    }
+  }
+  pdl_launch_dependents();
+}
+
+template <int NVF>
+__global__ void __launch_bounds__(256, 4) face_sum_kernel(FeatParams p) {
+  pdl_wait();
+  constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
+  constexpr int H = NSLOT / 2;   // table rows in flight per lane at a time
+  const int lane = lane_id();
+  const int n_rows = p.counts->n_faces;
+  const int D = p.D, d4 = D >> 2;
+  const int items = 2 * d4;     // float4 columns of a pair of rows
+  const int n_warps = gridDim.x * (blockDim.x >> 5);
+  for (int pair = blockIdx.x * (blockDim.x >> 5) + warp_id(); 2 * pair < n_rows; pair += n_warps) {
+    const int r0 = 2 * pair;
+    const bool two = r0 + 1 < n_rows;
+    // lane s holds table row id s of row r0 (low half) and of row r0 + 1 (high half)
+    unsigned ids = 0;
+    if (lane < NSLOT) {
+      ids = p.bins_out[(size_t)r0 * NSLOT + lane];
+      if (two) ids |= (unsigned)p.bins_out[(size_t)(r0 + 1) * NSLOT + lane] << 16;
+    }
+    for (int item = lane; item < items; item += 32) {
+      const int second = item >= d4;
+      const int i4 = item - second * d4;
+      float4 acc = __ldg(reinterpret_cast<const float4*>(p.bias) + i4);
+      float4 t[H];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int s = 0; s < H; ++s) {
+          const unsigned both = __shfl_sync(0xffffffffu, ids, half * H + s);
+          const unsigned id = second ? (both >> 16) : (both & 0xffffu);
+          t[s] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)id * D) + i4);
+        }
+#pragma unroll
+        for (int s = 0; s < H; ++s) { acc.x += t[s].x; acc.y += t[s].y; acc.z += t[s].z; acc.w += t[s].w; }
+      }
+      const long long row = r0 + second;
+      if (!second || two) {
+        if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)row * D + i4 * 4) = acc;
+        if (p.x0_image) tc::image_store4(p.x0_image, D, row, i4 * 4, acc);
       }
     }
-    __syncthreads();
-    // ---- phase 2 ----
-    const int rows_here = min(ROWS, n_rows - base);
-    for (int r0 = warp * RPW; r0 < min(rows_here, warp * RPW + RPW); r0 += 2) {
-      const bool two = r0 + 1 < rows_here;
-      const unsigned short* ba = sbins[r0];
-      const unsigned short* bb = sbins[two ? r0 + 1 : r0];
-      for (int i4 = lane; i4 < d4; i4 += 32) {
-        const float4 bias = __ldg(reinterpret_cast<const float4*>(p.bias) + i4);
-        float4 acc_a = bias, acc_b = bias;
-        float4 ta[NSLOT], tb[NSLOT];
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          ta[s] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)(p.slot_off[s] + ba[s]) * D) + i4);
-          tb[s] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)(p.slot_off[s] + bb[s]) * D) + i4);
-        }
-#pragma unroll
-        for (int s = 0; s < NSLOT; ++s) {
-          acc_a.x += ta[s].x; acc_a.y += ta[s].y; acc_a.z += ta[s].z; acc_a.w += ta[s].w;
-          acc_b.x += tb[s].x; acc_b.y += tb[s].y; acc_b.z += tb[s].z; acc_b.w += tb[s].w;
-        }
-        const long long ra = base + r0;
-        if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)ra * D + i4 * 4) = acc_a;
-        if (p.x0_image) tc::image_store4(p.x0_image, D, ra, i4 * 4, acc_a);
-        if (two) {
-          if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)(ra + 1) * D + i4 * 4) = acc_b;
-          if (p.x0_image) tc::image_store4(p.x0_image, D, ra + 1, i4 * 4, acc_b);
-        }
-      }
-    }
-    __syncthreads();
   }
   pdl_launch_dependents();
 }
@@ -149,10 +158,19 @@ __global__ void __launch_bounds__(256) face_embed_kernel(FeatParams p) {
 
 int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(p.D % 4 == 0, "face_embed: dim_codebook must be a multiple of 4 (got %d)", p.D);
-  MT_CHECK_ARG(max(max(p.n_coor, p.n_angle), max(p.n_area, p.n_normal)) <= 65535, "face_embed: at most 65535 bins per feature");
-  const int blocks = max(1, min(ceil_div(max_rows, 64), 148 * 2));
-  if (p.nvf == 3) MT_LAUNCH_PDL(face_embed_kernel<3>, blocks, 256, 0, stream, p);
-  else MT_LAUNCH_PDL(face_embed_kernel<4>, blocks, 256, 0, stream, p);
+  MT_CHECK_ARG(p.bins_out != nullptr, "face_embed: no workspace for the bin ids");
+  {
+    int rows_total = 0;
+    rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
+    MT_CHECK_ARG(rows_total <= 65535, "face_embed: at most 65535 folded table rows (got %d)", rows_total);
+  }
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks1 = max(1, min(ceil_div(max_rows, 128), 148 * 16));
+  if (p.nvf == 3) MT_LAUNCH_PDL(face_bins_kernel<3>, blocks1, 128, 0, stream, p);
+  else MT_LAUNCH_PDL(face_bins_kernel<4>, blocks1, 128, 0, stream, p);
+  const int blocks2 = max(1, min(ceil_div(ceil_div(max_rows, 2), 8), 148 * 4));
+  if (p.nvf == 3) MT_LAUNCH_PDL(face_sum_kernel<3>, blocks2, 256, 0, stream, p);
+  else MT_LAUNCH_PDL(face_sum_kernel<4>, blocks2, 256, 0, stream, p);
   return MESHTOK_OK;
 }
 

@@ -19,6 +19,7 @@ struct FeatParams {
   float* x0;                // (rows, D) fp32 or null
   uint8_t* x0_image;        // split-bf16 activation image of x0 (tc_common.cuh) or null
   int64_t* face_coords_out; // (B,F,nvf*3) or null
+  uint16_t* bins_out;       // (rows, nvf*4+4) workspace: folded-table row id (slot offset + bin) of every slot of every packed row
 };
 int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
 
