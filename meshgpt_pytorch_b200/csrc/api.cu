@@ -244,7 +244,7 @@ int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* 
 // `resid` and the codes in vcodes (R x Q).
 int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes,
             unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, uint8_t* rimg, const int* n_dev, int max_rows,
-            bool exact, cudaStream_t s) {
+            bool exact, bool prepped, cudaStream_t s) {
   const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
   if (max_rows == 0) return MESHTOK_OK;
   int rc;
@@ -269,8 +269,10 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
   }
   uint8_t* row_image = variant == 2 ? rimg : nullptr;
   const float c_scale = m->codebook_image_scale / (2.f * rvq_e2_kappa(m->codebook_max_norm));   // powers of two: exact
-  { ProfScope ps(PROF_RVQ_PREP_UPDATE, s); rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, c_scale, n_dev, max_rows, s); }
-  if (rc != MESHTOK_OK) return rc;
+  if (!prepped) {   // (the pipeline's scatter_mean already left resid / rscale / the row image)
+    ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
+    if ((rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, c_scale, n_dev, max_rows, s)) != MESHTOK_OK) return rc;
+  }
   MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
   for (int level = 0; level < Q; ++level) {
     if (exact) {
@@ -568,7 +570,18 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     LinearRowEpilogue epi{0, nullptr, nullptr, nullptr, nullptr, enc_ssq, enc_ssq_parts};
     if ((rc = linear(simt, enc, enc_img, enc_dim(m), nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, nvf * D, n_faces_dev, max_rows, false, s,
                      enc_ssq ? &epi : nullptr)) != MESHTOK_OK) return rc; }
-  { ProfScope ps(PROF_SCATTER_MEAN, s); if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, s)) != MESHTOK_OK) return rc; }
+  const bool rvq_tc_path = !m->use_lfq && !a->rvq_exact && m->codebook_f16_tiles != nullptr;
+  { ProfScope ps(PROF_SCATTER_MEAN, s);
+    RvqPrepOut prep;
+    memset(&prep, 0, sizeof(prep));
+    if (rvq_tc_path) {
+      prep.resid = w.resid; prep.rscale = w.rscale;
+      if (rvq_tc_variant(m->codebook_size) == 2) {
+        prep.row_image = w.rimg;
+        prep.c_scale = m->codebook_image_scale / (2.f * rvq_e2_kappa(m->codebook_max_norm));
+      }
+    }
+    if ((rc = launch_scatter_mean(w.y, D, w.vptr, w.vinc, w.avg, w.counts, max_vrows, rvq_tc_path ? &prep : nullptr, s)) != MESHTOK_OK) return rc; }
   const float* pad_row = nullptr;
   if (m->use_lfq) {
     int bits = 0;
@@ -589,7 +602,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   } else {
     MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
     if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.packed, w.amb_list, w.amb_count, w.partial, w.rimg, n_vrows_dev, max_vrows,
-                      a->rvq_exact != 0, s)) != MESHTOK_OK) return rc;
+                      a->rvq_exact != 0, rvq_tc_path, s)) != MESHTOK_OK) return rc;
     if (a->quantized_out) {
       const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
       sub_rows_kernel<<<blocks, 256, 0, s>>>(w.avg, w.resid, w.qrows, D, n_vrows_dev, (long long)max_vrows * D);
@@ -666,7 +679,7 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
   MT_CHECK_LAUNCH();
-  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, s);
+  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, false, s);
   if (rc != MESHTOK_OK) return rc;
   if (residual_out && R > 0)
     MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));

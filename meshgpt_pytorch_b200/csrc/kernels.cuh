@@ -39,8 +39,15 @@ int launch_linear_simt(const float* A1, int K1, const float* A2, int K2, const f
 
 // ---- K6/K7/K8b/K9 --------------------------------------------------------------------------------
 // avg[vrow] = (sum over incidence entries e of y[e*D .. ]) / count      (scatter_mean, meshgpt_pytorch.py:243-257)
+// prep (optional): also leave every averaged row ready as level 0's residual of the residual VQ (what launch_rvq_prep does)
+struct RvqPrepOut {
+  float* resid;        // (rows, D) copy of avg, or null
+  float* rscale;       // (rows) power-of-two row scales
+  uint8_t* row_image;  // fp16 row image for the CTA-pair search, or null
+  float c_scale;
+};
 int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc, float* avg, const Counts* counts,
-                        int max_vrows, cudaStream_t stream);
+                        int max_vrows, const RvqPrepOut* prep, cudaStream_t stream);
 // residual LFQ codes of rows (R x D): codes (R x Q) int32; optional quantized_out (R x D) = project_out(sum q).
 int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, int bits, int Q, const float* w_out,
                const float* b_out, int32_t* codes, float* quantized_out, const int* n_rows_dev, int max_rows,

@@ -6,8 +6,11 @@
 // no (b, nf*nvf, d) int64 index tensor); ResidualLFQ (vector_quantize_pytorch, called at :842) becomes
 // log2(K) dot products + sign tests per vertex; the two get_at gathers and masked_fills (:856-866,
 // :1018) become one kernel that writes the final int64 codes and the codebook-usage histogram.
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
+#include "rvq_screen.cuh"
 
 namespace meshtok {
 
@@ -16,7 +19,7 @@ namespace {
 template <int PER2>  // float2 per lane: D <= 64 * PER2
 __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restrict__ y, int D, const int* __restrict__ vptr,
                                                            const int* __restrict__ vinc, float* __restrict__ avg,
-                                                           const Counts* counts) {
+                                                           const Counts* counts, RvqPrepOut prep) {
   pdl_wait();
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
@@ -41,10 +44,28 @@ __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restri
     }
     const float cnt = fmaxf((float)(e - s), 1e-5f);  // den.clamp(min = eps)
     float2* out = reinterpret_cast<float2*>(avg + (size_t)row * D);
+    float2 v[PER2];
+    float vmax = 0.f;
 #pragma unroll
     for (int i = 0; i < PER2; ++i) {
       const int c = lane + 32 * i;
-      if (c < d2) out[c] = make_float2(__fdiv_rn(acc[i].x, cnt), __fdiv_rn(acc[i].y, cnt));
+      v[i] = make_float2(0.f, 0.f);
+      if (c < d2) {
+        v[i] = make_float2(__fdiv_rn(acc[i].x, cnt), __fdiv_rn(acc[i].y, cnt));
+        out[c] = v[i];
+        vmax = fmaxf(vmax, fmaxf(fabsf(v[i].x), fabsf(v[i].y)));
+      }
+    }
+    if (prep.resid != nullptr) {
+      // the averaged vertex row is level 0's residual of the residual VQ: leave it ready for the screening search
+      // (copy, power-of-two row scale, fp16 row image) instead of running a separate preparation pass
+      float2* res = reinterpret_cast<float2*>(prep.resid + (size_t)row * D);
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d2) res[c] = v[i];
+      }
+      rvq_emit_row_scale_and_image<PER2>(v, vmax, row, D, prep.rscale, prep.row_image, prep.c_scale);
     }
   }
   pdl_launch_dependents();
@@ -194,11 +215,15 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float4* __restrict
 }  // namespace
 
 int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc, float* avg, const Counts* counts,
-                        int max_vrows, cudaStream_t stream) {
+                        int max_vrows, const RvqPrepOut* prep, cudaStream_t stream) {
   MT_CHECK_ARG(D % 2 == 0 && D <= 512, "scatter_mean: dim %d must be even and <= 512", D);
   const int blocks = max(1, min(ceil_div(max_vrows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define SM(P) MT_LAUNCH_PDL(scatter_mean_kernel<P>, blocks, 256, 0, stream, y, D, vptr, vinc, avg, counts)
+  RvqPrepOut po;
+  memset(&po, 0, sizeof(po));
+  if (prep) po = *prep;
+  MT_CHECK_ARG(po.row_image == nullptr || (D % 64 == 0 && po.c_scale > 0.f), "scatter_mean: a row image needs dim %% 64 == 0 and c_scale > 0");
+#define SM(P) MT_LAUNCH_PDL(scatter_mean_kernel<P>, blocks, 256, 0, stream, y, D, vptr, vinc, avg, counts, po)
   if (per2 <= 1) SM(1);
   else if (per2 <= 2) SM(2);
   else if (per2 <= 3) SM(3);

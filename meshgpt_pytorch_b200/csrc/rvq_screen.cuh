@@ -6,6 +6,7 @@
 // row go to the exact fp32 scan.  CHUNK = 4 keeps the exact re-evaluation at 4 codebook rows (3 KB) per candidate - the
 // re-score kernel is bound by those L2 reads, not by arithmetic - and TOPK = 4 makes the exact scan a rare event.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 
@@ -32,6 +33,53 @@ inline float rvq_e2_kappa(float max_norm) {
   e = e > 100 ? 100 : (e < -100 ? -100 : e);
   return ldexpf(1.f, -e);
 }   // float4 per partial entry: {b0, i0, b1, i1}, {b2, i2, b3, i3}
+
+// power of two s such that max|v| * s lies in [0.5, 1)  (1 for an all-zero row)
+__device__ __forceinline__ float rvq_pow2_scale(float vmax) {
+  if (!(vmax > 0.f) || !(vmax < INFINITY)) return 1.f;
+  int e;
+  frexpf(vmax, &e);  // vmax = m * 2^e, m in [0.5, 1)
+  e = max(-100, min(100, e));
+  return ldexpf(1.f, -e);
+}
+
+// One warp leaves one residual row ready for the next screening search: lane l holds columns 2 * (l + 32 i), + 1 in v[i].
+// rscale[row] = the row's power-of-two scale; row_image (optional, CTA-pair kernel): fp16(r * scale) at
+// [128-row tile]{[64-dim chunk][128 rows x 128 B, SWIZZLE_128B], 4 KB extra K block}, the extra block holding
+// c = scale * c_scale in columns 0 and 1 (it multiplies the codebook's (hi, lo) of -kappa |e|^2), zeros elsewhere.
+template <int PER2>
+__device__ __forceinline__ void rvq_emit_row_scale_and_image(const float2 (&v)[PER2], float vmax_lane, int row, int D, float* __restrict__ rscale,
+                                                             uint8_t* __restrict__ row_image, float c_scale) {
+  const int lane = threadIdx.x & 31;
+  const int d2 = D >> 1;
+  float vmax = vmax_lane;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  float sc = rvq_pow2_scale(vmax);
+  // the pair kernel multiplies the folded |e|^2 column by c = sc * c_scale, which must stay a finite fp16 power of two
+  if (row_image) sc = fminf(sc, 32768.f / c_scale);
+  if (lane == 0 && rscale) rscale[row] = sc;
+  if (row_image) {
+    uint8_t* tile = row_image + (size_t)(row >> 7) * rvq_image_tile_bytes(D);
+    const int r = row & 127;
+#pragma unroll
+    for (int i = 0; i < PER2; ++i) {
+      const int c = lane + 32 * i;
+      if (c < d2) {
+        const int k = 2 * c;
+        const __half2 h = __floats2half2_rn(v[i].x * sc, v[i].y * sc);
+        const uint32_t off = (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)r * 128u + ((uint32_t)(((k >> 3) ^ r) & 7) << 4) + (uint32_t)(k & 7) * 2u;
+        *reinterpret_cast<__half2*>(tile + off) = h;
+      }
+    }
+    if (lane < 2) {
+      const __half ch = __float2half_rn(sc * c_scale);
+      const __half2 cc = __halves2half2(ch, ch);
+      uint8_t* ex = tile + (size_t)128 * D * 2 + (size_t)(r >> 3) * RVQ_EXTRA_SBO + (size_t)(r & 7) * 16 + (size_t)lane * 128;
+      *reinterpret_cast<uint4*>(ex) = lane == 0 ? make_uint4(*reinterpret_cast<const uint32_t*>(&cc), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+}
 
 struct RvqTop {   // scalars (not arrays) so that everything stays in registers
   float b0, b1, b2, b3;

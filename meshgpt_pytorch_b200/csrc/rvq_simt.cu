@@ -143,15 +143,6 @@ __global__ void rvq_exact_init_kernel(const int* __restrict__ row_list, const in
   if (i < n) packed[row_list ? row_list[i] : i] = ~0ull;
 }
 
-// power of two s such that max|v| * s lies in [0.5, 1)  (1 for an all-zero row)
-__device__ __forceinline__ float pow2_scale(float vmax) {
-  if (!(vmax > 0.f) || !(vmax < INFINITY)) return 1.f;
-  int e;
-  frexpf(vmax, &e);  // vmax = m * 2^e, m in [0.5, 1)
-  e = max(-100, min(100, e));
-  return ldexpf(1.f, -e);
-}
-
 template <int PER2, bool UPDATE>   // float2 pairs per lane: D <= 64 * PER2
 __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict__ rows_in, float* __restrict__ rows, int D,
                                                          const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
@@ -189,35 +180,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
         vmax = fmaxf(vmax, fmaxf(fabsf(v[i].x), fabsf(v[i].y)));
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-    float sc = pow2_scale(vmax);
-    // the pair kernel multiplies the folded |e|^2 column by c = sc * c_scale, which must stay a finite fp16 power of two
-    if (row_image) sc = fminf(sc, 32768.f / c_scale);
-    if (lane == 0 && rscale) rscale[row] = sc;
-    if (row_image) {
-      // fp16(r * scale) at [128-row tile]{[64-dim chunk][128 rows x 128 B, SWIZZLE_128B], 4 KB extra K block} (what rvq_tc2.cu
-      // bulk-copies); the extra block holds c = scale * c_scale in columns 0 and 1 (times the codebook's (hi, lo) of
-      // -kappa |e|^2), zeros elsewhere
-      uint8_t* tile = row_image + (size_t)(row >> 7) * rvq_image_tile_bytes(D);
-      const int r = row & 127;
-#pragma unroll
-      for (int i = 0; i < PER2; ++i) {
-        const int c = lane + 32 * i;
-        if (c < d2) {
-          const int k = 2 * c;
-          const __half2 h = __floats2half2_rn(v[i].x * sc, v[i].y * sc);
-          const uint32_t off = (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)r * 128u + ((uint32_t)(((k >> 3) ^ r) & 7) << 4) + (uint32_t)(k & 7) * 2u;
-          *reinterpret_cast<__half2*>(tile + off) = h;
-        }
-      }
-      if (lane < 2) {
-        const __half ch = __float2half_rn(sc * c_scale);
-        const __half2 cc = __halves2half2(ch, ch);
-        uint8_t* ex = tile + (size_t)128 * D * 2 + (size_t)(r >> 3) * RVQ_EXTRA_SBO + (size_t)(r & 7) * 16 + (size_t)lane * 128;
-        *reinterpret_cast<uint4*>(ex) = lane == 0 ? make_uint4(*reinterpret_cast<const uint32_t*>(&cc), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
-      }
-    }
+    rvq_emit_row_scale_and_image<PER2>(v, vmax, row, D, rscale, row_image, c_scale);
   }
   pdl_launch_dependents();
 }
