@@ -62,7 +62,7 @@ struct Workspace {
   int* amb_count;
   float4* partial;
   uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
-  float* ssq;        // (B*F, 8): parts of the squared row norms of the last SAGE layer (deferred normalisation)
+  float* ssq;        // (B*F, 16): parts of the squared row norms of the last SAGE layer (deferred normalisation)
   uint16_t* bins;    // (B*F, nvf*4+4): folded-table row ids of every packed row
   size_t total;
 };
@@ -188,7 +188,7 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->img_x[0] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_x[1] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
-  w->ssq = c.take<float>(BF * 8);
+  w->ssq = c.take<float>(BF * 16);
   w->bins = c.take<uint16_t>(BF * (size_t)(m->nvf * 4 + 4));
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
@@ -518,7 +518,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       const bool fused = !simt && linear_tc_fused_norm_ok(ly.dim_out, mode) == MESHTOK_OK;
       // a last layer too wide for the fused epilogue leaves its rows un-normalised (image + squared norms) and
       // project_dim_codebook divides by the norm in ITS epilogue: W (x / |x|) + b = (W x) / |x| + b
-      const bool deferred = !simt && !fused && last && !first && linear_tc_ssq_parts(ly.dim_out) <= 8;
+      const bool deferred = !simt && !fused && last && !first && linear_tc_ssq_parts(ly.dim_out) <= 16;
       const bool need_fp32 = a->keep_taps || (last && (a->encoded_out != nullptr || a->stop_after_encode));
       // xp = relu(lin(x))
       { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }

@@ -24,6 +24,8 @@
 //     straight into the NEXT linear's activation image: 16 B hi + 16 B lo per 8 columns, 8 lanes = 128 contiguous bytes.
 // Warp roles (384 threads): w0 producer, w1 MMA issuer, w2 TMEM allocator, w3 idle, w4-11 epilogue
 // (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -36,22 +38,37 @@ using namespace tc;
 
 constexpr int M_TILE = IMG_ROWS;   // 128
 constexpr int KC = IMG_KC;         // 32
-constexpr int STAGES = 4;
 constexpr int NT_MAX = 256;
-constexpr int NUM_THREADS = 384;
-constexpr int EPI_WARPS = 8;
 constexpr uint32_t SBO = (KC / 8) * 128;                   // 512
 constexpr uint32_t A_PART = IMG_PART;                      // 8 KB (hi or lo)
-constexpr uint32_t W_PART_MAX = NT_MAX * KC * 2;           // 16 KB
-constexpr uint32_t STAGE_BYTES = 2 * A_PART + 2 * W_PART_MAX;  // 48 KB
-constexpr uint32_t BAR_OFF = STAGES * STAGE_BYTES;
 constexpr int EPI_LD = 20;                                 // padded row length (floats) of the 32 x 16 epilogue staging tiles
-constexpr uint32_t EPI_OFF = BAR_OFF + 256;
-constexpr uint32_t XCH_OFF = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;   // [2 unit parities][3 sums][2 halves][128 rows] floats
-constexpr uint32_t VEC_OFF = XCH_OFF + 2 * 3 * 2 * 128 * 4;          // bias (N <= 1024), gamma, beta (N <= 64) staged once per CTA
 constexpr int VEC_MAX_N = 1024;
-constexpr uint32_t SMEM_TOTAL = VEC_OFF + (VEC_MAX_N + 2 * 64) * 4;
-static_assert(SMEM_TOTAL <= 227 * 1024, "shared memory budget");
+
+// PAIR = two CTAs of a cluster work on one 256-row tile with tcgen05.mma.cta_group::2: every CTA stages its own 128 rows
+// of A and HALF of the W chunk, so the bytes pulled from L2 per MMA cycle drop from (128 + NT) to (128 + NT / 2) rows.
+// ncu on the single-CTA kernel (profiles/r01h_*) had the two widest linears at 10.5 TB/s of L2 -> SM traffic, the
+// measured cap of the L2 slices, with the tensor pipe waiting.
+template <bool PAIR, int CPARTS_>
+struct Cfg {
+  static constexpr int MAX_STAGES = 10;
+  static constexpr int CPARTS = CPARTS_;                   // column parts of a pass = epilogue warps per TMEM lane quarter
+  static constexpr int EPI_WARPS = 4 * CPARTS;
+  static constexpr int NUM_THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr uint32_t BAR_OFF = 0;
+  static constexpr uint32_t EPI_OFF = BAR_OFF + 256;
+  static constexpr uint32_t XCH_OFF = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;      // [2 unit parities][3 sums][CPARTS][128 rows] floats
+  static constexpr uint32_t VEC_OFF = XCH_OFF + 2 * 3 * CPARTS * 128 * 4;         // bias (N <= 1024), gamma, beta (N <= 64) staged once per CTA
+  static constexpr uint32_t RING_OFF = (VEC_OFF + (VEC_MAX_N + 2 * 64) * 4 + 127) / 128 * 128;
+  static constexpr uint32_t SMEM_TOTAL = 227 * 1024;
+  // stage = own A block (hi + lo, 16 KB) + the W rows this CTA stages (hi + lo); as many stages as fit, the smaller the
+  // pass the deeper the ring (a CTA pair's stage round trip crosses the cluster twice and needs the depth)
+  __host__ __device__ static constexpr uint32_t stage_bytes(int NT) { return 2 * A_PART + 2 * (uint32_t)(PAIR ? NT / 2 : NT) * KC * 2; }
+  __host__ __device__ static constexpr int stages(int NT) {
+    const int n = (int)((SMEM_TOTAL - RING_OFF) / stage_bytes(NT));
+    return n < MAX_STAGES ? n : MAX_STAGES;
+  }
+};
+static_assert(Cfg<false, 2>::stages(NT_MAX) >= 4 && Cfg<true, 2>::stages(NT_MAX) >= 6, "shared memory budget");
 
 struct LinArgs {
   const uint8_t* a1_image;
@@ -69,7 +86,7 @@ struct LinArgs {
   const float* beta;
   uint8_t* out_image;       // activation image of the output rows (K = N) or null
   // plain mode, deferred row normalisation (layers too wide for the fused epilogue):
-  float* ssq_out;           // (M, 2 * passes): sum of squares of this CTA's part of every output row, or null
+  float* ssq_out;           // (M, CPARTS * passes): sum of squares of this warp's part of every output row, or null
   const float* row_ssq;     // (M, row_ssq_parts): parts of |x_row|^2 of the INPUT rows; C = acc / max(|x|, 1e-12) + bias
   int row_ssq_parts;
 };
@@ -84,122 +101,190 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
+template <bool PAIR, int CPARTS>
+__device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
+  using G = Cfg<PAIR, CPARTS>;
+  constexpr int EPI_WARPS = G::EPI_WARPS;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BAR_OFF);
-  uint64_t* full = bars;               // [STAGES]  producer (expect_tx of both copies)
-  uint64_t* empty = bars + STAGES;     // [STAGES]  MMA commit
-  uint64_t* acc_full = empty + STAGES; // [2]
-  uint64_t* acc_empty = acc_full + 2;  // [2]
+  const int STAGES = G::stages(a.NT);
+  const uint32_t stage_bytes = G::stage_bytes(a.NT);
+  uint8_t* ring = smem + G::RING_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
+  uint64_t* full = bars;                        // [STAGES]  producer expect_tx (+ in a pair, on the leader: the peer's forwarded arrival)
+  uint64_t* empty = bars + G::MAX_STAGES;       // [STAGES]  MMA commit (multicast to both CTAs of a pair)
+  uint64_t* acc_full = empty + G::MAX_STAGES;   // [2]
+  uint64_t* acc_empty = acc_full + 2;  // [2]       (in a pair the leader's are the ones waited on)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = warp_id(), lane = lane_id();
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
   const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
   const int kchunks = kch1 + kch2;
-  const uint32_t w_part = (uint32_t)a.NT * KC * 2;
+  const uint32_t w_part = (uint32_t)a.NT * KC * 2;          // hi (or lo) bytes of one W chunk
+  const uint32_t w_mine = PAIR ? w_part / 2 : w_part;       // ... of the rows this CTA stages
 
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], EPI_WARPS); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], PAIR && leader ? 2 : 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * EPI_WARPS); }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(tmem_slot, 512);
+    else tmem_alloc(tmem_slot, 512);
+  }
   // bias / gamma / beta -> shared memory (the epilogue reads them per 16-column block; as global loads they sat on its
   // critical path)
-  float* sbias = reinterpret_cast<float*>(smem + VEC_OFF);
+  float* sbias = reinterpret_cast<float*>(smem + G::VEC_OFF);
   float* sgamma = sbias + VEC_MAX_N;
   float* sbeta = sgamma + 64;
-  for (int i = threadIdx.x; i < a.N; i += NUM_THREADS) {
+  for (int i = threadIdx.x; i < a.N; i += G::NUM_THREADS) {
     sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
     if (a.norm_mode == 2) { sgamma[i] = __ldg(a.gamma + i); sbeta[i] = __ldg(a.beta + i); }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // everything above is independent of earlier kernels; from here on their results are read
   pdl_wait();
   const int M = a.m_dev ? min(*a.m_dev, a.m_max) : a.m_max;
   const int m_tiles = (M + M_TILE - 1) / M_TILE;
-  const int units = m_tiles * a.passes;
+  const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;   // a group = the row tile(s) one MMA covers
+  const int units = m_groups * a.passes;
+  const int u0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0) {
-    // ===== producer (warp-converged; one elected lane issues): one A block (16 KB) + one W block (2 * NT * 64 B) per stage =====
-    uint32_t it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x) {
-      const int m_tile = u / a.passes, pass = u % a.passes;
-      const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part);
+    // ===== producer (warp-converged; one elected lane issues): own A block (16 KB) + own rows of the W chunk per stage =====
+    uint32_t it = 0, s = 0, ph = 0;
+    for (int u = u0; u < units; u += ustep) {
+      const int grp = u / a.passes, pass = u % a.passes;
+      const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
+      const bool have_a = m_tile < m_tiles;   // an odd tile count leaves the peer of the last pair without rows
+      const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part) + (size_t)rank * w_mine;
       const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
       const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
       for (int kc = 0; kc < kchunks; ++kc, ++it) {
-        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], IMG_BLOCK + 2 * w_part);
-          uint8_t* stage = smem + s * STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], (have_a ? IMG_BLOCK : 0u) + 2 * w_mine);
+          uint8_t* stage = ring + s * stage_bytes;
           const uint8_t* asrc = kc < kch1 ? a1src + (size_t)kc * IMG_BLOCK : a2src + (size_t)(kc - kch1) * IMG_BLOCK;
-          bulk_g2s(stage, asrc, IMG_BLOCK, &full[s]);
-          bulk_g2s(stage + 2 * A_PART, wsrc + (size_t)kc * (2 * w_part), 2 * w_part, &full[s]);
+          if (have_a) bulk_g2s(stage, asrc, IMG_BLOCK, &full[s]);
+          const uint8_t* wc = wsrc + (size_t)kc * (2 * w_part);
+          if (PAIR) {
+            bulk_g2s(stage + 2 * A_PART, wc, w_mine, &full[s]);
+            bulk_g2s(stage + 2 * A_PART + w_mine, wc + w_part, w_mine, &full[s]);
+          } else {
+            bulk_g2s(stage + 2 * A_PART, wc, 2 * w_part, &full[s]);
+          }
         }
         __syncwarp();
+        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+    if (PAIR) {   // drain: every multicast commit aimed at this CTA has landed before the CTA may exit
+      const uint32_t pending = it < (uint32_t)STAGES ? it : (uint32_t)STAGES;
+      for (uint32_t i = 0; i < pending; ++i) {
+        const uint32_t j = it - 1 - i;
+        mbar_wait(&empty[j % STAGES], (j / STAGES) & 1);
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (warp-converged; one elected lane issues) =====
-    const uint32_t idesc = make_idesc_f16_f32(M_TILE, a.NT, /*bf16=*/true);
-    const uint32_t s0 = smem_u32(smem);
-    uint32_t it = 0, acc_it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
-      const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
-      mbar_wait(&acc_empty[buf], aph ^ 1);
-      tcgen05_fence_after();
-      const uint32_t d = tmem_base + buf * NT_MAX;
-      for (int kc = 0; kc < kchunks; ++kc, ++it) {
-        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+    // ===== MMA issuer (the leader CTA of a pair; warp-converged, one elected lane issues) =====
+    if (leader) {
+      const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * M_TILE : M_TILE, a.NT, /*bf16=*/true);
+      const uint32_t s0 = smem_u32(ring);
+      uint32_t acc_it = 0, s = 0, ph = 0;
+      for (int u = u0; u < units; u += ustep, ++acc_it) {
+        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+        mbar_wait(&acc_empty[buf], aph ^ 1);
         tcgen05_fence_after();
-        if (elect_one()) {
-          const uint32_t ah = s0 + s * STAGE_BYTES, al = ah + A_PART;
-          const uint32_t wh = ah + 2 * A_PART, wl = wh + w_part;
+        const uint32_t d = tmem_base + buf * NT_MAX;
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&full[s], ph);
+          tcgen05_fence_after();
+          if (elect_one()) {
+            const uint32_t ah = s0 + s * stage_bytes, al = ah + A_PART;
+            const uint32_t wh = ah + 2 * A_PART, wl = wh + w_mine;
 #pragma unroll
-          for (int k16 = 0; k16 < KC / 16; ++k16) {
-            const uint32_t ko = k16 * 256;
-            const uint64_t dah = make_smem_desc(ah + ko, 128, SBO), dal = make_smem_desc(al + ko, 128, SBO);
-            const uint64_t dwh = make_smem_desc(wh + ko, 128, SBO), dwl = make_smem_desc(wl + ko, 128, SBO);
-            umma_f16(d, dal, dwh, idesc, (kc | k16) != 0 ? 1u : 0u);  // small terms first
-            umma_f16(d, dah, dwl, idesc, 1u);
-            umma_f16(d, dah, dwh, idesc, 1u);
+            for (int k16 = 0; k16 < KC / 16; ++k16) {
+              const uint32_t ko = k16 * 256;
+              const uint64_t dah = make_smem_desc(ah + ko, 128, SBO), dal = make_smem_desc(al + ko, 128, SBO);
+              const uint64_t dwh = make_smem_desc(wh + ko, 128, SBO), dwl = make_smem_desc(wl + ko, 128, SBO);
+              const uint32_t acc = (kc | k16) != 0 ? 1u : 0u;
+              if (PAIR) {
+                umma_f16_pair(d, dal, dwh, idesc, acc);  // small terms first
+                umma_f16_pair(d, dah, dwl, idesc, 1u);
+                umma_f16_pair(d, dah, dwh, idesc, 1u);
+              } else {
+                umma_f16(d, dal, dwh, idesc, acc);
+                umma_f16(d, dah, dwl, idesc, 1u);
+                umma_f16(d, dah, dwh, idesc, 1u);
+              }
+            }
+            if (PAIR) umma_commit_pair_mc(&empty[s], 3);
+            else umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+        }
+        if (elect_one()) {
+          if (PAIR) umma_commit_pair_mc(&acc_full[buf], 3);
+          else umma_commit(&acc_full[buf]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&acc_full[buf]);
-      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ===== completion forwarder (peer CTA of a pair): tells the leader that this CTA's copies have landed; lane s follows stage s =====
+    if (PAIR && !leader && lane < STAGES) {
+      const int my_units = u0 < units ? (units - u0 + ustep - 1) / ustep : 0;
+      const uint32_t total_it = (uint32_t)my_units * (uint32_t)kchunks;
+      const uint32_t remote = mapa_shared(smem_u32(&full[lane]), 0);
+      uint32_t ph = 0;
+      for (uint32_t it = lane; it < total_it; it += STAGES, ph ^= 1) {
+        mbar_wait(&full[lane], ph);
+        // relaxed: the bytes are in this CTA's shared memory once the phase flips, and only the tensor core reads them.
+        // (A release.cluster arrive costs a full memory barrier per stage; ncu had this warp in membar stalls most of
+        // the time and the leader's MMA warp waiting for it.)
+        mbar_arrive_cluster_relaxed(remote);
+      }
     }
   } else if (warp >= 4) {
-    // ===== epilogue =====
+    // ===== epilogue (both CTAs of a pair, each on its own 128 rows) =====
     const int ew = warp - 4;
     const int q = warp & 3;
-    const int chalf = ew >> 2;   // which half of the NT columns this warp stores
-    float* stage = reinterpret_cast<float*>(smem + EPI_OFF) + ew * (32 * EPI_LD);
+    const int cpart = ew >> 2;   // which part of the NT columns this warp handles
+    float* stage = reinterpret_cast<float*>(smem + G::EPI_OFF) + ew * (32 * EPI_LD);
+    const uint32_t acc_empty_remote0 = PAIR ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
+    const uint32_t acc_empty_remote1 = PAIR ? mapa_shared(smem_u32(&acc_empty[1]), 0) : 0u;
+    const int part_cols = (((a.NT + CPARTS - 1) / CPARTS + 15) / 16) * 16;
+    const int c_lo = min(a.NT, cpart * part_cols), c_hi = min(a.NT, c_lo + part_cols);
     uint32_t acc_it = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++acc_it) {
-      const int m_tile = u / a.passes, pass = u % a.passes;
+    for (int u = u0; u < units; u += ustep, ++acc_it) {
+      const int grp = u / a.passes, pass = u % a.passes;
+      const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT_MAX;
       const int n0 = pass * a.NT;
       const int row0 = m_tile * M_TILE + q * 32;
-      const int half_cols = ((a.NT / 2 + 15) / 16) * 16;
-      const int c_lo = chalf * half_cols, c_hi = chalf ? a.NT : min(a.NT, half_cols);
       if (a.norm_mode != 0) {
         // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0) ----
-        float* xs = reinterpret_cast<float*>(smem + XCH_OFF) + (acc_it & 1) * (3 * 256);
+        float* xs = reinterpret_cast<float*>(smem + G::XCH_OFF) + (acc_it & 1) * (3 * CPARTS * 128);
         const int rit = q * 32 + lane;
         const long long grow = (long long)row0 + lane;
         const bool live = grow < M;
+        auto xsum = [&](int k) {   // row total of exchange slot k over the column parts
+          float t = 0.f;
+#pragma unroll
+          for (int p = 0; p < CPARTS; ++p) t += xs[(k * CPARTS + p) * 128 + rit];
+          return t;
+        };
         auto put = [&](int c, const float (&o)[16]) {   // 16 consecutive columns of this thread's row
           if (!live) return;
           if (a.C) {
@@ -232,6 +317,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
             o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
           }
         };
+        // x / max(|x|, eps) is done as x * (1 / max(|x|, eps)): one rounding more than the reference's division, far
+        // below the 1e-5 of the split-bf16 product itself, at a tenth of the instructions
         if (a.norm_mode == 1) {
           float ss = 0.f;
           for (int c = c_lo; c < c_hi; c += 16) {
@@ -240,14 +327,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) ss = fmaf(o[j], o[j], ss);
           }
-          xs[chalf * 128 + rit] = ss;
+          xs[cpart * 128 + rit] = ss;
           named_bar_sync(2, EPI_WARPS * 32);
-          const float den = fmaxf(sqrtf(xs[rit] + xs[128 + rit]), 1e-12f);
+          const float inv = 1.f / fmaxf(sqrtf(xsum(0)), 1e-12f);
           for (int c = c_lo; c < c_hi; c += 16) {
             float o[16];
             load16(c, o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = __fdiv_rn(o[j], den);
+            for (int j = 0; j < 16; ++j) o[j] *= inv;
             put(c, o);
           }
         } else {
@@ -261,20 +348,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           float ss = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) { ss = fmaf(o0[j], o0[j], ss); ss = fmaf(o1[j], o1[j], ss); }
-          xs[chalf * 128 + rit] = ss;
+          xs[cpart * 128 + rit] = ss;
           named_bar_sync(2, EPI_WARPS * 32);
-          const float den = fmaxf(sqrtf(xs[rit] + xs[128 + rit]), 1e-12f);
+          const float inv = 1.f / fmaxf(sqrtf(xsum(0)), 1e-12f);
           float sum = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float t0 = __fdiv_rn(o0[j], den), t1 = __fdiv_rn(o1[j], den);
+            const float t0 = o0[j] * inv, t1 = o1[j] * inv;
             o0[j] = h0 ? __fdiv_rn(t0, 1.f + expf(-t0)) : 0.f;
             o1[j] = h1 ? __fdiv_rn(t1, 1.f + expf(-t1)) : 0.f;
             sum += o0[j] + o1[j];
           }
-          xs[256 + chalf * 128 + rit] = sum;
+          xs[(CPARTS + cpart) * 128 + rit] = sum;
           named_bar_sync(2, EPI_WARPS * 32);
-          const float mean = (xs[256 + rit] + xs[256 + 128 + rit]) / (float)a.N;
+          const float mean = xsum(1) / (float)a.N;
           float var = 0.f;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -282,9 +369,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
             var = fmaf(d0, d0, var);
             var = fmaf(d1, d1, var);
           }
-          xs[512 + chalf * 128 + rit] = var;
+          xs[(2 * CPARTS + cpart) * 128 + rit] = var;
           named_bar_sync(2, EPI_WARPS * 32);
-          const float rstd = 1.f / sqrtf((xs[512 + rit] + xs[512 + 128 + rit]) / (float)a.N + 1e-5f);
+          const float rstd = 1.f / sqrtf(xsum(2) / (float)a.N + 1e-5f);
           if (h0) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) o0[j] = (o0[j] - mean) * rstd * sgamma[c_lo + j] + sbeta[c_lo + j];
@@ -359,22 +446,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_tc_kernel(LinArgs a) {
           __syncwarp();
         }
       }
-      if (a.ssq_out && live) a.ssq_out[(size_t)grow * (2 * a.passes) + 2 * pass + chalf] = ss;
+      if (a.ssq_out && live) a.ssq_out[(size_t)grow * (CPARTS * a.passes) + CPARTS * pass + cpart] = ss;
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) {   // the TMEM reads are complete (wait::ld); nothing is handed over through memory, hence relaxed
+        if (leader) mbar_arrive(&acc_empty[buf]);
+        else mbar_arrive_cluster_relaxed(buf ? acc_empty_remote1 : acc_empty_remote0);
+      }
     }
   }
 
   pdl_launch_dependents();   // this CTA's work is done: let the next kernel's CTAs start their prologue
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // nothing of the pair is still in flight towards either CTA
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if (PAIR) tmem_dealloc_pair(tmem_base, 512);
+    else tmem_dealloc(tmem_base, 512);
   }
 }
+
+__global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_kernel(LinArgs a) { linear_tc_body<false, 2>(a); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_kernel(LinArgs a) { linear_tc_body<true, 2>(a); }
 
 // W (N, K) fp32 -> image [pass][kchunk]{hi (NT x 32), lo (NT x 32)} canonical K-major, SBO 512.
 __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restrict__ W, int N, int K, int NT, uint8_t* __restrict__ image) {
@@ -441,6 +536,14 @@ int linear_tc_fused_norm_ok(int N, int norm_mode) {
   return MESHTOK_OK;
 }
 
+// CTA pairs unless MESHTOK_LINEAR_TC=1 asks for the single-CTA kernel (kept for A/B runs).  (A pair kernel with 16
+// epilogue warps was tried too: 96 registers per thread -> spills, and a shallower ring; slower than 8 warps.)
+static bool linear_tc_pair() {
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("MESHTOK_LINEAR_TC"); pair = (e && atoi(e) == 1) ? 0 : 1; }
+  return pair == 1;
+}
+
 int linear_tc_ssq_parts(int N) { return 2 * ceil_div(N, NT_MAX); }
 
 size_t linear_tc_image_bytes(int N, int K) { return (size_t)N * K * 4; }
@@ -500,12 +603,21 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
   if (rc != MESHTOK_OK) return rc;
   static bool configured = false;
   if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
+    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
     configured = true;
   }
-  const int units = ceil_div(m_max, M_TILE) * a.passes;
-  const int grid = min(units, 148);
-  MT_LAUNCH_PDL(linear_tc_kernel, grid, NUM_THREADS, SMEM_TOTAL, stream, a);
+  if (linear_tc_pair()) {
+    using P2 = Cfg<true, 2>;
+    const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * a.passes;
+    const int grid = 2 * min(units, 148 / 2);
+    MT_LAUNCH_PDL(linear_tc_pair_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, a);
+  } else {
+    using S2 = Cfg<false, 2>;
+    const int units = ceil_div(m_max, M_TILE) * a.passes;
+    const int grid = min(units, 148);
+    MT_LAUNCH_PDL(linear_tc_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, a);
+  }
   return MESHTOK_OK;
 }
 

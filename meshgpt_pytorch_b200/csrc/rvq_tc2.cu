@@ -222,13 +222,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
         uint32_t ph = 0;
         for (uint32_t it = lane; it < total_it; it += STAGES, ph ^= 1) {
           mbar_wait(&b_full[lane], ph);
-          mbar_arrive_cluster(remote);
+          mbar_arrive_cluster_relaxed(remote);   // see linear_tc.cu: no data travels with this arrival, a release fence per stage is wasted time
         }
       } else if (lane == STAGES) {
         const uint32_t remote = mapa_shared(smem_u32(a_full), 0);
         for (uint32_t i = 0; i < n_a; ++i) {
           mbar_wait(a_full, i & 1);
-          mbar_arrive_cluster(remote);
+          mbar_arrive_cluster_relaxed(remote);
         }
       }
     }

@@ -88,7 +88,10 @@ __global__ void __launch_bounds__(384, 1) mma_bench(long long* cycles, const uin
           const uint32_t d = tmem_base + (it & 1) * 256;
 #pragma unroll
           for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t da = make_smem_desc_sw128(a0 + k16 * 32), db = make_smem_desc_sw128(b0 + k16 * 32);
+            // mode bit 3: SWIZZLE_NONE canonical K-major operands (32-wide K chunks: LBO 128, SBO 512) as the split-bf16 linear uses
+            const uint32_t ko = (mode & 8) ? (k16 & 1) * 256 + (k16 >> 1) * 8192 : k16 * 32;
+            const uint64_t da = (mode & 8) ? make_smem_desc(a0 + (k16 & 1) * 256 + (k16 >> 1) * 4096, 128, 512) : make_smem_desc_sw128(a0 + ko);
+            const uint64_t db = (mode & 8) ? make_smem_desc(b0 + ko, 128, 512) : make_smem_desc_sw128(b0 + ko);
             if (CG == 1) umma_f16(d, da, db, idesc, k16 ? 1u : 0u);
             else umma_f16_pair(d, da, db, idesc, k16 ? 1u : 0u);
           }
@@ -199,7 +202,15 @@ int main() {
   run<128, 1>(4, d_cycles, gsrc, d_ld);
   run<256, 1>(4, d_cycles, gsrc, d_ld);
   run<256, 2>(4, d_cycles, gsrc, d_ld);
-  for (int mode = 0; mode < 2; ++mode) {
+  for (int mode = 8; mode < 12; ++mode) {   // SWIZZLE_NONE operands: alone, + tcgen05.ld, + bulk copies, + both
+    run<128, 1>(mode, d_cycles, gsrc, d_ld);
+    run<192, 1>(mode, d_cycles, gsrc, d_ld);
+    run<256, 1>(mode, d_cycles, gsrc, d_ld);
+    run<192, 2>(mode, d_cycles, gsrc, d_ld);
+    run<256, 2>(mode, d_cycles, gsrc, d_ld);
+  }
+  for (int mode = 0; mode < 4; ++mode) {
+    run<192, 2>(mode, d_cycles, gsrc, d_ld);
     run<64, 1>(mode, d_cycles, gsrc, d_ld);
     run<128, 1>(mode, d_cycles, gsrc, d_ld);
     run<192, 1>(mode, d_cycles, gsrc, d_ld);
