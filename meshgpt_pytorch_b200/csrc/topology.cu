@@ -57,12 +57,6 @@ __device__ __forceinline__ int warp_emit_bits(const uint32_t* words, int wlo, in
   return base;
 }
 
-__device__ __forceinline__ int warp_count_bits(const uint32_t* words, int wlo, int whi) {
-  int c = 0;
-  for (int w = wlo + lane_id(); w <= whi; w += 32) c += __popc(words[w]);
-  return warp_sum_int(c);
-}
-
 template <int MODE, int NVF>   // NVF compile-time: the (face, slot) index arithmetic divides by it everywhere
 __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   extern __shared__ int smem[];
@@ -178,93 +172,99 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   __syncthreads();
 
   // ---- 3. adjacency ---------------------------------------------------------------------------
-  // counting: degrees only (MODE_COUNT: both, to global; MODE_CSR: in-degree into fptr[]);  else: emit the
+  // One thread per face.  The incidence lists are sorted, so a k-way merge over the lists of the face's distinct
+  // vertices visits every candidate face k exactly once and in ascending order - no bitmap, no sort, no warp
+  // reductions.  (The first version gave a warp to every face and collected the neighbours in per-warp bitmaps: ~6 of
+  // 32 lanes had a list entry to look at and every face paid a dozen warp-wide reductions; 100 us for 64 x 800 faces.)
+  // visit(k, n_ik, n_ki): n_ik = vertex slots of i found in k, n_ki = vertex slots of k found in i.
+  auto for_each_candidate = [&](const int i, auto&& visit) {
+    int mine[4], pos[4], end[4], head[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) mine[c] = c < nvf ? fv[i * nvf + c] : -2 - c;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      pos[c] = 0; end[c] = 0;
+      if (c < nvf) {
+        bool dup = false;
+#pragma unroll
+        for (int c0 = 0; c0 < 4; ++c0) dup |= c0 < c && mine[c0] == mine[c];
+        if (!dup) { pos[c] = vstart[mine[c]]; end[c] = vstart[mine[c] + 1]; }   // a repeated vertex: same list again
+      }
+      head[c] = pos[c] < end[c] ? inc[pos[c]] / nvf : INT_MAX;
+    }
+    for (;;) {
+      int k = INT_MAX;
+#pragma unroll
+      for (int c = 0; c < nvf; ++c) k = min(k, head[c]);
+      if (k == INT_MAX) break;
+#pragma unroll
+      for (int c = 0; c < nvf; ++c) {
+        while (head[c] == k) {   // a face with a repeated vertex sits in the list once per slot
+          ++pos[c];
+          head[c] = pos[c] < end[c] ? inc[pos[c]] / nvf : INT_MAX;
+        }
+      }
+      int other[4];
+#pragma unroll
+      for (int d = 0; d < 4; ++d) other[d] = d < nvf ? fv[k * nvf + d] : -7 - d;
+      int n_ik = 0, n_ki = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        bool in_k = false, in_i = false;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          in_k |= mine[a] == other[d];
+          in_i |= other[a] == mine[d];
+        }
+        n_ik += (a < nvf) && in_k;
+        n_ki += (a < nvf) && in_i;
+      }
+      visit(k, n_ik, n_ki);
+    }
+  };
+  // counting: degrees only (MODE_COUNT: both, to global; CSR modes: in-degree into fptr[]);  else: emit the
   // neighbours in ascending order at fptr[i] (dense list by source / CSR by target).
   auto adjacency = [&](const bool counting, const int face_off, const int edge_off) {
-    uint32_t* obits = bits + warp * Ww;
-    uint32_t* ibits = obits + Wf;
     const int thr = p.threshold;
     const bool keep3 = p.include_self != 0;
-    for (int i = warp; i < F; i += nwarps) {
-      int wmin = INT_MAX, wmax = -1;
+    int total_out = 0;
+    for (int i = tid; i < F; i += nt) {
+      int dout = 0, din = 0, r = 0;
       if (face_valid(i)) {
-        int mine[4];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) mine[c] = c < nvf ? fv[i * nvf + c] : -2 - c;
-        for (int c = 0; c < nvf; ++c) {
-          const int v = mine[c];
-          bool dup = false;
-          for (int c0 = 0; c0 < c; ++c0) dup |= mine[c0] == v;
-          if (dup) continue;  // same list again
-          const int s = vstart[v], e = vstart[v + 1];
-          for (int q = s + lane; q < e; q += 32) {
-            const int k = inc[q] / nvf;
-            int other[4];
-#pragma unroll
-            for (int d = 0; d < 4; ++d) other[d] = d < nvf ? fv[k * nvf + d] : -7 - d;
-            int n_ik = 0, n_ki = 0;
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              bool in_k = false, in_i = false;
-#pragma unroll
-              for (int d = 0; d < 4; ++d) {
-                in_k |= mine[a] == other[d];
-                in_i |= other[a] == mine[d];
-              }
-              n_ik += (a < nvf) && in_k;
-              n_ki += (a < nvf) && in_i;
+        const int mybase = counting ? 0 : fptr[i];
+        for_each_candidate(i, [&](const int k, const int n_ik, const int n_ki) {
+          const bool eo = !kLookBack && n_ik >= thr && (keep3 || n_ik != 3);
+          const bool ei = (MODE != MODE_FILL_DENSE) && n_ki >= thr && (keep3 || n_ki != 3);
+          if (counting) {
+            dout += eo;
+            din += ei;
+          } else if (MODE == MODE_FILL_DENSE) {
+            if (eo) {
+              int64_t* dst = p.dense_out + ((size_t)b * p.emax + mybase + r) * 2;
+              dst[0] = i;
+              dst[1] = k;
+              ++r;
             }
-            const bool eo = !kLookBack && n_ik >= thr && (keep3 || n_ik != 3);
-            const bool ei = (MODE != MODE_FILL_DENSE) && n_ki >= thr && (keep3 || n_ki != 3);
-            if (eo) atomicOr(&obits[k >> 5], 1u << (k & 31));
-            if (ei) atomicOr(&ibits[k >> 5], 1u << (k & 31));
-            if (eo || ei) { wmin = min(wmin, k >> 5); wmax = max(wmax, k >> 5); }
+          } else if (ei) {
+            const long long at = (long long)edge_off + mybase + r;
+            if (at < p.edge_capacity) p.src[at] = face_off + frank[k];
+            ++r;
           }
-        }
-        wmin = warp_min_int(wmin);
-        wmax = warp_max_int(wmax);
-        __syncwarp();
-      }
-      if (wmax < 0) {   // padded face, or no neighbour at all
-        if (counting && lane == 0) {
-          if (MODE == MODE_COUNT) {
-            p.deg_out[(size_t)b * F + i] = 0;
-            p.deg_in[(size_t)b * F + i] = 0;
-          } else {
-            fptr[i] = 0;
-          }
-        }
-        continue;
+        });
       }
       if (counting) {
         if (MODE == MODE_COUNT) {
-          const int dout = warp_count_bits(obits, wmin, wmax);
-          const int din = warp_count_bits(ibits, wmin, wmax);
-          if (lane == 0) {
-            p.deg_out[(size_t)b * F + i] = dout;
-            p.deg_in[(size_t)b * F + i] = din;
-            atomicAdd(&scratch[41], dout);
-          }
+          p.deg_out[(size_t)b * F + i] = dout;
+          p.deg_in[(size_t)b * F + i] = din;
+          total_out += dout;
         } else {
-          const int din = warp_count_bits(ibits, wmin, wmax);
-          if (lane == 0) fptr[i] = din;
+          fptr[i] = din;
         }
-      } else if (MODE == MODE_FILL_DENSE) {
-        int64_t* dst = p.dense_out + ((size_t)b * p.emax + fptr[i]) * 2;
-        warp_emit_bits(obits, wmin, wmax, [&](int r, int k) {
-          dst[2 * r] = i;
-          dst[2 * r + 1] = k;
-        });
-      } else {
-        const int base = edge_off + fptr[i];
-        warp_emit_bits(ibits, wmin, wmax, [&](int r, int k) {
-          const long long pos = (long long)base + r;
-          if (pos < p.edge_capacity) p.src[pos] = face_off + frank[k];
-        });
       }
-      __syncwarp();
-      for (int w = wmin + lane; w <= wmax; w += 32) { obits[w] = 0u; ibits[w] = 0u; }
-      __syncwarp();
+    }
+    if (counting && MODE == MODE_COUNT) {
+      total_out = warp_sum_int(total_out);
+      if (lane == 0 && total_out) atomicAdd(&scratch[41], total_out);
     }
   };
 
