@@ -8,6 +8,8 @@
 //
 // This file is compiled with -fmad=false: the discretisation chain must round exactly like the
 // reference's separate fp32 ops ((t-lo)/(hi-lo), *n, -0.5, round-half-even; meshgpt_pytorch.py:197-201).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -154,6 +156,75 @@ __global__ void __launch_bounds__(256, 4) face_sum_kernel(FeatParams p) {
   pdl_launch_dependents();
 }
 
+// The same sum with the tables staged in shared memory.  The folded tables (2048 rows x 64 floats = 512 KB for the default
+// model) do not fit one SM, a slice of S of the D columns does: CTA (g, slice) copies columns [slice * S, +S) of every
+// table row into shared memory once (rows_total x S floats, 128 KB) and sums them for face group g.  S / 4 consecutive
+// threads take one face (a float4 column each), so a warp reads S * 4-byte pieces of 32 / (S / 4) table rows per slot from
+// shared memory instead of L2, and writes whole 128-byte segments of the activation image.  Same slot order of the
+// additions as face_sum_kernel -> the same bits.
+template <int NVF, int S>
+__global__ void __launch_bounds__(512, 1) face_sum_smem_kernel(FeatParams p, int rows_total, int groups) {
+  extern __shared__ float4 stab[];   // [rows_total][S / 4]
+  constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
+  constexpr int s4 = S >> 2, ROWS_PER_IT = 512 / s4;
+  const int D = p.D, nslices = D / S;
+  const int slice = blockIdx.x % nslices, g = blockIdx.x / nslices;
+  const int tid = threadIdx.x;
+  const int c = tid % s4;
+  // the tables are model constants: staged before the wait on the preceding kernels
+  for (int i = tid; i < rows_total * s4; i += 512) {
+    const int row = i / s4, cc = i % s4;
+    stab[i] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)row * D + slice * S) + cc);
+  }
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + slice * S) + c);
+  pdl_wait();
+  __syncthreads();
+  const int n_rows = p.counts->n_faces;
+  const int per = (((n_rows + groups - 1) / groups) + 7) & ~7;   // whole 8-row groups of the image per CTA
+  const int r_lo = g * per, r_hi = min(n_rows, r_lo + per);
+  int row = r_lo + tid / s4;
+  uint32_t w[NSLOT / 2], wn[NSLOT / 2];
+  auto load_ids = [&](int r, uint32_t (&dst)[NSLOT / 2]) {
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(p.bins_out + (size_t)r * NSLOT);
+#pragma unroll
+    for (int s2 = 0; s2 < NSLOT / 2; ++s2) dst[s2] = __ldg(bp + s2);
+  };
+  if (row < r_hi) load_ids(row, w);
+  for (; row < r_hi; row += ROWS_PER_IT) {
+    if (row + ROWS_PER_IT < r_hi) load_ids(row + ROWS_PER_IT, wn);   // the next row's ids travel while this row is summed
+    float4 acc = b4;
+#pragma unroll
+    for (int s2 = 0; s2 < NSLOT / 2; ++s2) {
+      const float4 t0 = stab[(w[s2] & 0xffffu) * s4 + c];
+      const float4 t1 = stab[(w[s2] >> 16) * s4 + c];
+      acc.x += t0.x; acc.y += t0.y; acc.z += t0.z; acc.w += t0.w;
+      acc.x += t1.x; acc.y += t1.y; acc.z += t1.z; acc.w += t1.w;
+    }
+    const int col = slice * S + c * 4;
+    if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)row * D + col) = acc;
+    if (p.x0_image) tc::image_store4(p.x0_image, D, row, col, acc);
+#pragma unroll
+    for (int s2 = 0; s2 < NSLOT / 2; ++s2) w[s2] = wn[s2];
+  }
+  pdl_launch_dependents();
+}
+
+template <int NVF, int S>
+int launch_face_sum_smem(const FeatParams& p, int rows_total, int max_rows, cudaStream_t stream) {
+  static bool configured = false;
+  const size_t smem = (size_t)rows_total * S * sizeof(float);
+  if (!configured) {
+    MT_CHECK_CUDA(cudaFuncSetAttribute(face_sum_smem_kernel<NVF, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const int nslices = p.D / S;
+  const int groups = max(1, min(148 / nslices, ceil_div(max_rows, 64)));
+  MT_LAUNCH_PDL((face_sum_smem_kernel<NVF, S>), groups * nslices, 512, smem, stream, p, rows_total, groups);
+  return MESHTOK_OK;
+}
+
+constexpr int FACE_SUM_SMEM_MAX = 200 * 1024;
+
 }  // namespace
 
 int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
@@ -168,6 +239,21 @@ int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
   const int blocks1 = max(1, min(ceil_div(max_rows, 128), 148 * 16));
   if (p.nvf == 3) MT_LAUNCH_PDL(face_bins_kernel<3>, blocks1, 128, 0, stream, p);
   else MT_LAUNCH_PDL(face_bins_kernel<4>, blocks1, 128, 0, stream, p);
+  // table slices in shared memory when a slice of >= 8 columns fits; else table rows straight from L2
+  const int rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
+  int S = 0;
+  for (int cand = 32; cand >= 8 && S == 0; cand >>= 1)
+    if (p.D % cand == 0 && (size_t)rows_total * cand * sizeof(float) <= (size_t)FACE_SUM_SMEM_MAX) S = cand;
+  static int use_smem = -1;
+  if (use_smem < 0) { const char* e = getenv("MESHTOK_FACE_SUM_L2"); use_smem = (e && atoi(e) == 1) ? 0 : 1; }
+  if (S != 0 && use_smem && p.D / S <= 148) {
+    if (p.nvf == 3) return S == 32 ? launch_face_sum_smem<3, 32>(p, rows_total, max_rows, stream)
+                         : S == 16 ? launch_face_sum_smem<3, 16>(p, rows_total, max_rows, stream)
+                                   : launch_face_sum_smem<3, 8>(p, rows_total, max_rows, stream);
+    return S == 32 ? launch_face_sum_smem<4, 32>(p, rows_total, max_rows, stream)
+         : S == 16 ? launch_face_sum_smem<4, 16>(p, rows_total, max_rows, stream)
+                   : launch_face_sum_smem<4, 8>(p, rows_total, max_rows, stream);
+  }
   const int blocks2 = max(1, min(ceil_div(ceil_div(max_rows, 2), 8), 148 * 4));
   if (p.nvf == 3) MT_LAUNCH_PDL(face_sum_kernel<3>, blocks2, 256, 0, stream, p);
   else MT_LAUNCH_PDL(face_sum_kernel<4>, blocks2, 256, 0, stream, p);
