@@ -124,6 +124,10 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
   const uint32_t w_part = (uint32_t)a.NT * KC * 2;          // hi (or lo) bytes of one W chunk
   const uint32_t w_mine = PAIR ? w_part / 2 : w_part;       // ... of the rows this CTA stages
 
+  // Earlier kernels' results are read from here on (the row count first: its load travels while the barriers and TMEM are
+  // set up).  With PDL enabled this gives up the overlap of the prologue; PDL is opt-in and measured slower anyway.
+  pdl_wait();
+  const int M = a.m_dev ? min(__ldg(a.m_dev), a.m_max) : a.m_max;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], PAIR && leader ? 2 : 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * EPI_WARPS); }
@@ -133,23 +137,14 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
     if (PAIR) tmem_alloc_pair(tmem_slot, 512);
     else tmem_alloc(tmem_slot, 512);
   }
-  // bias / gamma / beta -> shared memory (the epilogue reads them per 16-column block; as global loads they sat on its
-  // critical path)
   float* sbias = reinterpret_cast<float*>(smem + G::VEC_OFF);
   float* sgamma = sbias + VEC_MAX_N;
   float* sbeta = sgamma + 64;
-  for (int i = threadIdx.x; i < a.N; i += G::NUM_THREADS) {
-    sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-    if (a.norm_mode == 2) { sgamma[i] = __ldg(a.gamma + i); sbeta[i] = __ldg(a.beta + i); }
-  }
   tcgen05_fence_before();
   __syncthreads();
   if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above is independent of earlier kernels; from here on their results are read
-  pdl_wait();
-  const int M = a.m_dev ? min(*a.m_dev, a.m_max) : a.m_max;
   const int m_tiles = (M + M_TILE - 1) / M_TILE;
   const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;   // a group = the row tile(s) one MMA covers
   const int units = m_groups * a.passes;
@@ -261,6 +256,13 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
     float* stage = reinterpret_cast<float*>(smem + G::EPI_OFF) + ew * (32 * EPI_LD);
     const uint32_t acc_empty_remote0 = PAIR ? mapa_shared(smem_u32(&acc_empty[0]), 0) : 0u;
     const uint32_t acc_empty_remote1 = PAIR ? mapa_shared(smem_u32(&acc_empty[1]), 0) : 0u;
+    // bias / gamma / beta -> shared memory, by the epilogue warps themselves while the first stages are in flight (the
+    // epilogue reads them per 16-column block; as global loads they sat on its critical path)
+    for (int i = threadIdx.x - 128; i < a.N; i += EPI_WARPS * 32) {
+      sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
+      if (a.norm_mode == 2) { sgamma[i] = __ldg(a.gamma + i); sbeta[i] = __ldg(a.beta + i); }
+    }
+    named_bar_sync(3, EPI_WARPS * 32);
     const int part_cols = (((a.NT + CPARTS - 1) / CPARTS + 15) / 16) * 16;
     const int c_lo = min(a.NT, cpart * part_cols), c_hi = min(a.NT, c_lo + part_cols);
     uint32_t acc_it = 0;
