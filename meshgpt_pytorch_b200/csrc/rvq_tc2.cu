@@ -103,6 +103,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  // earlier kernels' results are read from here on; the row count first, so that its load travels during the set-up
+  pdl_wait();
+  const int n_rows = min(__ldg(a.n_rows_dev), a.max_rows);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], leader ? 2 : 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
@@ -116,9 +119,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // everything above is independent of earlier kernels; from here on their results are read
-  pdl_wait();
-  const int n_rows = min(*a.n_rows_dev, a.max_rows);
   const int G = (n_rows + M_PAIR - 1) / M_PAIR;
   const int T = a.T;
   const long long S = (long long)G * T;
