@@ -240,11 +240,11 @@ int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* 
   return launch_linear_tc(A1_img, K1, A2_img, K2, w_img, bias, C, N, m_dev, m_max, relu, epi, s);
 }
 
-// One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the final residual in
-// `resid` and the codes in vcodes (R x Q).
+// One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the codes in vcodes (R x Q) and, with
+// need_resid, the final residual in `resid` (else the residual of the last-but-one level: the last subtraction is skipped).
 int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes,
             unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, uint8_t* rimg, const int* n_dev, int max_rows,
-            bool exact, bool prepped, cudaStream_t s) {
+            bool exact, bool prepped, bool need_resid, cudaStream_t s) {
   const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
   if (max_rows == 0) return MESHTOK_OK;
   int rc;
@@ -298,7 +298,8 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
       if (rc != MESHTOK_OK) return rc;
     }
     { ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
-      rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, c_scale, n_dev, max_rows, s); }
+      if (level + 1 == Q && !need_resid) rc = launch_rvq_codes_only(packed, vcodes, Q, level, n_dev, max_rows, s);
+      else rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, c_scale, n_dev, max_rows, s); }
     if (rc != MESHTOK_OK) return rc;
   }
   return MESHTOK_OK;
@@ -602,7 +603,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   } else {
     MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
     if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.packed, w.amb_list, w.amb_count, w.partial, w.rimg, n_vrows_dev, max_vrows,
-                      a->rvq_exact != 0, rvq_tc_path, s)) != MESHTOK_OK) return rc;
+                      a->rvq_exact != 0, rvq_tc_path, a->quantized_out != nullptr, s)) != MESHTOK_OK) return rc;
     if (a->quantized_out) {
       const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
       sub_rows_kernel<<<blocks, 256, 0, s>>>(w.avg, w.resid, w.qrows, D, n_vrows_dev, (long long)max_vrows * D);
@@ -679,7 +680,7 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
   MT_CHECK_LAUNCH();
-  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, false, s);
+  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, false, residual_out != nullptr, s);
   if (rc != MESHTOK_OK) return rc;
   if (residual_out && R > 0)
     MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));

@@ -81,6 +81,8 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
 // so that this constant stays a finite fp16 power of two.
 int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
                       float* rscale, void* row_image, float c_scale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
+int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, const int* n_rows_dev, int max_rows,
+                          cudaStream_t stream);
 // resid <- rows_in (copy), rscale and row_image as above.
 int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, float c_scale, const int* n_rows_dev,
                     int max_rows, cudaStream_t stream);

@@ -46,7 +46,7 @@ constexpr int VEC_MAX_N = 1024;
 
 // PAIR = two CTAs of a cluster work on one 256-row tile with tcgen05.mma.cta_group::2: every CTA stages its own 128 rows
 // of A and HALF of the W chunk, so the bytes pulled from L2 per MMA cycle drop from (128 + NT) to (128 + NT / 2) rows.
-// ncu on the single-CTA kernel (profiles/r01h_*) had the two widest linears at 10.5 TB/s of L2 -> SM traffic, the
+// ncu on the single-CTA kernel (capture r01h, in the git history of profiles/) had the two widest linears at 10.5 TB/s of L2 -> SM traffic, the
 // measured cap of the L2 slices, with the tensor pipe waiting.
 template <bool PAIR, int CPARTS_>
 struct Cfg {

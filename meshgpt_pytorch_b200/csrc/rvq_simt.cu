@@ -185,7 +185,25 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
   pdl_launch_dependents();
 }
 
+// codes[row, level] = winner of packed[row]; the last level of a call that does not return the residual needs no more
+__global__ void __launch_bounds__(256) rvq_codes_only_kernel(const unsigned long long* __restrict__ packed, int32_t* __restrict__ codes, int Q,
+                                                             int level, const int* __restrict__ n_dev, int max_rows) {
+  pdl_wait();
+  const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x)
+    codes[(size_t)row * Q + level] = (int)(unsigned int)(packed[row] & 0xffffffffull);
+  pdl_launch_dependents();
+}
+
 }  // namespace
+
+int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, const int* n_rows_dev, int max_rows,
+                          cudaStream_t stream) {
+  if (max_rows == 0) return MESHTOK_OK;
+  const int blocks = max(1, min(ceil_div(max_rows, 256), 148 * 4));
+  MT_LAUNCH_PDL(rvq_codes_only_kernel, blocks, 256, 0, stream, packed, codes, Q, level, n_rows_dev, max_rows);
+  return MESHTOK_OK;
+}
 
 int launch_rvq_exact(const float* rows, int D, const float* codebook, const float* e2, int K, const int* row_list,
                      const int* n_dev, int max_rows, unsigned long long* packed, cudaStream_t stream) {
