@@ -524,7 +524,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       // xp = relu(lin(x))
       { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
       if ((rc = join_edges()) != MESHTOK_OK) return rc;
-      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, s)) != MESHTOK_OK) return rc; }
+      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s)) != MESHTOK_OK) return rc; }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {
         LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1], nullptr, nullptr, 0};

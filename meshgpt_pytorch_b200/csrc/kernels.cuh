@@ -27,7 +27,8 @@ int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
 // agg[t] = mean over in-edges (s -> t) of x[s]; sum in ascending CSR order / max(count, 1).
 // agg (fp32 rows) and agg_image (split-bf16 activation image) are both optional outputs.
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity,
-                       float* agg, void* agg_image, const Counts* counts, int max_rows, cudaStream_t stream);
+                       float* agg, void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F,
+                       cudaStream_t stream);
 // in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).
 // image_out (optional): the same rows as a split-bf16 activation image for the next tcgen05 linear.
 int launch_row_norm(float* x, int d, const float* gamma, const float* beta, void* image_out, const Counts* counts,

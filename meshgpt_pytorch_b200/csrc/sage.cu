@@ -3,9 +3,14 @@
 // Replaces the message passing of torch_geometric.nn.SAGEConv (scatter-add of x[edge_index[0]] onto
 // edge_index[1], divided by clamp(count, 1)) called at meshgpt_pytorch.py:764 and :769, the
 // F.normalize(p=2) that ends every SAGEConv (normalize=True, :471-474) and init_encoder_act_and_norm
-// (SiLU + LayerNorm, :545-548, applied at :766).  One warp per face row; neighbour rows are summed in
-// ascending source order, the order the reference's CPU scatter_add visits them in, so the result is
-// deterministic (the reference's GPU path uses atomics and is not).
+// (SiLU + LayerNorm, :545-548, applied at :766).  Neighbour rows are summed in ascending source order, the
+// order the reference's CPU scatter_add visits them in, so the result is deterministic (the reference's GPU
+// path uses atomics and is not).  Two aggregation kernels: per-mesh column slices staged in shared memory
+// (default; MEASURED against the other with scripts/gpu_gather_ab.sh: 128 vs 137 us at C2, 1.66 vs 2.09 ms at 1 024
+// meshes per launch) and one warp per face row reading neighbour rows from L2 (meshes too large for a slice,
+// batches too small to fill the SMs).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
@@ -79,6 +84,100 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
   pdl_launch_dependents();
 }
 
+// The same aggregation with the neighbour rows read from shared memory.  Edges never leave a mesh, so CTA (mesh, slice)
+// copies columns [slice * S, +S) of the mesh's x rows into shared memory once (F x S floats; 100 KB for 800 faces and
+// S = 32, two CTAs per SM) and every neighbour read is a 16-byte shared-memory load: S / 4 threads per face, a quarter
+// warp reads one 128-byte row slice (no bank conflicts).  L2 -> SM traffic drops from (neighbours + 1) x to 1 x the
+// activation - the warp-per-row kernel above ran at the bandwidth cap of the L2 slices (8-9 TB/s into the SMs).  Same
+// neighbour order and the same rounding as above, hence the same bits.
+template <int S>
+__global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
+                                                                  const int* __restrict__ src, long long cap, float* __restrict__ agg,
+                                                                  uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
+                                                                  int rows_cap, int edges_cap) {
+  // [rows_cap + 1][S / 4] x slice (the last row stays zero) | [rows_cap + 1] local row pointers | [edges_cap] source row * S/4 (u16)
+  extern __shared__ float4 sx[];
+  constexpr int s4 = S >> 2;
+  constexpr int ROWS_PER_IT = 512 / s4;
+  int* sptr = reinterpret_cast<int*>(sx + (size_t)(rows_cap + 1) * s4);
+  unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
+  pdl_wait();
+  const int nslices = d / S;
+  const int b = blockIdx.x / nslices, slice = blockIdx.x % nslices;
+  const int r0 = face_off[b];
+  const int n_b = min(face_off[b + 1] - r0, rows_cap);
+  const int tid = threadIdx.x;
+  const int c = tid % s4;
+  // x slice: 16-byte cp.async copies, all of a thread's in flight at once (a load-then-store loop paid one memory round
+  // trip per iteration: 12 per thread)
+  const float* xs = x + (size_t)r0 * d + slice * S;
+  const uint32_t sx_addr = tc::smem_u32(sx);
+  for (int i = tid; i < n_b * s4; i += 512) {
+    const int row = i / s4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (uint32_t)i * 16u), "l"(xs + (size_t)row * d + c * 4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  if (tid < s4) sx[n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
+  // the mesh's part of the CSR: row pointers relative to its first edge, sources as shared-memory row offsets
+  const int e0 = indptr[r0];
+  const long long e1_true = indptr[r0 + n_b];
+  const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);   // edges that exist in memory (capacity overflow is flagged elsewhere)
+  const bool fast = n_e <= edges_cap && e1_true <= cap && (rows_cap + 1) * s4 <= 65536;
+  for (int i = tid; i <= n_b; i += 512) sptr[i] = indptr[r0 + i] - e0;
+  if (fast) {
+    for (int base = tid; base < n_e; base += 512 * 8) {
+      int t[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t[j] = base + j * 512 < n_e ? __ldg(src + e0 + base + j * 512) : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (base + j * 512 < n_e) {
+          const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
+          ssrc[base + j * 512] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
+        }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  // image address of (row, this thread's 4 columns): the column part is fixed, the row part is cheap
+  const int col = slice * S + c * 4;
+  const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u + (uint32_t)(col & 7) * 2u;
+  const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
+  const float4* sxc = sx + c;
+  for (int lrow = tid / s4; lrow < n_b; lrow += ROWS_PER_IT) {
+    const int s = sptr[lrow];
+    const int e_true = sptr[lrow + 1];
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (fast) {
+      for (int q = s; q < e_true; ++q) {
+        const float4 v = sxc[ssrc[q]];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    } else {   // a mesh with more edges than the staging area holds, or a list cut by the edge capacity
+      const int e = min(e_true, n_e);
+      for (int q = s; q < e; ++q) {
+        const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
+        const float4 v = sxc[(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    const float cnt = fmaxf((float)(e_true - s), 1.f);
+    const float rc = __frcp_rn(cnt);
+    const float4 o = make_float4(div_count(acc.x, cnt, rc), div_count(acc.y, cnt, rc), div_count(acc.z, cnt, rc), div_count(acc.w, cnt, rc));
+    const int row = r0 + lrow;
+    if (agg) *reinterpret_cast<float4*>(agg + (size_t)row * d + col) = o;
+    if (agg_image) {
+      uint2 hi, lo;
+      tc::split2(o.x, o.y, hi.x, lo.x);
+      tc::split2(o.z, o.w, hi.y, lo.y);
+      uint8_t* pimg = agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_col;
+      *reinterpret_cast<uint2*>(pimg) = hi;
+      *reinterpret_cast<uint2*>(pimg + tc::IMG_PART) = lo;
+    }
+  }
+  pdl_launch_dependents();
+}
+
 template <int PER2>  // float2 pairs per lane (d <= 64 * PER2, d even)
 __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, int d, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, uint8_t* __restrict__ image,
@@ -145,8 +244,26 @@ __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, in
 }  // namespace
 
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity, float* agg,
-                       void* agg_image, const Counts* counts, int max_rows, cudaStream_t stream) {
+                       void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F, cudaStream_t stream) {
   MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
+  if (max_rows == 0) return MESHTOK_OK;
+  // per-mesh slices in shared memory when a 32-column slice of the largest mesh fits (two CTAs per SM up to 880 faces,
+  // one up to 1 760); MESHTOK_GATHER_L2=1 keeps the warp-per-row kernel for A/B runs
+  static int use_smem = -1;
+  if (use_smem < 0) { const char* e = getenv("MESHTOK_GATHER_L2"); use_smem = (e && atoi(e) == 1) ? 0 : 1; }
+  constexpr int S = 32;
+  const int edges_cap = 5 * F;   // staged source ids per mesh (u16); a mesh with more edges reads them from global memory
+  const size_t smem = align_up((size_t)(F + 1) * S * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
+  if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && (long long)B * (d / S) >= 64) {
+    static bool configured = false;
+    if (!configured) {
+      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      configured = true;
+    }
+    MT_LAUNCH_PDL(gather_mean_smem_kernel<S>, B * (d / S), 512, smem, stream, x, d, indptr, src, edge_capacity, agg,
+                  static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+    return MESHTOK_OK;
+  }
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int chunks = ceil_div(d / 4, 32);
 #define GM(C) MT_LAUNCH_PDL(gather_mean_kernel<C>, blocks, 256, 0, stream, x, d, indptr, src, edge_capacity, agg, static_cast<uint8_t*>(agg_image), counts)
