@@ -463,9 +463,9 @@ class MeshAutoencoder(nn.Module):
         run first (status word, edge-buffer size).  See GraphedTokenizer."""
         return GraphedTokenizer(self, vertices, faces, histogram, face_edges)
 
-    def host_pipeline(self, vertices: Tensor, faces: Tensor) -> "HostPipeline":
-        """Double-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
-        return HostPipeline(self, vertices, faces)
+    def host_pipeline(self, vertices: Tensor, faces: Tensor, depth: int = 2) -> "HostPipeline":
+        """Multi-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
+        return HostPipeline(self, vertices, faces, depth)
 
     # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
     @torch.no_grad()
@@ -551,14 +551,17 @@ class HostPipeline:
 
         pipe = model.host_pipeline(example_vertices, example_faces)      # CUDA tensors of the batch shape
         for v, f in batches:                                             # pinned host tensors
-            done = pipe.submit(v, f)        # -> (ticket, codes) of the batch submitted TWO calls ago, or None
+            done = pipe.submit(v, f)        # -> (ticket, codes) of the batch submitted `depth` calls ago, or None
         for ticket, codes in pipe.drain(): ...
 
-    The returned codes tensor is the slot's pinned buffer: copy it before the slot is used again (two submits later)."""
+    The returned codes tensor is the slot's pinned buffer: copy it before the slot is used again (`depth` submits later).
+    depth > 2 lets more batches overlap on the SMs (each kernel's ramp and tail is filled by the other batches' kernels) at the
+    price of one workspace per slot."""
 
-    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor):
+    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, depth: int = 2):
+        assert depth >= 1
         self.slots = []
-        for _ in range(2):
+        for _ in range(depth):
             stream = torch.cuda.Stream()
             torch.cuda.current_stream().synchronize()
             with torch.cuda.stream(stream):
@@ -575,7 +578,7 @@ class HostPipeline:
         return slot["ticket"], slot["out"]
 
     def submit(self, vertices: Tensor, faces: Tensor):
-        slot = self.slots[self.n % 2]
+        slot = self.slots[self.n % len(self.slots)]
         finished = self._collect(slot) if slot["busy"] else None
         with torch.cuda.stream(slot["stream"]):
             codes = slot["graph"](vertices, faces)

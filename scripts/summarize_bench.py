@@ -1,6 +1,8 @@
 """Prints a compact view of a bench.py JSON line (stdin or file)."""
+import signal
 import json
 import sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)
 
 line = [l for l in (open(sys.argv[1]) if len(sys.argv) > 1 else sys.stdin) if l.startswith("{")][-1]
 d = json.loads(line)
