@@ -254,7 +254,9 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   constexpr int S = 32;
   const int edges_cap = 5 * F;   // staged source ids per mesh (u16); a mesh with more edges reads them from global memory
   const size_t smem = align_up((size_t)(F + 1) * S * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
-  if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && (long long)B * (d / S) >= 64) {
+  // one CTA per (mesh, slice): enough CTAs to fill the machine, or so little work that it does not matter
+  const bool enough_ctas = (long long)B * (d / S) >= 64 || max_rows <= 8192;
+  if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && enough_ctas) {
     static bool configured = false;
     if (!configured) {
       MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));

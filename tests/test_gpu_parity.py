@@ -398,12 +398,27 @@ def test_graphed_with_precomputed_edges():
     assert match_rate(g(face_edges=fe[:, perm].cuda()), m.tokenize(v.cuda(), f.cuda())) > 0.995
 
 
+def test_dense_user_edges_through_the_aggregation_kernels():
+    """User-supplied face_edges with far more edges per face than the derived default (neighbours by ONE shared vertex,
+    about 13 per face): the shared-memory aggregation kernel's staging area for source ids overflows and it reads them
+    from global memory; duplicates count twice as in the reference."""
+    o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+    v, f = synth.ragged_batch("tri", 12, 12, [288, 288, 100, 288], [0, 1, 2, 3])
+    fe = O.derive_face_edges_from_faces(f, neighbor_if_share_one_vertex=True)
+    fe = torch.cat([fe, fe[:, :50]], dim=1)          # some edges twice
+    got = m.tokenize(v.cuda(), f.cuda(), face_edges=fe.cuda()).cpu()
+    want = o.tokenize(v, f, face_edges=fe)
+    assert torch.equal(got == -1, want == -1)
+    assert match_rate(got, want) > 0.97, match_rate(got, want)
+
+
 @pytest.mark.parametrize("cfg,kind,grid,counts", [
     (dict(SMALL_CFG, use_residual_lfq=False, quads=True), "quad", (6, 7), [42, 17, 3]),              # quads + RVQ (CTA-pair search)
     (dict(SMALL_CFG, use_residual_lfq=False, codebook_size=384), "tri", (8, 8), [128, 1]),          # K % 256 != 0 -> single-CTA search
     (dict(SMALL_CFG, use_residual_lfq=False, codebook_size=200), "tri", (8, 8), [90, 60]),          # no tcgen05 image -> exact fp32 scan
     (dict(SMALL_CFG, num_quantizers=3, codebook_size=512), "tri", (8, 8), [128, 128, 5, 77]),       # LFQ, 3 levels, 9 bits
     (dict(dim_codebook=192, encoder_dims_through_depth=(64, 128), codebook_size=1024, use_residual_lfq=False), "tri", (10, 10), [200, 150]),
+    (dict(SMALL_CFG, use_residual_lfq=False), "tri", (45, 20), [1800, 900]),      # meshes too large for a shared-memory slice -> L2 aggregation kernel
 ])
 def test_config_matrix_end_to_end(cfg, kind, grid, counts):
     """Other constructor configurations end to end against the oracle (token agreement; exact pad positions)."""
