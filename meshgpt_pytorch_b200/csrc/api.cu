@@ -512,6 +512,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     // second linear, which writes the next layer's image directly; fp32 rows are then only kept for the parity taps.
     const float* x = w.x0;
     int cur = 0;
+    bool xp_ready = false;   // the previous layer's launch already computed this layer's relu(lin(x)) (two linears back to back)
     for (int l = 0; l < L; ++l) {
       const meshtok_sage_layer& ly = m->sage[l];
       const bool first = l == 0, last = l == L - 1;
@@ -522,15 +523,26 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       const bool deferred = !simt && !fused && last && !first && linear_tc_ssq_parts(ly.dim_out) <= 16;
       const bool need_fp32 = a->keep_taps || (last && (a->encoded_out != nullptr || a->stop_after_encode));
       // xp = relu(lin(x))
-      { ProfScope ps(PROF_SAGE_LINEAR, s); if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc; }
+      if (!xp_ready) {
+        ProfScope ps(PROF_SAGE_LINEAR, s);
+        if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc;
+      }
+      xp_ready = false;
       if ((rc = join_edges()) != MESHTOK_OK) return rc;
       { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s)) != MESHTOK_OK) return rc; }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {
         LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1], nullptr, nullptr, 0};
         ProfScope ps(PROF_SAGE_LINEAR, s);
-        if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
-                         need_fp32 ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;
+        // the next layer's lin reads exactly the rows this launch writes: run it in the same launch, tile by tile
+        const bool b2b = !last && ly.cat_w_img != nullptr && m->sage[l + 1].lin_w_img != nullptr && m->sage[l + 1].dim_in == ly.dim_out &&
+                         linear_tc_b2b_ok(ly.dim_out, mode);
+        if (b2b) {
+          if ((rc = launch_linear_tc_b2b(w.img_agg, ly.dim_in, w.img_x[cur], ly.dim_in, ly.cat_w_img, ly.lin_l_b, need_fp32 ? w.layer_out[l] : nullptr,
+                                         ly.dim_out, n_faces_dev, max_rows, &epi, m->sage[l + 1].lin_w_img, m->sage[l + 1].lin_b, w.xp, s)) != MESHTOK_OK) return rc;
+          xp_ready = true;
+        } else if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
+                                need_fp32 ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;
       } else if (deferred) {
         LinearRowEpilogue epi{0, nullptr, nullptr, w.img_x[cur ^ 1], w.ssq, nullptr, 0};
         { ProfScope ps(PROF_SAGE_LINEAR, s);

@@ -101,43 +101,80 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
+// One launch runs one linear (nphase == 1) or two back to back (nphase == 2): phase 0 = a layer's output linear with the fused
+// normalisation epilogue, phase 1 = `lin` of the NEXT layer, whose input rows are exactly the 128-row tile phase 0 has just
+// written (as an activation image, to global memory = L2).  A CTA (pair) interleaves its tiles as A0 A1 A2 B0 A3 B1 ... so the
+// tensor pipe works on other tiles while the epilogue of tile i normalises and stores; the producer waits on a_done[] (arrivals
+// of the epilogue warps after a gpu-scope fence and a proxy fence) before it bulk-copies a tile back in for phase 1.  Saves a
+// launch with its ramp (prologue, first loads, last epilogue, ~10 us at C2) per SAGE layer.
+struct LinArgs2 {
+  LinArgs p[2];
+  int nphase;
+};
+
+struct UnitSeq {   // this CTA (pair)'s units in issue order
+  int n, u0, ustep, passes, nphase;
+  __device__ __forceinline__ int count() const { return nphase == 2 ? 2 * n : n; }
+  // j -> phase, row group (tile or tile pair), pass, and for two phases the ordinal i of the row group within this CTA
+  __device__ __forceinline__ void get(int j, int& phase, int& grp, int& pass, int& i) const {
+    if (nphase == 1) {
+      const int u = u0 + j * ustep;
+      phase = 0; grp = u / passes; pass = u % passes; i = j;
+      return;
+    }
+    // A0 A1 | A2 B0 | A3 B1 | ... | B(n-2) B(n-1): phase 1 of a tile is issued two phase-0 units after its phase 0, so the
+    // epilogue of tile i (normalise, store, fence) and the copy back in have two units of MMA time to hide behind
+    if (n == 1) { phase = j; i = 0; }
+    else if (j < 2) { phase = 0; i = j; }
+    else {
+      const int t = j - 2;
+      if (t < 2 * (n - 2)) { phase = t & 1; i = (t & 1) ? (t >> 1) : (t >> 1) + 2; }
+      else { phase = 1; i = n - 2 + (t - 2 * (n - 2)); }
+    }
+    grp = u0 + i * ustep; pass = 0;
+  }
+};
+
 template <bool PAIR, int CPARTS>
-__device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
+__device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   using G = Cfg<PAIR, CPARTS>;
   constexpr int EPI_WARPS = G::EPI_WARPS;
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int STAGES = G::stages(a.NT);
-  const uint32_t stage_bytes = G::stage_bytes(a.NT);
+  const int nphase = g.nphase;
+  const int ring_nt = nphase == 2 ? max(g.p[0].NT, g.p[1].NT) : g.p[0].NT;   // the ring is laid out for the wider phase
+  const int STAGES = G::stages(ring_nt);
+  const uint32_t stage_bytes = G::stage_bytes(ring_nt);
   uint8_t* ring = smem + G::RING_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
   uint64_t* full = bars;                        // [STAGES]  producer expect_tx (+ in a pair, on the leader: the peer's forwarded arrival)
   uint64_t* empty = bars + G::MAX_STAGES;       // [STAGES]  MMA commit (multicast to both CTAs of a pair)
   uint64_t* acc_full = empty + G::MAX_STAGES;   // [2]
-  uint64_t* acc_empty = acc_full + 2;  // [2]       (in a pair the leader's are the ones waited on)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 2;           // [2]       (in a pair the leader's are the ones waited on)
+  uint64_t* a_done = acc_empty + 2;             // [4]       phase-0 tile i of this CTA is in global memory (epilogue warps -> producer)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_done + 4);
 
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
-  const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
-  const int kchunks = kch1 + kch2;
-  const uint32_t w_part = (uint32_t)a.NT * KC * 2;          // hi (or lo) bytes of one W chunk
-  const uint32_t w_mine = PAIR ? w_part / 2 : w_part;       // ... of the rows this CTA stages
 
   // Earlier kernels' results are read from here on (the row count first: its load travels while the barriers and TMEM are
   // set up).  With PDL enabled this gives up the overlap of the prologue; PDL is opt-in and measured slower anyway.
   pdl_wait();
-  const int M = a.m_dev ? min(__ldg(a.m_dev), a.m_max) : a.m_max;
+  const int M = g.p[0].m_dev ? min(__ldg(g.p[0].m_dev), g.p[0].m_max) : g.p[0].m_max;
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], PAIR && leader ? 2 : 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * EPI_WARPS);
+    }
+    for (int i = 0; i < 4; ++i) mbar_init(&a_done[i], EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) {
     if (PAIR) tmem_alloc_pair(tmem_slot, 512);
     else tmem_alloc(tmem_slot, 512);
   }
-  float* sbias = reinterpret_cast<float*>(smem + G::VEC_OFF);
+  float* sbias = reinterpret_cast<float*>(smem + G::VEC_OFF);   // phase p at sbias + p * 512 (two phases: N <= 256 each)
   float* sgamma = sbias + VEC_MAX_N;
   float* sbeta = sgamma + 64;
   tcgen05_fence_before();
@@ -147,17 +184,34 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
   const uint32_t tmem_base = *tmem_slot;
   const int m_tiles = (M + M_TILE - 1) / M_TILE;
   const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;   // a group = the row tile(s) one MMA covers
-  const int units = m_groups * a.passes;
-  const int u0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  UnitSeq seq;
+  seq.u0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  seq.ustep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  seq.passes = g.p[0].passes;
+  seq.nphase = nphase;
+  {
+    const int total = nphase == 2 ? m_groups : m_groups * g.p[0].passes;
+    seq.n = seq.u0 < total ? (total - seq.u0 + seq.ustep - 1) / seq.ustep : 0;
+  }
+  const int n_units = seq.count();
 
   if (warp == 0) {
     // ===== producer (warp-converged; one elected lane issues): own A block (16 KB) + own rows of the W chunk per stage =====
     uint32_t it = 0, s = 0, ph = 0;
-    for (int u = u0; u < units; u += ustep) {
-      const int grp = u / a.passes, pass = u % a.passes;
+    for (int j = 0; j < n_units; ++j) {
+      int phase, grp, pass, ti;
+      seq.get(j, phase, grp, pass, ti);
+      const LinArgs& a = g.p[phase];
+      const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
+      const int kchunks = kch1 + kch2;
+      const uint32_t w_part = (uint32_t)a.NT * KC * 2;          // hi (or lo) bytes of one W chunk
+      const uint32_t w_mine = PAIR ? w_part / 2 : w_part;       // ... of the rows this CTA stages
       const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
       const bool have_a = m_tile < m_tiles;   // an odd tile count leaves the peer of the last pair without rows
+      if (phase == 1) {   // the rows of this unit are the image tile this CTA's epilogue wrote in phase 0
+        mbar_wait(&a_done[ti & 3], (uint32_t)(ti >> 2) & 1u);
+        fence_proxy_async_all();
+      }
       const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part) + (size_t)rank * w_mine;
       const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
       const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
@@ -183,18 +237,24 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
     if (PAIR) {   // drain: every multicast commit aimed at this CTA has landed before the CTA may exit
       const uint32_t pending = it < (uint32_t)STAGES ? it : (uint32_t)STAGES;
       for (uint32_t i = 0; i < pending; ++i) {
-        const uint32_t j = it - 1 - i;
-        mbar_wait(&empty[j % STAGES], (j / STAGES) & 1);
+        const uint32_t jj = it - 1 - i;
+        mbar_wait(&empty[jj % STAGES], (jj / STAGES) & 1);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (the leader CTA of a pair; warp-converged, one elected lane issues) =====
     if (leader) {
-      const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * M_TILE : M_TILE, a.NT, /*bf16=*/true);
       const uint32_t s0 = smem_u32(ring);
-      uint32_t acc_it = 0, s = 0, ph = 0;
-      for (int u = u0; u < units; u += ustep, ++acc_it) {
-        const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      uint32_t s = 0, ph = 0;
+      for (int j = 0; j < n_units; ++j) {
+        int phase, grp, pass, ti;
+        seq.get(j, phase, grp, pass, ti);
+        const LinArgs& a = g.p[phase];
+        const int kchunks = (a.K1 + a.K2) / KC;
+        const uint32_t w_part = (uint32_t)a.NT * KC * 2;
+        const uint32_t w_mine = PAIR ? w_part / 2 : w_part;
+        const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * M_TILE : M_TILE, a.NT, /*bf16=*/true);
+        const uint32_t buf = (uint32_t)j & 1, aph = ((uint32_t)j >> 1) & 1;
         mbar_wait(&acc_empty[buf], aph ^ 1);
         tcgen05_fence_after();
         const uint32_t d = tmem_base + buf * NT_MAX;
@@ -236,8 +296,8 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
   } else if (warp == 3) {
     // ===== completion forwarder (peer CTA of a pair): tells the leader that this CTA's copies have landed; lane s follows stage s =====
     if (PAIR && !leader && lane < STAGES) {
-      const int my_units = u0 < units ? (units - u0 + ustep - 1) / ustep : 0;
-      const uint32_t total_it = (uint32_t)my_units * (uint32_t)kchunks;
+      uint32_t total_it = (uint32_t)seq.n * (uint32_t)((g.p[0].K1 + g.p[0].K2) / KC);
+      if (nphase == 2) total_it += (uint32_t)seq.n * (uint32_t)((g.p[1].K1 + g.p[1].K2) / KC);
       const uint32_t remote = mapa_shared(smem_u32(&full[lane]), 0);
       uint32_t ph = 0;
       for (uint32_t it = lane; it < total_it; it += STAGES, ph ^= 1) {
@@ -258,16 +318,22 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
     const uint32_t acc_empty_remote1 = PAIR ? mapa_shared(smem_u32(&acc_empty[1]), 0) : 0u;
     // bias / gamma / beta -> shared memory, by the epilogue warps themselves while the first stages are in flight (the
     // epilogue reads them per 16-column block; as global loads they sat on its critical path)
-    for (int i = threadIdx.x - 128; i < a.N; i += EPI_WARPS * 32) {
-      sbias[i] = a.bias ? __ldg(a.bias + i) : 0.f;
-      if (a.norm_mode == 2) { sgamma[i] = __ldg(a.gamma + i); sbeta[i] = __ldg(a.beta + i); }
+    for (int p = 0; p < nphase; ++p) {
+      const LinArgs& ap = g.p[p];
+      for (int i = threadIdx.x - 128; i < ap.N; i += EPI_WARPS * 32) {
+        sbias[p * 512 + i] = ap.bias ? __ldg(ap.bias + i) : 0.f;
+        if (ap.norm_mode == 2) { sgamma[i] = __ldg(ap.gamma + i); sbeta[i] = __ldg(ap.beta + i); }
+      }
     }
     named_bar_sync(3, EPI_WARPS * 32);
-    const int part_cols = (((a.NT + CPARTS - 1) / CPARTS + 15) / 16) * 16;
-    const int c_lo = min(a.NT, cpart * part_cols), c_hi = min(a.NT, c_lo + part_cols);
-    uint32_t acc_it = 0;
-    for (int u = u0; u < units; u += ustep, ++acc_it) {
-      const int grp = u / a.passes, pass = u % a.passes;
+    for (int j = 0; j < n_units; ++j) {
+      int phase, grp, pass, ti;
+      seq.get(j, phase, grp, pass, ti);
+      const LinArgs& a = g.p[phase];
+      const float* sb = sbias + phase * 512;
+      const int part_cols = (((a.NT + CPARTS - 1) / CPARTS + 15) / 16) * 16;
+      const int c_lo = min(a.NT, cpart * part_cols), c_hi = min(a.NT, c_lo + part_cols);
+      const uint32_t acc_it = (uint32_t)j;
       const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
       mbar_wait(&acc_full[buf], aph);
@@ -277,7 +343,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
       const int row0 = m_tile * M_TILE + q * 32;
       if (a.norm_mode != 0) {
         // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0) ----
-        float* xs = reinterpret_cast<float*>(smem + G::XCH_OFF) + (acc_it & 1) * (3 * CPARTS * 128);
+        float* xs = reinterpret_cast<float*>(smem + G::XCH_OFF) + (ti & 1) * (3 * CPARTS * 128);   // alternates per phase-0 unit
         const int rit = q * 32 + lane;
         const long long grow = (long long)row0 + lane;
         const bool live = grow < M;
@@ -314,7 +380,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(sbias + c + j);
+            const float4 bb = *reinterpret_cast<const float4*>(sb + c + j);
             o[j] = __uint_as_float(v[j]) + bb.x; o[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
             o[j + 2] = __uint_as_float(v[j + 2]) + bb.z; o[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
           }
@@ -409,7 +475,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sbias + n0 + c + j);
+          const float4 bb = *reinterpret_cast<const float4*>(sb + n0 + c + j);
           o[j] = fmaf(__uint_as_float(v[j]), scale, bb.x); o[j + 1] = fmaf(__uint_as_float(v[j + 1]), scale, bb.y);
           o[j + 2] = fmaf(__uint_as_float(v[j + 2]), scale, bb.z); o[j + 3] = fmaf(__uint_as_float(v[j + 3]), scale, bb.w);
         }
@@ -451,10 +517,16 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
       if (a.ssq_out && live) a.ssq_out[(size_t)grow * (CPARTS * a.passes) + CPARTS * pass + cpart] = ss;
       }
       tcgen05_fence_before();
+      if (nphase == 2 && phase == 0) {
+        // this warp's share of the image tile must be in L2 and ordered before the producer's bulk copy (async proxy) reads it
+        __threadfence();
+        fence_proxy_async_all();
+      }
       __syncwarp();
       if (lane == 0) {   // the TMEM reads are complete (wait::ld); nothing is handed over through memory, hence relaxed
         if (leader) mbar_arrive(&acc_empty[buf]);
         else mbar_arrive_cluster_relaxed(buf ? acc_empty_remote1 : acc_empty_remote0);
+        if (nphase == 2 && phase == 0) mbar_arrive(&a_done[ti & 3]);
       }
     }
   }
@@ -470,8 +542,8 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs& a) {
   }
 }
 
-__global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_kernel(LinArgs a) { linear_tc_body<false, 2>(a); }
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_kernel(LinArgs a) { linear_tc_body<true, 2>(a); }
+__global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<false, 2>(a); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2>(a); }
 
 // W (N, K) fp32 -> image [pass][kchunk]{hi (NT x 32), lo (NT x 32)} canonical K-major, SBO 512.
 __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restrict__ W, int N, int K, int NT, uint8_t* __restrict__ image) {
@@ -574,11 +646,9 @@ int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, voi
   return MESHTOK_OK;
 }
 
-int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
-                     int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream) {
-  if (m_max == 0) return MESHTOK_OK;
+static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias,
+                         float* C, int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi) {
   MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
-  LinArgs a;
   a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
   a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
   if (epi != nullptr && epi->norm_mode == 0) {
@@ -601,26 +671,66 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
   a.a1_image = static_cast<const uint8_t*>(a1_image); a.a2_image = static_cast<const uint8_t*>(a2_image);
   a.K1 = K1; a.K2 = K2; a.w_image = static_cast<const uint8_t*>(w_image); a.bias = bias; a.C = C;
   a.N = N; a.m_dev = m_dev; a.m_max = m_max; a.relu = relu ? 1 : 0;
-  int rc = linear_tc_plan(N, K1, K2, &a.passes, &a.NT);
-  if (rc != MESHTOK_OK) return rc;
+  return linear_tc_plan(N, K1, K2, &a.passes, &a.NT);
+}
+
+static int launch_lin2(const LinArgs2& g, int m_max, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
     MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
     configured = true;
   }
+  const int passes = g.nphase == 2 ? 1 : g.p[0].passes;
   if (linear_tc_pair()) {
     using P2 = Cfg<true, 2>;
-    const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * a.passes;
+    const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * passes;
     const int grid = 2 * min(units, 148 / 2);
-    MT_LAUNCH_PDL(linear_tc_pair_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, a);
+    MT_LAUNCH_PDL(linear_tc_pair_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, g);
   } else {
     using S2 = Cfg<false, 2>;
-    const int units = ceil_div(m_max, M_TILE) * a.passes;
+    const int units = ceil_div(m_max, M_TILE) * passes;
     const int grid = min(units, 148);
-    MT_LAUNCH_PDL(linear_tc_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, a);
+    MT_LAUNCH_PDL(linear_tc_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, g);
   }
   return MESHTOK_OK;
+}
+
+int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
+                     int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream) {
+  if (m_max == 0) return MESHTOK_OK;
+  LinArgs2 g;
+  memset(&g, 0, sizeof(g));
+  g.nphase = 1;
+  int rc = fill_lin_args(g.p[0], a1_image, K1, a2_image, K2, w_image, bias, C, N, m_dev, m_max, relu, epi);
+  if (rc != MESHTOK_OK) return rc;
+  return launch_lin2(g, m_max, stream);
+}
+
+// MESHTOK_LINEAR_B2B=0 keeps every linear in its own launch (A/B runs)
+bool linear_tc_b2b_ok(int N, int norm_mode) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MESHTOK_LINEAR_B2B"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  // both phases single pass; phase 1 reads the image phase 0 writes: K = N, a multiple of the 32-column image chunk
+  return on == 1 && norm_mode != 0 && N <= NT_MAX && N % KC == 0 && (norm_mode != 2 || N <= 64);
+}
+
+// phase 0: C/out_image = norm([A1 | A2] W^T + bias) (epi: fused row epilogue, out_image required);  phase 1: C2 = relu(out W2^T + bias2)
+int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
+                         int N, const int* m_dev, int m_max, const LinearRowEpilogue* epi, const void* w2_image, const float* bias2,
+                         float* C2, cudaStream_t stream) {
+  if (m_max == 0) return MESHTOK_OK;
+  MT_CHECK_ARG(epi != nullptr && epi->norm_mode != 0 && epi->out_image != nullptr, "tcgen05 linear pair of phases: phase 0 needs the fused row epilogue and an output image");
+  MT_CHECK_ARG(linear_tc_b2b_ok(N, epi->norm_mode), "tcgen05 linear pair of phases: width %d not supported", N);
+  LinArgs2 g;
+  memset(&g, 0, sizeof(g));
+  g.nphase = 2;
+  int rc = fill_lin_args(g.p[0], a1_image, K1, a2_image, K2, w_image, bias, C, N, m_dev, m_max, false, epi);
+  if (rc != MESHTOK_OK) return rc;
+  rc = fill_lin_args(g.p[1], epi->out_image, N, nullptr, 0, w2_image, bias2, C2, N, m_dev, m_max, true, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(g.p[0].passes == 1 && g.p[1].passes == 1, "tcgen05 linear pair of phases: both must be single pass");
+  return launch_lin2(g, m_max, stream);
 }
 
 }  // namespace meshtok
