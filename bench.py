@@ -79,8 +79,29 @@ def build_models(name, want_cuda):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons of one GPU while the bench runs: NVML polled every ~2 ms from a thread (nvidia-smi -lms
+    100 as the fallback), so that even a 20 ms timed region gets several samples.  window_begin() / window_end() bracket the
+    device-timed loop; the reported median is over the samples inside the window (all samples if none fell inside)."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.rows, self.proc, self.nvml, self.stop_flag = [], None, None, False
+        self.t0 = self.t1 = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            try:   # the CUDA device may not be NVML device `index` (CUDA_VISIBLE_DEVICES): go by UUID
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
@@ -90,33 +111,60 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self):
-        if self.proc is None:
-            return None
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
             try:
-                sm.append(float(r[0]))
-                smax.append(float(r[1]))
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                try:
+                    mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.rows.append((time.perf_counter(), sm, self.smax, {name for name, bit in self.REASONS if mask & bit}))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def _pump(self):
+        names = [n for n, _ in self.REASONS]
+        for line in self.proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]),
+                                  {n for n, v in zip(names, r[3:7]) if v.lower().startswith("active")}))
             except (ValueError, IndexError):
                 continue
-            for n, v in zip(names, r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        if not sm:
+
+    def window_begin(self):
+        self.t0 = time.perf_counter()
+
+    def window_end(self):
+        self.t1 = time.perf_counter()
+
+    def stop(self):
+        if self.nvml is None and self.proc is None:
             return None
-        busy = sorted(s for s in sm if s >= 0.5 * max(sm)) or sorted(sm)
-        return dict(sm_mhz=busy[len(busy) // 2], sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.thread.join(timeout=1)
+        rows = list(self.rows)
+        if not rows:
+            return None
+        inside = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[0] <= self.t1]
+        use = inside or rows
+        sm = sorted(r[1] for r in use)
+        reasons = set()
+        for r in use:
+            reasons |= r[3]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_min_mhz=sm[0], sm_max_mhz=max(r[2] for r in use), reasons=sorted(reasons),
+                    samples=len(use), samples_total=len(rows), source="nvml" if self.nvml is not None else "nvidia-smi",
+                    window="device-timed loop" if inside else "whole measurement")
 
 
 def section_work(model, n_faces, n_vrows, n_edges, batch, F, V):
@@ -160,7 +208,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     oracle, _ = build_models(args.workload, want_cuda=False)
-    n = args.cpu_meshes
+    n = min(args.cpu_meshes, WORKLOADS[args.workload].get("batch", args.cpu_meshes))
     faces, times = cpu_time_oracle(oracle, args.workload, n, args.steps, args.warmup)
     ms = 1e3 * sum(times) / len(times)
     val = faces / (ms / 1e3)
@@ -181,7 +229,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-meshes", type=int, default=16, help="meshes in the CPU baseline sample")
+    ap.add_argument("--cpu-meshes", type=int, default=64, help="meshes in the CPU baseline sample (capped at the batch size)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline-depth", type=int, default=2, help="batches in flight in the host-to-host pipeline (e2e)")
     ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
@@ -314,7 +362,11 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.meshtok_kernel_launch_count()
+    if sampler:
+        sampler.window_begin()
     ms_dev, wall_dev, _, _ = timed(device_step, args.steps)
+    if sampler:
+        sampler.window_end()
     launches = lib.meshtok_kernel_launch_count() - launches0
     if graphed is not None:
         launches = launches_per_graph * args.steps          # kernels inside the replayed graphs
@@ -400,9 +452,11 @@ def main():
                             flops_per_launch=flops, ms_per_launch=per_launch_ms)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            faces_s, times = cpu_time_oracle(oracle, args.workload, args.cpu_meshes, repeats=2, warmup=1)
+            n_cpu = min(args.cpu_meshes, batch)
+            faces_s, times = cpu_time_oracle(oracle, args.workload, n_cpu, repeats=5, warmup=1)
             cpu = dict(value=faces_s / min(times), unit=UNIT, cores=os.cpu_count(), kind="port",
-                       sample=f"oracle on {args.cpu_meshes} of the workload's {batch} meshes ({faces_s} faces), best of 2 after 1 warm-up")
+                       sample=f"oracle on {n_cpu} of the workload's {batch} meshes ({faces_s} faces), best of 5 after 1 warm-up, "
+                              f"{sum(times):.1f} s of CPU work")
         h2d = v_pin.numel() * v_pin.element_size() + f_pin.numel() * f_pin.element_size()
         d2h = codes_pin.numel() * codes_pin.element_size()
         line = dict(metric=METRIC, value=total_faces / (ms_dev * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
