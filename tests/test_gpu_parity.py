@@ -358,6 +358,19 @@ def test_full_size_properties_c2_and_c3():
         assert bool((c[:, 500 * nvf:] == -1).all()) and bool((c[:, :500 * nvf] >= 0).all())
 
 
+@pytest.mark.parametrize("kind,cfg,nxny", [("tri", dict(use_residual_lfq=False), (20, 20)), ("quad", dict(quads=True), (20, 40))])
+def test_full_model_tokens_against_oracle(kind, cfg, nxny):
+    """The full-size model (192-d, 16384 codes, encoder 64-128-256-256-576) on meshes of the BASELINE shape (800 faces),
+    token by token against the CPU oracle.  Measured agreement: 100 % (scripts/gpu_match_rates.py); the bar leaves room
+    for near-ties only."""
+    o, m = make_pair(**cfg)
+    v, f = synth.grid_batch(kind, *nxny, [0, 1, 2, 3])
+    want = o.tokenize(v, f)
+    got = m.tokenize(v.cuda(), f.cuda()).cpu()
+    assert got.shape == want.shape
+    assert match_rate(got, want) >= 0.999, match_rate(got, want)
+
+
 def test_face_edges_cache_bulk_fill(tmp_path):
     """the GPU adjacency kernel fills the reference's on-disk face-edge cache for a whole batch."""
     import numpy as np
