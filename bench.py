@@ -233,6 +233,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--pipeline-depth", type=int, default=2, help="batches in flight in the host-to-host pipeline (e2e)")
     ap.add_argument("--no-hist", action="store_true", help="experiment: skip the codebook-usage histogram")
+    ap.add_argument("--hist-every-step", action="store_true", help="all-reduce the histogram after every step instead of once after the last")
     ap.add_argument("--precomputed-edges", action="store_true",
                     help="pass face_edges (derived once, outside the timed region) instead of deriving them inside tokenize (BASELINE config 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch the pipeline kernel by kernel instead of replaying its CUDA graph")
@@ -281,12 +282,19 @@ def main():
 
     step_hist = torch.zeros_like(hist)
 
-    def eager_step():
-        step_hist.zero_()
-        model.forward(vertices=v_dev, faces=f_dev, face_edges=e_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
-        if world > 1:
+    # The codebook-usage histogram is a statistic of the JOB: every rank accumulates its own on the device (the kernels add
+    # into step_hist) and the ranks exchange it ONCE, after the last step, inside the timed region ("reduced once
+    # per run (or per batch)").  --hist-every-step all-reduces after every step instead (a cross-rank sync per step).
+    def reduce_hist():
+        if world > 1 and not args.no_hist:
             dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
-        hist.add_(step_hist)
+
+    def eager_step():
+        model.forward(vertices=v_dev, faces=f_dev, face_edges=e_dev, return_codes=True, histogram=None if args.no_hist else step_hist, check_status=False)
+        if args.hist_every_step:
+            reduce_hist()
+            hist.add_(step_hist)
+            step_hist.zero_()
 
     # the whole pipeline of a batch as ONE CUDA graph (the C ABI never allocates or synchronises)
     graphed = None
@@ -299,11 +307,11 @@ def main():
     def device_step():
         if graphed is None:
             return eager_step()
-        step_hist.zero_()
         graphed()
-        if world > 1:
-            dist.all_reduce(step_hist, op=dist.ReduceOp.SUM, async_op=True).wait()
-        hist.add_(step_hist)
+        if args.hist_every_step:
+            reduce_hist()
+            hist.add_(step_hist)
+            step_hist.zero_()
 
     codes_pin = torch.empty((batch, f_cpu.shape[1] * f_cpu.shape[2], Q), dtype=torch.int64, pin_memory=True)
 
@@ -315,7 +323,7 @@ def main():
         else:
             graphed.tokenize_host(v_pin, f_pin, pinned_out=codes_pin)
 
-    def timed(step_fn, steps, profile=False):
+    def timed(step_fn, steps, profile=False, finalize=None):
         evs = []
         if profile:
             lib.meshtok_profile_enable(1)
@@ -326,6 +334,12 @@ def main():
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn()
+            b.record()
+            evs.append((a, b))
+        if finalize is not None:    # the job's one exchange: timed, and charged to the steps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            finalize()
             b.record()
             evs.append((a, b))
         barrier()
@@ -364,10 +378,15 @@ def main():
     launches0 = lib.meshtok_kernel_launch_count()
     if sampler:
         sampler.window_begin()
-    ms_dev, wall_dev, _, _ = timed(device_step, args.steps)
+    step_hist.zero_()
+    ms_dev, wall_dev, _, _ = timed(device_step, args.steps, finalize=None if args.hist_every_step else reduce_hist)
     if sampler:
         sampler.window_end()
     launches = lib.meshtok_kernel_launch_count() - launches0
+    if not args.no_hist:   # the job's histogram: every valid token of every step of every rank, once per quantizer level
+        got_tokens = int((hist if args.hist_every_step else step_hist).sum().item())
+        want_tokens = args.steps * world * n_faces_rank * model.num_vertices_per_face * Q
+        assert got_tokens == want_tokens, f"histogram holds {got_tokens} tokens, expected {want_tokens}"
     if graphed is not None:
         launches = launches_per_graph * args.steps          # kernels inside the replayed graphs
     # second pass, kernel by kernel, with cudaEvent pairs around every pipeline section (kept out of the headline timing)
@@ -465,7 +484,7 @@ def main():
                     data="synthetic",
                     config=dict(workload=args.workload + ": " + w["desc"], meshes_per_rank=batch, faces_per_step=total_faces,
                                 quantizer_rows_per_rank=R, l2="flushed between steps (512 MiB memset outside the timed events)",
-                                sharding="meshes by rank, weights replicated; NCCL all-reduce of the (Q,K) int64 histogram per step",
+                                sharding="meshes by rank, weights replicated; (Q,K) int64 histogram accumulated per rank on the device, " + ("NCCL all-reduce after every step" if args.hist_every_step else "ONE NCCL all-reduce after the last step, inside the timed region"),
                                 launch="one CUDA graph replay per step" if graphed is not None else "kernel by kernel",
                                 face_edges="precomputed (user-supplied edge lists -> CSR by target on the device)" if e_dev is not None else "derived inside tokenize",
                                 wall_ms_per_step_incl_flush=1e3 * wall_dev / args.steps,
