@@ -180,7 +180,10 @@ def section_work(model, n_faces, n_vrows, n_edges, batch, F, V):
         "face_embed": ("hbm", faces_b + batch * V * 12 + N * D * 4),
         "sage_gather_mean": ("hbm", sum(2 * N * d * 4 for d in dims_in) + len(dims_in) * 4 * (E + N)),
         "sage_row_norm": ("hbm", 3 * N * dims_out[-1] * 4),
-        "scatter_mean": ("hbm", N * nvf * D * 4 + R * D * 4 + 4 * (N * nvf + R)),
+        # read y once, write the vertex means once, the vertex incidence CSR; for RVQ models the kernel also emits the level-0
+        # residual copy, row scales and the fp16 row image (2 D + 32 B per row) the search kernel reads
+        "scatter_mean": ("hbm", N * nvf * D * 4 + R * D * 4 + 4 * (N * nvf + R)
+                         + (0 if getattr(model, "use_residual_lfq", True) else R * (D * 4 + 4 + 2 * D + 32))),
         "gather_codes": ("hbm", faces_b + R * Q * 4 + batch * F * nvf * Q * 8),
         "lfq": ("hbm", R * D * 4 + R * Q * 4),
         # fp32-equivalent flops; the split-bf16 scheme issues 3 bf16 MMAs per product
