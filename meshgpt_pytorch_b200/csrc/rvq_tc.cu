@@ -300,6 +300,18 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n = min(*n_dev, max_rows);
+  // loop invariants, hoisted by hand (the 64-bit divisions of the work split were a third of this kernel's instructions
+  // when they sat in the row loop): W = steps per cluster of the CTA-pair search, see rvq_tc2.cu
+  unsigned W = 1u;
+  if (lay.mode == 2) {
+    const long long S = (long long)((n + 255) >> 8) * lay.T;
+    long long w = (S + lay.n_clusters - 1) / lay.n_clusters;
+    if (w < lay.w_min) w = lay.w_min;
+    W = (unsigned)w;
+  }
+  const float sqrt_d = sqrtf((float)D);
+  const float mn2 = max_norm * max_norm;
+  const float inv_escale = 1.f / escale;   // powers of two: the reciprocals are exact
   for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
     float x[PER];
     float x2 = 0.f;
@@ -311,22 +323,20 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
     }
     x2 = warp_sum(x2);
     const float xn = sqrtf(x2);
+    const float rs = rscale[row];
     float delta = 0.001953125f * 1.01f * xn * max_norm +
-                  5.96e-8f * sqrtf((float)D) * (max_norm / rscale[row] + xn / escale) + 1e-7f * (x2 + max_norm * max_norm);
+                  5.96e-8f * sqrt_d * (max_norm * __frcp_rn(rs) + xn * inv_escale) + 1e-7f * (x2 + mn2);
     if (c_scale > 0.f) {
       // CTA-pair kernel: |e|^2 enters the MMA chain as an fp16 (hi, lo) pair (relative error 2^-21) times the row constant
       // rscale * c_scale; should that constant underflow fp16 (astronomically large rows) the |e|^2 term is lost altogether
-      delta += 1e-6f * max_norm * max_norm;
-      if (rscale[row] * c_scale < 5.9604645e-8f) delta += max_norm * max_norm;
+      delta += 1e-6f * mn2;
+      if (rs * c_scale < 5.9604645e-8f) delta += mn2;
     }
-    // this row's candidate entries (see RvqPartialLayout)
+    // this row's candidate entries (see RvqPartialLayout): the slots of the clusters whose step range meets the row tile's
     int n_splits = lay.stride;
     if (lay.mode == 2) {
-      const long long g = row >> 8;                                    // 256-row tile
-      const long long S = (long long)((n + 255) >> 8) * lay.T;
-      long long W = (S + lay.n_clusters - 1) / lay.n_clusters;
-      if (W < lay.w_min) W = lay.w_min;
-      n_splits = lay.parts * (int)((g * lay.T + lay.T - 1) / W - (g * lay.T) / W + 1);
+      const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;      // first step of the 256-row tile (the launcher checks the range)
+      n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
     }
     // lane s holds entry s (n_splits <= 32 is checked by the launcher): one parallel load instead of a serial walk
     const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
@@ -495,6 +505,8 @@ int launch_rvq_rescore(const float* rows, const float* rscale, int D, const floa
                        unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   MT_CHECK_ARG(layout.stride <= 32, "rvq re-score: at most 32 candidate entries per row (got %d)", layout.stride);
+  MT_CHECK_ARG(layout.mode != 2 || (long long)ceil_div(max_rows, 256) * layout.T < (1ll << 31),
+               "rvq re-score: %d rows x %d code tiles exceed the 32-bit step range", max_rows, layout.T);
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, c_scale, rscale, partial, layout, n_rows_dev,
                 max_rows, packed, amb_list, amb_count);
