@@ -71,9 +71,29 @@ __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restri
   pdl_launch_dependents();
 }
 
+// sum over the warp of 16 per-lane values at once: a halving butterfly (8 + 4 + 2 + 1 + 1 shuffles instead of 16 x 5);
+// afterwards every lane holds the total of value number (lane >> 1) & 15
+__device__ __forceinline__ float warp_sum16(float (&p)[16]) {
+  const int lane = lane_id();
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send = up ? p[j] : p[j + half];
+      const float keep = up ? p[j + half] : p[j];
+      p[j] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return p[0] + __shfl_xor_sync(0xffffffffu, p[0], 1);
+}
+
 // Residual LFQ (eval).  x = W_in v + b; level l: bit_d = r_d > 0, q_d = +-2^-l, r <- r - q;
 // code = sum_d bit_d << (bits-1-d)  (dimension 0 is the most significant bit).
 // The soft clamp tanh(r/c)*c of the upstream module preserves the sign and is therefore skipped.
+// Two rows per warp pass: every weight is loaded once for both, and the `bits` (<= 16) dot products of a row are reduced
+// together (warp_sum16).  The first version reduced one dot product at a time: 14 x 5 shuffles per row, 57 us for the
+// 55 168 rows of the quad workload.
 template <int PER>
 __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows, int D, const float* __restrict__ w_in,
                                                   const float* __restrict__ b_in, int bits, int Q,
@@ -83,47 +103,61 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows
   const int lane = lane_id();
   const int wpb = blockDim.x >> 5;
   const int n = n_rows_dev ? min(*n_rows_dev, max_rows) : max_rows;
-  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
-    float v[PER];
+  const int d_mine = (lane >> 1) & 15;   // the projected dimension whose total this lane ends up with
+  const float bias_mine = d_mine < bits ? b_in[d_mine] : 0.f;
+  for (int row0 = 2 * (blockIdx.x * wpb + warp_id()); row0 < n; row0 += 2 * gridDim.x * wpb) {
+    const bool two = row0 + 1 < n;
+    float v0[PER], v1[PER];
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
-      v[i] = c < D ? rows[(size_t)row * D + c] : 0.f;
+      v0[i] = c < D ? rows[(size_t)row0 * D + c] : 0.f;
+      v1[i] = (c < D && two) ? rows[(size_t)(row0 + 1) * D + c] : 0.f;
     }
-    float x_mine = 0.f;  // lane d keeps projected dimension d
-    for (int dd = 0; dd < bits; ++dd) {
-      float part = 0.f;
+    float p0[16], p1[16];
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int c = lane + 32 * i;
-        if (c < D) part = fmaf(v[i], __ldg(w_in + (size_t)dd * D + c), part);
-      }
-      part = warp_sum(part) + b_in[dd];
-      if (lane == dd) x_mine = part;
-    }
-    float r = x_mine, qsum = 0.f;
-    for (int l = 0; l < Q; ++l) {
-      const float scale = exp2f(-(float)l);
-      const bool bit = (lane < bits) && (r > 0.f);
-      const unsigned m = __ballot_sync(0xffffffffu, bit);
-      // lane d holds bit (bits-1-d) of the code: reverse the low `bits` bits of the ballot
-      const unsigned code = __brev(m) >> (32 - bits);
-      if (lane == 0) codes[(size_t)row * Q + l] = (int32_t)code;
-      const float q = bit ? scale : -scale;
-      r -= q;
-      qsum += q;
-    }
-    if (quantized_out != nullptr) {
-      // project_out: (D x bits) . qsum + b_out
+    for (int dd = 0; dd < 16; ++dd) {
+      p0[dd] = 0.f; p1[dd] = 0.f;
+      if (dd < bits) {
 #pragma unroll
-      for (int i = 0; i < PER; ++i) {
-        const int c = lane + 32 * i;
-        float o = 0.f;
-        for (int dd = 0; dd < bits; ++dd) {
-          const float qd = __shfl_sync(0xffffffffu, qsum, dd);
-          if (c < D) o = fmaf(qd, __ldg(w_out + (size_t)c * bits + dd), o);
+        for (int i = 0; i < PER; ++i) {
+          const int c = lane + 32 * i;
+          if (c < D) {
+            const float w = __ldg(w_in + (size_t)dd * D + c);
+            p0[dd] = fmaf(v0[i], w, p0[dd]);
+            p1[dd] = fmaf(v1[i], w, p1[dd]);
+          }
         }
-        if (c < D) quantized_out[(size_t)row * D + c] = o + b_out[c];
+      }
+    }
+    const float x0 = warp_sum16(p0) + bias_mine, x1 = warp_sum16(p1) + bias_mine;
+#pragma unroll
+    for (int rr = 0; rr < 2; ++rr) {
+      if (rr == 1 && !two) break;
+      const int row = row0 + rr;
+      float r = rr ? x1 : x0, qsum = 0.f;
+      for (int l = 0; l < Q; ++l) {
+        const float scale = exp2f(-(float)l);
+        const bool bit = (d_mine < bits) && (r > 0.f);
+        // dimension 0 is the most significant bit; the two lanes that hold a dimension contribute the same bit
+        const unsigned code = __reduce_or_sync(0xffffffffu, bit ? (1u << (bits - 1 - d_mine)) : 0u);
+        if (lane == 0) codes[(size_t)row * Q + l] = (int32_t)code;
+        const float q = bit ? scale : -scale;
+        r -= q;
+        qsum += q;
+      }
+      if (quantized_out != nullptr) {
+        // project_out: (D x bits) . qsum + b_out   (lane 2 * dd holds dimension dd)
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+          const int c = lane + 32 * i;
+          float o = 0.f;
+          for (int dd = 0; dd < bits; ++dd) {
+            const float qd = __shfl_sync(0xffffffffu, qsum, 2 * dd);
+            if (c < D) o = fmaf(qd, __ldg(w_out + (size_t)c * bits + dd), o);
+          }
+          if (c < D) quantized_out[(size_t)row * D + c] = o + b_out[c];
+        }
       }
     }
   }
@@ -239,7 +273,8 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
   MT_CHECK_ARG(bits >= 1 && bits <= 30, "lfq: codebook_size must be 2^1..2^30 (bits=%d)", bits);
   MT_CHECK_ARG(D >= 1 && D <= 512, "lfq: dim %d must be <= 512", D);
   if (max_rows == 0) return MESHTOK_OK;
-  const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
+  MT_CHECK_ARG(bits >= 1 && bits <= 16, "lfq: %d bits per level (codebook_size up to 65536 is supported)", bits);
+  const int blocks = max(1, min(ceil_div(max_rows, 16), 148 * 16));
   const int per = ceil_div(D, 32);
 #define LQ(P) lfq_kernel<P><<<blocks, 256, 0, stream>>>(rows, D, w_in, b_in, bits, Q, w_out, b_out, codes, quantized_out, n_rows_dev, max_rows)
   if (per <= 2) LQ(2);
