@@ -94,7 +94,9 @@ __device__ __forceinline__ float warp_sum16(float (&p)[16]) {
 // Two rows per warp pass: every weight is loaded once for both, and the `bits` (<= 16) dot products of a row are reduced
 // together (warp_sum16).  The first version reduced one dot product at a time: 14 x 5 shuffles per row, 57 us for the
 // 55 168 rows of the quad workload.
-template <int PER>
+// PER = elements per lane; VEC2: D is a multiple of 64 and a lane owns PER / 2 pairs of adjacent columns (8-byte loads, no
+// tail predicates: half the load instructions of the scalar layout, which is kept for other widths)
+template <int PER, bool VEC2>
 __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows, int D, const float* __restrict__ w_in,
                                                   const float* __restrict__ b_in, int bits, int Q,
                                                   const float* __restrict__ w_out, const float* __restrict__ b_out,
@@ -108,24 +110,51 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows
   for (int row0 = 2 * (blockIdx.x * wpb + warp_id()); row0 < n; row0 += 2 * gridDim.x * wpb) {
     const bool two = row0 + 1 < n;
     float v0[PER], v1[PER];
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int c = lane + 32 * i;
-      v0[i] = c < D ? rows[(size_t)row0 * D + c] : 0.f;
-      v1[i] = (c < D && two) ? rows[(size_t)(row0 + 1) * D + c] : 0.f;
-    }
     float p0[16], p1[16];
+    if (VEC2) {
+      const int np = D >> 6;   // pairs per lane (D / 64); PER / 2 at most
 #pragma unroll
-    for (int dd = 0; dd < 16; ++dd) {
-      p0[dd] = 0.f; p1[dd] = 0.f;
-      if (dd < bits) {
+      for (int i = 0; i < PER / 2; ++i) {
+        float2 a = make_float2(0.f, 0.f), b = a;
+        if (i < np) {
+          a = *reinterpret_cast<const float2*>(rows + (size_t)row0 * D + 2 * (lane + 32 * i));
+          if (two) b = *reinterpret_cast<const float2*>(rows + (size_t)(row0 + 1) * D + 2 * (lane + 32 * i));
+        }
+        v0[2 * i] = a.x; v0[2 * i + 1] = a.y; v1[2 * i] = b.x; v1[2 * i + 1] = b.y;
+      }
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-          const int c = lane + 32 * i;
-          if (c < D) {
-            const float w = __ldg(w_in + (size_t)dd * D + c);
-            p0[dd] = fmaf(v0[i], w, p0[dd]);
-            p1[dd] = fmaf(v1[i], w, p1[dd]);
+      for (int dd = 0; dd < 16; ++dd) {
+        p0[dd] = 0.f; p1[dd] = 0.f;
+        if (dd < bits) {
+#pragma unroll
+          for (int i = 0; i < PER / 2; ++i) {
+            if (i < np) {
+              const float2 w = __ldg(reinterpret_cast<const float2*>(w_in + (size_t)dd * D) + lane + 32 * i);
+              p0[dd] = fmaf(v0[2 * i + 1], w.y, fmaf(v0[2 * i], w.x, p0[dd]));
+              p1[dd] = fmaf(v1[2 * i + 1], w.y, fmaf(v1[2 * i], w.x, p1[dd]));
+            }
+          }
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        v0[i] = c < D ? rows[(size_t)row0 * D + c] : 0.f;
+        v1[i] = (c < D && two) ? rows[(size_t)(row0 + 1) * D + c] : 0.f;
+      }
+#pragma unroll
+      for (int dd = 0; dd < 16; ++dd) {
+        p0[dd] = 0.f; p1[dd] = 0.f;
+        if (dd < bits) {
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            const int c = lane + 32 * i;
+            if (c < D) {
+              const float w = __ldg(w_in + (size_t)dd * D + c);
+              p0[dd] = fmaf(v0[i], w, p0[dd]);
+              p1[dd] = fmaf(v1[i], w, p1[dd]);
+            }
           }
         }
       }
@@ -276,11 +305,15 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
   MT_CHECK_ARG(bits >= 1 && bits <= 16, "lfq: %d bits per level (codebook_size up to 65536 is supported)", bits);
   const int blocks = max(1, min(ceil_div(max_rows, 16), 148 * 16));
   const int per = ceil_div(D, 32);
-#define LQ(P) lfq_kernel<P><<<blocks, 256, 0, stream>>>(rows, D, w_in, b_in, bits, Q, w_out, b_out, codes, quantized_out, n_rows_dev, max_rows)
-  if (per <= 2) LQ(2);
-  else if (per <= 6) LQ(6);
-  else if (per <= 8) LQ(8);
-  else LQ(16);
+#define LQ(P, V) lfq_kernel<P, V><<<blocks, 256, 0, stream>>>(rows, D, w_in, b_in, bits, Q, w_out, b_out, codes, quantized_out, n_rows_dev, max_rows)
+  const bool vec2 = D % 64 == 0 && (reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(w_in)) % 8 == 0;
+  if (vec2 && per <= 2) LQ(2, true);
+  else if (vec2 && per <= 6) LQ(6, true);
+  else if (vec2 && per <= 8) LQ(8, true);
+  else if (per <= 2) LQ(2, false);
+  else if (per <= 6) LQ(6, false);
+  else if (per <= 8) LQ(8, false);
+  else LQ(16, false);
 #undef LQ
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
