@@ -9,7 +9,7 @@ run t_linear  python -m pytest tests/test_gpu_parity.py -q -m gpu -k "linear"
 run t_quant   python -m pytest tests/test_gpu_parity.py -q -m gpu -k "lfq or rvq"
 run t_encoder python -m pytest tests/test_gpu_parity.py -q -m gpu -k "encoder or encode_and"
 run t_e2e     python -m pytest tests/test_gpu_parity.py -q -m gpu -k "golden or variants or histogram or full_size or full_model"
-run t_misc    python -m pytest tests/test_gpu_parity.py -q -m gpu -k "pipeline or cache or precomputed or config_matrix or dense_user"
+run t_misc    python -m pytest tests/test_gpu_parity.py -q -m gpu -k "pipeline or cache or precomputed or config_matrix or dense_user or fallback"
 run smoke     python __graft_entry__.py smoke
 run bench     python bench.py --steps 10 --warmup 3
 python scripts/summarize_bench.py gpurun_out/bench.log
