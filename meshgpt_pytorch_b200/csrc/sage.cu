@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
 
 // The same aggregation with the neighbour rows read from shared memory.  Edges never leave a mesh, so CTA (mesh, slice)
 // copies columns [slice * S, +S) of the mesh's x rows into shared memory once (F x S floats; 100 KB for 800 faces and
-// S = 32, two CTAs per SM) and every neighbour read is a 16-byte shared-memory load: S / 4 threads per face, a quarter
+// S = 32, two CTAs per SM) and every neighbour read is a 16-byte shared-memory load: S / 8 threads per face, a quarter
 // warp reads one 128-byte row slice (no bank conflicts).  L2 -> SM traffic drops from (neighbours + 1) x to 1 x the
 // activation - the warp-per-row kernel above ran at the bandwidth cap of the L2 slices (8-9 TB/s into the SMs).  Same
 // neighbour order and the same rounding as above, hence the same bits.
@@ -98,7 +98,6 @@ __global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* _
   // [rows_cap + 1][S / 4] x slice (the last row stays zero) | [rows_cap + 1] local row pointers | [edges_cap] source row * S/4 (u16)
   extern __shared__ float4 sx[];
   constexpr int s4 = S >> 2;
-  constexpr int ROWS_PER_IT = 512 / s4;
   int* sptr = reinterpret_cast<int*>(sx + (size_t)(rows_cap + 1) * s4);
   unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
   pdl_wait();
@@ -139,40 +138,58 @@ __global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* _
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  // image address of (row, this thread's 4 columns): the column part is fixed, the row part is cheap
-  const int col = slice * S + c * 4;
-  const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u + (uint32_t)(col & 7) * 2u;
+  // S / 8 threads per face, 8 adjacent columns (two 16-byte chunks) each.  The two faces of a quarter warp read their chunks
+  // in opposite order (even chunk first / odd chunk first), so the eight 16-byte reads of one instruction fall on eight
+  // different bank groups whatever rows they come from.
+  constexpr int TPR = s4 / 2;
+  const int g = tid % TPR;
+  const int swap = (tid / TPR) & 1;
+  const int col = slice * S + g * 8;
+  const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u;
   const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
-  const float4* sxc = sx + c;
-  for (int lrow = tid / s4; lrow < n_b; lrow += ROWS_PER_IT) {
+  const float4* sx_first = sx + 2 * g + swap;
+  const float4* sx_second = sx + 2 * g + (swap ^ 1);
+  for (int lrow = tid / TPR; lrow < n_b; lrow += 512 / TPR) {
     const int s = sptr[lrow];
     const int e_true = sptr[lrow + 1];
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
     if (fast) {
       for (int q = s; q < e_true; ++q) {
-        const float4 v = sxc[ssrc[q]];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const int off = ssrc[q];
+        const float4 v = sx_first[off], w = sx_second[off];
+        a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+        a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
       }
     } else {   // a mesh with more edges than the staging area holds, or a list cut by the edge capacity
       const int e = min(e_true, n_e);
       for (int q = s; q < e; ++q) {
         const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
-        const float4 v = sxc[(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        const int off = (int)(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4;
+        const float4 v = sx_first[off], w = sx_second[off];
+        a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+        a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
       }
     }
+    const float4 lo4 = swap ? a2 : a1, hi4 = swap ? a1 : a2;   // columns col .. col+3 and col+4 .. col+7
     const float cnt = fmaxf((float)(e_true - s), 1.f);
     const float rc = __frcp_rn(cnt);
-    const float4 o = make_float4(div_count(acc.x, cnt, rc), div_count(acc.y, cnt, rc), div_count(acc.z, cnt, rc), div_count(acc.w, cnt, rc));
+    const float4 o0 = make_float4(div_count(lo4.x, cnt, rc), div_count(lo4.y, cnt, rc), div_count(lo4.z, cnt, rc), div_count(lo4.w, cnt, rc));
+    const float4 o1 = make_float4(div_count(hi4.x, cnt, rc), div_count(hi4.y, cnt, rc), div_count(hi4.z, cnt, rc), div_count(hi4.w, cnt, rc));
     const int row = r0 + lrow;
-    if (agg) *reinterpret_cast<float4*>(agg + (size_t)row * d + col) = o;
+    if (agg) {
+      float4* dst = reinterpret_cast<float4*>(agg + (size_t)row * d + col);
+      dst[0] = o0;
+      dst[1] = o1;
+    }
     if (agg_image) {
-      uint2 hi, lo;
-      tc::split2(o.x, o.y, hi.x, lo.x);
-      tc::split2(o.z, o.w, hi.y, lo.y);
+      uint4 hi, lo;
+      tc::split2(o0.x, o0.y, hi.x, lo.x);
+      tc::split2(o0.z, o0.w, hi.y, lo.y);
+      tc::split2(o1.x, o1.y, hi.z, lo.z);
+      tc::split2(o1.z, o1.w, hi.w, lo.w);
       uint8_t* pimg = agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_col;
-      *reinterpret_cast<uint2*>(pimg) = hi;
-      *reinterpret_cast<uint2*>(pimg + tc::IMG_PART) = lo;
+      *reinterpret_cast<uint4*>(pimg) = hi;
+      *reinterpret_cast<uint4*>(pimg + tc::IMG_PART) = lo;
     }
   }
   pdl_launch_dependents();
