@@ -67,6 +67,7 @@ SIGNATURES = {
     "meshtok_version": (C.c_int, []),
     "meshtok_last_error_string": (C.c_char_p, []),
     "meshtok_kernel_launch_count": (C.c_int64, []),
+    "meshtok_debug_linear_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "meshtok_profile_enable": (C.c_int, [C.c_int]),
     "meshtok_profile_sections": (C.c_int, []),
     "meshtok_profile_section_name": (C.c_char_p, [C.c_int]),

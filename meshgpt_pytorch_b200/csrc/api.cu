@@ -314,6 +314,8 @@ extern "C" {
 
 int meshtok_version(void) { return MESHTOK_ABI_VERSION; }
 
+int meshtok_debug_linear_trace(long long* out, int n) { return linear_tc_read_trace(out, n); }
+
 const char* meshtok_last_error_string(void) { return g_error; }
 
 int meshtok_topology_workspace_bytes(int B, int F, int nvf, int V, int E_user, size_t* bytes) {

@@ -145,6 +145,7 @@ bool linear_tc_b2b_ok(int N, int norm_mode);   // layer output linear + the next
 int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                          int N, const int* m_dev, int m_max, const LinearRowEpilogue* epi, const void* w2_image, const float* bias2,
                          float* C2, cudaStream_t stream);
+int linear_tc_read_trace(long long* out, int n);   // timing experiments, see linear_tc.cu
 int linear_tc_ssq_parts(int N);   // (column parts per pass) * passes of an N-wide tcgen05 linear, at most 16
 int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,

@@ -110,7 +110,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 struct LinArgs2 {
   LinArgs p[2];
   int nphase;
+  long long* trace;   // timing experiments (MESHTOK_LINEAR_TRACE): clock64 stamps of cluster 0, [2 ranks][8 events][16 units]; else null
 };
+
+#define LT_STAMP(ev, unit)                                                                          \
+  do {                                                                                              \
+    if (g.trace != nullptr && blockIdx.x < 2 && (unit) < 16)                                        \
+      g.trace[((int)blockIdx.x * 8 + (ev)) * 16 + (unit)] = clock64();                              \
+  } while (0)
 
 struct UnitSeq {   // this CTA (pair)'s units in issue order
   int n, u0, ustep, passes, nphase;
@@ -212,6 +219,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         mbar_wait(&a_done[ti & 3], (uint32_t)(ti >> 2) & 1u);
         fence_proxy_async_all();
       }
+      if (lane == 0) LT_STAMP(0, j);   // producer: free to issue this unit's loads
       const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part) + (size_t)rank * w_mine;
       const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
       const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
@@ -233,6 +241,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         __syncwarp();
         if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
       }
+      if (lane == 0) LT_STAMP(1, j);   // producer: last load of the unit issued
     }
     if (PAIR) {   // drain: every multicast commit aimed at this CTA has landed before the CTA may exit
       const uint32_t pending = it < (uint32_t)STAGES ? it : (uint32_t)STAGES;
@@ -255,12 +264,15 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         const uint32_t w_mine = PAIR ? w_part / 2 : w_part;
         const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * M_TILE : M_TILE, a.NT, /*bf16=*/true);
         const uint32_t buf = (uint32_t)j & 1, aph = ((uint32_t)j >> 1) & 1;
+        if (lane == 0) LT_STAMP(2, j);   // MMA: previous unit committed, waiting for the accumulator buffer
         mbar_wait(&acc_empty[buf], aph ^ 1);
         tcgen05_fence_after();
+        if (lane == 0) LT_STAMP(3, j);   // MMA: accumulator buffer free
         const uint32_t d = tmem_base + buf * NT_MAX;
         for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&full[s], ph);
           tcgen05_fence_after();
+          if (kc == 0 && lane == 0) LT_STAMP(4, j);   // MMA: first stage of the unit has landed
           if (elect_one()) {
             const uint32_t ah = s0 + s * stage_bytes, al = ah + A_PART;
             const uint32_t wh = ah + 2 * A_PART, wl = wh + w_mine;
@@ -336,8 +348,10 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       const uint32_t acc_it = (uint32_t)j;
       const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
       const uint32_t buf = acc_it & 1, aph = (acc_it >> 1) & 1;
+      if (ew == 0 && lane == 0) LT_STAMP(5, j);   // epilogue: ready for the unit
       mbar_wait(&acc_full[buf], aph);
       tcgen05_fence_after();
+      if (ew == 0 && lane == 0) LT_STAMP(6, j);   // epilogue: accumulator complete (= the unit's MMAs are done)
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT_MAX;
       const int n0 = pass * a.NT;
       const int row0 = m_tile * M_TILE + q * 32;
@@ -465,13 +479,16 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         scale = 1.f / fmaxf(sqrtf(t), 1e-12f);
       }
       float ss = 0.f;
-      uint32_t va[16], vb[16];
-      if (c_lo < c_hi) tmem_ld16(taddr + c_lo, va);
-      int parity = 0;
-      for (int c = c_lo; c < c_hi; c += 16, parity ^= 1) {
-        tmem_ld_wait();
-        uint32_t(&v)[16] = parity ? vb : va;
-        if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, parity ? va : vb);
+      // row-major destinations of the four 8-row groups this lane stores after the transpose (null: row beyond M)
+      float* cdst[4];
+#pragma unroll
+      for (int it2 = 0; it2 < 4; ++it2) {
+        const int r = it2 * 8 + rsub;
+        cdst[it2] = (a.C != nullptr && row0 + r < M) ? a.C + (size_t)(row0 + r) * a.N + n0 + c4 : nullptr;
+      }
+      const float* stage_rd = stage + rsub * EPI_LD + c4;
+      float* stage_wr = stage + lane * EPI_LD;
+      auto process = [&](const int c, const uint32_t (&v)[16]) {   // one 16-column block of this thread's row
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -489,35 +506,49 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         }
         if (a.out_image && live) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int gg = 0; gg < 2; ++gg) {
             uint4 hi, lo;
-            split2(o[8 * g + 0], o[8 * g + 1], hi.x, lo.x);
-            split2(o[8 * g + 2], o[8 * g + 3], hi.y, lo.y);
-            split2(o[8 * g + 4], o[8 * g + 5], hi.z, lo.z);
-            split2(o[8 * g + 6], o[8 * g + 7], hi.w, lo.w);
-            uint8_t* pimg = a.out_image + image_offset(a.N, grow, n0 + c + 8 * g);
+            split2(o[8 * gg + 0], o[8 * gg + 1], hi.x, lo.x);
+            split2(o[8 * gg + 2], o[8 * gg + 3], hi.y, lo.y);
+            split2(o[8 * gg + 4], o[8 * gg + 5], hi.z, lo.z);
+            split2(o[8 * gg + 6], o[8 * gg + 7], hi.w, lo.w);
+            uint8_t* pimg = a.out_image + image_offset(a.N, grow, n0 + c + 8 * gg);
             *reinterpret_cast<uint4*>(pimg) = hi;
             *reinterpret_cast<uint4*>(pimg + IMG_PART) = lo;
           }
         }
         if (a.C) {
-          float* mine = stage + lane * EPI_LD;
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(mine + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(stage_wr + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           __syncwarp();
 #pragma unroll
           for (int it2 = 0; it2 < 4; ++it2) {
-            const int r = it2 * 8 + rsub;
-            if (row0 + r < M)
-              *reinterpret_cast<float4*>(a.C + (size_t)(row0 + r) * a.N + n0 + c + c4) = *reinterpret_cast<const float4*>(stage + r * EPI_LD + c4);
+            const float4 t = *reinterpret_cast<const float4*>(stage_rd + it2 * 8 * EPI_LD);
+            if (cdst[it2] != nullptr) *reinterpret_cast<float4*>(cdst[it2] + c) = t;
           }
           __syncwarp();
+        }
+      };
+      // two blocks per iteration with fixed register sets (va, vb): written with `parity ? vb : va` the compiler kept the
+      // loop rolled and paid 60 SEL / MOV per block to pick the set - a third of the epilogue's instructions, on a path that
+      // is bound by the latency of one warp's dependent instruction stream (clock64 trace: ~800 cycles per block)
+      uint32_t va[16], vb[16];
+      if (c_lo < c_hi) tmem_ld16(taddr + c_lo, va);
+      for (int c = c_lo; c < c_hi; c += 32) {
+        tmem_ld_wait();
+        if (c + 16 < c_hi) tmem_ld16(taddr + c + 16, vb);
+        process(c, va);
+        if (c + 16 < c_hi) {
+          tmem_ld_wait();
+          if (c + 32 < c_hi) tmem_ld16(taddr + c + 32, va);
+          process(c + 16, vb);
         }
       }
       if (a.ssq_out && live) a.ssq_out[(size_t)grow * (CPARTS * a.passes) + CPARTS * pass + cpart] = ss;
       }
       tcgen05_fence_before();
       __syncwarp();
+      if (ew == 0 && lane == 0) LT_STAMP(7, j);   // epilogue: unit stored
       if (lane == 0) {   // the TMEM reads are complete (wait::ld); nothing is handed over through memory, hence relaxed
         if (leader) mbar_arrive(&acc_empty[buf]);
         else mbar_arrive_cluster_relaxed(buf ? acc_empty_remote1 : acc_empty_remote0);
@@ -679,7 +710,19 @@ static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a
   return linear_tc_plan(N, K1, K2, &a.passes, &a.NT);
 }
 
-static int launch_lin2(const LinArgs2& g, int m_max, cudaStream_t stream) {
+// MESHTOK_LINEAR_TRACE=k: the k-th (mod 7) tcgen05 linear launch of every step records clock64 stamps of its cluster 0
+static long long* g_lin_trace = nullptr;
+static int g_lin_trace_k = -2;
+static long long g_lin_launches = 0;
+
+static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
+  LinArgs2 g = g_in;
+  if (g_lin_trace_k == -2) {
+    const char* e = getenv("MESHTOK_LINEAR_TRACE");
+    g_lin_trace_k = e ? atoi(e) : -1;
+    if (g_lin_trace_k >= 0) { MT_CHECK_CUDA(cudaMalloc(&g_lin_trace, 2 * 8 * 16 * sizeof(long long))); MT_CHECK_CUDA(cudaMemset(g_lin_trace, 0, 2 * 8 * 16 * sizeof(long long))); }
+  }
+  g.trace = (g_lin_trace_k >= 0 && (g_lin_launches++ % 7) == g_lin_trace_k) ? g_lin_trace : nullptr;
   static bool configured = false;
   if (!configured) {
     MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
@@ -736,6 +779,13 @@ int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(g.p[0].passes == 1 && g.p[1].passes == 1, "tcgen05 linear pair of phases: both must be single pass");
   return launch_lin2(g, m_max, stream);
+}
+
+int linear_tc_read_trace(long long* out, int n) {
+  if (g_lin_trace == nullptr) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_lin_trace, sizeof(long long) * (size_t)min(n, 2 * 8 * 16), cudaMemcpyDeviceToHost);
+  return min(n, 2 * 8 * 16);
 }
 
 }  // namespace meshtok
