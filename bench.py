@@ -303,9 +303,11 @@ def main():
     graphed = None
     launches_per_graph = 0
     if not args.no_graph:
+        eager_step()                                                            # first call: also builds the weight images
         l0 = lib.meshtok_kernel_launch_count()
+        eager_step()                                                            # the same call the graph captures
+        launches_per_graph = lib.meshtok_kernel_launch_count() - l0
         graphed = model.graphed(v_dev, f_dev, histogram=None if args.no_hist else step_hist, face_edges=e_dev)
-        launches_per_graph = (lib.meshtok_kernel_launch_count() - l0) // 3      # eager check run + side-stream warm-up + capture
 
     def device_step():
         if graphed is None:
