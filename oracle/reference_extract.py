@@ -18,6 +18,9 @@ not installed and there is no network).  Only these dependency-free helpers can 
     meshgpt_pytorch.py:155-183      get_derived_face_features
     meshgpt_pytorch.py:187-201      discretize
     meshgpt_pytorch.py:243-257      scatter_mean
+and, for the decode groundwork (oracle/decode_oracle.py):
+    meshgpt_pytorch.py:203-218      undiscretize
+    meshgpt_pytorch.py:286-379      PixelNorm, SqueezeExcite, Block, ResnetBlock (classes)
 """
 from __future__ import annotations
 
@@ -31,7 +34,8 @@ _WANTED = {
     "meshgpt_pytorch/data.py": ["derive_face_edges_from_faces"],
     "meshgpt_pytorch/meshgpt_pytorch.py": [
         "exists", "default", "l2norm", "pad_at_dim", "derive_angle",
-        "get_derived_face_features", "discretize", "scatter_mean",
+        "get_derived_face_features", "discretize", "scatter_mean", "undiscretize",
+        "PixelNorm", "SqueezeExcite", "Block", "ResnetBlock",
     ],
 }
 
@@ -57,16 +61,19 @@ def load() -> SimpleNamespace:
     import torch
     import torch.nn.functional as F
     from einops import rearrange, reduce, repeat
-    from torch import einsum
+    from math import sqrt
+    from einops.layers.torch import Rearrange
+    from torch import einsum, nn
     from torch.nn.utils.rnn import pad_sequence
 
     env = dict(torch=torch, F=F, einsum=einsum, rearrange=rearrange, reduce=reduce, repeat=repeat,
-               pad_sequence=pad_sequence, Tensor=torch.Tensor)
+               pad_sequence=pad_sequence, Tensor=torch.Tensor, nn=nn, Module=nn.Module, ModuleList=nn.ModuleList,
+               sqrt=sqrt, Rearrange=Rearrange, Tuple=tuple)
     for rel, names in _WANTED.items():
         path = os.path.join(REFERENCE_ROOT, rel)
         with open(path, "r") as fh:
             tree = ast.parse(fh.read(), filename=path)
-        picked = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+        picked = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
         missing = set(names) - {n.name for n in picked}
         if missing:
             raise RuntimeError(f"{path}: functions not found: {sorted(missing)}")

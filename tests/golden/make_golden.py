@@ -5,6 +5,8 @@
 own_code.pt   outputs of the REFERENCE'S OWN functions (executed from /root/reference source by
               oracle/reference_extract.py) on seeded inputs: derive_face_edges_from_faces,
               get_derived_face_features, discretize, scatter_mean.  These pin the oracle's own-code stages.
+decode_own_code.pt   the same for the decoder building blocks (groundwork for the decode path): PixelNorm, SqueezeExcite,
+              Block, ResnetBlock, undiscretize.
 pipeline_*.pt inputs, a small state dict and the ORACLE's stage-by-stage outputs for small models (LFQ tri,
               RVQ tri, LFQ quad + ragged padding).  The third-party stages inside them (SAGEConv,
               ResidualVQ/LFQ) are restatements - parity unpinned, see oracle/meshtok_oracle.py.
@@ -72,6 +74,35 @@ def own_code():
     torch.save(fix, os.path.join(OUT, "own_code.pt"))
 
 
+def decode_own_code():
+    """Outputs of the reference's OWN decoder building blocks (PixelNorm, SqueezeExcite, Block, ResnetBlock, undiscretize,
+    meshgpt_pytorch.py:203-218, 286-379) on seeded weights and inputs: the pins of oracle/decode_oracle.py."""
+    R = reference_extract.load()
+    g = torch.Generator().manual_seed(11)
+    fix = {}
+    x = torch.randn(3, 16, 37, generator=g)
+    mask = torch.ones(3, 1, 37, dtype=torch.bool)
+    mask[1, :, 20:] = False
+    mask[2, :, 1:] = False
+    fix["x"], fix["mask"] = x, mask
+    fix["pixelnorm"] = R.PixelNorm(dim=1)(x)
+    blocks = {}
+    for name, (din, dout) in dict(same=(16, 16), wider=(16, 24)).items():
+        torch.manual_seed(3)
+        blk = R.ResnetBlock(din, dout).eval()
+        for p_ in blk.parameters():                      # default inits are tiny for the biases: make every term count
+            p_.data = torch.randn(p_.shape, generator=g) * 0.3
+        with torch.no_grad():
+            blocks[name] = dict(dims=(din, dout), state_dict={k: v.clone() for k, v in blk.state_dict().items()},
+                                out_masked=blk(x, mask=mask), out_unmasked=blk(x),
+                                block1=blk.block1(x, mask=mask), excite=blk.excite(blk.block2(blk.block1(x, mask=mask), mask=mask), mask=mask))
+    fix["resnet"] = blocks
+    bins = torch.randint(0, 128, (2, 5, 3, 3), generator=g)
+    fix["undiscretize"] = dict(bins=bins, out=R.undiscretize(bins.clone(), continuous_range=(-1.0, 1.0), num_discrete=128),
+                               out_other=R.undiscretize(bins.clone() % 64, continuous_range=(0.0, 4.0), num_discrete=64))
+    torch.save(fix, os.path.join(OUT, "decode_own_code.pt"))
+
+
 def pipeline(name, cfg, vertices, faces):
     o = helpers.make_oracle(seed=42, **cfg)
     codes, stages = o.forward_codes(vertices=vertices, faces=faces, return_stages=True)
@@ -82,6 +113,7 @@ def pipeline(name, cfg, vertices, faces):
 
 if __name__ == "__main__":
     own_code()
+    decode_own_code()
     v, f = synth.readme_batch(0, batch=2, num_vertices=121, num_faces=64)
     pipeline("lfq_tri", dict(helpers.SMALL_CFG), v, f)
     v, f = synth.grid_batch("tri", 6, 5, [0, 1, 2])
