@@ -432,6 +432,8 @@ def test_dense_user_edges_through_the_aggregation_kernels():
     (dict(SMALL_CFG, num_quantizers=3, codebook_size=512), "tri", (8, 8), [128, 128, 5, 77]),       # LFQ, 3 levels, 9 bits
     (dict(dim_codebook=192, encoder_dims_through_depth=(64, 128), codebook_size=1024, use_residual_lfq=False), "tri", (10, 10), [200, 150]),
     (dict(SMALL_CFG, use_residual_lfq=False), "tri", (45, 20), [1800, 900]),      # meshes too large for a shared-memory slice -> L2 aggregation kernel
+    (dict(SMALL_CFG, num_discrete_coors=100, num_discrete_angle=64, num_discrete_area=32, num_discrete_normals=96), "tri", (8, 8), [128, 77]),   # unequal table sizes
+    (dict(SMALL_CFG, quads=True, num_discrete_coors=72, num_discrete_angle=128, num_discrete_area=16, num_discrete_normals=40), "quad", (6, 7), [42, 30]),
 ])
 def test_config_matrix_end_to_end(cfg, kind, grid, counts):
     """Other constructor configurations end to end against the oracle (token agreement; exact pad positions)."""
