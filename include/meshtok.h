@@ -239,6 +239,39 @@ int meshtok_rows_build_image(const float* A, int M, int K, void* image, meshtok_
 int meshtok_linear(const float* A, const void* a_image, const float* W, const void* w_image, const float* bias,
                    float* C, int M, int N, int K, int relu, int simt, meshtok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Decode path: the stages of MeshAutoencoder.decode_from_codes_to_faces (meshgpt_pytorch.py:898-947) and
+ * decode (:872-896) that are not linears.  Rows are (b, n) for every face slot of the batch, R = B * nf; `valid` (R bytes) is the
+ * face mask.  A Conv1d(k) is meshtok_dec_im2col_image followed by meshtok_linear with the weight re-tiled to (C_out, k * C_in),
+ * tap-major.  The host side (meshgpt_pytorch_b200/decoder.py) strings them together like the reference's decode().
+ * ------------------------------------------------------------------------------------------ */
+/* vector_quantize_pytorch get_output_from_indices as called at :917.  codes (n_tokens, Q) int64, negative = masked. */
+int meshtok_dec_dequantize_rvq(const int64_t* codes, const float* codebook, int n_tokens, int Q, int D, float* out,
+                               meshtok_stream_t stream);
+int meshtok_dec_dequantize_lfq(const int64_t* codes, const float* w_out, const float* b_out, int n_tokens, int Q, int bits,
+                               int D, float* out, meshtok_stream_t stream);
+/* x (R, C) fp32 -> split-bf16 activation image (R, k * C): column t * C + c of row (b, n) = x[(b, n + t - k/2)][c], zero outside the
+ * mesh and on masked faces (the masked_fill + zero padding of Block.forward, :341-349).  Size: meshtok_rows_image_bytes(R, k * C). */
+int meshtok_dec_im2col_image(const float* x, const uint8_t* valid, int R, int nf, int C, int k, void* image,
+                             meshtok_stream_t stream);
+/* Block tail (:345-351): PixelNorm (F.normalize eps, * sqrt(C)) then SiLU on valid rows, zeros elsewhere; in place. */
+int meshtok_dec_pixelnorm_silu(float* x, const uint8_t* valid, int R, int C, float eps, meshtok_stream_t stream);
+/* init_decoder_conv tail (:621-627): SiLU then LayerNorm(gamma, beta, eps); in place. */
+int meshtok_dec_silu_layernorm(float* x, int R, int C, const float* gamma, const float* beta, float eps,
+                               meshtok_stream_t stream);
+/* SqueezeExcite (:296-324): masked mean over the faces of every mesh -> Linear(w1, b1) -> SiLU -> Linear(w2, b2) -> Sigmoid.
+ * mean_ws, gate: (B, C) fp32. */
+int meshtok_dec_squeeze_excite_gate(const float* x, const uint8_t* valid, int B, int nf, int C, int inner, const float* w1,
+                                    const float* b1, const float* w2, const float* b2, float* mean_ws, float* gate,
+                                    meshtok_stream_t stream);
+/* ResnetBlock tail (:378-379): out = h * gate[b] + res on valid rows, zeros elsewhere. */
+int meshtok_dec_gate_residual(const float* h, const float* gate, const float* res, const uint8_t* valid, int R, int nf, int C,
+                              float* out, meshtok_stream_t stream);
+/* :928-942: arg-max over the nbins logits of every coordinate (first maximum) -> undiscretize; masked faces: NaN (bins: 0).
+ * logits (R, ncoord * nbins); coords (R, ncoord) fp32; bins (R, ncoord) int64 or NULL. */
+int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, int ncoord, int nbins, float lo, float hi,
+                              float* coords, int64_t* bins, meshtok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

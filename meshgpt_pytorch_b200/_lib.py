@@ -68,6 +68,16 @@ SIGNATURES = {
     "meshtok_last_error_string": (C.c_char_p, []),
     "meshtok_kernel_launch_count": (C.c_int64, []),
     "meshtok_debug_linear_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    "meshtok_dec_dequantize_rvq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "meshtok_dec_dequantize_lfq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "meshtok_dec_im2col_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "meshtok_dec_pixelnorm_silu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "meshtok_dec_silu_layernorm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "meshtok_dec_squeeze_excite_gate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "meshtok_dec_gate_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "meshtok_dec_argmax_coords": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p,
+                                            C.c_void_p]),
     "meshtok_profile_enable": (C.c_int, [C.c_int]),
     "meshtok_profile_sections": (C.c_int, []),
     "meshtok_profile_section_name": (C.c_char_p, [C.c_int]),

@@ -1,0 +1,326 @@
+// Decode path: the memory-bound stages between the tcgen05 linears of
+// MeshAutoencoder.decode_from_codes_to_faces (meshgpt_pytorch.py:898-947) and decode (:872-896).
+//
+// The decoder is a stack of 1-d convolutions over the face sequence of every mesh.  Rows are UNPACKED here: row = b * nf + n
+// for every face slot of the batch, with a per-row validity flag (a padded face is a zero input to every convolution, exactly
+// like a position beyond the end of the mesh: meshgpt_pytorch.py:341-349 masks before and after each Conv1d).  A Conv1d with
+// kernel k is run as ONE split-bf16 tcgen05 linear (linear_tc.cu) on an im2col activation image: column t * C + c of row n
+// holds x[n + t - k/2][c] (zero outside the mesh / on padded faces), the weight (C_out, C_in, k) is re-tiled at load time to
+// (C_out, k * C_in) in the same tap-major order.  Everything else is here:
+//   dequantize_*      codes -> summed codebook vectors (get_output_from_indices of vector_quantize_pytorch, called at :917)
+//   im2col_image      fp32 rows -> split-bf16 im2col image
+//   pixelnorm_silu    Block: mask, PixelNorm (F.normalize eps 1e-4, * sqrt(C)), SiLU          (:286-294, :345-351)
+//   silu_layernorm    init_decoder_conv tail: SiLU, LayerNorm(eps 1e-5)                       (:621-627)
+//   segment_mean      SqueezeExcite: masked mean over the faces of a mesh                      (:313-319)
+//   se_gate           Linear -> SiLU -> Linear -> Sigmoid on the (B, C) means                  (:304-310)
+//   gate_residual     h * gate[b] + res                                                        (:324, :378-379)
+//   argmax_coords     logits -> arg-max bin per coordinate -> undiscretize, NaN on padded faces (:928-942)
+#include "common.cuh"
+#include "kernels.cuh"
+#include "tc_common.cuh"
+
+namespace meshtok {
+
+namespace {
+
+// codes (R * nvf, Q) int64 -> rows (R, nvf * D): sum over the levels of codebook[code]; a negative code contributes zeros
+__global__ void __launch_bounds__(256) dequantize_rvq_kernel(const int64_t* __restrict__ codes, const float* __restrict__ codebook, int n_tok, int Q,
+                                                             int D, float* __restrict__ out) {
+  const int d4 = D >> 2;
+  const long long total = (long long)n_tok * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long tok = i / d4;
+    const int c = (int)(i % d4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < Q; ++q) {
+      const long long code = codes[tok * Q + q];
+      if (code >= 0) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(codebook + (size_t)code * D) + c);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    reinterpret_cast<float4*>(out + (size_t)tok * D)[c] = acc;
+  }
+}
+
+// LFQ: bits of every level -> +-2^-level, summed over the levels, then project_out (D x bits) + bias; one warp per token
+__global__ void __launch_bounds__(256) dequantize_lfq_kernel(const int64_t* __restrict__ codes, const float* __restrict__ w_out,
+                                                             const float* __restrict__ b_out, int n_tok, int Q, int bits, int D,
+                                                             float* __restrict__ out) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  for (int tok = blockIdx.x * wpb + warp_id(); tok < n_tok; tok += gridDim.x * wpb) {
+    float mine = 0.f;   // lane d keeps dimension d of the summed +-scale vector
+    for (int q = 0; q < Q; ++q) {
+      const long long code = codes[(size_t)tok * Q + q];
+      if (code >= 0 && lane < bits) {
+        const float scale = exp2f(-(float)q);
+        mine += ((code >> (bits - 1 - lane)) & 1) ? scale : -scale;
+      }
+    }
+    for (int c = lane; c < D; c += 32) {
+      float o = b_out[c];
+      for (int dd = 0; dd < bits; ++dd) o = fmaf(__shfl_sync(0xffffffffu, mine, dd), __ldg(w_out + (size_t)c * bits + dd), o);
+      out[(size_t)tok * D + c] = o;
+    }
+  }
+}
+
+// im2col activation image: (R, k * C) with column t * C + c of row (b, n) = x[(b, n + t - k/2)][c], zero when that face is outside
+// the mesh or not valid.  One thread per 4 columns.
+__global__ void __launch_bounds__(256) im2col_image_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, int R, int nf, int C,
+                                                           int k, uint8_t* __restrict__ image) {
+  const int c4 = C >> 2, KC = k * C;
+  const long long total = (long long)R * k * c4;
+  const int half = k >> 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / (k * c4);
+    const int rem = (int)(i % (k * c4));
+    const int t = rem / c4, c = (rem % c4) * 4;
+    const int n = (int)(row % nf);
+    const int nn = n + t - half;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nn >= 0 && nn < nf) {
+      const long long src = row + (t - half);
+      if (valid[src]) v = *reinterpret_cast<const float4*>(x + (size_t)src * C + c);
+    }
+    tc::image_store4(image, KC, row, t * C + c, v);
+  }
+}
+
+// y = silu(F.normalize(x, eps) * sqrt(C)) on valid rows, 0 on the others (in place); one warp per row
+__global__ void __launch_bounds__(256) pixelnorm_silu_kernel(float* __restrict__ x, const uint8_t* __restrict__ valid, int R, int C, float eps) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  const float root_c = sqrtf((float)C);
+  for (int row = blockIdx.x * wpb + warp_id(); row < R; row += gridDim.x * wpb) {
+    float* xr = x + (size_t)row * C;
+    if (!valid[row]) {
+      for (int c = lane; c < C; c += 32) xr[c] = 0.f;
+      continue;
+    }
+    float ss = 0.f;
+    for (int c = lane; c < C; c += 32) ss = fmaf(xr[c], xr[c], ss);
+    ss = warp_sum(ss);
+    const float den = fmaxf(sqrtf(ss), eps);
+    for (int c = lane; c < C; c += 32) {
+      const float t = __fdiv_rn(xr[c], den) * root_c;
+      xr[c] = __fdiv_rn(t, 1.f + expf(-t));
+    }
+  }
+}
+
+// y = LayerNorm(silu(x)) (biased variance, eps) in place; one warp per row
+__global__ void __launch_bounds__(256) silu_layernorm_kernel(float* __restrict__ x, int R, int C, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float eps) {
+  const int lane = lane_id();
+  const int wpb = blockDim.x >> 5;
+  for (int row = blockIdx.x * wpb + warp_id(); row < R; row += gridDim.x * wpb) {
+    float* xr = x + (size_t)row * C;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float t = xr[c];
+      const float s = __fdiv_rn(t, 1.f + expf(-t));
+      xr[c] = s;
+      sum += s;
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = xr[c] - mean; var = fmaf(d, d, var); }
+    var = warp_sum(var) / (float)C;
+    const float rstd = 1.f / sqrtf(var + eps);
+    for (int c = lane; c < C; c += 32) xr[c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+  }
+}
+
+// mean[b][c] = sum over the valid faces of mesh b of x[(b, n)][c] / max(#valid, 1e-5); one CTA per (mesh, 32-column group),
+// rows summed in ascending order by every thread group, combined in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) segment_mean_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, int nf, int C,
+                                                           float* __restrict__ mean) {
+  __shared__ float part[8][32];
+  __shared__ int cnt[8];
+  const int b = blockIdx.x, c = blockIdx.y * 32 + (threadIdx.x & 31), g = threadIdx.x >> 5;
+  float acc = 0.f;
+  int n_valid = 0;
+  for (int n = g; n < nf; n += 8) {
+    const long long row = (long long)b * nf + n;
+    if (valid[row]) {
+      ++n_valid;
+      if (c < C) acc += x[(size_t)row * C + c];
+    }
+  }
+  part[g][threadIdx.x & 31] = acc;
+  if ((threadIdx.x & 31) == 0) cnt[g] = n_valid;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float t = 0.f;
+    int nv = 0;
+    for (int i = 0; i < 8; ++i) { t += part[i][threadIdx.x & 31]; nv += cnt[i]; }
+    mean[(size_t)b * C + c] = t / fmaxf((float)nv, 1e-5f);
+  }
+}
+
+// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2); one CTA per mesh (C <= 1024, inner <= 256)
+__global__ void __launch_bounds__(256) se_gate_kernel(const float* __restrict__ mean, int C, int inner, const float* __restrict__ w1,
+                                                      const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+                                                      float* __restrict__ gate) {
+  __shared__ float sm[1024];
+  __shared__ float sh[256];
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) sm[c] = mean[(size_t)b * C + c];
+  __syncthreads();
+  for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+    float t = b1[j];
+    for (int c = 0; c < C; ++c) t = fmaf(w1[(size_t)j * C + c], sm[c], t);
+    sh[j] = __fdiv_rn(t, 1.f + expf(-t));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = b2[c];
+    for (int j = 0; j < inner; ++j) t = fmaf(w2[(size_t)c * inner + j], sh[j], t);
+    gate[(size_t)b * C + c] = 1.f / (1.f + expf(-t));
+  }
+}
+
+// out = h * gate[b] + res on valid rows, 0 elsewhere
+__global__ void __launch_bounds__(256) gate_residual_kernel(const float* __restrict__ h, const float* __restrict__ gate, const float* __restrict__ res,
+                                                            const uint8_t* __restrict__ valid, int R, int nf, int C, float* __restrict__ out) {
+  const int c4 = C >> 2;
+  const long long total = (long long)R * c4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / c4;
+    const int c = (int)(i % c4);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid[row]) {
+      const float4 hv = reinterpret_cast<const float4*>(h + (size_t)row * C)[c];
+      const float4 gv = reinterpret_cast<const float4*>(gate + (size_t)(row / nf) * C)[c];
+      const float4 rv = reinterpret_cast<const float4*>(res + (size_t)row * C)[c];
+      o = make_float4(fmaf(hv.x, gv.x, rv.x), fmaf(hv.y, gv.y, rv.y), fmaf(hv.z, gv.z, rv.z), fmaf(hv.w, gv.w, rv.w));
+    }
+    reinterpret_cast<float4*>(out + (size_t)row * C)[c] = o;
+  }
+}
+
+// logits (R, ncoord * nbins) -> arg-max bin per coordinate (first maximum, like torch.argmax) -> bin centre; padded faces: NaN / -1.
+// One warp per (row, coordinate).
+__global__ void __launch_bounds__(256) argmax_coords_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ valid, int R, int ncoord,
+                                                            int nbins, float lo, float hi, float* __restrict__ coords, int64_t* __restrict__ bins) {
+  const int lane = lane_id();
+  const long long total = (long long)R * ncoord;
+  const int wpb = blockDim.x >> 5;
+  for (long long item = (long long)blockIdx.x * wpb + warp_id(); item < total; item += (long long)gridDim.x * wpb) {
+    const long long row = item / ncoord;
+    if (!valid[row]) {
+      if (lane == 0) { coords[item] = __int_as_float(0x7fc00000); if (bins) bins[item] = 0; }
+      continue;
+    }
+    const float* lr = logits + item * nbins;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < nbins; j += 32) {
+      const float v = lr[j];
+      if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;   // a row of NaN logits
+      // undiscretize (meshgpt_pytorch.py:203-218): ((bin + 0.5) / nbins) * (hi - lo) + lo, in that order
+      float t = (float)bi;
+      t = __fadd_rn(t, 0.5f);
+      t = __fdiv_rn(t, (float)nbins);
+      coords[item] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+      if (bins) bins[item] = bi;
+    }
+  }
+}
+
+inline unsigned grid_for(long long items, int per_block) {
+  const long long want = (items + per_block - 1) / per_block;
+  return (unsigned)(want < 1 ? 1 : (want > 148ll * 16 ? 148ll * 16 : want));
+}
+
+}  // namespace
+}  // namespace meshtok
+
+using namespace meshtok;
+
+extern "C" {
+
+int meshtok_dec_dequantize_rvq(const int64_t* codes, const float* codebook, int n_tokens, int Q, int D, float* out, meshtok_stream_t stream) {
+  MT_CHECK_ARG(codes && codebook && out && n_tokens >= 0 && Q >= 1 && D % 4 == 0, "dequantize: bad arguments");
+  if (n_tokens == 0) return MESHTOK_OK;
+  dequantize_rvq_kernel<<<grid_for((long long)n_tokens * (D / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, codebook, n_tokens, Q, D, out);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_dequantize_lfq(const int64_t* codes, const float* w_out, const float* b_out, int n_tokens, int Q, int bits, int D, float* out,
+                               meshtok_stream_t stream) {
+  MT_CHECK_ARG(codes && w_out && b_out && out && n_tokens >= 0 && Q >= 1 && bits >= 1 && bits <= 32, "dequantize: bad arguments");
+  if (n_tokens == 0) return MESHTOK_OK;
+  dequantize_lfq_kernel<<<grid_for(n_tokens, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, w_out, b_out, n_tokens, Q, bits, D, out);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_im2col_image(const float* x, const uint8_t* valid, int R, int nf, int C, int k, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && image && R >= 0 && nf >= 1 && C % 4 == 0 && (k & 1) == 1 && (k * C) % tc::IMG_KC == 0,
+               "im2col: width %d x kernel %d must be a multiple of %d, kernel odd", C, k, tc::IMG_KC);
+  if (R == 0) return MESHTOK_OK;
+  im2col_image_kernel<<<grid_for((long long)R * k * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, valid, R, nf, C, k, static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_pixelnorm_silu(float* x, const uint8_t* valid, int R, int C, float eps, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && R >= 0 && C >= 1, "pixelnorm: bad arguments");
+  if (R == 0) return MESHTOK_OK;
+  pixelnorm_silu_kernel<<<grid_for(R, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, valid, R, C, eps);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_silu_layernorm(float* x, int R, int C, const float* gamma, const float* beta, float eps, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && gamma && beta && R >= 0 && C >= 1, "layernorm: bad arguments");
+  if (R == 0) return MESHTOK_OK;
+  silu_layernorm_kernel<<<grid_for(R, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, R, C, gamma, beta, eps);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_squeeze_excite_gate(const float* x, const uint8_t* valid, int B, int nf, int C, int inner, const float* w1, const float* b1,
+                                    const float* w2, const float* b2, float* mean_ws, float* gate, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && w1 && b1 && w2 && b2 && mean_ws && gate && C <= 1024 && inner <= 256, "squeeze-excite: bad arguments (C <= 1024, inner <= 256)");
+  if (B == 0) return MESHTOK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  segment_mean_kernel<<<dim3(B, (C + 31) / 32), 256, 0, s>>>(x, valid, nf, C, mean_ws);
+  MT_CHECK_LAUNCH();
+  se_gate_kernel<<<B, 256, 0, s>>>(mean_ws, C, inner, w1, b1, w2, b2, gate);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_gate_residual(const float* h, const float* gate, const float* res, const uint8_t* valid, int R, int nf, int C, float* out,
+                              meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && gate && res && valid && out && C % 4 == 0, "gate_residual: bad arguments");
+  if (R == 0) return MESHTOK_OK;
+  gate_residual_kernel<<<grid_for((long long)R * (C / 4), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, gate, res, valid, R, nf, C, out);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, int ncoord, int nbins, float lo, float hi, float* coords,
+                              int64_t* bins, meshtok_stream_t stream) {
+  MT_CHECK_ARG(logits && valid && coords && ncoord >= 1 && nbins >= 1, "argmax_coords: bad arguments");
+  if (R == 0) return MESHTOK_OK;
+  argmax_coords_kernel<<<grid_for((long long)R * ncoord, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, R, ncoord, nbins, lo, hi, coords, bins);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+}  // extern "C"

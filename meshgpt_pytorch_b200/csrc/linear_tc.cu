@@ -42,7 +42,7 @@ constexpr int NT_MAX = 256;
 constexpr uint32_t SBO = (KC / 8) * 128;                   // 512
 constexpr uint32_t A_PART = IMG_PART;                      // 8 KB (hi or lo)
 constexpr int EPI_LD = 20;                                 // padded row length (floats) of the 32 x 16 epilogue staging tiles
-constexpr int VEC_MAX_N = 1024;
+constexpr int VEC_MAX_N = 1536;   // widest output (the decoder's 9 x 128 coordinate logits = 1152)
 
 // PAIR = two CTAs of a cluster work on one 256-row tile with tcgen05.mma.cta_group::2: every CTA stages its own 128 rows
 // of A and HALF of the W chunk, so the bytes pulled from L2 per MMA cycle drop from (128 + NT) to (128 + NT / 2) rows.
@@ -628,9 +628,11 @@ int linear_tc_plan(int N, int K1, int K2, int* passes, int* NT) {
     set_error("tcgen05 linear: input widths must be multiples of %d (got %d, %d); use the SIMT path", KC, K1, K2);
     return MESHTOK_ERR_UNSUPPORTED;
   }
-  const int p = ceil_div(N, NT_MAX);
-  if (N % p != 0 || (N / p) % 16 != 0) {
-    set_error("tcgen05 linear: output width %d does not split into %d passes of a multiple of 16 columns; use the SIMT path", N, p);
+  // fewest passes of equal width (a multiple of 16, at most NT_MAX columns)
+  int p = ceil_div(N, NT_MAX);
+  while (p <= N / 16 && (N % p != 0 || (N / p) % 16 != 0)) ++p;
+  if (p > N / 16 || N % p != 0 || (N / p) % 16 != 0) {
+    set_error("tcgen05 linear: output width %d does not split into passes of a multiple of 16 columns; use the SIMT path", N);
     return MESHTOK_ERR_UNSUPPORTED;
   }
   *passes = p;
@@ -654,7 +656,11 @@ static bool linear_tc_pair() {
   return pair == 1;
 }
 
-int linear_tc_ssq_parts(int N) { return 2 * ceil_div(N, NT_MAX); }
+int linear_tc_ssq_parts(int N) {
+  int passes = 0, NT = 0;
+  if (linear_tc_plan(N, KC, 0, &passes, &NT) != MESHTOK_OK) return 1 << 20;   // not a tcgen05 shape: no deferred normalisation
+  return 2 * passes;
+}
 
 size_t linear_tc_image_bytes(int N, int K) { return (size_t)N * K * 4; }
 

@@ -1,0 +1,219 @@
+"""Decode half of MeshAutoencoder on the B200: codes -> face coordinates.
+
+Mirrors the reference's `MeshAutoencoder.decode_from_codes_to_faces` (meshgpt_pytorch.py:898-947) and `decode` (:872-896,
+attn_decoder_depth == 0) with the decoder modules under their reference names (init_decoder_conv.{0,3}, decoders.{i}.
+block{1,2}.proj, .excite.net.{0,2}, .residual_conv, to_coor_logits.0), so a reference state dict loads key for key.
+Every Conv1d / Linear runs as a split-bf16 tcgen05 linear (csrc/linear_tc.cu) on an im2col activation image; the stages in
+between are the kernels of csrc/decode.cu, all called through the C ABI (include/meshtok.h, meshtok_dec_*).  PyTorch holds the
+device buffers and nothing else; there is no CPU path.
+
+    dec = MeshDecoder(autoencoder)                    # same decoder keywords as the reference constructor
+    dec.load_reference_state_dict(reference.state_dict())
+    coords, face_mask = dec.cuda().decode_from_codes_to_faces(codes)      # (b, nf, nvf, 3) fp32, NaN on padded faces
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+
+class _Block(nn.Module):                      # meshgpt_pytorch.py:326-353 (parameters only)
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.proj = nn.Conv1d(dim, dim_out, 3, padding=1)
+
+
+class _Excite(nn.Module):                     # :296-324
+    def __init__(self, dim, reduction_factor=4, min_dim=16):
+        super().__init__()
+        inner = max(dim // reduction_factor, min_dim)
+        self.net = nn.Sequential(nn.Linear(dim, inner), nn.SiLU(), nn.Linear(inner, dim), nn.Sigmoid())
+
+
+class _ResnetBlock(nn.Module):                # :355-379
+    def __init__(self, dim, dim_out):
+        super().__init__()
+        self.block1 = _Block(dim, dim_out)
+        self.block2 = _Block(dim_out, dim_out)
+        self.excite = _Excite(dim_out)
+        self.residual_conv = nn.Conv1d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+
+
+class MeshDecoder(nn.Module):
+    def __init__(self, autoencoder, init_decoder_conv_kernel: int = 7,
+                 decoder_dims_through_depth: Tuple[int, ...] = (128, 128, 128, 128, 192, 192, 192, 192, 256, 256, 256, 256, 256, 256, 384, 384, 384),
+                 attn_decoder_depth: int = 0):
+        super().__init__()
+        if attn_decoder_depth != 0:
+            raise NotImplementedError("attn_decoder_depth > 0 is out of scope for the B200 decode path")
+        if init_decoder_conv_kernel % 2 != 1:
+            raise ValueError("init_decoder_conv_kernel must be odd")
+        object.__setattr__(self, "autoencoder", autoencoder)      # not a sub-module: its keys are not this module's
+        a = autoencoder
+        self.nvf, self.dim_codebook = a.num_vertices_per_face, a.dim_codebook
+        self.num_quantizers, self.codebook_size, self.pad_id = a.num_quantizers, a.codebook_size, a.pad_id
+        self.num_discrete_coors, self.coor_range = a.num_discrete_coors, a.coor_continuous_range
+        init_dim, *rest = decoder_dims_through_depth
+        self.init_decoder_conv = nn.ModuleDict({
+            "0": nn.Conv1d(self.dim_codebook * self.nvf, init_dim, init_decoder_conv_kernel, padding=init_decoder_conv_kernel // 2),
+            "3": nn.LayerNorm(init_dim)})
+        self.decoders = nn.ModuleList()
+        cur = init_dim
+        for d in rest:
+            self.decoders.append(_ResnetBlock(cur, d))
+            cur = d
+        self.to_coor_logits = nn.ModuleDict({"0": nn.Linear(cur, self.num_discrete_coors * self.nvf * 3)})
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._prep = None
+        self._prep_key = None
+
+    def load_reference_state_dict(self, state_dict: Dict[str, Tensor]):
+        own = self.state_dict()
+        missing = [k for k in own if k not in state_dict]
+        if missing:
+            raise KeyError(f"state dict lacks decoder keys: {missing[:8]}{'...' if len(missing) > 8 else ''}")
+        self.load_state_dict({k: state_dict[k] for k in own}, strict=True)
+        self._prep = None
+
+    # ---- weights -> images ------------------------------------------------------------------------
+    def _prepare(self):
+        key = tuple((t.data_ptr(), t._version) for t in self.parameters())
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        dev = self.to_coor_logits["0"].weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("MeshDecoder must live on a CUDA device (call .cuda()); there is no CPU path")
+        f32 = dict(dtype=torch.float32, device=dev)
+
+        def conv(cv: nn.Conv1d):
+            w = cv.weight.detach().to(**f32)                       # (co, ci, k)
+            co, ci, k = w.shape
+            mat = w.permute(0, 2, 1).reshape(co, k * ci).contiguous()   # tap-major columns: t * ci + c, like the im2col image
+            nbytes = C.c_size_t()
+            check(lib.meshtok_linear_image_bytes(co, k * ci, C.byref(nbytes)))
+            img = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            check(lib.meshtok_linear_build_image(ptr(mat), co, k * ci, ptr(img), stream_ptr()))
+            return dict(img=img, bias=cv.bias.detach().to(**f32).contiguous(), n=co, c=ci, k=k, mat=mat)
+
+        def _as_conv(l: nn.Linear):
+            cv = nn.Conv1d(l.in_features, l.out_features, 1)
+            cv.weight.data = l.weight.detach()[:, :, None]
+            cv.bias.data = l.bias.detach()
+            return cv.to(dev)
+
+        with torch.cuda.device(dev):
+            prep = dict(init=conv(self.init_decoder_conv["0"]),
+                        ln=(self.init_decoder_conv["3"].weight.detach().to(**f32).contiguous(), self.init_decoder_conv["3"].bias.detach().to(**f32).contiguous()),
+                        blocks=[], logits=conv(_as_conv(self.to_coor_logits["0"])))
+            for blk in self.decoders:
+                e = blk.excite.net
+                prep["blocks"].append(dict(
+                    c1=conv(blk.block1.proj), c2=conv(blk.block2.proj),
+                    res=None if isinstance(blk.residual_conv, nn.Identity) else conv(blk.residual_conv),
+                    se=tuple(t.detach().to(**f32).contiguous() for t in (e[0].weight, e[0].bias, e[2].weight, e[2].bias))))
+        self._prep, self._prep_key = prep, key
+        return prep
+
+    # ---- stages -----------------------------------------------------------------------------------
+    @staticmethod
+    def _conv(x: Tensor, valid: Tensor, nf: int, w: dict) -> Tensor:
+        """Conv1d over the face sequence as im2col image + tcgen05 linear.  x (R, C) fp32 -> (R, n) fp32."""
+        R, Cc = x.shape
+        assert Cc == w["c"]
+        K = w["k"] * Cc
+        nbytes = C.c_size_t()
+        check(lib.meshtok_rows_image_bytes(R, K, C.byref(nbytes)))
+        img = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
+        check(lib.meshtok_dec_im2col_image(ptr(x), ptr(valid), R, nf, Cc, w["k"], ptr(img), stream_ptr()))
+        out = torch.empty(R, w["n"], dtype=torch.float32, device=x.device)
+        check(lib.meshtok_linear(None, ptr(img), None, ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], K, 0, 0, stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def dequantize(self, codes: Tensor) -> Tensor:
+        """get_output_from_indices of the quantizer (:917): codes (b, n, Q) int64 -> (b, n, dim_codebook) fp32."""
+        a = self.autoencoder
+        b, n, q = codes.shape
+        codes = codes.contiguous().long()
+        out = torch.empty(b, n, self.dim_codebook, dtype=torch.float32, device=codes.device)
+        if a.use_residual_lfq:
+            bits = int(round(math.log2(self.codebook_size)))
+            w = a.quantizer.project_out.weight.detach().float().contiguous()
+            bias = a.quantizer.project_out.bias.detach().float().contiguous()
+            check(lib.meshtok_dec_dequantize_lfq(ptr(codes), ptr(w), ptr(bias), b * n, q, bits, self.dim_codebook, ptr(out), stream_ptr()))
+        else:
+            book = a.quantizer.layers[0]._codebook.embed[0].detach().float().contiguous()
+            check(lib.meshtok_dec_dequantize_rvq(ptr(codes), ptr(book), b * n, q, self.dim_codebook, ptr(out), stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def decode(self, quantized: Tensor, face_mask: Tensor) -> Tensor:
+        """quantized (b, nf, nvf * dim_codebook) fp32, face_mask (b, nf) bool -> (b, nf, last decoder dim); rows of padded faces are 0."""
+        p = self._prepare()
+        b, nf, d = quantized.shape
+        R = b * nf
+        dev = quantized.device
+        valid = face_mask.reshape(R).to(torch.uint8).contiguous()
+        x = quantized.reshape(R, d).float().contiguous()
+        with torch.cuda.device(dev):
+            x = self._conv(x, valid, nf, p["init"])
+            check(lib.meshtok_dec_silu_layernorm(ptr(x), R, x.shape[1], ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, stream_ptr()))
+            for blk in p["blocks"]:
+                cout = blk["c1"]["n"]
+                if blk["res"] is None:
+                    res = x
+                else:
+                    res = self._conv(x, valid, nf, blk["res"])
+                h = self._conv(x, valid, nf, blk["c1"])
+                check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
+                h = self._conv(h, valid, nf, blk["c2"])
+                check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
+                w1, b1, w2, b2 = blk["se"]
+                mean = torch.empty(b, cout, dtype=torch.float32, device=dev)
+                gate = torch.empty(b, cout, dtype=torch.float32, device=dev)
+                check(lib.meshtok_dec_squeeze_excite_gate(ptr(h), ptr(valid), b, nf, cout, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                                          ptr(mean), ptr(gate), stream_ptr()))
+                out = torch.empty(R, cout, dtype=torch.float32, device=dev)
+                check(lib.meshtok_dec_gate_residual(ptr(h), ptr(gate), ptr(res), ptr(valid), R, nf, cout, ptr(out), stream_ptr()))
+                x = out
+        return x.reshape(b, nf, -1)
+
+    @torch.no_grad()
+    def decode_from_codes_to_faces(self, codes: Tensor, face_mask: Optional[Tensor] = None, return_discrete_codes: bool = False):
+        """Same contract as the reference (:898-947): codes (b, nf * nvf, Q) or any (b, ...) layout of them, int64, pad_id on padded
+        faces -> (continuous face coordinates (b, nf, nvf, 3) with NaN on padded faces[, discrete bins], face_mask)."""
+        if not codes.is_cuda:
+            raise RuntimeError("codes must be a CUDA tensor; there is no CPU path")
+        p = self._prepare()
+        b = codes.shape[0]
+        codes = codes.reshape(b, -1)
+        nvf, q = self.nvf, self.num_quantizers
+        if face_mask is None:
+            face_mask = (codes != self.pad_id).reshape(b, -1, nvf * q).all(dim=-1)
+        codes = codes.reshape(b, -1, q)
+        quantized = self.dequantize(codes).reshape(b, -1, nvf * self.dim_codebook)
+        nf = quantized.shape[1]
+        R = b * nf
+        decoded = self.decode(quantized, face_mask)            # rows of padded faces are already zero (:924)
+        valid = face_mask.reshape(R).to(torch.uint8).contiguous()
+        dev = codes.device
+        with torch.cuda.device(dev):
+            ones = torch.ones(R, dtype=torch.uint8, device=dev)        # to_coor_logits is a plain Linear: no neighbours, no mask
+            logits = self._conv(decoded.reshape(R, -1).contiguous(), ones, nf, p["logits"])
+            ncoord = nvf * 3
+            coords = torch.empty(b, nf, nvf, 3, dtype=torch.float32, device=dev)
+            bins = torch.empty(b, nf, nvf, 3, dtype=torch.int64, device=dev)
+            lo, hi = self.coor_range
+            check(lib.meshtok_dec_argmax_coords(ptr(logits), ptr(valid), R, ncoord, self.num_discrete_coors, float(lo), float(hi),
+                                                ptr(coords), ptr(bins), stream_ptr()))
+        if return_discrete_codes:
+            return coords, bins, face_mask
+        return coords, face_mask
