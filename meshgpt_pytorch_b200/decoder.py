@@ -217,3 +217,29 @@ class MeshDecoder(nn.Module):
         if return_discrete_codes:
             return coords, bins, face_mask
         return coords, face_mask
+
+    def graphed(self, codes: Tensor) -> "GraphedDecoder":
+        """decode_from_codes_to_faces for one codes shape as a CUDA graph (the ~160 launches of the decoder stack replayed at once)."""
+        return GraphedDecoder(self, codes)
+
+
+class GraphedDecoder:
+    """Static input / output buffers + the captured graph.  Call it with new codes of the captured shape."""
+
+    def __init__(self, decoder: MeshDecoder, codes: Tensor):
+        self.codes = codes.clone()
+        decoder.decode_from_codes_to_faces(self.codes)                 # eager: weight images, shared-memory attributes
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            decoder.decode_from_codes_to_faces(self.codes)
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.coords, self.bins, self.face_mask = decoder.decode_from_codes_to_faces(self.codes, return_discrete_codes=True)
+
+    def __call__(self, codes: Optional[Tensor] = None):
+        if codes is not None:
+            self.codes.copy_(codes, non_blocking=True)
+        self.graph.replay()
+        return self.coords, self.face_mask
