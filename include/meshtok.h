@@ -272,6 +272,35 @@ int meshtok_dec_gate_residual(const float* h, const float* gate, const float* re
 int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, int ncoord, int nbins, float lo, float hi,
                               float* coords, int64_t* bins, meshtok_stream_t stream);
 
+/* ---- fused decode stages: every producer writes the im2col image of the convolution that follows it, so no activation makes a
+ * separate fp32 -> image pass.  All need widths that are multiples of 32 (the image chunk); `ld` / `ldh` / `ldres` are row strides in
+ * floats (a linear that computes block1.proj and residual_conv in one launch leaves both side by side in one (R, 2 C) buffer). ---- */
+/* number of face slices per mesh the SqueezeExcite partial sums use; slice_ws holds B * S * C floats + B * S int32 */
+int meshtok_dec_se_slices(int B, int nf);
+/* x (R, C) fp32 -> image (R, k * C), like meshtok_dec_im2col_image but 16-byte stores, a warp per 8-row group */
+int meshtok_dec_rows_im2col(const float* x, int ld, const uint8_t* valid, int R, int nf, int C, int k, void* image,
+                            meshtok_stream_t stream);
+/* get_output_from_indices (:917) + masked_fill (:924) + the image of init_decoder_conv.0 (:621): codes (R * nvf, Q) -> image
+ * (R, k * nvf * D); the summed codebook vectors are never stored as fp32 */
+int meshtok_dec_dequantize_rvq_im2col(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int nf, int nvf,
+                                      int Q, int D, int k, void* image, meshtok_stream_t stream);
+/* init_decoder_conv tail (:621-627) -> out (R, C) fp32 (the first residual input) + image (R, k * C) (NULL: none); masked faces 0 */
+int meshtok_dec_silu_layernorm_im2col(const float* x, const uint8_t* valid, int R, int nf, int C, const float* gamma,
+                                      const float* beta, float eps, float* out, int k, void* image, meshtok_stream_t stream);
+/* Block tail (:345-351) written only as the image of the next convolution; h is not modified */
+int meshtok_dec_pixelnorm_silu_im2col(const float* h, int ld, const uint8_t* valid, int R, int nf, int C, float eps, int k,
+                                      void* image, meshtok_stream_t stream);
+/* second Block tail + SqueezeExcite (:296-324) without storing the activation: den (R) = max(||h[row]||, eps) and gate (B, C) from the
+ * masked mean of silu(PixelNorm(h)); slice sums are combined in a fixed order (deterministic) */
+int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int nf, int C, float eps,
+                                              int inner, const float* w1, const float* b1, const float* w2, const float* b2,
+                                              float* den, float* slice_ws, float* gate, meshtok_stream_t stream);
+/* ResnetBlock tail (:378-379): out = silu(h / den * sqrt(C)) * gate[b] + res (den NULL: h * gate[b] + res) -> out (R, C) fp32 and,
+ * image != NULL, the image (R, k * C) of the next convolution; masked faces 0 */
+int meshtok_dec_gate_residual_im2col(const float* h, int ldh, const float* den, const float* gate, const float* res, int ldres,
+                                     const uint8_t* valid, int R, int nf, int C, float* out, int k, void* image,
+                                     meshtok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -239,6 +239,328 @@ __global__ void __launch_bounds__(256) argmax_coords_kernel(const float* __restr
   }
 }
 
+
+// ---- fused stages: every producer writes the next convolution's im2col image itself ------------------------------------
+// Thread layout of the kernels below ("8 x 4"): a warp owns one aligned group of 8 rows, lane = colsub * 8 + rowsub
+// (rowsub = lane & 7 the row of the group, colsub = lane >> 3), and walks the row in steps of 32 columns, 8 adjacent columns
+// per lane.  A warp-wide image store is then 512 contiguous bytes of hi and 512 of lo (the 8 rows x 32 columns block of the
+// canonical layout), a warp-wide fp32 load is 8 rows x 128 contiguous bytes, and a row reduction is two shuffles (xor 8, 16).
+// Needs C % 32 == 0.
+struct Lane84 {
+  long long row;   // global row (b * nf + n); may be >= R in the last group
+  int n;           // face slot inside its mesh
+  int b;           // mesh
+  int colsub;
+  bool active;     // row < R
+};
+__device__ __forceinline__ Lane84 lane84(long long group, int R, int nf) {
+  Lane84 l;
+  const int lane = lane_id();
+  l.row = group * 8 + (lane & 7);
+  l.colsub = lane >> 3;
+  l.active = l.row < R;
+  l.b = (int)(l.row / nf);
+  l.n = (int)(l.row - (long long)l.b * nf);
+  return l;
+}
+__device__ __forceinline__ float row_sum84(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  return v;
+}
+__device__ __forceinline__ void image_store8(uint8_t* img, int K, long long row, int col, const uint4& hi, const uint4& lo) {
+  uint8_t* p = img + tc::image_offset(K, row, col);
+  *reinterpret_cast<uint4*>(p) = hi;
+  *reinterpret_cast<uint4*>(p + tc::IMG_PART) = lo;
+}
+// 8 adjacent values v[0..8) of (row, columns col .. col+7) of a (R, C) activation -> the k cells of the im2col image (R, k * C) they
+// feed: cell (row + half - t, tap t) for every tap whose target face is inside the mesh.  The cells of THIS row whose source face
+// lies outside the mesh (the zero padding of Conv1d) are written here too, so every cell of the image is written exactly once.
+// v must already be zero for a masked face.
+__device__ __forceinline__ void emit_taps(uint8_t* img, int C, int k, long long row, int n, int nf, int col, const float (&v)[8]) {
+  uint4 hi, lo;
+  tc::split2(v[0], v[1], hi.x, lo.x);
+  tc::split2(v[2], v[3], hi.y, lo.y);
+  tc::split2(v[4], v[5], hi.z, lo.z);
+  tc::split2(v[6], v[7], hi.w, lo.w);
+  const int KC = k * C, half = k >> 1;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (int t = 0; t < k; ++t) {
+    const int target_n = n + half - t;
+    if (target_n >= 0 && target_n < nf) image_store8(img, KC, row + (half - t), t * C + col, hi, lo);
+    const int source_n = n + t - half;
+    if (source_n < 0 || source_n >= nf) image_store8(img, KC, row, t * C + col, zero, zero);
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ float silu_rn(float t) { return __fdiv_rn(t, 1.f + expf(-t)); }
+
+// x (R, C; row stride ld) fp32 -> im2col image, zero on masked faces
+__global__ void __launch_bounds__(256) rows_im2col_kernel(const float* __restrict__ x, int ld, const uint8_t* __restrict__ valid, int R, int nf,
+                                                          int C, int k, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3;
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, nf);
+    if (!l.active) continue;
+    const bool ok = valid[l.row] != 0;
+    for (int col = l.colsub * 8; col < C; col += 32) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) load8(x + (size_t)l.row * ld + col, v);
+      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+    }
+  }
+}
+
+// codes (R * nvf, Q) -> summed codebook rows (R, nvf * D) -> im2col image of the first convolution; never stored as fp32
+__global__ void __launch_bounds__(256) dequantize_rvq_im2col_kernel(const int64_t* __restrict__ codes, const float* __restrict__ codebook,
+                                                                    const uint8_t* __restrict__ valid, int R, int nf, int nvf, int Q, int D, int k,
+                                                                    uint8_t* __restrict__ image) {
+  const int C = nvf * D;
+  const long long groups = ((long long)R + 7) >> 3;
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, nf);
+    if (!l.active) continue;
+    const bool ok = valid[l.row] != 0;
+    for (int col = l.colsub * 8; col < C; col += 32) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        const int slot = col / D, d = col - slot * D;
+        const long long tok = l.row * nvf + slot;
+        for (int q = 0; q < Q; ++q) {
+          const long long code = codes[tok * Q + q];
+          if (code >= 0) {
+            float w[8];
+            load8(codebook + (size_t)code * D + d, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+          }
+        }
+      }
+      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+    }
+  }
+}
+
+// init_decoder_conv tail + the first block's image: y = LayerNorm(silu(x)) -> out (fp32, the residual input) and im2col image.
+// Masked faces: zeros in both.
+__global__ void __launch_bounds__(256) silu_layernorm_im2col_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, int R, int nf, int C,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                    float* __restrict__ out, int k, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3;
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, nf);
+    const bool ok = l.active && valid[l.row] != 0;
+    const float* xr = x + (size_t)(l.active ? l.row : 0) * C;
+    float sum = 0.f;
+    if (ok)
+      for (int col = l.colsub * 8; col < C; col += 32) {
+        float v[8];
+        load8(xr + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sum += silu_rn(v[i]);
+      }
+    const float mean = row_sum84(sum) / (float)C;
+    float var = 0.f;
+    if (ok)
+      for (int col = l.colsub * 8; col < C; col += 32) {
+        float v[8];
+        load8(xr + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float d = silu_rn(v[i]) - mean; var = fmaf(d, d, var); }
+      }
+    var = row_sum84(var) / (float)C;
+    const float rstd = 1.f / sqrtf(var + eps);
+    if (!l.active) continue;
+    for (int col = l.colsub * 8; col < C; col += 32) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        float gm[8], bt[8];
+        load8(xr + col, v);
+        load8(gamma + col, gm);
+        load8(beta + col, bt);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (silu_rn(v[i]) - mean) * rstd * gm[i] + bt[i];
+      }
+      store8(out + (size_t)l.row * C + col, v);
+      if (image) emit_taps(image, C, k, l.row, l.n, nf, col, v);
+    }
+  }
+}
+
+// Block tail feeding the next convolution: silu(PixelNorm(h)) written ONLY as the im2col image (h: row stride ld, left untouched)
+__global__ void __launch_bounds__(256) pixelnorm_silu_im2col_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int R, int nf,
+                                                                    int C, float eps, int k, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3;
+  const float root_c = sqrtf((float)C);
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, nf);
+    const bool ok = l.active && valid[l.row] != 0;
+    const float* hr = h + (size_t)(l.active ? l.row : 0) * ld;
+    float ss = 0.f;
+    if (ok)
+      for (int col = l.colsub * 8; col < C; col += 32) {
+        float v[8];
+        load8(hr + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
+      }
+    const float den = fmaxf(sqrtf(row_sum84(ss)), eps);
+    if (!l.active) continue;
+    for (int col = l.colsub * 8; col < C; col += 32) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        load8(hr + col, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = silu_rn(__fdiv_rn(v[i], den) * root_c);
+      }
+      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+    }
+  }
+}
+
+// Second Block tail + SqueezeExcite's mean, without storing the activation: den[row] = max(||h[row]||, eps) and, per
+// (mesh, slice of its faces), the column sums of silu(PixelNorm(h)) over the valid faces of the slice.  CTA (mesh, slice); a warp
+// per face, lane owns columns lane * 4 + 128 j; rows are added in ascending order per warp and the 8 warps are combined in a fixed
+// order, so the result does not depend on scheduling.
+constexpr int SE_MAX_C = 1024;
+__global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int nf, int C,
+                                                               float eps, int S, float* __restrict__ den_out, float* __restrict__ part,
+                                                               int* __restrict__ part_cnt) {
+  __shared__ float4 sm[8][SE_MAX_C / 4];
+  __shared__ int cnt[8];
+  const int b = blockIdx.x, s = blockIdx.y, lane = lane_id(), w = warp_id();
+  const int per = (nf + S - 1) / S;
+  const int n0 = s * per, n1 = min(nf, n0 + per);
+  const float root_c = sqrtf((float)C);
+  const int nj = (C + 127) >> 7;
+  float4 acc[SE_MAX_C / 128];
+#pragma unroll
+  for (int j = 0; j < SE_MAX_C / 128; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int n_valid = 0;
+  for (int n = n0 + w; n < n1; n += 8) {
+    const long long row = (long long)b * nf + n;
+    if (!valid[row]) {
+      if (lane == 0) den_out[row] = 1.f;
+      continue;
+    }
+    ++n_valid;
+    const float* hr = h + (size_t)row * ld;
+    float4 v[SE_MAX_C / 128];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < SE_MAX_C / 128; ++j) {
+      const int c = lane * 4 + j * 128;
+      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < nj && c < C) v[j] = *reinterpret_cast<const float4*>(hr + c);
+      ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
+    }
+    const float den = fmaxf(sqrtf(warp_sum(ss)), eps);
+    if (lane == 0) den_out[row] = den;
+#pragma unroll
+    for (int j = 0; j < SE_MAX_C / 128; ++j) {
+      if (j < nj) {
+        acc[j].x += silu_rn(__fdiv_rn(v[j].x, den) * root_c);
+        acc[j].y += silu_rn(__fdiv_rn(v[j].y, den) * root_c);
+        acc[j].z += silu_rn(__fdiv_rn(v[j].z, den) * root_c);
+        acc[j].w += silu_rn(__fdiv_rn(v[j].w, den) * root_c);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < SE_MAX_C / 128; ++j)
+    if (j < nj) sm[w][lane + j * 32] = acc[j];
+  if (lane == 0) cnt[w] = n_valid;
+  __syncthreads();
+  float* out = part + ((size_t)b * S + s) * C;
+  for (int c4 = threadIdx.x; c4 < (C >> 2); c4 += blockDim.x) {
+    float4 t = sm[0][c4];
+    for (int i = 1; i < 8; ++i) { const float4 o = sm[i][c4]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
+    // silu(PixelNorm(0)) = 0 for the lanes' padding columns; columns >= C are never read (c4 < C / 4)
+    reinterpret_cast<float4*>(out)[c4] = t;
+  }
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int i = 0; i < 8; ++i) t += cnt[i];
+    part_cnt[b * S + s] = t;
+  }
+}
+
+// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2) with mean[b] = (sum of the S slice sums) / max(#valid faces, 1e-5); one CTA per
+// mesh, a warp per output (coalesced weight rows, shuffle reduction)
+__global__ void __launch_bounds__(256) se_gate_slices_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
+                                                             const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
+                                                             const float* __restrict__ b2, float* __restrict__ gate) {
+  __shared__ float sm[SE_MAX_C];
+  __shared__ float sh[256];
+  const int b = blockIdx.x, lane = lane_id(), w = warp_id();
+  int nv = 0;
+  for (int s = 0; s < S; ++s) nv += part_cnt[b * S + s];
+  const float inv = 1.f / fmaxf((float)nv, 1e-5f);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < S; ++s) t += part[((size_t)b * S + s) * C + c];
+    sm[c] = t * inv;
+  }
+  __syncthreads();
+  for (int j = w; j < inner; j += 8) {
+    float t = 0.f;
+    for (int c = lane; c < C; c += 32) t = fmaf(w1[(size_t)j * C + c], sm[c], t);
+    t = warp_sum(t) + b1[j];
+    if (lane == 0) sh[j] = silu_rn(t);
+  }
+  __syncthreads();
+  for (int c = w; c < C; c += 8) {
+    float t = 0.f;
+    for (int j = lane; j < inner; j += 32) t = fmaf(w2[(size_t)c * inner + j], sh[j], t);
+    t = warp_sum(t) + b2[c];
+    if (lane == 0) gate[(size_t)b * C + c] = 1.f / (1.f + expf(-t));
+  }
+}
+
+// ResnetBlock tail + the next convolution's image: out = silu(h / den * sqrt(C)) * gate[b] + res (den == NULL: out = h * gate[b] + res)
+// on valid faces, zeros elsewhere; out as fp32 (the next residual input) and, when image != NULL, as the im2col image of kernel k.
+__global__ void __launch_bounds__(256) gate_residual_im2col_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ den,
+                                                                   const float* __restrict__ gate, const float* __restrict__ res, int ldres,
+                                                                   const uint8_t* __restrict__ valid, int R, int nf, int C, float* __restrict__ out, int k,
+                                                                   uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3;
+  const float root_c = sqrtf((float)C);
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, nf);
+    if (!l.active) continue;
+    const bool ok = valid[l.row] != 0;
+    const float dn = (ok && den) ? den[l.row] : 1.f;
+    for (int col = l.colsub * 8; col < C; col += 32) {
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        float gt[8], rs[8];
+        load8(h + (size_t)l.row * ldh + col, v);
+        load8(gate + (size_t)l.b * C + col, gt);
+        load8(res + (size_t)l.row * ldres + col, rs);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float a = den ? silu_rn(__fdiv_rn(v[i], dn) * root_c) : v[i];
+          v[i] = fmaf(a, gt[i], rs[i]);
+        }
+      }
+      store8(out + (size_t)l.row * C + col, v);
+      if (image) emit_taps(image, C, k, l.row, l.n, nf, col, v);
+    }
+  }
+}
+
+inline unsigned grid_groups(long long R) {
+  const long long want = (((R + 7) >> 3) + 7) >> 3;
+  return (unsigned)(want < 1 ? 1 : (want > 148ll * 8 ? 148ll * 8 : want));
+}
+
 inline unsigned grid_for(long long items, int per_block) {
   const long long want = (items + per_block - 1) / per_block;
   return (unsigned)(want < 1 ? 1 : (want > 148ll * 16 ? 148ll * 16 : want));
@@ -319,6 +641,82 @@ int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, 
   MT_CHECK_ARG(logits && valid && coords && ncoord >= 1 && nbins >= 1, "argmax_coords: bad arguments");
   if (R == 0) return MESHTOK_OK;
   argmax_coords_kernel<<<grid_for((long long)R * ncoord, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, R, ncoord, nbins, lo, hi, coords, bins);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+/* ---- fused stages (every producer writes the next convolution's image) ---- */
+int meshtok_dec_se_slices(int B, int nf) {
+  if (B < 1 || nf < 1) return 1;
+  int S = (148 * 4 + B - 1) / B;
+  const int most = (nf + 15) / 16;     /* at least 16 faces per slice */
+  if (S > most) S = most;
+  if (S > 64) S = 64;
+  return S < 1 ? 1 : S;
+}
+
+int meshtok_dec_rows_im2col(const float* x, int ld, const uint8_t* valid, int R, int nf, int C, int k, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && image && R >= 0 && nf >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && (k & 1) == 1, "rows_im2col: width %d must be a multiple of 32, kernel %d odd", C, k);
+  if (R == 0) return MESHTOK_OK;
+  rows_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, valid, R, nf, C, k, static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_dequantize_rvq_im2col(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int nf, int nvf, int Q, int D, int k,
+                                      void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(codes && codebook && valid && image && R >= 0 && nf >= 1 && nvf >= 1 && Q >= 1 && D % 8 == 0 && (nvf * D) % 32 == 0 && (k & 1) == 1,
+               "dequantize_rvq_im2col: D %d must be a multiple of 8, nvf * D of 32, kernel %d odd", D, k);
+  if (R == 0) return MESHTOK_OK;
+  dequantize_rvq_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, codebook, valid, R, nf, nvf, Q, D, k,
+                                                                                             static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_silu_layernorm_im2col(const float* x, const uint8_t* valid, int R, int nf, int C, const float* gamma, const float* beta, float eps,
+                                      float* out, int k, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && gamma && beta && out && R >= 0 && nf >= 1 && C % 32 == 0 && (k & 1) == 1, "silu_layernorm_im2col: width %d must be a multiple of 32", C);
+  if (R == 0) return MESHTOK_OK;
+  silu_layernorm_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, valid, R, nf, C, gamma, beta, eps, out, k,
+                                                                                             static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_pixelnorm_silu_im2col(const float* h, int ld, const uint8_t* valid, int R, int nf, int C, float eps, int k, void* image,
+                                      meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && valid && image && R >= 0 && nf >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && (k & 1) == 1, "pixelnorm_silu_im2col: width %d must be a multiple of 32", C);
+  if (R == 0) return MESHTOK_OK;
+  pixelnorm_silu_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ld, valid, R, nf, C, eps, k, static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int nf, int C, float eps, int inner, const float* w1,
+                                              const float* b1, const float* w2, const float* b2, float* den, float* slice_ws, float* gate,
+                                              meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && valid && w1 && b1 && w2 && b2 && den && slice_ws && gate && C % 4 == 0 && C <= SE_MAX_C && inner <= 256 && ld >= C && ld % 4 == 0,
+               "pixelnorm_squeeze_excite_gate: bad arguments (C %% 4 == 0, C <= %d, inner <= 256)", SE_MAX_C);
+  if (B == 0) return MESHTOK_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int S = meshtok_dec_se_slices(B, nf);
+  int* cnt = reinterpret_cast<int*>(slice_ws + (size_t)B * S * C);
+  pixelnorm_colsum_kernel<<<dim3(B, S), 256, 0, s>>>(h, ld, valid, nf, C, eps, S, den, slice_ws, cnt);
+  MT_CHECK_LAUNCH();
+  se_gate_slices_kernel<<<B, 256, 0, s>>>(slice_ws, cnt, S, C, inner, w1, b1, w2, b2, gate);
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_gate_residual_im2col(const float* h, int ldh, const float* den, const float* gate, const float* res, int ldres, const uint8_t* valid,
+                                     int R, int nf, int C, float* out, int k, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && gate && res && valid && out && R >= 0 && nf >= 1 && C % 32 == 0 && ldh >= C && ldh % 4 == 0 && ldres >= C && ldres % 4 == 0 &&
+                   (image == nullptr || (k & 1) == 1),
+               "gate_residual_im2col: width %d must be a multiple of 32", C);
+  if (R == 0) return MESHTOK_OK;
+  gate_residual_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, den, gate, res, ldres, valid, R, nf, C, out, k,
+                                                                                            static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

@@ -7,6 +7,13 @@ Every Conv1d / Linear runs as a split-bf16 tcgen05 linear (csrc/linear_tc.cu) on
 between are the kernels of csrc/decode.cu, all called through the C ABI (include/meshtok.h, meshtok_dec_*).  PyTorch holds the
 device buffers and nothing else; there is no CPU path.
 
+Default ("fused") schedule, when every width is a multiple of 32: each stage writes the im2col image of the convolution that
+follows it (de-quantise -> image of the k=7 convolution; SiLU+LayerNorm -> x + image; PixelNorm+SiLU -> image only; PixelNorm +
+SqueezeExcite mean without storing the activation; gate * h + res -> x + image), and a block's residual_conv (k=1) rides in the
+same linear as block1.proj (its weight sits in the centre tap of a (2 C_out, 3 C_in) matrix).  6 launches per ResnetBlock instead
+of 10-12.  MESHTOK_DEC_FUSED=0, or a width that is not a multiple of 32, takes the stage-by-stage schedule (same kernels as the
+first version; kept for A/B runs and odd widths).
+
     dec = MeshDecoder(autoencoder)                    # same decoder keywords as the reference constructor
     dec.load_reference_state_dict(reference.state_dict())
     coords, face_mask = dec.cuda().decode_from_codes_to_faces(codes)      # (b, nf, nvf, 3) fp32, NaN on padded faces
@@ -15,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 from typing import Dict, Optional, Tuple
 
 import torch
@@ -103,6 +111,21 @@ class MeshDecoder(nn.Module):
             check(lib.meshtok_linear_build_image(ptr(mat), co, k * ci, ptr(img), stream_ptr()))
             return dict(img=img, bias=cv.bias.detach().to(**f32).contiguous(), n=co, c=ci, k=k, mat=mat)
 
+        def image_of(mat, bias, ci, k):
+            co = mat.shape[0]
+            nbytes = C.c_size_t()
+            check(lib.meshtok_linear_image_bytes(co, mat.shape[1], C.byref(nbytes)))
+            img = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+            check(lib.meshtok_linear_build_image(ptr(mat), co, mat.shape[1], ptr(img), stream_ptr()))
+            return dict(img=img, bias=bias.contiguous(), n=co, c=ci, k=k, mat=mat)
+
+        def conv_with_residual(c1: dict, res: dict):
+            """block1.proj (C_out, 3 C_in) and residual_conv (C_out, C_in) as one (2 C_out, 3 C_in) matrix on the k=3 image."""
+            ci = c1["c"]
+            pad = torch.zeros(res["n"], 3 * ci, **f32)
+            pad[:, ci:2 * ci] = res["mat"]
+            return image_of(torch.cat([c1["mat"], pad]).contiguous(), torch.cat([c1["bias"], res["bias"]]), ci, 3)
+
         def _as_conv(l: nn.Linear):
             cv = nn.Conv1d(l.in_features, l.out_features, 1)
             cv.weight.data = l.weight.detach()[:, :, None]
@@ -119,6 +142,8 @@ class MeshDecoder(nn.Module):
                     c1=conv(blk.block1.proj), c2=conv(blk.block2.proj),
                     res=None if isinstance(blk.residual_conv, nn.Identity) else conv(blk.residual_conv),
                     se=tuple(t.detach().to(**f32).contiguous() for t in (e[0].weight, e[0].bias, e[2].weight, e[2].bias))))
+                last = prep["blocks"][-1]
+                last["c1r"] = conv_with_residual(last["c1"], last["res"]) if last["res"] is not None and last["c1"]["k"] == 3 else None
         self._prep, self._prep_key = prep, key
         return prep
 
@@ -154,6 +179,88 @@ class MeshDecoder(nn.Module):
             check(lib.meshtok_dec_dequantize_rvq(ptr(codes), ptr(book), b * n, q, self.dim_codebook, ptr(out), stream_ptr()))
         return out
 
+    # ---- fused schedule ----------------------------------------------------------------------------
+    def fused(self) -> bool:
+        if os.environ.get("MESHTOK_DEC_FUSED", "1") == "0":
+            return False
+        widths = [self.init_decoder_conv["0"].out_channels] + [blk.block1.proj.out_channels for blk in self.decoders]
+        return all(w % 32 == 0 for w in widths) and (self.nvf * self.dim_codebook) % 32 == 0 and self.dim_codebook % 8 == 0
+
+    @staticmethod
+    def _image(R: int, K: int, dev) -> Tensor:
+        nbytes = C.c_size_t()
+        check(lib.meshtok_rows_image_bytes(R, K, C.byref(nbytes)))
+        return torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+
+    @staticmethod
+    def _linear(img: Tensor, R: int, w: dict) -> Tensor:
+        out = torch.empty(R, w["n"], dtype=torch.float32, device=img.device)
+        check(lib.meshtok_linear(None, ptr(img), None, ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], w["k"] * w["c"], 0, 0, stream_ptr()))
+        return out
+
+    def _decode_fused(self, init_img: Tensor, valid: Tensor, b: int, nf: int, logits_image: bool):
+        """init_img: im2col image of the (masked) quantized rows for init_decoder_conv.0.  Returns (decoded (R, C) fp32 with zero rows
+        on padded faces, the k=1 image of it for to_coor_logits or None)."""
+        p = self._prepare()
+        R, dev = b * nf, init_img.device
+        blocks = p["blocks"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        x0 = self._linear(init_img, R, p["init"])
+        c = p["init"]["n"]
+        k_next = 3 if blocks else (1 if logits_image else 0)
+        x = torch.empty(R, c, **f32)
+        img = self._image(R, k_next * c, dev) if k_next else None
+        check(lib.meshtok_dec_silu_layernorm_im2col(ptr(x0), ptr(valid), R, nf, c, ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, ptr(x), k_next, ptr(img),
+                                                    stream_ptr()))
+        S = lib.meshtok_dec_se_slices(b, nf)
+        for i, blk in enumerate(blocks):
+            cout = blk["c1"]["n"]
+            if blk["c1r"] is not None:
+                h = self._linear(img, R, blk["c1r"])                 # (R, 2 cout): [block1.proj | residual_conv]
+                ldh, res_ptr, ldres = 2 * cout, h.data_ptr() + 4 * cout, 2 * cout
+            else:
+                h = self._linear(img, R, blk["c1"])
+                ldh, res_ptr, ldres = cout, x.data_ptr(), x.shape[1]
+            img2 = self._image(R, 3 * cout, dev)
+            check(lib.meshtok_dec_pixelnorm_silu_im2col(ptr(h), ldh, ptr(valid), R, nf, cout, 1e-4, 3, ptr(img2), stream_ptr()))
+            h2 = self._linear(img2, R, blk["c2"])
+            w1, b1, w2, b2 = blk["se"]
+            den = torch.empty(R, **f32)
+            ws = torch.empty(b * S * (cout + 1), **f32)
+            gate = torch.empty(b, cout, **f32)
+            check(lib.meshtok_dec_pixelnorm_squeeze_excite_gate(ptr(h2), cout, ptr(valid), b, nf, cout, 1e-4, w1.shape[0], ptr(w1), ptr(b1), ptr(w2),
+                                                                ptr(b2), ptr(den), ptr(ws), ptr(gate), stream_ptr()))
+            k_next = 3 if i + 1 < len(blocks) else (1 if logits_image else 0)
+            out = torch.empty(R, cout, **f32)
+            img = self._image(R, k_next * cout, dev) if k_next else None
+            check(lib.meshtok_dec_gate_residual_im2col(ptr(h2), cout, ptr(den), ptr(gate), res_ptr, ldres, ptr(valid), R, nf, cout, ptr(out), k_next,
+                                                       ptr(img), stream_ptr()))
+            x = out
+        return x, img
+
+    def _decode_staged(self, x: Tensor, valid: Tensor, b: int, nf: int) -> Tensor:
+        """The first version's schedule: one kernel per stage, a separate im2col pass in front of every convolution."""
+        p = self._prepare()
+        R, dev = b * nf, x.device
+        x = self._conv(x, valid, nf, p["init"])
+        check(lib.meshtok_dec_silu_layernorm(ptr(x), R, x.shape[1], ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, stream_ptr()))
+        for blk in p["blocks"]:
+            cout = blk["c1"]["n"]
+            res = x if blk["res"] is None else self._conv(x, valid, nf, blk["res"])
+            h = self._conv(x, valid, nf, blk["c1"])
+            check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
+            h = self._conv(h, valid, nf, blk["c2"])
+            check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
+            w1, b1, w2, b2 = blk["se"]
+            mean = torch.empty(b, cout, dtype=torch.float32, device=dev)
+            gate = torch.empty(b, cout, dtype=torch.float32, device=dev)
+            check(lib.meshtok_dec_squeeze_excite_gate(ptr(h), ptr(valid), b, nf, cout, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                                      ptr(mean), ptr(gate), stream_ptr()))
+            out = torch.empty(R, cout, dtype=torch.float32, device=dev)
+            check(lib.meshtok_dec_gate_residual(ptr(h), ptr(gate), ptr(res), ptr(valid), R, nf, cout, ptr(out), stream_ptr()))
+            x = out
+        return x
+
     @torch.no_grad()
     def decode(self, quantized: Tensor, face_mask: Tensor) -> Tensor:
         """quantized (b, nf, nvf * dim_codebook) fp32, face_mask (b, nf) bool -> (b, nf, last decoder dim); rows of padded faces are 0."""
@@ -164,26 +271,13 @@ class MeshDecoder(nn.Module):
         valid = face_mask.reshape(R).to(torch.uint8).contiguous()
         x = quantized.reshape(R, d).float().contiguous()
         with torch.cuda.device(dev):
-            x = self._conv(x, valid, nf, p["init"])
-            check(lib.meshtok_dec_silu_layernorm(ptr(x), R, x.shape[1], ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, stream_ptr()))
-            for blk in p["blocks"]:
-                cout = blk["c1"]["n"]
-                if blk["res"] is None:
-                    res = x
-                else:
-                    res = self._conv(x, valid, nf, blk["res"])
-                h = self._conv(x, valid, nf, blk["c1"])
-                check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
-                h = self._conv(h, valid, nf, blk["c2"])
-                check(lib.meshtok_dec_pixelnorm_silu(ptr(h), ptr(valid), R, cout, 1e-4, stream_ptr()))
-                w1, b1, w2, b2 = blk["se"]
-                mean = torch.empty(b, cout, dtype=torch.float32, device=dev)
-                gate = torch.empty(b, cout, dtype=torch.float32, device=dev)
-                check(lib.meshtok_dec_squeeze_excite_gate(ptr(h), ptr(valid), b, nf, cout, w1.shape[0], ptr(w1), ptr(b1), ptr(w2), ptr(b2),
-                                                          ptr(mean), ptr(gate), stream_ptr()))
-                out = torch.empty(R, cout, dtype=torch.float32, device=dev)
-                check(lib.meshtok_dec_gate_residual(ptr(h), ptr(gate), ptr(res), ptr(valid), R, nf, cout, ptr(out), stream_ptr()))
-                x = out
+            if self.fused():
+                k = p["init"]["k"]
+                img = self._image(R, k * d, dev)
+                check(lib.meshtok_dec_rows_im2col(ptr(x), d, ptr(valid), R, nf, d, k, ptr(img), stream_ptr()))
+                x, _ = self._decode_fused(img, valid, b, nf, logits_image=False)
+            else:
+                x = self._decode_staged(x, valid, b, nf)
         return x.reshape(b, nf, -1)
 
     @torch.no_grad()
@@ -193,21 +287,35 @@ class MeshDecoder(nn.Module):
         if not codes.is_cuda:
             raise RuntimeError("codes must be a CUDA tensor; there is no CPU path")
         p = self._prepare()
+        a = self.autoencoder
         b = codes.shape[0]
         codes = codes.reshape(b, -1)
         nvf, q = self.nvf, self.num_quantizers
         if face_mask is None:
             face_mask = (codes != self.pad_id).reshape(b, -1, nvf * q).all(dim=-1)
-        codes = codes.reshape(b, -1, q)
-        quantized = self.dequantize(codes).reshape(b, -1, nvf * self.dim_codebook)
-        nf = quantized.shape[1]
+        codes = codes.reshape(b, -1, q).contiguous().long()
+        nf = codes.shape[1] // nvf
         R = b * nf
-        decoded = self.decode(quantized, face_mask)            # rows of padded faces are already zero (:924)
-        valid = face_mask.reshape(R).to(torch.uint8).contiguous()
         dev = codes.device
+        valid = face_mask.reshape(R).to(torch.uint8).contiguous()
         with torch.cuda.device(dev):
-            ones = torch.ones(R, dtype=torch.uint8, device=dev)        # to_coor_logits is a plain Linear: no neighbours, no mask
-            logits = self._conv(decoded.reshape(R, -1).contiguous(), ones, nf, p["logits"])
+            if self.fused():
+                k, d = p["init"]["k"], nvf * self.dim_codebook
+                img = self._image(R, k * d, dev)
+                if a.use_residual_lfq:
+                    quantized = self.dequantize(codes)
+                    check(lib.meshtok_dec_rows_im2col(ptr(quantized), d, ptr(valid), R, nf, d, k, ptr(img), stream_ptr()))
+                else:
+                    book = a.quantizer.layers[0]._codebook.embed[0].detach().float().contiguous()
+                    check(lib.meshtok_dec_dequantize_rvq_im2col(ptr(codes), ptr(book), ptr(valid), R, nf, nvf, q, self.dim_codebook, k, ptr(img),
+                                                                stream_ptr()))
+                decoded, limg = self._decode_fused(img, valid, b, nf, logits_image=True)
+                logits = self._linear(limg, R, p["logits"])
+            else:
+                quantized = self.dequantize(codes).reshape(R, nvf * self.dim_codebook)
+                decoded = self._decode_staged(quantized, valid, b, nf)      # rows of padded faces are already zero (:924)
+                ones = torch.ones(R, dtype=torch.uint8, device=dev)        # to_coor_logits is a plain Linear: no neighbours, no mask
+                logits = self._conv(decoded, ones, nf, p["logits"])
             ncoord = nvf * 3
             coords = torch.empty(b, nf, nvf, 3, dtype=torch.float32, device=dev)
             bins = torch.empty(b, nf, nvf, 3, dtype=torch.int64, device=dev)

@@ -1,5 +1,9 @@
 """Decode throughput (faces decoded / s, device-timed) at the C2 shape with the reference's default decoder, next to the CPU
-decode oracle on a sample.  First-version numbers: the path is correct, not yet tuned."""
+decode oracle on a sample.  Prints one JSON line for the fused schedule (graph replay = the number to quote, eager beside it) and
+one for the stage-by-stage schedule (MESHTOK_DEC_FUSED=0).
+
+    python scripts/gpu_decode_bench.py [meshes] [profile]      # profile: one eager step between cudaProfilerStart / Stop
+"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
@@ -18,35 +22,41 @@ md.load_reference_state_dict({k: v for k, v in od.state_dict().items() if not k.
 md = md.cuda()
 v, f = synth.grid_batch("tri", 20, 20, list(range(B)))
 codes = m.tokenize(v.cuda(), f.cuda())
-for _ in range(3):
-    md.decode_from_codes_to_faces(codes)
-torch.cuda.synchronize()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB), written between timed steps
+
+
+def timed(fn, steps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); out = fn(); b.record(); evs.append((a, b))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in evs) / steps, out
+
+
 if len(sys.argv) > 2 and sys.argv[2] == "profile":     # ncu --profile-from-start off: one eager step
+    for _ in range(3):
+        md.decode_from_codes_to_faces(codes)
+    torch.cuda.synchronize()
     torch.cuda.profiler.start(); md.decode_from_codes_to_faces(codes); torch.cuda.synchronize(); torch.cuda.profiler.stop()
     sys.exit(0)
-l0 = lib.meshtok_kernel_launch_count()
-steps = 10
-evs = []
-for _ in range(steps):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); coords, mask = md.decode_from_codes_to_faces(codes); b.record(); evs.append((a, b))
-torch.cuda.synchronize()
-ms = sum(a.elapsed_time(b) for a, b in evs) / steps
-launches = (lib.meshtok_kernel_launch_count() - l0) / steps
+
 n_cpu = min(B, 8)
 t0 = time.perf_counter(); od.decode_from_codes_to_faces(codes[:n_cpu].cpu()); cpu_s = time.perf_counter() - t0
-g = md.graphed(codes)
-for _ in range(3):
-    g()
-torch.cuda.synchronize()
-evs = []
-for _ in range(steps):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); gc, gm = g(); b.record(); evs.append((a, b))
-torch.cuda.synchronize()
-ms_graph = sum(a.elapsed_time(b) for a, b in evs) / steps
-assert torch.equal(torch.nan_to_num(gc), torch.nan_to_num(coords))
-ms_eager, ms = ms, ms_graph
-print(json.dumps(dict(eager_ms_per_step=ms_eager, metric="faces decoded/sec (device-timed)", value=B * 800 / (ms * 1e-3), unit="faces/s", ms_per_step=ms, meshes=B,
-                      counted_launches_per_step=launches,
-                      cpu_baseline=dict(value=n_cpu * 800 / cpu_s, unit="faces/s", cores=os.cpu_count(), kind="port", sample=f"decode oracle on {n_cpu} meshes"))))
+cpu = dict(value=n_cpu * 800 / cpu_s, unit="faces/s", cores=os.cpu_count(), kind="port", sample=f"decode oracle on {n_cpu} meshes")
+for schedule in ("fused", "staged"):
+    os.environ["MESHTOK_DEC_FUSED"] = "1" if schedule == "fused" else "0"
+    l0 = lib.meshtok_kernel_launch_count()
+    md.decode_from_codes_to_faces(codes)
+    launches = lib.meshtok_kernel_launch_count() - l0
+    ms_eager, (coords, mask) = timed(lambda: md.decode_from_codes_to_faces(codes))
+    g = md.graphed(codes)
+    ms_graph, (gc, gm) = timed(lambda: g())
+    assert torch.equal(torch.nan_to_num(gc), torch.nan_to_num(coords))
+    print(json.dumps(dict(schedule=schedule, metric="faces decoded/sec (device-timed, graph replay, L2 flushed between steps)",
+                          value=B * 800 / (ms_graph * 1e-3), unit="faces/s", ms_per_step=ms_graph, eager_ms_per_step=ms_eager, meshes=B,
+                          counted_launches_per_step=launches, cpu_baseline=cpu)))

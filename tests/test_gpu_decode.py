@@ -77,3 +77,84 @@ def test_decode_full_size_decoder_round_trip():
     assert got_c.shape == (2, 800, 3, 3) and bool(got_mask.all())
     same = (got_bins.cpu() == want_bins).float().mean()
     assert float(same) >= 0.98, float(same)
+
+
+def _image_bytes(R, K):
+    import ctypes as C
+    from meshgpt_pytorch_b200._lib import lib, check
+    n = C.c_size_t()
+    check(lib.meshtok_rows_image_bytes(R, K, C.byref(n)))
+    return n.value
+
+
+def _live_image(img, R, K):
+    """The bytes of an activation image that belong to rows < R (pad rows of the last 128-row tile are never written)."""
+    full = (R // 128) * (K // 32) * 16384
+    head = img[:full]
+    if R % 128 == 0:
+        return head
+    tail = img[full:].reshape(K // 32, 2, 16, 4, 8, 16)[:, :, :, :, :, :]       # chunk, hi/lo, 8-row group, k group, row, 16 B
+    rows = (torch.arange(16, device=img.device)[:, None] * 8 + torch.arange(8, device=img.device)[None, :]) < (R % 128)
+    keep = rows[None, None, :, None, :, None].expand_as(tail)
+    return torch.cat([head, tail[keep]])
+
+
+@pytest.mark.parametrize("k", [1, 3, 7])
+def test_fused_image_writers_are_bit_exact_with_the_im2col_pass(k):
+    """rows_im2col and dequantize_rvq_im2col write, byte for byte, the image the stand-alone im2col pass builds from the same rows
+    (ragged meshes, masked faces in the middle of a mesh, a row count that is not a multiple of 8 or 128)."""
+    from meshgpt_pytorch_b200._lib import lib, check, ptr, stream_ptr
+    torch.manual_seed(k)
+    b, nf, c = 3, 77, 96
+    R = b * nf
+    x = torch.randn(R, c, device="cuda")
+    valid = (torch.rand(R, device="cuda") > 0.2).to(torch.uint8)
+    valid[nf - 5:nf] = 0
+    n = _image_bytes(R, k * c)
+    want = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    got = torch.full((n,), 0xAB, dtype=torch.uint8, device="cuda")
+    check(lib.meshtok_dec_im2col_image(ptr(x), ptr(valid), R, nf, c, k, ptr(want), stream_ptr()))
+    check(lib.meshtok_dec_rows_im2col(ptr(x), c, ptr(valid), R, nf, c, k, ptr(got), stream_ptr()))
+    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
+    # a strided source: the second half of a (R, 2 c) buffer
+    wide = torch.randn(R, 2 * c, device="cuda")
+    wide[:, c:] = x
+    got.fill_(0xCD)
+    check(lib.meshtok_dec_rows_im2col(wide.data_ptr() + 4 * c, 2 * c, ptr(valid), R, nf, c, k, ptr(got), stream_ptr()))
+    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
+    # codes -> image
+    nvf, q, d, ksz = 3, 2, 32, 50
+    book = torch.randn(ksz, d, device="cuda")
+    codes = torch.randint(0, ksz, (R * nvf, q), device="cuda")
+    codes[(valid == 0).repeat_interleave(nvf)] = -1
+    rows = torch.empty(R * nvf, d, device="cuda")
+    check(lib.meshtok_dec_dequantize_rvq(ptr(codes), ptr(book), R * nvf, q, d, ptr(rows), stream_ptr()))
+    check(lib.meshtok_dec_im2col_image(ptr(rows), ptr(valid), R, nf, nvf * d, k, ptr(want), stream_ptr()))
+    got.fill_(0xEF)
+    check(lib.meshtok_dec_dequantize_rvq_im2col(ptr(codes), ptr(book), ptr(valid), R, nf, nvf, q, d, k, ptr(got), stream_ptr()))
+    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
+
+
+@pytest.mark.parametrize("cfg,dims,kind", [
+    (dict(SMALL_CFG, use_residual_lfq=False), (32, 32, 64, 64, 96), "tri"),
+    (dict(SMALL_CFG, quads=True), (64, 32), "quad"),
+])
+def test_fused_schedule_matches_the_staged_one(cfg, dims, kind, monkeypatch):
+    """Same decoder, same codes: the fused schedule (producers write the next image, residual_conv inside block1's linear, PixelNorm
+    folded into the SqueezeExcite mean and the block tail) against the stage-by-stage schedule.  Only summation orders differ."""
+    o, m, od, md = make_decoders(cfg, dims)
+    v, f = synth.ragged_batch(kind, 9, 8, [130, 61, 8, 1] if kind == "tri" else [72, 30, 5, 1], [0, 1, 2, 3])
+    codes = m.tokenize(v.cuda(), f.cuda())
+    assert md.fused()
+    c1, b1, m1 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    q = md.dequantize(codes.reshape(codes.shape[0], -1, o.num_quantizers)).reshape(codes.shape[0], -1, o.nvf * o.dim_codebook)
+    d1 = md.decode(q, m1)
+    monkeypatch.setenv("MESHTOK_DEC_FUSED", "0")
+    assert not md.fused()
+    c0, b0, m0 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    d0 = md.decode(q, m0)
+    assert torch.equal(m0, m1)
+    assert float((d1 - d0).abs().max() / d0.abs().max()) < 1e-4
+    assert float((d1[~m1]).abs().max()) == 0.0
+    assert float((b1[m1] == b0[m1]).float().mean()) >= 0.995
+    assert torch.isnan(c1[~m1]).all()
