@@ -272,34 +272,49 @@ int meshtok_dec_gate_residual(const float* h, const float* gate, const float* re
 int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, int ncoord, int nbins, float lo, float hi,
                               float* coords, int64_t* bins, meshtok_stream_t stream);
 
-/* ---- fused decode stages: every producer writes the im2col image of the convolution that follows it, so no activation makes a
- * separate fp32 -> image pass.  All need widths that are multiples of 32 (the image chunk); `ld` / `ldh` / `ldres` are row strides in
- * floats (a linear that computes block1.proj and residual_conv in one launch leaves both side by side in one (R, 2 C) buffer). ---- */
+/* ---- fused decode stages: no im2col.
+ * PADDED ROW SPACE: activations are rows b * P + lead + n (P = nf + lead, lead = half width of the widest kernel), `lead` separator
+ * rows in front of every mesh and after the last one: R = B * P + lead; `valid` (R bytes) is 0 on separators and padded faces.  Every
+ * stage writes zero image rows for non-valid rows, so a tap that reaches over the end of a mesh reads zeros (Conv1d's zero padding and
+ * the masked_fill of Block.forward, :341-349, at once).
+ * HALO IMAGE: the split-bf16 image of an (R, C) activation in which consecutive rows are 16 bytes apart and every 128-row tile carries
+ * the `halo` rows before and after it; the tcgen05 kernel reads tap t of a convolution from the same block, 16 t bytes further
+ * (meshtok_conv1d).  Widths must be multiples of 32.  `ld` / `ldh` / `ldres` are row strides in floats (the linear that computes
+ * block1.proj and residual_conv in one launch leaves both side by side in one (R, 2 C) buffer). ---- */
+int meshtok_halo_image_bytes(int R, int C, int halo, size_t* bytes);
+/* out (R, N) fp32 = Conv1d(C_in -> N, kernel k, zero padding k / 2) over the rows of a halo image (halo >= k / 2) + bias;
+ * w_image = meshtok_linear_build_image of the (N, k * C_in) matrix weight.permute(0, 2, 1) (tap-major columns).  k = 1: a Linear. */
+int meshtok_conv1d(const void* a_halo_image, const void* w_image, const float* bias, float* out, int R, int N, int C_in, int k,
+                   int halo, meshtok_stream_t stream);
 /* number of face slices per mesh the SqueezeExcite partial sums use; slice_ws holds B * S * C floats + B * S int32 */
 int meshtok_dec_se_slices(int B, int nf);
-/* x (R, C) fp32 -> image (R, k * C), like meshtok_dec_im2col_image but 16-byte stores, a warp per 8-row group */
-int meshtok_dec_rows_im2col(const float* x, int ld, const uint8_t* valid, int R, int nf, int C, int k, void* image,
-                            meshtok_stream_t stream);
-/* get_output_from_indices (:917) + masked_fill (:924) + the image of init_decoder_conv.0 (:621): codes (R * nvf, Q) -> image
- * (R, k * nvf * D); the summed codebook vectors are never stored as fp32 */
-int meshtok_dec_dequantize_rvq_im2col(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int nf, int nvf,
-                                      int Q, int D, int k, void* image, meshtok_stream_t stream);
-/* init_decoder_conv tail (:621-627) -> out (R, C) fp32 (the first residual input) + image (R, k * C) (NULL: none); masked faces 0 */
-int meshtok_dec_silu_layernorm_im2col(const float* x, const uint8_t* valid, int R, int nf, int C, const float* gamma,
-                                      const float* beta, float eps, float* out, int k, void* image, meshtok_stream_t stream);
-/* Block tail (:345-351) written only as the image of the next convolution; h is not modified */
-int meshtok_dec_pixelnorm_silu_im2col(const float* h, int ld, const uint8_t* valid, int R, int nf, int C, float eps, int k,
-                                      void* image, meshtok_stream_t stream);
-/* second Block tail + SqueezeExcite (:296-324) without storing the activation: den (R) = max(||h[row]||, eps) and gate (B, C) from the
- * masked mean of silu(PixelNorm(h)); slice sums are combined in a fixed order (deterministic) */
-int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int nf, int C, float eps,
-                                              int inner, const float* w1, const float* b1, const float* w2, const float* b2,
-                                              float* den, float* slice_ws, float* gate, meshtok_stream_t stream);
-/* ResnetBlock tail (:378-379): out = silu(h / den * sqrt(C)) * gate[b] + res (den NULL: h * gate[b] + res) -> out (R, C) fp32 and,
- * image != NULL, the image (R, k * C) of the next convolution; masked faces 0 */
-int meshtok_dec_gate_residual_im2col(const float* h, int ldh, const float* den, const float* gate, const float* res, int ldres,
-                                     const uint8_t* valid, int R, int nf, int C, float* out, int k, void* image,
-                                     meshtok_stream_t stream);
+/* x (B * nf, C) fp32, UNPADDED rows -> halo image in the padded row space */
+int meshtok_dec_rows_halo(const float* x, int ld, const uint8_t* valid, int R, int P, int lead, int C, int halo, void* image,
+                          meshtok_stream_t stream);
+/* get_output_from_indices (:917) + masked_fill (:924) -> the halo image init_decoder_conv.0 (:621) reads: codes (B * nf * nvf, Q),
+ * unpadded -> image (R, nvf * D); the summed codebook vectors are never stored as fp32 */
+int meshtok_dec_dequantize_rvq_halo(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int P, int lead, int nvf,
+                                    int Q, int D, int halo, void* image, meshtok_stream_t stream);
+/* init_decoder_conv tail (:621-627) -> out (R, C) fp32 (the first residual input) + halo image (NULL: none); non-valid rows 0 */
+int meshtok_dec_silu_layernorm_halo(const float* x, const uint8_t* valid, int R, int P, int C, const float* gamma, const float* beta,
+                                    float eps, float* out, int halo, void* image, meshtok_stream_t stream);
+/* Block tail (:345-351) written only as the halo image of the next convolution; h is not modified */
+int meshtok_dec_pixelnorm_silu_halo(const float* h, int ld, const uint8_t* valid, int R, int P, int C, float eps, int halo,
+                                    void* image, meshtok_stream_t stream);
+/* second Block tail + SqueezeExcite (:296-324) without storing the activation: scale (R) = sqrt(C) / max(||h[row]||, eps) on valid rows
+ * and gate (B, C) from the masked mean of silu(h * scale); slice sums are combined in a fixed order (deterministic).  The two
+ * SqueezeExcite weights are passed TRANSPOSED: w1t (C, inner) = excite.net.0.weight^T, w2t (inner, C) = excite.net.2.weight^T. */
+int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int P, int lead, int C, float eps,
+                                              int inner, const float* w1t, const float* b1, const float* w2t, const float* b2,
+                                              float* scale, float* slice_ws, float* gate, meshtok_stream_t stream);
+/* ResnetBlock tail (:378-379): out = silu(h * scale[row]) * gate[b] + res (scale NULL: h * gate[b] + res) -> out (R, C) fp32 and,
+ * image != NULL, the halo image of the next convolution; non-valid rows 0 */
+int meshtok_dec_gate_residual_halo(const float* h, int ldh, const float* scale, const float* gate, const float* res, int ldres,
+                                   const uint8_t* valid, int R, int P, int C, float* out, int halo, void* image,
+                                   meshtok_stream_t stream);
+/* meshtok_dec_argmax_coords for logits in the padded row space: coords / bins are written for the UNPADDED faces (B * nf, ncoord) */
+int meshtok_dec_argmax_coords_padded(const float* logits, const uint8_t* valid, int B, int P, int lead, int ncoord, int nbins,
+                                     float lo, float hi, float* coords, int64_t* bins, meshtok_stream_t stream);
 
 #ifdef __cplusplus
 }

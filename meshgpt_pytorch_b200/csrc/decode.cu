@@ -240,27 +240,33 @@ __global__ void __launch_bounds__(256) argmax_coords_kernel(const float* __restr
 }
 
 
-// ---- fused stages: every producer writes the next convolution's im2col image itself ------------------------------------
-// Thread layout of the kernels below ("8 x 4"): a warp owns one aligned group of 8 rows, lane = colsub * 8 + rowsub
-// (rowsub = lane & 7 the row of the group, colsub = lane >> 3), and walks the row in steps of 32 columns, 8 adjacent columns
-// per lane.  A warp-wide image store is then 512 contiguous bytes of hi and 512 of lo (the 8 rows x 32 columns block of the
-// canonical layout), a warp-wide fp32 load is 8 rows x 128 contiguous bytes, and a row reduction is two shuffles (xor 8, 16).
-// Needs C % 32 == 0.
+// ---- fused stages: no im2col ------------------------------------------------------------------------------------------------
+// PADDED ROW SPACE.  The fused schedule keeps every activation as rows b * P + lead + n (P = nf + lead, lead = the widest kernel's
+// half width), i.e. `lead` separator rows in front of every mesh and after the last one: R = B * P + lead rows, `valid` = 0 on
+// separators and padded faces.  Every stage writes zeros to the image rows of non-valid rows, so a convolution tap that reaches over
+// the end of a mesh reads a zero row - the zero padding of Conv1d and the masked_fill of Block.forward (meshgpt_pytorch.py:341-349)
+// at once, with no per-tap boundary test anywhere.
+// HALO IMAGES (tc_common.cuh).  A stage writes its output once, as the split-bf16 halo image of the convolution that follows; the
+// tcgen05 kernel reads tap t of the kernel from the same block 16 t bytes further (linear_tc.cu, conv mode).  The first version's
+// im2col image (k copies of every activation) is gone: a k=3 convolution's input is written as 4 bytes per element instead of 12.
+// Thread layout ("8 x 4"): a warp owns one aligned group of 8 rows, lane = colsub * 8 + rowsub; it walks the row in steps of 32
+// columns, 8 adjacent columns (16 bytes of hi, 16 of lo) per lane.  A warp-wide image store is 4 x 128 contiguous bytes of hi and
+// of lo, a warp-wide fp32 load 8 rows x 128 contiguous bytes, a row reduction two shuffles (xor 8, 16).  Needs C % 32 == 0.
+// The float chains here use reciprocal multiplies and __expf (PixelNorm / SiLU are tolerance-checked stages, not bit-exact ones);
+// the staged kernels above keep the IEEE divisions.
 struct Lane84 {
-  long long row;   // global row (b * nf + n); may be >= R in the last group
-  int n;           // face slot inside its mesh
-  int b;           // mesh
+  long long row;   // padded row; may be >= R in the last group
+  int b;           // mesh (row / P; == B on the trailing separators)
   int colsub;
   bool active;     // row < R
 };
-__device__ __forceinline__ Lane84 lane84(long long group, int R, int nf) {
+__device__ __forceinline__ Lane84 lane84(long long group, int R, int P) {
   Lane84 l;
   const int lane = lane_id();
   l.row = group * 8 + (lane & 7);
   l.colsub = lane >> 3;
   l.active = l.row < R;
-  l.b = (int)(l.row / nf);
-  l.n = (int)(l.row - (long long)l.b * nf);
+  l.b = (int)(l.row / P);
   return l;
 }
 __device__ __forceinline__ float row_sum84(float v) {
@@ -268,28 +274,29 @@ __device__ __forceinline__ float row_sum84(float v) {
   v += __shfl_xor_sync(0xffffffffu, v, 16);
   return v;
 }
-__device__ __forceinline__ void image_store8(uint8_t* img, int K, long long row, int col, const uint4& hi, const uint4& lo) {
-  uint8_t* p = img + tc::image_offset(K, row, col);
-  *reinterpret_cast<uint4*>(p) = hi;
-  *reinterpret_cast<uint4*>(p + tc::IMG_PART) = lo;
-}
-// 8 adjacent values v[0..8) of (row, columns col .. col+7) of a (R, C) activation -> the k cells of the im2col image (R, k * C) they
-// feed: cell (row + half - t, tap t) for every tap whose target face is inside the mesh.  The cells of THIS row whose source face
-// lies outside the mesh (the zero padding of Conv1d) are written here too, so every cell of the image is written exactly once.
-// v must already be zero for a masked face.
-__device__ __forceinline__ void emit_taps(uint8_t* img, int C, int k, long long row, int n, int nf, int col, const float (&v)[8]) {
+// 8 adjacent values of (row, columns col .. col + 7) -> the halo image (R, C): the row's own tile and, for the first / last `halo`
+// rows of a tile, the halo copy in the neighbouring tile.  v must already be zero for a non-valid row.
+__device__ __forceinline__ void emit_halo(uint8_t* img, int C, int halo, long long n_tiles, long long row, int col, const float (&v)[8]) {
   uint4 hi, lo;
   tc::split2(v[0], v[1], hi.x, lo.x);
   tc::split2(v[2], v[3], hi.y, lo.y);
   tc::split2(v[4], v[5], hi.z, lo.z);
   tc::split2(v[6], v[7], hi.w, lo.w);
-  const int KC = k * C, half = k >> 1;
-  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  for (int t = 0; t < k; ++t) {
-    const int target_n = n + half - t;
-    if (target_n >= 0 && target_n < nf) image_store8(img, KC, row + (half - t), t * C + col, hi, lo);
-    const int source_n = n + t - half;
-    if (source_n < 0 || source_n >= nf) image_store8(img, KC, row, t * C + col, zero, zero);
+  const long long tile = row >> 7;
+  const int r = (int)(row & 127);
+  const uint32_t lo_off = 64u * (uint32_t)(tc::IMG_ROWS + 2 * halo);
+  uint8_t* p = img + tc::halo_offset(C, halo, tile, r, col);
+  *reinterpret_cast<uint4*>(p) = hi;
+  *reinterpret_cast<uint4*>(p + lo_off) = lo;
+  if (r < halo && tile > 0) {
+    p = img + tc::halo_offset(C, halo, tile - 1, r + tc::IMG_ROWS, col);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + lo_off) = lo;
+  }
+  if (r >= tc::IMG_ROWS - halo && tile + 1 < n_tiles) {
+    p = img + tc::halo_offset(C, halo, tile + 1, r - tc::IMG_ROWS, col);
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + lo_off) = lo;
   }
 }
 __device__ __forceinline__ void load8(const float* p, float (&v)[8]) {
@@ -300,39 +307,42 @@ __device__ __forceinline__ void store8(float* p, const float (&v)[8]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
 }
-__device__ __forceinline__ float silu_rn(float t) { return __fdiv_rn(t, 1.f + expf(-t)); }
+__device__ __forceinline__ float silu_fast(float t) { return __fdividef(t, 1.f + __expf(-t)); }
 
-// x (R, C; row stride ld) fp32 -> im2col image, zero on masked faces
-__global__ void __launch_bounds__(256) rows_im2col_kernel(const float* __restrict__ x, int ld, const uint8_t* __restrict__ valid, int R, int nf,
-                                                          int C, int k, uint8_t* __restrict__ image) {
-  const long long groups = ((long long)R + 7) >> 3;
+// x (B * nf rows of C floats, UNPADDED, row stride ld) -> halo image in the padded row space; zero rows on separators / masked faces
+__global__ void __launch_bounds__(256) rows_halo_kernel(const float* __restrict__ x, int ld, const uint8_t* __restrict__ valid, int R, int P, int lead,
+                                                        int C, int halo, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
+  const int nf = P - lead;
   for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
-    const Lane84 l = lane84(g, R, nf);
+    const Lane84 l = lane84(g, R, P);
     if (!l.active) continue;
     const bool ok = valid[l.row] != 0;
+    const long long src = (long long)l.b * nf + (l.row - (long long)l.b * P - lead);
     for (int col = l.colsub * 8; col < C; col += 32) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) load8(x + (size_t)l.row * ld + col, v);
-      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+      if (ok) load8(x + (size_t)src * ld + col, v);
+      emit_halo(image, C, halo, n_tiles, l.row, col, v);
     }
   }
 }
 
-// codes (R * nvf, Q) -> summed codebook rows (R, nvf * D) -> im2col image of the first convolution; never stored as fp32
-__global__ void __launch_bounds__(256) dequantize_rvq_im2col_kernel(const int64_t* __restrict__ codes, const float* __restrict__ codebook,
-                                                                    const uint8_t* __restrict__ valid, int R, int nf, int nvf, int Q, int D, int k,
-                                                                    uint8_t* __restrict__ image) {
-  const int C = nvf * D;
-  const long long groups = ((long long)R + 7) >> 3;
+// codes (B * nf * nvf, Q; unpadded) -> summed codebook rows (nvf * D per face) -> halo image of the first convolution; never stored as fp32
+__global__ void __launch_bounds__(256) dequantize_rvq_halo_kernel(const int64_t* __restrict__ codes, const float* __restrict__ codebook,
+                                                                  const uint8_t* __restrict__ valid, int R, int P, int lead, int nvf, int Q, int D, int halo,
+                                                                  uint8_t* __restrict__ image) {
+  const int C = nvf * D, nf = P - lead;
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
   for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
-    const Lane84 l = lane84(g, R, nf);
+    const Lane84 l = lane84(g, R, P);
     if (!l.active) continue;
     const bool ok = valid[l.row] != 0;
+    const long long face = (long long)l.b * nf + (l.row - (long long)l.b * P - lead);
     for (int col = l.colsub * 8; col < C; col += 32) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (ok) {
         const int slot = col / D, d = col - slot * D;
-        const long long tok = l.row * nvf + slot;
+        const long long tok = face * nvf + slot;
         for (int q = 0; q < Q; ++q) {
           const long long code = codes[tok * Q + q];
           if (code >= 0) {
@@ -343,19 +353,20 @@ __global__ void __launch_bounds__(256) dequantize_rvq_im2col_kernel(const int64_
           }
         }
       }
-      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+      emit_halo(image, C, halo, n_tiles, l.row, col, v);
     }
   }
 }
 
-// init_decoder_conv tail + the first block's image: y = LayerNorm(silu(x)) -> out (fp32, the residual input) and im2col image.
-// Masked faces: zeros in both.
-__global__ void __launch_bounds__(256) silu_layernorm_im2col_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, int R, int nf, int C,
-                                                                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                                                    float* __restrict__ out, int k, uint8_t* __restrict__ image) {
-  const long long groups = ((long long)R + 7) >> 3;
+// init_decoder_conv tail + the first block's image: y = LayerNorm(silu(x)) -> out (fp32, the residual input) and halo image.
+// Non-valid rows: zeros in both.
+__global__ void __launch_bounds__(256) silu_layernorm_halo_kernel(const float* __restrict__ x, const uint8_t* __restrict__ valid, int R, int P, int C,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                  float* __restrict__ out, int halo, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
+  const float inv_c = 1.f / (float)C;
   for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
-    const Lane84 l = lane84(g, R, nf);
+    const Lane84 l = lane84(g, R, P);
     const bool ok = l.active && valid[l.row] != 0;
     const float* xr = x + (size_t)(l.active ? l.row : 0) * C;
     float sum = 0.f;
@@ -364,19 +375,19 @@ __global__ void __launch_bounds__(256) silu_layernorm_im2col_kernel(const float*
         float v[8];
         load8(xr + col, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sum += silu_rn(v[i]);
+        for (int i = 0; i < 8; ++i) sum += silu_fast(v[i]);
       }
-    const float mean = row_sum84(sum) / (float)C;
+    const float mean = row_sum84(sum) * inv_c;
     float var = 0.f;
     if (ok)
       for (int col = l.colsub * 8; col < C; col += 32) {
         float v[8];
         load8(xr + col, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float d = silu_rn(v[i]) - mean; var = fmaf(d, d, var); }
+        for (int i = 0; i < 8; ++i) { const float d = silu_fast(v[i]) - mean; var = fmaf(d, d, var); }
       }
-    var = row_sum84(var) / (float)C;
-    const float rstd = 1.f / sqrtf(var + eps);
+    var = row_sum84(var) * inv_c;
+    const float rstd = rsqrtf(var + eps);
     if (!l.active) continue;
     for (int col = l.colsub * 8; col < C; col += 32) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -386,21 +397,21 @@ __global__ void __launch_bounds__(256) silu_layernorm_im2col_kernel(const float*
         load8(gamma + col, gm);
         load8(beta + col, bt);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = (silu_rn(v[i]) - mean) * rstd * gm[i] + bt[i];
+        for (int i = 0; i < 8; ++i) v[i] = fmaf((silu_fast(v[i]) - mean) * rstd, gm[i], bt[i]);
       }
       store8(out + (size_t)l.row * C + col, v);
-      if (image) emit_taps(image, C, k, l.row, l.n, nf, col, v);
+      if (image) emit_halo(image, C, halo, n_tiles, l.row, col, v);
     }
   }
 }
 
-// Block tail feeding the next convolution: silu(PixelNorm(h)) written ONLY as the im2col image (h: row stride ld, left untouched)
-__global__ void __launch_bounds__(256) pixelnorm_silu_im2col_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int R, int nf,
-                                                                    int C, float eps, int k, uint8_t* __restrict__ image) {
-  const long long groups = ((long long)R + 7) >> 3;
+// Block tail feeding the next convolution: silu(PixelNorm(h)) written ONLY as the halo image (h: row stride ld, left untouched)
+__global__ void __launch_bounds__(256) pixelnorm_silu_halo_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int R, int P,
+                                                                  int C, float eps, int halo, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
   const float root_c = sqrtf((float)C);
   for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
-    const Lane84 l = lane84(g, R, nf);
+    const Lane84 l = lane84(g, R, P);
     const bool ok = l.active && valid[l.row] != 0;
     const float* hr = h + (size_t)(l.active ? l.row : 0) * ld;
     float ss = 0.f;
@@ -411,78 +422,85 @@ __global__ void __launch_bounds__(256) pixelnorm_silu_im2col_kernel(const float*
 #pragma unroll
         for (int i = 0; i < 8; ++i) ss = fmaf(v[i], v[i], ss);
       }
-    const float den = fmaxf(sqrtf(row_sum84(ss)), eps);
+    const float scale = root_c / fmaxf(sqrtf(row_sum84(ss)), eps);
     if (!l.active) continue;
     for (int col = l.colsub * 8; col < C; col += 32) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (ok) {
         load8(hr + col, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = silu_rn(__fdiv_rn(v[i], den) * root_c);
+        for (int i = 0; i < 8; ++i) v[i] = silu_fast(v[i] * scale);
       }
-      emit_taps(image, C, k, l.row, l.n, nf, col, v);
+      emit_halo(image, C, halo, n_tiles, l.row, col, v);
     }
   }
 }
 
-// Second Block tail + SqueezeExcite's mean, without storing the activation: den[row] = max(||h[row]||, eps) and, per
-// (mesh, slice of its faces), the column sums of silu(PixelNorm(h)) over the valid faces of the slice.  CTA (mesh, slice); a warp
+// Second Block tail + SqueezeExcite's mean, without storing the activation: scale[row] = sqrt(C) / max(||h[row]||, eps) and, per
+// (mesh, slice of its faces), the column sums of silu(h * scale) over the valid faces of the slice.  CTA (mesh, slice); a warp
 // per face, lane owns columns lane * 4 + 128 j; rows are added in ascending order per warp and the 8 warps are combined in a fixed
-// order, so the result does not depend on scheduling.
+// order, so the result does not depend on scheduling.  Rows of mesh b: b * P + lead + n.
 constexpr int SE_MAX_C = 1024;
-__global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int nf, int C,
-                                                               float eps, int S, float* __restrict__ den_out, float* __restrict__ part,
+template <int NJ>   // NJ = ceil(C / 128) float4 per lane
+__global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int P, int lead, int C,
+                                                               float eps, int S, float* __restrict__ scale_out, float* __restrict__ part,
                                                                int* __restrict__ part_cnt) {
-  __shared__ float4 sm[8][SE_MAX_C / 4];
+  extern __shared__ float4 sm_dyn[];   // [8 warps][NJ * 32]
   __shared__ int cnt[8];
   const int b = blockIdx.x, s = blockIdx.y, lane = lane_id(), w = warp_id();
+  const int nf = P - lead;
   const int per = (nf + S - 1) / S;
   const int n0 = s * per, n1 = min(nf, n0 + per);
+  const long long base = (long long)b * P + lead;
   const float root_c = sqrtf((float)C);
-  const int nj = (C + 127) >> 7;
-  float4 acc[SE_MAX_C / 128];
+  float4 acc[NJ];
 #pragma unroll
-  for (int j = 0; j < SE_MAX_C / 128; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = 0; j < NJ; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   int n_valid = 0;
-  for (int n = n0 + w; n < n1; n += 8) {
-    const long long row = (long long)b * nf + n;
-    if (!valid[row]) {
-      if (lane == 0) den_out[row] = 1.f;
-      continue;
+  // the next row's loads are issued before this row's reduction (one row of latency hidden per warp)
+  float4 nxt[NJ];
+  bool nxt_ok = false;
+  auto fetch = [&](int n) {
+    nxt_ok = n < n1 && valid[base + n] != 0;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const int c = lane * 4 + j * 128;
+      nxt[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nxt_ok && c < C) nxt[j] = *reinterpret_cast<const float4*>(h + (size_t)(base + n) * ld + c);
     }
+  };
+  fetch(n0 + w);
+  for (int n = n0 + w; n < n1; n += 8) {
+    float4 v[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) v[j] = nxt[j];
+    const bool ok = nxt_ok;
+    fetch(n + 8);
+    if (!ok) continue;      // scale is only read on valid rows
     ++n_valid;
-    const float* hr = h + (size_t)row * ld;
-    float4 v[SE_MAX_C / 128];
     float ss = 0.f;
 #pragma unroll
-    for (int j = 0; j < SE_MAX_C / 128; ++j) {
-      const int c = lane * 4 + j * 128;
-      v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (j < nj && c < C) v[j] = *reinterpret_cast<const float4*>(hr + c);
+    for (int j = 0; j < NJ; ++j) {
       ss = fmaf(v[j].x, v[j].x, ss); ss = fmaf(v[j].y, v[j].y, ss); ss = fmaf(v[j].z, v[j].z, ss); ss = fmaf(v[j].w, v[j].w, ss);
     }
-    const float den = fmaxf(sqrtf(warp_sum(ss)), eps);
-    if (lane == 0) den_out[row] = den;
+    const float scale = root_c / fmaxf(sqrtf(warp_sum(ss)), eps);
+    if (lane == 0) scale_out[base + n] = scale;
 #pragma unroll
-    for (int j = 0; j < SE_MAX_C / 128; ++j) {
-      if (j < nj) {
-        acc[j].x += silu_rn(__fdiv_rn(v[j].x, den) * root_c);
-        acc[j].y += silu_rn(__fdiv_rn(v[j].y, den) * root_c);
-        acc[j].z += silu_rn(__fdiv_rn(v[j].z, den) * root_c);
-        acc[j].w += silu_rn(__fdiv_rn(v[j].w, den) * root_c);
-      }
+    for (int j = 0; j < NJ; ++j) {   // padding columns hold 0: silu(0) = 0
+      acc[j].x += silu_fast(v[j].x * scale);
+      acc[j].y += silu_fast(v[j].y * scale);
+      acc[j].z += silu_fast(v[j].z * scale);
+      acc[j].w += silu_fast(v[j].w * scale);
     }
   }
 #pragma unroll
-  for (int j = 0; j < SE_MAX_C / 128; ++j)
-    if (j < nj) sm[w][lane + j * 32] = acc[j];
+  for (int j = 0; j < NJ; ++j) sm_dyn[w * (NJ * 32) + lane + j * 32] = acc[j];
   if (lane == 0) cnt[w] = n_valid;
   __syncthreads();
   float* out = part + ((size_t)b * S + s) * C;
   for (int c4 = threadIdx.x; c4 < (C >> 2); c4 += blockDim.x) {
-    float4 t = sm[0][c4];
-    for (int i = 1; i < 8; ++i) { const float4 o = sm[i][c4]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
-    // silu(PixelNorm(0)) = 0 for the lanes' padding columns; columns >= C are never read (c4 < C / 4)
+    float4 t = sm_dyn[c4];
+    for (int i = 1; i < 8; ++i) { const float4 o = sm_dyn[i * (NJ * 32) + c4]; t.x += o.x; t.y += o.y; t.z += o.z; t.w += o.w; }
     reinterpret_cast<float4*>(out)[c4] = t;
   }
   if (threadIdx.x == 0) {
@@ -492,51 +510,76 @@ __global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __re
   }
 }
 
-// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2) with mean[b] = (sum of the S slice sums) / max(#valid faces, 1e-5); one CTA per
-// mesh, a warp per output (coalesced weight rows, shuffle reduction)
-__global__ void __launch_bounds__(256) se_gate_slices_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
-                                                             const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2,
-                                                             const float* __restrict__ b2, float* __restrict__ gate) {
+// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2) with mean[b] = (sum of the S slice sums) / max(#valid faces, 1e-5); one CTA of
+// 1024 threads per mesh.  The whole thing is a chain of three dependent global-memory round trips (slice sums, W1, W2), so every
+// phase is spread over all threads with all of a thread's loads independent: both weight matrices are read TRANSPOSED (w1t (C,
+// inner), w2t (inner, C), built once by the host side: a warp reads consecutive floats), a thread owns (part of the reduction
+// range, output), and the parts are added in a fixed order through shared memory.
+__global__ void __launch_bounds__(1024) se_gate_slices_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
+                                                              const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                              const float* __restrict__ b2, float* __restrict__ gate) {
   __shared__ float sm[SE_MAX_C];
+  __shared__ float sq[1024];
   __shared__ float sh[256];
-  const int b = blockIdx.x, lane = lane_id(), w = warp_id();
+  const int b = blockIdx.x, tid = threadIdx.x;
   int nv = 0;
   for (int s = 0; s < S; ++s) nv += part_cnt[b * S + s];
   const float inv = 1.f / fmaxf((float)nv, 1e-5f);
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+  for (int c = tid; c < C; c += 1024) {
     float t = 0.f;
     for (int s = 0; s < S; ++s) t += part[((size_t)b * S + s) * C + c];
     sm[c] = t * inv;
   }
   __syncthreads();
-  for (int j = w; j < inner; j += 8) {
+  {  // hidden = silu(W1 mean + b1): thread (part p of the C range, hidden unit j)
+    const int jn = (inner + 31) & ~31, parts = 1024 / jn, p = tid / jn, j = tid - p * jn;
+    const int span = (C + parts - 1) / parts;
     float t = 0.f;
-    for (int c = lane; c < C; c += 32) t = fmaf(w1[(size_t)j * C + c], sm[c], t);
-    t = warp_sum(t) + b1[j];
-    if (lane == 0) sh[j] = silu_rn(t);
+    if (p < parts && j < inner) {
+      const int c1 = min(C, (p + 1) * span);
+#pragma unroll 16
+      for (int c = p * span; c < c1; ++c) t = fmaf(w1t[(size_t)c * inner + j], sm[c], t);
+    }
+    sq[tid] = t;
+    __syncthreads();
+    if (tid < inner) {
+      float a = b1[tid];
+      for (int q = 0; q < parts; ++q) a += sq[q * jn + tid];
+      sh[tid] = silu_fast(a);
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int c = w; c < C; c += 8) {
+  {  // gate = sigmoid(W2 hidden + b2): thread (part p of the hidden range, column c); C > 1024 is refused by the launcher
+    const int cn = (C + 31) & ~31, parts = 1024 / cn, p = tid / cn, c = tid - p * cn;
+    const int span = (inner + parts - 1) / parts;
     float t = 0.f;
-    for (int j = lane; j < inner; j += 32) t = fmaf(w2[(size_t)c * inner + j], sh[j], t);
-    t = warp_sum(t) + b2[c];
-    if (lane == 0) gate[(size_t)b * C + c] = 1.f / (1.f + expf(-t));
+    if (p < parts && c < C) {
+      const int j1 = min(inner, (p + 1) * span);
+#pragma unroll 16
+      for (int j = p * span; j < j1; ++j) t = fmaf(w2t[(size_t)j * C + c], sh[j], t);
+    }
+    sq[tid] = t;
+    __syncthreads();
+    if (tid < C) {
+      float a = b2[tid];
+      for (int q = 0; q < parts; ++q) a += sq[q * cn + tid];
+      gate[(size_t)b * C + tid] = __fdividef(1.f, 1.f + __expf(-a));
+    }
   }
 }
 
-// ResnetBlock tail + the next convolution's image: out = silu(h / den * sqrt(C)) * gate[b] + res (den == NULL: out = h * gate[b] + res)
-// on valid faces, zeros elsewhere; out as fp32 (the next residual input) and, when image != NULL, as the im2col image of kernel k.
-__global__ void __launch_bounds__(256) gate_residual_im2col_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ den,
-                                                                   const float* __restrict__ gate, const float* __restrict__ res, int ldres,
-                                                                   const uint8_t* __restrict__ valid, int R, int nf, int C, float* __restrict__ out, int k,
-                                                                   uint8_t* __restrict__ image) {
-  const long long groups = ((long long)R + 7) >> 3;
-  const float root_c = sqrtf((float)C);
+// ResnetBlock tail + the next convolution's image: out = silu(h * scale[row]) * gate[b] + res (scale == NULL: h * gate[b] + res)
+// on valid rows, zeros elsewhere; out as fp32 (the next residual input) and, when image != NULL, as a halo image.
+__global__ void __launch_bounds__(256) gate_residual_halo_kernel(const float* __restrict__ h, int ldh, const float* __restrict__ scale,
+                                                                 const float* __restrict__ gate, const float* __restrict__ res, int ldres,
+                                                                 const uint8_t* __restrict__ valid, int R, int P, int C, float* __restrict__ out, int halo,
+                                                                 uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
   for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
-    const Lane84 l = lane84(g, R, nf);
+    const Lane84 l = lane84(g, R, P);
     if (!l.active) continue;
     const bool ok = valid[l.row] != 0;
-    const float dn = (ok && den) ? den[l.row] : 1.f;
+    const float sc = (ok && scale) ? scale[l.row] : 1.f;
     for (int col = l.colsub * 8; col < C; col += 32) {
       float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       if (ok) {
@@ -545,13 +588,50 @@ __global__ void __launch_bounds__(256) gate_residual_im2col_kernel(const float* 
         load8(gate + (size_t)l.b * C + col, gt);
         load8(res + (size_t)l.row * ldres + col, rs);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = den ? silu_rn(__fdiv_rn(v[i], dn) * root_c) : v[i];
-          v[i] = fmaf(a, gt[i], rs[i]);
-        }
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(scale ? silu_fast(v[i] * sc) : v[i], gt[i], rs[i]);
       }
       store8(out + (size_t)l.row * C + col, v);
-      if (image) emit_taps(image, C, k, l.row, l.n, nf, col, v);
+      if (image) emit_halo(image, C, halo, n_tiles, l.row, col, v);
+    }
+  }
+}
+
+// logits in the padded row space -> coordinates / bins of the UNPADDED faces (b * nf + n); same arithmetic as argmax_coords_kernel
+__global__ void __launch_bounds__(256) argmax_coords_padded_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ valid, int B, int P, int lead,
+                                                                   int ncoord, int nbins, float lo, float hi, float* __restrict__ coords,
+                                                                   int64_t* __restrict__ bins) {
+  const int lane = lane_id(), nf = P - lead;
+  const long long total = (long long)B * nf * ncoord;
+  const int wpb = blockDim.x >> 5;
+  for (long long item = (long long)blockIdx.x * wpb + warp_id(); item < total; item += (long long)gridDim.x * wpb) {
+    const long long face = item / ncoord;
+    const int coord = (int)(item - face * ncoord);
+    const int b = (int)(face / nf);
+    const long long row = (long long)b * P + lead + (face - (long long)b * nf);
+    if (!valid[row]) {
+      if (lane == 0) { coords[item] = __int_as_float(0x7fc00000); if (bins) bins[item] = 0; }
+      continue;
+    }
+    const float* lr = logits + ((size_t)row * ncoord + coord) * nbins;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = lane; j < nbins; j += 32) {
+      const float v = lr[j];
+      if (v > best || (v == best && j < bi)) { best = v; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      if (bi == 0x7fffffff) bi = 0;
+      float t = (float)bi;
+      t = __fadd_rn(t, 0.5f);
+      t = __fdiv_rn(t, (float)nbins);
+      coords[item] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+      if (bins) bins[item] = bi;
     }
   }
 }
@@ -645,78 +725,118 @@ int meshtok_dec_argmax_coords(const float* logits, const uint8_t* valid, int R, 
   return MESHTOK_OK;
 }
 
-/* ---- fused stages (every producer writes the next convolution's image) ---- */
+/* ---- fused stages: padded row space, halo images (see the comment above the kernels) ---- */
 int meshtok_dec_se_slices(int B, int nf) {
   if (B < 1 || nf < 1) return 1;
-  int S = (148 * 4 + B - 1) / B;
+  int S = (148 * 4) / B;               /* one wave of four 8-warp CTAs per SM */
   const int most = (nf + 15) / 16;     /* at least 16 faces per slice */
   if (S > most) S = most;
   if (S > 64) S = 64;
   return S < 1 ? 1 : S;
 }
 
-int meshtok_dec_rows_im2col(const float* x, int ld, const uint8_t* valid, int R, int nf, int C, int k, void* image, meshtok_stream_t stream) {
-  MT_CHECK_ARG(x && valid && image && R >= 0 && nf >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && (k & 1) == 1, "rows_im2col: width %d must be a multiple of 32, kernel %d odd", C, k);
+int meshtok_halo_image_bytes(int R, int C, int halo, size_t* bytes) {
+  MT_CHECK_ARG(bytes && R >= 0 && C > 0 && C % 32 == 0 && halo >= 0 && halo <= 8, "halo image: width %d must be a multiple of 32, halo %d in [0, 8]", C, halo);
+  *bytes = tc::halo_image_bytes(R, C, halo);
+  return MESHTOK_OK;
+}
+
+int meshtok_conv1d(const void* a_halo_image, const void* w_image, const float* bias, float* out, int R, int N, int C_in, int k, int halo,
+                   meshtok_stream_t stream) {
+  MT_CHECK_ARG(a_halo_image && w_image && out && R >= 0 && N > 0 && C_in > 0, "conv1d: bad arguments");
+  return launch_conv_tc(a_halo_image, C_in, k, halo, w_image, bias, out, N, R, static_cast<cudaStream_t>(stream));
+}
+
+#define MT_ROWSPACE_OK(R, P, lead) ((R) >= 0 && (lead) >= 0 && (P) > (lead) && ((R) - (lead)) % (P) == 0)
+
+int meshtok_dec_rows_halo(const float* x, int ld, const uint8_t* valid, int R, int P, int lead, int C, int halo, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && image && MT_ROWSPACE_OK(R, P, lead) && C % 32 == 0 && ld >= C && ld % 4 == 0 && halo >= 0 && halo <= lead,
+               "rows_halo: width %d must be a multiple of 32, R = B * P + lead, halo <= lead", C);
   if (R == 0) return MESHTOK_OK;
-  rows_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, valid, R, nf, C, k, static_cast<uint8_t*>(image));
+  rows_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, ld, valid, R, P, lead, C, halo, static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int meshtok_dec_dequantize_rvq_im2col(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int nf, int nvf, int Q, int D, int k,
-                                      void* image, meshtok_stream_t stream) {
-  MT_CHECK_ARG(codes && codebook && valid && image && R >= 0 && nf >= 1 && nvf >= 1 && Q >= 1 && D % 8 == 0 && (nvf * D) % 32 == 0 && (k & 1) == 1,
-               "dequantize_rvq_im2col: D %d must be a multiple of 8, nvf * D of 32, kernel %d odd", D, k);
+int meshtok_dec_dequantize_rvq_halo(const int64_t* codes, const float* codebook, const uint8_t* valid, int R, int P, int lead, int nvf, int Q, int D,
+                                    int halo, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(codes && codebook && valid && image && MT_ROWSPACE_OK(R, P, lead) && nvf >= 1 && Q >= 1 && D % 8 == 0 && (nvf * D) % 32 == 0 && halo >= 0 &&
+                   halo <= lead,
+               "dequantize_rvq_halo: D %d must be a multiple of 8, nvf * D of 32, R = B * P + lead, halo <= lead", D);
   if (R == 0) return MESHTOK_OK;
-  dequantize_rvq_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, codebook, valid, R, nf, nvf, Q, D, k,
-                                                                                             static_cast<uint8_t*>(image));
+  dequantize_rvq_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(codes, codebook, valid, R, P, lead, nvf, Q, D, halo,
+                                                                                           static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int meshtok_dec_silu_layernorm_im2col(const float* x, const uint8_t* valid, int R, int nf, int C, const float* gamma, const float* beta, float eps,
-                                      float* out, int k, void* image, meshtok_stream_t stream) {
-  MT_CHECK_ARG(x && valid && gamma && beta && out && R >= 0 && nf >= 1 && C % 32 == 0 && (k & 1) == 1, "silu_layernorm_im2col: width %d must be a multiple of 32", C);
+int meshtok_dec_silu_layernorm_halo(const float* x, const uint8_t* valid, int R, int P, int C, const float* gamma, const float* beta, float eps,
+                                    float* out, int halo, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(x && valid && gamma && beta && out && R >= 0 && P >= 1 && C % 32 == 0 && halo >= 0 && halo <= 8, "silu_layernorm_halo: width %d must be a multiple of 32", C);
   if (R == 0) return MESHTOK_OK;
-  silu_layernorm_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, valid, R, nf, C, gamma, beta, eps, out, k,
-                                                                                             static_cast<uint8_t*>(image));
+  silu_layernorm_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, valid, R, P, C, gamma, beta, eps, out, halo,
+                                                                                           static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int meshtok_dec_pixelnorm_silu_im2col(const float* h, int ld, const uint8_t* valid, int R, int nf, int C, float eps, int k, void* image,
-                                      meshtok_stream_t stream) {
-  MT_CHECK_ARG(h && valid && image && R >= 0 && nf >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && (k & 1) == 1, "pixelnorm_silu_im2col: width %d must be a multiple of 32", C);
+int meshtok_dec_pixelnorm_silu_halo(const float* h, int ld, const uint8_t* valid, int R, int P, int C, float eps, int halo, void* image,
+                                    meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && valid && image && R >= 0 && P >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && halo >= 0 && halo <= 8, "pixelnorm_silu_halo: width %d must be a multiple of 32", C);
   if (R == 0) return MESHTOK_OK;
-  pixelnorm_silu_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ld, valid, R, nf, C, eps, k, static_cast<uint8_t*>(image));
+  pixelnorm_silu_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ld, valid, R, P, C, eps, halo, static_cast<uint8_t*>(image));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int nf, int C, float eps, int inner, const float* w1,
-                                              const float* b1, const float* w2, const float* b2, float* den, float* slice_ws, float* gate,
-                                              meshtok_stream_t stream) {
-  MT_CHECK_ARG(h && valid && w1 && b1 && w2 && b2 && den && slice_ws && gate && C % 4 == 0 && C <= SE_MAX_C && inner <= 256 && ld >= C && ld % 4 == 0,
+int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int P, int lead, int C, float eps, int inner,
+                                              const float* w1t, const float* b1, const float* w2t, const float* b2, float* scale, float* slice_ws,
+                                              float* gate, meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && valid && w1t && b1 && w2t && b2 && scale && slice_ws && gate && C % 4 == 0 && C <= SE_MAX_C && inner >= 1 && inner <= 256 && ld >= C &&
+                   ld % 4 == 0 && lead >= 0 && P > lead,
                "pixelnorm_squeeze_excite_gate: bad arguments (C %% 4 == 0, C <= %d, inner <= 256)", SE_MAX_C);
   if (B == 0) return MESHTOK_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int S = meshtok_dec_se_slices(B, nf);
+  const int S = meshtok_dec_se_slices(B, P - lead);
   int* cnt = reinterpret_cast<int*>(slice_ws + (size_t)B * S * C);
-  pixelnorm_colsum_kernel<<<dim3(B, S), 256, 0, s>>>(h, ld, valid, nf, C, eps, S, den, slice_ws, cnt);
+  const int nj = (C + 127) / 128;
+  const size_t sm_bytes = (size_t)8 * nj * 32 * sizeof(float4);
+#define MT_COLSUM(NJ) pixelnorm_colsum_kernel<NJ><<<dim3(B, S), 256, sm_bytes, s>>>(h, ld, valid, P, lead, C, eps, S, scale, slice_ws, cnt)
+  switch (nj) {
+    case 1: MT_COLSUM(1); break;
+    case 2: MT_COLSUM(2); break;
+    case 3: MT_COLSUM(3); break;
+    case 4: MT_COLSUM(4); break;
+    case 5: MT_COLSUM(5); break;
+    case 6: MT_COLSUM(6); break;
+    case 7: MT_COLSUM(7); break;
+    default: MT_COLSUM(8); break;
+  }
+#undef MT_COLSUM
   MT_CHECK_LAUNCH();
-  se_gate_slices_kernel<<<B, 256, 0, s>>>(slice_ws, cnt, S, C, inner, w1, b1, w2, b2, gate);
+  se_gate_slices_kernel<<<B, 1024, 0, s>>>(slice_ws, cnt, S, C, inner, w1t, b1, w2t, b2, gate);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int meshtok_dec_gate_residual_im2col(const float* h, int ldh, const float* den, const float* gate, const float* res, int ldres, const uint8_t* valid,
-                                     int R, int nf, int C, float* out, int k, void* image, meshtok_stream_t stream) {
-  MT_CHECK_ARG(h && gate && res && valid && out && R >= 0 && nf >= 1 && C % 32 == 0 && ldh >= C && ldh % 4 == 0 && ldres >= C && ldres % 4 == 0 &&
-                   (image == nullptr || (k & 1) == 1),
-               "gate_residual_im2col: width %d must be a multiple of 32", C);
+int meshtok_dec_gate_residual_halo(const float* h, int ldh, const float* scale, const float* gate, const float* res, int ldres, const uint8_t* valid,
+                                   int R, int P, int C, float* out, int halo, void* image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(h && gate && res && valid && out && R >= 0 && P >= 1 && C % 32 == 0 && ldh >= C && ldh % 4 == 0 && ldres >= C && ldres % 4 == 0 && halo >= 0 &&
+                   halo <= 8,
+               "gate_residual_halo: width %d must be a multiple of 32", C);
   if (R == 0) return MESHTOK_OK;
-  gate_residual_im2col_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, den, gate, res, ldres, valid, R, nf, C, out, k,
-                                                                                            static_cast<uint8_t*>(image));
+  gate_residual_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ldh, scale, gate, res, ldres, valid, R, P, C, out, halo,
+                                                                                          static_cast<uint8_t*>(image));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
+int meshtok_dec_argmax_coords_padded(const float* logits, const uint8_t* valid, int B, int P, int lead, int ncoord, int nbins, float lo, float hi,
+                                     float* coords, int64_t* bins, meshtok_stream_t stream) {
+  MT_CHECK_ARG(logits && valid && coords && B >= 0 && lead >= 0 && P > lead && ncoord >= 1 && nbins >= 1, "argmax_coords_padded: bad arguments");
+  if (B == 0) return MESHTOK_OK;
+  argmax_coords_padded_kernel<<<grid_for((long long)B * (P - lead) * ncoord, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, B, P, lead, ncoord,
+                                                                                                                             nbins, lo, hi, coords, bins);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

@@ -150,6 +150,8 @@ int linear_tc_ssq_parts(int N);   // (column parts per pass) * passes of an N-wi
 int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                      int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream);
+int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, float* C, int N, int m_max,
+                   cudaStream_t stream);   // Conv1d over the rows of a halo image, see linear_tc.cu
 size_t rows_image_bytes(long long rows, int K);
 int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream);
 

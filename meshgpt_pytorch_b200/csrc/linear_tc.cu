@@ -62,9 +62,12 @@ struct Cfg {
   static constexpr uint32_t SMEM_TOTAL = 227 * 1024;
   // stage = own A block (hi + lo, 16 KB) + the W rows this CTA stages (hi + lo); as many stages as fit, the smaller the
   // pass the deeper the ring (a CTA pair's stage round trip crosses the cluster twice and needs the depth)
-  __host__ __device__ static constexpr uint32_t stage_bytes(int NT) { return 2 * A_PART + 2 * (uint32_t)(PAIR ? NT / 2 : NT) * KC * 2; }
-  __host__ __device__ static constexpr int stages(int NT) {
-    const int n = (int)((SMEM_TOTAL - RING_OFF) / stage_bytes(NT));
+  // (a_slot: bytes reserved for the A block; 16 KB for the plain image, 128 * (128 + 2 halo) for a halo image)
+  __host__ __device__ static constexpr uint32_t stage_bytes(int NT, uint32_t a_slot = 2 * A_PART) {
+    return a_slot + 2 * (uint32_t)(PAIR ? NT / 2 : NT) * KC * 2;
+  }
+  __host__ __device__ static constexpr int stages(int NT, uint32_t a_slot = 2 * A_PART) {
+    const int n = (int)((SMEM_TOTAL - RING_OFF) / stage_bytes(NT, a_slot));
     return n < MAX_STAGES ? n : MAX_STAGES;
   }
 };
@@ -89,7 +92,12 @@ struct LinArgs {
   float* ssq_out;           // (M, CPARTS * passes): sum of squares of this warp's part of every output row, or null
   const float* row_ssq;     // (M, row_ssq_parts): parts of |x_row|^2 of the INPUT rows; C = acc / max(|x|, 1e-12) + bias
   int row_ssq_parts;
+  // Conv1d over the row sequence (decode path): a1_image is a HALO image (tc::halo_*): every (128-row tile, 32-column chunk) block
+  // holds rows -halo .. 128 + halo of the tile with consecutive rows 16 bytes apart, so tap t of the kernel is the SAME block read
+  // through a descriptor that starts t * 16 bytes further (LBO = rows * 16, SBO = 128).  K = taps * K1, W columns tap-major.
+  int conv, taps, halo;
 };
+__host__ __device__ inline int lin_chunks(const LinArgs& a) { return (a.conv ? a.taps : 1) * (a.K1 / KC) + a.K2 / KC; }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -149,8 +157,9 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nphase = g.nphase;
   const int ring_nt = nphase == 2 ? max(g.p[0].NT, g.p[1].NT) : g.p[0].NT;   // the ring is laid out for the wider phase
-  const int STAGES = G::stages(ring_nt);
-  const uint32_t stage_bytes = G::stage_bytes(ring_nt);
+  const uint32_t a_slot = g.p[0].conv ? tc::halo_block_bytes(g.p[0].halo) : 2 * A_PART;   // conv: single phase only
+  const int STAGES = G::stages(ring_nt, a_slot);
+  const uint32_t stage_bytes = G::stage_bytes(ring_nt, a_slot);
   uint8_t* ring = smem + G::RING_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::BAR_OFF);
   uint64_t* full = bars;                        // [STAGES]  producer expect_tx (+ in a pair, on the leader: the peer's forwarded arrival)
@@ -210,7 +219,9 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       seq.get(j, phase, grp, pass, ti);
       const LinArgs& a = g.p[phase];
       const int kch1 = a.K1 / KC, kch2 = a.K2 / KC;
-      const int kchunks = kch1 + kch2;
+      const int kchunks = lin_chunks(a);
+      const int taps = a.conv ? a.taps : 1;
+      const uint32_t a_blk = a.conv ? a_slot : IMG_BLOCK;
       const uint32_t w_part = (uint32_t)a.NT * KC * 2;          // hi (or lo) bytes of one W chunk
       const uint32_t w_mine = PAIR ? w_part / 2 : w_part;       // ... of the rows this CTA stages
       const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
@@ -221,24 +232,27 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       }
       if (lane == 0) LT_STAMP(0, j);   // producer: free to issue this unit's loads
       const uint8_t* wsrc = a.w_image + (size_t)pass * kchunks * (2 * w_part) + (size_t)rank * w_mine;
-      const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * IMG_BLOCK;
+      const uint8_t* a1src = a.a1_image + (size_t)m_tile * kch1 * a_blk;
       const uint8_t* a2src = a.a2_image ? a.a2_image + (size_t)m_tile * kch2 * IMG_BLOCK : nullptr;
-      for (int kc = 0; kc < kchunks; ++kc, ++it) {
+      // conv: the block of column chunk ka is staged once per tap (ka outer, tap inner: the re-reads hit L2), with the W chunk of
+      // columns tap * K1 + ka * 32
+      for (int kc = 0, ka = 0, tap = 0; kc < kchunks; ++kc, ++it) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], (have_a ? IMG_BLOCK : 0u) + 2 * w_mine);
+          mbar_arrive_expect_tx(&full[s], (have_a ? a_blk : 0u) + 2 * w_mine);
           uint8_t* stage = ring + s * stage_bytes;
-          const uint8_t* asrc = kc < kch1 ? a1src + (size_t)kc * IMG_BLOCK : a2src + (size_t)(kc - kch1) * IMG_BLOCK;
-          if (have_a) bulk_g2s(stage, asrc, IMG_BLOCK, &full[s]);
-          const uint8_t* wc = wsrc + (size_t)kc * (2 * w_part);
+          const uint8_t* asrc = ka < kch1 ? a1src + (size_t)ka * a_blk : a2src + (size_t)(ka - kch1) * IMG_BLOCK;
+          if (have_a) bulk_g2s(stage, asrc, a_blk, &full[s]);
+          const uint8_t* wc = wsrc + (size_t)(a.conv ? tap * kch1 + ka : kc) * (2 * w_part);
           if (PAIR) {
-            bulk_g2s(stage + 2 * A_PART, wc, w_mine, &full[s]);
-            bulk_g2s(stage + 2 * A_PART + w_mine, wc + w_part, w_mine, &full[s]);
+            bulk_g2s(stage + a_slot, wc, w_mine, &full[s]);
+            bulk_g2s(stage + a_slot + w_mine, wc + w_part, w_mine, &full[s]);
           } else {
-            bulk_g2s(stage + 2 * A_PART, wc, 2 * w_part, &full[s]);
+            bulk_g2s(stage + a_slot, wc, 2 * w_part, &full[s]);
           }
         }
         __syncwarp();
+        if (++tap == taps) { tap = 0; ++ka; }
         if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
       }
       if (lane == 0) LT_STAMP(1, j);   // producer: last load of the unit issued
@@ -259,7 +273,11 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         int phase, grp, pass, ti;
         seq.get(j, phase, grp, pass, ti);
         const LinArgs& a = g.p[phase];
-        const int kchunks = (a.K1 + a.K2) / KC;
+        const int kchunks = lin_chunks(a);
+        const int taps = a.conv ? a.taps : 1;
+        const uint32_t rows_h = (uint32_t)(M_TILE + 2 * a.halo);
+        const uint32_t a_lbo = a.conv ? rows_h * 16 : 128, a_sbo = a.conv ? 128 : SBO;   // halo image: consecutive rows 16 B apart
+        const uint32_t a_lo = a.conv ? rows_h * 64 : A_PART;                              // offset of the lo part inside the block
         const uint32_t w_part = (uint32_t)a.NT * KC * 2;
         const uint32_t w_mine = PAIR ? w_part / 2 : w_part;
         const uint32_t idesc = make_idesc_f16_f32(PAIR ? 2 * M_TILE : M_TILE, a.NT, /*bf16=*/true);
@@ -269,17 +287,17 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         tcgen05_fence_after();
         if (lane == 0) LT_STAMP(3, j);   // MMA: accumulator buffer free
         const uint32_t d = tmem_base + buf * NT_MAX;
-        for (int kc = 0; kc < kchunks; ++kc) {
+        for (int kc = 0, tap = 0; kc < kchunks; ++kc) {
           mbar_wait(&full[s], ph);
           tcgen05_fence_after();
           if (kc == 0 && lane == 0) LT_STAMP(4, j);   // MMA: first stage of the unit has landed
           if (elect_one()) {
-            const uint32_t ah = s0 + s * stage_bytes, al = ah + A_PART;
-            const uint32_t wh = ah + 2 * A_PART, wl = wh + w_mine;
+            const uint32_t ah = s0 + s * stage_bytes + (uint32_t)(tap + a.halo - taps / 2) * 16, al = ah + a_lo;   // tap t = the block read t rows further
+            const uint32_t wh = s0 + s * stage_bytes + a_slot, wl = wh + w_mine;
 #pragma unroll
             for (int k16 = 0; k16 < KC / 16; ++k16) {
-              const uint32_t ko = k16 * 256;
-              const uint64_t dah = make_smem_desc(ah + ko, 128, SBO), dal = make_smem_desc(al + ko, 128, SBO);
+              const uint32_t ko = k16 * 256, koa = k16 * 2 * a_lbo;
+              const uint64_t dah = make_smem_desc(ah + koa, a_lbo, a_sbo), dal = make_smem_desc(al + koa, a_lbo, a_sbo);
               const uint64_t dwh = make_smem_desc(wh + ko, 128, SBO), dwl = make_smem_desc(wl + ko, 128, SBO);
               const uint32_t acc = (kc | k16) != 0 ? 1u : 0u;
               if (PAIR) {
@@ -296,6 +314,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
             else umma_commit(&empty[s]);
           }
           __syncwarp();
+          if (++tap == taps) tap = 0;
           if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
         }
         if (elect_one()) {
@@ -308,8 +327,8 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   } else if (warp == 3) {
     // ===== completion forwarder (peer CTA of a pair): tells the leader that this CTA's copies have landed; lane s follows stage s =====
     if (PAIR && !leader && lane < STAGES) {
-      uint32_t total_it = (uint32_t)seq.n * (uint32_t)((g.p[0].K1 + g.p[0].K2) / KC);
-      if (nphase == 2) total_it += (uint32_t)seq.n * (uint32_t)((g.p[1].K1 + g.p[1].K2) / KC);
+      uint32_t total_it = (uint32_t)seq.n * (uint32_t)lin_chunks(g.p[0]);
+      if (nphase == 2) total_it += (uint32_t)seq.n * (uint32_t)lin_chunks(g.p[1]);
       const uint32_t remote = mapa_shared(smem_u32(&full[lane]), 0);
       uint32_t ph = 0;
       for (uint32_t it = lane; it < total_it; it += STAGES, ph ^= 1) {
@@ -692,6 +711,7 @@ static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a
                          float* C, int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi) {
   MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
   a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
+  a.conv = 0; a.taps = 1; a.halo = 0;
   a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
   if (epi != nullptr && epi->norm_mode == 0) {
     // plain epilogue with the deferred-normalisation extras
@@ -757,6 +777,23 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
   memset(&g, 0, sizeof(g));
   g.nphase = 1;
   int rc = fill_lin_args(g.p[0], a1_image, K1, a2_image, K2, w_image, bias, C, N, m_dev, m_max, relu, epi);
+  if (rc != MESHTOK_OK) return rc;
+  return launch_lin2(g, m_max, stream);
+}
+
+// Conv1d(C_in -> N, kernel `taps`) over the rows of a halo image (padded row space: at least taps / 2 zero rows between two meshes);
+// w_image = image of the (N, taps * C_in) matrix with tap-major columns
+int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, float* C, int N, int m_max,
+                   cudaStream_t stream) {
+  if (m_max == 0) return MESHTOK_OK;
+  MT_CHECK_ARG(taps >= 1 && (taps & 1) == 1 && halo >= taps / 2 && halo <= 8 && C_in % KC == 0, "tcgen05 conv: kernel %d must be odd, halo %d >= kernel / 2 and <= 8, C_in %d a multiple of %d", taps, halo, C_in, KC);
+  LinArgs2 g;
+  memset(&g, 0, sizeof(g));
+  g.nphase = 1;
+  int rc = fill_lin_args(g.p[0], a_halo_image, C_in, nullptr, 0, w_image, bias, C, N, nullptr, m_max, false, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  g.p[0].conv = 1; g.p[0].taps = taps; g.p[0].halo = halo;
+  rc = linear_tc_plan(N, taps * C_in, 0, &g.p[0].passes, &g.p[0].NT);
   if (rc != MESHTOK_OK) return rc;
   return launch_lin2(g, m_max, stream);
 }

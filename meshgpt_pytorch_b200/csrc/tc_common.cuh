@@ -287,5 +287,21 @@ __device__ __forceinline__ void image_store4(uint8_t* img, int K, long long row,
   *reinterpret_cast<uint2*>(p + IMG_PART) = lo;
 }
 
+
+// ---- halo images (Conv1d over the row sequence) ------------------------------------------------------------
+// Same split-bf16 idea, different order inside a (128-row tile, 32-column chunk) block: [hi | lo][4 column groups of 8][128 + 2 halo
+// rows][16 bytes], i.e. CONSECUTIVE ROWS 16 BYTES APART, the tile's rows preceded by the last `halo` rows of the previous tile and
+// followed by the first `halo` rows of the next one (stored twice).  As a UMMA operand that is LBO = rows * 16, SBO = 128, and the
+// tile shifted down by t rows is the same block read from 16 t bytes further - tap t of a convolution needs no im2col copy.
+__host__ __device__ constexpr uint32_t halo_block_bytes(int halo) { return 128u * (uint32_t)(IMG_ROWS + 2 * halo); }
+__host__ __device__ inline size_t halo_image_bytes(long long rows, int C, int halo) {
+  return (size_t)((rows + IMG_ROWS - 1) / IMG_ROWS) * (size_t)(C / IMG_KC) * halo_block_bytes(halo);
+}
+// byte offset of the hi 16-byte group (tile, tile-relative row r in [-halo, 128 + halo), columns col .. col + 7); lo is 64 * rows further
+__device__ __forceinline__ size_t halo_offset(int C, int halo, long long tile, int r, int col) {
+  const uint32_t rows = (uint32_t)(IMG_ROWS + 2 * halo);
+  return ((size_t)tile * (C >> 5) + (col >> 5)) * (128u * rows) + (size_t)(((col >> 3) & 3) * rows + (uint32_t)(r + halo)) * 16u;
+}
+
 }  // namespace tc
 }  // namespace meshtok

@@ -7,11 +7,12 @@ Every Conv1d / Linear runs as a split-bf16 tcgen05 linear (csrc/linear_tc.cu) on
 between are the kernels of csrc/decode.cu, all called through the C ABI (include/meshtok.h, meshtok_dec_*).  PyTorch holds the
 device buffers and nothing else; there is no CPU path.
 
-Default ("fused") schedule, when every width is a multiple of 32: each stage writes the im2col image of the convolution that
+Default ("fused") schedule, when every width is a multiple of 32: NO im2col.  Activations live in a padded row space (separator
+rows between the meshes, zero in every image) and each stage writes its output once, as the "halo image" of the convolution that
 follows it (de-quantise -> image of the k=7 convolution; SiLU+LayerNorm -> x + image; PixelNorm+SiLU -> image only; PixelNorm +
-SqueezeExcite mean without storing the activation; gate * h + res -> x + image), and a block's residual_conv (k=1) rides in the
-same linear as block1.proj (its weight sits in the centre tap of a (2 C_out, 3 C_in) matrix).  6 launches per ResnetBlock instead
-of 10-12.  MESHTOK_DEC_FUSED=0, or a width that is not a multiple of 32, takes the stage-by-stage schedule (same kernels as the
+SqueezeExcite mean without storing the activation; gate * h + res -> x + image); the tcgen05 kernel reads tap t of a kernel from
+the same shared-memory block, one row further (meshtok_conv1d).  A block's residual_conv (k=1) rides in the same launch as
+block1.proj (its weight sits in the centre tap of a (2 C_out, 3 C_in) matrix).  6 launches per ResnetBlock instead of 10-12.  MESHTOK_DEC_FUSED=0, or a width that is not a multiple of 32, takes the stage-by-stage schedule (same kernels as the
 first version; kept for A/B runs and odd widths).
 
     dec = MeshDecoder(autoencoder)                    # same decoder keywords as the reference constructor
@@ -141,7 +142,8 @@ class MeshDecoder(nn.Module):
                 prep["blocks"].append(dict(
                     c1=conv(blk.block1.proj), c2=conv(blk.block2.proj),
                     res=None if isinstance(blk.residual_conv, nn.Identity) else conv(blk.residual_conv),
-                    se=tuple(t.detach().to(**f32).contiguous() for t in (e[0].weight, e[0].bias, e[2].weight, e[2].bias))))
+                    se=tuple(t.detach().to(**f32).contiguous() for t in (e[0].weight, e[0].bias, e[2].weight, e[2].bias)),
+                    se_t=tuple(t.detach().to(**f32).contiguous() for t in (e[0].weight.t(), e[0].bias, e[2].weight.t(), e[2].bias))))
                 last = prep["blocks"][-1]
                 last["c1r"] = conv_with_residual(last["c1"], last["res"]) if last["res"] is not None and last["c1"]["k"] == 3 else None
         self._prep, self._prep_key = prep, key
@@ -184,57 +186,76 @@ class MeshDecoder(nn.Module):
         if os.environ.get("MESHTOK_DEC_FUSED", "1") == "0":
             return False
         widths = [self.init_decoder_conv["0"].out_channels] + [blk.block1.proj.out_channels for blk in self.decoders]
-        return all(w % 32 == 0 for w in widths) and (self.nvf * self.dim_codebook) % 32 == 0 and self.dim_codebook % 8 == 0
+        return (all(w % 32 == 0 for w in widths) and (self.nvf * self.dim_codebook) % 32 == 0 and self.dim_codebook % 8 == 0
+                and self.init_decoder_conv["0"].kernel_size[0] // 2 <= 8)
+
+    @property
+    def lead(self) -> int:
+        """Separator rows in front of every mesh in the padded row space = half width of the widest kernel."""
+        return max(1, self.init_decoder_conv["0"].kernel_size[0] // 2)
+
+    def _padded_valid(self, face_mask: Tensor) -> Tuple[Tensor, int, int]:
+        """face_mask (b, nf) -> (valid bytes of the padded row space (b * P + lead), P, R)."""
+        b, nf = face_mask.shape
+        lead = self.lead
+        P = nf + lead
+        R = b * P + lead
+        valid = torch.zeros(R, dtype=torch.uint8, device=face_mask.device)
+        valid[:b * P].view(b, P)[:, lead:] = face_mask
+        return valid, P, R
 
     @staticmethod
-    def _image(R: int, K: int, dev) -> Tensor:
+    def _halo_image(R: int, Cc: int, halo: int, dev) -> Tensor:
         nbytes = C.c_size_t()
-        check(lib.meshtok_rows_image_bytes(R, K, C.byref(nbytes)))
+        check(lib.meshtok_halo_image_bytes(R, Cc, halo, C.byref(nbytes)))
         return torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
 
     @staticmethod
-    def _linear(img: Tensor, R: int, w: dict) -> Tensor:
+    def _conv1d(img: Tensor, R: int, w: dict) -> Tensor:
         out = torch.empty(R, w["n"], dtype=torch.float32, device=img.device)
-        check(lib.meshtok_linear(None, ptr(img), None, ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], w["k"] * w["c"], 0, 0, stream_ptr()))
+        check(lib.meshtok_conv1d(ptr(img), ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], w["c"], w["k"], w["k"] // 2, stream_ptr()))
         return out
 
-    def _decode_fused(self, init_img: Tensor, valid: Tensor, b: int, nf: int, logits_image: bool):
-        """init_img: im2col image of the (masked) quantized rows for init_decoder_conv.0.  Returns (decoded (R, C) fp32 with zero rows
-        on padded faces, the k=1 image of it for to_coor_logits or None)."""
+    def _decode_fused(self, init_img: Tensor, valid: Tensor, b: int, P: int, R: int, logits_image: bool):
+        """init_img: halo image of the (masked) quantized rows for init_decoder_conv.0, padded row space.  Returns (decoded (R, C) fp32
+        with zero rows on separators / padded faces, the halo-0 image of it for to_coor_logits or None)."""
         p = self._prepare()
-        R, dev = b * nf, init_img.device
+        dev = init_img.device
+        lead = self.lead
         blocks = p["blocks"]
         f32 = dict(dtype=torch.float32, device=dev)
-        x0 = self._linear(init_img, R, p["init"])
+        x0 = self._conv1d(init_img, R, p["init"])
         c = p["init"]["n"]
-        k_next = 3 if blocks else (1 if logits_image else 0)
+        halo = 1 if blocks else 0
+        want = bool(blocks) or logits_image
         x = torch.empty(R, c, **f32)
-        img = self._image(R, k_next * c, dev) if k_next else None
-        check(lib.meshtok_dec_silu_layernorm_im2col(ptr(x0), ptr(valid), R, nf, c, ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, ptr(x), k_next, ptr(img),
-                                                    stream_ptr()))
-        S = lib.meshtok_dec_se_slices(b, nf)
+        img = self._halo_image(R, c, halo, dev) if want else None
+        check(lib.meshtok_dec_silu_layernorm_halo(ptr(x0), ptr(valid), R, P, c, ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, ptr(x), halo, ptr(img),
+                                                  stream_ptr()))
+        S = lib.meshtok_dec_se_slices(b, P - lead)
         for i, blk in enumerate(blocks):
             cout = blk["c1"]["n"]
             if blk["c1r"] is not None:
-                h = self._linear(img, R, blk["c1r"])                 # (R, 2 cout): [block1.proj | residual_conv]
+                h = self._conv1d(img, R, blk["c1r"])                 # (R, 2 cout): [block1.proj | residual_conv]
                 ldh, res_ptr, ldres = 2 * cout, h.data_ptr() + 4 * cout, 2 * cout
             else:
-                h = self._linear(img, R, blk["c1"])
+                h = self._conv1d(img, R, blk["c1"])
                 ldh, res_ptr, ldres = cout, x.data_ptr(), x.shape[1]
-            img2 = self._image(R, 3 * cout, dev)
-            check(lib.meshtok_dec_pixelnorm_silu_im2col(ptr(h), ldh, ptr(valid), R, nf, cout, 1e-4, 3, ptr(img2), stream_ptr()))
-            h2 = self._linear(img2, R, blk["c2"])
-            w1, b1, w2, b2 = blk["se"]
-            den = torch.empty(R, **f32)
+            img2 = self._halo_image(R, cout, 1, dev)
+            check(lib.meshtok_dec_pixelnorm_silu_halo(ptr(h), ldh, ptr(valid), R, P, cout, 1e-4, 1, ptr(img2), stream_ptr()))
+            h2 = self._conv1d(img2, R, blk["c2"])
+            w1, b1, w2, b2 = blk["se_t"]                              # transposed: (C, inner), (inner, C)
+            scale = torch.empty(R, **f32)
             ws = torch.empty(b * S * (cout + 1), **f32)
             gate = torch.empty(b, cout, **f32)
-            check(lib.meshtok_dec_pixelnorm_squeeze_excite_gate(ptr(h2), cout, ptr(valid), b, nf, cout, 1e-4, w1.shape[0], ptr(w1), ptr(b1), ptr(w2),
-                                                                ptr(b2), ptr(den), ptr(ws), ptr(gate), stream_ptr()))
-            k_next = 3 if i + 1 < len(blocks) else (1 if logits_image else 0)
+            check(lib.meshtok_dec_pixelnorm_squeeze_excite_gate(ptr(h2), cout, ptr(valid), b, P, lead, cout, 1e-4, w1.shape[1], ptr(w1), ptr(b1),
+                                                                ptr(w2), ptr(b2), ptr(scale), ptr(ws), ptr(gate), stream_ptr()))
+            last = i + 1 == len(blocks)
+            halo = 0 if last else 1
             out = torch.empty(R, cout, **f32)
-            img = self._image(R, k_next * cout, dev) if k_next else None
-            check(lib.meshtok_dec_gate_residual_im2col(ptr(h2), cout, ptr(den), ptr(gate), res_ptr, ldres, ptr(valid), R, nf, cout, ptr(out), k_next,
-                                                       ptr(img), stream_ptr()))
+            img = self._halo_image(R, cout, halo, dev) if (not last or logits_image) else None
+            check(lib.meshtok_dec_gate_residual_halo(ptr(h2), cout, ptr(scale), ptr(gate), res_ptr, ldres, ptr(valid), R, P, cout, ptr(out), halo,
+                                                     ptr(img), stream_ptr()))
             x = out
         return x, img
 
@@ -273,9 +294,12 @@ class MeshDecoder(nn.Module):
         with torch.cuda.device(dev):
             if self.fused():
                 k = p["init"]["k"]
-                img = self._image(R, k * d, dev)
-                check(lib.meshtok_dec_rows_im2col(ptr(x), d, ptr(valid), R, nf, d, k, ptr(img), stream_ptr()))
-                x, _ = self._decode_fused(img, valid, b, nf, logits_image=False)
+                lead = self.lead
+                vp, P, Rp = self._padded_valid(face_mask)
+                img = self._halo_image(Rp, d, k // 2, dev)
+                check(lib.meshtok_dec_rows_halo(ptr(x), d, ptr(vp), Rp, P, lead, d, k // 2, ptr(img), stream_ptr()))
+                xp, _ = self._decode_fused(img, vp, b, P, Rp, logits_image=False)
+                x = xp[:b * P].view(b, P, -1)[:, lead:].contiguous()
             else:
                 x = self._decode_staged(x, valid, b, nf)
         return x.reshape(b, nf, -1)
@@ -299,29 +323,33 @@ class MeshDecoder(nn.Module):
         dev = codes.device
         valid = face_mask.reshape(R).to(torch.uint8).contiguous()
         with torch.cuda.device(dev):
+            ncoord = nvf * 3
+            coords = torch.empty(b, nf, nvf, 3, dtype=torch.float32, device=dev)
+            bins = torch.empty(b, nf, nvf, 3, dtype=torch.int64, device=dev)
+            lo, hi = self.coor_range
             if self.fused():
                 k, d = p["init"]["k"], nvf * self.dim_codebook
-                img = self._image(R, k * d, dev)
+                lead = self.lead
+                vp, P, Rp = self._padded_valid(face_mask)
+                img = self._halo_image(Rp, d, k // 2, dev)
                 if a.use_residual_lfq:
                     quantized = self.dequantize(codes)
-                    check(lib.meshtok_dec_rows_im2col(ptr(quantized), d, ptr(valid), R, nf, d, k, ptr(img), stream_ptr()))
+                    check(lib.meshtok_dec_rows_halo(ptr(quantized), d, ptr(vp), Rp, P, lead, d, k // 2, ptr(img), stream_ptr()))
                 else:
                     book = a.quantizer.layers[0]._codebook.embed[0].detach().float().contiguous()
-                    check(lib.meshtok_dec_dequantize_rvq_im2col(ptr(codes), ptr(book), ptr(valid), R, nf, nvf, q, self.dim_codebook, k, ptr(img),
-                                                                stream_ptr()))
-                decoded, limg = self._decode_fused(img, valid, b, nf, logits_image=True)
-                logits = self._linear(limg, R, p["logits"])
+                    check(lib.meshtok_dec_dequantize_rvq_halo(ptr(codes), ptr(book), ptr(vp), Rp, P, lead, nvf, q, self.dim_codebook, k // 2,
+                                                              ptr(img), stream_ptr()))
+                decoded, limg = self._decode_fused(img, vp, b, P, Rp, logits_image=True)
+                logits = self._conv1d(limg, Rp, p["logits"])
+                check(lib.meshtok_dec_argmax_coords_padded(ptr(logits), ptr(vp), b, P, lead, ncoord, self.num_discrete_coors, float(lo), float(hi),
+                                                           ptr(coords), ptr(bins), stream_ptr()))
             else:
                 quantized = self.dequantize(codes).reshape(R, nvf * self.dim_codebook)
                 decoded = self._decode_staged(quantized, valid, b, nf)      # rows of padded faces are already zero (:924)
                 ones = torch.ones(R, dtype=torch.uint8, device=dev)        # to_coor_logits is a plain Linear: no neighbours, no mask
                 logits = self._conv(decoded, ones, nf, p["logits"])
-            ncoord = nvf * 3
-            coords = torch.empty(b, nf, nvf, 3, dtype=torch.float32, device=dev)
-            bins = torch.empty(b, nf, nvf, 3, dtype=torch.int64, device=dev)
-            lo, hi = self.coor_range
-            check(lib.meshtok_dec_argmax_coords(ptr(logits), ptr(valid), R, ncoord, self.num_discrete_coors, float(lo), float(hi),
-                                                ptr(coords), ptr(bins), stream_ptr()))
+                check(lib.meshtok_dec_argmax_coords(ptr(logits), ptr(valid), R, ncoord, self.num_discrete_coors, float(lo), float(hi),
+                                                    ptr(coords), ptr(bins), stream_ptr()))
         if return_discrete_codes:
             return coords, bins, face_mask
         return coords, face_mask

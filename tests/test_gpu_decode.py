@@ -79,60 +79,127 @@ def test_decode_full_size_decoder_round_trip():
     assert float(same) >= 0.98, float(same)
 
 
-def _image_bytes(R, K):
+def _halo_bytes(R, c, halo):
     import ctypes as C
     from meshgpt_pytorch_b200._lib import lib, check
     n = C.c_size_t()
-    check(lib.meshtok_rows_image_bytes(R, K, C.byref(n)))
+    check(lib.meshtok_halo_image_bytes(R, c, halo, C.byref(n)))
     return n.value
 
 
-def _live_image(img, R, K):
-    """The bytes of an activation image that belong to rows < R (pad rows of the last 128-row tile are never written)."""
-    full = (R // 128) * (K // 32) * 16384
-    head = img[:full]
-    if R % 128 == 0:
-        return head
-    tail = img[full:].reshape(K // 32, 2, 16, 4, 8, 16)[:, :, :, :, :, :]       # chunk, hi/lo, 8-row group, k group, row, 16 B
-    rows = (torch.arange(16, device=img.device)[:, None] * 8 + torch.arange(8, device=img.device)[None, :]) < (R % 128)
-    keep = rows[None, None, :, None, :, None].expand_as(tail)
-    return torch.cat([head, tail[keep]])
+def _padded(mask, lead):
+    """face mask (b, nf) -> (valid bytes of the padded row space, P, R): rows b * P + lead + n, `lead` separators after the last mesh."""
+    b, nf = mask.shape
+    P = nf + lead
+    R = b * P + lead
+    valid = torch.zeros(R, dtype=torch.uint8, device=mask.device)
+    valid[:b * P].view(b, P)[:, lead:] = mask
+    return valid, P, R
 
 
-@pytest.mark.parametrize("k", [1, 3, 7])
-def test_fused_image_writers_are_bit_exact_with_the_im2col_pass(k):
-    """rows_im2col and dequantize_rvq_im2col write, byte for byte, the image the stand-alone im2col pass builds from the same rows
-    (ragged meshes, masked faces in the middle of a mesh, a row count that is not a multiple of 8 or 128)."""
+def _halo_rows(img, R, c, halo):
+    """Read a halo image back: (hi + lo as fp32 of every row < R from the row's own tile, the same rows from the halo copies in the
+    neighbouring tiles with NaN where a row has no copy)."""
+    rows = 128 + 2 * halo
+    tiles = (R + 127) // 128
+    blocks = img.view(torch.bfloat16).reshape(tiles, c // 32, 2, 4, rows, 8).float()      # tile, chunk, hi/lo, column group, row, 8 columns
+    val = blocks.permute(0, 2, 4, 1, 3, 5).reshape(tiles, 2, rows, c)                       # tile, hi/lo, row, column
+    own = val[:, :, halo:halo + 128].permute(1, 0, 2, 3).reshape(2, tiles * 128, c)[:, :R]
+    copies = torch.full((2, 2, tiles * 128, c), float("nan"), device=img.device)           # [before / after copy][hi / lo]
+    if halo and tiles > 1:
+        v = val.permute(1, 0, 2, 3)                                                         # hi/lo, tile, row, column
+        idx = torch.arange(tiles * 128, device=img.device).view(tiles, 128)
+        copies[0][:, idx[:-1, 128 - halo:].reshape(-1)] = v[:, 1:, :halo].reshape(2, -1, c)       # last rows of tile t in front of tile t + 1
+        copies[1][:, idx[1:, :halo].reshape(-1)] = v[:, :-1, halo + 128:].reshape(2, -1, c)       # first rows of tile t + 1 behind tile t
+    return own, copies[:, :, :R]
+
+
+def _split(x):
+    hi = x.to(torch.bfloat16).float()
+    return torch.stack([hi, (x - hi).to(torch.bfloat16).float()])
+
+
+@pytest.mark.parametrize("halo", [0, 1, 3])
+def test_halo_image_writers_are_bit_exact(halo):
+    """rows_halo and dequantize_rvq_halo against a torch restatement of the layout (tc_common.cuh): hi = bf16(x), lo = bf16(x - hi), rows
+    of the padded row space, zero rows on separators and masked faces, the first / last `halo` rows of a tile stored again in the
+    neighbouring tile (ragged meshes, masked faces inside a mesh, a row count that is not a multiple of 8 or 128)."""
     from meshgpt_pytorch_b200._lib import lib, check, ptr, stream_ptr
-    torch.manual_seed(k)
-    b, nf, c = 3, 77, 96
-    R = b * nf
-    x = torch.randn(R, c, device="cuda")
-    valid = (torch.rand(R, device="cuda") > 0.2).to(torch.uint8)
-    valid[nf - 5:nf] = 0
-    n = _image_bytes(R, k * c)
-    want = torch.zeros(n, dtype=torch.uint8, device="cuda")
-    got = torch.full((n,), 0xAB, dtype=torch.uint8, device="cuda")
-    check(lib.meshtok_dec_im2col_image(ptr(x), ptr(valid), R, nf, c, k, ptr(want), stream_ptr()))
-    check(lib.meshtok_dec_rows_im2col(ptr(x), c, ptr(valid), R, nf, c, k, ptr(got), stream_ptr()))
-    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
-    # a strided source: the second half of a (R, 2 c) buffer
-    wide = torch.randn(R, 2 * c, device="cuda")
+    torch.manual_seed(halo)
+    b, nf, c, lead = 3, 125, 96, 3
+    mask = torch.rand(b, nf, device="cuda") > 0.2
+    mask[0, nf - 5:] = False
+    valid, P, R = _padded(mask, lead)
+    x = torch.randn(b * nf, c, device="cuda")
+    want_rows = torch.zeros(R, c, device="cuda")
+    want_rows[:b * P].view(b, P, c)[:, lead:] = x.view(b, nf, c) * mask[..., None]
+    want = _split(want_rows)
+
+    def check_image(got):
+        own, copies = _halo_rows(got, R, c, halo)
+        assert torch.equal(own, want)
+        r = torch.arange(R, device="cuda")
+        tiles = (R + 127) // 128
+        expect = ((r % 128 >= 128 - halo) & (r // 128 + 1 < tiles), (r % 128 < halo) & (r // 128 > 0))
+        for side in range(2):
+            assert torch.equal(~torch.isnan(copies[side][0, :, 0]), expect[side])
+            assert torch.equal(copies[side][:, expect[side]], want[:, expect[side]])
+
+    n = _halo_bytes(R, c, halo)
+    got = torch.full((n,), 0x7F, dtype=torch.uint8, device="cuda")          # 0x7F7F: a bf16 NaN wherever nothing is written
+    check(lib.meshtok_dec_rows_halo(ptr(x), c, ptr(valid), R, P, lead, c, halo, ptr(got), stream_ptr()))
+    check_image(got)
+    # a strided source: the second half of a (rows, 2 c) buffer
+    wide = torch.randn(b * nf, 2 * c, device="cuda")
     wide[:, c:] = x
-    got.fill_(0xCD)
-    check(lib.meshtok_dec_rows_im2col(wide.data_ptr() + 4 * c, 2 * c, ptr(valid), R, nf, c, k, ptr(got), stream_ptr()))
-    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
+    got.fill_(0x7F)
+    check(lib.meshtok_dec_rows_halo(wide.data_ptr() + 4 * c, 2 * c, ptr(valid), R, P, lead, c, halo, ptr(got), stream_ptr()))
+    check_image(got)
     # codes -> image
     nvf, q, d, ksz = 3, 2, 32, 50
     book = torch.randn(ksz, d, device="cuda")
-    codes = torch.randint(0, ksz, (R * nvf, q), device="cuda")
-    codes[(valid == 0).repeat_interleave(nvf)] = -1
-    rows = torch.empty(R * nvf, d, device="cuda")
-    check(lib.meshtok_dec_dequantize_rvq(ptr(codes), ptr(book), R * nvf, q, d, ptr(rows), stream_ptr()))
-    check(lib.meshtok_dec_im2col_image(ptr(rows), ptr(valid), R, nf, nvf * d, k, ptr(want), stream_ptr()))
-    got.fill_(0xEF)
-    check(lib.meshtok_dec_dequantize_rvq_im2col(ptr(codes), ptr(book), ptr(valid), R, nf, nvf, q, d, k, ptr(got), stream_ptr()))
-    assert torch.equal(_live_image(got, R, k * c), _live_image(want, R, k * c))
+    codes = torch.randint(0, ksz, (b * nf * nvf, q), device="cuda")
+    codes[(~mask).reshape(-1).repeat_interleave(nvf)] = -1
+    rows = torch.empty(b * nf * nvf, d, device="cuda")
+    check(lib.meshtok_dec_dequantize_rvq(ptr(codes), ptr(book), b * nf * nvf, q, d, ptr(rows), stream_ptr()))
+    want_rows.zero_()
+    want_rows[:b * P].view(b, P, c)[:, lead:] = rows.view(b, nf, c) * mask[..., None]
+    want = _split(want_rows)
+    got.fill_(0x7F)
+    check(lib.meshtok_dec_dequantize_rvq_halo(ptr(codes), ptr(book), ptr(valid), R, P, lead, nvf, q, d, halo, ptr(got), stream_ptr()))
+    check_image(got)
+
+
+@pytest.mark.parametrize("k,halo,c_in,n", [(1, 0, 64, 48), (3, 1, 96, 160), (7, 3, 32, 64), (3, 3, 64, 384), (1, 1, 32, 1152)])
+def test_conv1d_on_a_halo_image_matches_torch(k, halo, c_in, n):
+    """meshtok_conv1d (tcgen05, tap t = the same shared-memory block read t rows further) against torch's Conv1d in fp64 on every mesh
+    separately: zero padding at the ends of a mesh, meshes that straddle 128-row tiles, an image whose halo is wider than the kernel."""
+    import ctypes as C
+    from meshgpt_pytorch_b200._lib import lib, check, ptr, stream_ptr
+    torch.manual_seed(k * 100 + n)
+    b, nf, lead = 5, 171, 3
+    mask = torch.ones(b, nf, dtype=torch.bool, device="cuda")
+    mask[1, 150:] = False
+    mask[4, 1:] = False
+    valid, P, R = _padded(mask, lead)
+    x = torch.randn(b * nf, c_in, device="cuda")
+    w = torch.randn(n, c_in, k, device="cuda") / (c_in * k) ** 0.5
+    bias = torch.randn(n, device="cuda")
+    img = torch.full((_halo_bytes(R, c_in, halo),), 0x7F, dtype=torch.uint8, device="cuda")
+    check(lib.meshtok_dec_rows_halo(ptr(x), c_in, ptr(valid), R, P, lead, c_in, halo, ptr(img), stream_ptr()))
+    mat = w.permute(0, 2, 1).reshape(n, k * c_in).contiguous()
+    nb = C.c_size_t()
+    check(lib.meshtok_linear_image_bytes(n, k * c_in, C.byref(nb)))
+    wimg = torch.empty(nb.value, dtype=torch.uint8, device="cuda")
+    check(lib.meshtok_linear_build_image(ptr(mat), n, k * c_in, ptr(wimg), stream_ptr()))
+    out = torch.empty(R, n, device="cuda")
+    check(lib.meshtok_conv1d(ptr(img), ptr(wimg), ptr(bias), ptr(out), R, n, c_in, k, halo, stream_ptr()))
+    got = out[:b * P].view(b, P, n)[:, lead:]
+    xm = (x.view(b, nf, c_in) * mask[..., None]).double().cpu()
+    want = torch.nn.functional.conv1d(xm.transpose(1, 2), w.double().cpu(), bias.double().cpu(), padding=k // 2).transpose(1, 2)
+    m = mask.cpu()
+    err = (got.cpu().double() - want)[m].abs().max() / want[m].abs().max()
+    assert float(err) < 2e-5, float(err)                        # split bf16: 3 products, ~2^-16 relative
 
 
 @pytest.mark.parametrize("cfg,dims,kind", [
