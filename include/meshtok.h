@@ -316,6 +316,24 @@ int meshtok_dec_gate_residual_halo(const float* h, int ldh, const float* scale, 
 int meshtok_dec_argmax_coords_padded(const float* logits, const uint8_t* valid, int B, int P, int lead, int ncoord, int nbins,
                                      float lo, float hi, float* coords, int64_t* bins, meshtok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Token-embedding front end of MeshTransformer.forward_on_codes, meshgpt_pytorch/meshgpt_pytorch.py:1526-1570
+ * (the step that follows tokenization).  n = nvf * Q codes per face.
+ * ------------------------------------------------------------------------------------------ */
+/* :1528-1547 + :1560: out (B, ceil(L / n) * n, D) fp32 = ((token_embed[code, pad_id -> 0] + abs_pos_emb[t]) + level_embed[t % Q]) +
+ * vertex_embed[(t / Q) % nvf], added in the reference's order (bit-exact); rows t >= L (the incomplete last face) are zero.
+ * token_embed (n_embed, D) with n_embed = codebook_size + 1 (eos), abs_pos_emb (>= L, D), level_embed (Q, D), vertex_embed (nvf, D). */
+int meshtok_frontend_fine_tokens(const int64_t* codes, int B, int L, int D, int64_t pad_id, int Q, int nvf, int n_embed,
+                                 const float* token_embed, const float* abs_pos_emb, const float* level_embed, const float* vertex_embed,
+                                 float* out, meshtok_stream_t stream);
+/* :1564-1570: out (B, L / n, D) fp32 = LayerNorm(Linear(n * D -> D)(the n fine tokens of a face)) for the complete faces, computed from
+ * tables folded at load time: folded_tables (n, n_embed, D) with folded_tables[j] = token_embed @ W[:, j * D : (j + 1) * D]^T, and
+ * face_pos (>= L / n, D) with face_pos[f] = sum_j W_j (abs_pos_emb[n f + j] + level_embed[j % Q] + vertex_embed[j / Q]) + bias.
+ * D must be a multiple of 128, at most 1024; n <= 32. */
+int meshtok_frontend_face_tokens(const int64_t* codes, int B, int L, int n, int D, int64_t pad_id, int n_embed, const float* folded_tables,
+                                 const float* face_pos, const float* ln_gamma, const float* ln_beta, float eps, float* out,
+                                 meshtok_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -9,5 +9,6 @@ from ._lib import LIB_PATH, MeshtokError  # noqa: F401  (loads the shared librar
 from .autoencoder import GraphedTokenizer, HostPipeline, MeshAutoencoder, ResidualLFQ, ResidualVQ, SAGEConv  # noqa: F401
 from .data import cache_face_edges, derive_face_edges_from_faces, write_face_edges_cache  # noqa: F401
 from .decoder import MeshDecoder  # noqa: F401
+from .frontend import MeshTransformerFrontEnd  # noqa: F401
 
 __version__ = "0.1.0"

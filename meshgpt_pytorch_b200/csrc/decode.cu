@@ -249,9 +249,11 @@ __global__ void __launch_bounds__(256) argmax_coords_kernel(const float* __restr
 // HALO IMAGES (tc_common.cuh).  A stage writes its output once, as the split-bf16 halo image of the convolution that follows; the
 // tcgen05 kernel reads tap t of the kernel from the same block 16 t bytes further (linear_tc.cu, conv mode).  The first version's
 // im2col image (k copies of every activation) is gone: a k=3 convolution's input is written as 4 bytes per element instead of 12.
-// Thread layout ("8 x 4"): a warp owns one aligned group of 8 rows, lane = colsub * 8 + rowsub; it walks the row in steps of 32
-// columns, 8 adjacent columns (16 bytes of hi, 16 of lo) per lane.  A warp-wide image store is 4 x 128 contiguous bytes of hi and
-// of lo, a warp-wide fp32 load 8 rows x 128 contiguous bytes, a row reduction two shuffles (xor 8, 16).  Needs C % 32 == 0.
+// Thread layout ("8 x 4"): a warp owns one aligned group of 8 rows, lane = rowsub * 4 + colsub; it walks the row in steps of 32
+// columns, 8 adjacent columns (16 bytes of hi, 16 of lo) per lane.  The four lanes of a row sit next to each other, so a quarter
+// warp's 16-byte loads fall into 2 cache lines (the first layout, lane = colsub * 8 + rowsub, made the image stores contiguous but
+// spread every quarter warp's loads over 8 lines: ncu showed the L1 data pipe at 93 % of its wavefront peak and DRAM at 34 %).
+// A row reduction is two shuffles (xor 1, 2).  Needs C % 32 == 0.
 // The float chains here use reciprocal multiplies and __expf (PixelNorm / SiLU are tolerance-checked stages, not bit-exact ones);
 // the staged kernels above keep the IEEE divisions.
 struct Lane84 {
@@ -263,15 +265,15 @@ struct Lane84 {
 __device__ __forceinline__ Lane84 lane84(long long group, int R, int P) {
   Lane84 l;
   const int lane = lane_id();
-  l.row = group * 8 + (lane & 7);
-  l.colsub = lane >> 3;
+  l.row = group * 8 + (lane >> 2);
+  l.colsub = lane & 3;
   l.active = l.row < R;
   l.b = (int)(l.row / P);
   return l;
 }
 __device__ __forceinline__ float row_sum84(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 8);
-  v += __shfl_xor_sync(0xffffffffu, v, 16);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
   return v;
 }
 // 8 adjacent values of (row, columns col .. col + 7) -> the halo image (R, C): the row's own tile and, for the first / last `halo`
@@ -436,6 +438,44 @@ __global__ void __launch_bounds__(256) pixelnorm_silu_halo_kernel(const float* _
   }
 }
 
+// The same with the whole row slice of a lane in registers (C <= 32 * NIT): every load of the row is in flight before the first use
+// and h is read once.  The loop version above keeps one 32-column step in flight per warp and reads h twice; with all warps of the
+// grid resident in a single wave its run time is the sum of a warp's dependent memory round trips (ncu: DRAM at 35 % of peak).
+template <int NIT>
+__global__ void __launch_bounds__(256) pixelnorm_silu_halo_rows_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int R,
+                                                                       int P, int C, float eps, int halo, uint8_t* __restrict__ image) {
+  const long long groups = ((long long)R + 7) >> 3, n_tiles = ((long long)R + 127) >> 7;
+  const float root_c = sqrtf((float)C);
+  for (long long g = (long long)blockIdx.x * 8 + warp_id(); g < groups; g += (long long)gridDim.x * 8) {
+    const Lane84 l = lane84(g, R, P);
+    const bool ok = l.active && valid[l.row] != 0;
+    const float* hr = h + (size_t)(l.active ? l.row : 0) * ld + l.colsub * 8;
+    float v[NIT][8];
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[u][i] = 0.f;
+      if (ok && u * 32 < C) load8(hr + u * 32, v[u]);
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int u = 0; u < NIT; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss = fmaf(v[u][i], v[u][i], ss);
+    const float scale = root_c / fmaxf(sqrtf(row_sum84(ss)), eps);
+    if (!l.active) continue;
+#pragma unroll
+    for (int u = 0; u < NIT; ++u) {
+      if (u * 32 >= C) break;
+      if (ok) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[u][i] = silu_fast(v[u][i] * scale);
+      }
+      emit_halo(image, C, halo, n_tiles, l.row, l.colsub * 8 + u * 32, v[u]);
+    }
+  }
+}
+
 // Second Block tail + SqueezeExcite's mean, without storing the activation: scale[row] = sqrt(C) / max(||h[row]||, eps) and, per
 // (mesh, slice of its faces), the column sums of silu(h * scale) over the valid faces of the slice.  CTA (mesh, slice); a warp
 // per face, lane owns columns lane * 4 + 128 j; rows are added in ascending order per warp and the 8 warps are combined in a fixed
@@ -580,18 +620,33 @@ __global__ void __launch_bounds__(256) gate_residual_halo_kernel(const float* __
     if (!l.active) continue;
     const bool ok = valid[l.row] != 0;
     const float sc = (ok && scale) ? scale[l.row] : 1.f;
-    for (int col = l.colsub * 8; col < C; col += 32) {
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        float gt[8], rs[8];
-        load8(h + (size_t)l.row * ldh + col, v);
-        load8(gate + (size_t)l.b * C + col, gt);
-        load8(res + (size_t)l.row * ldres + col, rs);
+    // U = 4 steps of 32 columns per round: the 16 loads of a round are issued before the first use (one step per round left a warp
+    // with 2 KB in flight and the kernel, a single wave of warps, bound by the sum of its memory round trips)
+    constexpr int U = 4;
+    for (int col0 = l.colsub * 8; col0 < C; col0 += 32 * U) {
+      float v[U][8], rs[U][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = fmaf(scale ? silu_fast(v[i] * sc) : v[i], gt[i], rs[i]);
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[u][i] = 0.f; rs[u][i] = 0.f; }
+        if (ok && col0 + 32 * u < C) {
+          load8(h + (size_t)l.row * ldh + col0 + 32 * u, v[u]);
+          load8(res + (size_t)l.row * ldres + col0 + 32 * u, rs[u]);
+        }
       }
-      store8(out + (size_t)l.row * C + col, v);
-      if (image) emit_halo(image, C, halo, n_tiles, l.row, col, v);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int col = col0 + 32 * u;
+        if (col >= C) break;
+        if (ok) {
+          float gt[8];
+          load8(gate + (size_t)l.b * C + col, gt);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] = fmaf(scale ? silu_fast(v[u][i] * sc) : v[u][i], gt[i], rs[u][i]);
+        }
+        store8(out + (size_t)l.row * C + col, v[u]);
+        if (image) emit_halo(image, C, halo, n_tiles, l.row, col, v[u]);
+      }
     }
   }
 }
@@ -632,6 +687,55 @@ __global__ void __launch_bounds__(256) argmax_coords_padded_kernel(const float* 
       t = __fdiv_rn(t, (float)nbins);
       coords[item] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
       if (bins) bins[item] = bi;
+    }
+  }
+}
+
+// nbins == 128: a warp per face, lane owns 4 adjacent bins of every coordinate (one 16-byte load), U coordinates' loads in flight at
+// a time.  (The kernel above, a warp per (face, coordinate) with scalar loads, kept 512 bytes in flight per warp: 1.8 TB/s.)
+__global__ void __launch_bounds__(256) argmax_coords_padded128_kernel(const float* __restrict__ logits, const uint8_t* __restrict__ valid, int B, int P,
+                                                                      int lead, int ncoord, float lo, float hi, float* __restrict__ coords,
+                                                                      int64_t* __restrict__ bins) {
+  constexpr int U = 3;
+  const int lane = lane_id(), nf = P - lead;
+  const long long total = (long long)B * nf;
+  for (long long face = (long long)blockIdx.x * 8 + warp_id(); face < total; face += (long long)gridDim.x * 8) {
+    const int b = (int)(face / nf);
+    const long long row = (long long)b * P + lead + (face - (long long)b * nf);
+    if (!valid[row]) {
+      for (int k = lane; k < ncoord; k += 32) { coords[face * ncoord + k] = __int_as_float(0x7fc00000); if (bins) bins[face * ncoord + k] = 0; }
+      continue;
+    }
+    const float4* lr = reinterpret_cast<const float4*>(logits + (size_t)row * ncoord * 128) + lane;
+    for (int k0 = 0; k0 < ncoord; k0 += U) {
+      float4 x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (k0 + u < ncoord) x[u] = __ldcs(lr + (size_t)(k0 + u) * 32);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (k0 + u >= ncoord) break;
+        float best = -INFINITY;                    // first maximum wins, like torch.argmax; same comparisons as the scalar kernel
+        int bi = 0x7fffffff;
+        const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (xv[i] > best || (xv[i] == best && lane * 4 + i < bi)) { best = xv[i]; bi = lane * 4 + i; }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) {
+          if (bi == 0x7fffffff) bi = 0;
+          float t = (float)bi;
+          t = __fadd_rn(t, 0.5f);
+          t = __fdiv_rn(t, 128.f);
+          coords[face * ncoord + k0 + u] = __fadd_rn(__fmul_rn(t, __fsub_rn(hi, lo)), lo);
+          if (bins) bins[face * ncoord + k0 + u] = bi;
+        }
+      }
     }
   }
 }
@@ -784,7 +888,12 @@ int meshtok_dec_pixelnorm_silu_halo(const float* h, int ld, const uint8_t* valid
                                     meshtok_stream_t stream) {
   MT_CHECK_ARG(h && valid && image && R >= 0 && P >= 1 && C % 32 == 0 && ld >= C && ld % 4 == 0 && halo >= 0 && halo <= 8, "pixelnorm_silu_halo: width %d must be a multiple of 32", C);
   if (R == 0) return MESHTOK_OK;
-  pixelnorm_silu_halo_kernel<<<grid_groups(R), 256, 0, static_cast<cudaStream_t>(stream)>>>(h, ld, valid, R, P, C, eps, halo, static_cast<uint8_t*>(image));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* img = static_cast<uint8_t*>(image);
+  if (C <= 128) pixelnorm_silu_halo_rows_kernel<4><<<grid_groups(R), 256, 0, st>>>(h, ld, valid, R, P, C, eps, halo, img);
+  else if (C <= 256) pixelnorm_silu_halo_rows_kernel<8><<<grid_groups(R), 256, 0, st>>>(h, ld, valid, R, P, C, eps, halo, img);
+  else if (C <= 384) pixelnorm_silu_halo_rows_kernel<12><<<grid_groups(R), 256, 0, st>>>(h, ld, valid, R, P, C, eps, halo, img);
+  else pixelnorm_silu_halo_kernel<<<grid_groups(R), 256, 0, st>>>(h, ld, valid, R, P, C, eps, halo, img);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
@@ -835,8 +944,12 @@ int meshtok_dec_argmax_coords_padded(const float* logits, const uint8_t* valid, 
                                      float* coords, int64_t* bins, meshtok_stream_t stream) {
   MT_CHECK_ARG(logits && valid && coords && B >= 0 && lead >= 0 && P > lead && ncoord >= 1 && nbins >= 1, "argmax_coords_padded: bad arguments");
   if (B == 0) return MESHTOK_OK;
-  argmax_coords_padded_kernel<<<grid_for((long long)B * (P - lead) * ncoord, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, B, P, lead, ncoord,
-                                                                                                                             nbins, lo, hi, coords, bins);
+  if (nbins == 128)
+    argmax_coords_padded128_kernel<<<grid_for((long long)B * (P - lead), 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, B, P, lead, ncoord, lo, hi,
+                                                                                                                         coords, bins);
+  else
+    argmax_coords_padded_kernel<<<grid_for((long long)B * (P - lead) * ncoord, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, valid, B, P, lead, ncoord,
+                                                                                                                               nbins, lo, hi, coords, bins);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

@@ -1,0 +1,135 @@
+"""Token-embedding front end of the reference's MeshTransformer.forward_on_codes (meshgpt_pytorch.py:1526-1570): the
+step that follows tokenization.  codes (b, L) -> the per-code "fine" tokens (token + absolute position + quantizer-level + vertex
+embeddings, zero-padded to whole faces and grouped per face) and the per-face "coarse" tokens (to_face_tokens = Linear + LayerNorm
+over the n = nvf * Q fine tokens of a face).
+
+    fe = MeshTransformerFrontEnd(autoencoder, dim=512, max_seq_len=8192)      # the transformer's keywords that matter here
+    fe.load_reference_state_dict(transformer.state_dict())                     # token_embed.*, abs_pos_emb.*, quantize_level_embed,
+    grouped_codes, face_codes = fe.cuda().embed_codes(codes)                   #   vertex_embed, to_face_tokens.{0,1}.*
+
+Both outputs come from csrc/frontend.cu through the C ABI (meshtok_frontend_*); there is no CPU path.  The fine tokens are bit-exact
+(four adds in the reference's order).  The face tokens never run the (n * dim -> dim) Linear: it is folded at load time into n
+tables token_embed @ W_j^T plus one position row per face index (fp64 products rounded once to fp32), so a face token is n + 1 row
+gathers and a LayerNorm - HBM traffic instead of 3.1 MFLOP per face.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from ._lib import check, lib, ptr, stream_ptr
+
+
+class MeshTransformerFrontEnd(nn.Module):
+    def __init__(self, autoencoder=None, *, dim: int = 512, max_seq_len: int = 8192, pad_id: int = -1, codebook_size: int | None = None,
+                 num_quantizers: int | None = None, quads: bool | None = None):
+        super().__init__()
+        if autoencoder is not None:
+            codebook_size = autoencoder.codebook_size if codebook_size is None else codebook_size
+            num_quantizers = autoencoder.num_quantizers if num_quantizers is None else num_quantizers
+            quads = (autoencoder.num_vertices_per_face == 4) if quads is None else quads
+        if codebook_size is None or num_quantizers is None:
+            raise ValueError("give an autoencoder or codebook_size / num_quantizers / quads")
+        self.num_vertices_per_face = 4 if quads else 3                                    # :1131
+        self.codebook_size, self.num_quantizers = codebook_size, num_quantizers           # :1140-1141
+        self.eos_token_id = codebook_size                                                 # :1143
+        n = self.num_vertices_per_face * num_quantizers
+        if max_seq_len % n != 0:                                                          # :1156
+            raise ValueError(f"max_seq_len ({max_seq_len}) must be divisible by {n}")
+        if dim % 128 != 0 or dim > 1024:
+            raise NotImplementedError(f"dim {dim}: the face-token kernel needs a multiple of 128, at most 1024")
+        self.dim, self.max_seq_len, self.pad_id = dim, max_seq_len, pad_id
+        self.token_embed = nn.Embedding(codebook_size + 1, dim)                           # :1158
+        self.quantize_level_embed = nn.Parameter(torch.randn(num_quantizers, dim))        # :1160
+        self.vertex_embed = nn.Parameter(torch.randn(self.num_vertices_per_face, dim))    # :1161
+        self.abs_pos_emb = nn.Embedding(max_seq_len, dim)                                 # :1163
+        self.to_face_tokens = nn.Sequential(nn.Linear(n * dim, dim), nn.LayerNorm(dim))   # :1191-1194
+        for p in self.parameters():
+            p.requires_grad_(False)
+        self._prep = None
+        self._prep_key = None
+
+    def load_reference_state_dict(self, state_dict: Dict[str, Tensor]):
+        """Takes the front end's keys out of a MeshTransformer state dict (every other key is ignored)."""
+        own = self.state_dict()
+        missing = [k for k in own if k not in state_dict]
+        if missing:
+            raise KeyError(f"state dict lacks front-end keys: {missing}")
+        self.load_state_dict({k: state_dict[k] for k in own}, strict=True)
+        self._prep = None
+
+    # ---- load time: fold to_face_tokens.0 into per-slot tables ---------------------------------------
+    def _prepare(self):
+        key = tuple((t.data_ptr(), t._version) for t in self.parameters())
+        if self._prep is not None and self._prep_key == key:
+            return self._prep
+        dev = self.token_embed.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("MeshTransformerFrontEnd must live on a CUDA device (call .cuda()); there is no CPU path")
+        q, nvf, d = self.num_quantizers, self.num_vertices_per_face, self.dim
+        n = q * nvf
+        f32 = dict(dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            W = self.to_face_tokens[0].weight.detach().double().view(d, n, d)             # [out, slot j, in]
+            tok = self.token_embed.weight.detach().double()
+            tables = torch.empty(n, tok.shape[0], d, **f32)
+            for j in range(n):
+                tables[j] = (tok @ W[:, j].t()).float()                                   # T_j = token_embed @ W_j^T
+            # position / level / vertex part of slot j at face f: W_j (abs_pos_emb[n f + j] + level[j % q] + vertex[j // q]), summed over j
+            pos = self.abs_pos_emb.weight.detach().double().view(self.max_seq_len // n, n, d)
+            slot = (self.quantize_level_embed.detach().double().repeat(nvf, 1)
+                    + self.vertex_embed.detach().double().repeat_interleave(q, dim=0))    # (n, d): t = (vertex, level), level fastest
+            face_pos = torch.einsum("fjd,ojd->fo", pos + slot[None], W) + self.to_face_tokens[0].bias.detach().double()
+            prep = dict(tables=tables.contiguous(), face_pos=face_pos.float().contiguous(),
+                        tok=self.token_embed.weight.detach().to(**f32).contiguous(), pos=self.abs_pos_emb.weight.detach().to(**f32).contiguous(),
+                        level=self.quantize_level_embed.detach().to(**f32).contiguous(), vert=self.vertex_embed.detach().to(**f32).contiguous(),
+                        gamma=self.to_face_tokens[1].weight.detach().to(**f32).contiguous(),
+                        beta=self.to_face_tokens[1].bias.detach().to(**f32).contiguous(), eps=float(self.to_face_tokens[1].eps))
+        self._prep, self._prep_key = prep, key
+        return prep
+
+    # ---- :1526-1570 -------------------------------------------------------------------------------
+    def _check(self, codes: Tensor) -> Tensor:
+        if codes.device.type != "cuda":
+            raise RuntimeError("codes must be a CUDA tensor; there is no CPU path")
+        if codes.ndim != 2:
+            raise ValueError("codes must be (batch, seq_len); flatten (b, n, q) codes with 'b n q -> b (n q)' like the reference (:1494)")
+        if codes.shape[1] > self.max_seq_len:                                             # :1502
+            raise ValueError(f"received codes of length {codes.shape[1]} but needs to be less than or equal to set max_seq_len {self.max_seq_len}")
+        return codes.to(torch.int64).contiguous()
+
+    @torch.no_grad()
+    def fine_tokens(self, codes: Tensor) -> Tensor:
+        """grouped_codes (b, ceil(L / n), n, dim) of :1564 - every code's embedding, zero rows behind an incomplete last face."""
+        codes = self._check(codes)
+        p = self._prepare()
+        b, L = codes.shape
+        n = self.num_quantizers * self.num_vertices_per_face
+        nfp = -(-L // n)
+        out = torch.empty(b, nfp, n, self.dim, dtype=torch.float32, device=codes.device)
+        with torch.cuda.device(codes.device):
+            check(lib.meshtok_frontend_fine_tokens(ptr(codes), b, L, self.dim, self.pad_id, self.num_quantizers, self.num_vertices_per_face,
+                                                   self.codebook_size + 1, ptr(p["tok"]), ptr(p["pos"]), ptr(p["level"]), ptr(p["vert"]), ptr(out),
+                                                   stream_ptr()))
+        return out
+
+    @torch.no_grad()
+    def face_tokens(self, codes: Tensor) -> Tensor:
+        """face_codes (b, L // n, dim) of :1570 - one token per complete face."""
+        codes = self._check(codes)
+        p = self._prepare()
+        b, L = codes.shape
+        n = self.num_quantizers * self.num_vertices_per_face
+        out = torch.empty(b, L // n, self.dim, dtype=torch.float32, device=codes.device)
+        with torch.cuda.device(codes.device):
+            check(lib.meshtok_frontend_face_tokens(ptr(codes), b, L, n, self.dim, self.pad_id, self.codebook_size + 1, ptr(p["tables"]),
+                                                   ptr(p["face_pos"]), ptr(p["gamma"]), ptr(p["beta"]), p["eps"], ptr(out), stream_ptr()))
+        return out
+
+    def embed_codes(self, codes: Tensor) -> Tuple[Tensor, Tensor]:
+        """(grouped_codes, face_codes) as forward_on_codes holds them after :1570."""
+        return self.fine_tokens(codes), self.face_tokens(codes)
+
+    forward = embed_codes
