@@ -303,10 +303,12 @@ int meshtok_dec_pixelnorm_silu_halo(const float* h, int ld, const uint8_t* valid
                                     void* image, meshtok_stream_t stream);
 /* second Block tail + SqueezeExcite (:296-324) without storing the activation: scale (R) = sqrt(C) / max(||h[row]||, eps) on valid rows
  * and gate (B, C) from the masked mean of silu(h * scale); slice sums are combined in a fixed order (deterministic).  The two
- * SqueezeExcite weights are passed TRANSPOSED: w1t (C, inner) = excite.net.0.weight^T, w2t (inner, C) = excite.net.2.weight^T. */
+ * SqueezeExcite weights are passed TRANSPOSED: w1t (C, inner) = excite.net.0.weight^T, w2t (inner, C) = excite.net.2.weight^T.
+ * tickets: B int32, ZERO on entry and zero again when the kernel has finished (one buffer serves every call on a stream): the CTA
+ * that finishes a mesh's last slice computes its gate, so the whole stage is one launch.  NULL: the gate runs as a second launch. */
 int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int P, int lead, int C, float eps,
                                               int inner, const float* w1t, const float* b1, const float* w2t, const float* b2,
-                                              float* scale, float* slice_ws, float* gate, meshtok_stream_t stream);
+                                              float* scale, float* slice_ws, int32_t* tickets, float* gate, meshtok_stream_t stream);
 /* ResnetBlock tail (:378-379): out = silu(h * scale[row]) * gate[b] + res (scale NULL: h * gate[b] + res) -> out (R, C) fp32 and,
  * image != NULL, the halo image of the next convolution; non-valid rows 0 */
 int meshtok_dec_gate_residual_halo(const float* h, int ldh, const float* scale, const float* gate, const float* res, int ldres,

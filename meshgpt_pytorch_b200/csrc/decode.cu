@@ -481,12 +481,18 @@ __global__ void __launch_bounds__(256) pixelnorm_silu_halo_rows_kernel(const flo
 // per face, lane owns columns lane * 4 + 128 j; rows are added in ascending order per warp and the 8 warps are combined in a fixed
 // order, so the result does not depend on scheduling.  Rows of mesh b: b * P + lead + n.
 constexpr int SE_MAX_C = 1024;
+__device__ __forceinline__ void se_gate_tail(int b, int T, const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
+                                             const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+                                             const float* __restrict__ b2, float* __restrict__ gate, float* sm, float* sq, float* sh);
 template <int NJ>   // NJ = ceil(C / 128) float4 per lane
 __global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __restrict__ h, int ld, const uint8_t* __restrict__ valid, int P, int lead, int C,
                                                                float eps, int S, float* __restrict__ scale_out, float* __restrict__ part,
-                                                               int* __restrict__ part_cnt) {
-  extern __shared__ float4 sm_dyn[];   // [8 warps][NJ * 32]
+                                                               int* __restrict__ part_cnt, int* __restrict__ tickets, int inner,
+                                                               const float* __restrict__ w1t, const float* __restrict__ b1,
+                                                               const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ gate) {
+  extern __shared__ float4 sm_dyn[];   // [8 warps][NJ * 32]; the gate tail reuses it (C + 256 + 256 floats; the launcher sizes it for both)
   __shared__ int cnt[8];
+  __shared__ int is_last;
   const int b = blockIdx.x, s = blockIdx.y, lane = lane_id(), w = warp_id();
   const int nf = P - lead;
   const int per = (nf + S - 1) / S;
@@ -548,37 +554,50 @@ __global__ void __launch_bounds__(256) pixelnorm_colsum_kernel(const float* __re
     for (int i = 0; i < 8; ++i) t += cnt[i];
     part_cnt[b * S + s] = t;
   }
+  if (tickets == nullptr) return;
+  // The CTA that finishes a mesh's last slice computes the mesh's gate (a launch of its own cost 12 us of ramp per ResnetBlock):
+  // every thread's slice sums are fenced to the device, then one ticket per CTA; the ticket counter is left at 0 for the next launch.
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(tickets + b, 1);
+    is_last = t == S - 1;
+    if (is_last) tickets[b] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float* fs = reinterpret_cast<float*>(sm_dyn);
+  se_gate_tail(b, 256, part, part_cnt, S, C, inner, w1t, b1, w2t, b2, gate, fs, fs + C, fs + C + 256);
 }
 
-// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2) with mean[b] = (sum of the S slice sums) / max(#valid faces, 1e-5); one CTA of
-// 1024 threads per mesh.  The whole thing is a chain of three dependent global-memory round trips (slice sums, W1, W2), so every
+// gate[b] = sigmoid(W2 silu(W1 mean[b] + b1) + b2) with mean[b] = (sum of the S slice sums) / max(#valid faces, 1e-5), by one CTA
+// of T threads (T a multiple of 32, inner <= T).  A chain of three dependent global-memory round trips (slice sums, W1, W2), so every
 // phase is spread over all threads with all of a thread's loads independent: both weight matrices are read TRANSPOSED (w1t (C,
-// inner), w2t (inner, C), built once by the host side: a warp reads consecutive floats), a thread owns (part of the reduction
-// range, output), and the parts are added in a fixed order through shared memory.
-__global__ void __launch_bounds__(1024) se_gate_slices_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
-                                                              const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
-                                                              const float* __restrict__ b2, float* __restrict__ gate) {
-  __shared__ float sm[SE_MAX_C];
-  __shared__ float sq[1024];
-  __shared__ float sh[256];
-  const int b = blockIdx.x, tid = threadIdx.x;
+// inner), w2t (inner, C), built once by the host side: a warp reads consecutive floats); in the first linear a thread owns (part of
+// the reduction range, hidden unit) and the parts are added in a fixed order through shared memory.
+// sm: C floats, sq: T floats, sh: 256 floats of shared memory.  part / part_cnt were written by other CTAs: read through L2.
+__device__ __forceinline__ void se_gate_tail(int b, int T, const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
+                                             const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+                                             const float* __restrict__ b2, float* __restrict__ gate, float* sm, float* sq, float* sh) {
+  const int tid = threadIdx.x;
   int nv = 0;
-  for (int s = 0; s < S; ++s) nv += part_cnt[b * S + s];
+  for (int s = 0; s < S; ++s) nv += __ldcg(part_cnt + b * S + s);
   const float inv = 1.f / fmaxf((float)nv, 1e-5f);
-  for (int c = tid; c < C; c += 1024) {
+  for (int c = tid; c < C; c += T) {
     float t = 0.f;
-    for (int s = 0; s < S; ++s) t += part[((size_t)b * S + s) * C + c];
+    for (int s = 0; s < S; ++s) t += __ldcg(part + ((size_t)b * S + s) * C + c);
     sm[c] = t * inv;
   }
   __syncthreads();
   {  // hidden = silu(W1 mean + b1): thread (part p of the C range, hidden unit j)
-    const int jn = (inner + 31) & ~31, parts = 1024 / jn, p = tid / jn, j = tid - p * jn;
+    const int jn = (inner + 31) & ~31, parts = T / jn, p = tid / jn, j = tid - p * jn;
     const int span = (C + parts - 1) / parts;
     float t = 0.f;
     if (p < parts && j < inner) {
       const int c1 = min(C, (p + 1) * span);
 #pragma unroll 16
-      for (int c = p * span; c < c1; ++c) t = fmaf(w1t[(size_t)c * inner + j], sm[c], t);
+      for (int c = p * span; c < c1; ++c) t = fmaf(__ldg(w1t + (size_t)c * inner + j), sm[c], t);
     }
     sq[tid] = t;
     __syncthreads();
@@ -589,23 +608,23 @@ __global__ void __launch_bounds__(1024) se_gate_slices_kernel(const float* __res
     }
     __syncthreads();
   }
-  {  // gate = sigmoid(W2 hidden + b2): thread (part p of the hidden range, column c); C > 1024 is refused by the launcher
-    const int cn = (C + 31) & ~31, parts = 1024 / cn, p = tid / cn, c = tid - p * cn;
-    const int span = (inner + parts - 1) / parts;
-    float t = 0.f;
-    if (p < parts && c < C) {
-      const int j1 = min(inner, (p + 1) * span);
+  // gate = sigmoid(W2 hidden + b2): a thread per column, `inner` (<= 256) independent coalesced loads each
+  for (int c = tid; c < C; c += T) {
+    float a = b2[c];
 #pragma unroll 16
-      for (int j = p * span; j < j1; ++j) t = fmaf(w2t[(size_t)j * C + c], sh[j], t);
-    }
-    sq[tid] = t;
-    __syncthreads();
-    if (tid < C) {
-      float a = b2[tid];
-      for (int q = 0; q < parts; ++q) a += sq[q * cn + tid];
-      gate[(size_t)b * C + tid] = __fdividef(1.f, 1.f + __expf(-a));
-    }
+    for (int j = 0; j < inner; ++j) a = fmaf(__ldg(w2t + (size_t)j * C + c), sh[j], a);
+    gate[(size_t)b * C + c] = __fdividef(1.f, 1.f + __expf(-a));
   }
+}
+
+// stand-alone launch of the gate (one CTA of 1024 threads per mesh); the fused schedule runs se_gate_tail in the last column-sum CTA
+__global__ void __launch_bounds__(1024) se_gate_slices_kernel(const float* __restrict__ part, const int* __restrict__ part_cnt, int S, int C, int inner,
+                                                              const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2t,
+                                                              const float* __restrict__ b2, float* __restrict__ gate) {
+  __shared__ float sm[SE_MAX_C];
+  __shared__ float sq[1024];
+  __shared__ float sh[256];
+  se_gate_tail(blockIdx.x, 1024, part, part_cnt, S, C, inner, w1t, b1, w2t, b2, gate, sm, sq, sh);
 }
 
 // ResnetBlock tail + the next convolution's image: out = silu(h * scale[row]) * gate[b] + res (scale == NULL: h * gate[b] + res)
@@ -900,7 +919,7 @@ int meshtok_dec_pixelnorm_silu_halo(const float* h, int ld, const uint8_t* valid
 
 int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint8_t* valid, int B, int P, int lead, int C, float eps, int inner,
                                               const float* w1t, const float* b1, const float* w2t, const float* b2, float* scale, float* slice_ws,
-                                              float* gate, meshtok_stream_t stream) {
+                                              int32_t* tickets, float* gate, meshtok_stream_t stream) {
   MT_CHECK_ARG(h && valid && w1t && b1 && w2t && b2 && scale && slice_ws && gate && C % 4 == 0 && C <= SE_MAX_C && inner >= 1 && inner <= 256 && ld >= C &&
                    ld % 4 == 0 && lead >= 0 && P > lead,
                "pixelnorm_squeeze_excite_gate: bad arguments (C %% 4 == 0, C <= %d, inner <= 256)", SE_MAX_C);
@@ -909,8 +928,10 @@ int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint
   const int S = meshtok_dec_se_slices(B, P - lead);
   int* cnt = reinterpret_cast<int*>(slice_ws + (size_t)B * S * C);
   const int nj = (C + 127) / 128;
-  const size_t sm_bytes = (size_t)8 * nj * 32 * sizeof(float4);
-#define MT_COLSUM(NJ) pixelnorm_colsum_kernel<NJ><<<dim3(B, S), 256, sm_bytes, s>>>(h, ld, valid, P, lead, C, eps, S, scale, slice_ws, cnt)
+  size_t sm_bytes = (size_t)8 * nj * 32 * sizeof(float4);
+  if (tickets != nullptr && sm_bytes < (size_t)(C + 512) * sizeof(float)) sm_bytes = (size_t)(C + 512) * sizeof(float);
+#define MT_COLSUM(NJ) \
+  pixelnorm_colsum_kernel<NJ><<<dim3(B, S), 256, sm_bytes, s>>>(h, ld, valid, P, lead, C, eps, S, scale, slice_ws, cnt, tickets, inner, w1t, b1, w2t, b2, gate)
   switch (nj) {
     case 1: MT_COLSUM(1); break;
     case 2: MT_COLSUM(2); break;
@@ -923,8 +944,10 @@ int meshtok_dec_pixelnorm_squeeze_excite_gate(const float* h, int ld, const uint
   }
 #undef MT_COLSUM
   MT_CHECK_LAUNCH();
-  se_gate_slices_kernel<<<B, 1024, 0, s>>>(slice_ws, cnt, S, C, inner, w1t, b1, w2t, b2, gate);
-  MT_CHECK_LAUNCH();
+  if (tickets == nullptr) {   // no ticket counters: the gate as a launch of its own
+    se_gate_slices_kernel<<<B, 1024, 0, s>>>(slice_ws, cnt, S, C, inner, w1t, b1, w2t, b2, gate);
+    MT_CHECK_LAUNCH();
+  }
   return MESHTOK_OK;
 }
 

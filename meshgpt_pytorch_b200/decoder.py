@@ -233,6 +233,7 @@ class MeshDecoder(nn.Module):
         check(lib.meshtok_dec_silu_layernorm_halo(ptr(x0), ptr(valid), R, P, c, ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, ptr(x), halo, ptr(img),
                                                   stream_ptr()))
         S = lib.meshtok_dec_se_slices(b, P - lead)
+        tickets = None if os.environ.get("MESHTOK_DEC_SE_TAIL", "1") == "0" else torch.zeros(b, dtype=torch.int32, device=dev)   # self-resetting
         for i, blk in enumerate(blocks):
             cout = blk["c1"]["n"]
             if blk["c1r"] is not None:
@@ -249,7 +250,7 @@ class MeshDecoder(nn.Module):
             ws = torch.empty(b * S * (cout + 1), **f32)
             gate = torch.empty(b, cout, **f32)
             check(lib.meshtok_dec_pixelnorm_squeeze_excite_gate(ptr(h2), cout, ptr(valid), b, P, lead, cout, 1e-4, w1.shape[1], ptr(w1), ptr(b1),
-                                                                ptr(w2), ptr(b2), ptr(scale), ptr(ws), ptr(gate), stream_ptr()))
+                                                                ptr(w2), ptr(b2), ptr(scale), ptr(ws), ptr(tickets), ptr(gate), stream_ptr()))
             last = i + 1 == len(blocks)
             halo = 0 if last else 1
             out = torch.empty(R, cout, **f32)
