@@ -133,3 +133,46 @@ def test_face_edges_cache_file_format(tmp_path):
     assert np.load(ic_file, mmap_mode="r").tolist() == [False, True, True, True, True]
     with pytest.raises(AssertionError):
         M.write_face_edges_cache(tmp_path / "small", 5, 0, edges, max_edges_len=3)
+
+
+# ---- the decode path and the token-embedding front end: host-side contract (no kernel runs on CPU) ----
+
+def test_decoder_and_front_end_key_layout_matches_the_reference_names():
+    a = M.MeshAutoencoder(use_residual_lfq=False)
+    d = M.MeshDecoder(a)
+    sd = d.state_dict()
+    assert tuple(sd["init_decoder_conv.0.weight"].shape) == (128, 576, 7)            # Conv1d(dim_codebook * 3 -> 128, k = 7), :621-623
+    assert tuple(sd["init_decoder_conv.3.weight"].shape) == (128,)                   # LayerNorm sits at index 3 of the Sequential, :626
+    assert tuple(sd["decoders.3.residual_conv.weight"].shape) == (192, 128, 1)       # 128 -> 192: a 1x1 residual conv, :367
+    assert "decoders.0.residual_conv.weight" not in sd                               # 128 -> 128: nn.Identity
+    assert tuple(sd["decoders.15.block2.proj.weight"].shape) == (384, 384, 3)
+    assert tuple(sd["decoders.0.excite.net.0.weight"].shape) == (32, 128)            # max(dim // 4, 16), :304
+    assert tuple(sd["to_coor_logits.0.weight"].shape) == (128 * 9, 384)              # :639
+    fe = M.MeshTransformerFrontEnd(a, dim=512, max_seq_len=8190)
+    sd = fe.state_dict()
+    assert tuple(sd["token_embed.weight"].shape) == (16385, 512)                     # codebook_size + 1 (eos), :1158
+    assert tuple(sd["abs_pos_emb.weight"].shape) == (8190, 512)
+    assert tuple(sd["quantize_level_embed"].shape) == (2, 512) and tuple(sd["vertex_embed"].shape) == (3, 512)
+    assert tuple(sd["to_face_tokens.0.weight"].shape) == (512, 6 * 512) and tuple(sd["to_face_tokens.1.weight"].shape) == (512,)
+
+
+def test_decoder_and_front_end_refuse_what_they_do_not_cover():
+    a = M.MeshAutoencoder(**SMALL_CFG)
+    with pytest.raises(NotImplementedError):
+        M.MeshDecoder(a, attn_decoder_depth=2)
+    with pytest.raises(ValueError):
+        M.MeshDecoder(a, init_decoder_conv_kernel=4)
+    with pytest.raises(KeyError):
+        M.MeshDecoder(a, decoder_dims_through_depth=(32, 32)).load_reference_state_dict({})
+    with pytest.raises(ValueError):
+        M.MeshTransformerFrontEnd(a, dim=128, max_seq_len=100)                       # not a multiple of 3 x 2 codes per face (:1156)
+    with pytest.raises(NotImplementedError):
+        M.MeshTransformerFrontEnd(a, dim=100, max_seq_len=60)
+    fe = M.MeshTransformerFrontEnd(a, dim=128, max_seq_len=60)
+    with pytest.raises(KeyError):
+        fe.load_reference_state_dict({"token_embed.weight": torch.zeros(257, 128)})
+    with pytest.raises(RuntimeError):
+        fe.embed_codes(torch.zeros(1, 6, dtype=torch.int64))                         # CPU tensor: there is no CPU path
+    d = M.MeshDecoder(a, decoder_dims_through_depth=(32, 32))
+    with pytest.raises(RuntimeError):
+        d.decode_from_codes_to_faces(torch.zeros(1, 6, 2, dtype=torch.int64))
