@@ -20,7 +20,12 @@ m.load_reference_state_dict(o.state_dict())
 m = m.cuda()
 codes = torch.randint(0, K, (B, L), device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB), written between timed steps
-peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+try:
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))     # DRAM bytes per launch from the committed ncu capture
+except OSError:
+    traffic = {}
 
 
 def timed(fn, steps=10):
@@ -58,7 +63,8 @@ print(json.dumps(dict(
     metric="faces embedded/sec (fine tokens + face tokens, device-timed, L2 flushed between steps)", value=faces / (ms_both * 1e-3), unit="faces/s",
     ms_per_step=ms_both, meshes=B, gpu_launches_per_step=2,
     roofline=dict(kernel="face_tokens_kernel<4>", bound="hbm", achieved=bytes_face / (ms_face * 1e-3) / 1e9, peak=hbm, unit="GB/s",
-                  frac=bytes_face / (ms_face * 1e-3) / 1e9 / hbm, traffic=None, ms_per_launch=ms_face, bytes_per_launch=bytes_face),
+                  frac=bytes_face / (ms_face * 1e-3) / 1e9 / hbm,
+                  traffic=traffic.get("frontend_face_tokens", {}).get("dram_bytes_per_launch") if B == 64 else None, ms_per_launch=ms_face, bytes_per_launch=bytes_face),
     fine_tokens=dict(ms_per_launch=ms_fine, bytes_per_launch=bytes_fine, achieved_gbs=bytes_fine / (ms_fine * 1e-3) / 1e9,
                      frac_of_hbm_peak=bytes_fine / (ms_fine * 1e-3) / 1e9 / hbm),
     cpu_baseline=dict(value=n_cpu * NF / cpu_s, unit="faces/s", cores=os.cpu_count(), kind="port", sample=f"front-end oracle on {n_cpu} meshes"))))
