@@ -286,6 +286,13 @@ int meshtok_halo_image_bytes(int R, int C, int halo, size_t* bytes);
  * w_image = meshtok_linear_build_image of the (N, k * C_in) matrix weight.permute(0, 2, 1) (tap-major columns).  k = 1: a Linear. */
 int meshtok_conv1d(const void* a_halo_image, const void* w_image, const float* bias, float* out, int R, int N, int C_in, int k,
                    int halo, meshtok_stream_t stream);
+/* meshtok_conv1d with the Block tail (:345-351) in the epilogue: the first `width` output columns are written ONLY as the halo image
+ * (halo out_halo) of silu(PixelNorm(row, eps)), zero rows where valid is 0 - no fp32 copy, no separate pixelnorm_silu launch.  N == width,
+ * or N == 2 * width with residual_conv's rows in the second half: those go to out (R, N) fp32, columns width .. N (the first half of
+ * `out` is not written).  Needs width <= 256, a multiple of 32, so that a row is one pass of the kernel; otherwise MESHTOK_ERR_UNSUPPORTED
+ * (use meshtok_conv1d + meshtok_dec_pixelnorm_silu_halo). */
+int meshtok_conv1d_pixelnorm_silu(const void* a_halo_image, const void* w_image, const float* bias, const uint8_t* valid, float* out, int R, int N,
+                                  int C_in, int k, int halo, int width, float eps, int out_halo, void* out_image, meshtok_stream_t stream);
 /* number of face slices per mesh the SqueezeExcite partial sums use; slice_ws holds B * S * C floats + B * S int32 */
 int meshtok_dec_se_slices(int B, int nf);
 /* x (B * nf, C) fp32, UNPADDED rows -> halo image in the padded row space */

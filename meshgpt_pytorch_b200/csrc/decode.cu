@@ -872,6 +872,16 @@ int meshtok_conv1d(const void* a_halo_image, const void* w_image, const float* b
 
 #define MT_ROWSPACE_OK(R, P, lead) ((R) >= 0 && (lead) >= 0 && (P) > (lead) && ((R) - (lead)) % (P) == 0)
 
+/* Conv1d + the Block tail in the convolution's epilogue: the first `width` output columns (block1.proj / block2.proj) leave the kernel only
+ * as the halo image of silu(PixelNorm(row)); columns width .. N (residual_conv riding in the same launch, N == 2 * width) go to `out`. */
+int meshtok_conv1d_pixelnorm_silu(const void* a_halo_image, const void* w_image, const float* bias, const uint8_t* valid, float* out, int R, int N,
+                                  int C_in, int k, int halo, int width, float eps, int out_halo, void* out_image, meshtok_stream_t stream) {
+  MT_CHECK_ARG(a_halo_image && w_image && valid && out_image && R >= 0 && N > 0 && C_in > 0 && (N == width || (N == 2 * width && out)),
+               "conv1d_pixelnorm_silu: bad arguments (N must be width, or 2 * width with an fp32 output for the second half)");
+  ConvBlockTail tail{width, valid, out_image, out_halo, eps};
+  return launch_conv_tc(a_halo_image, C_in, k, halo, w_image, bias, out, N, R, static_cast<cudaStream_t>(stream), &tail);
+}
+
 int meshtok_dec_rows_halo(const float* x, int ld, const uint8_t* valid, int R, int P, int lead, int C, int halo, void* image, meshtok_stream_t stream) {
   MT_CHECK_ARG(x && valid && image && MT_ROWSPACE_OK(R, P, lead) && C % 32 == 0 && ld >= C && ld % 4 == 0 && halo >= 0 && halo <= lead,
                "rows_halo: width %d must be a multiple of 32, R = B * P + lead, halo <= lead", C);

@@ -150,8 +150,16 @@ int linear_tc_ssq_parts(int N);   // (column parts per pass) * passes of an N-wi
 int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width
 int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                      int N, const int* m_dev, int m_max, bool relu, const LinearRowEpilogue* epi, cudaStream_t stream);
+// Block tail fused into the convolution's epilogue (decode path): the first `width` output columns -> silu(PixelNorm(row)) as a halo image
+struct ConvBlockTail {
+  int width;
+  const uint8_t* valid;   // (rows) 0: zero image row
+  void* out_image;        // halo image (rows, width) with halo out_halo
+  int out_halo;
+  float eps;
+};
 int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, float* C, int N, int m_max,
-                   cudaStream_t stream);   // Conv1d over the rows of a halo image, see linear_tc.cu
+                   cudaStream_t stream, const ConvBlockTail* tail = nullptr);   // Conv1d over the rows of a halo image, see linear_tc.cu
 size_t rows_image_bytes(long long rows, int K);
 int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream);
 

@@ -84,7 +84,7 @@ struct LinArgs {
   const int* m_dev;
   int m_max;
   int relu;
-  int norm_mode;            // 0 plain, 1 row L2-normalise, 2 L2-normalise + SiLU + LayerNorm(gamma, beta)
+  int norm_mode;            // 0 plain, 1 row L2-normalise, 2 L2-normalise + SiLU + LayerNorm(gamma, beta), 3 PixelNorm + SiLU -> halo image
   const float* gamma;
   const float* beta;
   uint8_t* out_image;       // activation image of the output rows (K = N) or null
@@ -96,6 +96,12 @@ struct LinArgs {
   // holds rows -halo .. 128 + halo of the tile with consecutive rows 16 bytes apart, so tap t of the kernel is the SAME block read
   // through a descriptor that starts t * 16 bytes further (LBO = rows * 16, SBO = 128).  K = taps * K1, W columns tap-major.
   int conv, taps, halo;
+  // norm_mode 3 (decode path, Block tail :345-351): pass 0 of the launch holds whole rows of width NT; its epilogue writes
+  // silu(PixelNorm(row)) = silu(x * sqrt(NT) / max(|x|, eps)) ONLY as the halo image `out_image` (width NT, halo out_halo), zero rows
+  // where row_valid is 0.  A second pass (residual_conv riding in the same launch) takes the plain epilogue into C.
+  const uint8_t* row_valid;
+  int out_halo;
+  float norm_eps;
 };
 __host__ __device__ inline int lin_chunks(const LinArgs& a) { return (a.conv ? a.taps : 1) * (a.K1 / KC) + a.K2 / KC; }
 
@@ -150,7 +156,9 @@ struct UnitSeq {   // this CTA (pair)'s units in issue order
   }
 };
 
-template <bool PAIR, int CPARTS>
+// TAIL: the instantiation that carries the norm_mode 3 epilogue (decode path); the tokenizer's linears run the one without it
+// (with the extra epilogue in the same kernel they had 4 registers more and were 1 - 2 % slower)
+template <bool PAIR, int CPARTS, bool TAIL = false>
 __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   using G = Cfg<PAIR, CPARTS>;
   constexpr int EPI_WARPS = G::EPI_WARPS;
@@ -357,6 +365,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       }
     }
     named_bar_sync(3, EPI_WARPS * 32);
+    int tail_units = 0;
     for (int j = 0; j < n_units; ++j) {
       int phase, grp, pass, ti;
       seq.get(j, phase, grp, pass, ti);
@@ -374,9 +383,12 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * NT_MAX;
       const int n0 = pass * a.NT;
       const int row0 = m_tile * M_TILE + q * 32;
-      if (a.norm_mode != 0) {
-        // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0) ----
-        float* xs = reinterpret_cast<float*>(smem + G::XCH_OFF) + (ti & 1) * (3 * CPARTS * 128);   // alternates per phase-0 unit
+      const bool mode3 = TAIL && a.norm_mode == 3;
+      if (a.norm_mode != 0 && !(mode3 && pass != 0)) {
+        // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0; mode 3: pass 0 of at most two) ----
+        // alternates per phase-0 unit; mode 3 counts its own units (plain second-pass units in between have no barrier)
+        const int xsel = mode3 ? (tail_units++ & 1) : (ti & 1);
+        float* xs = reinterpret_cast<float*>(smem + G::XCH_OFF) + xsel * (3 * CPARTS * 128);
         const int rit = q * 32 + lane;
         const long long grow = (long long)row0 + lane;
         const bool live = grow < M;
@@ -420,7 +432,55 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         };
         // x / max(|x|, eps) is done as x * (1 / max(|x|, eps)): one rounding more than the reference's division, far
         // below the 1e-5 of the split-bf16 product itself, at a tenth of the instructions
-        if (a.norm_mode == 1) {
+        if (mode3) {
+          float ss = 0.f;
+          for (int c = c_lo; c < c_hi; c += 16) {
+            float o[16];
+            load16(c, o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) ss = fmaf(o[j], o[j], ss);
+          }
+          xs[cpart * 128 + rit] = ss;
+          named_bar_sync(2, EPI_WARPS * 32);
+          const bool okrow = live && a.row_valid[grow] != 0;
+          const float sc = sqrtf((float)a.NT) / fmaxf(sqrtf(xsum(0)), a.norm_eps);
+          const int halo = a.out_halo;
+          const long long tile = grow >> 7, n_tiles = ((long long)M + 127) >> 7;
+          const int r = (int)(grow & 127);
+          const uint32_t lo_off = 64u * (uint32_t)(IMG_ROWS + 2 * halo);
+          for (int c = c_lo; c < c_hi; c += 16) {
+            float o[16];
+            load16(c, o);
+            if (!live) continue;
+#pragma unroll
+            for (int gg = 0; gg < 2; ++gg) {
+              uint4 hi = make_uint4(0u, 0u, 0u, 0u), lo = hi;
+              if (okrow) {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { const float x = o[8 * gg + j] * sc; t[j] = __fdividef(x, 1.f + __expf(-x)); }
+                split2(t[0], t[1], hi.x, lo.x);
+                split2(t[2], t[3], hi.y, lo.y);
+                split2(t[4], t[5], hi.z, lo.z);
+                split2(t[6], t[7], hi.w, lo.w);
+              }
+              const int col = c + 8 * gg;
+              uint8_t* pimg = a.out_image + halo_offset(a.NT, halo, tile, r, col);
+              *reinterpret_cast<uint4*>(pimg) = hi;
+              *reinterpret_cast<uint4*>(pimg + lo_off) = lo;
+              if (r < halo && tile > 0) {                       // the copy behind the previous tile
+                pimg = a.out_image + halo_offset(a.NT, halo, tile - 1, r + IMG_ROWS, col);
+                *reinterpret_cast<uint4*>(pimg) = hi;
+                *reinterpret_cast<uint4*>(pimg + lo_off) = lo;
+              }
+              if (r >= IMG_ROWS - halo && tile + 1 < n_tiles) {  // the copy in front of the next tile
+                pimg = a.out_image + halo_offset(a.NT, halo, tile + 1, r - IMG_ROWS, col);
+                *reinterpret_cast<uint4*>(pimg) = hi;
+                *reinterpret_cast<uint4*>(pimg + lo_off) = lo;
+              }
+            }
+          }
+        } else if (a.norm_mode == 1) {
           float ss = 0.f;
           for (int c = c_lo; c < c_hi; c += 16) {
             float o[16];
@@ -523,7 +583,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) ss = fmaf(o[j], o[j], ss);
         }
-        if (a.out_image && live) {
+        if (a.out_image && live && !mode3) {   // (mode 3: out_image is the halo image of pass 0, not of these columns)
 #pragma unroll
           for (int gg = 0; gg < 2; ++gg) {
             uint4 hi, lo;
@@ -599,6 +659,8 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
 
 __global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<false, 2>(a); }
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2>(a); }
+__global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_tail_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<false, 2, true>(a); }
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_tail_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2, true>(a); }
 
 // W (N, K) fp32 -> image [pass][kchunk]{hi (NT x 32), lo (NT x 32)} canonical K-major, SBO 512.
 __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restrict__ W, int N, int K, int NT, uint8_t* __restrict__ image) {
@@ -712,6 +774,7 @@ static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a
   MT_CHECK_ARG(w_image != nullptr && a1_image != nullptr && (K2 == 0 || a2_image != nullptr), "tcgen05 linear: operand image is null");
   a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
   a.conv = 0; a.taps = 1; a.halo = 0;
+  a.row_valid = nullptr; a.out_halo = 0; a.norm_eps = 0.f;
   a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
   if (epi != nullptr && epi->norm_mode == 0) {
     // plain epilogue with the deferred-normalisation extras
@@ -753,19 +816,24 @@ static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
   if (!configured) {
     MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
     MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
+    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
+    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
     configured = true;
   }
   const int passes = g.nphase == 2 ? 1 : g.p[0].passes;
+  const bool tail = g.p[0].norm_mode == 3;   // decode path: Block tail in the epilogue
   if (linear_tc_pair()) {
     using P2 = Cfg<true, 2>;
     const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * passes;
     const int grid = 2 * min(units, 148 / 2);
-    MT_LAUNCH_PDL(linear_tc_pair_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, g);
+    if (tail) { MT_LAUNCH_PDL(linear_tc_pair_tail_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, g); }
+    else { MT_LAUNCH_PDL(linear_tc_pair_kernel, grid, P2::NUM_THREADS, P2::SMEM_TOTAL, stream, g); }
   } else {
     using S2 = Cfg<false, 2>;
     const int units = ceil_div(m_max, M_TILE) * passes;
     const int grid = min(units, 148);
-    MT_LAUNCH_PDL(linear_tc_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, g);
+    if (tail) { MT_LAUNCH_PDL(linear_tc_tail_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, g); }
+    else { MT_LAUNCH_PDL(linear_tc_kernel, grid, S2::NUM_THREADS, S2::SMEM_TOTAL, stream, g); }
   }
   return MESHTOK_OK;
 }
@@ -784,17 +852,35 @@ int launch_linear_tc(const void* a1_image, int K1, const void* a2_image, int K2,
 // Conv1d(C_in -> N, kernel `taps`) over the rows of a halo image (padded row space: at least taps / 2 zero rows between two meshes);
 // w_image = image of the (N, taps * C_in) matrix with tap-major columns
 int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, float* C, int N, int m_max,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const ConvBlockTail* tail) {
   if (m_max == 0) return MESHTOK_OK;
   MT_CHECK_ARG(taps >= 1 && (taps & 1) == 1 && halo >= taps / 2 && halo <= 8 && C_in % KC == 0, "tcgen05 conv: kernel %d must be odd, halo %d >= kernel / 2 and <= 8, C_in %d a multiple of %d", taps, halo, C_in, KC);
   LinArgs2 g;
   memset(&g, 0, sizeof(g));
   g.nphase = 1;
-  int rc = fill_lin_args(g.p[0], a_halo_image, C_in, nullptr, 0, w_image, bias, C, N, nullptr, m_max, false, nullptr);
+  // (a fused tail without a second pass has no fp32 output: fill_lin_args only needs to see SOME output pointer)
+  float* c_seen = (C == nullptr && tail != nullptr) ? static_cast<float*>(tail->out_image) : C;
+  int rc = fill_lin_args(g.p[0], a_halo_image, C_in, nullptr, 0, w_image, bias, c_seen, N, nullptr, m_max, false, nullptr);
   if (rc != MESHTOK_OK) return rc;
+  g.p[0].C = C;
   g.p[0].conv = 1; g.p[0].taps = taps; g.p[0].halo = halo;
   rc = linear_tc_plan(N, taps * C_in, 0, &g.p[0].passes, &g.p[0].NT);
   if (rc != MESHTOK_OK) return rc;
+  if (tail != nullptr) {
+    // the first tail->width output columns are whole rows of a Block: they must be exactly pass 0
+    if (g.p[0].NT != tail->width || g.p[0].passes > 2 || tail->width % KC != 0) {
+      set_error("tcgen05 conv: the fused Block tail needs the %d block columns to be one pass (N %d splits into %d passes of %d)", tail->width, N,
+                g.p[0].passes, g.p[0].NT);
+      return MESHTOK_ERR_UNSUPPORTED;
+    }
+    MT_CHECK_ARG(tail->valid && tail->out_image && tail->out_halo >= 0 && tail->out_halo <= 8 && (g.p[0].passes == 1 || C != nullptr),
+                 "tcgen05 conv: fused Block tail needs valid, an output image and (two passes) the fp32 output for the second pass");
+    g.p[0].norm_mode = 3;
+    g.p[0].row_valid = tail->valid;
+    g.p[0].out_image = static_cast<uint8_t*>(tail->out_image);
+    g.p[0].out_halo = tail->out_halo;
+    g.p[0].norm_eps = tail->eps;
+  }
   return launch_lin2(g, m_max, stream);
 }
 

@@ -189,6 +189,15 @@ class MeshDecoder(nn.Module):
         return (all(w % 32 == 0 for w in widths) and (self.nvf * self.dim_codebook) % 32 == 0 and self.dim_codebook % 8 == 0
                 and self.init_decoder_conv["0"].kernel_size[0] // 2 <= 8)
 
+    @staticmethod
+    def _tail_in_epilogue(n: int, cout: int) -> bool:
+        """True when the tcgen05 kernel's pass 0 is exactly the `cout` block columns (linear_tc_plan: fewest equal passes of a multiple of
+        16, at most 256 columns), i.e. when meshtok_conv1d_pixelnorm_silu covers this convolution."""
+        p = -(-n // 256)
+        while p <= n // 16 and (n % p != 0 or (n // p) % 16 != 0):
+            p += 1
+        return cout % 32 == 0 and n % p == 0 and n // p == cout and p <= 2
+
     @property
     def lead(self) -> int:
         """Separator rows in front of every mesh in the padded row space = half width of the widest kernel."""
@@ -233,17 +242,25 @@ class MeshDecoder(nn.Module):
         check(lib.meshtok_dec_silu_layernorm_halo(ptr(x0), ptr(valid), R, P, c, ptr(p["ln"][0]), ptr(p["ln"][1]), 1e-5, ptr(x), halo, ptr(img),
                                                   stream_ptr()))
         S = lib.meshtok_dec_se_slices(b, P - lead)
+        epi_tail = os.environ.get("MESHTOK_DEC_EPI", "1") != "0"
         tickets = None if os.environ.get("MESHTOK_DEC_SE_TAIL", "1") == "0" else torch.zeros(b, dtype=torch.int32, device=dev)   # self-resetting
         for i, blk in enumerate(blocks):
             cout = blk["c1"]["n"]
-            if blk["c1r"] is not None:
-                h = self._conv1d(img, R, blk["c1r"])                 # (R, 2 cout): [block1.proj | residual_conv]
-                ldh, res_ptr, ldres = 2 * cout, h.data_ptr() + 4 * cout, 2 * cout
-            else:
-                h = self._conv1d(img, R, blk["c1"])
-                ldh, res_ptr, ldres = cout, x.data_ptr(), x.shape[1]
+            w1 = blk["c1r"] if blk["c1r"] is not None else blk["c1"]
             img2 = self._halo_image(R, cout, 1, dev)
-            check(lib.meshtok_dec_pixelnorm_silu_halo(ptr(h), ldh, ptr(valid), R, P, cout, 1e-4, 1, ptr(img2), stream_ptr()))
+            if epi_tail and self._tail_in_epilogue(w1["n"], cout):
+                # block1.proj leaves the convolution only as the image of silu(PixelNorm(.)); residual_conv (second pass) as fp32
+                h = torch.empty(R, 2 * cout, **f32) if blk["c1r"] is not None else None
+                check(lib.meshtok_conv1d_pixelnorm_silu(ptr(img), ptr(w1["img"]), ptr(w1["bias"]), ptr(valid), ptr(h), R, w1["n"], w1["c"], w1["k"],
+                                                        w1["k"] // 2, cout, 1e-4, 1, ptr(img2), stream_ptr()))
+                res_ptr, ldres = (h.data_ptr() + 4 * cout, 2 * cout) if h is not None else (x.data_ptr(), x.shape[1])
+            else:
+                h = self._conv1d(img, R, w1)                         # c1r: (R, 2 cout) = [block1.proj | residual_conv]
+                if blk["c1r"] is not None:
+                    ldh, res_ptr, ldres = 2 * cout, h.data_ptr() + 4 * cout, 2 * cout
+                else:
+                    ldh, res_ptr, ldres = cout, x.data_ptr(), x.shape[1]
+                check(lib.meshtok_dec_pixelnorm_silu_halo(ptr(h), ldh, ptr(valid), R, P, cout, 1e-4, 1, ptr(img2), stream_ptr()))
             h2 = self._conv1d(img2, R, blk["c2"])
             w1, b1, w2, b2 = blk["se_t"]                              # transposed: (C, inner), (inner, C)
             scale = torch.empty(R, **f32)

@@ -2,7 +2,7 @@
 decode oracle on a sample.  Prints one JSON line for the fused schedule (graph replay = the number to quote, eager beside it) and
 one for the stage-by-stage schedule (MESHTOK_DEC_FUSED=0).
 
-    python scripts/gpu_decode_bench.py [meshes] [profile]      # profile: one eager step between cudaProfilerStart / Stop
+    python scripts/gpu_decode_bench.py [meshes] [profile | fusedonly]      # profile: one eager step between cudaProfilerStart / Stop
 """
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -48,7 +48,7 @@ if len(sys.argv) > 2 and sys.argv[2] == "profile":     # ncu --profile-from-star
 n_cpu = min(B, 8)
 t0 = time.perf_counter(); od.decode_from_codes_to_faces(codes[:n_cpu].cpu()); cpu_s = time.perf_counter() - t0
 cpu = dict(value=n_cpu * 800 / cpu_s, unit="faces/s", cores=os.cpu_count(), kind="port", sample=f"decode oracle on {n_cpu} meshes")
-for schedule in ("fused", "staged"):
+for schedule in (("fused",) if "fusedonly" in sys.argv else ("fused", "staged")):
     os.environ["MESHTOK_DEC_FUSED"] = "1" if schedule == "fused" else "0"
     l0 = lib.meshtok_kernel_launch_count()
     md.decode_from_codes_to_faces(codes)

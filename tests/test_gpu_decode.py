@@ -225,3 +225,27 @@ def test_fused_schedule_matches_the_staged_one(cfg, dims, kind, monkeypatch):
     assert float((d1[~m1]).abs().max()) == 0.0
     assert float((b1[m1] == b0[m1]).float().mean()) >= 0.995
     assert torch.isnan(c1[~m1]).all()
+
+
+@pytest.mark.parametrize("dims", [(32, 32, 64), (64, 160, 160), (128, 192, 256, 256)])
+def test_block_tail_in_the_convolution_epilogue_matches_the_separate_launch(dims, monkeypatch):
+    """meshtok_conv1d_pixelnorm_silu (PixelNorm + SiLU + mask in the epilogue of block1.proj's convolution; with a residual_conv the
+    block columns are pass 0 of two) against meshtok_conv1d + meshtok_dec_pixelnorm_silu_halo, and both against the oracle.
+    dims: one pass without residual_conv (32 -> 32), two passes (64 -> 160: N = 320 = 2 x 160; 128 -> 192, 192 -> 256), and blocks the
+    fused epilogue does not cover (32 -> 64: N = 128 is one pass of both halves) in the same decoder."""
+    cfg = dict(SMALL_CFG, use_residual_lfq=False)
+    o, m, od, md = make_decoders(cfg, dims)
+    widths = list(zip((dims[0],) + tuple(dims[:-1]), dims))                # (c_in, c_out) of every ResnetBlock
+    assert sum(md._tail_in_epilogue(c if ci == c else 2 * c, c) for ci, c in widths) >= 2
+    v, f = synth.ragged_batch("tri", 12, 12, [288, 131, 127, 1], [0, 1, 2, 3])
+    codes = m.tokenize(v.cuda(), f.cuda())
+    monkeypatch.setenv("MESHTOK_DEC_EPI", "1")
+    c1, b1, m1 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    monkeypatch.setenv("MESHTOK_DEC_EPI", "0")
+    c0, b0, m0 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    assert torch.equal(m0, m1)
+    assert float((b1[m1] == b0[m1]).float().mean()) >= 0.995
+    assert torch.isnan(c1[~m1]).all()
+    want_c, want_bins, want_mask = od.decode_from_codes_to_faces(codes.cpu(), return_discrete_codes=True)
+    assert torch.equal(m1.cpu(), want_mask)
+    assert float((b1.cpu()[want_mask] == want_bins[want_mask]).float().mean()) >= 0.99
