@@ -46,6 +46,7 @@ enum meshtok_status {
 #define MESHTOK_WS_STATUS_VERTEX_RANGE 1 /* a non-pad face references a vertex id outside [0, V) */
 #define MESHTOK_WS_STATUS_EDGE_OVERFLOW 2 /* more edges than edge_capacity */
 #define MESHTOK_WS_STATUS_EDGE_RANGE 4    /* a user-supplied edge references a face row outside the batch */
+#define MESHTOK_WS_STATUS_RAGGED_BOUNDS 8 /* ragged input: a mesh has more faces than F or more vertices than V, or decreasing offsets */
 
 int meshtok_version(void);
 const char* meshtok_last_error_string(void);
@@ -173,6 +174,18 @@ typedef struct meshtok_tokenize_args {
   int32_t gemm_simt;         /* 1: fp32 SIMT linears instead of the tcgen05 split-bf16 GEMM */
   int32_t keep_taps;         /* 1: also store the fp32 form of every intermediate activation (meshtok_tokenize_taps);
                                 0: activations that only feed tcgen05 linears exist as split-bf16 images only */
+  /* Ragged input (CSR of meshes, SURVEY 8f rank 3: what custom_collate, data.py:347-369, would have padded with pad_id).
+   * Both NULL: the padded layout above.  Both given (device, int32, B + 1 entries, non-decreasing, [0] == 0):
+   *   faces (total_faces, nvf), mesh b owns rows face_offsets[b] .. face_offsets[b + 1]; vertex ids are mesh-local;
+   *   vertices (vertex_offsets[B], 3), mesh b owns rows vertex_offsets[b] .. vertex_offsets[b + 1];
+   *   F and V are upper bounds of the per-mesh face / vertex counts (they size the workspace; a mesh above them sets
+   *   MESHTOK_WS_STATUS_RAGGED_BOUNDS and is tokenized as empty);
+   *   codes_out (total_faces * nvf, Q): the tokens of the meshes back to back, no pad tokens between them (a face that
+   *   contains pad_id still yields pad_id tokens); face_coords_out (total_faces, nvf * 3).
+   * Not available in this layout (MESHTOK_ERR_UNSUPPORTED): face_edges, encoded_in, encoded_out, quantized_out. */
+  const int32_t* face_offsets;
+  const int32_t* vertex_offsets;
+  int64_t total_faces;
 } meshtok_tokenize_args;
 
 int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E,

@@ -14,6 +14,7 @@ ABI_VERSION = 1
 WS_STATUS_VERTEX_RANGE = 1
 WS_STATUS_EDGE_OVERFLOW = 2
 WS_STATUS_EDGE_RANGE = 4
+WS_STATUS_RAGGED_BOUNDS = 8
 
 
 class SageLayer(C.Structure):
@@ -50,6 +51,7 @@ class TokenizeArgs(C.Structure):
         ("codes_out", C.c_void_p), ("encoded_out", C.c_void_p), ("face_coords_out", C.c_void_p),
         ("quantized_out", C.c_void_p), ("histogram", C.c_void_p),
         ("stop_after_encode", C.c_int32), ("rvq_exact", C.c_int32), ("gemm_simt", C.c_int32), ("keep_taps", C.c_int32),
+        ("face_offsets", C.c_void_p), ("vertex_offsets", C.c_void_p), ("total_faces", C.c_int64),
     ]
 
 

@@ -370,6 +370,8 @@ class MeshAutoencoder(nn.Module):
             raise IndexError("faces reference a vertex index outside [0, num_vertices) (the reference's gather would fail too)")
         if status & _lib.WS_STATUS_EDGE_RANGE:
             raise IndexError("face_edges reference a face outside the batch")
+        if status & _lib.WS_STATUS_RAGGED_BOUNDS:
+            raise IndexError("ragged input: a mesh has more faces / vertices than max_faces / max_vertices, or its offsets decrease")
         if status & _lib.WS_STATUS_EDGE_OVERFLOW:
             raise MeshtokError("edge buffer overflow")
 
@@ -454,6 +456,79 @@ class MeshAutoencoder(nn.Module):
         self.eval()
         codes = self.forward(vertices=vertices, faces=faces, face_edges=face_edges, return_codes=True, **kwargs)
         return codes[0] if batch_less else codes
+
+    # ---- ragged input: a CSR of meshes instead of pad_id padding --------------------
+    @torch.no_grad()
+    def tokenize_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, max_faces: Optional[int] = None,
+                        max_vertices: Optional[int] = None, histogram: Optional[Tensor] = None, return_face_coordinates: bool = False,
+                        check_status: bool = True):
+        """tokenize() for a batch that was never padded: what the reference's custom_collate (data.py:347-369) turns into
+        (b, nf, nvf) / (b, nv, 3) tensors full of pad_id stays a CSR of meshes here.
+
+        vertices (sum nv, 3) float and faces (sum nf, nvf) integer with MESH-LOCAL vertex ids, both CUDA; face_offsets / vertex_offsets:
+        B + 1 non-decreasing integers starting at 0 (list, CPU tensor or CUDA tensor): mesh b owns faces[face_offsets[b]:face_offsets[b+1]]
+        and vertices[vertex_offsets[b]:vertex_offsets[b+1]].  Returns codes (sum nf * nvf, num_quantizers) int64, the token sequences of
+        the meshes back to back: exactly tokenize(padded batch) with the pad tokens removed (same kernels, same summation orders).
+        max_faces / max_vertices: upper bounds of the per-mesh counts; computed from the offsets when omitted (a device sync if the
+        offsets live on the GPU).  The same kernels run as for the padded layout; only the three that touch the inputs and the output
+        (topology_kernel, face_bins_kernel, gather_codes_ragged_kernel) address them through the offsets."""
+        prep = self._prepare()
+        dev = prep["device"]
+        if not (faces.is_cuda and vertices.is_cuda):
+            raise RuntimeError("inputs must be CUDA tensors (no CPU path)")
+        nvf, Q = self.num_vertices_per_face, self.num_quantizers
+        assert faces.ndim == 2 and faces.shape[1] == nvf, f"faces must be (sum nf, {nvf})"
+        assert vertices.ndim == 2 and vertices.shape[1] == 3, "vertices must be (sum nv, 3)"
+        if self.training:
+            self.eval()
+
+        def offsets(o, total, what):
+            o = torch.as_tensor(o)
+            assert o.ndim == 1 and o.numel() >= 1 and not o.is_floating_point(), f"{what} must be B + 1 integers"
+            if not o.is_cuda:     # host-side offsets (the usual case: the loader knows the mesh sizes) are checked without a device sync
+                d = o[1:] - o[:-1]
+                assert int(o[0]) == 0 and int(o[-1]) == total and bool((d >= 0).all()), f"{what} must rise from 0 to {total}"
+                return o.to(device=dev, dtype=torch.int32), (int(d.max()) if d.numel() else 0)
+            return o.to(torch.int32).contiguous(), None
+        fo, fmax = offsets(face_offsets, faces.shape[0], "face_offsets")
+        vo, vmax = offsets(vertex_offsets, vertices.shape[0], "vertex_offsets")
+        assert fo.numel() == vo.numel(), "face_offsets and vertex_offsets must have B + 1 entries each"
+        B = fo.numel() - 1
+        if max_faces is None:
+            max_faces = fmax if fmax is not None else (int((fo[1:] - fo[:-1]).max()) if B else 0)
+        if max_vertices is None:
+            max_vertices = vmax if vmax is not None else (int((vo[1:] - vo[:-1]).max()) if B else 0)
+        total = faces.shape[0]
+        codes = torch.empty((total * nvf, Q), dtype=torch.int64, device=dev)
+        coords = torch.empty((total, nvf * 3), dtype=torch.int64, device=dev) if return_face_coordinates else None
+        if B == 0 or total == 0:
+            return (codes, coords) if return_face_coordinates else codes
+        F, V = max(int(max_faces), 1), max(int(max_vertices), 1)
+        faces64 = faces.to(torch.int64).contiguous()
+        vertices = vertices.to(torch.float32).contiguous()
+        cap = max(1024, self.edge_slots_per_face * B * F)
+        with torch.cuda.device(dev):
+            while True:
+                ws = self._workspace(prep, B, F, V, 0, cap, "ragged")
+                a = TokenizeArgs()
+                a.vertices, a.faces, a.face_offsets, a.vertex_offsets, a.total_faces = ptr(vertices), ptr(faces64), ptr(fo), ptr(vo), total
+                a.B, a.F, a.V, a.E = B, F, V, 0
+                a.pad_id, a.edge_capacity = int(self.pad_id), cap
+                a.codes_out, a.face_coords_out, a.histogram = ptr(codes), ptr(coords), ptr(histogram)
+                a.rvq_exact = int(self.force_rvq_exact or not prep["tc_rvq"])
+                a.gemm_simt = int(self.force_gemm_simt or not prep["tc_gemm"])
+                check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
+                self.last_workspace, self.last_shape = ws, (B, F, V, 0, cap)
+                if not check_status:
+                    break
+                status = int(ws[:4].view(torch.int32).item())
+                if status & _lib.WS_STATUS_EDGE_OVERFLOW and histogram is None:
+                    cap *= 4
+                    self.edge_slots_per_face *= 4
+                    continue
+                self._raise_on_status(status)
+                break
+        return (codes, coords) if return_face_coordinates else codes
 
     # ---- CUDA-graph replay of the whole pipeline ----------------------------------------------------
     def graphed(self, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None,

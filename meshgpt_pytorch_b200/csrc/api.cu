@@ -410,6 +410,15 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   MT_CHECK_ARG(a->face_edges == nullptr || a->E > 0, "face_edges given but E <= 0 (pass one all-pad edge for an empty list)");
   const int B = a->B, F = a->F, V = a->V, nvf = m->nvf, D = m->dim_codebook, Q = m->num_quantizers;
   const int E = a->face_edges ? a->E : 0;
+  const bool ragged = a->face_offsets != nullptr || a->vertex_offsets != nullptr;
+  if (ragged) {
+    MT_CHECK_ARG(a->face_offsets != nullptr && a->vertex_offsets != nullptr && a->total_faces >= 0 && a->total_faces <= (long long)B * F,
+                 "ragged input needs face_offsets and vertex_offsets (B + 1 int32 each) and 0 <= total_faces <= B * F");
+    if (a->face_edges || a->encoded_in || a->encoded_out || a->quantized_out) {
+      set_error("ragged input: face_edges, encoded_in, encoded_out and quantized_out exist only in the padded layout");
+      return MESHTOK_ERR_UNSUPPORTED;
+    }
+  }
   rc = topo_check_shape(B, F, nvf, V);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(a->edge_capacity > 0 && a->edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
@@ -433,6 +442,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   TopoParams p;
   memset(&p, 0, sizeof(p));
   p.faces = a->faces; p.B = B; p.F = F; p.nvf = nvf; p.V = V; p.pad_id = a->pad_id;
+  p.in_face_off = a->face_offsets; p.in_vert_off = a->vertex_offsets;
   p.threshold = 2; p.include_self = 1; p.do_adjacency = a->face_edges ? 0 : 1;
   p.status = w.status; p.mesh_counts = w.mesh_counts; p.deg_out = w.deg_out; p.deg_in = w.deg_in;
   p.mesh_prefix = w.mesh_counts + 4 * (size_t)B; p.ticket = w.mesh_counts + 8 * (size_t)B; p.counts = w.counts;
@@ -486,6 +496,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     FeatParams fp;
     memset(&fp, 0, sizeof(fp));
     fp.vertices = a->vertices; fp.faces = a->faces; fp.row_face = w.row_face; fp.counts = w.counts;
+    fp.in_face_off = a->face_offsets; fp.in_vert_off = a->vertex_offsets;
     fp.F = F; fp.V = V; fp.nvf = nvf; fp.D = D;
     fp.coor_lo = m->coor_lo;
     fp.coor_den = (float)((double)m->coor_hi - (double)m->coor_lo);
@@ -505,7 +516,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     fp.x0 = (simt || a->keep_taps) ? w.x0 : nullptr; fp.x0_image = simt ? nullptr : w.img_x[0]; fp.face_coords_out = a->face_coords_out;
     fp.bins_out = w.bins;
     if (a->face_coords_out)
-      MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)max_rows * nvf * 3, s));
+      MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(ragged ? a->total_faces : max_rows) * nvf * 3, s));
     { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }
 
     // tcgen05 path: every activation that feeds a linear exists as a split-bf16 image, written by the kernel that
@@ -625,7 +636,10 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   }
   { ProfScope ps(PROF_GATHER_CODES, s);
-    if ((rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out, s)) != MESHTOK_OK) return rc;
+    if (ragged) rc = launch_gather_codes_ragged(a->faces, a->face_offsets, w.face_row, w.vert_row, w.vcodes, a->total_faces, B, F, nvf, V, Q, a->pad_id,
+                                                a->codes_out, s);
+    else rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out, s);
+    if (rc != MESHTOK_OK) return rc;
     if (a->histogram)
       if ((rc = launch_histogram(w.vptr, w.vcodes, w.counts, max_vrows, Q, m->codebook_size,
                                  reinterpret_cast<unsigned long long*>(a->histogram), s)) != MESHTOK_OK) return rc; }

@@ -54,12 +54,15 @@ __global__ void __launch_bounds__(128) face_bins_kernel(FeatParams p) {
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
     const int pf = p.row_face[row];
     const int b = pf / p.F;
-    const int64_t* fptr = p.faces + (size_t)pf * NVF;
+    // where the face and its mesh's vertices sit in the inputs: slot b*F+f of the padded layout, or row in_face_off[b] + f of the ragged one
+    const size_t in_face = p.in_face_off ? (size_t)p.in_face_off[b] + (size_t)(pf - b * p.F) : (size_t)pf;
+    const size_t in_vert0 = p.in_vert_off ? (size_t)p.in_vert_off[b] : (size_t)b * p.V;
+    const int64_t* fptr = p.faces + in_face * NVF;
     float pos[NVF][3];
 #pragma unroll
     for (int k = 0; k < NVF; ++k) {
       const long long v = fptr[k];
-      const float* src = p.vertices + ((size_t)b * p.V + (size_t)v) * 3;
+      const float* src = p.vertices + (in_vert0 + (size_t)v) * 3;
       pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
     }
     unsigned short bins[NSLOT];
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(128) face_bins_kernel(FeatParams p) {
       dst[s / 2] = (uint32_t)(p.slot_off[s] + bins[s]) | ((uint32_t)(p.slot_off[s + 1] + bins[s + 1]) << 16);
     if (p.face_coords_out) {
 #pragma unroll
-      for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[(size_t)pf * (NVF * 3) + s] = bins[s];
+      for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[in_face * (NVF * 3) + s] = bins[s];
     }
   }
   pdl_launch_dependents();

@@ -9,6 +9,8 @@ struct FeatParams {
   const float* vertices;    // (B,V,3)
   const int64_t* faces;     // (B,F,nvf)
   const int* row_face;      // packed row -> b*F+f
+  const int32_t* in_face_off;   // ragged input ([B+1] each, null: padded layout): faces (in_face_off[B], nvf), vertices (in_vert_off[B], 3),
+  const int32_t* in_vert_off;   // face_coords_out (in_face_off[B], nvf*3)
   const Counts* counts;
   int F, V, nvf, D;
   float coor_lo, coor_den, angle_den, area_den, clip_lo, clip_hi;
@@ -61,6 +63,8 @@ int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* count
                      unsigned long long* hist, cudaStream_t stream);
 // quantized_out[b, f, c*D:(c+1)*D] = qrows[vert_row[b, faces[b,f,c]]]; padded faces get the pad-vertex row,
 // which the reference leaves at zero for LFQ / at the (zero) input for RVQ.
+int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off, const int* face_row, const int* vert_row, const int32_t* vcodes,
+                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream);
 int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
                             int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream);
 // encoded_out (B*F, d) <- packed rows, zeros on padded faces.

@@ -213,6 +213,32 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
   }
 }
 
+// The same for the ragged input layout: one thread per token of the flat (total_faces * nvf) sequence; the mesh of a face is found
+// by bisection in the (B + 1) input offsets (L1 resident), which gives its slot b * F + f in the workspace's maps.
+__global__ void __launch_bounds__(256) gather_codes_ragged_kernel(const int64_t* __restrict__ faces, const int32_t* __restrict__ in_face_off,
+                                                                  const int* __restrict__ face_row, const int* __restrict__ vert_row,
+                                                                  const int32_t* __restrict__ vcodes, long long total_faces, int B, int F,
+                                                                  int nvf, int V, int Q, int64_t pad_id, int64_t* __restrict__ codes_out) {
+  pdl_wait();
+  const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= total_faces * nvf) return;
+  const int g = (int)(tok / nvf);
+  int lo = 0, hi = B;            // the last b with in_face_off[b] <= g (empty meshes repeat an offset: the last one owns the face)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(in_face_off + mid) <= g) lo = mid; else hi = mid;
+  }
+  const int b = lo, f = g - __ldg(in_face_off + b);
+  int64_t* dst = codes_out + tok * Q;
+  const int row = (f < F && g < __ldg(in_face_off + b + 1)) ? face_row[(size_t)b * F + f] : -1;
+  if (row < 0) {
+    for (int q = 0; q < Q; ++q) dst[q] = pad_id;
+    return;
+  }
+  const int vr = vert_row[(size_t)b * V + faces[tok]];
+  for (int q = 0; q < Q; ++q) dst[q] = vcodes[(size_t)vr * Q + q];
+}
+
 // hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex.
 // One weighted atomic per DISTINCT code per warp and level: the 32 rows of a warp are combined first (codebook usage
 // is skewed, so many rows of a warp share a code and un-aggregated atomics serialise on a few hot addresses).
@@ -325,6 +351,15 @@ int launch_gather_codes(const int64_t* faces, const int* face_row, const int* ve
   if (n == 0) return MESHTOK_OK;
   MT_LAUNCH_PDL(gather_codes_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q, pad_id,
                 codes_out);
+  return MESHTOK_OK;
+}
+
+int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off, const int* face_row, const int* vert_row, const int32_t* vcodes,
+                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream) {
+  const long long n = total_faces * nvf;
+  if (n == 0) return MESHTOK_OK;
+  MT_LAUNCH_PDL(gather_codes_ragged_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, faces, in_face_off, face_row, vert_row, vcodes, total_faces,
+                B, F, nvf, V, Q, pad_id, codes_out);
   return MESHTOK_OK;
 }
 

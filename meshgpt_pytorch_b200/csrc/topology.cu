@@ -89,11 +89,22 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   // ---- 1. faces -------------------------------------------------------------------------------
   int bad = 0;
   const int64_t* fsrc = p.faces + (size_t)b * FN;
+  int fn_b = FN, v_b = V;   // this mesh's own (face, slot) and vertex counts: the padded sizes unless the input is ragged
+  if (p.in_face_off != nullptr) {
+    const int f0 = p.in_face_off[b], f1 = p.in_face_off[b + 1], v0 = p.in_vert_off[b], v1 = p.in_vert_off[b + 1];
+    fsrc = p.faces + (size_t)f0 * nvf;
+    fn_b = (f1 - f0) * nvf;
+    v_b = v1 - v0;
+    if (f0 < 0 || f1 < f0 || f1 - f0 > F || v1 < v0 || v_b > V) {   // does not fit the workspace: an empty mesh + a status bit
+      fn_b = 0;
+      if (tid == 0) atomicOr(p.status, MESHTOK_WS_STATUS_RAGGED_BOUNDS);
+    }
+  }
   for (int idx = tid; idx < FN; idx += nt) {
-    const long long v = fsrc[idx];
+    const long long v = idx < fn_b ? fsrc[idx] : p.pad_id;
     int iv;
     if (v == p.pad_id) iv = -1;
-    else if (v < 0 || v >= V) { iv = -1; bad = 1; }
+    else if (v < 0 || v >= v_b) { iv = -1; bad = 1; }
     else iv = (int)v;
     fv[idx] = iv;
   }

@@ -4,7 +4,9 @@
 namespace meshtok {
 
 struct TopoParams {
-  const int64_t* faces;   // (B,F,nvf)
+  const int64_t* faces;   // (B,F,nvf); ragged: (in_face_off[B], nvf)
+  const int32_t* in_face_off;   // ragged input: [B+1] first face of every mesh in `faces` (null: padded layout)
+  const int32_t* in_vert_off;   // ragged input: [B+1] first vertex of every mesh (only the per-mesh vertex COUNT is used here)
   int B, F, nvf, V;
   int64_t pad_id;
   int threshold;          // shared-slot threshold (2, or 1 for neighbor_if_share_one_vertex)

@@ -127,3 +127,55 @@ def cache_face_edges(faces: Tensor, cache_path, dataset_len: int, start: int, ma
     reference's face-edge cache for meshes [start, start + b) in one go instead of one Python call per __getitem__."""
     edges = derive_face_edges_from_faces(faces, pad_id=pad_id)
     return write_face_edges_cache(cache_path, dataset_len, start, edges, max_edges_len, pad_id, assert_edge_len_lt_max)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ragged batches: a CSR of meshes instead of the reference's pad_id padding (SURVEY section 8f, rank 3)
+# ---------------------------------------------------------------------------------------------------
+def ragged_collate(data, keys=("vertices", "faces")):
+    """Counterpart of the reference's custom_collate (meshgpt_pytorch/data.py:347-369) that does not pad: a list of meshes (dicts with
+    'vertices' (nv_i, 3) and 'faces' (nf_i, nvf), or (vertices, faces) tuples) -> dict(vertices (sum nv, 3), faces (sum nf, nvf),
+    face_offsets (B + 1) int32, vertex_offsets (B + 1) int32), the arguments of MeshAutoencoder.tokenize_ragged.  Vertex ids stay
+    mesh-local.  Offsets are CPU tensors (the loader knows the sizes; keeping them on the host spares tokenize_ragged a device sync)."""
+    vs, fs = [], []
+    for item in data:
+        v, f = (item[keys[0]], item[keys[1]]) if isinstance(item, dict) else (item[0], item[1])
+        assert v.ndim == 2 and v.shape[1] == 3 and f.ndim == 2, "a mesh is vertices (nv, 3) and faces (nf, nvf)"
+        vs.append(v)
+        fs.append(f)
+    nvf = fs[0].shape[1] if fs else 3
+    face_offsets = torch.zeros(len(fs) + 1, dtype=torch.int32)
+    vertex_offsets = torch.zeros(len(vs) + 1, dtype=torch.int32)
+    if fs:
+        face_offsets[1:] = torch.tensor([f.shape[0] for f in fs]).cumsum(0)
+        vertex_offsets[1:] = torch.tensor([v.shape[0] for v in vs]).cumsum(0)
+    return dict(vertices=torch.cat(vs) if vs else torch.zeros(0, 3), faces=torch.cat(fs) if fs else torch.zeros(0, nvf, dtype=torch.long),
+                face_offsets=face_offsets, vertex_offsets=vertex_offsets)
+
+
+def padded_to_ragged(vertices: Tensor, faces: Tensor, pad_id: int = -1, num_vertices=None):
+    """A custom_collate batch (vertices (b, nv, 3), faces (b, nf, nvf), trailing pad_id padding, data.py:347-369) -> the ragged_collate
+    form of the same meshes.  A mesh's faces are its leading rows without a pad_id entry (the reference's face mask, meshgpt_pytorch.py:
+    996, on trailing padding); its vertices are the first num_vertices[i] rows (default: up to the largest vertex id its faces use)."""
+    assert vertices.ndim == 3 and faces.ndim == 3 and vertices.shape[0] == faces.shape[0]
+    meshes = []
+    for i in range(faces.shape[0]):
+        valid = (faces[i] != pad_id).all(dim=-1)
+        nf = int(valid.sum())
+        assert bool(valid[:nf].all()), "padding must be trailing (data.py:358)"
+        f = faces[i, :nf]
+        nv = int(num_vertices[i]) if num_vertices is not None else (int(f.max()) + 1 if nf else 0)
+        meshes.append((vertices[i, :nv], f))
+    return ragged_collate(meshes)
+
+
+def ragged_to_padded_codes(codes: Tensor, face_offsets, nvf: int, pad_id: int = -1) -> Tensor:
+    """codes (sum nf * nvf, Q) from tokenize_ragged -> (b, max nf * nvf, Q) padded with pad_id: the tensor the reference's tokenize
+    returns for the custom_collate batch of the same meshes (meshgpt_pytorch.py:861-866)."""
+    fo = torch.as_tensor(face_offsets).long().cpu()
+    n = (fo[1:] - fo[:-1]) * nvf
+    B, T = n.numel(), (int(n.max()) if n.numel() else 0)
+    out = torch.full((B, T, codes.shape[-1]), pad_id, dtype=codes.dtype, device=codes.device)
+    for b in range(B):
+        out[b, : int(n[b])] = codes[int(fo[b]) * nvf: int(fo[b + 1]) * nvf]
+    return out

@@ -176,3 +176,42 @@ def test_decoder_and_front_end_refuse_what_they_do_not_cover():
     d = M.MeshDecoder(a, decoder_dims_through_depth=(32, 32))
     with pytest.raises(RuntimeError):
         d.decode_from_codes_to_faces(torch.zeros(1, 6, 2, dtype=torch.int64))
+
+
+def test_ragged_collate_is_custom_collate_without_the_padding():
+    """ragged_collate / padded_to_ragged / ragged_to_padded_codes against the padded form of the same meshes
+    (synth.ragged_batch pads like the reference's custom_collate, data.py:347-369)."""
+    from meshgpt_pytorch_b200 import data as Dt
+    counts = [13, 1, 40]
+    v, f = synth.ragged_batch("tri", 5, 4, counts, [0, 1, 2])
+    r = Dt.padded_to_ragged(v, f)
+    assert r["face_offsets"].tolist() == [0, 13, 14, 54] and r["face_offsets"].dtype == torch.int32
+    assert r["faces"].shape == (54, 3) and int(r["faces"].min()) >= 0
+    nv = [int(f[i][: counts[i]].max()) + 1 for i in range(3)]
+    assert r["vertex_offsets"].tolist() == [0, nv[0], nv[0] + nv[1], sum(nv)]
+    for i in range(3):
+        fo, vo = r["face_offsets"], r["vertex_offsets"]
+        assert torch.equal(r["faces"][fo[i]:fo[i + 1]], f[i, : counts[i]])                        # vertex ids stay mesh-local
+        assert torch.equal(r["vertices"][vo[i]:vo[i + 1]], v[i, : nv[i]])
+    # dict items, the reference's dataset item form
+    r2 = Dt.ragged_collate([dict(vertices=v[i, : nv[i]], faces=f[i, : counts[i]]) for i in range(3)])
+    assert all(torch.equal(r[k], r2[k]) for k in r)
+    # flat codes -> the padded tensor tokenize returns
+    codes = torch.arange(54 * 3 * 2).view(54 * 3, 2)
+    padded = Dt.ragged_to_padded_codes(codes, r["face_offsets"], 3)
+    assert padded.shape == (3, 40 * 3, 2)
+    assert torch.equal(padded[1, :3], codes[13 * 3: 14 * 3]) and bool((padded[1, 3:] == -1).all())
+    assert torch.equal(padded[2], codes[14 * 3:])
+    # padding that is not trailing is refused (the reference's prefix assumption, meshgpt_pytorch.py:748-750)
+    g = f.clone()
+    g[0, 2] = -1
+    with pytest.raises(AssertionError):
+        Dt.padded_to_ragged(v, g)
+    empty = Dt.ragged_collate([])
+    assert empty["face_offsets"].tolist() == [0] and empty["faces"].shape == (0, 3)
+
+
+def test_tokenize_ragged_needs_cuda_tensors():
+    m = M.MeshAutoencoder(**SMALL_CFG)
+    with pytest.raises((RuntimeError, AssertionError)):
+        m.tokenize_ragged(torch.zeros(3, 3), torch.zeros(1, 3, dtype=torch.long), [0, 1], [0, 3])
