@@ -180,12 +180,17 @@ typedef struct meshtok_tokenize_args {
    *   vertices (vertex_offsets[B], 3), mesh b owns rows vertex_offsets[b] .. vertex_offsets[b + 1];
    *   F and V are upper bounds of the per-mesh face / vertex counts (they size the workspace; a mesh above them sets
    *   MESHTOK_WS_STATUS_RAGGED_BOUNDS and is tokenized as empty);
+   *   total_faces = rows the faces / codes_out buffers hold (>= face_offsets[B], the live count the kernels use; a capacity is fine);
    *   codes_out (total_faces * nvf, Q): the tokens of the meshes back to back, no pad tokens between them (a face that
    *   contains pad_id still yields pad_id tokens); face_coords_out (total_faces, nvf * 3).
-   * Not available in this layout (MESHTOK_ERR_UNSUPPORTED): face_edges, encoded_in, encoded_out, quantized_out. */
+   *   face_edges (optional) (total_edges, 2) with mesh-local face indices, mesh b owns rows edge_offsets[b] .. edge_offsets[b + 1]
+   *   (E > 0 is then only the "edges are given" flag; edge_capacity >= total_edges).
+   * Not available in this layout (MESHTOK_ERR_UNSUPPORTED): encoded_in, encoded_out, quantized_out. */
   const int32_t* face_offsets;
   const int32_t* vertex_offsets;
   int64_t total_faces;
+  const int32_t* edge_offsets;
+  int64_t total_edges;
 } meshtok_tokenize_args;
 
 int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E,

@@ -52,6 +52,7 @@ class TokenizeArgs(C.Structure):
         ("quantized_out", C.c_void_p), ("histogram", C.c_void_p),
         ("stop_after_encode", C.c_int32), ("rvq_exact", C.c_int32), ("gemm_simt", C.c_int32), ("keep_taps", C.c_int32),
         ("face_offsets", C.c_void_p), ("vertex_offsets", C.c_void_p), ("total_faces", C.c_int64),
+        ("edge_offsets", C.c_void_p), ("total_edges", C.c_int64),
     ]
 
 

@@ -459,8 +459,8 @@ class MeshAutoencoder(nn.Module):
 
     # ---- ragged input: a CSR of meshes instead of pad_id padding --------------------
     @torch.no_grad()
-    def tokenize_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, max_faces: Optional[int] = None,
-                        max_vertices: Optional[int] = None, histogram: Optional[Tensor] = None, return_face_coordinates: bool = False,
+    def tokenize_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, face_edges: Optional[Tensor] = None,
+                        edge_offsets=None, max_faces: Optional[int] = None, max_vertices: Optional[int] = None, histogram: Optional[Tensor] = None, return_face_coordinates: bool = False,
                         check_status: bool = True):
         """tokenize() for a batch that was never padded: what the reference's custom_collate (data.py:347-369) turns into
         (b, nf, nvf) / (b, nv, 3) tensors full of pad_id stays a CSR of meshes here.
@@ -469,6 +469,8 @@ class MeshAutoencoder(nn.Module):
         B + 1 non-decreasing integers starting at 0 (list, CPU tensor or CUDA tensor): mesh b owns faces[face_offsets[b]:face_offsets[b+1]]
         and vertices[vertex_offsets[b]:vertex_offsets[b+1]].  Returns codes (sum nf * nvf, num_quantizers) int64, the token sequences of
         the meshes back to back: exactly tokenize(padded batch) with the pad tokens removed (same kernels, same summation orders).
+        face_edges (sum ne, 2) + edge_offsets (B + 1), optional: precomputed edges (the face-edge cache's content without its padding)
+        with MESH-LOCAL face indices, any order, duplicates allowed - the ragged form of tokenize(face_edges=...).
         max_faces / max_vertices: upper bounds of the per-mesh counts; computed from the offsets when omitted (a device sync if the
         offsets live on the GPU).  The same kernels run as for the padded layout; only the three that touch the inputs and the output
         (topology_kernel, face_bins_kernel, gather_codes_ragged_kernel) address them through the offsets."""
@@ -494,6 +496,16 @@ class MeshAutoencoder(nn.Module):
         vo, vmax = offsets(vertex_offsets, vertices.shape[0], "vertex_offsets")
         assert fo.numel() == vo.numel(), "face_offsets and vertex_offsets must have B + 1 entries each"
         B = fo.numel() - 1
+        eo, n_edges = None, 0
+        if face_edges is not None:
+            assert edge_offsets is not None and face_edges.is_cuda and face_edges.ndim == 2 and face_edges.shape[1] == 2, \
+                "face_edges must be a CUDA tensor (sum ne, 2) with edge_offsets"
+            n_edges = face_edges.shape[0]
+            eo, _ = offsets(edge_offsets, n_edges, "edge_offsets")
+            assert eo.numel() == B + 1, "edge_offsets must have B + 1 entries"
+            face_edges = face_edges.to(torch.int64).contiguous()
+            if n_edges == 0:      # an empty list still means "edges are given": one all-pad edge, like the padded layout
+                face_edges = torch.full((1, 2), self.pad_id, dtype=torch.int64, device=dev)
         if max_faces is None:
             max_faces = fmax if fmax is not None else (int((fo[1:] - fo[:-1]).max()) if B else 0)
         if max_vertices is None:
@@ -506,29 +518,43 @@ class MeshAutoencoder(nn.Module):
         F, V = max(int(max_faces), 1), max(int(max_vertices), 1)
         faces64 = faces.to(torch.int64).contiguous()
         vertices = vertices.to(torch.float32).contiguous()
-        cap = max(1024, self.edge_slots_per_face * B * F)
-        with torch.cuda.device(dev):
+        self._launch_ragged(vertices, faces64, fo, vo, B, F, V, total, codes, coords, histogram, face_edges, eo, n_edges, check_status, "ragged")
+        return (codes, coords) if return_face_coordinates else codes
+
+    def _launch_ragged(self, vertices, faces64, fo, vo, B, F, V, total, codes, coords=None, histogram=None, face_edges=None, eo=None,
+                       n_edges=0, check_status=True, workspace_tag="ragged"):
+        """One meshtok_tokenize call in the ragged layout on prepared device tensors.  `total` is the number of face rows the buffers
+        hold (the kernels take the live count from face_offsets[B] on the device, so it may be a capacity)."""
+        prep = self._prepare()
+        E = 0 if face_edges is None else 1      # only the "edges are given" flag in this layout
+        cap = max(1024, self.edge_slots_per_face * B * F, n_edges)
+        with torch.cuda.device(prep["device"]):
             while True:
-                ws = self._workspace(prep, B, F, V, 0, cap, "ragged")
+                ws = self._workspace(prep, B, F, V, E, cap, workspace_tag)
                 a = TokenizeArgs()
                 a.vertices, a.faces, a.face_offsets, a.vertex_offsets, a.total_faces = ptr(vertices), ptr(faces64), ptr(fo), ptr(vo), total
-                a.B, a.F, a.V, a.E = B, F, V, 0
+                a.face_edges, a.edge_offsets, a.total_edges = ptr(face_edges), ptr(eo), n_edges
+                a.B, a.F, a.V, a.E = B, F, V, E
                 a.pad_id, a.edge_capacity = int(self.pad_id), cap
                 a.codes_out, a.face_coords_out, a.histogram = ptr(codes), ptr(coords), ptr(histogram)
                 a.rvq_exact = int(self.force_rvq_exact or not prep["tc_rvq"])
                 a.gemm_simt = int(self.force_gemm_simt or not prep["tc_gemm"])
                 check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
-                self.last_workspace, self.last_shape = ws, (B, F, V, 0, cap)
+                self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
                 if not check_status:
                     break
                 status = int(ws[:4].view(torch.int32).item())
-                if status & _lib.WS_STATUS_EDGE_OVERFLOW and histogram is None:
+                if status & _lib.WS_STATUS_EDGE_OVERFLOW and histogram is None and face_edges is None:
                     cap *= 4
                     self.edge_slots_per_face *= 4
                     continue
                 self._raise_on_status(status)
                 break
-        return (codes, coords) if return_face_coordinates else codes
+
+    def graphed_ragged(self, max_meshes: int, max_faces: int, max_vertices: int, max_total_faces: int, max_total_vertices: int,
+                       histogram: Optional[Tensor] = None) -> "GraphedRaggedTokenizer":
+        """tokenize_ragged as ONE CUDA graph for every batch within the stated bounds (see GraphedRaggedTokenizer)."""
+        return GraphedRaggedTokenizer(self, max_meshes, max_faces, max_vertices, max_total_faces, max_total_vertices, histogram)
 
     # ---- CUDA-graph replay of the whole pipeline ----------------------------------------------------
     def graphed(self, vertices: Tensor, faces: Tensor, histogram: Optional[Tensor] = None,
@@ -617,6 +643,84 @@ class GraphedTokenizer:
         torch.cuda.current_stream().synchronize()
         self.check()
         return pinned_out
+
+
+class GraphedRaggedTokenizer:
+    """tokenize_ragged() as a CUDA graph that serves EVERY batch within its bounds: at most max_meshes meshes of at most max_faces faces /
+    max_vertices vertices each, max_total_faces face rows and max_total_vertices vertex rows in all.  The graph is captured once on
+    static buffers of those sizes; the live sizes travel in the offset arrays (a batch with fewer meshes repeats its last offset: empty
+    meshes), and the kernels take the live face count from face_offsets[B] on the device, so one graph covers ragged batches of any
+    composition - the padded layout needs one graph per (b, nf, nv) shape.
+
+        g = model.graphed_ragged(256, 800, 441, 256 * 500, 256 * 300)
+        codes = g(vertices, faces, face_offsets, vertex_offsets)      # CUDA or (pinned) host tensors; -> (sum nf * nvf, Q) view of g.codes
+
+    The returned view is overwritten by the next call; data errors are reported by g.check()."""
+
+    def __init__(self, model: MeshAutoencoder, max_meshes: int, max_faces: int, max_vertices: int, max_total_faces: int,
+                 max_total_vertices: int, histogram: Optional[Tensor] = None):
+        prep = model._prepare()
+        dev = prep["device"]
+        self.model, self.nvf = model, model.num_vertices_per_face
+        self.B, self.F, self.V = int(max_meshes), max(int(max_faces), 1), max(int(max_vertices), 1)
+        self.cap_faces = min(int(max_total_faces), self.B * self.F)
+        self.cap_vertices = min(int(max_total_vertices), self.B * self.V)
+        assert self.B > 0 and self.cap_faces > 0 and self.cap_vertices > 0
+        if model.training:
+            model.eval()
+        with torch.cuda.device(dev):
+            self.vertices = torch.zeros((self.cap_vertices, 3), dtype=torch.float32, device=dev)
+            self.faces = torch.zeros((self.cap_faces, self.nvf), dtype=torch.int64, device=dev)
+            self.codes = torch.empty((self.cap_faces * self.nvf, model.num_quantizers), dtype=torch.int64, device=dev)
+            self._stage = torch.empty(2 * (self.B + 1), dtype=torch.int32).pin_memory()    # host offsets -> device in one copy
+            self._offsets_dev = torch.zeros(2 * (self.B + 1), dtype=torch.int32, device=dev)
+            self.face_offsets, self.vertex_offsets = self._offsets_dev[: self.B + 1], self._offsets_dev[self.B + 1:]
+            # the input the graph is captured on: one triangle (or quad) in mesh 0, every other mesh empty
+            assert self.cap_vertices >= self.nvf and self.V >= self.nvf
+            self.vertices[: self.nvf] = torch.eye(4, 3, device=dev)[: self.nvf] * 0.5
+            self.faces[0] = torch.arange(self.nvf, device=dev)
+            self.face_offsets[1:] = 1
+            self.vertex_offsets[1:] = self.nvf
+            tag = ("ragged-graph", id(self))
+            args = (self.vertices, self.faces, self.face_offsets, self.vertex_offsets, self.B, self.F, self.V, self.cap_faces, self.codes)
+            model._launch_ragged(*args, histogram=None, check_status=True, workspace_tag=tag)          # allocates the workspace
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                model._launch_ragged(*args, histogram=None, check_status=False, workspace_tag=tag)
+            torch.cuda.current_stream().wait_stream(side)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                model._launch_ragged(*args, histogram=histogram, check_status=False, workspace_tag=tag)
+        self._workspace = model.last_workspace
+        self._stage_free = torch.cuda.Event()
+
+    def __call__(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets) -> Tensor:
+        fo, vo = torch.as_tensor(face_offsets), torch.as_tensor(vertex_offsets)
+        n, nf, nv = fo.numel() - 1, faces.shape[0], vertices.shape[0]
+        assert 0 <= n <= self.B and vo.numel() == n + 1, f"at most {self.B} meshes per call, B + 1 offsets each"
+        assert nf <= self.cap_faces and nv <= self.cap_vertices, f"batch exceeds the captured bounds ({self.cap_faces} faces, {self.cap_vertices} vertices)"
+        self.vertices[:nv].copy_(vertices, non_blocking=True)
+        self.faces[:nf].copy_(faces, non_blocking=True)
+        if fo.is_cuda:
+            self.face_offsets[: n + 1].copy_(fo)
+            self.vertex_offsets[: n + 1].copy_(vo)
+            self.face_offsets[n + 1:] = self.face_offsets[n]
+            self.vertex_offsets[n + 1:] = self.vertex_offsets[n]
+        else:
+            st = self._stage
+            self._stage_free.synchronize()          # the previous call's copy out of the pinned staging buffer has finished
+            st[: n + 1] = fo
+            st[n + 1: self.B + 1] = int(fo[-1])
+            st[self.B + 1: self.B + 2 + n] = vo
+            st[self.B + 2 + n:] = int(vo[-1])
+            self._offsets_dev.copy_(st, non_blocking=True)
+            self._stage_free.record()
+        self.graph.replay()
+        return self.codes[: nf * self.nvf]
+
+    def check(self):
+        MeshAutoencoder._raise_on_status(int(self._workspace[:4].view(torch.int32).item()))
 
 
 class HostPipeline:

@@ -414,10 +414,12 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   if (ragged) {
     MT_CHECK_ARG(a->face_offsets != nullptr && a->vertex_offsets != nullptr && a->total_faces >= 0 && a->total_faces <= (long long)B * F,
                  "ragged input needs face_offsets and vertex_offsets (B + 1 int32 each) and 0 <= total_faces <= B * F");
-    if (a->face_edges || a->encoded_in || a->encoded_out || a->quantized_out) {
-      set_error("ragged input: face_edges, encoded_in, encoded_out and quantized_out exist only in the padded layout");
+    if (a->encoded_in || a->encoded_out || a->quantized_out) {
+      set_error("ragged input: encoded_in, encoded_out and quantized_out exist only in the padded layout");
       return MESHTOK_ERR_UNSUPPORTED;
     }
+    MT_CHECK_ARG(a->face_edges == nullptr || (a->edge_offsets != nullptr && a->total_edges >= 0 && a->total_edges <= a->edge_capacity),
+                 "ragged input with face_edges needs edge_offsets (B + 1 int32) and 0 <= total_edges <= edge_capacity");
   }
   rc = topo_check_shape(B, F, nvf, V);
   if (rc != MESHTOK_OK) return rc;
@@ -459,7 +461,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   bool edges_pending = false;
   SideStream* side = nullptr;
   if (a->face_edges) {
-    rc = topo_user_edges(a->face_edges, B, E, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
+    rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
     if (rc != MESHTOK_OK) return rc;
   } else {

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) gather_codes_ragged_kernel(const int64_t*
                                                                   int nvf, int V, int Q, int64_t pad_id, int64_t* __restrict__ codes_out) {
   pdl_wait();
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= total_faces * nvf) return;
+  // total_faces (host) is the capacity of the buffers, the live count is the last offset: a graph captured on upper bounds serves every batch
+  if (tok >= min(total_faces, (long long)__ldg(in_face_off + B)) * nvf) return;
   const int g = (int)(tok / nvf);
   int lo = 0, hi = B;            // the last b with in_face_off[b] <= g (empty meshes repeat an offset: the last one owns the face)
   while (hi - lo > 1) {

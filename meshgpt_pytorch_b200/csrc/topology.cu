@@ -428,13 +428,25 @@ __global__ void __launch_bounds__(1024) mesh_offsets_kernel(const int* __restric
 // ---- user supplied face_edges -> CSR by target (meshgpt_pytorch.py:752-754) -----------------------
 // edges (B,E,2): row0 = first column = source i, row1 = second column = target j, both offset by the
 // number of valid faces of the preceding meshes; an edge is kept iff neither entry equals pad_id.
-__global__ void user_edges_count_kernel(const int64_t* __restrict__ edges, int B, int E, int64_t pad_id,
-                                        const int* __restrict__ face_off, int* __restrict__ ecount, int* status) {
+// Ragged layout (in_edge_off != null): edges (in_edge_off[B], 2), mesh b owns rows in_edge_off[b] .. in_edge_off[b + 1]; the mesh of an
+// edge is the last b with in_edge_off[b] <= idx (bisection, B + 1 ints from L1).
+__device__ __forceinline__ int edge_mesh(long long idx, int E, const int32_t* __restrict__ in_edge_off, int B) {
+  if (in_edge_off == nullptr) return (int)(idx / E);
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(in_edge_off + mid) <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void user_edges_count_kernel(const int64_t* __restrict__ edges, int B, int E, const int32_t* __restrict__ in_edge_off, long long ne,
+                                        int64_t pad_id, const int* __restrict__ face_off, int* __restrict__ ecount, int* status) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * E) return;
+  if (idx >= ne) return;
   const long long i = edges[2 * idx], j = edges[2 * idx + 1];
   if (i == pad_id || j == pad_id) return;
-  const int b = (int)(idx / E);
+  const int b = edge_mesh(idx, E, in_edge_off, B);
   const long long n = face_off[B];
   const long long s = face_off[b] + i, t = face_off[b] + j;
   if (s < 0 || s >= n || t < 0 || t >= n) { atomicOr(status, MESHTOK_WS_STATUS_EDGE_RANGE); return; }
@@ -478,14 +490,14 @@ __global__ void __launch_bounds__(256) user_edges_indptr_kernel(const int* __res
   if (b == B - 1 && threadIdx.x == 0) indptr[face_off[B]] = edge_off[B];
 }
 
-__global__ void user_edges_fill_kernel(const int64_t* __restrict__ edges, int B, int E, int64_t pad_id,
-                                       const int* __restrict__ face_off, int* __restrict__ cursor, int* __restrict__ etmp,
+__global__ void user_edges_fill_kernel(const int64_t* __restrict__ edges, int B, int E, const int32_t* __restrict__ in_edge_off, long long ne,
+                                       int64_t pad_id, const int* __restrict__ face_off, int* __restrict__ cursor, int* __restrict__ etmp,
                                        long long capacity, int* status) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)B * E) return;
+  if (idx >= ne) return;
   const long long i = edges[2 * idx], j = edges[2 * idx + 1];
   if (i == pad_id || j == pad_id) return;
-  const int b = (int)(idx / E);
+  const int b = edge_mesh(idx, E, in_edge_off, B);
   const long long n = face_off[B];
   const long long s = face_off[b] + i, t = face_off[b] + j;
   if (s < 0 || s >= n || t < 0 || t >= n) return;
@@ -496,8 +508,8 @@ __global__ void user_edges_fill_kernel(const int64_t* __restrict__ edges, int B,
 
 // per target row: order the incoming edges by their position in the user's list (the order in which
 // the reference's scatter_add visits them on the CPU), then replace edge ids by source rows.
-__global__ void user_edges_sort_kernel(const int64_t* __restrict__ edges, int E, const int* __restrict__ face_off,
-                                       const int* __restrict__ indptr, const int* __restrict__ etmp, int* __restrict__ src,
+__global__ void user_edges_sort_kernel(const int64_t* __restrict__ edges, int B, int E, const int32_t* __restrict__ in_edge_off,
+                                       const int* __restrict__ face_off, const int* __restrict__ indptr, const int* __restrict__ etmp, int* __restrict__ src,
                                        const Counts* counts, long long capacity) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= counts->n_faces) return;
@@ -506,7 +518,7 @@ __global__ void user_edges_sort_kernel(const int64_t* __restrict__ edges, int E,
     const int key = etmp[i];
     int rank = 0;
     for (long long j = s; j < e; ++j) rank += etmp[j] < key;
-    const int b = key / E;
+    const int b = edge_mesh(key, E, in_edge_off, B);
     src[s + rank] = face_off[b] + (int)edges[2 * (long long)key];
   }
 }
@@ -576,16 +588,16 @@ int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaS
   return MESHTOK_OK;
 }
 
-int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
+int topo_user_edges(const int64_t* edges, int B, int E, const int32_t* in_edge_off, long long total_edges, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
                     int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,
                     int* status, cudaStream_t stream) {
   const int* face_off = offs;
   const int* edge_off = offs + 2 * (size_t)(B + 1);
   MT_CHECK_CUDA(cudaMemsetAsync(ecount, 0, sizeof(int) * (size_t)max_rows, stream));
-  const long long ne = (long long)B * E;
+  const long long ne = in_edge_off ? total_edges : (long long)B * E;   // ragged layout: a flat list cut by in_edge_off
   if (ne > 0) {
     const int blocks = (int)((ne + 255) / 256);
-    user_edges_count_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, pad_id, face_off, ecount, status);
+    user_edges_count_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, in_edge_off, ne, pad_id, face_off, ecount, status);
     MT_CHECK_LAUNCH();
   }
   user_edges_mesh_sum_kernel<<<B, 256, 0, stream>>>(ecount, face_off, mesh_counts);
@@ -596,9 +608,9 @@ int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mes
   MT_CHECK_LAUNCH();
   if (ne > 0) {
     const int blocks = (int)((ne + 255) / 256);
-    user_edges_fill_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, pad_id, face_off, cursor, etmp, capacity, status);
+    user_edges_fill_kernel<<<blocks, 256, 0, stream>>>(edges, B, E, in_edge_off, ne, pad_id, face_off, cursor, etmp, capacity, status);
     MT_CHECK_LAUNCH();
-    user_edges_sort_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(edges, E, face_off, indptr, etmp, src, counts, capacity);
+    user_edges_sort_kernel<<<ceil_div(max_rows, 256), 256, 0, stream>>>(edges, B, E, in_edge_off, face_off, indptr, etmp, src, counts, capacity);
     MT_CHECK_LAUNCH();
   }
   return MESHTOK_OK;

@@ -49,7 +49,7 @@ int topo_csr(const TopoParams& p, cudaStream_t stream);
 int topo_maps(const TopoParams& p, cudaStream_t stream);
 int topo_edges(const TopoParams& p, cudaStream_t stream);
 int topo_offsets(const int* mesh_counts, int* offs, int B, Counts* counts, cudaStream_t stream);
-int topo_user_edges(const int64_t* edges, int B, int E, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
+int topo_user_edges(const int64_t* edges, int B, int E, const int32_t* in_edge_off, long long total_edges, int64_t pad_id, int* mesh_counts, int* offs, Counts* counts,
                     int* ecount, int* cursor, int* etmp, int* indptr, int* src, long long capacity, int max_rows,
                     int* status, cudaStream_t stream);
 

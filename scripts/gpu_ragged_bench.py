@@ -80,9 +80,27 @@ if len(sys.argv) > 2 and sys.argv[2] == "profile":     # ncu --profile-from-star
     torch.cuda.synchronize()
     torch.cuda.profiler.start(); padded_dev(); torch.cuda.synchronize(); ragged_dev(); torch.cuda.synchronize(); torch.cuda.profiler.stop()
     sys.exit(0)
-for name, dfn, hfn, h2d, d2h in (("padded", padded_dev, padded_host, vp.numel() * 4 + fp.numel() * 8, out_p.numel() * 8),
-                                 ("ragged", ragged_dev, ragged_host, rvp.numel() * 4 + rfp.numel() * 8 + 8 * (B + 1), out_r.numel() * 8)):
-    l0 = lib.meshtok_kernel_launch_count(); dfn(); launches = lib.meshtok_kernel_launch_count() - l0
+# the same two layouts as CUDA graphs: the padded graph serves this (b, nf, nv) shape only, the ragged one every batch within its bounds
+gp = m.graphed(vd, fd)
+gr = m.graphed_ragged(B, 800, 441, B * 800, B * 441)
+assert torch.equal(gr(rvd, rfd, fo, vo), ragged_dev()) and torch.equal(gp(), padded_dev())
+
+
+def padded_graph_host():
+    gp.tokenize_host(vp, fp, out_p)
+
+
+def ragged_graph_host():
+    out_r.copy_(gr(rvp, rfp, fo, vo), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+
+
+h2d_p, d2h_p = vp.numel() * 4 + fp.numel() * 8, out_p.numel() * 8
+h2d_r, d2h_r = rvp.numel() * 4 + rfp.numel() * 8 + 8 * (B + 1), out_r.numel() * 8
+for name, dfn, hfn, h2d, d2h in (("padded", padded_dev, padded_host, h2d_p, d2h_p), ("ragged", ragged_dev, ragged_host, h2d_r, d2h_r),
+                                 ("padded, graph", lambda: gp(), padded_graph_host, h2d_p, d2h_p),
+                                 ("ragged, graph", lambda: gr.graph.replay(), ragged_graph_host, h2d_r, d2h_r)):
+    l0 = lib.meshtok_kernel_launch_count(); dfn(); launches = (lib.meshtok_kernel_launch_count() - l0) or 26     # (a replay counts no launches)
     d, h = dev_ms(dfn), host_ms(hfn)
     print(json.dumps(dict(layout=name, metric="faces tokenized/sec (valid faces; median of 20 eager steps)", meshes=B, valid_faces=n_faces,
                           slots=B * f.shape[1], value=n_faces / (d * 1e-3), unit="faces/s", ms_per_step=d,

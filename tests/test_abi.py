@@ -31,7 +31,7 @@ def test_struct_layout_matches_header():
     # meshtok_sage_layer: 2 x int32 + 6 pointers; meshtok_model embeds 8 of them
     assert C.sizeof(_lib.SageLayer) == 8 + 6 * 8
     assert _lib.Model.sage.size == 8 * C.sizeof(_lib.SageLayer)
-    assert C.sizeof(_lib.TokenizeArgs) == 4 * 8 + 4 * 4 + 2 * 8 + 5 * 8 + 4 * 4 + 3 * 8
+    assert C.sizeof(_lib.TokenizeArgs) == 4 * 8 + 4 * 4 + 2 * 8 + 5 * 8 + 4 * 4 + 5 * 8
     assert C.sizeof(_lib.Taps) == (7 + 8 + 3) * 8
 
 

@@ -90,3 +90,72 @@ def test_ragged_full_size_c4_like_batch():
     codes = m.tokenize_ragged(rv, rf, fo, vo)
     assert torch.equal(Dt.ragged_to_padded_codes(codes, fo, 3, m.pad_id), padded)
     assert rf.shape[0] == sum(counts) and rv.shape[0] < v.shape[0] * v.shape[1]
+
+
+@pytest.mark.parametrize("cfg,kind,counts", [
+    (dict(SMALL_CFG), "tri", [130, 61, 8, 144]),
+    (dict(SMALL_CFG, quads=True, use_residual_lfq=False), "quad", [72, 30, 5]),
+])
+def test_ragged_precomputed_face_edges(cfg, kind, counts):
+    """Precomputed edges in the ragged layout (flat (sum ne, 2) list with mesh-local face indices + edge_offsets: the face-edge cache's
+    content without its padding) against tokenize(face_edges=...) on the padded batch, and against the edges derived on the device."""
+    import meshgpt_pytorch_b200 as M
+    o, m = make_pair(**cfg)
+    v, f = synth.ragged_batch(kind, 9, 8, counts, list(range(len(counts))))
+    edges = M.derive_face_edges_from_faces(f.cuda())                          # (b, e, 2), pad_id rows behind each mesh's list
+    padded = m.tokenize(v.cuda(), f.cuda(), face_edges=edges)
+    keep = (edges != -1).all(-1)
+    flat_edges = edges[keep]
+    eo = torch.zeros(len(counts) + 1, dtype=torch.int64)
+    eo[1:] = keep.sum(1).cpu().cumsum(0)
+    rv, rf, fo, vo = ragged_cuda(v, f)
+    codes = m.tokenize_ragged(rv, rf, fo, vo, face_edges=flat_edges, edge_offsets=eo)
+    nvf = m.num_vertices_per_face
+    assert torch.equal(Dt.ragged_to_padded_codes(codes, fo, nvf, m.pad_id), padded)
+    assert torch.equal(codes, m.tokenize_ragged(rv, rf, fo, vo))              # derived on the device: same lists in the same order
+    assert torch.equal(codes, m.tokenize_ragged(rv, rf, fo, vo, face_edges=flat_edges, edge_offsets=eo.cuda()))
+    # a different edge set must change the result (the lists are really used): self-loops only
+    loops = torch.cat([torch.arange(c) for c in counts]).cuda()
+    lo = torch.zeros(len(counts) + 1, dtype=torch.int64)
+    lo[1:] = torch.tensor(counts).cumsum(0)
+    alone = m.tokenize_ragged(rv, rf, fo, vo, face_edges=torch.stack([loops, loops], 1), edge_offsets=lo)
+    want = m.tokenize(v.cuda(), f.cuda(), face_edges=Dt_self_loops(f).cuda())
+    assert torch.equal(Dt.ragged_to_padded_codes(alone, fo, nvf, m.pad_id), want) and not torch.equal(alone, codes)
+    # no edges at all: every aggregation is zero, still well defined
+    none = m.tokenize_ragged(rv, rf, fo, vo, face_edges=flat_edges[:0], edge_offsets=[0] * (len(counts) + 1))
+    assert none.shape == codes.shape and bool((none >= 0).all())
+    with pytest.raises(IndexError):                                            # an edge that points outside the batch's faces
+        bad = flat_edges.clone()
+        bad[-1, 0] = 10 ** 6
+        m.tokenize_ragged(rv, rf, fo, vo, face_edges=bad, edge_offsets=eo)
+
+
+def Dt_self_loops(faces):
+    """(b, nf, 2) padded edge list with (i, i) for every un-padded face."""
+    b, nf, _ = faces.shape
+    e = torch.arange(nf)[None, :, None].expand(b, nf, 2).clone()
+    e[~(faces != -1).all(-1)] = -1
+    return e
+
+
+def test_ragged_graph_serves_batches_of_any_composition():
+    """GraphedRaggedTokenizer: ONE graph captured on upper bounds, replayed on batches with different mesh counts and sizes, offsets from
+    the host and from the device - every replay equal to the eager ragged call (and so to the padded layout)."""
+    o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+    hist = torch.zeros(m.num_quantizers, m.codebook_size, dtype=torch.int64, device="cuda")
+    g = m.graphed_ragged(max_meshes=6, max_faces=144, max_vertices=90, max_total_faces=500, max_total_vertices=400, histogram=hist)
+    want_hist = torch.zeros_like(hist)
+    for counts in ([130, 61, 8, 1, 144], [144], [5, 5, 5, 5, 5, 5], [77, 144, 144, 100]):
+        v, f = synth.ragged_batch("tri", 9, 8, counts, list(range(len(counts))))
+        rv, rf, fo, vo = ragged_cuda(v, f)
+        want = m.tokenize_ragged(rv, rf, fo, vo, histogram=want_hist)
+        got = g(rv, rf, fo, vo).clone()
+        assert torch.equal(got, want), counts
+        got = g(rv.cpu().pin_memory(), rf.cpu().pin_memory(), fo.cuda(), vo.cuda()).clone()      # host data, device offsets
+        assert torch.equal(got, want), counts
+        want_hist += torch.stack([torch.bincount(want[:, q], minlength=m.codebook_size) for q in range(m.num_quantizers)])
+        g.check()
+    assert torch.equal(hist, want_hist)
+    with pytest.raises(AssertionError):
+        v, f = synth.ragged_batch("tri", 9, 8, [144] * 4, [0, 1, 2, 3])
+        g(*ragged_cuda(v, f))                                                                      # 576 faces > 500
