@@ -179,3 +179,14 @@ def ragged_to_padded_codes(codes: Tensor, face_offsets, nvf: int, pad_id: int = 
     for b in range(B):
         out[b, : int(n[b])] = codes[int(fo[b]) * nvf: int(fo[b + 1]) * nvf]
     return out
+
+
+def ragged_slice(batch: dict, lo: int, hi: int) -> dict:
+    """Meshes [lo, hi) of a ragged_collate batch as a batch of their own (offsets re-based to 0; tensors are views).  With
+    sharding.balanced_contiguous_shards over the face counts this is a rank's share of a ragged collection (meshes shard by
+    contiguous blocks, no activation crosses a link)."""
+    fo, vo = batch["face_offsets"], batch["vertex_offsets"]
+    assert 0 <= lo <= hi <= fo.numel() - 1
+    f0, f1, v0, v1 = int(fo[lo]), int(fo[hi]), int(vo[lo]), int(vo[hi])
+    return dict(vertices=batch["vertices"][v0:v1], faces=batch["faces"][f0:f1],
+                face_offsets=(fo[lo: hi + 1] - f0).to(torch.int32), vertex_offsets=(vo[lo: hi + 1] - v0).to(torch.int32))

@@ -209,6 +209,12 @@ def test_ragged_collate_is_custom_collate_without_the_padding():
         Dt.padded_to_ragged(v, g)
     empty = Dt.ragged_collate([])
     assert empty["face_offsets"].tolist() == [0] and empty["faces"].shape == (0, 3)
+    # a rank's share of a ragged collection: contiguous meshes, cut by the number of faces, offsets re-based
+    cuts = sharding.balanced_contiguous_shards(counts, 2)
+    parts = [Dt.ragged_slice(r, lo, hi) for lo, hi in cuts]
+    assert cuts == [(0, 2), (2, 3)] and parts[0]["face_offsets"].tolist() == [0, 13, 14] and parts[1]["face_offsets"].tolist() == [0, 40]
+    assert torch.equal(torch.cat([p["faces"] for p in parts]), r["faces"]) and torch.equal(torch.cat([p["vertices"] for p in parts]), r["vertices"])
+    assert parts[1]["vertex_offsets"].tolist() == [0, nv[2]] and Dt.ragged_slice(r, 1, 1)["faces"].shape == (0, 3)
 
 
 def test_tokenize_ragged_needs_cuda_tensors():
