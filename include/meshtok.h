@@ -311,6 +311,14 @@ int meshtok_conv1d(const void* a_halo_image, const void* w_image, const float* b
  * (use meshtok_conv1d + meshtok_dec_pixelnorm_silu_halo). */
 int meshtok_conv1d_pixelnorm_silu(const void* a_halo_image, const void* w_image, const float* bias, const uint8_t* valid, float* out, int R, int N,
                                   int C_in, int k, int halo, int width, float eps, int out_halo, void* out_image, meshtok_stream_t stream);
+/* meshtok_conv1d + meshtok_dec_argmax_coords_padded in one launch (to_coor_logits :639 + argmax / undiscretize :935-944): w_image is the
+ * image of the (N, k * C_in) weight with N = passes * 2 * nbins rows - coordinate c owns rows c * nbins .. (c + 1) * nbins, rows of coordinates
+ * >= ncoord are zero padding - so that every pass of the tcgen05 kernel holds two whole coordinates; each epilogue thread takes the arg-max of
+ * its row's nbins logits from TMEM (first maximum wins) and writes coords / bins (B, P - lead, ncoord) of the unpadded faces, NaN / 0 where
+ * valid is 0.  The logits never reach global memory.  MESHTOK_ERR_UNSUPPORTED when a pass is not 2 * nbins wide (nbins = 128). */
+int meshtok_conv1d_argmax_coords(const void* a_halo_image, const void* w_image, const float* bias, const uint8_t* valid, int R, int N, int C_in, int k,
+                                 int halo, int B, int P, int lead, int ncoord, int nbins, float lo, float hi, float* coords, int64_t* bins,
+                                 meshtok_stream_t stream);
 /* number of face slices per mesh the SqueezeExcite partial sums use; slice_ws holds B * S * C floats + B * S int32 */
 int meshtok_dec_se_slices(int B, int nf);
 /* x (B * nf, C) fp32, UNPADDED rows -> halo image in the padded row space */

@@ -882,6 +882,16 @@ int meshtok_conv1d_pixelnorm_silu(const void* a_halo_image, const void* w_image,
   return launch_conv_tc(a_halo_image, C_in, k, halo, w_image, bias, out, N, R, static_cast<cudaStream_t>(stream), &tail);
 }
 
+/* to_coor_logits + arg-max + undiscretize in one launch: the logits stay in TMEM */
+int meshtok_conv1d_argmax_coords(const void* a_halo_image, const void* w_image, const float* bias, const uint8_t* valid, int R, int N, int C_in, int k,
+                                 int halo, int B, int P, int lead, int ncoord, int nbins, float lo, float hi, float* coords, int64_t* bins,
+                                 meshtok_stream_t stream) {
+  MT_CHECK_ARG(a_halo_image && w_image && valid && coords && MT_ROWSPACE_OK(R, P, lead) && (long long)B * P + lead == R && N > 0 && C_in > 0,
+               "conv1d_argmax_coords: bad arguments (R must be B * P + lead)");
+  ConvArgmax am{valid, B, P, lead, ncoord, nbins, lo, hi, coords, bins};
+  return launch_conv_argmax_tc(a_halo_image, C_in, k, halo, w_image, bias, N, R, am, static_cast<cudaStream_t>(stream));
+}
+
 int meshtok_dec_rows_halo(const float* x, int ld, const uint8_t* valid, int R, int P, int lead, int C, int halo, void* image, meshtok_stream_t stream) {
   MT_CHECK_ARG(x && valid && image && MT_ROWSPACE_OK(R, P, lead) && C % 32 == 0 && ld >= C && ld % 4 == 0 && halo >= 0 && halo <= lead,
                "rows_halo: width %d must be a multiple of 32, R = B * P + lead, halo <= lead", C);

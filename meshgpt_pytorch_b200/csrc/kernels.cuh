@@ -164,6 +164,17 @@ struct ConvBlockTail {
 };
 int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, float* C, int N, int m_max,
                    cudaStream_t stream, const ConvBlockTail* tail = nullptr);   // Conv1d over the rows of a halo image, see linear_tc.cu
+// to_coor_logits + arg-max in the convolution's epilogue (decode path)
+struct ConvArgmax {
+  const uint8_t* valid;   // (rows of the padded row space) 0: NaN coordinate, bin 0
+  int B, P, lead;         // rows = B * P + lead, the faces of mesh b are rows b * P + lead .. (b + 1) * P
+  int ncoord, nbins;
+  float lo, hi;
+  float* coords;          // (B, P - lead, ncoord)
+  int64_t* bins;          // same shape or null
+};
+int launch_conv_argmax_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, int N, int m_max,
+                          const ConvArgmax& am, cudaStream_t stream);
 size_t rows_image_bytes(long long rows, int K);
 int launch_rows_to_image(const float* A, int K, const int* m_dev, int m_max, void* image, cudaStream_t stream);
 

@@ -102,6 +102,13 @@ struct LinArgs {
   const uint8_t* row_valid;
   int out_halo;
   float norm_eps;
+  // norm_mode 4 (decode path, to_coor_logits + arg-max :935-944): a pass is CPARTS coordinates of part_cols == nbins logits each; every
+  // epilogue thread takes the arg-max of its row's nbins logits of coordinate pass * CPARTS + cpart (first maximum wins) straight from
+  // TMEM and writes the bin and the undiscretised coordinate of the UNPADDED face (b * nf + f) - the logits never reach global memory.
+  float* am_coords;         // (B, P - lead, ncoord) fp32, NaN where row_valid is 0
+  long long* am_bins;       // the same shape, int64 (0 where row_valid is 0), or null
+  int am_B, am_P, am_lead, am_ncoord;
+  float am_lo, am_hi;
 };
 __host__ __device__ inline int lin_chunks(const LinArgs& a) { return (a.conv ? a.taps : 1) * (a.K1 / KC) + a.K2 / KC; }
 
@@ -384,7 +391,39 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       const int n0 = pass * a.NT;
       const int row0 = m_tile * M_TILE + q * 32;
       const bool mode3 = TAIL && a.norm_mode == 3;
-      if (a.norm_mode != 0 && !(mode3 && pass != 0)) {
+      if (TAIL && a.norm_mode == 4) {
+        // ---- arg-max epilogue: thread = row, this warp's column part = one coordinate's logits ----
+        const long long grow = (long long)row0 + lane;
+        const int coord = pass * CPARTS + cpart;
+        float best = -INFINITY;
+        int bi = 0;
+        for (int c = c_lo; c < c_hi; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float x = __uint_as_float(v[j]) + sb[n0 + c + j];
+            if (x > best) { best = x; bi = c - c_lo + j; }   // ascending bins, strict: the first maximum wins like torch.argmax
+          }
+        }
+        if (grow < M && coord < a.am_ncoord) {
+          const int b = (int)(grow / a.am_P);
+          const int f = (int)(grow - (long long)b * a.am_P) - a.am_lead;
+          if (b < a.am_B && f >= 0) {   // not a separator row
+            const long long item = ((long long)b * (a.am_P - a.am_lead) + f) * a.am_ncoord + coord;
+            if (a.row_valid[grow] == 0) {
+              a.am_coords[item] = __int_as_float(0x7fc00000);
+              if (a.am_bins) a.am_bins[item] = 0;
+            } else {
+              float t = __fadd_rn((float)bi, 0.5f);
+              t = __fdiv_rn(t, (float)(c_hi - c_lo));
+              a.am_coords[item] = __fadd_rn(__fmul_rn(t, __fsub_rn(a.am_hi, a.am_lo)), a.am_lo);
+              if (a.am_bins) a.am_bins[item] = bi;
+            }
+          }
+        }
+      } else if (a.norm_mode != 0 && !(mode3 && pass != 0)) {
         // ---- fused row epilogue (passes == 1, so NT == N and n0 == 0; mode 3: pass 0 of at most two) ----
         // alternates per phase-0 unit; mode 3 counts its own units (plain second-pass units in between have no barrier)
         const int xsel = mode3 ? (tail_units++ & 1) : (ti & 1);
@@ -775,6 +814,7 @@ static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a
   a.norm_mode = 0; a.gamma = a.beta = nullptr; a.out_image = nullptr;
   a.conv = 0; a.taps = 1; a.halo = 0;
   a.row_valid = nullptr; a.out_halo = 0; a.norm_eps = 0.f;
+  a.am_coords = nullptr; a.am_bins = nullptr; a.am_B = a.am_P = a.am_lead = a.am_ncoord = 0; a.am_lo = a.am_hi = 0.f;
   a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
   if (epi != nullptr && epi->norm_mode == 0) {
     // plain epilogue with the deferred-normalisation extras
@@ -821,7 +861,7 @@ static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
     configured = true;
   }
   const int passes = g.nphase == 2 ? 1 : g.p[0].passes;
-  const bool tail = g.p[0].norm_mode == 3;   // decode path: Block tail in the epilogue
+  const bool tail = g.p[0].norm_mode == 3 || g.p[0].norm_mode == 4;   // decode path: Block tail / arg-max in the epilogue
   if (linear_tc_pair()) {
     using P2 = Cfg<true, 2>;
     const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * passes;
@@ -881,6 +921,37 @@ int launch_conv_tc(const void* a_halo_image, int C_in, int taps, int halo, const
     g.p[0].out_halo = tail->out_halo;
     g.p[0].norm_eps = tail->eps;
   }
+  return launch_lin2(g, m_max, stream);
+}
+
+// to_coor_logits + arg-max (decode path): Conv1d / Linear whose passes are pairs of coordinates (N = passes * 2 * nbins, the weight rows of
+// coordinates >= ncoord zero padding); the epilogue keeps only the arg-max of every coordinate's nbins logits, see LinArgs::am_*
+int launch_conv_argmax_tc(const void* a_halo_image, int C_in, int taps, int halo, const void* w_image, const float* bias, int N, int m_max,
+                          const ConvArgmax& am, cudaStream_t stream) {
+  if (m_max == 0) return MESHTOK_OK;
+  MT_CHECK_ARG(taps >= 1 && (taps & 1) == 1 && halo >= taps / 2 && halo <= 8 && C_in % KC == 0, "tcgen05 conv: kernel %d must be odd, halo %d >= kernel / 2 and <= 8, C_in %d a multiple of %d", taps, halo, C_in, KC);
+  MT_CHECK_ARG(am.valid && am.coords && am.B >= 0 && am.lead >= 0 && am.P > am.lead && am.ncoord >= 1 && am.nbins >= 16 && (long long)am.B * am.P <= m_max,
+               "tcgen05 conv + arg-max: bad row space / outputs");
+  LinArgs2 g;
+  memset(&g, 0, sizeof(g));
+  g.nphase = 1;
+  int rc = fill_lin_args(g.p[0], a_halo_image, C_in, nullptr, 0, w_image, bias, am.coords, N, nullptr, m_max, false, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  g.p[0].C = nullptr;
+  g.p[0].conv = 1; g.p[0].taps = taps; g.p[0].halo = halo;
+  rc = linear_tc_plan(N, taps * C_in, 0, &g.p[0].passes, &g.p[0].NT);
+  if (rc != MESHTOK_OK) return rc;
+  constexpr int CP = Cfg<true, 2>::CPARTS;
+  if (g.p[0].NT != CP * am.nbins || am.nbins % 16 != 0 || g.p[0].passes * CP < am.ncoord) {
+    set_error("tcgen05 conv + arg-max: a pass must be %d coordinates of %d logits (N %d splits into %d passes of %d for %d coordinates)", CP, am.nbins, N,
+              g.p[0].passes, g.p[0].NT, am.ncoord);
+    return MESHTOK_ERR_UNSUPPORTED;
+  }
+  g.p[0].norm_mode = 4;
+  g.p[0].row_valid = am.valid;
+  g.p[0].am_coords = am.coords; g.p[0].am_bins = reinterpret_cast<long long*>(am.bins);
+  g.p[0].am_B = am.B; g.p[0].am_P = am.P; g.p[0].am_lead = am.lead; g.p[0].am_ncoord = am.ncoord;
+  g.p[0].am_lo = am.lo; g.p[0].am_hi = am.hi;
   return launch_lin2(g, m_max, stream);
 }
 

@@ -137,6 +137,17 @@ class MeshDecoder(nn.Module):
             prep = dict(init=conv(self.init_decoder_conv["0"]),
                         ln=(self.init_decoder_conv["3"].weight.detach().to(**f32).contiguous(), self.init_decoder_conv["3"].bias.detach().to(**f32).contiguous()),
                         blocks=[], logits=conv(_as_conv(self.to_coor_logits["0"])))
+            # to_coor_logits for the arg-max epilogue (meshtok_conv1d_argmax_coords): rows padded to whole passes of two coordinates
+            lg, nb, ncoord = prep["logits"], self.num_discrete_coors, self.nvf * 3
+            prep["logits_am"] = None
+            if nb == 128 and lg["c"] % 32 == 0:
+                n_am = -(-ncoord // 2) * 2 * nb
+                if n_am <= 1536:
+                    mat = torch.zeros(n_am, lg["mat"].shape[1], **f32)
+                    mat[: lg["n"]] = lg["mat"]
+                    bias = torch.zeros(n_am, **f32)
+                    bias[: lg["n"]] = lg["bias"]
+                    prep["logits_am"] = image_of(mat, bias, lg["c"], 1)
             for blk in self.decoders:
                 e = blk.excite.net
                 prep["blocks"].append(dict(
@@ -358,9 +369,14 @@ class MeshDecoder(nn.Module):
                     check(lib.meshtok_dec_dequantize_rvq_halo(ptr(codes), ptr(book), ptr(vp), Rp, P, lead, nvf, q, self.dim_codebook, k // 2,
                                                               ptr(img), stream_ptr()))
                 decoded, limg = self._decode_fused(img, vp, b, P, Rp, logits_image=True)
-                logits = self._conv1d(limg, Rp, p["logits"])
-                check(lib.meshtok_dec_argmax_coords_padded(ptr(logits), ptr(vp), b, P, lead, ncoord, self.num_discrete_coors, float(lo), float(hi),
-                                                           ptr(coords), ptr(bins), stream_ptr()))
+                am = p["logits_am"] if os.environ.get("MESHTOK_DEC_ARGMAX", "1") != "0" else None
+                if am is not None:      # to_coor_logits + arg-max + undiscretize in one launch: the logits stay in TMEM
+                    check(lib.meshtok_conv1d_argmax_coords(ptr(limg), ptr(am["img"]), ptr(am["bias"]), ptr(vp), Rp, am["n"], am["c"], 1, 0, b, P, lead,
+                                                           ncoord, self.num_discrete_coors, float(lo), float(hi), ptr(coords), ptr(bins), stream_ptr()))
+                else:
+                    logits = self._conv1d(limg, Rp, p["logits"])
+                    check(lib.meshtok_dec_argmax_coords_padded(ptr(logits), ptr(vp), b, P, lead, ncoord, self.num_discrete_coors, float(lo), float(hi),
+                                                               ptr(coords), ptr(bins), stream_ptr()))
             else:
                 quantized = self.dequantize(codes).reshape(R, nvf * self.dim_codebook)
                 decoded = self._decode_staged(quantized, valid, b, nf)      # rows of padded faces are already zero (:924)

@@ -50,6 +50,7 @@ t0 = time.perf_counter(); od.decode_from_codes_to_faces(codes[:n_cpu].cpu()); cp
 cpu = dict(value=n_cpu * 800 / cpu_s, unit="faces/s", cores=os.cpu_count(), kind="port", sample=f"decode oracle on {n_cpu} meshes")
 for schedule in (("fused",) if "fusedonly" in sys.argv else ("fused", "staged")):
     os.environ["MESHTOK_DEC_FUSED"] = "1" if schedule == "fused" else "0"
+    md.decode_from_codes_to_faces(codes)          # first call: builds the weight images (one-time launches, not part of a step)
     l0 = lib.meshtok_kernel_launch_count()
     md.decode_from_codes_to_faces(codes)
     launches = lib.meshtok_kernel_launch_count() - l0

@@ -249,3 +249,24 @@ def test_block_tail_in_the_convolution_epilogue_matches_the_separate_launch(dims
     want_c, want_bins, want_mask = od.decode_from_codes_to_faces(codes.cpu(), return_discrete_codes=True)
     assert torch.equal(m1.cpu(), want_mask)
     assert float((b1.cpu()[want_mask] == want_bins[want_mask]).float().mean()) >= 0.99
+
+
+@pytest.mark.parametrize("cfg,dims,kind,counts", [
+    (dict(SMALL_CFG, use_residual_lfq=False), (32, 64, 96), "tri", [288, 131, 127, 1]),      # 9 coordinates: 5 passes, the last one half padding
+    (dict(SMALL_CFG, quads=True), (64, 32), "quad", [72, 30, 5, 1]),                          # 12 coordinates: 6 full passes
+])
+def test_argmax_in_the_logits_epilogue_matches_the_separate_launch(cfg, dims, kind, counts, monkeypatch):
+    """meshtok_conv1d_argmax_coords (to_coor_logits with the arg-max + undiscretize in the tcgen05 epilogue, logits never stored) against
+    meshtok_conv1d + meshtok_dec_argmax_coords_padded: the same accumulators, so bins and coordinates must be identical; and the oracle."""
+    o, m, od, md = make_decoders(cfg, dims)
+    assert md._prepare()["logits_am"] is not None
+    v, f = synth.ragged_batch(kind, 12, 12, counts, [0, 1, 2, 3])
+    codes = m.tokenize(v.cuda(), f.cuda())
+    monkeypatch.setenv("MESHTOK_DEC_ARGMAX", "1")
+    c1, b1, m1 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    monkeypatch.setenv("MESHTOK_DEC_ARGMAX", "0")
+    c0, b0, m0 = md.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    assert torch.equal(m0, m1) and torch.equal(b1, b0)
+    assert torch.equal(torch.nan_to_num(c1, nan=-7.0), torch.nan_to_num(c0, nan=-7.0)) and torch.isnan(c1[~m1]).all()
+    want_c, want_bins, want_mask = od.decode_from_codes_to_faces(codes.cpu(), return_discrete_codes=True)
+    assert float((b1.cpu()[want_mask] == want_bins[want_mask]).float().mean()) >= 0.99
