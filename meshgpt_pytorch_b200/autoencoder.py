@@ -460,8 +460,8 @@ class MeshAutoencoder(nn.Module):
     # ---- ragged input: a CSR of meshes instead of pad_id padding --------------------
     @torch.no_grad()
     def tokenize_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, face_edges: Optional[Tensor] = None,
-                        edge_offsets=None, max_faces: Optional[int] = None, max_vertices: Optional[int] = None, histogram: Optional[Tensor] = None, return_face_coordinates: bool = False,
-                        check_status: bool = True):
+                        edge_offsets=None, max_faces: Optional[int] = None, max_vertices: Optional[int] = None,
+                        histogram: Optional[Tensor] = None, return_face_coordinates: bool = False, check_status: bool = True):
         """tokenize() for a batch that was never padded: what the reference's custom_collate (data.py:347-369) turns into
         (b, nf, nvf) / (b, nv, 3) tensors full of pad_id stays a CSR of meshes here.
 
