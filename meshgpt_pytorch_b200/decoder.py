@@ -55,6 +55,27 @@ class _ResnetBlock(nn.Module):                # :355-379
         self.residual_conv = nn.Conv1d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
 
 
+conv_trace = None      # set to a list by scripts/gpu_decode_bench.py: (rows, N, K, start event, end event) of every convolution launch
+
+
+class _conv_timer:
+    """CUDA events around one convolution launch while `conv_trace` is a list (measurement only; a no-op otherwise)."""
+
+    def __init__(self, rows: int, n: int, k: int):
+        self.item = (rows, n, k)
+
+    def __enter__(self):
+        if conv_trace is not None:
+            self.a, self.b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if conv_trace is not None:
+            self.b.record()
+            conv_trace.append(self.item + (self.a, self.b))
+        return False
+
+
 class MeshDecoder(nn.Module):
     def __init__(self, autoencoder, init_decoder_conv_kernel: int = 7,
                  decoder_dims_through_depth: Tuple[int, ...] = (128, 128, 128, 128, 192, 192, 192, 192, 256, 256, 256, 256, 256, 256, 384, 384, 384),
@@ -233,7 +254,8 @@ class MeshDecoder(nn.Module):
     @staticmethod
     def _conv1d(img: Tensor, R: int, w: dict) -> Tensor:
         out = torch.empty(R, w["n"], dtype=torch.float32, device=img.device)
-        check(lib.meshtok_conv1d(ptr(img), ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], w["c"], w["k"], w["k"] // 2, stream_ptr()))
+        with _conv_timer(R, w["n"], w["k"] * w["c"]):
+            check(lib.meshtok_conv1d(ptr(img), ptr(w["img"]), ptr(w["bias"]), ptr(out), R, w["n"], w["c"], w["k"], w["k"] // 2, stream_ptr()))
         return out
 
     def _decode_fused(self, init_img: Tensor, valid: Tensor, b: int, P: int, R: int, logits_image: bool):
@@ -262,8 +284,9 @@ class MeshDecoder(nn.Module):
             if epi_tail and self._tail_in_epilogue(w1["n"], cout):
                 # block1.proj leaves the convolution only as the image of silu(PixelNorm(.)); residual_conv (second pass) as fp32
                 h = torch.empty(R, 2 * cout, **f32) if blk["c1r"] is not None else None
-                check(lib.meshtok_conv1d_pixelnorm_silu(ptr(img), ptr(w1["img"]), ptr(w1["bias"]), ptr(valid), ptr(h), R, w1["n"], w1["c"], w1["k"],
-                                                        w1["k"] // 2, cout, 1e-4, 1, ptr(img2), stream_ptr()))
+                with _conv_timer(R, w1["n"], w1["k"] * w1["c"]):
+                    check(lib.meshtok_conv1d_pixelnorm_silu(ptr(img), ptr(w1["img"]), ptr(w1["bias"]), ptr(valid), ptr(h), R, w1["n"], w1["c"], w1["k"],
+                                                            w1["k"] // 2, cout, 1e-4, 1, ptr(img2), stream_ptr()))
                 res_ptr, ldres = (h.data_ptr() + 4 * cout, 2 * cout) if h is not None else (x.data_ptr(), x.shape[1])
             else:
                 h = self._conv1d(img, R, w1)                         # c1r: (R, 2 cout) = [block1.proj | residual_conv]
@@ -371,8 +394,9 @@ class MeshDecoder(nn.Module):
                 decoded, limg = self._decode_fused(img, vp, b, P, Rp, logits_image=True)
                 am = p["logits_am"] if os.environ.get("MESHTOK_DEC_ARGMAX", "1") != "0" else None
                 if am is not None:      # to_coor_logits + arg-max + undiscretize in one launch: the logits stay in TMEM
-                    check(lib.meshtok_conv1d_argmax_coords(ptr(limg), ptr(am["img"]), ptr(am["bias"]), ptr(vp), Rp, am["n"], am["c"], 1, 0, b, P, lead,
-                                                           ncoord, self.num_discrete_coors, float(lo), float(hi), ptr(coords), ptr(bins), stream_ptr()))
+                    with _conv_timer(Rp, p["logits"]["n"], am["c"]):      # (the algorithmic width, without the padding rows)
+                        check(lib.meshtok_conv1d_argmax_coords(ptr(limg), ptr(am["img"]), ptr(am["bias"]), ptr(vp), Rp, am["n"], am["c"], 1, 0, b, P, lead,
+                                                               ncoord, self.num_discrete_coors, float(lo), float(hi), ptr(coords), ptr(bins), stream_ptr()))
                 else:
                     logits = self._conv1d(limg, Rp, p["logits"])
                     check(lib.meshtok_dec_argmax_coords_padded(ptr(logits), ptr(vp), b, P, lead, ncoord, self.num_discrete_coors, float(lo), float(hi),

@@ -22,6 +22,7 @@ md.load_reference_state_dict({k: v for k, v in od.state_dict().items() if not k.
 md = md.cuda()
 v, f = synth.grid_batch("tri", 20, 20, list(range(B)))
 codes = m.tokenize(v.cuda(), f.cuda())
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB), written between timed steps
 
 
@@ -58,6 +59,21 @@ for schedule in (("fused",) if "fusedonly" in sys.argv else ("fused", "staged"))
     g = md.graphed(codes)
     ms_graph, (gc, gm) = timed(lambda: g())
     assert torch.equal(torch.nan_to_num(gc), torch.nan_to_num(coords))
-    print(json.dumps(dict(schedule=schedule, metric="faces decoded/sec (device-timed, graph replay, L2 flushed between steps)",
+    # roofline of the dominant kernel class, the tcgen05 convolutions (tensor bound): issued bf16 flops = 3 MMAs per split-bf16 product x
+    # 2 R N K, over the event-timed duration of every convolution launch of one eager step (L2 flushed before the step)
+    from meshgpt_pytorch_b200 import decoder as dec_mod
+    flush.fill_(1)
+    dec_mod.conv_trace = []
+    md.decode_from_codes_to_faces(codes)
+    torch.cuda.synchronize()
+    trace, dec_mod.conv_trace = dec_mod.conv_trace, None
+    conv_ms = sum(a.elapsed_time(b) for *_, a, b in trace)
+    conv_flops = sum(6.0 * r * n * k for r, n, k, *_ in trace)
+    peak = peaks["bf16_tflops_sustained"]
+    roofline = None if not trace else dict(
+        kernel=f"linear_tc_pair(_tail)_kernel, conv mode: {len(trace)} launches per step", bound="tensor", achieved=conv_flops / (conv_ms * 1e-3) / 1e12,
+        peak=peak, unit="TFLOP/s", frac=conv_flops / (conv_ms * 1e-3) / 1e12 / peak, traffic=None, peak_source="measured (bf16_tflops_sustained)",
+        flops_per_step=conv_flops, conv_ms_per_step=conv_ms, conv_share_of_eager_step=conv_ms / ms_eager)
+    print(json.dumps(dict(schedule=schedule, roofline=roofline, metric="faces decoded/sec (device-timed, graph replay, L2 flushed between steps)",
                           value=B * 800 / (ms_graph * 1e-3), unit="faces/s", ms_per_step=ms_graph, eager_ms_per_step=ms_eager, meshes=B,
                           counted_launches_per_step=launches, cpu_baseline=cpu)))
