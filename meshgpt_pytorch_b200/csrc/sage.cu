@@ -90,8 +90,8 @@ __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restric
 // warp reads one 128-byte row slice (no bank conflicts).  L2 -> SM traffic drops from (neighbours + 1) x to 1 x the
 // activation - the warp-per-row kernel above ran at the bandwidth cap of the L2 slices (8-9 TB/s into the SMs).  Same
 // neighbour order and the same rounding as above, hence the same bits.
-template <int S>
-__global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
+template <int S, int NTHR, int CTAS>   // slice width, threads per CTA, CTAs per SM the registers must allow
+__global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                                   const int* __restrict__ src, long long cap, float* __restrict__ agg,
                                                                   uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
                                                                   int rows_cap, int edges_cap) {
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* _
   // trip per iteration: 12 per thread)
   const float* xs = x + (size_t)r0 * d + slice * S;
   const uint32_t sx_addr = tc::smem_u32(sx);
-  for (int i = tid; i < n_b * s4; i += 512) {
+  for (int i = tid; i < n_b * s4; i += NTHR) {
     const int row = i / s4;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (uint32_t)i * 16u), "l"(xs + (size_t)row * d + c * 4) : "memory");
   }
@@ -122,17 +122,17 @@ __global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* _
   const long long e1_true = indptr[r0 + n_b];
   const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);   // edges that exist in memory (capacity overflow is flagged elsewhere)
   const bool fast = n_e <= edges_cap && e1_true <= cap && (rows_cap + 1) * s4 <= 65536;
-  for (int i = tid; i <= n_b; i += 512) sptr[i] = indptr[r0 + i] - e0;
+  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = indptr[r0 + i] - e0;
   if (fast) {
-    for (int base = tid; base < n_e; base += 512 * 8) {
+    for (int base = tid; base < n_e; base += NTHR * 8) {
       int t[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) t[j] = base + j * 512 < n_e ? __ldg(src + e0 + base + j * 512) : 0;
+      for (int j = 0; j < 8; ++j) t[j] = base + j * NTHR < n_e ? __ldg(src + e0 + base + j * NTHR) : 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        if (base + j * 512 < n_e) {
+        if (base + j * NTHR < n_e) {
           const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
-          ssrc[base + j * 512] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
+          ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
         }
     }
   }
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(512, 2) gather_mean_smem_kernel(const float* _
   const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
   const float4* sx_first = sx + 2 * g + swap;
   const float4* sx_second = sx + 2 * g + (swap ^ 1);
-  for (int lrow = tid / TPR; lrow < n_b; lrow += 512 / TPR) {
+  for (int lrow = tid / TPR; lrow < n_b; lrow += NTHR / TPR) {
     const int s = sptr[lrow];
     const int e_true = sptr[lrow + 1];
     float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
@@ -268,7 +268,10 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   // one up to 1 760); MESHTOK_GATHER_L2=1 keeps the warp-per-row kernel for A/B runs
   static int use_smem = -1;
   if (use_smem < 0) { const char* e = getenv("MESHTOK_GATHER_L2"); use_smem = (e && atoi(e) == 1) ? 0 : 1; }
-  constexpr int S = 32;
+  // slice width: 32 columns (2 CTAs per SM at 800 faces), or 16 with 256 threads (MESHTOK_GATHER_S=16: 3 CTAs per SM, A/B switch)
+  static int slice_cols = -1;
+  if (slice_cols < 0) { const char* e = getenv("MESHTOK_GATHER_S"); slice_cols = (e && atoi(e) == 16) ? 16 : 32; }
+  const int S = slice_cols;
   const int edges_cap = 5 * F;   // staged source ids per mesh (u16); a mesh with more edges reads them from global memory
   const size_t smem = align_up((size_t)(F + 1) * S * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
   // one CTA per (mesh, slice): enough CTAs to fill the machine, or so little work that it does not matter
@@ -276,11 +279,17 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && enough_ctas) {
     static bool configured = false;
     if (!configured) {
-      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<32, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<16, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
       configured = true;
     }
-    MT_LAUNCH_PDL(gather_mean_smem_kernel<S>, B * (d / S), 512, smem, stream, x, d, indptr, src, edge_capacity, agg,
-                  static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+    if (S == 32) {
+      MT_LAUNCH_PDL((gather_mean_smem_kernel<32, 512, 2>), B * (d / S), 512, smem, stream, x, d, indptr, src, edge_capacity, agg,
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+    } else {
+      MT_LAUNCH_PDL((gather_mean_smem_kernel<16, 256, 3>), B * (d / S), 256, smem, stream, x, d, indptr, src, edge_capacity, agg,
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+    }
     return MESHTOK_OK;
   }
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
