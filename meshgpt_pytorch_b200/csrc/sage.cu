@@ -195,6 +195,120 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const floa
   pdl_launch_dependents();
 }
 
+// The same aggregation with one CTA per (mesh, GROUP of consecutive slices): the mesh's CSR is staged once for the group and the x slices
+// are double buffered - the cp.async copies of slice k + 1 are in flight while slice k is summed and stored, inside one CTA instead of
+// between two independent ones.  2 x (F + 1) x 128 bytes + CSR = 216 KB for 800 faces, 1 024 threads, one CTA per SM.  Large batches only
+// (a group of >= 2 slices per CTA must still leave >= 2 CTAs per SM's worth of work): see launch_gather_mean for when it is taken.
+template <int S, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
+                                                                         const int* __restrict__ src, long long cap, float* __restrict__ agg,
+                                                                         uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
+                                                                         int rows_cap, int edges_cap, int group) {
+  extern __shared__ float4 sx[];
+  constexpr int s4 = S >> 2;
+  const int buf_stride = (rows_cap + 1) * s4;   // float4 per buffer
+  int* sptr = reinterpret_cast<int*>(sx + 2 * (size_t)buf_stride);
+  unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
+  pdl_wait();
+  const int nslices = d / S;
+  const int ngroups = (nslices + group - 1) / group;
+  const int b = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
+  const int slice0 = grp * group, slice1 = min(nslices, slice0 + group);
+  const int r0 = face_off[b];
+  const int n_b = min(face_off[b + 1] - r0, rows_cap);
+  const int tid = threadIdx.x;
+  const int c = tid % s4;
+  const uint32_t sx_addr = tc::smem_u32(sx);
+  auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf, one commit group
+    const float* xs = x + (size_t)r0 * d + slice * S;
+    const uint32_t base = sx_addr + (uint32_t)buf * (uint32_t)buf_stride * 16u;
+    for (int i = tid; i < n_b * s4; i += NTHR) {
+      const int row = i / s4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)i * 16u), "l"(xs + (size_t)row * d + c * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(slice0, 0);
+  if (tid < s4) {   // the row an invalid source id points at, in both buffers
+    sx[n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    sx[buf_stride + n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int e0 = indptr[r0];
+  const long long e1_true = indptr[r0 + n_b];
+  const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
+  const bool fast = n_e <= edges_cap && e1_true <= cap && (rows_cap + 1) * s4 <= 65536;
+  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = indptr[r0 + i] - e0;
+  if (fast) {
+    for (int i = tid; i < n_e; i += NTHR) {
+      const unsigned nb = (unsigned)(__ldg(src + e0 + i) - r0);
+      ssrc[i] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
+    }
+  }
+  constexpr int TPR = s4 / 2;
+  const int g = tid % TPR;
+  const int swap = (tid / TPR) & 1;
+  const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;
+  for (int slice = slice0; slice < slice1; ++slice) {
+    const int buf = (slice - slice0) & 1;
+    if (slice + 1 < slice1) {
+      issue(slice + 1, buf ^ 1);   // (its last readers passed the barrier that ends the previous iteration)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    const int col = slice * S + g * 8;
+    const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u;
+    const float4* sx_first = sx + (size_t)buf * buf_stride + 2 * g + swap;
+    const float4* sx_second = sx + (size_t)buf * buf_stride + 2 * g + (swap ^ 1);
+    for (int lrow = tid / TPR; lrow < n_b; lrow += NTHR / TPR) {
+      const int s = sptr[lrow];
+      const int e_true = sptr[lrow + 1];
+      float4 a1 = make_float4(0.f, 0.f, 0.f, 0.f), a2 = a1;
+      if (fast) {
+        for (int q = s; q < e_true; ++q) {
+          const int off = ssrc[q];
+          const float4 v = sx_first[off], w = sx_second[off];
+          a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+          a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
+        }
+      } else {
+        const int e = min(e_true, n_e);
+        for (int q = s; q < e; ++q) {
+          const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
+          const int off = (int)(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4;
+          const float4 v = sx_first[off], w = sx_second[off];
+          a1.x += v.x; a1.y += v.y; a1.z += v.z; a1.w += v.w;
+          a2.x += w.x; a2.y += w.y; a2.z += w.z; a2.w += w.w;
+        }
+      }
+      const float4 lo4 = swap ? a2 : a1, hi4 = swap ? a1 : a2;
+      const float cnt = fmaxf((float)(e_true - s), 1.f);
+      const float rc = __frcp_rn(cnt);
+      const float4 o0 = make_float4(div_count(lo4.x, cnt, rc), div_count(lo4.y, cnt, rc), div_count(lo4.z, cnt, rc), div_count(lo4.w, cnt, rc));
+      const float4 o1 = make_float4(div_count(hi4.x, cnt, rc), div_count(hi4.y, cnt, rc), div_count(hi4.z, cnt, rc), div_count(hi4.w, cnt, rc));
+      const int row = r0 + lrow;
+      if (agg) {
+        float4* dst = reinterpret_cast<float4*>(agg + (size_t)row * d + col);
+        dst[0] = o0;
+        dst[1] = o1;
+      }
+      if (agg_image) {
+        uint4 hi, lo;
+        tc::split2(o0.x, o0.y, hi.x, lo.x);
+        tc::split2(o0.z, o0.w, hi.y, lo.y);
+        tc::split2(o1.x, o1.y, hi.z, lo.z);
+        tc::split2(o1.z, o1.w, hi.w, lo.w);
+        uint8_t* pimg = agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_col;
+        *reinterpret_cast<uint4*>(pimg) = hi;
+        *reinterpret_cast<uint4*>(pimg + tc::IMG_PART) = lo;
+      }
+    }
+    __syncthreads();   // every read of this buffer is done before the iteration after next refills it
+  }
+  pdl_launch_dependents();
+}
+
 template <int PER2>  // float2 pairs per lane (d <= 64 * PER2, d even)
 __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, int d, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, uint8_t* __restrict__ image,
@@ -276,6 +390,27 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   const size_t smem = align_up((size_t)(F + 1) * S * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
   // one CTA per (mesh, slice): enough CTAs to fill the machine, or so little work that it does not matter
   const bool enough_ctas = (long long)B * (d / S) >= 64 || max_rows <= 8192;
+  // Large batches take the double-buffered kernel, one CTA per (mesh, group of slices): by default from 512 meshes per launch (measured at
+  // 1 024: 1.74 -> 1.54 ms over the five layers, bit-identical rows); MESHTOK_GATHER_GROUP=1 takes it whenever a group holds >= 2 slices,
+  // =0 never (A/B, scripts/gpu_gather_group_ab.sh)
+  static int use_group = -1;
+  if (use_group < 0) { const char* e = getenv("MESHTOK_GATHER_GROUP"); use_group = e ? (atoi(e) == 1 ? 1 : 0) : 2; }
+  if ((use_group == 1 || (use_group == 2 && B >= 512)) && use_smem && face_off != nullptr && d % 32 == 0) {
+    const int nslices = d / 32;
+    const int group = (int)min((long long)nslices, (long long)B * nslices / 296);   // keep >= 2 CTAs' worth of work per SM
+    const size_t smem2 = align_up(2 * (size_t)(F + 1) * 32 * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
+    if (group >= 2 && smem2 <= 226 * 1024) {
+      static bool configured2 = false;
+      if (!configured2) {
+        MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_group_kernel<32, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+        configured2 = true;
+      }
+      const int ngroups = ceil_div(nslices, group);
+      MT_LAUNCH_PDL((gather_mean_smem_group_kernel<32, 1024>), B * ngroups, 1024, smem2, stream, x, d, indptr, src, edge_capacity, agg,
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, group);
+      return MESHTOK_OK;
+    }
+  }
   if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && enough_ctas) {
     static bool configured = false;
     if (!configured) {
