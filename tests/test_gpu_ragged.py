@@ -159,3 +159,34 @@ def test_ragged_graph_serves_batches_of_any_composition():
     with pytest.raises(AssertionError):
         v, f = synth.ragged_batch("tri", 9, 8, [144] * 4, [0, 1, 2, 3])
         g(*ragged_cuda(v, f))                                                                      # 576 faces > 500
+
+
+_GROUP_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from helpers import SMALL_CFG, make_pair
+from meshgpt_pytorch_b200 import synth
+o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+g = torch.Generator().manual_seed(11)
+counts = torch.randint(1, 41, (320,), generator=g).tolist()
+v, f = synth.ragged_batch("tri", 5, 4, counts, list(range(320)))
+torch.save(m.tokenize(v.cuda(), f.cuda()).cpu(), sys.argv[1])
+"""
+
+
+def test_large_batch_aggregation_kernel_gives_the_same_tokens(tmp_path):
+    """gather_mean_smem_group_kernel (one CTA per mesh and group of slices, double-buffered slices; the default from 512 meshes per launch)
+    forced on with MESHTOK_GATHER_GROUP=1 on a 320-mesh ragged batch (64-wide layers: groups of 2 slices) against MESHTOK_GATHER_GROUP=0:
+    same neighbour order, same rounding, so the tokens must be identical.  The switch is read once per process, hence subprocesses."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "run.py"
+    script.write_text(_GROUP_SCRIPT.format(root=root, tests=os.path.join(root, "tests")))
+    outs = {}
+    for knob in ("0", "1"):
+        path = tmp_path / f"group{knob}.pt"
+        r = subprocess.run([sys.executable, str(script), str(path)], env=dict(os.environ, MESHTOK_GATHER_GROUP=knob), capture_output=True, text=True,
+                           timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs[knob] = torch.load(path)
+    assert outs["0"].shape == outs["1"].shape and torch.equal(outs["0"], outs["1"])
