@@ -45,7 +45,7 @@ enum meshtok_status {
 /* bits of the device-side status word (int32 at workspace offset 0) */
 #define MESHTOK_WS_STATUS_VERTEX_RANGE 1 /* a non-pad face references a vertex id outside [0, V) */
 #define MESHTOK_WS_STATUS_EDGE_OVERFLOW 2 /* more edges than edge_capacity */
-#define MESHTOK_WS_STATUS_EDGE_RANGE 4    /* a user-supplied edge references a face row outside the batch */
+#define MESHTOK_WS_STATUS_EDGE_RANGE 4    /* a user-supplied edge references a face outside the valid faces of its own mesh */
 #define MESHTOK_WS_STATUS_RAGGED_BOUNDS 8 /* ragged input: a mesh has more faces than F or more vertices than V, or decreasing offsets */
 
 int meshtok_version(void);

@@ -154,7 +154,10 @@ class MeshAutoencoder(nn.Module):
             p.requires_grad_(False)
         self._prep: Optional[dict] = None
         self._prep_key = None
-        self._ws_cache: Dict[tuple, Tensor] = {}
+        self._ws_cache: Dict[object, Tensor] = {}     # one grow-only workspace per tag (see _workspace)
+        self._status_pin: Optional[Tensor] = None     # pinned ring of status words of calls whose check is deferred
+        self._status_pending: list = []               # (event, ring slot, context) of those calls, oldest first
+        self._status_next = 0
         self.force_gemm_simt = False      # parity tests: fp32 SIMT linears instead of tcgen05 split-bf16
         self.force_rvq_exact = False      # parity tests: fp32 SIMT nearest-code scan instead of tcgen05 screening
         self.keep_taps = False            # parity tests: also store every intermediate activation as fp32 rows (see taps())
@@ -284,21 +287,61 @@ class MeshAutoencoder(nn.Module):
 
     # ---- the pipeline call ------------------------------------------------------------------------
     def _workspace(self, prep, B, F, V, E, cap, tag=None) -> Tensor:
-        key = (B, F, V, E, cap, tag)          # tag: callers that run concurrently (two graphs in flight) keep apart
-        ws = self._ws_cache.get(key)
-        if ws is None:
-            nbytes = C.c_size_t()
-            check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, E, cap, C.byref(nbytes)))
-            if len(self._ws_cache) > 8:
-                self._ws_cache.clear()
+        """One grow-only buffer per tag (callers that run concurrently - two graphs in flight - use different tags and so keep
+        apart).  Batches from a collate function change F and V nearly every step; the C side only needs workspace_bytes >= its
+        carve total, so the buffer is reallocated only when a call needs more than it holds.  A captured graph pins the buffer it
+        was captured on (GraphedTokenizer keeps a reference), so growing the tag's buffer later never invalidates a graph."""
+        nbytes = C.c_size_t()
+        check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, E, cap, C.byref(nbytes)))
+        ws = self._ws_cache.get(tag)
+        if ws is None or ws.numel() < nbytes.value or ws.device != prep["device"]:
+            ws = None
+            self._ws_cache.pop(tag, None)             # release the old buffer before asking for the larger one
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=prep["device"])
-            self._ws_cache[key] = ws
+            self._ws_cache[tag] = ws
         return ws
+
+    # ---- deferred data-error checks: no host sync on the default path ------------------------------------------
+    _STATUS_RING = 16
+
+    def _defer_status(self, ws: Tensor, context: str):
+        """Copies the call's status word into a pinned ring slot behind the kernels (an async 4-byte D2H on the current stream) and
+        remembers an event; _poll_status() looks at the finished ones when the NEXT call starts, check_last_status() waits for all."""
+        if self._status_pin is None:
+            self._status_pin = torch.zeros(self._STATUS_RING, dtype=torch.int32).pin_memory()
+        if len(self._status_pending) >= self._STATUS_RING:
+            self._poll_status(block=True)
+        slot = self._status_next % self._STATUS_RING
+        self._status_next += 1
+        self._status_pin[slot: slot + 1].copy_(ws[:4].view(torch.int32), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._status_pending.append((ev, slot, context))
+
+    def _poll_status(self, block: bool):
+        while self._status_pending:
+            ev, slot, context = self._status_pending[0]
+            if block:
+                ev.synchronize()
+            elif not ev.query():
+                return
+            self._status_pending.pop(0)
+            status = int(self._status_pin[slot])
+            if status & _lib.WS_STATUS_EDGE_OVERFLOW and not (status & ~_lib.WS_STATUS_EDGE_OVERFLOW):
+                self.edge_slots_per_face *= 4          # later calls get the larger buffer; the flagged batch must be re-run
+                raise MeshtokError(f"edge buffer overflow in an earlier {context} call (its codes are incomplete): edge_slots_per_face "
+                                   f"raised to {self.edge_slots_per_face}, tokenize that batch again (check_status=True re-runs by itself)")
+            self._raise_on_status(status)
 
     def _run(self, *, vertices, faces, face_edges=None, encoded_in=None, want_codes=True, want_encoded=False,
              want_face_coords=False, want_quantized=False, histogram=None, check_status=True, workspace_tag=None):
+        """check_status: True - read the device-side status word after the call (one host sync; re-runs with a larger edge buffer
+        by itself); "deferred" - copy it to pinned memory behind the kernels and raise when the next call starts or at
+        check_last_status() (no sync); False - the caller checks (graphs, pipelines)."""
         prep = self._prepare()
         dev = prep["device"]
+        if check_status == "deferred":
+            self._poll_status(block=False)
         if not faces.is_cuda:
             raise RuntimeError("inputs must be CUDA tensors (no CPU path)")
         nvf, D, Q = self.num_vertices_per_face, self.dim_codebook, self.num_quantizers
@@ -353,6 +396,9 @@ class MeshAutoencoder(nn.Module):
                 self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
                 if not check_status:
                     break
+                if check_status == "deferred":
+                    self._defer_status(ws, "tokenize")
+                    break
                 status = int(ws[:4].view(torch.int32).item())
                 if status & _lib.WS_STATUS_EDGE_OVERFLOW and face_edges is None:
                     cap *= 4                       # rare: very high-valence meshes; rerun with a larger edge buffer
@@ -369,14 +415,16 @@ class MeshAutoencoder(nn.Module):
         if status & _lib.WS_STATUS_VERTEX_RANGE:
             raise IndexError("faces reference a vertex index outside [0, num_vertices) (the reference's gather would fail too)")
         if status & _lib.WS_STATUS_EDGE_RANGE:
-            raise IndexError("face_edges reference a face outside the batch")
+            raise IndexError("face_edges reference a face outside the valid faces of their own mesh")
         if status & _lib.WS_STATUS_RAGGED_BOUNDS:
             raise IndexError("ragged input: a mesh has more faces / vertices than max_faces / max_vertices, or its offsets decrease")
         if status & _lib.WS_STATUS_EDGE_OVERFLOW:
             raise MeshtokError("edge buffer overflow")
 
     def check_last_status(self):
-        """Deferred form of the data-error check for callers that ran with check_status=False."""
+        """Raises for any data error of the calls made so far: waits for the deferred checks (the default of tokenize / forward /
+        tokenize_ragged) and reads the last call's status word (callers that ran with check_status=False)."""
+        self._poll_status(block=True)
         if self.last_workspace is not None:
             self._raise_on_status(int(self.last_workspace[:4].view(torch.int32).item()))
 
@@ -412,7 +460,9 @@ class MeshAutoencoder(nn.Module):
     # ---- reference API ----------------------------------------------------------------------------
     @torch.no_grad()
     def encode(self, *, vertices, faces, face_edges, face_mask, face_edges_mask, return_face_coordinates=False):
-        """meshgpt_pytorch.py:686-785.  -> (b, nf, dims[-1]) fp32 [, (b, nf, nvf*3) int64]."""
+        """meshgpt_pytorch.py:686-785.  -> (b, nf, dims[-1]) fp32 [, (b, nf, nvf*3) int64].
+        Rows of PADDED faces: the embedding rows are zero like the reference's (:771-773); the discretised coordinates are 0 there,
+        where the reference returns the coordinates of vertex 0 (its pad -> 0 fill, :711) - values every caller masks out."""
         faces = faces.masked_fill(~face_mask[:, :, None], self.pad_id)
         face_edges = face_edges.masked_fill(~face_edges_mask[:, :, None], self.pad_id)
         out = self._run(vertices=vertices, faces=faces, face_edges=face_edges, want_codes=False, want_encoded=True,
@@ -424,16 +474,20 @@ class MeshAutoencoder(nn.Module):
     @torch.no_grad()
     def quantize(self, *, faces, face_mask, face_embed, pad_id=None, rvq_sample_codebook_temp=1.0):
         """meshgpt_pytorch.py:787-870.  -> (face_embed_output (b, nf, nvf*dim), codes (b, nf*nvf, q) int64,
-        commit_loss).  Eval semantics: no codebook sampling noise, commit loss is zero."""
+        commit_loss).  Eval semantics: no codebook sampling noise, commit loss is zero.
+        face_embed_output on PADDED faces is unspecified: the reference gathers its pad-vertex row there (the quantiser applied to the
+        mean of project_dim_codebook's bias chunks, :814-829); here it is quantize(zero row) for LFQ and zeros for RVQ.  Decode and the
+        losses mask those rows (:924, :1061-1064); the codes of padded tokens are pad_id exactly like the reference's."""
         faces = faces.masked_fill(~face_mask[:, :, None], self.pad_id)
         out = self._run(vertices=None, faces=faces, encoded_in=face_embed, want_codes=True, want_quantized=True)
         commit_loss = torch.zeros(self.num_quantizers, device=faces.device)
         return out["quantized"], out["codes"], commit_loss
 
     @torch.no_grad()
-    def forward(self, *, vertices, faces, face_edges=None, return_codes=False, histogram=None, check_status=True, **kwargs):
+    def forward(self, *, vertices, faces, face_edges=None, return_codes=False, histogram=None, check_status="deferred", **kwargs):
         """meshgpt_pytorch.py:978-1019 with return_codes=True (the tokenization branch).  The training /
-        reconstruction branches are out of scope."""
+        reconstruction branches are out of scope.  No host sync: data errors (a vertex id out of range, ...) raise when the next
+        call starts or at check_last_status(); check_status=True checks before returning (one sync)."""
         if not return_codes:
             raise NotImplementedError("only forward(return_codes=True) (tokenization) is implemented on this path")
         if kwargs.get("return_recon_faces"):
@@ -461,7 +515,7 @@ class MeshAutoencoder(nn.Module):
     @torch.no_grad()
     def tokenize_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, face_edges: Optional[Tensor] = None,
                         edge_offsets=None, max_faces: Optional[int] = None, max_vertices: Optional[int] = None,
-                        histogram: Optional[Tensor] = None, return_face_coordinates: bool = False, check_status: bool = True):
+                        histogram: Optional[Tensor] = None, return_face_coordinates: bool = False, check_status="deferred"):
         """tokenize() for a batch that was never padded: what the reference's custom_collate (data.py:347-369) turns into
         (b, nf, nvf) / (b, nv, 3) tensors full of pad_id stays a CSR of meshes here.
 
@@ -526,6 +580,8 @@ class MeshAutoencoder(nn.Module):
         """One meshtok_tokenize call in the ragged layout on prepared device tensors.  `total` is the number of face rows the buffers
         hold (the kernels take the live count from face_offsets[B] on the device, so it may be a capacity)."""
         prep = self._prepare()
+        if check_status == "deferred":
+            self._poll_status(block=False)
         E = 0 if face_edges is None else 1      # only the "edges are given" flag in this layout
         cap = max(1024, self.edge_slots_per_face * B * F, n_edges)
         with torch.cuda.device(prep["device"]):
@@ -542,6 +598,9 @@ class MeshAutoencoder(nn.Module):
                 check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
                 self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
                 if not check_status:
+                    break
+                if check_status == "deferred":
+                    self._defer_status(ws, "tokenize_ragged")
                     break
                 status = int(ws[:4].view(torch.int32).item())
                 if status & _lib.WS_STATUS_EDGE_OVERFLOW and histogram is None and face_edges is None:
@@ -619,6 +678,7 @@ class GraphedTokenizer:
             self.codes = model._run(vertices=self.vertices, faces=self.faces, face_edges=self.face_edges, histogram=histogram,
                                     check_status=False, workspace_tag=tag)["codes"]
         self._workspace = model.last_workspace
+        model._ws_cache.pop(tag, None)        # the graph owns its workspace from here on (no entry left behind when it is dropped)
 
     def __call__(self, vertices: Optional[Tensor] = None, faces: Optional[Tensor] = None, face_edges: Optional[Tensor] = None) -> Tensor:
         if vertices is not None:
@@ -693,6 +753,7 @@ class GraphedRaggedTokenizer:
             with torch.cuda.graph(self.graph):
                 model._launch_ragged(*args, histogram=histogram, check_status=False, workspace_tag=tag)
         self._workspace = model.last_workspace
+        model._ws_cache.pop(tag, None)
         self._stage_free = torch.cuda.Event()
 
     def __call__(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets) -> Tensor:

@@ -58,8 +58,7 @@ struct Workspace {
   int32_t* vcodes;
   int32_t* best;
   unsigned long long* packed;
-  int* amb_list;
-  int* amb_count;
+  int* rvq_stats;    // [4] inside the status block: [1] = rows of this call that needed the exact codebook scan
   float4* partial;
   uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
   float* ssq;        // (B*F, 16): parts of the squared row norms of the last SAGE layer (deferred normalisation)
@@ -142,9 +141,12 @@ void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E
   meshtok_taps dummy;
   meshtok_taps* t = taps ? taps : &dummy;
   const size_t BF = (size_t)B * F, BV = (size_t)B * V;
-  w->status = c.take<int>(16, &t->status);
+  // one block, cleared by ONE memset together with mesh_counts behind it: [0..8) status word, [8..16) Counts, [16..20) RVQ statistics
+  w->status = c.take<int>(64, &t->status);
   w->counts = reinterpret_cast<Counts*>(w->status ? w->status + 8 : nullptr);
+  w->rvq_stats = w->status ? w->status + 16 : nullptr;
   t->counts = t->status + 32;
+  t->rvq_stats = t->status + 64;
   w->mesh_counts = c.take<int>(2 * ((size_t)B * 8 + 4));   // two look-back blocks (maps launch, edges launch), each
                                                             // [B][4] aggregates, [B][4] inclusive prefixes, ticket; one memset
   w->offs = c.take<int>(3 * (size_t)(B + 1));
@@ -201,8 +203,6 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->vcodes = c.take<int32_t>(BV * Q, &t->vertex_codes);
   w->best = c.take<int32_t>(BV);
   w->packed = c.take<unsigned long long>(BV);
-  w->amb_list = c.take<int>(BV);
-  w->amb_count = c.take<int>(4, &t->rvq_stats);
   w->partial = nullptr;
   w->rimg = nullptr;
   if (!m->use_lfq && m->codebook_f16_tiles != nullptr) {
@@ -242,9 +242,12 @@ int linear(bool simt, const float* A1, const void* A1_img, int K1, const float* 
 
 // One residual-VQ pass over `n` rows (device count) starting from rows_in; leaves the codes in vcodes (R x Q) and, with
 // need_resid, the final residual in `resid` (else the residual of the last-but-one level: the last subtraction is skipped).
+// tcgen05 path: TWO launches per level - the screening search and the re-score kernel, which also scans the rare ambiguous row,
+// writes the code and updates the residual / row scale / row image.  stats[1] counts the rows that needed the exact scan
+// (clear_stats: zero it here; the pipeline has cleared it with its status block already).
 int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* rscale, int32_t* vcodes,
-            unsigned long long* packed, int* amb_list, int* amb_count, float4* partial, uint8_t* rimg, const int* n_dev, int max_rows,
-            bool exact, bool prepped, bool need_resid, cudaStream_t s) {
+            unsigned long long* packed, int* stats, float4* partial, uint8_t* rimg, const int* n_dev, int max_rows,
+            bool exact, bool prepped, bool need_resid, bool clear_stats, cudaStream_t s) {
   const int D = m->dim_codebook, K = m->codebook_size, Q = m->num_quantizers;
   if (max_rows == 0) return MESHTOK_OK;
   int rc;
@@ -273,33 +276,30 @@ int run_rvq(const meshtok_model* m, const float* rows_in, float* resid, float* r
     ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
     if ((rc = launch_rvq_prep(rows_in, D, resid, rscale, row_image, c_scale, n_dev, max_rows, s)) != MESHTOK_OK) return rc;
   }
-  MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int) * 4, s));
+  if (clear_stats) MT_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(int) * 4, s));
   for (int level = 0; level < Q; ++level) {
+    const bool last = level + 1 == Q;
     if (exact) {
       { ProfScope ps(PROF_RVQ_EXACT, s); rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, nullptr, n_dev, max_rows, packed, s); }
       if (rc != MESHTOK_OK) return rc;
-    } else {
-      MT_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, sizeof(int), s));  // [0] per level; [1] running total of the call
-      { ProfScope ps(PROF_RVQ_SEARCH, s);
-        if (variant == 2)
-          rc = launch_rvq_tc2_search(rimg, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, n_dev,
-                                     max_rows, plan2, partial, s);
-        else
-          rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
-                                    n_dev, max_rows, plan, partial, s); }
+      { ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
+        if (last && !need_resid) rc = launch_rvq_codes_only(packed, vcodes, Q, level, K, n_dev, max_rows, s);
+        else rc = launch_rvq_update(resid, D, m->codebook, K, packed, vcodes, Q, level, rscale, nullptr, c_scale, n_dev, max_rows, s); }
       if (rc != MESHTOK_OK) return rc;
-      { ProfScope ps(PROF_RVQ_RESCORE, s);
-        rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, m->codebook_max_norm,
-                                m->codebook_image_scale, variant == 2 ? c_scale : 0.f, partial, layout, n_dev, max_rows, packed, amb_list,
-                                amb_count, s); }
-      if (rc != MESHTOK_OK) return rc;
-      { ProfScope ps(PROF_RVQ_EXACT, s);
-        rc = launch_rvq_exact(resid, D, m->codebook, m->codebook_sqnorm, K, amb_list, amb_count, max_rows, packed, s); }
-      if (rc != MESHTOK_OK) return rc;
+      continue;
     }
-    { ProfScope ps(PROF_RVQ_PREP_UPDATE, s);
-      if (level + 1 == Q && !need_resid) rc = launch_rvq_codes_only(packed, vcodes, Q, level, n_dev, max_rows, s);
-      else rc = launch_rvq_update(resid, D, m->codebook, packed, vcodes, Q, level, rscale, level + 1 < Q ? row_image : nullptr, c_scale, n_dev, max_rows, s); }
+    { ProfScope ps(PROF_RVQ_SEARCH, s);
+      if (variant == 2)
+        rc = launch_rvq_tc2_search(rimg, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, n_dev,
+                                   max_rows, plan2, partial, s);
+      else
+        rc = launch_rvq_tc_search(resid, rscale, D, m->codebook_f16_tiles, m->codebook_image_scale, m->codebook_sqnorm, K,
+                                  n_dev, max_rows, plan, partial, s); }
+    if (rc != MESHTOK_OK) return rc;
+    { ProfScope ps(PROF_RVQ_RESCORE, s);
+      rc = launch_rvq_rescore(resid, rscale, D, m->codebook, m->codebook_sqnorm, K, m->codebook_max_norm,
+                              m->codebook_image_scale, variant == 2 ? c_scale : 0.f, partial, layout, n_dev, max_rows,
+                              vcodes, Q, level, !last || need_resid, last ? nullptr : row_image, stats, s); }
     if (rc != MESHTOK_OK) return rc;
   }
   return MESHTOK_OK;
@@ -440,7 +440,9 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   const bool simt = a->gemm_simt != 0;
 
   // ---- topology -------------------------------------------------------------------------------
-  MT_CHECK_CUDA(cudaMemsetAsync(w.status, 0, 64, s));
+  // status word, counts, RVQ statistics and the look-back descriptors behind them: ONE memset node
+  MT_CHECK_CUDA(cudaMemsetAsync(w.status, 0, (size_t)(reinterpret_cast<char*>(w.mesh_counts) - reinterpret_cast<char*>(w.status)) +
+                                                 sizeof(int) * 2 * ((size_t)B * 8 + 4), s));
   TopoParams p;
   memset(&p, 0, sizeof(p));
   p.faces = a->faces; p.B = B; p.F = F; p.nvf = nvf; p.V = V; p.pad_id = a->pad_id;
@@ -456,7 +458,6 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
   // side stream next to them and is joined before the first neighbour aggregation.  Inside a stream capture the side
   // stream becomes a parallel branch of the graph.
-  MT_CHECK_CUDA(cudaMemsetAsync(w.mesh_counts, 0, sizeof(int) * 2 * ((size_t)B * 8 + 4), s));
   if ((rc = topo_maps(p, s)) != MESHTOK_OK) return rc;
   bool edges_pending = false;
   SideStream* side = nullptr;
@@ -629,8 +630,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   } else {
     MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
-    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.packed, w.amb_list, w.amb_count, w.partial, w.rimg, n_vrows_dev, max_vrows,
-                      a->rvq_exact != 0, rvq_tc_path, a->quantized_out != nullptr, s)) != MESHTOK_OK) return rc;
+    if ((rc = run_rvq(m, w.avg, w.resid, w.rscale, w.vcodes, w.packed, w.rvq_stats, w.partial, w.rimg, n_vrows_dev, max_vrows,
+                      a->rvq_exact != 0, rvq_tc_path, a->quantized_out != nullptr, /*clear_stats=*/false, s)) != MESHTOK_OK) return rc;
     if (a->quantized_out) {
       const int blocks = max(1, min((int)(((long long)max_vrows * D + 255) / 256), 148 * 8));
       sub_rows_kernel<<<blocks, 256, 0, s>>>(w.avg, w.resid, w.qrows, D, n_vrows_dev, (long long)max_vrows * D);
@@ -638,13 +639,12 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   }
   { ProfScope ps(PROF_GATHER_CODES, s);
+    GatherHist gh{w.vptr, w.counts, max_vrows, reinterpret_cast<unsigned long long*>(a->histogram)};
     if (ragged) rc = launch_gather_codes_ragged(a->faces, a->face_offsets, w.face_row, w.vert_row, w.vcodes, a->total_faces, B, F, nvf, V, Q, a->pad_id,
-                                                a->codes_out, s);
-    else rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out, s);
-    if (rc != MESHTOK_OK) return rc;
-    if (a->histogram)
-      if ((rc = launch_histogram(w.vptr, w.vcodes, w.counts, max_vrows, Q, m->codebook_size,
-                                 reinterpret_cast<unsigned long long*>(a->histogram), s)) != MESHTOK_OK) return rc; }
+                                                a->codes_out, a->histogram ? &gh : nullptr, m->codebook_size, s);
+    else rc = launch_gather_codes(a->faces, w.face_row, w.vert_row, w.vcodes, B, F, nvf, V, Q, a->pad_id, a->codes_out,
+                                  a->histogram ? &gh : nullptr, m->codebook_size, s);
+    if (rc != MESHTOK_OK) return rc; }
   if (a->quantized_out)
     if ((rc = launch_gather_quantized(a->faces, w.face_row, w.vert_row, w.qrows, B, F, nvf, V, D, pad_row, a->quantized_out, s)) != MESHTOK_OK) return rc;
   return MESHTOK_OK;
@@ -664,7 +664,7 @@ int meshtok_lfq_codes(const meshtok_model* m, const float* rows, int R, int32_t*
 
 // carves the stand-alone RVQ workspace; base == nullptr only measures
 static int carve_rvq(const meshtok_model* m, int R, void* base, float** resid, float** rscale, unsigned long long** packed,
-                     int** amb_list, int** amb_count, int** n_dev, float4** partial, uint8_t** rimg, size_t* total) {
+                     int** stats, int** n_dev, float4** partial, uint8_t** rimg, size_t* total) {
   size_t pb = 0, rb = 0;
   const bool tc = m->codebook_f16_tiles != nullptr || base == nullptr;
   if (tc) {
@@ -675,8 +675,7 @@ static int carve_rvq(const meshtok_model* m, int R, void* base, float** resid, f
   *resid = c.take<float>((size_t)R * m->dim_codebook);
   *rscale = c.take<float>(R);
   *packed = c.take<unsigned long long>(R);
-  *amb_list = c.take<int>(R);
-  *amb_count = c.take<int>(4);
+  *stats = c.take<int>(4);
   *n_dev = c.take<int>(4);
   *partial = pb ? c.take<float4>(pb / sizeof(float4)) : nullptr;
   *rimg = rb ? c.take<uint8_t>(rb) : nullptr;
@@ -688,8 +687,8 @@ int meshtok_rvq_workspace_bytes(const meshtok_model* m, int R, size_t* bytes) {
   int rc = check_model(m);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(bytes && R >= 0, "bad arguments");
-  float *resid, *rscale; unsigned long long* packed; int *amb_list, *amb_count, *n_dev; float4* partial; uint8_t* rimg;
-  return carve_rvq(m, R, nullptr, &resid, &rscale, &packed, &amb_list, &amb_count, &n_dev, &partial, &rimg, bytes);
+  float *resid, *rscale; unsigned long long* packed; int *stats, *n_dev; float4* partial; uint8_t* rimg;
+  return carve_rvq(m, R, nullptr, &resid, &rscale, &packed, &stats, &n_dev, &partial, &rimg, bytes);
 }
 
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
@@ -700,9 +699,9 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(rows && codes && workspace && R >= 0, "rows / codes / workspace is null");
   MT_CHECK_ARG(m->codebook && m->codebook_sqnorm, "model.codebook / codebook_sqnorm is null");
-  float *resid, *rscale; unsigned long long* packed; int *amb_list, *amb_count, *n_dev; float4* partial; uint8_t* rimg;
+  float *resid, *rscale; unsigned long long* packed; int *stats, *n_dev; float4* partial; uint8_t* rimg;
   size_t total = 0;
-  if ((rc = carve_rvq(m, R, workspace, &resid, &rscale, &packed, &amb_list, &amb_count, &n_dev, &partial, &rimg, &total)) != MESHTOK_OK) return rc;
+  if ((rc = carve_rvq(m, R, workspace, &resid, &rscale, &packed, &stats, &n_dev, &partial, &rimg, &total)) != MESHTOK_OK) return rc;
   if (total > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", total, workspace_bytes);
     return MESHTOK_ERR_WORKSPACE;
@@ -710,7 +709,7 @@ int meshtok_rvq_codes(const meshtok_model* m, const float* rows, int R, int exac
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   set_int_kernel<<<1, 1, 0, s>>>(n_dev, R);
   MT_CHECK_LAUNCH();
-  rc = run_rvq(m, rows, resid, rscale, codes, packed, amb_list, amb_count, partial, rimg, n_dev, R, exact != 0, false, residual_out != nullptr, s);
+  rc = run_rvq(m, rows, resid, rscale, codes, packed, stats, partial, rimg, n_dev, R, exact != 0, false, residual_out != nullptr, /*clear_stats=*/true, s);
   if (rc != MESHTOK_OK) return rc;
   if (residual_out && R > 0)
     MT_CHECK_CUDA(cudaMemcpyAsync(residual_out, resid, sizeof(float) * (size_t)R * m->dim_codebook, cudaMemcpyDeviceToDevice, s));

@@ -27,6 +27,14 @@ void set_error(const char* fmt, ...);
     }                                                                                         \
   } while (0)
 
+// opt a kernel in to `bytes` of dynamic shared memory on the CURRENT device (remembered per kernel and device, profile.cu)
+int ensure_dynamic_smem(const void* kernel, int bytes);
+#define MT_ENSURE_SMEM(kernel, bytes)                                                                         \
+  do {                                                                                                        \
+    const int _rc = ::meshtok::ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), (int)(bytes));      \
+    if (_rc != MESHTOK_OK) return _rc;                                                                        \
+  } while (0)
+
 extern long long g_launch_count;   // kernels launched by this library (bench.py reports it as gpu_launches)
 #define MT_CHECK_LAUNCH()                  \
   do {                                     \

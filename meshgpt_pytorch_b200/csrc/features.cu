@@ -214,12 +214,8 @@ __global__ void __launch_bounds__(512, 1) face_sum_smem_kernel(FeatParams p, int
 
 template <int NVF, int S>
 int launch_face_sum_smem(const FeatParams& p, int rows_total, int max_rows, cudaStream_t stream) {
-  static bool configured = false;
   const size_t smem = (size_t)rows_total * S * sizeof(float);
-  if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(face_sum_smem_kernel<NVF, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  MT_ENSURE_SMEM((face_sum_smem_kernel<NVF, S>), 200 * 1024);
   const int nslices = p.D / S;
   const int groups = max(1, min(148 / nslices, ceil_div(max_rows, 64)));
   MT_LAUNCH_PDL((face_sum_smem_kernel<NVF, S>), groups * nslices, 512, smem, stream, p, rows_total, groups);

@@ -56,15 +56,21 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
                const float* b_out, int32_t* codes, float* quantized_out, const int* n_rows_dev, int max_rows,
                cudaStream_t stream);
 // codes_out[b, f*nvf+c, q] = vcodes[vert_row[b, faces[b,f,c]], q] (pad_id on padded faces).
+// gh (optional): also hist[q][code] += incidence count of every quantizer row (= non-pad output tokens carrying the code), in the
+// same launch (the first CTAs of the grid take the vertex rows).
+struct GatherHist {
+  const int* vptr;
+  const Counts* counts;
+  int max_vrows;
+  unsigned long long* hist;   // (Q, K)
+};
 int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
-                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream);
-// hist[q][code] += incidence count of every quantizer row (= non-pad output tokens carrying the code).
-int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* counts, int max_vrows, int Q, int K,
-                     unsigned long long* hist, cudaStream_t stream);
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, const GatherHist* gh, int K, cudaStream_t stream);
 // quantized_out[b, f, c*D:(c+1)*D] = qrows[vert_row[b, faces[b,f,c]]]; padded faces get the pad-vertex row,
 // which the reference leaves at zero for LFQ / at the (zero) input for RVQ.
 int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off, const int* face_row, const int* vert_row, const int32_t* vcodes,
-                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream);
+                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out,
+                               const GatherHist* gh, int K, cudaStream_t stream);
 int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
                             int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream);
 // encoded_out (B*F, d) <- packed rows, zeros on padded faces.
@@ -84,9 +90,9 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
 // row_image (optional): fp16(r * rscale) in the layout the CTA-pair search bulk-copies, with the per-row constant
 // rscale * c_scale of the folded |e|^2 column (c_scale = codebook scale / (2 kappa), rvq_screen.cuh); rscale is then capped
 // so that this constant stays a finite fp16 power of two.
-int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
+int launch_rvq_update(float* rows, int D, const float* codebook, int K, const unsigned long long* packed, int32_t* codes, int Q, int level,
                       float* rscale, void* row_image, float c_scale, const int* n_rows_dev, int max_rows, cudaStream_t stream);
-int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, const int* n_rows_dev, int max_rows,
+int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, int K, const int* n_rows_dev, int max_rows,
                           cudaStream_t stream);
 // resid <- rows_in (copy), rscale and row_image as above.
 int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, void* row_image, float c_scale, const int* n_rows_dev,
@@ -106,12 +112,13 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
 struct RvqPartialLayout {
   int mode, stride, T, n_clusters, w_min, parts;
 };
-// re-score: exact fp32 distance of the screened candidates with the reference formula, pick the best,
-// flag rows whose candidate list may be incomplete (-> exact scan).
+// re-score: exact fp32 distance of the screened candidates with the reference formula -> the row's code; a row whose candidate
+// list may be incomplete is scanned exactly by its CTA in the same launch (stats[1] counts them); then codes[row, level] = idx and,
+// with `update`, r <- r - e[idx], rscale[row] and (row_image != null) the fp16 row image of the next level's search.
 // c_scale: 0 for the single-CTA screening kernel, the folded-|e|^2 row constant factor for the CTA-pair kernel
-int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
+int launch_rvq_rescore(float* rows, float* rscale, int D, const float* codebook, const float* e2, int K, float max_norm,
                        float escale, float c_scale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
-                       unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream);
+                       int32_t* codes, int Q, int level, bool update, void* row_image, int* stats, cudaStream_t stream);
 
 // CTA-pair (cta_group::2) screening search (rvq_tc2.cu)
 struct RvqTc2Plan {

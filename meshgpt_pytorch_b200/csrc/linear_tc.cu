@@ -852,14 +852,10 @@ static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
     if (g_lin_trace_k >= 0) { MT_CHECK_CUDA(cudaMalloc(&g_lin_trace, 2 * 8 * 16 * sizeof(long long))); MT_CHECK_CUDA(cudaMemset(g_lin_trace, 0, 2 * 8 * 16 * sizeof(long long))); }
   }
   g.trace = (g_lin_trace_k >= 0 && (g_lin_launches++ % 7) == g_lin_trace_k) ? g_lin_trace : nullptr;
-  static bool configured = false;
-  if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
-    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
-    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false, 2>::SMEM_TOTAL));
-    MT_CHECK_CUDA(cudaFuncSetAttribute(linear_tc_pair_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true, 2>::SMEM_TOTAL));
-    configured = true;
-  }
+  MT_ENSURE_SMEM(linear_tc_kernel, (Cfg<false, 2>::SMEM_TOTAL));
+  MT_ENSURE_SMEM(linear_tc_pair_kernel, (Cfg<true, 2>::SMEM_TOTAL));
+  MT_ENSURE_SMEM(linear_tc_tail_kernel, (Cfg<false, 2>::SMEM_TOTAL));
+  MT_ENSURE_SMEM(linear_tc_pair_tail_kernel, (Cfg<true, 2>::SMEM_TOTAL));
   const int passes = g.nphase == 2 ? 1 : g.p[0].passes;
   const bool tail = g.p[0].norm_mode == 3 || g.p[0].norm_mode == 4;   // decode path: Block tail / arg-max in the epilogue
   if (linear_tc_pair()) {

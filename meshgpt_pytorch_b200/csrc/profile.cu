@@ -16,6 +16,25 @@ bool pdl_enabled() {
   return on == 1;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute of a kernel: a process that moves to a second GPU must opt
+// in again there.  One bit per (kernel, device); devices beyond 63 simply set the attribute before every launch.
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+  struct Entry { const void* fn; int bytes; unsigned long long devices; };
+  static std::mutex mu;
+  static std::vector<Entry> table;
+  int dev = 0;
+  MT_CHECK_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  Entry* e = nullptr;
+  for (Entry& t : table)
+    if (t.fn == kernel && t.bytes == bytes) { e = &t; break; }
+  if (e == nullptr) { table.push_back(Entry{kernel, bytes, 0ull}); e = &table.back(); }
+  if (dev >= 0 && dev < 64 && ((e->devices >> dev) & 1ull)) return MESHTOK_OK;
+  MT_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (dev >= 0 && dev < 64) e->devices |= 1ull << dev;
+  return MESHTOK_OK;
+}
+
 namespace {
 struct Rec { int section; cudaEvent_t a, b; };
 std::mutex g_mu;

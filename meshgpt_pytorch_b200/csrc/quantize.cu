@@ -192,11 +192,43 @@ __global__ void __launch_bounds__(256) lfq_kernel(const float* __restrict__ rows
   }
 }
 
+// hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex.
+// One weighted atomic per DISTINCT code per warp and level: the 32 rows of a warp are combined first (codebook usage
+// is skewed, so many rows of a warp share a code and un-aggregated atomics serialise on a few hot addresses).
+// Rides in the first ceil(rows / 256) CTAs of the code-gather kernels (it used to be a launch of its own: ~5 us of work
+// behind ~2 us of launch latency); every thread of the CTA must call it.
+struct HistArgs {
+  const int* vptr;
+  const Counts* counts;
+  int K, blocks;                 // blocks = CTAs that carry histogram rows (0: no histogram)
+  unsigned long long* hist;      // (Q, K) or null
+};
+__device__ __forceinline__ void histogram_rows(const HistArgs& h, const int32_t* __restrict__ vcodes, int Q) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = row < h.counts->n_vrows;
+  const unsigned w = live ? (unsigned)(h.vptr[row + 1] - h.vptr[row]) : 0u;
+  const int lane = lane_id();
+  for (int q = 0; q < Q; ++q) {
+    int c = live ? vcodes[(size_t)row * Q + q] : -1;
+    if (c >= h.K) c = -1;
+    unsigned sum = 0;
+    int leader = 32;
+#pragma unroll
+    for (int l = 0; l < 32; ++l) {
+      const int cl = __shfl_sync(0xffffffffu, c, l);
+      const unsigned wl = __shfl_sync(0xffffffffu, w, l);
+      if (cl == c) { sum += wl; leader = min(leader, l); }
+    }
+    if (c >= 0 && leader == lane && sum) atomicAdd(h.hist + (size_t)q * h.K + c, (unsigned long long)sum);
+  }
+}
+
 __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
                                                            const int* __restrict__ vert_row, const int32_t* __restrict__ vcodes,
                                                            int BF, int F, int nvf, int V, int Q, int64_t pad_id,
-                                                           int64_t* __restrict__ codes_out) {
+                                                           int64_t* __restrict__ codes_out, HistArgs h) {
   pdl_wait();
+  if ((int)blockIdx.x < h.blocks) histogram_rows(h, vcodes, Q);
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= (long long)BF * nvf) return;
   const int pf = (int)(tok / nvf);
@@ -218,8 +250,9 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
 __global__ void __launch_bounds__(256) gather_codes_ragged_kernel(const int64_t* __restrict__ faces, const int32_t* __restrict__ in_face_off,
                                                                   const int* __restrict__ face_row, const int* __restrict__ vert_row,
                                                                   const int32_t* __restrict__ vcodes, long long total_faces, int B, int F,
-                                                                  int nvf, int V, int Q, int64_t pad_id, int64_t* __restrict__ codes_out) {
+                                                                  int nvf, int V, int Q, int64_t pad_id, int64_t* __restrict__ codes_out, HistArgs h) {
   pdl_wait();
+  if ((int)blockIdx.x < h.blocks) histogram_rows(h, vcodes, Q);
   const long long tok = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // total_faces (host) is the capacity of the buffers, the live count is the last offset: a graph captured on upper bounds serves every batch
   if (tok >= min(total_faces, (long long)__ldg(in_face_off + B)) * nvf) return;
@@ -238,31 +271,6 @@ __global__ void __launch_bounds__(256) gather_codes_ragged_kernel(const int64_t*
   }
   const int vr = vert_row[(size_t)b * V + faces[tok]];
   for (int q = 0; q < Q; ++q) dst[q] = vcodes[(size_t)vr * Q + q];
-}
-
-// hist[q][code] += number of output tokens that carry the code = number of (face, slot) incidences of the vertex.
-// One weighted atomic per DISTINCT code per warp and level: the 32 rows of a warp are combined first (codebook usage
-// is skewed, so many rows of a warp share a code and un-aggregated atomics serialise on a few hot addresses).
-__global__ void __launch_bounds__(256) histogram_kernel(const int* __restrict__ vptr, const int32_t* __restrict__ vcodes,
-                                                        const Counts* counts, int Q, int K, unsigned long long* __restrict__ hist) {
-  pdl_wait();
-  const int row = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = row < counts->n_vrows;
-  const unsigned w = live ? (unsigned)(vptr[row + 1] - vptr[row]) : 0u;
-  const int lane = lane_id();
-  for (int q = 0; q < Q; ++q) {
-    int c = live ? vcodes[(size_t)row * Q + q] : -1;
-    if (c >= K) c = -1;
-    unsigned sum = 0;
-    int leader = 32;
-#pragma unroll
-    for (int l = 0; l < 32; ++l) {
-      const int cl = __shfl_sync(0xffffffffu, c, l);
-      const unsigned wl = __shfl_sync(0xffffffffu, w, l);
-      if (cl == c) { sum += wl; leader = min(leader, l); }
-    }
-    if (c >= 0 && leader == lane && sum) atomicAdd(hist + (size_t)q * K + c, (unsigned long long)sum);
-  }
 }
 
 __global__ void __launch_bounds__(256) gather_quantized_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
@@ -346,28 +354,35 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
   return MESHTOK_OK;
 }
 
+static HistArgs hist_args(const GatherHist* gh, int K) {
+  HistArgs h;
+  memset(&h, 0, sizeof(h));
+  if (gh != nullptr && gh->hist != nullptr && gh->max_vrows > 0) {
+    h.vptr = gh->vptr; h.counts = gh->counts; h.K = K; h.hist = gh->hist;
+    h.blocks = ceil_div(gh->max_vrows, 256);
+  }
+  return h;
+}
+
 int launch_gather_codes(const int64_t* faces, const int* face_row, const int* vert_row, const int32_t* vcodes, int B,
-                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream) {
+                        int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, const GatherHist* gh, int K, cudaStream_t stream) {
   const long long n = (long long)B * F * nvf;
-  if (n == 0) return MESHTOK_OK;
-  MT_LAUNCH_PDL(gather_codes_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q, pad_id,
-                codes_out);
+  const HistArgs h = hist_args(gh, K);
+  if (n == 0 && h.blocks == 0) return MESHTOK_OK;
+  const unsigned blocks = (unsigned)max((long long)h.blocks, (n + 255) / 256);
+  MT_LAUNCH_PDL(gather_codes_kernel, blocks, 256, 0, stream, faces, face_row, vert_row, vcodes, B * F, F, nvf, V, Q, pad_id, codes_out, h);
   return MESHTOK_OK;
 }
 
 int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off, const int* face_row, const int* vert_row, const int32_t* vcodes,
-                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out, cudaStream_t stream) {
+                               long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out,
+                               const GatherHist* gh, int K, cudaStream_t stream) {
   const long long n = total_faces * nvf;
-  if (n == 0) return MESHTOK_OK;
-  MT_LAUNCH_PDL(gather_codes_ragged_kernel, (unsigned)((n + 255) / 256), 256, 0, stream, faces, in_face_off, face_row, vert_row, vcodes, total_faces,
-                B, F, nvf, V, Q, pad_id, codes_out);
-  return MESHTOK_OK;
-}
-
-int launch_histogram(const int* vptr, const int32_t* vcodes, const Counts* counts, int max_vrows, int Q, int K,
-                     unsigned long long* hist, cudaStream_t stream) {
-  if (max_vrows == 0) return MESHTOK_OK;
-  MT_LAUNCH_PDL(histogram_kernel, ceil_div(max_vrows, 256), 256, 0, stream, vptr, vcodes, counts, Q, K, hist);
+  const HistArgs h = hist_args(gh, K);
+  if (n == 0 && h.blocks == 0) return MESHTOK_OK;
+  const unsigned blocks = (unsigned)max((long long)h.blocks, (n + 255) / 256);
+  MT_LAUNCH_PDL(gather_codes_ragged_kernel, blocks, 256, 0, stream, faces, in_face_off, face_row, vert_row, vcodes, total_faces,
+                B, F, nvf, V, Q, pad_id, codes_out, h);
   return MESHTOK_OK;
 }
 

@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(256) rvq_exact_kernel(const float* __restrict_
       const int it = red_i[tid][t];
       if (dt < d || (dt == d && it < ix)) { d = dt; ix = it; }
     }
+    if (ix == 0x7fffffff) { ix = 0; d = INFINITY; }   // a NaN row: no comparison succeeded; code 0, never an out-of-range index
     const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned int)ix;
     atomicMin(packed + rid[tid], key);
   }
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
                                                          const float* __restrict__ cb, const unsigned long long* __restrict__ packed,
                                                          int32_t* __restrict__ codes, int Q, int level, float* __restrict__ rscale,
                                                          uint8_t* __restrict__ row_image, float c_scale, const int* __restrict__ n_dev,
-                                                         int max_rows) {
+                                                         int max_rows, int K) {
   pdl_wait();
   const int wpb = blockDim.x >> 5;
   const int lane = lane_id();
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
     int idx = 0;
     if (UPDATE) {
       idx = (int)(unsigned int)(packed[row] & 0xffffffffull);   // low word of (distance bits, index)
+      idx = min(max(idx, 0), K - 1);                             // (defensive: the producers never leave an index outside the codebook)
       if (lane == 0) codes[(size_t)row * Q + level] = idx;
     }
     float2 v[PER2];
@@ -187,21 +189,21 @@ __global__ void __launch_bounds__(256) rvq_update_kernel(const float* __restrict
 
 // codes[row, level] = winner of packed[row]; the last level of a call that does not return the residual needs no more
 __global__ void __launch_bounds__(256) rvq_codes_only_kernel(const unsigned long long* __restrict__ packed, int32_t* __restrict__ codes, int Q,
-                                                             int level, const int* __restrict__ n_dev, int max_rows) {
+                                                             int level, const int* __restrict__ n_dev, int max_rows, int K) {
   pdl_wait();
   const int n = n_dev ? min(*n_dev, max_rows) : max_rows;
   for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n; row += gridDim.x * blockDim.x)
-    codes[(size_t)row * Q + level] = (int)(unsigned int)(packed[row] & 0xffffffffull);
+    codes[(size_t)row * Q + level] = min(max((int)(unsigned int)(packed[row] & 0xffffffffull), 0), K - 1);
   pdl_launch_dependents();
 }
 
 }  // namespace
 
-int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, const int* n_rows_dev, int max_rows,
+int launch_rvq_codes_only(const unsigned long long* packed, int32_t* codes, int Q, int level, int K, const int* n_rows_dev, int max_rows,
                           cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 256), 148 * 4));
-  MT_LAUNCH_PDL(rvq_codes_only_kernel, blocks, 256, 0, stream, packed, codes, Q, level, n_rows_dev, max_rows);
+  MT_LAUNCH_PDL(rvq_codes_only_kernel, blocks, 256, 0, stream, packed, codes, Q, level, n_rows_dev, max_rows, K);
   return MESHTOK_OK;
 }
 
@@ -225,14 +227,14 @@ int launch_rvq_exact(const float* rows, int D, const float* codebook, const floa
   return MESHTOK_OK;
 }
 
-int launch_rvq_update(float* rows, int D, const float* codebook, const unsigned long long* packed, int32_t* codes, int Q, int level,
+int launch_rvq_update(float* rows, int D, const float* codebook, int K, const unsigned long long* packed, int32_t* codes, int Q, int level,
                       float* rscale, void* row_image, float c_scale, const int* n_rows_dev, int max_rows, cudaStream_t stream) {
   MT_CHECK_ARG(D <= 512 && D % 2 == 0, "rvq: dim %d must be even and <= 512", D);
   MT_CHECK_ARG(row_image == nullptr || (D % 64 == 0 && c_scale > 0.f), "rvq: a row image needs dim %% 64 == 0 and c_scale > 0");
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RU(P) MT_LAUNCH_PDL((rvq_update_kernel<P, true>), blocks, 256, 0, stream, rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows)
+#define RU(P) MT_LAUNCH_PDL((rvq_update_kernel<P, true>), blocks, 256, 0, stream, rows, rows, D, codebook, packed, codes, Q, level, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows, K)
   if (per2 <= 3) RU(3);
   else RU(8);
 #undef RU
@@ -246,7 +248,7 @@ int launch_rvq_prep(const float* rows_in, int D, float* resid, float* rscale, vo
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   const int per2 = ceil_div(D / 2, 32);
-#define RP(P) MT_LAUNCH_PDL((rvq_update_kernel<P, false>), blocks, 256, 0, stream, rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows)
+#define RP(P) MT_LAUNCH_PDL((rvq_update_kernel<P, false>), blocks, 256, 0, stream, rows_in, resid, D, nullptr, nullptr, nullptr, 0, 0, rscale, static_cast<uint8_t*>(row_image), c_scale, n_rows_dev, max_rows, 1)
   if (per2 <= 3) RP(3);
   else RP(8);
 #undef RP

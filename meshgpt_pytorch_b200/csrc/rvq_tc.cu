@@ -281,25 +281,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) rvq_tc_search_kernel(SearchArg
   }
 }
 
-// ---- re-score ---------------------------------------------------------------------------------------
+// ---- re-score (+ exact scan of the rare ambiguous row + residual update), ONE launch per level ----------------------------
 // One warp per row.  Screening error bound: both operands are rounded to fp16 (relative 2^-11 each, the
 // power-of-two scalings are exact) so |s~ - s| <= 2 ((1+2^-11)^2 - 1) sum_d |r_d e_jd| < 2^-9 * 1.01 * |r| max|e|,
 // plus 2^-25 absolute per element that falls into the fp16 subnormal range after scaling  =: delta  (fp32
 // accumulation error is orders of magnitude below).  Every code whose true score ties the minimum therefore has
-// s~ <= min s~ + 2 delta; if some split's SECOND best is inside that window a third one may hide behind it and the
-// row is sent to the exact scan (with RVQ_TOPK kept chunks per slot: if the LAST of them is inside the window).
-template <int PER>
-__global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restrict__ rows, int D, const float* __restrict__ cb,
-                                                          const float* __restrict__ e2, float max_norm, float escale, float c_scale,
-                                                          const float* __restrict__ rscale,
+// s~ <= min s~ + 2 delta; if some slot's LAST kept chunk (RVQ_TOPK per slot) is inside that window a further one may hide
+// behind it: the row is "ambiguous" and gets the exact fp32 scan of the whole codebook.
+//
+// Round 1 ran this as four launches per level (re-score, exact scan of the flagged rows, residual update / codes-only); the
+// scan launch was empty at the bench workload (0 of 56 448 row-levels flagged) and still cost its launch latency twice per
+// step.  Now the warp that decided a row also finishes it: code id -> vcodes, r <- r - e[idx], the next level's row scale and
+// fp16 row image (the row is in its registers already).  An ambiguous row is scanned by ITS CTA, all warps together, one
+// code per thread at a time with the row broadcast from shared memory (sequential fmaf over the dimensions like
+// rvq_exact_kernel; the screened candidates are then ignored, so the result is the plain fp32 arg-min with the lowest
+// index on ties): ~20 us for the CTA that holds such a row, nothing for the others, no launch for the common case.
+template <int PER2>   // float2 pairs per lane: D <= 64 * PER2
+__global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ rows, int D, const float* __restrict__ cb,
+                                                          const float* __restrict__ e2, int K, float max_norm, float escale, float c_scale,
+                                                          float* __restrict__ rscale,
                                                           const float4* __restrict__ partial, RvqPartialLayout lay,
                                                           const int* __restrict__ n_dev, int max_rows,
-                                                          unsigned long long* __restrict__ packed,
-                                                          int* __restrict__ amb_list, int* __restrict__ amb_count) {
+                                                          int32_t* __restrict__ codes, int Q, int level, int update,
+                                                          uint8_t* __restrict__ row_image, int* __restrict__ stats) {
+  __shared__ float s_x[64 * PER2];
+  __shared__ float s_x2;
+  __shared__ int s_row[8];
+  __shared__ unsigned long long s_best[8];
   pdl_wait();
-  const int lane = lane_id();
-  const int wpb = blockDim.x >> 5;
+  const int lane = lane_id(), warp = warp_id();
+  const int wpb = blockDim.x >> 5;   // 8
   const int n = min(*n_dev, max_rows);
+  const int d2 = D >> 1;
   // loop invariants, hoisted by hand (the 64-bit divisions of the work split were a third of this kernel's instructions
   // when they sat in the row loop): W = steps per cluster of the CTA-pair search, see rvq_tc2.cu
   unsigned W = 1u;
@@ -312,86 +325,155 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(const float* __restric
   const float sqrt_d = sqrtf((float)D);
   const float mn2 = max_norm * max_norm;
   const float inv_escale = 1.f / escale;   // powers of two: the reciprocals are exact
-  for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
-    float x[PER];
+  const int stride = gridDim.x * wpb;
+  const int iters = (n + stride - 1) / stride;   // the same trip count for every warp of the grid: the loop holds CTA barriers
+  for (int it = 0; it < iters; ++it) {
+    const int row = it * stride + blockIdx.x * wpb + warp;
+    const bool active = row < n;
+    float2 x[PER2];
     float x2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < PER; ++i) {
-      const int c = lane + 32 * i;
-      x[i] = c < D ? rows[(size_t)row * D + c] : 0.f;
-      x2 = fmaf(x[i], x[i], x2);
-    }
-    x2 = warp_sum(x2);
-    const float xn = sqrtf(x2);
-    const float rs = rscale[row];
-    float delta = 0.001953125f * 1.01f * xn * max_norm +
-                  5.96e-8f * sqrt_d * (max_norm * __frcp_rn(rs) + xn * inv_escale) + 1e-7f * (x2 + mn2);
-    if (c_scale > 0.f) {
-      // CTA-pair kernel: |e|^2 enters the MMA chain as an fp16 (hi, lo) pair (relative error 2^-21) times the row constant
-      // rscale * c_scale; should that constant underflow fp16 (astronomically large rows) the |e|^2 term is lost altogether
-      delta += 1e-6f * mn2;
-      if (rs * c_scale < 5.9604645e-8f) delta += mn2;
-    }
-    // this row's candidate entries (see RvqPartialLayout): the slots of the clusters whose step range meets the row tile's
-    int n_splits = lay.stride;
-    if (lay.mode == 2) {
-      const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;      // first step of the 256-row tile (the launcher checks the range)
-      n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
-    }
-    // lane s holds entry s (n_splits <= 32 is checked by the launcher): one parallel load instead of a serial walk
-    const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
-    float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
-    if (lane < n_splits) { p0 = prow[lane * RVQ_SLOT_F4]; p1 = prow[lane * RVQ_SLOT_F4 + 1]; }
-    float smin = p0.x;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
-    const float window = smin + 2.f * delta;
-    // chunks of this lane's entry inside the window (ascending list -> a prefix), and whether the list may be incomplete
-    const int mine = (p0.x <= window) + (p0.z <= window) + (p1.x <= window) + (p1.z <= window);
-    const bool ambiguous = __any_sync(0xffffffffu, p1.z <= window);
     float bd = INFINITY;
     int bi = 0x7fffffff;
-    // walk the candidates entry by entry (ascending entry = ascending code range within a cluster's slots is not
-    // guaranteed, so ties are resolved explicitly on the code index below)
-    unsigned live = __ballot_sync(0xffffffffu, mine > 0);
-    while (live) {
-      const int owner = __ffs(live) - 1;
-      live &= live - 1;
-      const int cnt = __shfl_sync(0xffffffffu, mine, owner);
-      const float y0 = __shfl_sync(0xffffffffu, p0.y, owner), y1 = __shfl_sync(0xffffffffu, p0.w, owner);
-      const float y2 = __shfl_sync(0xffffffffu, p1.y, owner), y3 = __shfl_sync(0xffffffffu, p1.w, owner);
+    bool ambiguous = false;
+    if (active) {
+      const float2* xr = reinterpret_cast<const float2*>(rows + (size_t)row * D);
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
+        const int c = lane + 32 * i;
+        x[i] = c < d2 ? xr[c] : make_float2(0.f, 0.f);
+        x2 = fmaf(x[i].x, x[i].x, x2);
+        x2 = fmaf(x[i].y, x[i].y, x2);
+      }
+      x2 = warp_sum(x2);
+      const float xn = sqrtf(x2);
+      const float rs = rscale[row];
+      float delta = 0.001953125f * 1.01f * xn * max_norm +
+                    5.96e-8f * sqrt_d * (max_norm * __frcp_rn(rs) + xn * inv_escale) + 1e-7f * (x2 + mn2);
+      if (c_scale > 0.f) {
+        // CTA-pair kernel: |e|^2 enters the MMA chain as an fp16 (hi, lo) pair (relative error 2^-21) times the row constant
+        // rscale * c_scale; should that constant underflow fp16 (astronomically large rows) the |e|^2 term is lost altogether
+        delta += 1e-6f * mn2;
+        if (rs * c_scale < 5.9604645e-8f) delta += mn2;
+      }
+      // this row's candidate entries (see RvqPartialLayout): the slots of the clusters whose step range meets the row tile's
+      int n_splits = lay.stride;
+      if (lay.mode == 2) {
+        const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;      // first step of the 256-row tile (the launcher checks the range)
+        n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
+      }
+      // lane s holds entry s (n_splits <= 32 is checked by the launcher): one parallel load instead of a serial walk
+      const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
+      float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
+      if (lane < n_splits) { p0 = prow[lane * RVQ_SLOT_F4]; p1 = prow[lane * RVQ_SLOT_F4 + 1]; }
+      float smin = p0.x;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+      const float window = smin + 2.f * delta;
+      // chunks of this lane's entry inside the window (ascending list -> a prefix), and whether the list may be incomplete
+      const int mine = (p0.x <= window) + (p0.z <= window) + (p1.x <= window) + (p1.z <= window);
+      // (a NaN row has no chunk inside the window and is not ambiguous: it falls through to code 0 below)
+      ambiguous = __any_sync(0xffffffffu, p1.z <= window);
+      // walk the candidates entry by entry (ascending entry = ascending code range within a cluster's slots is not
+      // guaranteed, so ties are resolved explicitly on the code index below)
+      unsigned live = ambiguous ? 0u : __ballot_sync(0xffffffffu, mine > 0);   // (an ambiguous row is decided by the full scan alone)
+      while (live) {
+        const int owner = __ffs(live) - 1;
+        live &= live - 1;
+        const int cnt = __shfl_sync(0xffffffffu, mine, owner);
+        const float y0 = __shfl_sync(0xffffffffu, p0.y, owner), y1 = __shfl_sync(0xffffffffu, p0.w, owner);
+        const float y2 = __shfl_sync(0xffffffffu, p1.y, owner), y3 = __shfl_sync(0xffffffffu, p1.w, owner);
 #pragma unroll 1
-      for (int which = 0; which < cnt; ++which) {
-        const int code0 = __float_as_int(which == 0 ? y0 : which == 1 ? y1 : which == 2 ? y2 : y3) * CHUNK;
-        // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
-        float d[CHUNK];
+        for (int which = 0; which < cnt; ++which) {
+          const int code0 = __float_as_int(which == 0 ? y0 : which == 1 ? y1 : which == 2 ? y2 : y3) * CHUNK;
+          // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
+          float d[CHUNK];
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) d[j] = 0.f;
+          for (int j = 0; j < CHUNK; ++j) d[j] = 0.f;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) {
-          const int c = lane + 32 * i;
-          if (c < D) {
+          for (int i = 0; i < PER2; ++i) {
+            const int c = lane + 32 * i;
+            if (c < d2) {
 #pragma unroll
-            for (int j = 0; j < CHUNK; ++j) d[j] = fmaf(x[i], __ldg(cb + (size_t)(code0 + j) * D + c), d[j]);
+              for (int j = 0; j < CHUNK; ++j) {
+                const float2 e = __ldg(reinterpret_cast<const float2*>(cb + (size_t)(code0 + j) * D) + c);
+                d[j] = fmaf(x[i].x, e.x, d[j]);
+                d[j] = fmaf(x[i].y, e.y, d[j]);
+              }
+            }
           }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+          for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+            for (int j = 0; j < CHUNK; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
 #pragma unroll
-        for (int j = 0; j < CHUNK; ++j) {
-          const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, __ldg(e2 + code0 + j)), __fmul_rn(d[j], -2.f)), 0.f));
-          if (q < bd || (q == bd && code0 + j < bi)) { bd = q; bi = code0 + j; }
+          for (int j = 0; j < CHUNK; ++j) {
+            const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, __ldg(e2 + code0 + j)), __fmul_rn(d[j], -2.f)), 0.f));
+            if (q < bd || (q == bd && code0 + j < bi)) { bd = q; bi = code0 + j; }
+          }
         }
       }
     }
-    if (lane == 0) {
-      // (distance bits << 32 | index): non-negative floats order like unsigned ints, so the exact scan of an ambiguous
-      // row can merge into this with a 64-bit atomicMin and ties still resolve to the lowest index
-      if (bi == 0x7fffffff) { bi = 0; bd = INFINITY; }   // NaN row: no comparison succeeded
-      packed[row] = ((unsigned long long)__float_as_uint(bd) << 32) | (unsigned int)bi;
-      if (ambiguous) { amb_list[atomicAdd(amb_count, 1)] = row; atomicAdd(amb_count + 1, 1); }
+    // ---- ambiguous rows of this CTA: exact fp32 scan of the whole codebook by all warps (rare; the barrier is the common-case cost) ----
+    if (__syncthreads_or(ambiguous ? 1 : 0)) {
+      if (lane == 0) { s_row[warp] = ambiguous ? row : -1; s_best[warp] = ~0ull; }
+      __syncthreads();
+      for (int w = 0; w < wpb; ++w) {
+        const int r = s_row[w];
+        if (r < 0) continue;   // (uniform: shared memory)
+        for (int k = threadIdx.x; k < D; k += blockDim.x) s_x[k] = rows[(size_t)r * D + k];
+        if (warp == w && lane == 0) s_x2 = x2;   // the row's owner has |x|^2 (the same value for every code, whatever its rounding)
+        __syncthreads();
+        const float xx = s_x2;
+        float sd = INFINITY;
+        int si = 0x7fffffff;
+        for (int code = threadIdx.x; code < K; code += blockDim.x) {   // ascending per thread: strict < keeps the lowest index
+          const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * D);
+          float acc = 0.f;
+          for (int k4 = 0; k4 < (D >> 2); ++k4) {
+            const float4 e = __ldg(er + k4);
+            const float4 xv = *reinterpret_cast<const float4*>(s_x + 4 * k4);
+            acc = fmaf(xv.x, e.x, acc); acc = fmaf(xv.y, e.y, acc); acc = fmaf(xv.z, e.z, acc); acc = fmaf(xv.w, e.w, acc);
+          }
+          const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(xx, __ldg(e2 + code)), __fmul_rn(acc, -2.f)), 0.f));
+          if (q < sd) { sd = q; si = code; }
+        }
+        // (distance bits << 32 | index): non-negative floats order like unsigned ints, equal distances resolve to the lowest index
+        unsigned long long key = si == 0x7fffffff ? ~0ull : (((unsigned long long)__float_as_uint(sd) << 32) | (unsigned int)si);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other < key ? other : key;
+        }
+        if (lane == 0) atomicMin(&s_best[w], key);
+        __syncthreads();   // s_best[w] complete; s_x free for the next row
+      }
+      if (ambiguous) {
+        const unsigned long long key = s_best[warp];
+        bd = __uint_as_float((unsigned int)(key >> 32));
+        bi = key == ~0ull ? 0x7fffffff : (int)(unsigned int)(key & 0xffffffffull);
+        if (lane == 0) atomicAdd(stats + 1, 1);
+      }
+    }
+    if (!active) continue;
+    // ---- decided: code id, residual update, the next level's row scale and image ----
+    if (bi == 0x7fffffff) bi = 0;   // NaN row: no comparison succeeded (torch.argmax of an all-NaN row is 0 as well)
+    if (lane == 0) codes[(size_t)row * Q + level] = bi;
+    if (update) {
+      const float2* er = reinterpret_cast<const float2*>(cb + (size_t)bi * D);
+      float2* dst = reinterpret_cast<float2*>(rows + (size_t)row * D);
+      float vmax = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
+        const int c = lane + 32 * i;
+        if (c < d2) {
+          const float2 e = __ldg(er + c);
+          x[i].x = __fsub_rn(x[i].x, e.x);
+          x[i].y = __fsub_rn(x[i].y, e.y);
+          dst[c] = x[i];
+          vmax = fmaxf(vmax, fmaxf(fabsf(x[i].x), fabsf(x[i].y)));
+        }
+      }
+      rvq_emit_row_scale_and_image<PER2>(x, vmax, row, D, rscale, row_image, c_scale);
     }
   }
   pdl_launch_dependents();
@@ -432,11 +514,7 @@ __global__ void __launch_bounds__(256) build_image_kernel(const float* __restric
 
 template <int D, int DBG>
 int launch_search(const SearchArgs& a, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem<D>::TOTAL));
-    configured = true;
-  }
+  MT_ENSURE_SMEM((rvq_tc_search_kernel<D, DBG>), Smem<D>::TOTAL);
   MT_LAUNCH_PDL((rvq_tc_search_kernel<D, DBG>), grid, NUM_THREADS, Smem<D>::TOTAL, stream, a);
   return MESHTOK_OK;
 }
@@ -481,35 +559,41 @@ int launch_rvq_tc_search(const float* rows, const float* rscale, int D, const vo
   if (max_rows == 0) return MESHTOK_OK;
   SearchArgs a;
   a.rows = rows; a.rscale = rscale; a.escale = escale; a.image = static_cast<const uint8_t*>(codebook_tiles); a.e2 = e2; a.n_rows_dev = n_rows_dev;
-  static int debug = -1;
-  if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
-  a.debug = debug;
+  a.debug = 0;
   a.max_rows = max_rows; a.K = K; a.n_splits = plan.n_splits; a.tiles_per_split = plan.tiles_per_split; a.partial = partial;
   switch (D) {
     case 64: return launch_search<64, 0>(a, plan.grid, stream);
     case 128: return launch_search<128, 0>(a, plan.grid, stream);
-    case 192:
-      switch (a.debug) {   // timing experiments (MESHTOK_RVQ_DEBUG), D = 192 only
+    case 192: {
+#ifdef MESHTOK_EXPERIMENTS   // timing experiments that produce WRONG codes; never in a product build
+      static int debug = -1;
+      if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
+      a.debug = debug;
+      switch (a.debug) {
         case 1: return launch_search<192, 1>(a, plan.grid, stream);
         case 2: return launch_search<192, 2>(a, plan.grid, stream);
         case 3: return launch_search<192, 3>(a, plan.grid, stream);
       }
+#endif
       return launch_search<192, 0>(a, plan.grid, stream);
+    }
   }
   set_error("tcgen05 RVQ search: unsupported dim %d", D);
   return MESHTOK_ERR_UNSUPPORTED;
 }
 
-int launch_rvq_rescore(const float* rows, const float* rscale, int D, const float* codebook, const float* e2, float max_norm,
+int launch_rvq_rescore(float* rows, float* rscale, int D, const float* codebook, const float* e2, int K, float max_norm,
                        float escale, float c_scale, const float4* partial, const RvqPartialLayout& layout, const int* n_rows_dev, int max_rows,
-                       unsigned long long* packed, int* amb_list, int* amb_count, cudaStream_t stream) {
+                       int32_t* codes, int Q, int level, bool update, void* row_image, int* stats, cudaStream_t stream) {
   if (max_rows == 0) return MESHTOK_OK;
   MT_CHECK_ARG(layout.stride <= 32, "rvq re-score: at most 32 candidate entries per row (got %d)", layout.stride);
   MT_CHECK_ARG(layout.mode != 2 || (long long)ceil_div(max_rows, 256) * layout.T < (1ll << 31),
                "rvq re-score: %d rows x %d code tiles exceed the 32-bit step range", max_rows, layout.T);
+  MT_CHECK_ARG(D % 4 == 0 && D <= 192, "rvq re-score: dim %d must be a multiple of 4 and <= 192", D);
+  MT_CHECK_ARG(row_image == nullptr || (D % 64 == 0 && c_scale > 0.f), "rvq: a row image needs dim %% 64 == 0 and c_scale > 0");
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
-  MT_LAUNCH_PDL(rvq_rescore_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, max_norm, escale, c_scale, rscale, partial, layout, n_rows_dev,
-                max_rows, packed, amb_list, amb_count);
+  MT_LAUNCH_PDL(rvq_rescore_kernel<3>, blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
+                n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
   return MESHTOK_OK;
 }
 

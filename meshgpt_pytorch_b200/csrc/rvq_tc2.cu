@@ -309,11 +309,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
 
 template <int D, int DBG>
 int launch_search2(const Search2Args& a, int grid, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(rvq_tc2_search_kernel<D, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Smem2<D>::TOTAL));
-    configured = true;
-  }
+  MT_ENSURE_SMEM((rvq_tc2_search_kernel<D, DBG>), Smem2<D>::TOTAL);
   MT_LAUNCH_PDL((rvq_tc2_search_kernel<D, DBG>), grid, NUM_THREADS, Smem2<D>::TOTAL, stream, a);
   return MESHTOK_OK;
 }
@@ -360,9 +356,12 @@ int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, con
     case 64: return launch_search2<64, 0>(a, grid, stream);
     case 128: return launch_search2<128, 0>(a, grid, stream);
     case 192: {
+#ifdef MESHTOK_EXPERIMENTS   // timing experiments that produce WRONG codes (DBG = 1: nobody reads the accumulators); never in a product build
       static int debug = -1;
       if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
-      return debug == 1 ? launch_search2<192, 1>(a, grid, stream) : launch_search2<192, 0>(a, grid, stream);
+      if (debug == 1) return launch_search2<192, 1>(a, grid, stream);
+#endif
+      return launch_search2<192, 0>(a, grid, stream);
     }
   }
   set_error("tcgen05 CTA-pair RVQ search: unsupported dim %d", D);

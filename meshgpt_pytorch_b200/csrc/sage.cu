@@ -400,11 +400,7 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     const int group = (int)min((long long)nslices, (long long)B * nslices / 296);   // keep >= 2 CTAs' worth of work per SM
     const size_t smem2 = align_up(2 * (size_t)(F + 1) * 32 * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
     if (group >= 2 && smem2 <= 226 * 1024) {
-      static bool configured2 = false;
-      if (!configured2) {
-        MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_group_kernel<32, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-        configured2 = true;
-      }
+      MT_ENSURE_SMEM((gather_mean_smem_group_kernel<32, 1024>), 226 * 1024);
       const int ngroups = ceil_div(nslices, group);
       MT_LAUNCH_PDL((gather_mean_smem_group_kernel<32, 1024>), B * ngroups, 1024, smem2, stream, x, d, indptr, src, edge_capacity, agg,
                     static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, group);
@@ -412,12 +408,8 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     }
   }
   if (use_smem && face_off != nullptr && d % S == 0 && smem <= 220 * 1024 && enough_ctas) {
-    static bool configured = false;
-    if (!configured) {
-      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<32, 512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      MT_CHECK_CUDA(cudaFuncSetAttribute(gather_mean_smem_kernel<16, 256, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      configured = true;
-    }
+    MT_ENSURE_SMEM((gather_mean_smem_kernel<32, 512, 2>), 220 * 1024);
+    MT_ENSURE_SMEM((gather_mean_smem_kernel<16, 256, 3>), 220 * 1024);
     if (S == 32) {
       MT_LAUNCH_PDL((gather_mean_smem_kernel<32, 512, 2>), B * (d / S), 512, smem, stream, x, d, indptr, src, edge_capacity, agg,
                     static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);

@@ -8,14 +8,16 @@
 //   1. faces -> int32, validity (a face is padding if ANY slot == pad_id, data.py:317), rank of
 //      each valid face among the valid faces (= its packed row inside the mesh);
 //   2. counting sort of (face,slot) by vertex id -> incidence lists, each list ascending in
-//      (face, slot) = the order in which the reference's scatter_add visits them on the CPU;
-//   3. per face i (one warp): candidates = union of the incidence lists of its slots; for each
-//      candidate k the exact slot counts n(i,k), n(k,i) of data.py:324-325 are recomputed from the
-//      two faces and turned into bits of an out- and an in-bitmap; popc gives the degrees, a
-//      prefix-popc walk emits the neighbours in ascending order (= the reference's row-major order).
-// The relation is NOT symmetric for degenerate faces (SURVEY hard part 1), hence two bitmaps.
+//      (face, slot) = the order in which the reference's scatter_add visits them on the CPU
+//      (short lists: insertion sort by one thread; high-valence vertices: a per-warp bitmap sort);
+//   3. per face i (ONE THREAD): a k-way merge over the sorted incidence lists of the face's distinct
+//      vertices visits every candidate neighbour k exactly once, in ascending order (= the reference's
+//      row-major order); for each candidate the exact slot counts n(i,k), n(k,i) of data.py:324-325 are
+//      recomputed from the two faces.  A first pass counts the degrees, a second one emits the
+//      neighbours at the prefix of the degrees - no bitmap, no sort, no warp reductions on this path.
+// The relation is NOT symmetric for degenerate faces (SURVEY hard part 1), hence separate out- and in-degrees.
 //
-// The pipeline uses ONE launch (MODE_CSR): each CTA takes a mesh by ticket, counts its in-degrees, obtains the
+// The pipeline uses MODE_MAPS + MODE_EDGES (or ONE launch, MODE_CSR): each CTA takes a mesh by ticket, counts its in-degrees, obtains the
 // exclusive prefix of (valid faces, referenced vertices, edges) over the preceding meshes with a warp-wide decoupled
 // look-back over per-mesh descriptors in global memory (aggregate / inclusive-prefix flags, as in single-pass scans),
 // and then emits its slice of the batch-global CSR - no separate count launch, offsets kernel or host sync.  The
@@ -447,9 +449,11 @@ __global__ void user_edges_count_kernel(const int64_t* __restrict__ edges, int B
   const long long i = edges[2 * idx], j = edges[2 * idx + 1];
   if (i == pad_id || j == pad_id) return;
   const int b = edge_mesh(idx, E, in_edge_off, B);
-  const long long n = face_off[B];
-  const long long s = face_off[b] + i, t = face_off[b] + j;
-  if (s < 0 || s >= n || t < 0 || t >= n) { atomicOr(status, MESHTOK_WS_STATUS_EDGE_RANGE); return; }
+  // both ends must be valid faces of the edge's OWN mesh.  (The reference adds the mesh's row offset and gathers whatever row that is,
+  // a face of a neighbouring mesh included; here that is an error, reported through the status word, whichever aggregation kernel runs.)
+  const long long nb = face_off[b + 1] - face_off[b];
+  if (i < 0 || i >= nb || j < 0 || j >= nb) { atomicOr(status, MESHTOK_WS_STATUS_EDGE_RANGE); return; }
+  const long long t = face_off[b] + j;
   atomicAdd(&ecount[t], 1);
 }
 
@@ -498,9 +502,9 @@ __global__ void user_edges_fill_kernel(const int64_t* __restrict__ edges, int B,
   const long long i = edges[2 * idx], j = edges[2 * idx + 1];
   if (i == pad_id || j == pad_id) return;
   const int b = edge_mesh(idx, E, in_edge_off, B);
-  const long long n = face_off[B];
-  const long long s = face_off[b] + i, t = face_off[b] + j;
-  if (s < 0 || s >= n || t < 0 || t >= n) return;
+  const long long nb = face_off[b + 1] - face_off[b];
+  if (i < 0 || i >= nb || j < 0 || j >= nb) return;   // (flagged by the count kernel)
+  const long long t = face_off[b] + j;
   const int pos = atomicAdd(&cursor[t], 1);
   if (pos < capacity) etmp[pos] = (int)idx;
   else atomicOr(status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
@@ -561,11 +565,7 @@ static int launch_topology_nvf(TopoParams p, cudaStream_t stream) {
   int ww = 0;
   const size_t smem = topo_smem_bytes(p.F, p.nvf, p.V, nt, &ww);
   p.words_per_warp = ww;
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    MT_CHECK_CUDA(cudaFuncSetAttribute(topology_kernel<MODE, NVF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    configured = 220 * 1024;
-  }
+  if (smem > 48 * 1024) MT_ENSURE_SMEM((topology_kernel<MODE, NVF>), 220 * 1024);
   topology_kernel<MODE, NVF><<<p.B, nt, smem, stream>>>(p);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;

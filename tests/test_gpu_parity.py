@@ -313,8 +313,18 @@ def test_tokenize_variants_agree():
     assert torch.equal(g.tokenize_host(v, f), base.cpu())
     bad = f.clone()
     bad[0, 0, 0] = v.shape[1] + 5
+    with pytest.raises(IndexError):                       # check before returning (one host sync)
+        m.tokenize(v.cuda(), bad.cuda(), check_status=True)
+    # the default never syncs: the error of call n surfaces when call n + 1 starts, or at check_last_status()
+    m.tokenize(v.cuda(), bad.cuda())
     with pytest.raises(IndexError):
-        m.tokenize(v.cuda(), bad.cuda())
+        m.check_last_status()
+    m.tokenize(v.cuda(), bad.cuda())
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        m.tokenize(v.cuda(), f.cuda())
+    assert torch.equal(m.tokenize(v.cuda(), f.cuda()), base)      # and the model still works afterwards
+    m.check_last_status()
 
 
 def test_histogram_accumulates_codebook_usage():

@@ -67,11 +67,12 @@ def test_ragged_refusals():
     v, f = synth.ragged_batch("tri", 9, 8, [50, 144], [0, 1])
     rv, rf, fo, vo = ragged_cuda(v, f)
     with pytest.raises(IndexError):                                              # a mesh larger than the stated bound
-        m.tokenize_ragged(rv, rf, fo.cuda(), vo.cuda(), max_faces=100, max_vertices=128)
+        m.tokenize_ragged(rv, rf, fo.cuda(), vo.cuda(), max_faces=100, max_vertices=128, check_status=True)
     with pytest.raises(IndexError):                                              # mesh-local ids: mesh 0 must not reach into mesh 1's vertices
         bad = rf.clone()
         bad[3, 1] = int(vo[1])
         m.tokenize_ragged(rv, bad, fo, vo)
+        m.check_last_status()                                                    # (the default defers the check: no host sync in the call)
     with pytest.raises(AssertionError):
         m.tokenize_ragged(rv, rf, [0, 10, 5, rf.shape[0]], [0, 1, 2, rv.shape[0]])
     with pytest.raises(RuntimeError):
@@ -127,7 +128,11 @@ def test_ragged_precomputed_face_edges(cfg, kind, counts):
     with pytest.raises(IndexError):                                            # an edge that points outside the batch's faces
         bad = flat_edges.clone()
         bad[-1, 0] = 10 ** 6
-        m.tokenize_ragged(rv, rf, fo, vo, face_edges=bad, edge_offsets=eo)
+        m.tokenize_ragged(rv, rf, fo, vo, face_edges=bad, edge_offsets=eo, check_status=True)
+    with pytest.raises(IndexError):                                            # ... or into ANOTHER mesh's faces (inside the batch, outside its mesh)
+        bad = flat_edges.clone()
+        bad[0, 1] = counts[0]                                                  # first mesh's edge -> first face of the second mesh
+        m.tokenize_ragged(rv, rf, fo, vo, face_edges=bad, edge_offsets=eo, check_status=True)
 
 
 def Dt_self_loops(faces):
