@@ -188,6 +188,40 @@ def test_rvq_tc_small_codebooks_and_ragged_row_counts():
         assert _rvq_check(o, m, rows, exact=False) > 0.995
 
 
+def test_rvq_ambiguous_rows_take_the_exact_scan_inside_the_rescore_launch():
+    """A codebook of 16 distinct vectors repeated 64 times: the screened candidate lists of EVERY row are full of exact ties, so every row
+    is flagged ambiguous and decided by the CTA-cooperative fp32 scan inside rvq_rescore_kernel (round 1: a launch of its own).  The
+    winner among identical codes must be the lowest index, like torch.argmax; also checked: NaN rows do not fault (code 0)."""
+    from meshgpt_pytorch_b200._lib import check, lib, ptr, stream_ptr
+    cfg = dict(SMALL_CFG, use_residual_lfq=False, codebook_size=1024)
+    o, m = make_pair(**cfg)
+    g = torch.Generator().manual_seed(5)
+    base = torch.randn(16, 64, generator=g) * 0.05
+    cb = base.repeat(64, 1)
+    o.quantizer.layers[0]._codebook.embed.copy_(cb[None])
+    m.load_reference_state_dict(o.state_dict())
+    rows = torch.randn(1500, 64, generator=g) * 0.05
+    assert _rvq_check(o, m, rows, exact=False) > 0.999
+    # through the pipeline: the statistic says the scan ran, and the codes still agree with the oracle
+    v, f = synth.grid_batch("tri", 8, 8, [0, 1])
+    got = m.tokenize(v.cuda(), f.cuda()).cpu()
+    assert m.taps()["rvq_exact_rechecks"] > 0
+    assert int(got.max()) < 16, "identical codes: the lowest index (one of the first 16) must win"
+    assert match_rate(got, o.tokenize(v, f)) > 0.99
+    # a NaN row must not fault or produce an out-of-range id
+    prep = m._prepare()
+    bad = rows[:64].clone()
+    bad[3] = float("nan")
+    nbytes = C.c_size_t()
+    check(lib.meshtok_rvq_workspace_bytes(C.byref(prep["model"]), 64, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value, dtype=torch.uint8, device="cuda")
+    codes = torch.full((64, 2), -7, dtype=torch.int32, device="cuda")
+    for exact in (0, 1):
+        check(lib.meshtok_rvq_codes(C.byref(prep["model"]), ptr(bad.cuda()), 64, exact, ptr(codes), None, ptr(ws), nbytes.value, stream_ptr()))
+        torch.cuda.synchronize()
+        assert int(codes.min()) >= 0 and int(codes.max()) < 1024
+
+
 # ---------------------------------------------------------------------------------------------------
 # encoder, stage by stage (taps) and through encode()
 # ---------------------------------------------------------------------------------------------------
