@@ -199,6 +199,41 @@ int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, i
 int meshtok_tokenize(const meshtok_model* model, const meshtok_tokenize_args* args, void* workspace,
                      size_t workspace_bytes, meshtok_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-to-host batch pipeline (csrc/pipeline.cu).  Replaces the per-batch host work of a CPU-side caller of
+ * MeshAutoencoder.tokenize (meshgpt_pytorch.py:949-976 as called from MeshAutoencoderTrainer.tokenize, trainer.py:176-177, on
+ * batches that custom_collate, data.py:347-369, built on the host): a ring of `depth` slots, each with its own stream, CUDA graph of
+ * the whole tokenize pipeline and result buffer.  submit() enqueues H2D(vertices, faces) -> graph -> D2H(codes, status word) on the
+ * next slot's stream and returns at once, handing back the result of the batch that used that slot `depth` submits ago (waiting for
+ * it if need be); drain() waits for everything in flight, oldest first.  The caller owns all memory (passed per slot); the
+ * pipeline owns only its streams, events and graph executables and is the one part of the library that synchronises.
+ * vertices_host / faces_host should be pinned for the copies to be asynchronous.  Before _create, every slot's device staging
+ * buffers must hold a VALID example batch (they are tokenized once eagerly and once under capture).  histogram (device, (Q, K)
+ * int64, or NULL) is accumulated by every replay.  One thread at a time per pipeline.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct meshtok_pipeline meshtok_pipeline;
+typedef struct meshtok_pipeline_slot {
+  float* vertices;         /* device (B, V, 3) staging */
+  int64_t* faces;          /* device (B, F, nvf) staging */
+  int64_t* codes;          /* device (B, F*nvf, Q) */
+  void* workspace;         /* device, >= meshtok_tokenize_workspace_bytes(model, B, F, V, 0, edge_capacity), 256-byte aligned */
+  size_t workspace_bytes;
+  int64_t* codes_host;     /* pinned host (B, F*nvf, Q): where the slot's result lands */
+  int32_t* status_host;    /* pinned host int32[4]: [0] = the batch's MESHTOK_WS_STATUS_* word */
+} meshtok_pipeline_slot;
+typedef struct meshtok_pipeline_result {
+  int64_t ticket;          /* ordinal of the finished batch (0 for the first submit), -1: nothing finished */
+  int32_t slot;
+  int32_t status;          /* MESHTOK_WS_STATUS_* bits of that batch; non-zero: its codes are not valid */
+  const int64_t* codes_host;
+} meshtok_pipeline_result;
+int meshtok_pipeline_create(const meshtok_model* model, int B, int F, int V, int64_t pad_id, int64_t edge_capacity, int64_t* histogram,
+                            const meshtok_pipeline_slot* slots, int depth, meshtok_pipeline** out);
+int meshtok_pipeline_submit(meshtok_pipeline* p, const float* vertices_host, const int64_t* faces_host, meshtok_pipeline_result* finished);
+int meshtok_pipeline_drain(meshtok_pipeline* p, meshtok_pipeline_result* results /* depth entries */, int* n);
+meshtok_stream_t meshtok_pipeline_stream(meshtok_pipeline* p, int slot);   /* the slot's cudaStream_t (to order caller events against it) */
+int meshtok_pipeline_destroy(meshtok_pipeline* p);
+
 /* Debug / parity taps: after meshtok_tokenize with args.keep_taps = 1, describes where the intermediate tensors
  * live inside the workspace (byte offsets) so tests can compare them stage by stage with the oracle. */
 typedef struct meshtok_taps {

@@ -56,6 +56,17 @@ class TokenizeArgs(C.Structure):
     ]
 
 
+class PipelineSlot(C.Structure):
+    _fields_ = [
+        ("vertices", C.c_void_p), ("faces", C.c_void_p), ("codes", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("codes_host", C.c_void_p), ("status_host", C.c_void_p),
+    ]
+
+
+class PipelineResult(C.Structure):
+    _fields_ = [("ticket", C.c_int64), ("slot", C.c_int32), ("status", C.c_int32), ("codes_host", C.c_void_p)]
+
+
 class Taps(C.Structure):
     _fields_ = [
         ("status", C.c_int64), ("counts", C.c_int64), ("face_row", C.c_int64), ("vert_row", C.c_int64),
@@ -111,6 +122,12 @@ SIGNATURES = {
     "meshtok_tokenize_workspace_bytes": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                                    C.POINTER(C.c_size_t)]),
     "meshtok_tokenize": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "meshtok_pipeline_create": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(PipelineSlot), C.c_int,
+                                          C.POINTER(C.c_void_p)]),
+    "meshtok_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PipelineResult)]),
+    "meshtok_pipeline_drain": (C.c_int, [C.c_void_p, C.POINTER(PipelineResult), C.POINTER(C.c_int)]),
+    "meshtok_pipeline_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "meshtok_pipeline_destroy": (C.c_int, [C.c_void_p]),
     "meshtok_tokenize_taps": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(Taps)]),
     "meshtok_lfq_codes": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_rvq_workspace_bytes": (C.c_int, [C.POINTER(Model), C.c_int, C.POINTER(C.c_size_t)]),

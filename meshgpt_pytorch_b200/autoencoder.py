@@ -623,9 +623,9 @@ class MeshAutoencoder(nn.Module):
         run first (status word, edge-buffer size).  See GraphedTokenizer."""
         return GraphedTokenizer(self, vertices, faces, histogram, face_edges)
 
-    def host_pipeline(self, vertices: Tensor, faces: Tensor, depth: int = 2) -> "HostPipeline":
+    def host_pipeline(self, vertices: Tensor, faces: Tensor, depth: int = 2, histogram: Optional[Tensor] = None) -> "HostPipeline":
         """Multi-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
-        return HostPipeline(self, vertices, faces, depth)
+        return HostPipeline(self, vertices, faces, depth, histogram)
 
     # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
     @torch.no_grad()
@@ -785,49 +785,93 @@ class GraphedRaggedTokenizer:
 
 
 class HostPipeline:
-    """Host tensors in, host tensors out, with the copies of one batch overlapping the kernels of the other: two
-    GraphedTokenizers (own static inputs, workspace and pinned output each) alternate on two streams, so the H2D copy of
-    batch i+1 and the D2H copy of batch i-1 run on the copy engines while batch i is on the SMs.
+    """Host tensors in, host tensors out, with the copies of one batch overlapping the kernels of the others - the native batch
+    pipeline of libmeshtok (meshtok_pipeline_*, csrc/pipeline.cu): `depth` slots, each with its own stream, device staging, workspace,
+    CUDA graph of the whole tokenize pipeline and pinned result buffer.  A submit is ONE C call (two H2D copies, a graph launch, the
+    D2H of the codes and of the status word, an event); no Python-side stream juggling, no synchronising status read.
 
-        pipe = model.host_pipeline(example_vertices, example_faces)      # CUDA tensors of the batch shape
-        for v, f in batches:                                             # pinned host tensors
+        pipe = model.host_pipeline(example_vertices, example_faces)      # CUDA tensors of the batch shape (a valid batch)
+        for v, f in batches:                                             # pinned host tensors of that shape
             done = pipe.submit(v, f)        # -> (ticket, codes) of the batch submitted `depth` calls ago, or None
         for ticket, codes in pipe.drain(): ...
 
-    The returned codes tensor is the slot's pinned buffer: copy it before the slot is used again (`depth` submits later).
-    depth > 2 lets more batches overlap on the SMs (each kernel's ramp and tail is filled by the other batches' kernels) at the
-    price of one workspace per slot."""
+    The returned codes tensor is the slot's pinned buffer: copy it before the slot is used again (`depth` submits later).  A data
+    error in a batch (vertex id out of range, ...) raises when that batch is handed back.  depth > 2 lets more batches overlap on
+    the SMs at the price of one workspace per slot.  histogram (optional, (Q, K) int64 CUDA): accumulated by every batch."""
 
-    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, depth: int = 2):
-        assert depth >= 1
-        self.slots = []
-        for _ in range(depth):
-            stream = torch.cuda.Stream()
-            torch.cuda.current_stream().synchronize()
-            with torch.cuda.stream(stream):
-                g = GraphedTokenizer(model, vertices, faces)
-            stream.synchronize()
-            out = torch.empty(g.codes.shape, dtype=g.codes.dtype, pin_memory=True)
-            self.slots.append(dict(graph=g, stream=stream, out=out, done=torch.cuda.Event(), busy=False, ticket=-1))
+    def __init__(self, model: MeshAutoencoder, vertices: Tensor, faces: Tensor, depth: int = 2, histogram: Optional[Tensor] = None):
+        assert depth >= 1 and vertices.is_cuda and faces.is_cuda and vertices.ndim == 3 and faces.ndim == 3
+        prep = model._prepare()
+        dev = prep["device"]
+        model.eval()
+        v0 = vertices.to(torch.float32).contiguous()
+        f0 = faces.to(torch.int64).contiguous()
+        B, F, nvf = f0.shape
+        V = v0.shape[1]
+        assert nvf == model.num_vertices_per_face
+        model._run(vertices=v0, faces=f0, check_status=True)                 # raises on bad example data; sizes the edge buffer
+        cap = max(1024, model.edge_slots_per_face * B * F)
+        nbytes = C.c_size_t()
+        check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, 0, cap, C.byref(nbytes)))
+        self.model, self.depth, self.shape = model, depth, (B, F, V)
+        self._keep = []
+        slots = (_lib.PipelineSlot * depth)()
+        self.outs, self._status = [], []
+        with torch.cuda.device(dev):
+            for s in range(depth):
+                v, f = v0.clone(), f0.clone()
+                codes = torch.empty((B, F * nvf, model.num_quantizers), dtype=torch.int64, device=dev)
+                ws = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+                out = torch.empty(codes.shape, dtype=torch.int64).pin_memory()
+                st = torch.zeros(4, dtype=torch.int32).pin_memory()
+                self._keep += [v, f, codes, ws]
+                self.outs.append(out)
+                self._status.append(st)
+                slots[s].vertices, slots[s].faces, slots[s].codes = ptr(v), ptr(f), ptr(codes)
+                slots[s].workspace, slots[s].workspace_bytes = ptr(ws), ws.numel()
+                slots[s].codes_host, slots[s].status_host = ptr(out), ptr(st)
+            torch.cuda.synchronize(dev)
+            handle = C.c_void_p()
+            check(lib.meshtok_pipeline_create(C.byref(prep["model"]), B, F, V, int(model.pad_id), cap, ptr(histogram), slots, depth, C.byref(handle)))
+        self._h = handle
+        self._histogram = histogram
+        self._res = _lib.PipelineResult()
         self.n = 0
 
-    def _collect(self, slot):
-        slot["done"].synchronize()
-        slot["busy"] = False
-        slot["graph"].check()
-        return slot["ticket"], slot["out"]
+    def streams(self):
+        """The slots' CUDA streams as torch objects (to order events of the caller against the pipeline, e.g. for timing)."""
+        return [torch.cuda.ExternalStream(lib.meshtok_pipeline_stream(self._h, s)) for s in range(self.depth)]
+
+    def _result(self, r):
+        if r.ticket < 0:
+            return None
+        if r.status:
+            MeshAutoencoder._raise_on_status(int(r.status))
+        return int(r.ticket), self.outs[r.slot]
 
     def submit(self, vertices: Tensor, faces: Tensor):
-        slot = self.slots[self.n % len(self.slots)]
-        finished = self._collect(slot) if slot["busy"] else None
-        with torch.cuda.stream(slot["stream"]):
-            codes = slot["graph"](vertices, faces)
-            slot["out"].copy_(codes, non_blocking=True)
-            slot["done"].record()
-        slot["busy"], slot["ticket"] = True, self.n
+        B, F, V = self.shape
+        assert not vertices.is_cuda and not faces.is_cuda, "HostPipeline takes HOST tensors (pinned for asynchronous copies)"
+        assert vertices.dtype == torch.float32 and faces.dtype == torch.int64 and vertices.is_contiguous() and faces.is_contiguous()
+        assert tuple(vertices.shape) == (B, V, 3) and tuple(faces.shape[:2]) == (B, F), "batch shape differs from the one the pipeline was built for"
+        check(lib.meshtok_pipeline_submit(self._h, ptr(vertices), ptr(faces), C.byref(self._res)))
+        self._keep_host = (vertices, faces)          # the copies may still be reading them
         self.n += 1
-        return finished
+        return self._result(self._res)
 
     def drain(self):
-        order = sorted((s for s in self.slots if s["busy"]), key=lambda s: s["ticket"])
-        return [self._collect(s) for s in order]
+        res = (_lib.PipelineResult * self.depth)()
+        n = C.c_int()
+        check(lib.meshtok_pipeline_drain(self._h, res, C.byref(n)))
+        return [self._result(res[i]) for i in range(n.value)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.meshtok_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import torch
 import meshgpt_pytorch_b200 as M
 from helpers import make_pair
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 from meshgpt_pytorch_b200._lib import lib
 from oracle import decode_oracle as D
 

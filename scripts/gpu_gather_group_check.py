@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from helpers import make_pair
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 
 o, m = make_pair(use_residual_lfq=False)
 g = torch.Generator().manual_seed(7)

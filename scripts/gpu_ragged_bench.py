@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
 from helpers import make_pair
-from meshgpt_pytorch_b200 import data as Dt, synth
+from meshgpt_pytorch_b200 import data as Dt
+import synth
 from meshgpt_pytorch_b200._lib import lib
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256

@@ -23,7 +23,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from oracle import meshtok_oracle as O  # noqa: E402
 from oracle import reference_extract  # noqa: E402
-from meshgpt_pytorch_b200 import synth  # noqa: E402  (pure-torch generator; does not need the GPU)
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 import helpers  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))

@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from helpers import SMALL_CFG, make_pair
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 from oracle import decode_oracle as D
 
 pytestmark = pytest.mark.gpu

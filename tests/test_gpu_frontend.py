@@ -85,7 +85,7 @@ def test_front_end_against_the_reference_fixtures(name):
 def test_front_end_on_tokenizer_output():
     """tokenize -> front end, full-size shapes: 800-face meshes, 16384 codes + eos, dim 512, codes straight from the GPU tokenizer."""
     from helpers import make_pair as make_tokenizers
-    from meshgpt_pytorch_b200 import synth
+    import synth
     _, tok = make_tokenizers(use_residual_lfq=False)
     v, f = synth.ragged_batch("tri", 20, 20, [800, 423, 1], [0, 1, 2])
     codes = tok.tokenize(v.cuda(), f.cuda())                                 # (3, 2400, 2), -1 on padded faces

@@ -16,7 +16,7 @@ import torch
 
 from helpers import assert_tokens_match_or_attributed, make_pair, match_rate
 from meshgpt_pytorch_b200 import data as Dt
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 
 pytestmark = pytest.mark.gpu
 

@@ -16,14 +16,13 @@ import os
 import pytest
 import torch
 
-from helpers import GOLDEN_DIR, SMALL_CFG, make_oracle, make_pair, match_rate, rel_err
-from meshgpt_pytorch_b200 import synth
+from helpers import GOLDEN_DIR, SMALL_CFG, assert_tokens_match_or_attributed, make_oracle, make_pair, match_rate, rel_err
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 from oracle import meshtok_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-LFQ_EPS = 2e-5
-RVQ_EPS = 1e-4
+from helpers import LFQ_EPS, RVQ_EPS  # noqa: E402  (2e-5 / 1e-4: the stated epsilons of the quantizer contracts)
 ACT_RTOL, ACT_ATOL = 1e-3, 1e-4
 
 
@@ -312,13 +311,18 @@ def test_golden_pipeline_fixtures(name):
     assert codes.shape == fx["codes"].shape and codes.dtype == torch.int64
     pad = (fx["codes"] == -1)
     assert torch.equal(codes == -1, pad)
-    assert match_rate(codes, fx["codes"]) > 0.97, match_rate(codes, fx["codes"])
+    # token by token: equal to the frozen codes, or a near tie at the oracle's quantizer input (helpers.py); the oracle rebuilt from
+    # the fixture's weights reproduces the frozen codes exactly, so its stages are the fixture's
+    o = O.OracleMeshAutoencoder(**fx["cfg"]).eval()
+    o.load_state_dict(fx["state_dict"])
+    assert torch.equal(o.tokenize(fx["vertices"], fx["faces"]), fx["codes"])
+    assert_tokens_match_or_attributed(o, m, fx["vertices"], fx["faces"], codes, min_rate=0.995, label=name)
     enc, dc = m.encode(vertices=fx["vertices"].cuda(), faces=fx["faces"].cuda(), face_edges=fx["stages"]["face_edges"].cuda(),
                        face_mask=(fx["faces"] != -1).all(-1).cuda(), face_edges_mask=(fx["stages"]["face_edges"] != -1).all(-1).cuda(),
                        return_face_coordinates=True)
     fm = (fx["faces"] != -1).all(-1)
     assert torch.equal(dc.cpu()[fm], fx["stages"]["d_coords"][fm])
-    assert rel_err(enc, fx["stages"]["encoded"]) < 5e-2
+    assert rel_err(enc, fx["stages"]["encoded"]) < 2e-3
 
 
 def test_tokenize_variants_agree():
@@ -326,8 +330,7 @@ def test_tokenize_variants_agree():
     o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
     v, f = synth.ragged_batch("tri", 8, 8, [128, 50, 1], [0, 1, 2])
     base = m.tokenize(v.cuda(), f.cuda())
-    want = o.tokenize(v, f)
-    assert match_rate(base, want) > 0.97
+    assert_tokens_match_or_attributed(o, m, v, f, base, min_rate=0.995, label="variants")
     fe = O.derive_face_edges_from_faces(f)
     with_edges = m.tokenize(v.cuda(), f.cuda(), fe.cuda())
     assert torch.equal(with_edges, base)
@@ -409,10 +412,8 @@ def test_full_model_tokens_against_oracle(kind, cfg, nxny):
     for near-ties only."""
     o, m = make_pair(**cfg)
     v, f = synth.grid_batch(kind, *nxny, [0, 1, 2, 3])
-    want = o.tokenize(v, f)
     got = m.tokenize(v.cuda(), f.cuda()).cpu()
-    assert got.shape == want.shape
-    assert match_rate(got, want) >= 0.999, match_rate(got, want)
+    assert_tokens_match_or_attributed(o, m, v, f, got, min_rate=0.999, label=f"{kind} {cfg}")
 
 
 def test_face_edges_cache_bulk_fill(tmp_path):
@@ -443,6 +444,25 @@ def test_host_pipeline_matches_single_calls():
     assert sorted(got) == list(range(5))
     for i, (v, f) in enumerate(batches):
         assert torch.equal(got[i], m.tokenize(v.cuda(), f.cuda()).cpu()), i
+    # three slots in flight, the codebook-usage histogram accumulated by every batch, and a bad batch raising when it is handed back
+    hist = torch.zeros(2, 256, dtype=torch.int64, device="cuda")
+    pipe3 = m.host_pipeline(batches[0][0].cuda(), batches[0][1].cuda(), depth=3, histogram=hist)
+    outs = []
+    for v, f in batches:
+        done = pipe3.submit(v.pin_memory(), f.pin_memory())
+        if done is not None:
+            outs.append(done[1].clone())
+    outs += [c.clone() for _, c in pipe3.drain()]
+    assert all(torch.equal(a, got[i]) for i, a in enumerate(outs))
+    assert torch.equal(hist.cpu(), sum(O.codebook_usage_histogram(c, 2, 256) for c in outs))
+    bad = batches[0][1].clone()
+    bad[0, 0, 0] = batches[0][0].shape[1] + 3
+    pipe3.submit(batches[0][0].pin_memory(), bad.pin_memory())
+    with pytest.raises(IndexError):
+        pipe3.drain()
+    pipe3.submit(batches[1][0].pin_memory(), batches[1][1].pin_memory())
+    assert torch.equal(pipe3.drain()[0][1], got[1])                # the pipeline keeps working after a bad batch
+    pipe3.close()
 
 
 def test_graphed_with_precomputed_edges():
@@ -464,9 +484,7 @@ def test_dense_user_edges_through_the_aggregation_kernels():
     fe = O.derive_face_edges_from_faces(f, neighbor_if_share_one_vertex=True)
     fe = torch.cat([fe, fe[:, :50]], dim=1)          # some edges twice
     got = m.tokenize(v.cuda(), f.cuda(), face_edges=fe.cuda()).cpu()
-    want = o.tokenize(v, f, face_edges=fe)
-    assert torch.equal(got == -1, want == -1)
-    assert match_rate(got, want) > 0.97, match_rate(got, want)
+    assert_tokens_match_or_attributed(o, m, v, f, got, face_edges=fe, min_rate=0.995, label="dense user edges")
 
 
 @pytest.mark.parametrize("cfg,kind,grid,counts", [
@@ -484,9 +502,7 @@ def test_config_matrix_end_to_end(cfg, kind, grid, counts):
     o, m = make_pair(**cfg)
     v, f = synth.ragged_batch(kind, grid[0], grid[1], counts, list(range(len(counts))))
     got = m.tokenize(v.cuda(), f.cuda()).cpu()
-    want = o.tokenize(v, f)
-    assert got.shape == want.shape and torch.equal(got == -1, want == -1)
-    assert match_rate(got, want) > 0.97, match_rate(got, want)
+    assert_tokens_match_or_attributed(o, m, v, f, got, min_rate=0.995, label=str(cfg))
     # vertices nobody references and a lone single-face mesh do not disturb anything
     v2 = torch.cat([v, torch.rand(v.shape[0], 7, 3) * 2 - 1], dim=1)
     assert torch.equal(m.tokenize(v2.cuda(), f.cuda()).cpu(), got)
@@ -497,7 +513,7 @@ _FALLBACK_SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
 from helpers import make_pair
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 out = {{}}
 for name, cfg, kind, nxny, n in (("rvq", dict(use_residual_lfq=False), "tri", (20, 20), 3), ("lfq_quads", dict(quads=True), "quad", (10, 12), 5)):
     o, m = make_pair(**cfg)

@@ -40,7 +40,7 @@ def test_ragged_layout_equals_the_padded_layout(cfg, kind, grid, counts):
     assert torch.equal(coords.cpu(), want_coords.cpu()[mask])
     # and the oracle on the padded batch
     want = o.tokenize(v, f)
-    assert match_rate(Dt.ragged_to_padded_codes(codes, fo, nvf, m.pad_id).cpu(), want) > 0.97
+    assert match_rate(Dt.ragged_to_padded_codes(codes, fo, nvf, m.pad_id).cpu(), want) >= 0.995
 
 
 def test_ragged_empty_meshes_offsets_on_the_device_and_explicit_bounds():
@@ -170,7 +170,7 @@ _GROUP_SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
 from helpers import SMALL_CFG, make_pair
-from meshgpt_pytorch_b200 import synth
+import synth  # tests/synth.py: pure-torch mesh generator (test + bench infrastructure, not product)
 o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
 g = torch.Generator().manual_seed(11)
 counts = torch.randint(1, 41, (320,), generator=g).tolist()

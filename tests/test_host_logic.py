@@ -112,7 +112,7 @@ def test_face_edges_cache_file_format(tmp_path):
     (meshgpt_pytorch/data.py:184-214): float32 (dataset_len, max_edges_len, 2) padded with pad_id + bool flags."""
     import numpy as np
     import meshgpt_pytorch_b200 as M
-    from meshgpt_pytorch_b200 import synth
+    import synth
     from oracle import meshtok_oracle as O
     _, faces = synth.ragged_batch("tri", 6, 6, [72, 30, 1], [0, 1, 2])
     edges = O.derive_face_edges_from_faces(faces)                     # (3, e, 2) padded with -1
