@@ -9,7 +9,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from helpers import SMALL_CFG, make_oracle
-from meshgpt_pytorch_b200 import sharding, synth
+import synth
+from meshgpt_pytorch_b200 import sharding
 from oracle import meshtok_oracle as O
 
 N_MESHES = 5

@@ -5,7 +5,8 @@ import pytest
 import torch
 
 from helpers import SMALL_CFG, make_pair, match_rate
-from meshgpt_pytorch_b200 import data as Dt, synth
+import synth
+from meshgpt_pytorch_b200 import data as Dt
 
 pytestmark = pytest.mark.gpu
 

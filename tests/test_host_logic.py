@@ -5,7 +5,8 @@ import torch
 
 import meshgpt_pytorch_b200 as M
 from helpers import SMALL_CFG, make_oracle
-from meshgpt_pytorch_b200 import sharding, synth
+import synth
+from meshgpt_pytorch_b200 import sharding
 from oracle import meshtok_oracle as O
 
 REFERENCE_KEYS_TRI_LFQ = {
