@@ -55,6 +55,8 @@ const char* meshtok_last_error_string(void);
 int64_t meshtok_kernel_launch_count(void);
 /* Timing experiments (MESHTOK_LINEAR_TRACE=k): clock64 stamps of the k-th tcgen05 linear launch of a step, [2 CTAs][8 events][16 units]. */
 int meshtok_debug_linear_trace(long long* out, int n);
+/* Timing experiments (MESHTOK_GATHER_TRACE=k): per CTA of the k-th neighbour-aggregation launch of a step, 8 stamps (csrc/sage.cu). */
+int meshtok_debug_gather_trace(long long* out, int n);
 
 /* Optional device-side section timing: when enabled, the pipeline brackets each group of kernels with
  * cudaEvents on the caller's stream.  meshtok_profile_collect synchronises on those events, ADDS the elapsed

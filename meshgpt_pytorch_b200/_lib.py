@@ -82,6 +82,7 @@ SIGNATURES = {
     "meshtok_last_error_string": (C.c_char_p, []),
     "meshtok_kernel_launch_count": (C.c_int64, []),
     "meshtok_debug_linear_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
+    "meshtok_debug_gather_trace": (C.c_int, [C.POINTER(C.c_longlong), C.c_int]),
     "meshtok_dec_dequantize_rvq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_dec_dequantize_lfq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_dec_im2col_image": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

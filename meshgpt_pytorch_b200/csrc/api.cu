@@ -71,6 +71,7 @@ struct Workspace {
 struct SideStream {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
+  cudaEvent_t begin = nullptr, bins_done = nullptr;   // the feature-bin launch that runs next to the topology maps
 };
 SideStream* side_stream() {
   static thread_local SideStream ss;
@@ -80,11 +81,14 @@ SideStream* side_stream() {
   if (ss.stream != nullptr && dev == device) return &ss;
   if (ss.stream != nullptr) {   // the thread moved to another device: events and streams are per device
     cudaStreamDestroy(ss.stream); cudaEventDestroy(ss.fork); cudaEventDestroy(ss.join);
+    cudaEventDestroy(ss.begin); cudaEventDestroy(ss.bins_done);
     ss = SideStream();
   }
   if (cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
   if (cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   if (cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.begin, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  if (cudaEventCreateWithFlags(&ss.bins_done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
   device = dev;
   return &ss;
 }
@@ -315,6 +319,7 @@ extern "C" {
 int meshtok_version(void) { return MESHTOK_ABI_VERSION; }
 
 int meshtok_debug_linear_trace(long long* out, int n) { return linear_tc_read_trace(out, n); }
+int meshtok_debug_gather_trace(long long* out, int n) { return gather_mean_read_trace(out, n); }
 
 const char* meshtok_last_error_string(void) { return g_error; }
 
@@ -453,54 +458,19 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   p.face_off = w.offs; p.vert_off = w.offs + (B + 1); p.edge_off = w.offs + 2 * (size_t)(B + 1);
   p.face_row = w.face_row; p.row_face = w.row_face; p.vert_row = w.vert_row; p.vptr = w.vptr; p.vinc = w.vinc;
   p.indptr = w.indptr; p.src = w.src; p.edge_capacity = a->edge_capacity;
-  prof_begin(PROF_TOPOLOGY, s);
-  // Two launches: the maps (packed face rows, vertex incidence CSR) are all the feature kernel and the first linear
-  // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
-  // side stream next to them and is joined before the first neighbour aggregation.  Inside a stream capture the side
-  // stream becomes a parallel branch of the graph.
-  if ((rc = topo_maps(p, s)) != MESHTOK_OK) return rc;
-  bool edges_pending = false;
-  SideStream* side = nullptr;
-  if (a->face_edges) {
-    rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
-                         w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
-    if (rc != MESHTOK_OK) return rc;
-  } else {
-    side = side_stream();
-    MT_CHECK_ARG(side != nullptr, "could not create the side stream for the adjacency kernel");
-    TopoParams pe = p;
-    pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
-    pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
-    pe.ticket = pe.mesh_counts + 8 * (size_t)B;
-    MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
-    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    if ((rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
-    MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
-    edges_pending = true;
-  }
-  auto join_edges = [&]() -> int {
-    if (edges_pending) {
-      MT_CHECK_CUDA(cudaStreamWaitEvent(s, side->join, 0));
-      edges_pending = false;
-    }
-    return MESHTOK_OK;
-  };
-  prof_end(PROF_TOPOLOGY, s);
-  const int* n_faces_dev = &w.counts->n_faces;
-  const int* n_vrows_dev = &w.counts->n_vrows;
-
-  // ---- encoder --------------------------------------------------------------------------------
-  const int L = m->num_sage_layers;
-  const float* enc = nullptr;
-  const uint8_t* enc_img = w.img_x[0];
-  const float* enc_ssq = nullptr;   // set when the encoder left its output rows un-normalised (deferred to project_dim_codebook)
-  int enc_ssq_parts = 0;
-  if (a->encoded_in == nullptr) {
-    FeatParams fp;
-    memset(&fp, 0, sizeof(fp));
+  // ---- feature bins: gather, derived features, discretisation -> table row ids per INPUT face.  Nothing of it depends on the topology
+  // kernel, so it runs on the side stream next to the maps launch (round 1 ran it after the maps, on the critical path).
+  const bool want_features = a->encoded_in == nullptr;
+  FeatParams fp;
+  memset(&fp, 0, sizeof(fp));
+  SideStream* side = side_stream();
+  MT_CHECK_ARG(side != nullptr, "could not create the side stream");
+  bool bins_pending = false;
+  if (want_features) {
     fp.vertices = a->vertices; fp.faces = a->faces; fp.row_face = w.row_face; fp.counts = w.counts;
     fp.in_face_off = a->face_offsets; fp.in_vert_off = a->vertex_offsets;
-    fp.F = F; fp.V = V; fp.nvf = nvf; fp.D = D;
+    fp.pad_id = a->pad_id; fp.total_faces = a->total_faces;
+    fp.B = B; fp.F = F; fp.V = V; fp.nvf = nvf; fp.D = D;
     fp.coor_lo = m->coor_lo;
     fp.coor_den = (float)((double)m->coor_hi - (double)m->coor_lo);
     fp.angle_den = (float)3.141592653589793;
@@ -520,7 +490,59 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     fp.bins_out = w.bins;
     if (a->face_coords_out)
       MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(ragged ? a->total_faces : max_rows) * nvf * 3, s));
-    { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_embed(fp, max_rows, s)) != MESHTOK_OK) return rc; }
+    MT_CHECK_CUDA(cudaEventRecord(side->begin, s));
+    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->begin, 0));
+    if ((rc = launch_face_bins(fp, ragged ? a->total_faces : (long long)max_rows, side->stream)) != MESHTOK_OK) return rc;
+    MT_CHECK_CUDA(cudaEventRecord(side->bins_done, side->stream));
+    bins_pending = true;
+  }
+  prof_begin(PROF_TOPOLOGY, s);
+  // Two launches: the maps (packed face rows, vertex incidence CSR) are all the feature kernel and the first linear
+  // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
+  // side stream next to them and is joined before the first neighbour aggregation.  Inside a stream capture the side
+  // stream becomes a parallel branch of the graph.
+  if ((rc = topo_maps(p, s)) != MESHTOK_OK) return rc;
+  bool edges_pending = false;
+  if (a->face_edges) {
+    rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
+                         w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
+    if (rc != MESHTOK_OK) return rc;
+  } else {
+    TopoParams pe = p;
+    pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
+    pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
+    pe.ticket = pe.mesh_counts + 8 * (size_t)B;
+    MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
+    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+    if ((rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
+    MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+    edges_pending = true;
+  }
+  auto join_edges = [&]() -> int {
+    if (edges_pending) {
+      MT_CHECK_CUDA(cudaStreamWaitEvent(s, side->join, 0));
+      edges_pending = false;
+    }
+    if (bins_pending) {   // (a path that never ran face_sum: the side stream must still rejoin before the call returns)
+      MT_CHECK_CUDA(cudaStreamWaitEvent(s, side->bins_done, 0));
+      bins_pending = false;
+    }
+    return MESHTOK_OK;
+  };
+  prof_end(PROF_TOPOLOGY, s);
+  const int* n_faces_dev = &w.counts->n_faces;
+  const int* n_vrows_dev = &w.counts->n_vrows;
+
+  // ---- encoder --------------------------------------------------------------------------------
+  const int L = m->num_sage_layers;
+  const float* enc = nullptr;
+  const uint8_t* enc_img = w.img_x[0];
+  const float* enc_ssq = nullptr;   // set when the encoder left its output rows un-normalised (deferred to project_dim_codebook)
+  int enc_ssq_parts = 0;
+  if (a->encoded_in == nullptr) {
+    MT_CHECK_CUDA(cudaStreamWaitEvent(s, side->bins_done, 0));
+    bins_pending = false;
+    { ProfScope ps(PROF_FACE_EMBED, s); if ((rc = launch_face_sum(fp, max_rows, s)) != MESHTOK_OK) return rc; }
 
     // tcgen05 path: every activation that feeds a linear exists as a split-bf16 image, written by the kernel that
     // produces it (img_x[cur]: the layer input, img_agg: the aggregated neighbours).  Where the layer is narrow enough

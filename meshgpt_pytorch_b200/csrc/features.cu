@@ -50,19 +50,42 @@ template <int NVF>
 __global__ void __launch_bounds__(128) face_bins_kernel(FeatParams p) {
   pdl_wait();
   constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
-  const int n_rows = p.counts->n_faces;
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < n_rows; row += gridDim.x * blockDim.x) {
-    const int pf = p.row_face[row];
-    const int b = pf / p.F;
-    // where the face and its mesh's vertices sit in the inputs: slot b*F+f of the padded layout, or row in_face_off[b] + f of the ragged one
-    const size_t in_face = p.in_face_off ? (size_t)p.in_face_off[b] + (size_t)(pf - b * p.F) : (size_t)pf;
-    const size_t in_vert0 = p.in_vert_off ? (size_t)p.in_vert_off[b] : (size_t)b * p.V;
+  // One thread per INPUT face (slot b*F+f of the padded layout / row g of the ragged one), not per packed row: the bins depend on
+  // nothing the topology kernel computes, so this launch runs next to it on the side stream.  A face is skipped exactly when the
+  // topology kernel treats it as padding: any slot == pad_id, or a vertex id outside the mesh (it flags the latter in the status word).
+  const long long n_in = p.in_face_off ? min(p.total_faces, (long long)__ldg(p.in_face_off + p.B)) : (long long)p.B * p.F;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += (long long)gridDim.x * blockDim.x) {
+    int b, f;
+    if (p.in_face_off) {   // the last b with in_face_off[b] <= idx (empty meshes repeat an offset: the last one owns the face)
+      int lo = 0, hi = p.B;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((long long)__ldg(p.in_face_off + mid) <= idx) lo = mid; else hi = mid;
+      }
+      b = lo;
+      f = (int)(idx - __ldg(p.in_face_off + b));
+      if (f >= p.F || idx >= __ldg(p.in_face_off + b + 1)) continue;   // (a mesh above the stated bound: flagged by the topology kernel)
+    } else {
+      b = (int)(idx / p.F);
+      f = (int)(idx - (long long)b * p.F);
+    }
+    const size_t in_face = (size_t)idx;
+    const size_t in_vert0 = p.in_vert_off ? (size_t)__ldg(p.in_vert_off + b) : (size_t)b * p.V;
+    const long long v_b = p.in_vert_off ? (long long)(__ldg(p.in_vert_off + b + 1) - __ldg(p.in_vert_off + b)) : (long long)p.V;
     const int64_t* fptr = p.faces + in_face * NVF;
+    long long vid[NVF];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < NVF; ++k) {
+      vid[k] = fptr[k];
+      ok &= vid[k] != p.pad_id && vid[k] >= 0 && vid[k] < v_b;
+    }
+    if (!ok) continue;
+    const size_t row = (size_t)b * p.F + f;   // where face_sum looks the ids up: row_face[packed row] = b*F+f
     float pos[NVF][3];
 #pragma unroll
     for (int k = 0; k < NVF; ++k) {
-      const long long v = fptr[k];
-      const float* src = p.vertices + (in_vert0 + (size_t)v) * 3;
+      const float* src = p.vertices + (in_vert0 + (size_t)vid[k]) * 3;
       pos[k][0] = src[0]; pos[k][1] = src[1]; pos[k][2] = src[2];
     }
     unsigned short bins[NSLOT];
@@ -129,9 +152,9 @@ __global__ void __launch_bounds__(256, 4) face_sum_kernel(FeatParams p) {
     const bool two = r0 + 1 < n_rows;
     // lane s holds table row id s of row r0 (low half) and of row r0 + 1 (high half)
     unsigned ids = 0;
-    if (lane < NSLOT) {
-      ids = p.bins_out[(size_t)r0 * NSLOT + lane];
-      if (two) ids |= (unsigned)p.bins_out[(size_t)(r0 + 1) * NSLOT + lane] << 16;
+    if (lane < NSLOT) {   // (the bins are stored per input face slot: row_face maps the packed row to it)
+      ids = p.bins_out[(size_t)p.row_face[r0] * NSLOT + lane];
+      if (two) ids |= (unsigned)p.bins_out[(size_t)p.row_face[r0 + 1] * NSLOT + lane] << 16;
     }
     for (int item = lane; item < items; item += 32) {
       const int second = item >= d4;
@@ -188,7 +211,7 @@ __global__ void __launch_bounds__(512, 1) face_sum_smem_kernel(FeatParams p, int
   int row = r_lo + tid / s4;
   uint32_t w[NSLOT / 2], wn[NSLOT / 2];
   auto load_ids = [&](int r, uint32_t (&dst)[NSLOT / 2]) {
-    const uint32_t* bp = reinterpret_cast<const uint32_t*>(p.bins_out + (size_t)r * NSLOT);
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(p.bins_out + (size_t)__ldg(p.row_face + r) * NSLOT);
 #pragma unroll
     for (int s2 = 0; s2 < NSLOT / 2; ++s2) dst[s2] = __ldg(bp + s2);
   };
@@ -226,18 +249,30 @@ constexpr int FACE_SUM_SMEM_MAX = 200 * 1024;
 
 }  // namespace
 
-int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream) {
+static int face_embed_check(const FeatParams& p) {
   MT_CHECK_ARG(p.D % 4 == 0, "face_embed: dim_codebook must be a multiple of 4 (got %d)", p.D);
   MT_CHECK_ARG(p.bins_out != nullptr, "face_embed: no workspace for the bin ids");
-  {
-    int rows_total = 0;
-    rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
-    MT_CHECK_ARG(rows_total <= 65535, "face_embed: at most 65535 folded table rows (got %d)", rows_total);
-  }
-  if (max_rows == 0) return MESHTOK_OK;
-  const int blocks1 = max(1, min(ceil_div(max_rows, 128), 148 * 16));
+  const int rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
+  MT_CHECK_ARG(rows_total <= 65535, "face_embed: at most 65535 folded table rows (got %d)", rows_total);
+  return MESHTOK_OK;
+}
+
+// features + discretisation -> table row ids per input face; independent of the topology kernel (may run next to it)
+int launch_face_bins(const FeatParams& p, long long max_in_faces, cudaStream_t stream) {
+  int rc = face_embed_check(p);
+  if (rc != MESHTOK_OK) return rc;
+  if (max_in_faces == 0) return MESHTOK_OK;
+  const int blocks1 = (int)max(1ll, min((max_in_faces + 127) / 128, 148ll * 16));
   if (p.nvf == 3) MT_LAUNCH_PDL(face_bins_kernel<3>, blocks1, 128, 0, stream, p);
   else MT_LAUNCH_PDL(face_bins_kernel<4>, blocks1, 128, 0, stream, p);
+  return MESHTOK_OK;
+}
+
+// x0[row] = bias + sum of the table rows of the packed row's face (after launch_face_bins AND the topology maps)
+int launch_face_sum(const FeatParams& p, int max_rows, cudaStream_t stream) {
+  int rc = face_embed_check(p);
+  if (rc != MESHTOK_OK) return rc;
+  if (max_rows == 0) return MESHTOK_OK;
   // table slices in shared memory when a slice of >= 8 columns fits; else table rows straight from L2
   const int rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
   int S = 0;

@@ -12,7 +12,9 @@ struct FeatParams {
   const int32_t* in_face_off;   // ragged input ([B+1] each, null: padded layout): faces (in_face_off[B], nvf), vertices (in_vert_off[B], 3),
   const int32_t* in_vert_off;   // face_coords_out (in_face_off[B], nvf*3)
   const Counts* counts;
-  int F, V, nvf, D;
+  int64_t pad_id;
+  long long total_faces;    // ragged input: rows the faces buffer holds (the live count is in_face_off[B])
+  int B, F, V, nvf, D;
   float coor_lo, coor_den, angle_den, area_den, clip_lo, clip_hi;
   int n_coor, n_angle, n_area, n_normal;
   const float* tables;      // (sum bins, D)
@@ -21,9 +23,12 @@ struct FeatParams {
   float* x0;                // (rows, D) fp32 or null
   uint8_t* x0_image;        // split-bf16 activation image of x0 (tc_common.cuh) or null
   int64_t* face_coords_out; // (B,F,nvf*3) or null
-  uint16_t* bins_out;       // (rows, nvf*4+4) workspace: folded-table row id (slot offset + bin) of every slot of every packed row
+  uint16_t* bins_out;       // (B*F, nvf*4+4) workspace: folded-table row id (slot offset + bin) of every slot of every input face b*F+f
 };
-int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
+// features + discretisation -> table row ids per INPUT face: needs nothing from the topology kernel (runs next to it on the side stream)
+int launch_face_bins(const FeatParams& p, long long max_in_faces, cudaStream_t stream);
+// x0[row] = bias + sum of the table rows of the packed row's face; after launch_face_bins and the topology maps
+int launch_face_sum(const FeatParams& p, int max_rows, cudaStream_t stream);
 
 // ---- K4 ------------------------------------------------------------------------------------------
 // agg[t] = mean over in-edges (s -> t) of x[s]; sum in ascending CSR order / max(count, 1).
@@ -31,6 +36,7 @@ int launch_face_embed(const FeatParams& p, int max_rows, cudaStream_t stream);
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity,
                        float* agg, void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F,
                        cudaStream_t stream);
+int gather_mean_read_trace(long long* out, int n);   // timing experiments, see sage.cu
 // in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).
 // image_out (optional): the same rows as a split-bf16 activation image for the next tcgen05 linear.
 int launch_row_norm(float* x, int d, const float* gamma, const float* beta, void* image_out, const Counts* counts,

@@ -19,13 +19,21 @@ namespace meshtok {
 
 namespace {
 
-// x / cnt for a small positive integer-valued cnt with rc = 1 / cnt: one FMA correction of the reciprocal product gives
-// the correctly rounded quotient for normal operands (what div.rn's fast path does) without its special-case scaffolding -
-// the IEEE divide was a third of this kernel's instructions.
+// sum / cnt for a small positive integer-valued cnt, as sum * rc with rc = RN(1 / cnt): exact for cnt = 1, 2, 4, 8 (a manifold triangle
+// mesh: three neighbours + the self loop), within one rounding of the quotient otherwise - three orders of magnitude below the split-bf16
+// error of the linear that consumes it.  (Round 1 corrected the product to the exactly rounded quotient with two FMAs per element: a
+// sixth of the aggregation kernels' instructions, on a loop that is issue bound.)  Every aggregation kernel uses this one definition,
+// so their outputs stay bit-identical to each other.
 __device__ __forceinline__ float div_count(float x, float cnt, float rc) {
-  const float q = x * rc;
-  return fmaf(fmaf(-q, cnt, x), rc, q);
+  (void)cnt;
+  return x * rc;
 }
+
+// timing experiments (MESHTOK_GATHER_TRACE=k: the k-th aggregation launch of a step): per CTA [0] globaltimer at start, [1..5] clock64 at
+// start / x copies issued / CSR staged / data landed / rows done, [6] globaltimer at the end, [7] SM id
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ int smid() { int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#define GM_STAMP(i, v) do { if (trace != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) trace[blockIdx.x * 8 + (i)] = (v); } while (0)
 
 template <int CHUNKS>  // float4 chunks per lane (d = 128 * CHUNKS at most)
 __global__ void __launch_bounds__(256) gather_mean_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
@@ -94,13 +102,14 @@ template <int S, int NTHR, int CTAS>   // slice width, threads per CTA, CTAs per
 __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                                   const int* __restrict__ src, long long cap, float* __restrict__ agg,
                                                                   uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
-                                                                  int rows_cap, int edges_cap) {
+                                                                  int rows_cap, int edges_cap, long long* __restrict__ trace) {
   // [rows_cap + 1][S / 4] x slice (the last row stays zero) | [rows_cap + 1] local row pointers | [edges_cap] source row * S/4 (u16)
   extern __shared__ float4 sx[];
   constexpr int s4 = S >> 2;
   int* sptr = reinterpret_cast<int*>(sx + (size_t)(rows_cap + 1) * s4);
   unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
   pdl_wait();
+  GM_STAMP(0, gtimer()); GM_STAMP(1, clock64()); GM_STAMP(7, smid());
   const int nslices = d / S;
   const int b = blockIdx.x / nslices, slice = blockIdx.x % nslices;
   const int r0 = face_off[b];
@@ -116,6 +125,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const floa
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sx_addr + (uint32_t)i * 16u), "l"(xs + (size_t)row * d + c * 4) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
+  GM_STAMP(2, clock64());
   if (tid < s4) sx[n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
   // the mesh's part of the CSR: row pointers relative to its first edge, sources as shared-memory row offsets
   const int e0 = indptr[r0];
@@ -136,8 +146,10 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const floa
         }
     }
   }
+  GM_STAMP(3, clock64());
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  GM_STAMP(4, clock64());
   // S / 8 threads per face, 8 adjacent columns (two 16-byte chunks) each.  The two faces of a quarter warp read their chunks
   // in opposite order (even chunk first / odd chunk first), so the eight 16-byte reads of one instruction fall on eight
   // different bank groups whatever rows they come from.
@@ -192,6 +204,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_kernel(const floa
       *reinterpret_cast<uint4*>(pimg + tc::IMG_PART) = lo;
     }
   }
+  GM_STAMP(5, clock64()); GM_STAMP(6, gtimer());
   pdl_launch_dependents();
 }
 
@@ -203,13 +216,14 @@ template <int S, int NTHR>
 __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                                          const int* __restrict__ src, long long cap, float* __restrict__ agg,
                                                                          uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
-                                                                         int rows_cap, int edges_cap, int group) {
+                                                                         int rows_cap, int edges_cap, int group, long long* __restrict__ trace) {
   extern __shared__ float4 sx[];
   constexpr int s4 = S >> 2;
   const int buf_stride = (rows_cap + 1) * s4;   // float4 per buffer
   int* sptr = reinterpret_cast<int*>(sx + 2 * (size_t)buf_stride);
   unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
   pdl_wait();
+  GM_STAMP(0, gtimer()); GM_STAMP(1, clock64()); GM_STAMP(7, smid());
   const int nslices = d / S;
   const int ngroups = (nslices + group - 1) / group;
   const int b = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
@@ -248,6 +262,7 @@ __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const f
   const int g = tid % TPR;
   const int swap = (tid / TPR) & 1;
   const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;
+  GM_STAMP(3, clock64());
   for (int slice = slice0; slice < slice1; ++slice) {
     const int buf = (slice - slice0) & 1;
     if (slice + 1 < slice1) {
@@ -257,6 +272,7 @@ __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const f
       asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
+    if (slice == slice0) GM_STAMP(4, clock64());
     const int col = slice * S + g * 8;
     const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u;
     const float4* sx_first = sx + (size_t)buf * buf_stride + 2 * g + swap;
@@ -306,6 +322,143 @@ __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const f
     }
     __syncthreads();   // every read of this buffer is done before the iteration after next refills it
   }
+  GM_STAMP(5, clock64()); GM_STAMP(6, gtimer());
+  pdl_launch_dependents();
+}
+
+// Round 2 version of the shared-memory aggregation.  A clock64 trace of the kernels above (MESHTOK_GATHER_TRACE, scripts/gpu_gather_trace.py)
+// showed where their time goes at the bench workload: per (mesh, 32-column slice) 2.3 k cycles issuing the x copies, 5.6 k staging the CSR
+// (three dependent global round trips: face_off -> indptr -> src) and 15 k in the row loop, i.e. ~2.4 k cycles per 8 rows per warp at
+// ~0.7 instructions per cycle and scheduler - the loop is ISSUE bound, not memory bound: four threads per face with 8 columns each spend
+// ~190 instructions per row slice, half of them per-row overhead (row pointers, loop control, source ids, reciprocal, image addresses)
+// that every one of the four repeats.  Here TWO threads share a face, 16 columns each (four 16-byte shared-memory reads per neighbour),
+// the mean is sum * (1 / count) (one rounding more than the division, exact for the 1, 2, 4 neighbours of most faces), and the
+// mesh's first edge comes from the per-mesh edge offsets the topology kernel leaves next to the face offsets (one round trip less).
+// One CTA per (mesh, group of `group` consecutive slices), slices double buffered when group >= 2.  The eight threads of a quarter warp
+// (four faces x two halves) read eight different 16-byte chunks in every instruction whatever rows they come from: a face takes its two
+// 8-column pairs in the order (face & 1) and the two chunks of a pair in the order (face >> 1) & 1 - no bank conflicts.
+template <int NTHR, int CTAS>
+__global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
+                                                                           const int* __restrict__ src, long long cap, float* __restrict__ agg,
+                                                                           uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
+                                                                           const int* __restrict__ edge_off, int rows_cap, int edges_cap, int group,
+                                                                           int nbuf, long long* __restrict__ trace) {
+  extern __shared__ float4 sx[];
+  constexpr int S = 32, s4 = S >> 2;
+  const int buf_stride = (rows_cap + 1) * s4;   // float4 per buffer
+  int* sptr = reinterpret_cast<int*>(sx + (size_t)nbuf * buf_stride);
+  unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
+  pdl_wait();
+  GM_STAMP(0, gtimer()); GM_STAMP(1, clock64()); GM_STAMP(7, smid());
+  const int nslices = d / S;
+  const int ngroups = (nslices + group - 1) / group;
+  const int b = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
+  const int slice0 = grp * group, slice1 = min(nslices, slice0 + group);
+  const int r0 = __ldg(face_off + b);
+  const int n_b = min(__ldg(face_off + b + 1) - r0, rows_cap);
+  const int e0 = __ldg(edge_off + b);                       // = indptr[r0]
+  const long long e1_true = __ldg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
+  const int tid = threadIdx.x;
+  const int c = tid % s4;
+  const uint32_t sx_addr = tc::smem_u32(sx);
+  auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf, one commit group
+    const float* xs = x + (size_t)r0 * d + slice * S;
+    const uint32_t base = sx_addr + (uint32_t)buf * (uint32_t)buf_stride * 16u;
+    for (int i = tid; i < n_b * s4; i += NTHR) {
+      const int row = i / s4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + (uint32_t)i * 16u), "l"(xs + (size_t)row * d + c * 4) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue(slice0, 0);
+  GM_STAMP(2, clock64());
+  if (tid < s4)
+    for (int k = 0; k < nbuf; ++k) sx[(size_t)k * buf_stride + n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
+  const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
+  const bool fast = n_e <= edges_cap && e1_true <= cap && (rows_cap + 1) * s4 <= 65536;
+  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldg(indptr + r0 + i) - e0;
+  if (fast) {
+    for (int base = tid; base < n_e; base += NTHR * 4) {
+      int t[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) t[j] = base + j * NTHR < n_e ? __ldg(src + e0 + base + j * NTHR) : 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (base + j * NTHR < n_e) {
+          const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
+          ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
+        }
+    }
+  }
+  GM_STAMP(3, clock64());
+  const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
+  for (int slice = slice0; slice < slice1; ++slice) {
+    const int buf = nbuf == 2 ? ((slice - slice0) & 1) : 0;
+    if (nbuf == 2 && slice + 1 < slice1) {
+      issue(slice + 1, buf ^ 1);   // (its last readers passed the barrier that ends the previous iteration)
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();
+    if (slice == slice0) GM_STAMP(4, clock64());
+    const float4* sxb = sx + (size_t)buf * buf_stride;
+    for (int item = tid; item < 2 * n_b; item += NTHR) {
+      const int lrow = item >> 1, h = item & 1;
+      const int rot = lrow & 1, sw = (lrow >> 1) & 1;
+      // chunk (16 bytes = 4 columns) ids of this thread's four reads: pair p = (k + rot) & 1 of its half, inside the pair first chunk sw
+      const float4* p0a = sxb + 4 * h + 2 * rot + sw;
+      const float4* p0b = sxb + 4 * h + 2 * rot + (sw ^ 1);
+      const float4* p1a = sxb + 4 * h + 2 * (rot ^ 1) + sw;
+      const float4* p1b = sxb + 4 * h + 2 * (rot ^ 1) + (sw ^ 1);
+      const int s = sptr[lrow];
+      const int e_true = sptr[lrow + 1];
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      const int e = fast ? e_true : min(e_true, n_e);
+      for (int q = s; q < e; ++q) {
+        int off;
+        if (fast) off = ssrc[q];
+        else {   // a mesh with more edges than the staging area holds, or a list cut by the edge capacity
+          const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
+          off = (int)(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4;
+        }
+        const float4 v0 = p0a[off], v1 = p0b[off], v2 = p1a[off], v3 = p1b[off];
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+      }
+      const float rc = __frcp_rn(fmaxf((float)(e_true - s), 1.f));
+      const int row = r0 + lrow;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float4 fa = k == 0 ? a0 : a2, fb = k == 0 ? a1 : a3;   // first-read / second-read chunk of the pair
+        const float4 lo4 = sw ? fb : fa, hi4 = sw ? fa : fb;           // columns col .. col+3 and col+4 .. col+7
+        const float4 o0 = make_float4(lo4.x * rc, lo4.y * rc, lo4.z * rc, lo4.w * rc);
+        const float4 o1 = make_float4(hi4.x * rc, hi4.y * rc, hi4.z * rc, hi4.w * rc);
+        const int col = slice * S + h * 16 + ((k + rot) & 1) * 8;
+        if (agg) {
+          float4* dst = reinterpret_cast<float4*>(agg + (size_t)row * d + col);
+          dst[0] = o0;
+          dst[1] = o1;
+        }
+        if (agg_image) {
+          uint4 hi, lo;
+          tc::split2(o0.x, o0.y, hi.x, lo.x);
+          tc::split2(o0.z, o0.w, hi.y, lo.y);
+          tc::split2(o1.x, o1.y, hi.z, lo.z);
+          tc::split2(o1.z, o1.w, hi.w, lo.w);
+          const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u;
+          uint8_t* pimg = agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_col;
+          *reinterpret_cast<uint4*>(pimg) = hi;
+          *reinterpret_cast<uint4*>(pimg + tc::IMG_PART) = lo;
+        }
+      }
+    }
+    if (nbuf == 2) __syncthreads();   // every read of this buffer is done before the iteration after next refills it
+    else if (slice + 1 < slice1) { __syncthreads(); issue(slice + 1, 0); }
+  }
+  GM_STAMP(5, clock64()); GM_STAMP(6, gtimer());
   pdl_launch_dependents();
 }
 
@@ -374,10 +527,27 @@ __global__ void __launch_bounds__(256) row_norm_kernel(float* __restrict__ x, in
 
 }  // namespace
 
+static long long* g_gm_trace = nullptr;
+static int g_gm_trace_k = -2;
+static long long g_gm_launches = 0;
+
+int gather_mean_read_trace(long long* out, int n) {
+  if (g_gm_trace == nullptr) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, g_gm_trace, sizeof(long long) * (size_t)min(n, 1024 * 8), cudaMemcpyDeviceToHost);
+  return min(n, 1024 * 8);
+}
+
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity, float* agg,
                        void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F, cudaStream_t stream) {
   MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
   if (max_rows == 0) return MESHTOK_OK;
+  if (g_gm_trace_k == -2) {   // timing experiments only: MESHTOK_GATHER_TRACE=k stamps the k-th aggregation launch of every step (5 per step)
+    const char* e = getenv("MESHTOK_GATHER_TRACE");
+    g_gm_trace_k = e ? atoi(e) : -1;
+    if (g_gm_trace_k >= 0) { MT_CHECK_CUDA(cudaMalloc(&g_gm_trace, 1024 * 8 * sizeof(long long))); MT_CHECK_CUDA(cudaMemset(g_gm_trace, 0, 1024 * 8 * sizeof(long long))); }
+  }
+  long long* trace = (g_gm_trace_k >= 0 && (g_gm_launches++ % 5) == g_gm_trace_k) ? g_gm_trace : nullptr;
   // per-mesh slices in shared memory when a 32-column slice of the largest mesh fits (two CTAs per SM up to 880 faces,
   // one up to 1 760); MESHTOK_GATHER_L2=1 keeps the warp-per-row kernel for A/B runs
   static int use_smem = -1;
@@ -393,17 +563,71 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   // Large batches take the double-buffered kernel, one CTA per (mesh, group of slices): by default from 512 meshes per launch (measured at
   // 1 024: 1.74 -> 1.54 ms over the five layers, bit-identical rows); MESHTOK_GATHER_GROUP=1 takes it whenever a group holds >= 2 slices,
   // =0 never (A/B, scripts/gpu_gather_group_ab.sh)
-  static int use_group = -1;
-  if (use_group < 0) { const char* e = getenv("MESHTOK_GATHER_GROUP"); use_group = e ? (atoi(e) == 1 ? 1 : 0) : 2; }
-  if ((use_group == 1 || (use_group == 2 && B >= 512)) && use_smem && face_off != nullptr && d % 32 == 0) {
+  // round 2: two threads per face, 16 columns each (gather_mean_smem_wide_kernel); MESHTOK_GATHER_WIDE=0 keeps the kernels below (A/B)
+  static int use_wide = -1;
+  if (use_wide < 0) { const char* e = getenv("MESHTOK_GATHER_WIDE"); use_wide = (e && atoi(e) == 0) ? 0 : 1; }
+  if (use_wide && use_smem && face_off != nullptr && d % 32 == 0) {
     const int nslices = d / 32;
-    const int group = (int)min((long long)nslices, (long long)B * nslices / 296);   // keep >= 2 CTAs' worth of work per SM
+    const size_t per_buf = (size_t)(F + 1) * 32 * sizeof(float);
+    const size_t csr = (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short);
+    // slices per CTA: a CTA's time ~ (its slices + 1.5 slices' worth of staging the CSR and the first, un-overlapped x slice);
+    // the launch takes ceil(CTAs / (148 * CTAs per SM)) rounds of that.  One slice per CTA: 512 threads, two CTAs per SM.
+    static int forced_group = -2;
+    if (forced_group == -2) { const char* e = getenv("MESHTOK_GATHER_WIDE_GROUP"); forced_group = e ? atoi(e) : -1; }
+    int group = 1;
+    double best = 1e30;
+    for (int g = 1; g <= nslices; ++g) {
+      const bool two_bufs = g >= 2;
+      const size_t smem_g = align_up((two_bufs ? 2 : 1) * per_buf + csr, 16);
+      if (smem_g > 226 * 1024) continue;
+      const int per_sm = (g == 1 && 2 * (smem_g + 1024) <= 226 * 1024) ? 2 : 1;
+      const long long ctas = (long long)B * ceil_div(nslices, g);
+      const double rounds = (double)((ctas + 148 * per_sm - 1) / (148 * per_sm));
+      const double cost = rounds * (g + 1.5) * (per_sm == 2 ? 1.0 : 0.55);   // (a lone CTA with 1 024 threads runs a slice about twice as fast as one of two 512-thread CTAs)
+      if (cost < best - 1e-9) { best = cost; group = g; }
+    }
+    if (forced_group >= 1) group = min(forced_group, nslices);
+    if (best < 1e30) {
+      const int nbuf = group >= 2 ? 2 : 1;
+      const size_t smem_w = align_up(nbuf * per_buf + csr, 16);
+      const int ngroups = ceil_div(nslices, group);
+      const int* edge_off = face_off + 2 * (size_t)(B + 1);
+      if (group == 1) {
+        MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 113 * 1024);
+        MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace);
+      } else {
+        MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
+        MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<1024, 1>), B * ngroups, 1024, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace);
+      }
+      return MESHTOK_OK;
+    }
+  }
+  static int use_group = -1;
+  if (use_group < 0) { const char* e = getenv("MESHTOK_GATHER_GROUP"); use_group = e ? atoi(e) : 2; }
+  if (use_group != 0 && use_smem && face_off != nullptr && d % 32 == 0) {
+    const int nslices = d / 32;
+    // Slices per CTA.  One CTA (1 024 threads, 216 KB) per SM; a CTA's time ~ (its slices + half a slice for the first, un-overlapped
+    // staging); the launch takes ceil(CTAs / 148) rounds of that.  Large batches end up with whole rows per CTA; at 64 meshes the
+    // best cut is 128 CTAs (d = 256: 4 slices each), which beats 512 single-slice CTAs that each pay their own staging.
+    int group = 1;
+    if (use_group == 2 && B < 512) {
+      group = 1;   // default below 512 meshes per launch: the per-slice kernel (MESHTOK_GATHER_GROUP=1 applies the cost model everywhere)
+    } else {
+      double best = 1e30;
+      for (int g = 2; g <= nslices; ++g) {
+        const long long ctas = (long long)B * ceil_div(nslices, g);
+        const double cost = (double)((ctas + 147) / 148) * (g + 0.5);
+        if (cost < best - 1e-9) { best = cost; group = g; }
+      }
+    }
     const size_t smem2 = align_up(2 * (size_t)(F + 1) * 32 * sizeof(float) + (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short), 16);
     if (group >= 2 && smem2 <= 226 * 1024) {
       MT_ENSURE_SMEM((gather_mean_smem_group_kernel<32, 1024>), 226 * 1024);
       const int ngroups = ceil_div(nslices, group);
       MT_LAUNCH_PDL((gather_mean_smem_group_kernel<32, 1024>), B * ngroups, 1024, smem2, stream, x, d, indptr, src, edge_capacity, agg,
-                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, group);
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, group, trace);
       return MESHTOK_OK;
     }
   }
@@ -412,10 +636,10 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     MT_ENSURE_SMEM((gather_mean_smem_kernel<16, 256, 3>), 220 * 1024);
     if (S == 32) {
       MT_LAUNCH_PDL((gather_mean_smem_kernel<32, 512, 2>), B * (d / S), 512, smem, stream, x, d, indptr, src, edge_capacity, agg,
-                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, trace);
     } else {
       MT_LAUNCH_PDL((gather_mean_smem_kernel<16, 256, 3>), B * (d / S), 256, smem, stream, x, d, indptr, src, edge_capacity, agg,
-                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap);
+                    static_cast<uint8_t*>(agg_image), face_off, F, edges_cap, trace);
     }
     return MESHTOK_OK;
   }

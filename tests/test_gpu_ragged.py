@@ -181,18 +181,19 @@ torch.save(m.tokenize(v.cuda(), f.cuda()).cpu(), sys.argv[1])
 
 
 def test_large_batch_aggregation_kernel_gives_the_same_tokens(tmp_path):
-    """gather_mean_smem_group_kernel (one CTA per mesh and group of slices, double-buffered slices; the default from 512 meshes per launch)
-    forced on with MESHTOK_GATHER_GROUP=1 on a 320-mesh ragged batch (64-wide layers: groups of 2 slices) against MESHTOK_GATHER_GROUP=0:
-    same neighbour order, same rounding, so the tokens must be identical.  The switch is read once per process, hence subprocesses."""
+    """The aggregation kernel's work split - one CTA per (mesh, slice) or per (mesh, group of slices) with double-buffered slices (what
+    large launches take) - and the round-1 kernels (MESHTOK_GATHER_WIDE=0, four threads per face) on a 320-mesh ragged batch: same
+    neighbour order, same rounding, so the tokens must be identical.  The switches are read once per process, hence subprocesses."""
     import os, subprocess, sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = tmp_path / "run.py"
     script.write_text(_GROUP_SCRIPT.format(root=root, tests=os.path.join(root, "tests")))
     outs = {}
-    for knob in ("0", "1"):
-        path = tmp_path / f"group{knob}.pt"
-        r = subprocess.run([sys.executable, str(script), str(path)], env=dict(os.environ, MESHTOK_GATHER_GROUP=knob), capture_output=True, text=True,
-                           timeout=600)
+    for name, env in (("one slice", dict(MESHTOK_GATHER_WIDE_GROUP="1")), ("groups of 2", dict(MESHTOK_GATHER_WIDE_GROUP="2")), ("default", {}),
+                      ("round 1 per slice", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="0")), ("round 1 groups", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="1"))):
+        path = tmp_path / f"{name.replace(' ', '_')}.pt"
+        r = subprocess.run([sys.executable, str(script), str(path)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
-        outs[knob] = torch.load(path)
-    assert outs["0"].shape == outs["1"].shape and torch.equal(outs["0"], outs["1"])
+        outs[name] = torch.load(path)
+    for name, codes in outs.items():
+        assert codes.shape == outs["default"].shape and torch.equal(codes, outs["default"]), name
