@@ -52,7 +52,14 @@ def _headers():
     return hs
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """experiments: a SECOND library, lib/libmeshtok_exp.so, compiled with -DMESHTOK_EXPERIMENTS - the timing experiments that skip work
+    (and so produce wrong results) exist only there; load it with MESHTOK_LIBRARY=.../libmeshtok_exp.so.  The product build has none."""
+    global OBJ_DIR, LIB_PATH, COMMON_FLAGS
+    if experiments:
+        OBJ_DIR = os.path.join(HERE, "lib", "obj_exp")
+        LIB_PATH = os.path.join(HERE, "lib", "libmeshtok_exp.so")
+        COMMON_FLAGS = COMMON_FLAGS + ["-DMESHTOK_EXPERIMENTS"]
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     hdr_digest = _digest(_headers())
@@ -98,4 +105,4 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

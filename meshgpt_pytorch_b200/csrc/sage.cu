@@ -9,7 +9,10 @@
 // (default; MEASURED against the other with scripts/gpu_gather_ab.sh: 128 vs 137 us at C2, 1.66 vs 2.09 ms at 1 024
 // meshes per launch) and one warp per face row reading neighbour rows from L2 (meshes too large for a slice,
 // batches too small to fill the SMs).
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -18,6 +21,29 @@
 namespace meshtok {
 
 namespace {
+
+// Tensor map of a row-major fp32 matrix (rows x cols) for boxes of (box_rows x 32 columns): what the aggregation kernel's TMA loads walk.
+// cuTensorMapEncodeTiled is a driver entry point; it is fetched through the runtime (no link against libcuda).  false: not available.
+bool make_tmap_rows_f32(const float* base, int cols, long long rows, int box_rows, CUtensorMap* out) {
+  static PFN_cuTensorMapEncodeTiled encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+    else
+      (void)cudaGetLastError();
+  }
+  if (encode == nullptr || rows <= 0) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // sum / cnt for a small positive integer-valued cnt, as sum * rc with rc = RN(1 / cnt): exact for cnt = 1, 2, 4, 8 (a manifold triangle
 // mesh: three neighbours + the self loop), within one rounding of the quotient otherwise - three orders of magnitude below the split-bf16
@@ -342,12 +368,22 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
                                                                            const int* __restrict__ src, long long cap, float* __restrict__ agg,
                                                                            uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
                                                                            const int* __restrict__ edge_off, int rows_cap, int edges_cap, int group,
-                                                                           int nbuf, long long* __restrict__ trace) {
-  extern __shared__ float4 sx[];
+                                                                           int nbuf, long long* __restrict__ trace, int exp,
+                                                                           const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes) {
+  // [nbuf][buf_rows + 1][8] float4 x slices (row buf_rows stays zero: what an invalid source id points at) | [rows_cap + 1] local row
+  // pointers | [edges_cap] source row * 8 (u16) | [2] mbarriers.  box_rows > 0: the slices arrive by TMA (n_boxes boxes of box_rows x 32
+  // columns, one elected thread, completion on an mbarrier); box_rows == 0: by 16-byte cp.async copies of all threads.
+  extern __shared__ __align__(128) float4 sx[];
   constexpr int S = 32, s4 = S >> 2;
-  const int buf_stride = (rows_cap + 1) * s4;   // float4 per buffer
+#ifndef MESHTOK_EXPERIMENTS
+  exp = 0;   // (timing experiments that skip work - and produce wrong rows - exist only in the -DMESHTOK_EXPERIMENTS build)
+#endif
+  const bool tma = box_rows > 0;
+  const int buf_rows = tma ? box_rows * n_boxes : rows_cap;
+  const int buf_stride = (buf_rows + 1) * s4 + ((buf_rows + 1) & 1) * s4;   // float4 per buffer, a multiple of 256 bytes: every box lands 128-byte aligned
   int* sptr = reinterpret_cast<int*>(sx + (size_t)nbuf * buf_stride);
   unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
+  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ssrc + edges_cap + 3) & ~(uintptr_t)7);
   pdl_wait();
   GM_STAMP(0, gtimer()); GM_STAMP(1, clock64()); GM_STAMP(7, smid());
   const int nslices = d / S;
@@ -361,7 +397,21 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   const int tid = threadIdx.x;
   const int c = tid % s4;
   const uint32_t sx_addr = tc::smem_u32(sx);
-  auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf, one commit group
+  if (tma && tid == 0) {
+    for (int k = 0; k < nbuf; ++k) tc::mbar_init(&full[k], 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async_smem();
+  }
+  if (tma) __syncthreads();
+  auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf
+    if (tma) {
+      if (tid == 0) {   // rows beyond the mesh (the next mesh's, or zeros beyond the tensor) land in the buffer too and are never referenced
+        tc::mbar_arrive_expect_tx(&full[buf], (uint32_t)n_boxes * (uint32_t)box_rows * 128u);
+        for (int i = 0; i < n_boxes; ++i)
+          tc::tma_load_2d(sx + (size_t)buf * buf_stride + (size_t)i * box_rows * s4, &tmap, slice * S, r0 + i * box_rows, &full[buf]);
+      }
+      return;
+    }
     const float* xs = x + (size_t)r0 * d + slice * S;
     const uint32_t base = sx_addr + (uint32_t)buf * (uint32_t)buf_stride * 16u;
     for (int i = tid; i < n_b * s4; i += NTHR) {
@@ -371,11 +421,12 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
   issue(slice0, 0);
-  GM_STAMP(2, clock64());
+  GM_STAMP(2, 0);
+  const int zero_row = tma ? buf_rows : n_b;
   if (tid < s4)
-    for (int k = 0; k < nbuf; ++k) sx[(size_t)k * buf_stride + n_b * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
+    for (int k = 0; k < nbuf; ++k) sx[(size_t)k * buf_stride + zero_row * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
   const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
-  const bool fast = n_e <= edges_cap && e1_true <= cap && (rows_cap + 1) * s4 <= 65536;
+  const bool fast = n_e <= edges_cap && e1_true <= cap && (buf_rows + 1) * s4 <= 65536;
   for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldg(indptr + r0 + i) - e0;
   if (fast) {
     for (int base = tid; base < n_e; base += NTHR * 4) {
@@ -386,7 +437,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
       for (int j = 0; j < 4; ++j)
         if (base + j * NTHR < n_e) {
           const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
-          ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4);
+          ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4);
         }
     }
   }
@@ -394,14 +445,18 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
   for (int slice = slice0; slice < slice1; ++slice) {
     const int buf = nbuf == 2 ? ((slice - slice0) & 1) : 0;
-    if (nbuf == 2 && slice + 1 < slice1) {
-      issue(slice + 1, buf ^ 1);   // (its last readers passed the barrier that ends the previous iteration)
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    if (nbuf == 2 && slice + 1 < slice1) issue(slice + 1, buf ^ 1);   // (its last readers passed the barrier that ends the previous iteration)
+    const long long t_wait0 = trace ? clock64() : 0;
+    if (tma) {
+      __syncthreads();   // the CSR and the zero rows (first slice)
+      tc::mbar_wait(&full[buf], (uint32_t)(((slice - slice0) >> (nbuf == 2 ? 1 : 0)) & 1));
     } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      if (nbuf == 2 && slice + 1 < slice1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+      else asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
     }
-    __syncthreads();
     if (slice == slice0) GM_STAMP(4, clock64());
+    if (trace != nullptr && tid == 0 && blockIdx.x < 1024 && slice > slice0) trace[blockIdx.x * 8 + 2] += clock64() - t_wait0;   // waiting for slices 1.. (thread 0)
     const float4* sxb = sx + (size_t)buf * buf_stride;
     for (int item = tid; item < 2 * n_b; item += NTHR) {
       const int lrow = item >> 1, h = item & 1;
@@ -420,8 +475,9 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
         if (fast) off = ssrc[q];
         else {   // a mesh with more edges than the staging area holds, or a list cut by the edge capacity
           const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
-          off = (int)(nb < (unsigned)n_b ? nb : (unsigned)n_b) * s4;
+          off = (int)(nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4;
         }
+        if (exp == 2) { a0.x += __int_as_float(off); continue; }   // experiment: no neighbour row reads
         const float4 v0 = p0a[off], v1 = p0b[off], v2 = p1a[off], v3 = p1b[off];
         a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
         a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
@@ -430,6 +486,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
       }
       const float rc = __frcp_rn(fmaxf((float)(e_true - s), 1.f));
       const int row = r0 + lrow;
+      if (exp == 1 && a0.x + a1.y + a2.z + a3.w != 123.456f) continue;   // experiment: no epilogue, no stores
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
         const float4 fa = k == 0 ? a0 : a2, fb = k == 0 ? a1 : a3;   // first-read / second-read chunk of the pair
@@ -450,6 +507,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
           tc::split2(o1.z, o1.w, hi.w, lo.w);
           const uint32_t img_col = (uint32_t)(col >> 5) * tc::IMG_BLOCK + (uint32_t)((col & 31) >> 3) * 128u;
           uint8_t* pimg = agg_image + (size_t)(row >> 7) * img_tile + (uint32_t)((row & 127) >> 3) * 512u + (uint32_t)(row & 7) * 16u + img_col;
+          if (exp == 3 && (hi.x ^ lo.y) != 0x12345678u) continue;   // experiment: the whole epilogue but no stores
           *reinterpret_cast<uint4*>(pimg) = hi;
           *reinterpret_cast<uint4*>(pimg + tc::IMG_PART) = lo;
         }
@@ -568,38 +626,55 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
   if (use_wide < 0) { const char* e = getenv("MESHTOK_GATHER_WIDE"); use_wide = (e && atoi(e) == 0) ? 0 : 1; }
   if (use_wide && use_smem && face_off != nullptr && d % 32 == 0) {
     const int nslices = d / 32;
-    const size_t per_buf = (size_t)(F + 1) * 32 * sizeof(float);
-    const size_t csr = (size_t)(F + 1) * sizeof(int) + (size_t)edges_cap * sizeof(unsigned short);
-    // slices per CTA: a CTA's time ~ (its slices + 1.5 slices' worth of staging the CSR and the first, un-overlapped x slice);
-    // the launch takes ceil(CTAs / (148 * CTAs per SM)) rounds of that.  One slice per CTA: 512 threads, two CTAs per SM.
+    // x slices by TMA (cp.async.bulk.tensor.2d over a tensor map of x): boxes of box_rows x 32 columns, at most 256 rows each
+    static int use_tma = -1;
+    if (use_tma < 0) { const char* e = getenv("MESHTOK_GATHER_TMA"); use_tma = (e && atoi(e) == 0) ? 0 : 1; }
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    int n_boxes = ceil_div(F, 256), box_rows = ceil_div(F, n_boxes);
+    const bool tma = use_tma && make_tmap_rows_f32(x, d, (long long)max_rows, box_rows, &tmap);
+    if (!tma) { box_rows = 0; n_boxes = 0; }
+    const int buf_rows = tma ? box_rows * n_boxes : F;
+    const size_t per_buf = (size_t)((buf_rows + 1) + ((buf_rows + 1) & 1)) * 32 * sizeof(float);
+    const size_t csr = (size_t)(F + 1) * sizeof(int) + (size_t)(edges_cap + 4) * sizeof(unsigned short) + 2 * sizeof(uint64_t) + 8;
+    // Slices per CTA.  MEASURED (B200, scripts/gpu_ab.sh; 64 and 1 024 meshes per launch): one slice per CTA with 512 threads and two
+    // CTAs per SM - each slice arriving by TMA while the other CTA computes - is as fast as or faster than every grouping with
+    // double-buffered slices (C2: 126.7 us over the five layers against 132 - 202 us for groups of 2 / 4 / 8; 1 024 meshes: 1.50 ms
+    // against 1.58 - 1.73 ms), so groups are only formed when a single-slice CTA does not fit twice per SM (meshes above ~800 faces).
     static int forced_group = -2;
     if (forced_group == -2) { const char* e = getenv("MESHTOK_GATHER_WIDE_GROUP"); forced_group = e ? atoi(e) : -1; }
     int group = 1;
     double best = 1e30;
     for (int g = 1; g <= nslices; ++g) {
       const bool two_bufs = g >= 2;
-      const size_t smem_g = align_up((two_bufs ? 2 : 1) * per_buf + csr, 16);
+      const size_t smem_g = align_up((two_bufs ? 2 : 1) * per_buf + csr, 128);
       if (smem_g > 226 * 1024) continue;
       const int per_sm = (g == 1 && 2 * (smem_g + 1024) <= 226 * 1024) ? 2 : 1;
+      if (g == 1 && per_sm == 2) { best = 0.0; group = 1; break; }
       const long long ctas = (long long)B * ceil_div(nslices, g);
       const double rounds = (double)((ctas + 148 * per_sm - 1) / (148 * per_sm));
-      const double cost = rounds * (g + 1.5) * (per_sm == 2 ? 1.0 : 0.55);   // (a lone CTA with 1 024 threads runs a slice about twice as fast as one of two 512-thread CTAs)
+      const double cost = rounds * (g + 1.5);
       if (cost < best - 1e-9) { best = cost; group = g; }
     }
-    if (forced_group >= 1) group = min(forced_group, nslices);
+    if (forced_group >= 1 && best < 1e30) {
+      group = min(forced_group, nslices);
+      if (align_up((group >= 2 ? 2 : 1) * per_buf + csr, 128) > 226 * 1024) group = 1;
+    }
+    static int gexp = -1;
+    if (gexp < 0) { const char* e = getenv("MESHTOK_GATHER_EXP"); gexp = e ? atoi(e) : 0; }
     if (best < 1e30) {
       const int nbuf = group >= 2 ? 2 : 1;
-      const size_t smem_w = align_up(nbuf * per_buf + csr, 16);
+      const size_t smem_w = align_up(nbuf * per_buf + csr, 128);
       const int ngroups = ceil_div(nslices, group);
       const int* edge_off = face_off + 2 * (size_t)(B + 1);
       if (group == 1) {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 113 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes);
       } else {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<1024, 1>), B * ngroups, 1024, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes);
       }
       return MESHTOK_OK;
     }

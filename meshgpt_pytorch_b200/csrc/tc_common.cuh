@@ -77,6 +77,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS UTMALDG): box (c0 .., r0 ..) of the tensor described by `tmap` -> dst_smem (row major
+// box, 128-byte aligned), completion counted in bytes on `bar`.  Elements outside the tensor arrive as zeros and still count.
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const void* tmap, int c0, int r0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(r0), "r"(smem_u32(bar))
+               : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

@@ -24,7 +24,7 @@ t1 = max(r[6] for r in rows)
 print(f"layer {os.environ.get('MESHTOK_GATHER_TRACE')}: {len(rows)} CTAs, kernel span {(t1 - t0) / 1e3:.2f} us (globaltimer)")
 import statistics as st
 def col(fn): return [fn(r) for r in rows]
-for name, fn in (("start offset ns", lambda r: r[0] - t0), ("issue x copies", lambda r: r[2] - r[1]), ("stage CSR", lambda r: r[3] - r[2]), ("wait copies", lambda r: r[4] - r[3]),
+for name, fn in (("start offset ns", lambda r: r[0] - t0), ("waits slices 1..", lambda r: r[2]), ("prologue + CSR", lambda r: r[3] - r[1]), ("wait copies", lambda r: r[4] - r[3]),
                  ("row loop", lambda r: r[5] - r[4]), ("total cycles", lambda r: r[5] - r[1]), ("total ns", lambda r: r[6] - r[0])):
     c = col(fn)
     print(f"  {name:16s} min {min(c):8d}  median {int(st.median(c)):8d}  max {max(c):8d}")
