@@ -256,7 +256,38 @@ int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E
                           meshtok_taps* taps);
 
 /* ------------------------------------------------------------------------------------------
- * Stage entry points used by the parity tests with oracle-injected inputs.
+ * Per-stage entry points: the stages of meshtok_tokenize one by one, so that a single stage of the reference can be
+ * swapped.  All of them take the SAME (model, args, workspace) as meshtok_tokenize - same workspace size and layout, see
+ * meshtok_tokenize_taps for where the maps and counts live - and exchange fp32 ROWS: `*_rows` tensors are packed face rows
+ * (n_faces valid faces of the batch back to back, in (mesh, face) order; capacity B*F rows) or packed vertex rows (n_vrows
+ * referenced (mesh, vertex) pairs; capacity B*V rows).  Order of use: topology first (it fills the maps every other stage reads),
+ * then any of the others.  args fields used: faces, vertices, face_edges/E, B, F, V, pad_id, edge_capacity, the ragged offsets,
+ * gemm_simt, face_coords_out (features stage), codes_out / histogram (code gather).
+ *   meshtok_stage_topology              derive_face_edges_from_faces (data.py:297-340) or the user's edge list (meshgpt_pytorch.py:752-754)
+ *                                       -> face CSR by target + packed-row maps + vertex incidence CSR ("face_adjacency_csr" /
+ *                                       "csr_from_edge_list")
+ *   meshtok_stage_face_features_embed   meshgpt_pytorch.py:711-741 -> x0_rows (n_faces, dim_codebook)
+ *   meshtok_stage_sage_project          SAGEConv.lin + ReLU of layer `layer` (call sites :764, :769) -> xp_rows (n_faces, dim_in)
+ *   meshtok_stage_sage_aggregate_linear mean aggregation + lin_l/lin_r + F.normalize (+ SiLU + LayerNorm after layer 0, :766)
+ *                                       -> out_rows (n_faces, dim_out)
+ *   meshtok_stage_project_scatter_mean  project_dim_codebook + scatter_mean (:803-824) -> averaged_rows (n_vrows, dim_codebook);
+ *                                       quantise them with meshtok_lfq_codes / meshtok_rvq_codes
+ *   meshtok_stage_gather_codes          :856-866, :1018: vertex codes (n_vrows, Q) int32 -> args.codes_out (+ histogram)
+ * ------------------------------------------------------------------------------------------ */
+int meshtok_stage_topology(const meshtok_model* model, const meshtok_tokenize_args* args, void* workspace, size_t workspace_bytes, meshtok_stream_t stream);
+int meshtok_stage_face_features_embed(const meshtok_model* model, const meshtok_tokenize_args* args, float* x0_rows, void* workspace,
+                                      size_t workspace_bytes, meshtok_stream_t stream);
+int meshtok_stage_sage_project(const meshtok_model* model, const meshtok_tokenize_args* args, int layer, const float* x_rows, float* xp_rows,
+                               void* workspace, size_t workspace_bytes, meshtok_stream_t stream);
+int meshtok_stage_sage_aggregate_linear(const meshtok_model* model, const meshtok_tokenize_args* args, int layer, const float* x_rows,
+                                        const float* xp_rows, float* out_rows, void* workspace, size_t workspace_bytes, meshtok_stream_t stream);
+int meshtok_stage_project_scatter_mean(const meshtok_model* model, const meshtok_tokenize_args* args, const float* enc_rows, float* averaged_rows,
+                                       void* workspace, size_t workspace_bytes, meshtok_stream_t stream);
+int meshtok_stage_gather_codes(const meshtok_model* model, const meshtok_tokenize_args* args, const int32_t* vertex_codes, void* workspace,
+                               size_t workspace_bytes, meshtok_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Quantizer entry points on given rows (also used by the parity tests with oracle-injected inputs).
  * ------------------------------------------------------------------------------------------ */
 
 /* K8b residual LFQ on given rows.  Replaces vector_quantize_pytorch.ResidualLFQ.forward (eval),

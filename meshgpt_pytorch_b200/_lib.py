@@ -129,6 +129,13 @@ SIGNATURES = {
     "meshtok_pipeline_drain": (C.c_int, [C.c_void_p, C.POINTER(PipelineResult), C.POINTER(C.c_int)]),
     "meshtok_pipeline_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
     "meshtok_pipeline_destroy": (C.c_int, [C.c_void_p]),
+    "meshtok_stage_topology": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "meshtok_stage_face_features_embed": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "meshtok_stage_sage_project": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "meshtok_stage_sage_aggregate_linear": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                      C.c_size_t, C.c_void_p]),
+    "meshtok_stage_project_scatter_mean": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "meshtok_stage_gather_codes": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "meshtok_tokenize_taps": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.POINTER(Taps)]),
     "meshtok_lfq_codes": (C.c_int, [C.POINTER(Model), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_rvq_workspace_bytes": (C.c_int, [C.POINTER(Model), C.c_int, C.POINTER(C.c_size_t)]),

@@ -672,6 +672,187 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   return MESHTOK_OK;
 }
 
+// ---- per-stage entry points: the stages of meshtok_tokenize one by one, on the SAME workspace layout, with fp32 rows as
+// the interchange format so that a reference maintainer can swap a single stage.  Every stage validates the arguments it uses, carves
+// the workspace exactly like meshtok_tokenize and launches the kernels the pipeline launches for that stage.
+namespace {
+struct StageCtx {
+  Workspace w;
+  int B, F, V, E, nvf, D, Q, max_rows, max_vrows;
+  bool ragged, simt;
+  cudaStream_t s;
+};
+int stage_begin(const meshtok_model* m, const meshtok_tokenize_args* a, void* workspace, size_t workspace_bytes, meshtok_stream_t stream, StageCtx* c) {
+  int rc = check_model(m);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a != nullptr && workspace != nullptr, "args / workspace is null");
+  c->B = a->B; c->F = a->F; c->V = a->V; c->nvf = m->nvf; c->D = m->dim_codebook; c->Q = m->num_quantizers;
+  c->E = a->face_edges ? a->E : 0;
+  c->ragged = a->face_offsets != nullptr || a->vertex_offsets != nullptr;
+  if (c->ragged)
+    MT_CHECK_ARG(a->face_offsets != nullptr && a->vertex_offsets != nullptr && a->total_faces >= 0 && a->total_faces <= (long long)c->B * c->F,
+                 "ragged input needs face_offsets and vertex_offsets (B + 1 int32 each) and 0 <= total_faces <= B * F");
+  rc = topo_check_shape(c->B, c->F, c->nvf, c->V);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a->edge_capacity > 0 && a->edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
+  rc = carve_all(m, c->B, c->F, c->V, c->E, a->edge_capacity, workspace, &c->w, nullptr);
+  if (rc != MESHTOK_OK) return rc;
+  if (c->w.total > workspace_bytes) {
+    set_error("workspace too small: need %zu bytes, got %zu", c->w.total, workspace_bytes);
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) {
+    set_error("workspace must be 256-byte aligned");
+    return MESHTOK_ERR_WORKSPACE;
+  }
+  c->max_rows = c->B * c->F;
+  c->max_vrows = c->B * c->V;
+  c->simt = a->gemm_simt != 0;
+  c->s = static_cast<cudaStream_t>(stream);
+  return MESHTOK_OK;
+}
+}  // namespace
+
+int meshtok_stage_topology(const meshtok_model* m, const meshtok_tokenize_args* a, void* workspace, size_t workspace_bytes, meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a->faces != nullptr, "faces is null");
+  MT_CHECK_ARG(a->face_edges == nullptr || a->E > 0, "face_edges given but E <= 0 (pass one all-pad edge for an empty list)");
+  Workspace& w = c.w;
+  const int B = c.B;
+  MT_CHECK_CUDA(cudaMemsetAsync(w.status, 0, (size_t)(reinterpret_cast<char*>(w.mesh_counts) - reinterpret_cast<char*>(w.status)) +
+                                                 sizeof(int) * 2 * ((size_t)B * 8 + 4), c.s));
+  TopoParams p;
+  memset(&p, 0, sizeof(p));
+  p.faces = a->faces; p.B = B; p.F = c.F; p.nvf = c.nvf; p.V = c.V; p.pad_id = a->pad_id;
+  p.in_face_off = a->face_offsets; p.in_vert_off = a->vertex_offsets;
+  p.threshold = 2; p.include_self = 1; p.do_adjacency = a->face_edges ? 0 : 1;
+  p.status = w.status; p.mesh_counts = w.mesh_counts; p.deg_out = w.deg_out; p.deg_in = w.deg_in;
+  p.mesh_prefix = w.mesh_counts + 4 * (size_t)B; p.ticket = w.mesh_counts + 8 * (size_t)B; p.counts = w.counts;
+  p.face_off = w.offs; p.vert_off = w.offs + (B + 1); p.edge_off = w.offs + 2 * (size_t)(B + 1);
+  p.face_row = w.face_row; p.row_face = w.row_face; p.vert_row = w.vert_row; p.vptr = w.vptr; p.vinc = w.vinc;
+  p.indptr = w.indptr; p.src = w.src; p.edge_capacity = a->edge_capacity;
+  if ((rc = topo_maps(p, c.s)) != MESHTOK_OK) return rc;
+  if (a->face_edges)
+    return topo_user_edges(a->face_edges, B, c.E, c.ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount,
+                           w.cursor, w.etmp, w.indptr, w.src, a->edge_capacity, c.max_rows, w.status, c.s);
+  TopoParams pe = p;
+  pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
+  pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
+  pe.ticket = pe.mesh_counts + 8 * (size_t)B;
+  return topo_edges(pe, c.s);
+}
+
+int meshtok_stage_face_features_embed(const meshtok_model* m, const meshtok_tokenize_args* a, float* x0_rows, void* workspace, size_t workspace_bytes,
+                                      meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a->faces != nullptr && a->vertices != nullptr && x0_rows != nullptr, "faces / vertices / x0_rows is null");
+  Workspace& w = c.w;
+  FeatParams fp;
+  memset(&fp, 0, sizeof(fp));
+  fp.vertices = a->vertices; fp.faces = a->faces; fp.row_face = w.row_face; fp.counts = w.counts;
+  fp.in_face_off = a->face_offsets; fp.in_vert_off = a->vertex_offsets;
+  fp.pad_id = a->pad_id; fp.total_faces = a->total_faces;
+  fp.B = c.B; fp.F = c.F; fp.V = c.V; fp.nvf = c.nvf; fp.D = c.D;
+  fp.coor_lo = m->coor_lo;
+  fp.coor_den = (float)((double)m->coor_hi - (double)m->coor_lo);
+  fp.angle_den = (float)3.141592653589793;
+  fp.area_den = (float)(((double)m->coor_hi - (double)m->coor_lo) * ((double)m->coor_hi - (double)m->coor_lo));
+  fp.clip_lo = (float)(-1.0 + 1e-5); fp.clip_hi = (float)(1.0 - 1e-5);
+  fp.n_coor = m->num_discrete_coors; fp.n_angle = m->num_discrete_angle; fp.n_area = m->num_discrete_area; fp.n_normal = m->num_discrete_normals;
+  fp.tables = m->folded_tables; fp.bias = m->project_in_bias;
+  {
+    int off = 0, s_i = 0;
+    for (int k = 0; k < c.nvf * 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_coors; }
+    for (int k = 0; k < c.nvf; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_angle; }
+    fp.slot_off[s_i++] = off; off += m->num_discrete_area;
+    for (int k = 0; k < 3; ++k) { fp.slot_off[s_i++] = off; off += m->num_discrete_normals; }
+  }
+  fp.x0 = x0_rows; fp.x0_image = nullptr; fp.face_coords_out = a->face_coords_out; fp.bins_out = w.bins;
+  if (a->face_coords_out)
+    MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(c.ragged ? a->total_faces : c.max_rows) * c.nvf * 3, c.s));
+  if ((rc = launch_face_bins(fp, c.ragged ? a->total_faces : (long long)c.max_rows, c.s)) != MESHTOK_OK) return rc;
+  return launch_face_sum(fp, c.max_rows, c.s);
+}
+
+// xp = relu(lin(x)) of SAGE layer `layer`: the `project=True` half of SAGEConv
+int meshtok_stage_sage_project(const meshtok_model* m, const meshtok_tokenize_args* a, int layer, const float* x_rows, float* xp_rows, void* workspace,
+                               size_t workspace_bytes, meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(layer >= 0 && layer < m->num_sage_layers && x_rows && xp_rows, "bad layer / x_rows / xp_rows is null");
+  const meshtok_sage_layer& ly = m->sage[layer];
+  Workspace& w = c.w;
+  const bool simt = c.simt || ly.lin_w_img == nullptr || w.img_x[0] == nullptr;
+  if (!simt && (rc = launch_rows_to_image(x_rows, ly.dim_in, &w.counts->n_faces, c.max_rows, w.img_x[0], c.s)) != MESHTOK_OK) return rc;
+  return linear(simt, x_rows, w.img_x[0], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, xp_rows, ly.dim_in, &w.counts->n_faces,
+                c.max_rows, true, c.s);
+}
+
+// out = normalize(lin_l(mean over in-edges of xp) + lin_r(x)) [layer 0: -> SiLU -> LayerNorm]: the rest of SAGEConv
+int meshtok_stage_sage_aggregate_linear(const meshtok_model* m, const meshtok_tokenize_args* a, int layer, const float* x_rows, const float* xp_rows,
+                                        float* out_rows, void* workspace, size_t workspace_bytes, meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(layer >= 0 && layer < m->num_sage_layers && x_rows && xp_rows && out_rows, "bad layer / row pointers are null");
+  const meshtok_sage_layer& ly = m->sage[layer];
+  Workspace& w = c.w;
+  const bool first = layer == 0;
+  const bool simt = c.simt || ly.cat_w_img == nullptr || w.img_x[0] == nullptr;
+  const int* n_dev = &w.counts->n_faces;
+  if ((rc = launch_gather_mean(xp_rows, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts,
+                               c.max_rows, w.offs, c.B, c.F, c.s)) != MESHTOK_OK) return rc;
+  if (!simt) {
+    if ((rc = launch_rows_to_image(x_rows, ly.dim_in, n_dev, c.max_rows, w.img_x[0], c.s)) != MESHTOK_OK) return rc;
+    const int mode = first ? 2 : 1;
+    if (linear_tc_fused_norm_ok(ly.dim_out, mode) == MESHTOK_OK) {
+      LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, nullptr, nullptr, nullptr, 0};
+      return linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[0], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, out_rows, ly.dim_out, n_dev,
+                    c.max_rows, false, c.s, &epi);
+    }
+  }
+  if ((rc = linear(simt, w.agg, w.img_agg, ly.dim_in, x_rows, w.img_x[0], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b, out_rows, ly.dim_out, n_dev,
+                   c.max_rows, false, c.s)) != MESHTOK_OK) return rc;
+  return launch_row_norm(out_rows, ly.dim_out, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, nullptr, w.counts, c.max_rows, c.s);
+}
+
+// averaged[vertex row] = scatter_mean of project_dim_codebook(enc) over the faces of every referenced vertex (quantize()'s first half)
+int meshtok_stage_project_scatter_mean(const meshtok_model* m, const meshtok_tokenize_args* a, const float* enc_rows, float* averaged_rows, void* workspace,
+                                       size_t workspace_bytes, meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(enc_rows && averaged_rows, "enc_rows / averaged_rows is null");
+  Workspace& w = c.w;
+  const int ed = enc_dim(m);
+  const bool simt = c.simt || m->pdc_w_img == nullptr || w.img_x[0] == nullptr;
+  if (!simt && (rc = launch_rows_to_image(enc_rows, ed, &w.counts->n_faces, c.max_rows, w.img_x[0], c.s)) != MESHTOK_OK) return rc;
+  if ((rc = linear(simt, enc_rows, w.img_x[0], ed, nullptr, nullptr, 0, m->pdc_w, m->pdc_w_img, m->pdc_b, w.y, c.nvf * c.D, &w.counts->n_faces, c.max_rows,
+                   false, c.s)) != MESHTOK_OK) return rc;
+  return launch_scatter_mean(w.y, c.D, w.vptr, w.vinc, averaged_rows, w.counts, c.max_vrows, nullptr, c.s);
+}
+
+// codes_out[token] = vertex_codes[vertex row of the token's vertex] (pad_id on padded faces) (+ histogram): quantize()'s last step
+int meshtok_stage_gather_codes(const meshtok_model* m, const meshtok_tokenize_args* a, const int32_t* vertex_codes, void* workspace, size_t workspace_bytes,
+                               meshtok_stream_t stream) {
+  StageCtx c;
+  int rc = stage_begin(m, a, workspace, workspace_bytes, stream, &c);
+  if (rc != MESHTOK_OK) return rc;
+  MT_CHECK_ARG(a->faces && a->codes_out && vertex_codes, "faces / codes_out / vertex_codes is null");
+  Workspace& w = c.w;
+  GatherHist gh{w.vptr, w.counts, c.max_vrows, reinterpret_cast<unsigned long long*>(a->histogram)};
+  if (c.ragged)
+    return launch_gather_codes_ragged(a->faces, a->face_offsets, w.face_row, w.vert_row, vertex_codes, a->total_faces, c.B, c.F, c.nvf, c.V, c.Q, a->pad_id,
+                                      a->codes_out, a->histogram ? &gh : nullptr, m->codebook_size, c.s);
+  return launch_gather_codes(a->faces, w.face_row, w.vert_row, vertex_codes, c.B, c.F, c.nvf, c.V, c.Q, a->pad_id, a->codes_out,
+                             a->histogram ? &gh : nullptr, m->codebook_size, c.s);
+}
+
 int meshtok_lfq_codes(const meshtok_model* m, const float* rows, int R, int32_t* codes, meshtok_stream_t stream) {
   int rc = check_model(m);
   if (rc != MESHTOK_OK) return rc;
