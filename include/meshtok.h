@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MESHTOK_ABI_VERSION 1
+#define MESHTOK_ABI_VERSION 2
 
 typedef void* meshtok_stream_t; /* cudaStream_t */
 
@@ -187,16 +187,23 @@ typedef struct meshtok_tokenize_args {
    *   contains pad_id still yields pad_id tokens); face_coords_out (total_faces, nvf * 3).
    *   face_edges (optional) (total_edges, 2) with mesh-local face indices, mesh b owns rows edge_offsets[b] .. edge_offsets[b + 1]
    *   (E > 0 is then only the "edges are given" flag; edge_capacity >= total_edges).
-   * Not available in this layout (MESHTOK_ERR_UNSUPPORTED): encoded_in, encoded_out, quantized_out. */
+   *   encoded_in / encoded_out (total_faces, dims[-1]) and quantized_out (total_faces, nvf * dim_codebook): one row per flat face
+   *   (zeros / the pad row on faces that contain pad_id); with encoded_in only the offsets, faces and V are used (vertices may be NULL). */
   const int32_t* face_offsets;
   const int32_t* vertex_offsets;
   int64_t total_faces;
   const int32_t* edge_offsets;
   int64_t total_edges;
+  int64_t total_vertices;   /* ragged input: rows the vertices buffer holds (>= vertex_offsets[B]); 0 = unknown (B * V vertex rows are reserved) */
 } meshtok_tokenize_args;
 
 int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E,
                                      int64_t edge_capacity, size_t* bytes);
+/* The same for the ragged layout: the activation buffers are sized by total_faces face rows and total_vertices vertex rows (the values
+ * the call will carry in args.total_faces / args.total_vertices) instead of B * F and B * V - the workspace grows with the SUM of the
+ * mesh sizes, not with B x the largest mesh (C4: 116 k faces in 204 k padded slots).  0 = B * F / B * V. */
+int meshtok_tokenize_workspace_bytes_ragged(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                                            int64_t total_faces, int64_t total_vertices, size_t* bytes);
 
 int meshtok_tokenize(const meshtok_model* model, const meshtok_tokenize_args* args, void* workspace,
                      size_t workspace_bytes, meshtok_stream_t stream);
@@ -254,6 +261,8 @@ typedef struct meshtok_taps {
 
 int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
                           meshtok_taps* taps);
+int meshtok_tokenize_taps_ragged(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity, int64_t total_faces,
+                                 int64_t total_vertices, meshtok_taps* taps);
 
 /* ------------------------------------------------------------------------------------------
  * Per-stage entry points: the stages of meshtok_tokenize one by one, so that a single stage of the reference can be

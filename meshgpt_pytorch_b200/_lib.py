@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MESHTOK_LIBRARY") or os.path.join(HERE, "lib", "libmeshtok.so")   # override: A/B of two builds
 
 MAX_SAGE_LAYERS = 8
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 WS_STATUS_VERTEX_RANGE = 1
 WS_STATUS_EDGE_OVERFLOW = 2
@@ -52,7 +52,7 @@ class TokenizeArgs(C.Structure):
         ("quantized_out", C.c_void_p), ("histogram", C.c_void_p),
         ("stop_after_encode", C.c_int32), ("rvq_exact", C.c_int32), ("gemm_simt", C.c_int32), ("keep_taps", C.c_int32),
         ("face_offsets", C.c_void_p), ("vertex_offsets", C.c_void_p), ("total_faces", C.c_int64),
-        ("edge_offsets", C.c_void_p), ("total_edges", C.c_int64),
+        ("edge_offsets", C.c_void_p), ("total_edges", C.c_int64), ("total_vertices", C.c_int64),
     ]
 
 
@@ -122,6 +122,9 @@ SIGNATURES = {
                                           C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_tokenize_workspace_bytes": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                                    C.POINTER(C.c_size_t)]),
+    "meshtok_tokenize_workspace_bytes_ragged": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                                          C.POINTER(C.c_size_t)]),
+    "meshtok_tokenize_taps_ragged": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.POINTER(Taps)]),
     "meshtok_tokenize": (C.c_int, [C.POINTER(Model), C.POINTER(TokenizeArgs), C.c_void_p, C.c_size_t, C.c_void_p]),
     "meshtok_pipeline_create": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(PipelineSlot), C.c_int,
                                           C.POINTER(C.c_void_p)]),

@@ -286,13 +286,13 @@ class MeshAutoencoder(nn.Module):
         return self._prep
 
     # ---- the pipeline call ------------------------------------------------------------------------
-    def _workspace(self, prep, B, F, V, E, cap, tag=None) -> Tensor:
+    def _workspace(self, prep, B, F, V, E, cap, tag=None, total_faces=0, total_vertices=0) -> Tensor:
         """One grow-only buffer per tag (callers that run concurrently - two graphs in flight - use different tags and so keep
         apart).  Batches from a collate function change F and V nearly every step; the C side only needs workspace_bytes >= its
         carve total, so the buffer is reallocated only when a call needs more than it holds.  A captured graph pins the buffer it
         was captured on (GraphedTokenizer keeps a reference), so growing the tag's buffer later never invalidates a graph."""
-        nbytes = C.c_size_t()
-        check(lib.meshtok_tokenize_workspace_bytes(C.byref(prep["model"]), B, F, V, E, cap, C.byref(nbytes)))
+        nbytes = C.c_size_t()     # (total_faces / total_vertices: ragged layout - activation rows by the sum of the mesh sizes, not B x the largest)
+        check(lib.meshtok_tokenize_workspace_bytes_ragged(C.byref(prep["model"]), B, F, V, E, cap, int(total_faces), int(total_vertices), C.byref(nbytes)))
         ws = self._ws_cache.get(tag)
         if ws is None or ws.numel() < nbytes.value or ws.device != prep["device"]:
             ws = None
@@ -432,9 +432,9 @@ class MeshAutoencoder(nn.Module):
         """Views of the intermediate tensors of the last call (stage-wise parity tests).  The fp32 activations
         (x0, layer{i}) are only stored when the call ran with self.keep_taps = True."""
         prep = self._prepare()
-        B, F, V, E, cap = self.last_shape
+        B, F, V, E, cap, tot_f, tot_v = (tuple(self.last_shape) + (0, 0))[:7]
         t = Taps()
-        check(lib.meshtok_tokenize_taps(C.byref(prep["model"]), B, F, V, E, cap, C.byref(t)))
+        check(lib.meshtok_tokenize_taps_ragged(C.byref(prep["model"]), B, F, V, E, cap, tot_f, tot_v, C.byref(t)))
         ws = self.last_workspace
 
         def view(off, n, dtype):
@@ -528,13 +528,26 @@ class MeshAutoencoder(nn.Module):
         max_faces / max_vertices: upper bounds of the per-mesh counts; computed from the offsets when omitted (a device sync if the
         offsets live on the GPU).  The same kernels run as for the padded layout; only the three that touch the inputs and the output
         (topology_kernel, face_bins_kernel, gather_codes_ragged_kernel) address them through the offsets."""
+        r = self._ragged_args(vertices, faces, face_offsets, vertex_offsets, face_edges, edge_offsets, max_faces, max_vertices)
+        nvf, Q = self.num_vertices_per_face, self.num_quantizers
+        total, dev = r["total"], r["dev"]
+        codes = torch.empty((total * nvf, Q), dtype=torch.int64, device=dev)
+        coords = torch.empty((total, nvf * 3), dtype=torch.int64, device=dev) if return_face_coordinates else None
+        if r["B"] == 0 or total == 0:
+            return (codes, coords) if return_face_coordinates else codes
+        self._launch_ragged(r["vertices"], r["faces"], r["fo"], r["vo"], r["B"], r["F"], r["V"], total, codes, coords, histogram, r["face_edges"], r["eo"],
+                            r["n_edges"], check_status, "ragged")
+        return (codes, coords) if return_face_coordinates else codes
+
+    def _ragged_args(self, vertices, faces, face_offsets, vertex_offsets, face_edges=None, edge_offsets=None, max_faces=None, max_vertices=None):
+        """Checks and device-side form of a ragged batch (shared by tokenize_ragged / encode_ragged / quantize_ragged)."""
         prep = self._prepare()
         dev = prep["device"]
-        if not (faces.is_cuda and vertices.is_cuda):
+        if not faces.is_cuda or (vertices is not None and not vertices.is_cuda):
             raise RuntimeError("inputs must be CUDA tensors (no CPU path)")
-        nvf, Q = self.num_vertices_per_face, self.num_quantizers
+        nvf = self.num_vertices_per_face
         assert faces.ndim == 2 and faces.shape[1] == nvf, f"faces must be (sum nf, {nvf})"
-        assert vertices.ndim == 2 and vertices.shape[1] == 3, "vertices must be (sum nv, 3)"
+        assert vertices is None or (vertices.ndim == 2 and vertices.shape[1] == 3), "vertices must be (sum nv, 3)"
         if self.training:
             self.eval()
 
@@ -543,11 +556,11 @@ class MeshAutoencoder(nn.Module):
             assert o.ndim == 1 and o.numel() >= 1 and not o.is_floating_point(), f"{what} must be B + 1 integers"
             if not o.is_cuda:     # host-side offsets (the usual case: the loader knows the mesh sizes) are checked without a device sync
                 d = o[1:] - o[:-1]
-                assert int(o[0]) == 0 and int(o[-1]) == total and bool((d >= 0).all()), f"{what} must rise from 0 to {total}"
+                assert int(o[0]) == 0 and (total is None or int(o[-1]) == total) and bool((d >= 0).all()), f"{what} must rise from 0 to {total}"
                 return o.to(device=dev, dtype=torch.int32), (int(d.max()) if d.numel() else 0)
             return o.to(torch.int32).contiguous(), None
         fo, fmax = offsets(face_offsets, faces.shape[0], "face_offsets")
-        vo, vmax = offsets(vertex_offsets, vertices.shape[0], "vertex_offsets")
+        vo, vmax = offsets(vertex_offsets, None if vertices is None else vertices.shape[0], "vertex_offsets")
         assert fo.numel() == vo.numel(), "face_offsets and vertex_offsets must have B + 1 entries each"
         B = fo.numel() - 1
         eo, n_edges = None, 0
@@ -564,39 +577,64 @@ class MeshAutoencoder(nn.Module):
             max_faces = fmax if fmax is not None else (int((fo[1:] - fo[:-1]).max()) if B else 0)
         if max_vertices is None:
             max_vertices = vmax if vmax is not None else (int((vo[1:] - vo[:-1]).max()) if B else 0)
-        total = faces.shape[0]
-        codes = torch.empty((total * nvf, Q), dtype=torch.int64, device=dev)
-        coords = torch.empty((total, nvf * 3), dtype=torch.int64, device=dev) if return_face_coordinates else None
-        if B == 0 or total == 0:
-            return (codes, coords) if return_face_coordinates else codes
-        F, V = max(int(max_faces), 1), max(int(max_vertices), 1)
-        faces64 = faces.to(torch.int64).contiguous()
-        vertices = vertices.to(torch.float32).contiguous()
-        self._launch_ragged(vertices, faces64, fo, vo, B, F, V, total, codes, coords, histogram, face_edges, eo, n_edges, check_status, "ragged")
-        return (codes, coords) if return_face_coordinates else codes
+        return dict(dev=dev, B=B, F=max(int(max_faces), 1), V=max(int(max_vertices), 1), total=faces.shape[0], fo=fo, vo=vo, eo=eo, n_edges=n_edges,
+                    faces=faces.to(torch.int64).contiguous(), vertices=None if vertices is None else vertices.to(torch.float32).contiguous(),
+                    face_edges=face_edges)
+
+    @torch.no_grad()
+    def encode_ragged(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets, *, face_edges: Optional[Tensor] = None,
+                      edge_offsets=None, return_face_coordinates: bool = False):
+        """encode() (meshgpt_pytorch.py:686-785) on a ragged batch: -> face embeddings (sum nf, dims[-1]) fp32, one row per face in input
+        order (zero rows for faces that contain pad_id) [, discretised coordinates (sum nf, nvf*3) int64]."""
+        r = self._ragged_args(vertices, faces, face_offsets, vertex_offsets, face_edges, edge_offsets)
+        nvf, total, dev = self.num_vertices_per_face, r["total"], r["dev"]
+        enc = torch.zeros((total, self.encoder_dims[-1]), dtype=torch.float32, device=dev)
+        coords = torch.zeros((total, nvf * 3), dtype=torch.int64, device=dev) if return_face_coordinates else None
+        if r["B"] and total:
+            self._launch_ragged(r["vertices"], r["faces"], r["fo"], r["vo"], r["B"], r["F"], r["V"], total, None, coords, None, r["face_edges"], r["eo"],
+                                r["n_edges"], True, "ragged", encoded_out=enc)
+        return (enc, coords) if return_face_coordinates else enc
+
+    @torch.no_grad()
+    def quantize_ragged(self, faces: Tensor, face_offsets, vertex_offsets, face_embed: Tensor):
+        """quantize() (meshgpt_pytorch.py:787-870) on a ragged batch: face_embed (sum nf, dims[-1]) -> (face_embed_output (sum nf, nvf*dim),
+        codes (sum nf * nvf, q) int64, commit_loss).  vertex_offsets only carries the per-mesh vertex counts (ids are range-checked)."""
+        r = self._ragged_args(None, faces, face_offsets, vertex_offsets)
+        nvf, total, dev = self.num_vertices_per_face, r["total"], r["dev"]
+        assert face_embed.is_cuda and tuple(face_embed.shape) == (total, self.encoder_dims[-1])
+        codes = torch.empty((total * nvf, self.num_quantizers), dtype=torch.int64, device=dev)
+        quant = torch.zeros((total, nvf * self.dim_codebook), dtype=torch.float32, device=dev)
+        if r["B"] and total:
+            self._launch_ragged(None, r["faces"], r["fo"], r["vo"], r["B"], r["F"], r["V"], total, codes, None, None, None, None, 0, True, "ragged",
+                                encoded_in=face_embed.to(torch.float32).contiguous(), quantized_out=quant)
+        return quant, codes, torch.zeros(self.num_quantizers, device=dev)
 
     def _launch_ragged(self, vertices, faces64, fo, vo, B, F, V, total, codes, coords=None, histogram=None, face_edges=None, eo=None,
-                       n_edges=0, check_status=True, workspace_tag="ragged"):
+                       n_edges=0, check_status=True, workspace_tag="ragged", encoded_in=None, encoded_out=None, quantized_out=None):
         """One meshtok_tokenize call in the ragged layout on prepared device tensors.  `total` is the number of face rows the buffers
         hold (the kernels take the live count from face_offsets[B] on the device, so it may be a capacity)."""
         prep = self._prepare()
         if check_status == "deferred":
             self._poll_status(block=False)
         E = 0 if face_edges is None else 1      # only the "edges are given" flag in this layout
-        cap = max(1024, self.edge_slots_per_face * B * F, n_edges)
+        total_v = 0 if vertices is None else int(vertices.shape[0])      # 0: unknown - vertex rows reserved for B * V
+        cap = max(1024, self.edge_slots_per_face * min(B * F, max(int(total), 1)), n_edges)
         with torch.cuda.device(prep["device"]):
             while True:
-                ws = self._workspace(prep, B, F, V, E, cap, workspace_tag)
+                ws = self._workspace(prep, B, F, V, E, cap, workspace_tag, total, total_v)
                 a = TokenizeArgs()
                 a.vertices, a.faces, a.face_offsets, a.vertex_offsets, a.total_faces = ptr(vertices), ptr(faces64), ptr(fo), ptr(vo), total
+                a.total_vertices = total_v
                 a.face_edges, a.edge_offsets, a.total_edges = ptr(face_edges), ptr(eo), n_edges
                 a.B, a.F, a.V, a.E = B, F, V, E
                 a.pad_id, a.edge_capacity = int(self.pad_id), cap
                 a.codes_out, a.face_coords_out, a.histogram = ptr(codes), ptr(coords), ptr(histogram)
+                a.encoded_in, a.encoded_out, a.quantized_out = ptr(encoded_in), ptr(encoded_out), ptr(quantized_out)
+                a.stop_after_encode = int(codes is None and quantized_out is None)
                 a.rvq_exact = int(self.force_rvq_exact or not prep["tc_rvq"])
                 a.gemm_simt = int(self.force_gemm_simt or not prep["tc_gemm"])
                 check(lib.meshtok_tokenize(C.byref(prep["model"]), C.byref(a), ptr(ws), ws.numel(), stream_ptr()))
-                self.last_workspace, self.last_shape = ws, (B, F, V, E, cap)
+                self.last_workspace, self.last_shape = ws, (B, F, V, E, cap, int(total), total_v)
                 if not check_status:
                     break
                 if check_status == "deferred":

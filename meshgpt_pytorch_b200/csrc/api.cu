@@ -62,7 +62,8 @@ struct Workspace {
   float4* partial;
   uint8_t* rimg;     // fp16 image of the scaled residual rows (CTA-pair RVQ search)
   float* ssq;        // (B*F, 16): parts of the squared row norms of the last SAGE layer (deferred normalisation)
-  uint16_t* bins;    // (B*F, nvf*4+4): folded-table row ids of every packed row
+  uint16_t* bins;    // (B*F, nvf*4+4): folded-table row ids of every input face slot
+  int rows_cap, vrows_cap;   // packed face rows / quantizer rows the activation buffers hold (<= B*F, B*V)
   size_t total;
 };
 
@@ -141,10 +142,14 @@ int check_model(const meshtok_model* m) {
 
 int enc_dim(const meshtok_model* m) { return m->sage[m->num_sage_layers - 1].dim_out; }
 
-void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E, int64_t cap, meshtok_taps* taps) {
+// rows_cap / vrows_cap: how many packed face rows / quantizer (vertex) rows the batch can have at most - B*F and B*V for the padded
+// layout; for the ragged layout the rows the caller's faces / vertices buffers hold, so that the workspace grows with the sum of the
+// mesh sizes, not with B x the largest mesh.  Arrays indexed by input slot (b*F+f, b*V+v) keep their B*F / B*V size.
+void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E, int64_t cap, size_t rows_cap, size_t vrows_cap, meshtok_taps* taps) {
   meshtok_taps dummy;
   meshtok_taps* t = taps ? taps : &dummy;
   const size_t BF = (size_t)B * F, BV = (size_t)B * V;
+  const size_t RF = rows_cap, RV = vrows_cap;
   // one block, cleared by ONE memset together with mesh_counts behind it: [0..8) status word, [8..16) Counts, [16..20) RVQ statistics
   w->status = c.take<int>(64, &t->status);
   w->counts = reinterpret_cast<Counts*>(w->status ? w->status + 8 : nullptr);
@@ -157,28 +162,34 @@ void carve_topology(Carver& c, Workspace* w, int B, int F, int nvf, int V, int E
   w->deg_out = c.take<int>(BF);
   w->deg_in = c.take<int>(BF);
   w->face_row = c.take<int>(BF, &t->face_row);
-  w->row_face = c.take<int>(BF);
+  w->row_face = c.take<int>(RF);
   w->vert_row = c.take<int>(BV, &t->vert_row);
-  w->vptr = c.take<int>(BV + 1);
-  w->vinc = c.take<int>(BF * nvf);
-  w->indptr = c.take<int>(BF + 1, &t->indptr);
+  w->vptr = c.take<int>(RV + 1);
+  w->vinc = c.take<int>(RF * nvf);
+  w->indptr = c.take<int>(RF + 1, &t->indptr);
   w->src = c.take<int>((size_t)cap, &t->src);
   if (E > 0) {
-    w->ecount = c.take<int>(BF);
-    w->cursor = c.take<int>(BF);
+    w->ecount = c.take<int>(RF);
+    w->cursor = c.take<int>(RF);
     w->etmp = c.take<int>((size_t)cap);
   } else {
     w->ecount = w->cursor = w->etmp = nullptr;
   }
 }
 
-int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, void* base, Workspace* w, meshtok_taps* taps) {
+int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, long long total_faces, long long total_vertices, void* base, Workspace* w,
+              meshtok_taps* taps) {
   meshtok_taps dummy;
   meshtok_taps* t = taps ? taps : &dummy;
   memset(t, 0, sizeof(*t));
   Carver c(base);
-  carve_topology(c, w, B, F, m->nvf, V, E, cap, t);
-  const size_t BF = (size_t)B * F, BV = (size_t)B * V;
+  const size_t slots = (size_t)B * F;
+  // (inside this function BF / BV are ROW capacities; slot-indexed arrays use `slots`)
+  const size_t BF = total_faces > 0 ? (size_t)min((long long)slots, total_faces) : slots;
+  const size_t BV = total_vertices > 0 ? (size_t)min((long long)B * V, total_vertices) : (size_t)B * V;
+  carve_topology(c, w, B, F, m->nvf, V, E, cap, BF, BV, t);
+  w->rows_cap = (int)BF;
+  w->vrows_cap = (int)BV;
   const int D = m->dim_codebook, Q = m->num_quantizers;
   int max_in = 0;
   for (int l = 0; l < m->num_sage_layers; ++l) max_in = max(max_in, m->sage[l].dim_in);
@@ -195,7 +206,7 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, v
   w->img_x[1] = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_w)) : nullptr;
   w->img_agg = images ? c.take<uint8_t>(rows_image_bytes((long long)BF, max_in)) : nullptr;
   w->ssq = c.take<float>(BF * 16);
-  w->bins = c.take<uint16_t>(BF * (size_t)(m->nvf * 4 + 4));
+  w->bins = c.take<uint16_t>(slots * (size_t)(m->nvf * 4 + 4));
   for (int l = 0; l < m->num_sage_layers; ++l) w->layer_out[l] = c.take<float>(BF * m->sage[l].dim_out, &t->layer_out[l]);
   w->y = c.take<float>(BF * m->nvf * D);
   w->avg = c.take<float>(BV * D, &t->averaged);
@@ -329,7 +340,7 @@ int meshtok_topology_workspace_bytes(int B, int F, int nvf, int V, int E_user, s
   if (rc != MESHTOK_OK) return rc;
   Carver c(nullptr);
   Workspace w;
-  carve_topology(c, &w, B, F, nvf, V, E_user, 16, nullptr);
+  carve_topology(c, &w, B, F, nvf, V, E_user, 16, (size_t)B * F, (size_t)B * V, nullptr);
   *bytes = align_up(c.off, 256);
   return MESHTOK_OK;
 }
@@ -341,7 +352,7 @@ static int face_edges_common(const int64_t* faces, int B, int F, int nvf, int V,
   int rc = topo_check_shape(B, F, nvf, V);
   if (rc != MESHTOK_OK) return rc;
   Carver c(workspace);
-  carve_topology(c, w, B, F, nvf, V, 0, 16, nullptr);
+  carve_topology(c, w, B, F, nvf, V, 0, 16, (size_t)B * F, (size_t)B * V, nullptr);
   if (c.off > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", c.off, workspace_bytes);
     return MESHTOK_ERR_WORKSPACE;
@@ -380,28 +391,39 @@ int meshtok_face_edges_fill(const int64_t* faces, int B, int F, int nvf, int V, 
   return topo_fill_dense(p, static_cast<cudaStream_t>(stream));
 }
 
-int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
-                                     size_t* bytes) {
+int meshtok_tokenize_workspace_bytes_ragged(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity, int64_t total_faces,
+                                            int64_t total_vertices, size_t* bytes) {
   MT_CHECK_ARG(bytes != nullptr, "bytes is null");
   int rc = check_model(model);
   if (rc != MESHTOK_OK) return rc;
   rc = topo_check_shape(B, F, model->nvf, V);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(edge_capacity > 0 && edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
+  MT_CHECK_ARG(total_faces >= 0 && total_vertices >= 0, "total_faces / total_vertices must be >= 0 (0: B*F / B*V)");
   Workspace w;
-  rc = carve_all(model, B, F, V, E, edge_capacity, nullptr, &w, nullptr);
+  rc = carve_all(model, B, F, V, E, edge_capacity, total_faces, total_vertices, nullptr, &w, nullptr);
   if (rc != MESHTOK_OK) return rc;
   *bytes = w.total;
   return MESHTOK_OK;
 }
 
-int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
-                          meshtok_taps* taps) {
+int meshtok_tokenize_workspace_bytes(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                                     size_t* bytes) {
+  return meshtok_tokenize_workspace_bytes_ragged(model, B, F, V, E, edge_capacity, 0, 0, bytes);
+}
+
+int meshtok_tokenize_taps_ragged(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity, int64_t total_faces,
+                                 int64_t total_vertices, meshtok_taps* taps) {
   MT_CHECK_ARG(taps != nullptr, "taps is null");
   int rc = check_model(model);
   if (rc != MESHTOK_OK) return rc;
   Workspace w;
-  return carve_all(model, B, F, V, E, edge_capacity, nullptr, &w, taps);
+  return carve_all(model, B, F, V, E, edge_capacity, total_faces, total_vertices, nullptr, &w, taps);
+}
+
+int meshtok_tokenize_taps(const meshtok_model* model, int B, int F, int V, int E, int64_t edge_capacity,
+                          meshtok_taps* taps) {
+  return meshtok_tokenize_taps_ragged(model, B, F, V, E, edge_capacity, 0, 0, taps);
 }
 
 int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, void* workspace, size_t workspace_bytes,
@@ -411,6 +433,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   MT_CHECK_ARG(a != nullptr && workspace != nullptr, "args / workspace is null");
   MT_CHECK_ARG(a->faces != nullptr, "faces is null");
   MT_CHECK_ARG(a->vertices != nullptr || a->encoded_in != nullptr, "vertices is null");
+  MT_CHECK_ARG(a->vertices != nullptr || a->vertex_offsets == nullptr || a->encoded_in != nullptr, "vertices is null");
   MT_CHECK_ARG(a->stop_after_encode || a->codes_out != nullptr, "codes_out is null");
   MT_CHECK_ARG(a->face_edges == nullptr || a->E > 0, "face_edges given but E <= 0 (pass one all-pad edge for an empty list)");
   const int B = a->B, F = a->F, V = a->V, nvf = m->nvf, D = m->dim_codebook, Q = m->num_quantizers;
@@ -419,10 +442,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   if (ragged) {
     MT_CHECK_ARG(a->face_offsets != nullptr && a->vertex_offsets != nullptr && a->total_faces >= 0 && a->total_faces <= (long long)B * F,
                  "ragged input needs face_offsets and vertex_offsets (B + 1 int32 each) and 0 <= total_faces <= B * F");
-    if (a->encoded_in || a->encoded_out || a->quantized_out) {
-      set_error("ragged input: encoded_in, encoded_out and quantized_out exist only in the padded layout");
-      return MESHTOK_ERR_UNSUPPORTED;
-    }
+    MT_CHECK_ARG(a->total_vertices >= 0, "total_vertices must be >= 0 (0: unknown, the workspace is sized for B * V vertex rows)");
     MT_CHECK_ARG(a->face_edges == nullptr || (a->edge_offsets != nullptr && a->total_edges >= 0 && a->total_edges <= a->edge_capacity),
                  "ragged input with face_edges needs edge_offsets (B + 1 int32) and 0 <= total_edges <= edge_capacity");
   }
@@ -430,7 +450,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(a->edge_capacity > 0 && a->edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
   Workspace w;
-  rc = carve_all(m, B, F, V, E, a->edge_capacity, workspace, &w, nullptr);
+  rc = carve_all(m, B, F, V, E, a->edge_capacity, ragged ? a->total_faces : 0, ragged ? a->total_vertices : 0, workspace, &w, nullptr);
   if (rc != MESHTOK_OK) return rc;
   if (w.total > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", w.total, workspace_bytes);
@@ -441,7 +461,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     return MESHTOK_ERR_WORKSPACE;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const int max_rows = B * F, max_vrows = B * V;
+  const int slots = B * F;                                            // input face slots of the padded layout
+  const int max_rows = w.rows_cap, max_vrows = w.vrows_cap;           // packed rows the activation buffers hold
   const bool simt = a->gemm_simt != 0;
 
   // ---- topology -------------------------------------------------------------------------------
@@ -489,10 +510,10 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     fp.x0 = (simt || a->keep_taps) ? w.x0 : nullptr; fp.x0_image = simt ? nullptr : w.img_x[0]; fp.face_coords_out = a->face_coords_out;
     fp.bins_out = w.bins;
     if (a->face_coords_out)
-      MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(ragged ? a->total_faces : max_rows) * nvf * 3, s));
+      MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(ragged ? a->total_faces : slots) * nvf * 3, s));
     MT_CHECK_CUDA(cudaEventRecord(side->begin, s));
     MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->begin, 0));
-    if ((rc = launch_face_bins(fp, ragged ? a->total_faces : (long long)max_rows, side->stream)) != MESHTOK_OK) return rc;
+    if ((rc = launch_face_bins(fp, ragged ? a->total_faces : (long long)slots, side->stream)) != MESHTOK_OK) return rc;
     MT_CHECK_CUDA(cudaEventRecord(side->bins_done, side->stream));
     bins_pending = true;
   }
@@ -605,7 +626,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     enc = x;
   } else {
     if ((rc = join_edges()) != MESHTOK_OK) return rc;   // quantize(): no encoder, but the side stream must rejoin
-    if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, s)) != MESHTOK_OK) return rc;
+    if ((rc = launch_pack_rows(a->encoded_in, w.row_face, enc_dim(m), w.layer_out[L - 1], w.counts, max_rows, a->face_offsets, F, s)) != MESHTOK_OK) return rc;
     enc = w.layer_out[L - 1];
     if (!simt && !a->stop_after_encode) {
       MT_CHECK_ARG(w.img_x[0] != nullptr, "tcgen05 linear requested but the layer widths do not allow activation images (set gemm_simt)");
@@ -613,7 +634,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     }
   }
   if (a->encoded_out)
-    if ((rc = launch_unpack_rows(enc, w.face_row, max_rows, enc_dim(m), a->encoded_out, s)) != MESHTOK_OK) return rc;
+    if ((rc = launch_unpack_rows(enc, w.face_row, slots, enc_dim(m), a->encoded_out, a->face_offsets, B, F, a->total_faces, s)) != MESHTOK_OK) return rc;
   if (a->stop_after_encode) return MESHTOK_OK;
 
   // ---- quantize -------------------------------------------------------------------------------
@@ -668,7 +689,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
                                   a->histogram ? &gh : nullptr, m->codebook_size, s);
     if (rc != MESHTOK_OK) return rc; }
   if (a->quantized_out)
-    if ((rc = launch_gather_quantized(a->faces, w.face_row, w.vert_row, w.qrows, B, F, nvf, V, D, pad_row, a->quantized_out, s)) != MESHTOK_OK) return rc;
+    if ((rc = launch_gather_quantized(a->faces, w.face_row, w.vert_row, w.qrows, B, F, nvf, V, D, pad_row, a->quantized_out, a->face_offsets,
+                                      a->total_faces, s)) != MESHTOK_OK) return rc;
   return MESHTOK_OK;
 }
 
@@ -678,7 +700,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
 namespace {
 struct StageCtx {
   Workspace w;
-  int B, F, V, E, nvf, D, Q, max_rows, max_vrows;
+  int B, F, V, E, nvf, D, Q, slots, max_rows, max_vrows;
   bool ragged, simt;
   cudaStream_t s;
 };
@@ -695,7 +717,7 @@ int stage_begin(const meshtok_model* m, const meshtok_tokenize_args* a, void* wo
   rc = topo_check_shape(c->B, c->F, c->nvf, c->V);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(a->edge_capacity > 0 && a->edge_capacity < (1ll << 31), "edge_capacity must be in (0, 2^31)");
-  rc = carve_all(m, c->B, c->F, c->V, c->E, a->edge_capacity, workspace, &c->w, nullptr);
+  rc = carve_all(m, c->B, c->F, c->V, c->E, a->edge_capacity, c->ragged ? a->total_faces : 0, c->ragged ? a->total_vertices : 0, workspace, &c->w, nullptr);
   if (rc != MESHTOK_OK) return rc;
   if (c->w.total > workspace_bytes) {
     set_error("workspace too small: need %zu bytes, got %zu", c->w.total, workspace_bytes);
@@ -705,8 +727,9 @@ int stage_begin(const meshtok_model* m, const meshtok_tokenize_args* a, void* wo
     set_error("workspace must be 256-byte aligned");
     return MESHTOK_ERR_WORKSPACE;
   }
-  c->max_rows = c->B * c->F;
-  c->max_vrows = c->B * c->V;
+  c->slots = c->B * c->F;
+  c->max_rows = c->w.rows_cap;
+  c->max_vrows = c->w.vrows_cap;
   c->simt = a->gemm_simt != 0;
   c->s = static_cast<cudaStream_t>(stream);
   return MESHTOK_OK;
@@ -773,8 +796,8 @@ int meshtok_stage_face_features_embed(const meshtok_model* m, const meshtok_toke
   }
   fp.x0 = x0_rows; fp.x0_image = nullptr; fp.face_coords_out = a->face_coords_out; fp.bins_out = w.bins;
   if (a->face_coords_out)
-    MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(c.ragged ? a->total_faces : c.max_rows) * c.nvf * 3, c.s));
-  if ((rc = launch_face_bins(fp, c.ragged ? a->total_faces : (long long)c.max_rows, c.s)) != MESHTOK_OK) return rc;
+    MT_CHECK_CUDA(cudaMemsetAsync(a->face_coords_out, 0, sizeof(int64_t) * (size_t)(c.ragged ? a->total_faces : c.slots) * c.nvf * 3, c.s));
+  if ((rc = launch_face_bins(fp, c.ragged ? a->total_faces : (long long)c.slots, c.s)) != MESHTOK_OK) return rc;
   return launch_face_sum(fp, c.max_rows, c.s);
 }
 

@@ -78,12 +78,14 @@ int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off,
                                long long total_faces, int B, int F, int nvf, int V, int Q, int64_t pad_id, int64_t* codes_out,
                                const GatherHist* gh, int K, cudaStream_t stream);
 int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
-                            int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream);
-// encoded_out (B*F, d) <- packed rows, zeros on padded faces.
-int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, cudaStream_t stream);
-// packed rows <- (B*F, d) padded layout.
+                            int F, int nvf, int V, int D, const float* pad_row, float* out, const int32_t* in_face_off, long long total_faces,
+                            cudaStream_t stream);
+// encoded_out <- packed rows, zeros on padded faces: (B*F, d) in the padded layout, (total_faces, d) in the ragged one (in_face_off != null)
+int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, const int32_t* in_face_off, int B, int F,
+                       long long total_faces, cudaStream_t stream);
+// packed rows <- (B*F, d) padded layout / (total_faces, d) ragged layout.
 int launch_pack_rows(const float* padded, const int* row_face, int d, float* packed, const Counts* counts, int max_rows,
-                     cudaStream_t stream);
+                     const int32_t* in_face_off, int F, cudaStream_t stream);
 
 // ---- K8a -----------------------------------------------------------------------------------------
 // exact fp32 nearest-code search: best[r] = argmin_j sqrt(max(|x|^2 + |e_j|^2 - 2 x.e_j, 0)), lowest index on ties.

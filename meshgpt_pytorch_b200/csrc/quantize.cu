@@ -273,26 +273,56 @@ __global__ void __launch_bounds__(256) gather_codes_ragged_kernel(const int64_t*
   for (int q = 0; q < Q; ++q) dst[q] = vcodes[(size_t)vr * Q + q];
 }
 
+// ragged input: flat face g -> (mesh b, face f inside it); the last b with in_face_off[b] <= g (empty meshes repeat an offset)
+__device__ __forceinline__ int ragged_mesh_of_face(const int32_t* __restrict__ in_face_off, int B, long long g) {
+  int lo = 0, hi = B;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((long long)__ldg(in_face_off + mid) <= g) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void __launch_bounds__(256) gather_quantized_kernel(const int64_t* __restrict__ faces, const int* __restrict__ face_row,
                                                                const int* __restrict__ vert_row, const float* __restrict__ qrows,
                                                                int BF, int F, int nvf, int V, int D,
-                                                               const float* __restrict__ pad_row, float* __restrict__ out) {
+                                                               const float* __restrict__ pad_row, float* __restrict__ out,
+                                                               const int32_t* __restrict__ in_face_off, int B, long long total_faces) {
   const int wpb = blockDim.x >> 5;
   const long long tok = (long long)blockIdx.x * wpb + warp_id();
-  if (tok >= (long long)BF * nvf) return;
-  const int pf = (int)(tok / nvf);
-  const float* srcp;
-  if (face_row[pf] < 0) srcp = pad_row;
-  else {
-    const int b = pf / F;
-    srcp = qrows + (size_t)vert_row[(size_t)b * V + faces[tok]] * D;
+  int pf, b;
+  if (in_face_off != nullptr) {   // ragged layout: tok indexes the flat (total_faces * nvf) sequence
+    if (tok >= min(total_faces, (long long)__ldg(in_face_off + B)) * nvf) return;
+    const long long g = tok / nvf;
+    b = ragged_mesh_of_face(in_face_off, B, g);
+    const int f = (int)(g - __ldg(in_face_off + b));
+    pf = f < F ? b * F + f : -1;
+  } else {
+    if (tok >= (long long)BF * nvf) return;
+    pf = (int)(tok / nvf);
+    b = pf / F;
   }
+  const float* srcp;
+  if (pf < 0 || face_row[pf] < 0) srcp = pad_row;
+  else srcp = qrows + (size_t)vert_row[(size_t)b * V + faces[tok]] * D;
   for (int c = lane_id(); c < D; c += 32) out[tok * D + c] = srcp ? srcp[c] : 0.f;
 }
 
 __global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restrict__ packed, const int* __restrict__ face_row,
-                                                          int BF, int d4, float4* __restrict__ out) {
+                                                          int BF, int d4, float4* __restrict__ out, const int32_t* __restrict__ in_face_off, int B, int F,
+                                                          long long total_faces) {
   const int wpb = blockDim.x >> 5;
+  if (in_face_off != nullptr) {   // ragged layout: out is (total_faces, d), one row per flat face
+    const long long n = min(total_faces, (long long)__ldg(in_face_off + B));
+    for (long long g = (long long)blockIdx.x * wpb + warp_id(); g < n; g += (long long)gridDim.x * wpb) {
+      const int b = ragged_mesh_of_face(in_face_off, B, g);
+      const int f = (int)(g - __ldg(in_face_off + b));
+      const int row = f < F ? face_row[(size_t)b * F + f] : -1;
+      const float4* s = reinterpret_cast<const float4*>(packed) + (size_t)(row < 0 ? 0 : row) * d4;
+      for (int c = lane_id(); c < d4; c += 32) out[g * d4 + c] = row < 0 ? make_float4(0.f, 0.f, 0.f, 0.f) : s[c];
+    }
+    return;
+  }
   for (long long pf = (long long)blockIdx.x * wpb + warp_id(); pf < BF; pf += (long long)gridDim.x * wpb) {
     const int row = face_row[pf];
     const float4* s = reinterpret_cast<const float4*>(packed) + (size_t)(row < 0 ? 0 : row) * d4;
@@ -301,11 +331,17 @@ __global__ void __launch_bounds__(256) unpack_rows_kernel(const float* __restric
 }
 
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float4* __restrict__ padded, const int* __restrict__ row_face,
-                                                        int d4, float4* __restrict__ packed, const Counts* counts) {
+                                                        int d4, float4* __restrict__ packed, const Counts* counts, const int32_t* __restrict__ in_face_off,
+                                                        int F) {
   const int wpb = blockDim.x >> 5;
   const int n = counts->n_faces;
   for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
-    const float4* s = padded + (size_t)row_face[row] * d4;
+    size_t from = (size_t)row_face[row];   // slot b*F+f of the padded layout ...
+    if (in_face_off != nullptr) {          // ... or flat face in_face_off[b] + f of the ragged one
+      const int b = (int)(from / F);
+      from = (size_t)__ldg(in_face_off + b) + (from - (size_t)b * F);
+    }
+    const float4* s = padded + from * d4;
     for (int c = lane_id(); c < d4; c += 32) packed[(size_t)row * d4 + c] = s[c];
   }
 }
@@ -387,31 +423,34 @@ int launch_gather_codes_ragged(const int64_t* faces, const int32_t* in_face_off,
 }
 
 int launch_gather_quantized(const int64_t* faces, const int* face_row, const int* vert_row, const float* qrows, int B,
-                            int F, int nvf, int V, int D, const float* pad_row, float* out, cudaStream_t stream) {
-  const long long n = (long long)B * F * nvf;
+                            int F, int nvf, int V, int D, const float* pad_row, float* out, const int32_t* in_face_off, long long total_faces,
+                            cudaStream_t stream) {
+  const long long n = (in_face_off ? total_faces : (long long)B * F) * nvf;
   if (n == 0) return MESHTOK_OK;
   gather_quantized_kernel<<<(unsigned)((n + 7) / 8), 256, 0, stream>>>(faces, face_row, vert_row, qrows, B * F, F, nvf, V, D,
-                                                                      pad_row, out);
+                                                                      pad_row, out, in_face_off, B, total_faces);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
-int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, cudaStream_t stream) {
+int launch_unpack_rows(const float* packed, const int* face_row, int BF, int d, float* out, const int32_t* in_face_off, int B, int F,
+                       long long total_faces, cudaStream_t stream) {
   MT_CHECK_ARG(d % 4 == 0, "unpack_rows: width %d must be a multiple of 4", d);
-  if (BF == 0) return MESHTOK_OK;
-  const int blocks = max(1, min(ceil_div(BF, 8), 148 * 16));
-  unpack_rows_kernel<<<blocks, 256, 0, stream>>>(packed, face_row, BF, d / 4, reinterpret_cast<float4*>(out));
+  const long long n = in_face_off ? total_faces : (long long)BF;
+  if (n == 0) return MESHTOK_OK;
+  const int blocks = (int)max(1ll, min((n + 7) / 8, 148ll * 16));
+  unpack_rows_kernel<<<blocks, 256, 0, stream>>>(packed, face_row, BF, d / 4, reinterpret_cast<float4*>(out), in_face_off, B, F, total_faces);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }
 
 int launch_pack_rows(const float* padded, const int* row_face, int d, float* packed, const Counts* counts, int max_rows,
-                     cudaStream_t stream) {
+                     const int32_t* in_face_off, int F, cudaStream_t stream) {
   MT_CHECK_ARG(d % 4 == 0, "pack_rows: width %d must be a multiple of 4", d);
   if (max_rows == 0) return MESHTOK_OK;
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   pack_rows_kernel<<<blocks, 256, 0, stream>>>(reinterpret_cast<const float4*>(padded), row_face, d / 4,
-                                               reinterpret_cast<float4*>(packed), counts);
+                                               reinterpret_cast<float4*>(packed), counts, in_face_off, F);
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
 }

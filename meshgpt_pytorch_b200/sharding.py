@@ -19,18 +19,22 @@ def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
 
 def balanced_contiguous_shards(face_counts: Sequence[int], world: int) -> List[Tuple[int, int]]:
     """Contiguous cuts that balance the NUMBER OF FACES (the cost driver) rather than the number of meshes -
-    for ragged collections such as BASELINE config 4."""
-    total = sum(face_counts)
-    cuts, start, acc = [], 0, 0
+    for ragged collections such as BASELINE config 4.  Cut r is placed where the running face count is closest to
+    r / world of the total (from either side), every rank keeping at least one mesh while there are enough."""
+    n = len(face_counts)
+    prefix = [0]
+    for c in face_counts:
+        prefix.append(prefix[-1] + int(c))
+    total = prefix[-1]
+    cuts, start = [], 0
     for r in range(world):
-        target = total * (r + 1) / world
-        end = start
-        while end < len(face_counts) and (acc + face_counts[end] <= target or end == start) and len(face_counts) - end > world - r - 1:
-            acc += face_counts[end]
-            end += 1
         if r == world - 1:
-            acc += sum(face_counts[end:])
-            end = len(face_counts)
+            end = n
+        else:
+            target = total * (r + 1) / world
+            lo = min(n, start + 1) if n - start > world - r - 1 else start        # at least one mesh, if the others can still get one
+            hi = max(lo, n - (world - r - 1))                                     # leave one mesh for each remaining rank
+            end = min(range(lo, hi + 1), key=lambda e: (abs(prefix[e] - target), e))
         cuts.append((start, end))
         start = end
     return cuts
