@@ -432,19 +432,37 @@ int meshtok_dec_argmax_coords_padded(const float* logits, const uint8_t* valid, 
  * Token-embedding front end of MeshTransformer.forward_on_codes, meshgpt_pytorch/meshgpt_pytorch.py:1526-1570
  * (the step that follows tokenization).  n = nvf * Q codes per face.
  * ------------------------------------------------------------------------------------------ */
-/* :1528-1547 + :1560: out (B, ceil(L / n) * n, D) fp32 = ((token_embed[code, pad_id -> 0] + abs_pos_emb[t]) + level_embed[t % Q]) +
- * vertex_embed[(t / Q) % nvf], added in the reference's order (bit-exact); rows t >= L (the incomplete last face) are zero.
- * token_embed (n_embed, D) with n_embed = codebook_size + 1 (eos), abs_pos_emb (>= L, D), level_embed (Q, D), vertex_embed (nvf, D). */
-int meshtok_frontend_fine_tokens(const int64_t* codes, int B, int L, int D, int64_t pad_id, int Q, int nvf, int n_embed,
-                                 const float* token_embed, const float* abs_pos_emb, const float* level_embed, const float* vertex_embed,
-                                 float* out, meshtok_stream_t stream);
-/* :1564-1570: out (B, L / n, D) fp32 = LayerNorm(Linear(n * D -> D)(the n fine tokens of a face)) for the complete faces, computed from
- * tables folded at load time: folded_tables (n, n_embed, D) with folded_tables[j] = token_embed @ W[:, j * D : (j + 1) * D]^T, and
- * face_pos (>= L / n, D) with face_pos[f] = sum_j W_j (abs_pos_emb[n f + j] + level_embed[j % Q] + vertex_embed[j / Q]) + bias.
- * D must be a multiple of 128, at most 1024; n <= 32. */
-int meshtok_frontend_face_tokens(const int64_t* codes, int B, int L, int n, int D, int64_t pad_id, int n_embed, const float* folded_tables,
-                                 const float* face_pos, const float* ln_gamma, const float* ln_beta, float eps, float* out,
-                                 meshtok_stream_t stream);
+/* Where the codes come from.  Either `codes` (B, L) int64 - the tensor tokenize returns, flattened '(b n q -> b (n q))' - or, skipping
+ * that tensor, a meshtok_vertex_code_source: the tokenizer's per-vertex codes and the maps of its workspace (meshtok_tokenize_taps:
+ * vertex_codes, face_row, vert_row) plus the faces tensor; then L = F * nvf * Q and token t = (face, slot, level) is looked up as
+ * vertex_codes[vert_row[b, faces[b, face, slot]], level], pad_id on padded faces.  Exactly one of the two must be given.
+ * eos_id >= 0: append_eos (:1506-1518) - the sequence is one token longer, eos_id at the first pad position of every row (lens_ws: B
+ * int32 of scratch); eos_id < 0: none. */
+typedef struct meshtok_vertex_code_source {
+  const int64_t* faces;         /* (B, F, nvf) */
+  const int32_t* face_row;      /* (B*F) packed row of each face or -1 */
+  const int32_t* vert_row;      /* (B*V) quantizer row of each vertex or -1 */
+  const int32_t* vertex_codes;  /* (n_vrows, Q) */
+  int32_t F, nvf, V, Q;
+} meshtok_vertex_code_source;
+/* :1506-1518 as a tensor: out (B, L + 1) int64 (pad positions stay pad_id, the extra last column is 0 unless the eos landed there). */
+int meshtok_frontend_append_eos(const int64_t* codes, const meshtok_vertex_code_source* vsrc, int B, int L, int64_t pad_id, int64_t eos_id,
+                                int32_t* lens_ws, int64_t* out, meshtok_stream_t stream);
+/* :1528-1547 + :1560: out (B, ceil(Le / n) * n, D) fp32 = ((token_embed[code, pad_id -> 0] + abs_pos_emb[t]) + level_embed[t % Q]) +
+ * vertex_embed[(t / Q) % nvf], added in the reference's order (bit-exact); rows t >= Le (the incomplete last face) are zero; Le = L (+ 1
+ * with an eos).  token_embed (n_embed, D) with n_embed = codebook_size + 1 (eos), abs_pos_emb (>= Le, D), level_embed (Q, D),
+ * vertex_embed (nvf, D). */
+int meshtok_frontend_fine_tokens(const int64_t* codes, const meshtok_vertex_code_source* vsrc, int B, int L, int D, int64_t pad_id, int64_t eos_id,
+                                 int32_t* lens_ws, int Q, int nvf, int n_embed, const float* token_embed, const float* abs_pos_emb,
+                                 const float* level_embed, const float* vertex_embed, float* out, meshtok_stream_t stream);
+/* :1564-1570 (+ the sos rows of :1591-1594): out (B, n_sos + Le / n, D) fp32 = [sos (n_sos, D) ; LayerNorm(Linear(n * D -> D)(the n fine
+ * tokens of a face)) for the complete faces], computed from tables folded at load time: folded_tables (n, n_embed, D) with
+ * folded_tables[j] = token_embed @ W[:, j * D : (j + 1) * D]^T, and face_pos (>= Le / n, D) with
+ * face_pos[f] = sum_j W_j (abs_pos_emb[n f + j] + level_embed[j % Q] + vertex_embed[j / Q]) + bias.
+ * D must be a multiple of 128, at most 1024; n <= 32; n_sos = 0: no sos rows. */
+int meshtok_frontend_face_tokens(const int64_t* codes, const meshtok_vertex_code_source* vsrc, int B, int L, int n, int D, int64_t pad_id, int64_t eos_id,
+                                 int32_t* lens_ws, int n_embed, const float* folded_tables, const float* face_pos, const float* ln_gamma,
+                                 const float* ln_beta, float eps, const float* sos, int n_sos, float* out, meshtok_stream_t stream);
 
 #ifdef __cplusplus
 }

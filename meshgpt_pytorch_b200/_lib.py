@@ -67,6 +67,11 @@ class PipelineResult(C.Structure):
     _fields_ = [("ticket", C.c_int64), ("slot", C.c_int32), ("status", C.c_int32), ("codes_host", C.c_void_p)]
 
 
+class VertexCodeSource(C.Structure):
+    _fields_ = [("faces", C.c_void_p), ("face_row", C.c_void_p), ("vert_row", C.c_void_p), ("vertex_codes", C.c_void_p),
+                ("F", C.c_int32), ("nvf", C.c_int32), ("V", C.c_int32), ("Q", C.c_int32)]
+
+
 class Taps(C.Structure):
     _fields_ = [
         ("status", C.c_int64), ("counts", C.c_int64), ("face_row", C.c_int64), ("vert_row", C.c_int64),
@@ -107,10 +112,13 @@ SIGNATURES = {
     "meshtok_dec_pixelnorm_squeeze_excite_gate": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "meshtok_dec_gate_residual_halo": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "meshtok_dec_argmax_coords_padded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "meshtok_frontend_fine_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "meshtok_frontend_face_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                               C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
+    "meshtok_frontend_append_eos": (C.c_int, [C.c_void_p, C.POINTER(VertexCodeSource), C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]),
+    "meshtok_frontend_fine_tokens": (C.c_int, [C.c_void_p, C.POINTER(VertexCodeSource), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p,
+                                               C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "meshtok_frontend_face_tokens": (C.c_int, [C.c_void_p, C.POINTER(VertexCodeSource), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                               C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_int,
+                                               C.c_void_p, C.c_void_p]),
     "meshtok_profile_enable": (C.c_int, [C.c_int]),
     "meshtok_profile_sections": (C.c_int, []),
     "meshtok_profile_section_name": (C.c_char_p, [C.c_int]),

@@ -19,12 +19,15 @@ from typing import Dict, Tuple
 import torch
 from torch import Tensor, nn
 
+import ctypes as C
+
+from . import _lib
 from ._lib import check, lib, ptr, stream_ptr
 
 
 class MeshTransformerFrontEnd(nn.Module):
     def __init__(self, autoencoder=None, *, dim: int = 512, max_seq_len: int = 8192, pad_id: int = -1, codebook_size: int | None = None,
-                 num_quantizers: int | None = None, quads: bool | None = None):
+                 num_quantizers: int | None = None, quads: bool | None = None, num_sos_tokens: int = 1):
         super().__init__()
         if autoencoder is not None:
             codebook_size = autoencoder.codebook_size if codebook_size is None else codebook_size
@@ -46,6 +49,7 @@ class MeshTransformerFrontEnd(nn.Module):
         self.vertex_embed = nn.Parameter(torch.randn(self.num_vertices_per_face, dim))    # :1161
         self.abs_pos_emb = nn.Embedding(max_seq_len, dim)                                 # :1163
         self.to_face_tokens = nn.Sequential(nn.Linear(n * dim, dim), nn.LayerNorm(dim))   # :1191-1194
+        self.sos_token = nn.Parameter(torch.randn(num_sos_tokens, dim))                   # :1148-1152
         for p in self.parameters():
             p.requires_grad_(False)
         self._prep = None
@@ -85,6 +89,7 @@ class MeshTransformerFrontEnd(nn.Module):
             prep = dict(tables=tables.contiguous(), face_pos=face_pos.float().contiguous(),
                         tok=self.token_embed.weight.detach().to(**f32).contiguous(), pos=self.abs_pos_emb.weight.detach().to(**f32).contiguous(),
                         level=self.quantize_level_embed.detach().to(**f32).contiguous(), vert=self.vertex_embed.detach().to(**f32).contiguous(),
+                        sos=self.sos_token.detach().to(**f32).contiguous(),
                         gamma=self.to_face_tokens[1].weight.detach().to(**f32).contiguous(),
                         beta=self.to_face_tokens[1].bias.detach().to(**f32).contiguous(), eps=float(self.to_face_tokens[1].eps))
         self._prep, self._prep_key = prep, key
@@ -100,36 +105,84 @@ class MeshTransformerFrontEnd(nn.Module):
             raise ValueError(f"received codes of length {codes.shape[1]} but needs to be less than or equal to set max_seq_len {self.max_seq_len}")
         return codes.to(torch.int64).contiguous()
 
+    def _source(self, codes, source):
+        """(codes pointer, vertex-source struct or None, batch, L, device, keep-alive)."""
+        if source is None:
+            codes = self._check(codes)
+            return ptr(codes), None, codes.shape[0], codes.shape[1], codes.device, codes
+        autoencoder, faces = source
+        t = autoencoder.taps()                                    # views into the workspace of the tokenizer's last call
+        faces = faces.to(torch.int64).contiguous()
+        B, F, nvf = faces.shape
+        assert t["face_row"].shape == (B, F) and nvf == self.num_vertices_per_face, "faces must be the tensor the autoencoder's last call tokenized"
+        vs = _lib.VertexCodeSource()
+        vs.faces, vs.face_row, vs.vert_row, vs.vertex_codes = ptr(faces), ptr(t["face_row"]), ptr(t["vert_row"]), ptr(t["vertex_codes"])
+        vs.F, vs.nvf, vs.V, vs.Q = F, nvf, t["vert_row"].shape[1], self.num_quantizers
+        L = F * nvf * self.num_quantizers
+        if L > self.max_seq_len:
+            raise ValueError(f"received codes of length {L} but needs to be less than or equal to set max_seq_len {self.max_seq_len}")
+        return 0, vs, B, L, faces.device, (faces, t)
+
+    def _eos(self, append_eos, B, dev):
+        if not append_eos:
+            return -1, None
+        return self.eos_token_id, torch.empty(max(B, 1), dtype=torch.int32, device=dev)
+
     @torch.no_grad()
-    def fine_tokens(self, codes: Tensor) -> Tensor:
-        """grouped_codes (b, ceil(L / n), n, dim) of :1564 - every code's embedding, zero rows behind an incomplete last face."""
-        codes = self._check(codes)
-        p = self._prepare()
-        b, L = codes.shape
-        n = self.num_quantizers * self.num_vertices_per_face
-        nfp = -(-L // n)
-        out = torch.empty(b, nfp, n, self.dim, dtype=torch.float32, device=codes.device)
-        with torch.cuda.device(codes.device):
-            check(lib.meshtok_frontend_fine_tokens(ptr(codes), b, L, self.dim, self.pad_id, self.num_quantizers, self.num_vertices_per_face,
-                                                   self.codebook_size + 1, ptr(p["tok"]), ptr(p["pos"]), ptr(p["level"]), ptr(p["vert"]), ptr(out),
-                                                   stream_ptr()))
+    def append_eos(self, codes: Tensor) -> Tensor:
+        """:1506-1518 on the device: (b, L) -> (b, L + 1) with the eos id at the first pad position of every row."""
+        cp, vs, b, L, dev, keep = self._source(codes, None)
+        out = torch.empty(b, L + 1, dtype=torch.int64, device=dev)
+        lens = torch.empty(max(b, 1), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.meshtok_frontend_append_eos(cp, None, b, L, self.pad_id, self.eos_token_id, ptr(lens), ptr(out), stream_ptr()))
         return out
 
     @torch.no_grad()
-    def face_tokens(self, codes: Tensor) -> Tensor:
-        """face_codes (b, L // n, dim) of :1570 - one token per complete face."""
-        codes = self._check(codes)
+    def fine_tokens(self, codes: Tensor = None, append_eos: bool = False, source=None) -> Tensor:
+        """grouped_codes (b, ceil(L / n), n, dim) of :1564 - every code's embedding, zero rows behind an incomplete last face.
+        append_eos: of the eos-extended sequence (:1506-1518), without materialising it.  source=(autoencoder, faces): read the codes
+        from the tokenizer's per-vertex result instead of a codes tensor (see embed_tokenizer_output)."""
+        cp, vs, b, L, dev, keep = self._source(codes, source)
         p = self._prepare()
-        b, L = codes.shape
         n = self.num_quantizers * self.num_vertices_per_face
-        out = torch.empty(b, L // n, self.dim, dtype=torch.float32, device=codes.device)
-        with torch.cuda.device(codes.device):
-            check(lib.meshtok_frontend_face_tokens(ptr(codes), b, L, n, self.dim, self.pad_id, self.codebook_size + 1, ptr(p["tables"]),
-                                                   ptr(p["face_pos"]), ptr(p["gamma"]), ptr(p["beta"]), p["eps"], ptr(out), stream_ptr()))
+        eos, lens = self._eos(append_eos, b, dev)
+        Le = L + int(append_eos)
+        if Le > self.max_seq_len:
+            raise ValueError(f"received codes of length {Le} but needs to be less than or equal to set max_seq_len {self.max_seq_len}")
+        nfp = -(-Le // n)
+        out = torch.empty(b, nfp, n, self.dim, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.meshtok_frontend_fine_tokens(cp, None if vs is None else C.byref(vs), b, L, self.dim, self.pad_id, eos, ptr(lens),
+                                                   self.num_quantizers, self.num_vertices_per_face, self.codebook_size + 1, ptr(p["tok"]),
+                                                   ptr(p["pos"]), ptr(p["level"]), ptr(p["vert"]), ptr(out), stream_ptr()))
         return out
 
-    def embed_codes(self, codes: Tensor) -> Tuple[Tensor, Tensor]:
-        """(grouped_codes, face_codes) as forward_on_codes holds them after :1570."""
-        return self.fine_tokens(codes), self.face_tokens(codes)
+    @torch.no_grad()
+    def face_tokens(self, codes: Tensor = None, append_eos: bool = False, prepend_sos: bool = False, source=None) -> Tensor:
+        """face_codes (b, L // n, dim) of :1570 - one token per complete face; prepend_sos: the sos row(s) first (:1591-1594)."""
+        cp, vs, b, L, dev, keep = self._source(codes, source)
+        p = self._prepare()
+        n = self.num_quantizers * self.num_vertices_per_face
+        eos, lens = self._eos(append_eos, b, dev)
+        Le = L + int(append_eos)
+        n_sos = self.sos_token.shape[0] if prepend_sos else 0
+        out = torch.empty(b, n_sos + Le // n, self.dim, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.meshtok_frontend_face_tokens(cp, None if vs is None else C.byref(vs), b, L, n, self.dim, self.pad_id, eos, ptr(lens),
+                                                   self.codebook_size + 1, ptr(p["tables"]), ptr(p["face_pos"]), ptr(p["gamma"]), ptr(p["beta"]),
+                                                   p["eps"], ptr(p["sos"]) if n_sos else None, n_sos, ptr(out), stream_ptr()))
+        return out
+
+    def embed_codes(self, codes: Tensor, append_eos: bool = False, prepend_sos: bool = False) -> Tuple[Tensor, Tensor]:
+        """(grouped_codes, face_codes) as forward_on_codes holds them after :1570 (after :1594 with prepend_sos)."""
+        return self.fine_tokens(codes, append_eos), self.face_tokens(codes, append_eos, prepend_sos)
+
+    def embed_tokenizer_output(self, autoencoder, faces: Tensor, append_eos: bool = False, prepend_sos: bool = False) -> Tuple[Tensor, Tensor]:
+        """embed_codes for the batch `autoencoder` has just tokenized (its last tokenize / forward call on `faces`, padded layout),
+        WITHOUT the (b, nf * nvf, q) int64 code tensor in between: the kernels read the per-vertex codes and the face / vertex maps
+        the tokenizer left in its workspace ("codes -> first transformer input" without writing the codes to HBM)."""
+        src = (autoencoder, faces)
+        return self.fine_tokens(None, append_eos, src), self.face_tokens(None, append_eos, prepend_sos, src)
 
     forward = embed_codes

@@ -7,8 +7,10 @@ The product path (meshgpt_pytorch_b200/frontend.py + csrc/frontend.cu) never doe
 Follows /root/reference/meshgpt_pytorch/meshgpt_pytorch.py:
     MeshTransformer.__init__      :1140-1165 (codebook_size, eos_token_id, token_embed, quantize_level_embed, vertex_embed,
                                    abs_pos_emb, max_seq_len), :1191-1194 (to_face_tokens), :1254 (pad_id)
-    forward_on_codes              :1526-1570  pad -> 0, token_embed, + abs_pos_emb, + level embed, + vertex embed, zero-pad to a whole
+    forward_on_codes              :1506-1518  append_eos: the eos id at the first pad position of a one-longer sequence
+                                  :1526-1570  pad -> 0, token_embed, + abs_pos_emb, + level embed, + vertex embed, zero-pad to a whole
                                    number of faces, group per face, to_face_tokens on the complete faces
+                                  :1591-1594  the sos token(s) in front of the face tokens (no kv cache)
 
 PINNED: `reference_lines()` below executes the reference's OWN statements :1526-1570 (located with `ast` in the reference source,
 compiled in memory, nothing copied) with this module standing in for `self`; tests/golden/frontend_own_code.pt holds their
@@ -28,14 +30,16 @@ from torch import Tensor, nn
 
 REFERENCE_ROOT = os.environ.get("MESHTOK_REFERENCE_ROOT", "/root/reference")
 FIRST_LINE, LAST_LINE = 1526, 1570
+EOS_FIRST_LINE = 1506          # `if append_eos:` (:1506-1518); `if return_loss:` (:1522-1524) lies between and runs with return_loss = False
 
 
 class OracleTokenFrontEnd(nn.Module):
     """The parameters of MeshTransformer that :1526-1570 touch, under the reference's names."""
 
     def __init__(self, *, codebook_size: int = 16384, num_quantizers: int = 2, quads: bool = False, dim: int = 512,
-                 max_seq_len: int = 8192, pad_id: int = -1):
+                 max_seq_len: int = 8192, pad_id: int = -1, num_sos_tokens: int = 1):
         super().__init__()
+        self.sos_token = nn.Parameter(torch.randn(num_sos_tokens, dim))                 # :1148-1152
         self.num_vertices_per_face = 4 if quads else 3                                  # :1131
         self.codebook_size = codebook_size                                              # :1140
         self.num_quantizers = num_quantizers                                            # :1141
@@ -52,9 +56,27 @@ class OracleTokenFrontEnd(nn.Module):
         self.dim = dim
 
     @torch.no_grad()
-    def forward(self, codes: Tensor) -> Tuple[Tensor, Tensor]:
-        """codes (b, L) int64 -> (grouped_codes (b, ceil(L / n), n, dim), face_codes (b, L // n, dim)), n = nvf * Q."""
+    def append_eos(self, codes: Tensor) -> Tensor:
+        """:1506-1518: (b, L) -> (b, L + 1), the eos id at the first pad position of every row."""
+        code_lens = ((codes == self.pad_id).cumsum(dim=-1) == 0).sum(dim=-1)             # :1509
+        out = torch.nn.functional.pad(codes, (0, 1), value=0)                            # :1511
+        out[torch.arange(codes.shape[0]), code_lens] = self.eos_token_id                 # :1513-1518
+        return out
+
+    @torch.no_grad()
+    def forward(self, codes: Tensor, append_eos: bool = False, prepend_sos: bool = False) -> Tuple[Tensor, Tensor]:
+        """codes (b, L) int64 -> (grouped_codes (b, ceil(L / n), n, dim), face_codes (b, L // n, dim)), n = nvf * Q;
+        with append_eos L counts the eos; with prepend_sos face_codes carries the sos rows first (:1591-1594)."""
         assert codes.shape[-1] <= self.max_seq_len                                       # :1502
+        if append_eos:
+            codes = self.append_eos(codes)
+        g, f = self._embed(codes)
+        if prepend_sos:
+            f = torch.cat([self.sos_token[None].expand(f.shape[0], -1, -1), f], dim=1)   # :1593-1594
+        return g, f
+
+    @torch.no_grad()
+    def _embed(self, codes: Tensor) -> Tuple[Tensor, Tensor]:
         x = codes.masked_fill(codes == self.pad_id, 0)                                   # :1528
         x = self.token_embed(x)                                                          # :1529
         code_len = x.shape[1]
@@ -79,23 +101,24 @@ def reference_available() -> bool:
 
 
 @torch.no_grad()
-def reference_lines(module: OracleTokenFrontEnd, codes: Tensor) -> Tuple[Tensor, Tensor]:
-    """Runs the reference's statements :1526-1570 of MeshTransformer.forward_on_codes, as they stand in its source, with `module`
-    as `self`.  Container only (needs /root/reference)."""
+def reference_lines(module: OracleTokenFrontEnd, codes: Tensor, append_eos: bool = False) -> Tuple[Tensor, Tensor]:
+    """Runs the reference's statements :1526-1570 of MeshTransformer.forward_on_codes (with append_eos: from :1506 on, i.e. including
+    its `if append_eos:` block), as they stand in its source, with `module` as `self`.  Container only (needs /root/reference)."""
     from einops import rearrange, repeat
     path = os.path.join(REFERENCE_ROOT, "meshgpt_pytorch", "meshgpt_pytorch.py")
     src = open(path).read()
     tree = ast.parse(src)
     cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "MeshTransformer")
     fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "forward_on_codes")
-    body = [st for st in fn.body if FIRST_LINE <= st.lineno and st.end_lineno <= LAST_LINE]
-    assert body and body[0].lineno == 1528 and body[-1].end_lineno == LAST_LINE, "the reference source moved: re-derive the line range"
+    first = EOS_FIRST_LINE if append_eos else FIRST_LINE
+    body = [st for st in fn.body if first <= st.lineno and st.end_lineno <= LAST_LINE]
+    assert body and body[0].lineno == (1506 if append_eos else 1528) and body[-1].end_lineno == LAST_LINE, "the reference source moved: re-derive the line range"
     helpers = {}
     for name in ("divisible_by", "pad_at_dim", "pad_to_length"):
         node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
         exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), helpers)
-    env = dict(helpers, self=module, codes=codes, device=codes.device, rearrange=rearrange, repeat=repeat, ceil=ceil, torch=torch,
-               F=torch.nn.functional)
+    env = dict(helpers, self=module, codes=codes.clone(), device=codes.device, rearrange=rearrange, repeat=repeat, ceil=ceil, torch=torch,
+               F=torch.nn.functional, append_eos=append_eos, return_loss=False, batch=codes.shape[0], exists=lambda v: v is not None)
     helpers["F"] = torch.nn.functional
     exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), env)
     return env["grouped_codes"], env["face_codes"]

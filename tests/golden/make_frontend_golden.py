@@ -18,6 +18,9 @@ CASES = {   # name -> (constructor keywords, batch, code length, trailing pads i
     "tri_partial": (dict(codebook_size=64, num_quantizers=2, quads=False, dim=32, max_seq_len=96), 2, 41, 5),
     "quad_q3": (dict(codebook_size=32, num_quantizers=3, quads=True, dim=32, max_seq_len=120), 2, 60, 13),
     "eos_token": (dict(codebook_size=16, num_quantizers=2, quads=False, dim=32, max_seq_len=24), 2, 19, 0),
+    # append_eos (:1506-1518, executed from the reference source too): a full row (eos lands in the extra column) and a padded one
+    "append_eos": (dict(codebook_size=64, num_quantizers=2, quads=False, dim=32, max_seq_len=96), 3, 36, 8),
+    "append_eos_partial": (dict(codebook_size=32, num_quantizers=3, quads=True, dim=32, max_seq_len=120), 2, 47, 20),
 }
 
 
@@ -33,8 +36,9 @@ def main():
             codes[1, L - pads:] = -1
         if name == "eos_token":
             codes[0, L - 1] = kw["codebook_size"]                                  # eos id = codebook_size (:1143) is a valid row of token_embed
-        grouped, face = FO.reference_lines(m, codes)
-        out[name] = dict(kwargs=kw, state_dict=m.state_dict(), codes=codes, grouped_codes=grouped, face_codes=face)
+        eos = name.startswith("append_eos")
+        grouped, face = FO.reference_lines(m, codes, append_eos=eos)
+        out[name] = dict(kwargs=kw, state_dict=m.state_dict(), codes=codes, grouped_codes=grouped, face_codes=face, append_eos=eos)
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "frontend_own_code.pt")
     torch.save(out, path)
     print(path, os.path.getsize(path), "bytes")

@@ -15,16 +15,17 @@ def fx():
     return torch.load(os.path.join(GOLDEN_DIR, "frontend_own_code.pt"))
 
 
-@pytest.mark.parametrize("name", ["tri_whole", "tri_partial", "quad_q3", "eos_token"])
+@pytest.mark.parametrize("name", ["tri_whole", "tri_partial", "quad_q3", "eos_token", "append_eos", "append_eos_partial"])
 def test_front_end_golden(fx, name):
     case = fx[name]
     m = FO.OracleTokenFrontEnd(**case["kwargs"]).eval()
     m.load_state_dict(case["state_dict"])                       # the reference's key names, strict
-    grouped, face = m(case["codes"])
+    eos = bool(case.get("append_eos", False))                   # (those fixtures ran the reference's own `if append_eos:` block too)
+    grouped, face = m(case["codes"], append_eos=eos)
     assert torch.equal(grouped, case["grouped_codes"])           # same torch CPU ops in the same order: bit for bit
     assert torch.equal(face, case["face_codes"])
     n = m.num_quantizers * m.num_vertices_per_face
-    L = case["codes"].shape[1]
+    L = case["codes"].shape[1] + int(eos)
     assert grouped.shape[1] == -(-L // n) and face.shape[1] == L // n
     if L % n:                                                    # the zero padding of the incomplete last face (:1560)
         assert float(grouped[:, -1, L % n:].abs().max()) == 0.0
@@ -50,3 +51,7 @@ def test_restatement_equals_reference_lines_live():
         want_g, want_f = FO.reference_lines(m, codes)
         got_g, got_f = m(codes)
         assert torch.equal(got_g, want_g) and torch.equal(got_f, want_f)
+        if L < 600:                                                  # append_eos (:1506-1518) executed from the reference source as well
+            want_g, want_f = FO.reference_lines(m, codes, append_eos=True)
+            got_g, got_f = m(codes, append_eos=True)
+            assert torch.equal(got_g, want_g) and torch.equal(got_f, want_f)
