@@ -151,9 +151,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
           // the tile's last stage also brings its extra K block (|e|^2 columns).  Its ring slot was used EX_RING tiles ago (see Smem2),
           // and this stage slot only became free after that tile's MMAs - the extra one included - had completed.
           const bool last = kc == KCH - 1;
+          if (DBG == 2 && it >= (uint32_t)STAGES) {   // experiment: no codebook traffic after the ring's first fill (the MMAs re-read stale stages)
+            mbar_arrive(&b_full[s]);
+          } else {
           mbar_arrive_expect_tx(&b_full[s], STAGE_BYTES + (last ? RVQ_EXTRA_BYTES : 0));
           bulk_g2s(sB + s * STAGE_BYTES, src + (size_t)kc * STAGE_BYTES, STAGE_BYTES, &b_full[s]);
           if (last) bulk_g2s(sX + (tile_it % L::EX_RING) * RVQ_EXTRA_BYTES, src + (size_t)KCH * STAGE_BYTES, RVQ_EXTRA_BYTES, &b_full[s]);
+          }
         }
         __syncwarp();
       }
@@ -194,7 +198,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
               const uint64_t db = make_smem_desc_sw128(sB_addr + s * STAGE_BYTES + k16 * 32);
               umma_f16_pair(tmem_base + buf * N_PAIR, da, db, idesc, (kc | k16) != 0 ? 1u : 0u);
             }
-            if (kc == KCH - 1) {   // extra K block: + c_row * (hi, lo)(-kappa |e|^2)  ->  acc = -(rscale * escale / 2) * s~
+            if (kc == KCH - 1 && DBG != 3) {   // extra K block: + c_row * (hi, lo)(-kappa |e|^2)  ->  acc = -(rscale * escale / 2) * s~   (DBG 3: experiment without it)
               const uint64_t da = make_smem_desc(sA_addr + L::A_MAIN, 128, RVQ_EXTRA_SBO);
               const uint64_t db = make_smem_desc(smem_u32(sX) + (acc_it % L::EX_RING) * RVQ_EXTRA_BYTES, 128, RVQ_EXTRA_SBO);
               umma_f16_pair(tmem_base + buf * N_PAIR, da, db, idesc, 1u);
@@ -360,6 +364,8 @@ int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, con
       static int debug = -1;
       if (debug < 0) { const char* e = getenv("MESHTOK_RVQ_DEBUG"); debug = e ? atoi(e) : 0; }
       if (debug == 1) return launch_search2<192, 1>(a, grid, stream);
+      if (debug == 2) return launch_search2<192, 2>(a, grid, stream);
+      if (debug == 3) return launch_search2<192, 3>(a, grid, stream);
 #endif
       return launch_search2<192, 0>(a, grid, stream);
     }

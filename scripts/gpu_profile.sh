@@ -14,7 +14,7 @@ echo "launch list exit $?"; tail -2 gpurun_out/ncu_list_$tag.log | cut -c1-300
 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:$kre -f -o gpurun_out/prof_${tag} $CMD > gpurun_out/ncu_full_$tag.log 2>&1
 echo "full capture exit $?"; tail -2 gpurun_out/ncu_full_$tag.log | cut -c1-300
 ncu -i gpurun_out/prof_${tag}.ncu-rep --page raw --csv > gpurun_out/prof_${tag}_raw.csv 2> /dev/null
-for k in rvq_tc2_search linear_tc_pair linear_tc_kernel topology gather_mean face_ rescore; do
+for k in rvq_tc2_search linear_tc_pair linear_tc_kernel topology gather_mean face_sum face_bins rescore scatter_mean; do
   ncu -i gpurun_out/prof_${tag}.ncu-rep --page source --csv -k regex:$k -c 1 > gpurun_out/prof_${tag}_src_$k.csv 2> /dev/null
 done
 sz=$(stat -c %s gpurun_out/prof_${tag}.ncu-rep); if [ "$sz" -gt 30000000 ]; then rm gpurun_out/prof_${tag}.ncu-rep; echo "dropped ${sz}-byte report (CSV exports kept)"; fi
