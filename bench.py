@@ -744,6 +744,7 @@ def main():
     ap.add_argument("--precomputed-edges", action="store_true",
                     help="pass face_edges (derived once, outside the timed region) instead of deriving them inside tokenize (BASELINE config 4)")
     ap.add_argument("--no-graph", action="store_true", help="launch the pipeline kernel by kernel instead of replaying its CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true", help="experiments: skip the host-to-host measurement (the line then has no e2e: not a bench value)")
     ap.add_argument("--ncu-window", type=int, default=0,
                     help="profiling aid: after the warm-up run this many device steps between cudaProfilerStart/Stop and exit "
                          "(use with ncu --profile-from-start off); prints no bench line")
@@ -769,7 +770,7 @@ def main():
     model = build_model(args.workload, oracle)
     sampler = ClockSampler(local) if rank == 0 and not args.ncu_window else None
     head = measure_workload(ctx, args.workload, oracle, model, args.steps, args.warmup, precomputed_edges=args.precomputed_edges,
-                            want_cpu=not args.no_cpu_baseline, cpu_meshes=args.cpu_meshes, hist_every_step=args.hist_every_step,
+                            want_e2e=not args.no_e2e, want_cpu=not args.no_cpu_baseline, cpu_meshes=args.cpu_meshes, hist_every_step=args.hist_every_step,
                             no_hist=args.no_hist, no_graph=args.no_graph, pipeline_depth=args.pipeline_depth, headline=True, sampler=sampler)
     if args.ncu_window:
         if rank == 0:
