@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define MESHTOK_ABI_VERSION 2
+#define MESHTOK_ABI_VERSION 3
 
 typedef void* meshtok_stream_t; /* cudaStream_t */
 
@@ -235,11 +235,33 @@ typedef struct meshtok_pipeline_result {
   int32_t slot;
   int32_t status;          /* MESHTOK_WS_STATUS_* bits of that batch; non-zero: its codes are not valid */
   const int64_t* codes_host;
+  int64_t tokens;          /* ragged pipelines: code rows (faces * nvf) of that batch in codes_host; 0 for padded pipelines */
 } meshtok_pipeline_result;
 int meshtok_pipeline_create(const meshtok_model* model, int B, int F, int V, int64_t pad_id, int64_t edge_capacity, int64_t* histogram,
                             const meshtok_pipeline_slot* slots, int depth, meshtok_pipeline** out);
 int meshtok_pipeline_submit(meshtok_pipeline* p, const float* vertices_host, const int64_t* faces_host, meshtok_pipeline_result* finished);
 int meshtok_pipeline_drain(meshtok_pipeline* p, meshtok_pipeline_result* results /* depth entries */, int* n);
+/* The same ring for the RAGGED layout (a CSR of meshes, see meshtok_tokenize_args): every slot holds staging for up to max_meshes meshes,
+ * cap_faces face rows and cap_vertices vertex rows, and ONE graph captured on those capacities that serves batches of any composition.
+ * Before _create_ragged each slot's device staging (vertices, faces, offsets = [face_offsets (max_meshes + 1) | vertex_offsets
+ * (max_meshes + 1)] int32) must hold a valid example batch.  submit_ragged copies only the live part of a batch (offsets_host is
+ * pinned scratch of 2 * (max_meshes + 1) int32 per slot) and hands back flat codes (result.tokens rows of Q int64). */
+typedef struct meshtok_pipeline_ragged_slot {
+  float* vertices;         /* device (cap_vertices, 3) */
+  int64_t* faces;          /* device (cap_faces, nvf), mesh-local vertex ids */
+  int32_t* offsets;        /* device 2 * (max_meshes + 1) */
+  int64_t* codes;          /* device (cap_faces * nvf, Q) */
+  void* workspace;         /* device, >= meshtok_tokenize_workspace_bytes_ragged(model, max_meshes, F, V, 0, edge_capacity, cap_faces, cap_vertices) */
+  size_t workspace_bytes;
+  int64_t* codes_host;     /* pinned host (cap_faces * nvf, Q) */
+  int32_t* status_host;    /* pinned host int32[4] */
+  int32_t* offsets_host;   /* pinned host 2 * (max_meshes + 1) */
+} meshtok_pipeline_ragged_slot;
+int meshtok_pipeline_create_ragged(const meshtok_model* model, int max_meshes, int F, int V, int64_t cap_faces, int64_t cap_vertices, int64_t pad_id,
+                                   int64_t edge_capacity, int64_t* histogram, const meshtok_pipeline_ragged_slot* slots, int depth,
+                                   meshtok_pipeline** out);
+int meshtok_pipeline_submit_ragged(meshtok_pipeline* p, const float* vertices_host, const int64_t* faces_host, const int32_t* face_offsets_host,
+                                   const int32_t* vertex_offsets_host, int n_meshes, meshtok_pipeline_result* finished);
 meshtok_stream_t meshtok_pipeline_stream(meshtok_pipeline* p, int slot);   /* the slot's cudaStream_t (to order caller events against it) */
 int meshtok_pipeline_destroy(meshtok_pipeline* p);
 

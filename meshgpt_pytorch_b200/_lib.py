@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MESHTOK_LIBRARY") or os.path.join(HERE, "lib", "libmeshtok.so")   # override: A/B of two builds
 
 MAX_SAGE_LAYERS = 8
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 WS_STATUS_VERTEX_RANGE = 1
 WS_STATUS_EDGE_OVERFLOW = 2
@@ -64,7 +64,14 @@ class PipelineSlot(C.Structure):
 
 
 class PipelineResult(C.Structure):
-    _fields_ = [("ticket", C.c_int64), ("slot", C.c_int32), ("status", C.c_int32), ("codes_host", C.c_void_p)]
+    _fields_ = [("ticket", C.c_int64), ("slot", C.c_int32), ("status", C.c_int32), ("codes_host", C.c_void_p), ("tokens", C.c_int64)]
+
+
+class PipelineRaggedSlot(C.Structure):
+    _fields_ = [
+        ("vertices", C.c_void_p), ("faces", C.c_void_p), ("offsets", C.c_void_p), ("codes", C.c_void_p), ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t), ("codes_host", C.c_void_p), ("status_host", C.c_void_p), ("offsets_host", C.c_void_p),
+    ]
 
 
 class VertexCodeSource(C.Structure):
@@ -137,6 +144,9 @@ SIGNATURES = {
     "meshtok_pipeline_create": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(PipelineSlot), C.c_int,
                                           C.POINTER(C.c_void_p)]),
     "meshtok_pipeline_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(PipelineResult)]),
+    "meshtok_pipeline_create_ragged": (C.c_int, [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                                 C.POINTER(PipelineRaggedSlot), C.c_int, C.POINTER(C.c_void_p)]),
+    "meshtok_pipeline_submit_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PipelineResult)]),
     "meshtok_pipeline_drain": (C.c_int, [C.c_void_p, C.POINTER(PipelineResult), C.POINTER(C.c_int)]),
     "meshtok_pipeline_stream": (C.c_void_p, [C.c_void_p, C.c_int]),
     "meshtok_pipeline_destroy": (C.c_int, [C.c_void_p]),

@@ -665,6 +665,11 @@ class MeshAutoencoder(nn.Module):
         """Multi-buffered host-to-host tokenization for a stream of equally shaped batches (see HostPipeline)."""
         return HostPipeline(self, vertices, faces, depth, histogram)
 
+    def host_pipeline_ragged(self, max_meshes: int, max_faces: int, max_vertices: int, max_total_faces: int, max_total_vertices: int,
+                             depth: int = 2, histogram: Optional[Tensor] = None) -> "RaggedHostPipeline":
+        """The same ring for the ragged layout: one graph per slot serves batches of any composition (see RaggedHostPipeline)."""
+        return RaggedHostPipeline(self, max_meshes, max_faces, max_vertices, max_total_faces, max_total_vertices, depth, histogram)
+
     # ---- host-buffer entry (what a CPU-side caller of the reference would do) ---------------------
     @torch.no_grad()
     def tokenize_host(self, vertices: Tensor, faces: Tensor, face_edges: Optional[Tensor] = None, pinned_out: Optional[Tensor] = None):
@@ -894,6 +899,108 @@ class HostPipeline:
         assert tuple(vertices.shape) == (B, V, 3) and tuple(faces.shape[:2]) == (B, F), "batch shape differs from the one the pipeline was built for"
         check(lib.meshtok_pipeline_submit(self._h, ptr(vertices), ptr(faces), C.byref(self._res)))
         self._keep_host = (vertices, faces)          # the copies may still be reading them
+        self.n += 1
+        return self._result(self._res)
+
+    def drain(self):
+        res = (_lib.PipelineResult * self.depth)()
+        n = C.c_int()
+        check(lib.meshtok_pipeline_drain(self._h, res, C.byref(n)))
+        return [self._result(res[i]) for i in range(n.value)]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.meshtok_pipeline_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RaggedHostPipeline:
+    """HostPipeline for the ragged layout (a CSR of meshes): host buffers in, flat host codes out, `depth` batches in
+    flight.  Every slot holds ONE CUDA graph captured on the stated capacities; a submit copies only the live part of the batch
+    (vertices, faces, 2 * (max_meshes + 1) offsets), launches the graph and copies back the live code rows - one C call
+    (meshtok_pipeline_submit_ragged), no padding on the host, no pad tokens over the bus.
+
+        pipe = model.host_pipeline_ragged(256, 800, 441, 256 * 500, 256 * 300)
+        for b in loader:                                   # data.ragged_collate output: pinned host tensors
+            done = pipe.submit(b["vertices"], b["faces"], b["face_offsets"], b["vertex_offsets"])   # -> (ticket, codes (sum nf * nvf, Q)) or None
+        for ticket, codes in pipe.drain(): ...
+
+    The codes handed back are a view of the slot's pinned buffer (overwritten `depth` submits later)."""
+
+    def __init__(self, model: MeshAutoencoder, max_meshes: int, max_faces: int, max_vertices: int, max_total_faces: int,
+                 max_total_vertices: int, depth: int = 2, histogram: Optional[Tensor] = None):
+        prep = model._prepare()
+        dev = prep["device"]
+        model.eval()
+        self.model, self.depth, self.nvf, self.Q = model, int(depth), model.num_vertices_per_face, model.num_quantizers
+        self.B, self.F, self.V = int(max_meshes), max(int(max_faces), 1), max(int(max_vertices), self.nvf)
+        self.cap_faces = min(int(max_total_faces), self.B * self.F)
+        self.cap_vertices = min(int(max_total_vertices), self.B * self.V)
+        assert self.depth >= 1 and self.B > 0 and self.cap_faces > 0 and self.cap_vertices >= self.nvf
+        cap = max(1024, model.edge_slots_per_face * self.cap_faces)
+        nbytes = C.c_size_t()
+        check(lib.meshtok_tokenize_workspace_bytes_ragged(C.byref(prep["model"]), self.B, self.F, self.V, 0, cap, self.cap_faces, self.cap_vertices,
+                                                          C.byref(nbytes)))
+        slots = (_lib.PipelineRaggedSlot * self.depth)()
+        self._keep, self.outs = [], []
+        B1 = self.B + 1
+        with torch.cuda.device(dev):
+            for s in range(self.depth):
+                v = torch.zeros((self.cap_vertices, 3), dtype=torch.float32, device=dev)
+                f = torch.zeros((self.cap_faces, self.nvf), dtype=torch.int64, device=dev)
+                off = torch.zeros(2 * B1, dtype=torch.int32, device=dev)
+                # the batch the graph is captured on: one face in mesh 0, every other mesh empty
+                v[: self.nvf] = torch.eye(4, 3, device=dev)[: self.nvf] * 0.5
+                f[0] = torch.arange(self.nvf, device=dev)
+                off[1:B1] = 1
+                off[B1 + 1:] = self.nvf
+                codes = torch.empty((self.cap_faces * self.nvf, self.Q), dtype=torch.int64, device=dev)
+                ws = torch.zeros(nbytes.value, dtype=torch.uint8, device=dev)
+                out = torch.empty(codes.shape, dtype=torch.int64).pin_memory()
+                st = torch.zeros(4, dtype=torch.int32).pin_memory()
+                oh = torch.zeros(2 * B1, dtype=torch.int32).pin_memory()
+                self._keep += [v, f, off, codes, ws, st, oh]
+                self.outs.append(out)
+                sl = slots[s]
+                sl.vertices, sl.faces, sl.offsets, sl.codes = ptr(v), ptr(f), ptr(off), ptr(codes)
+                sl.workspace, sl.workspace_bytes = ptr(ws), ws.numel()
+                sl.codes_host, sl.status_host, sl.offsets_host = ptr(out), ptr(st), ptr(oh)
+            torch.cuda.synchronize(dev)
+            handle = C.c_void_p()
+            check(lib.meshtok_pipeline_create_ragged(C.byref(prep["model"]), self.B, self.F, self.V, self.cap_faces, self.cap_vertices, int(model.pad_id),
+                                                     cap, ptr(histogram), slots, self.depth, C.byref(handle)))
+        self._h = handle
+        self._histogram = histogram
+        self._res = _lib.PipelineResult()
+        self._keep_host = [None] * self.depth
+        self.n = 0
+
+    def streams(self):
+        return [torch.cuda.ExternalStream(lib.meshtok_pipeline_stream(self._h, s)) for s in range(self.depth)]
+
+    def _result(self, r):
+        if r.ticket < 0:
+            return None
+        if r.status:
+            MeshAutoencoder._raise_on_status(int(r.status))
+        return int(r.ticket), self.outs[r.slot][: int(r.tokens)]
+
+    def submit(self, vertices: Tensor, faces: Tensor, face_offsets, vertex_offsets):
+        fo = torch.as_tensor(face_offsets, dtype=torch.int32).contiguous()
+        vo = torch.as_tensor(vertex_offsets, dtype=torch.int32).contiguous()
+        assert not vertices.is_cuda and not faces.is_cuda and not fo.is_cuda and not vo.is_cuda, "RaggedHostPipeline takes HOST tensors"
+        assert vertices.dtype == torch.float32 and faces.dtype == torch.int64 and vertices.is_contiguous() and faces.is_contiguous()
+        n = fo.numel() - 1
+        assert vo.numel() == n + 1 and vertices.ndim == 2 and vertices.shape[1] == 3 and faces.ndim == 2 and faces.shape[1] == self.nvf
+        assert int(fo[-1]) == faces.shape[0] and int(vo[-1]) == vertices.shape[0], "the last offsets must equal the row counts"
+        check(lib.meshtok_pipeline_submit_ragged(self._h, ptr(vertices), ptr(faces), ptr(fo), ptr(vo), n, C.byref(self._res)))
+        self._keep_host[self.n % self.depth] = (vertices, faces)     # the slot's copies may still be reading them
         self.n += 1
         return self._result(self._res)
 

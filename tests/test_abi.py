@@ -32,7 +32,8 @@ def test_struct_layout_matches_header():
     assert C.sizeof(_lib.SageLayer) == 8 + 6 * 8
     assert _lib.Model.sage.size == 8 * C.sizeof(_lib.SageLayer)
     assert C.sizeof(_lib.TokenizeArgs) == 4 * 8 + 4 * 4 + 2 * 8 + 5 * 8 + 4 * 4 + 6 * 8
-    assert C.sizeof(_lib.PipelineSlot) == 7 * 8 and C.sizeof(_lib.PipelineResult) == 8 + 4 + 4 + 8
+    assert C.sizeof(_lib.PipelineSlot) == 7 * 8 and C.sizeof(_lib.PipelineResult) == 8 + 4 + 4 + 8 + 8
+    assert C.sizeof(_lib.PipelineRaggedSlot) == 9 * 8
     assert C.sizeof(_lib.Taps) == (7 + 8 + 3) * 8
 
 

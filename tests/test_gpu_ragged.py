@@ -167,6 +167,51 @@ def test_ragged_graph_serves_batches_of_any_composition():
         g(*ragged_cuda(v, f))                                                                      # 576 faces > 500
 
 
+def test_ragged_host_pipeline_matches_single_calls():
+    """RaggedHostPipeline (meshtok_pipeline_create_ragged / _submit_ragged): host buffers in, flat host codes out, two and three batches in
+    flight on one graph per slot - every batch equal to the eager ragged call on the same meshes; histogram = bincount over all batches;
+    a bad batch raises when it is handed back and the ring keeps working afterwards."""
+    o, m = make_pair(**dict(SMALL_CFG, use_residual_lfq=False))
+    hist = torch.zeros(m.num_quantizers, m.codebook_size, dtype=torch.int64, device="cuda")
+    compositions = ([130, 61, 8, 1, 144], [144], [5, 5, 5, 5, 5, 5], [77, 144, 144, 100], [1], [144, 144, 144])
+    for depth in (2, 3):
+        hist.zero_()
+        pipe = m.host_pipeline_ragged(6, 144, 90, 500, 400, depth=depth, histogram=hist)
+        want, got = [], {}
+        for i, counts in enumerate(compositions):
+            v, f = synth.ragged_batch("tri", 9, 8, counts, [10 * i + k for k in range(len(counts))])
+            rv, rf, fo, vo = ragged_cuda(v, f)
+            want.append(m.tokenize_ragged(rv, rf, fo, vo).cpu())
+            done = pipe.submit(rv.cpu().pin_memory(), rf.cpu().pin_memory(), fo.cpu(), vo.cpu())
+            if done is not None:
+                got[done[0]] = done[1].clone()
+        for ticket, codes in pipe.drain():
+            got[ticket] = codes.clone()
+        assert sorted(got) == list(range(len(compositions)))
+        for i, w in enumerate(want):
+            assert got[i].shape == w.shape and torch.equal(got[i], w), (depth, compositions[i])
+        allc = torch.cat(want)
+        assert torch.equal(hist.cpu(), torch.stack([torch.bincount(allc[:, q], minlength=m.codebook_size) for q in range(m.num_quantizers)]))
+        # an empty batch, then a vertex id that reaches into the next mesh: reported with the batch, not silently tokenized
+        assert pipe.submit(torch.zeros(0, 3).pin_memory(), torch.zeros(0, 3, dtype=torch.int64).pin_memory(), torch.zeros(1, dtype=torch.int32),
+                           torch.zeros(1, dtype=torch.int32)) is None
+        v, f = synth.ragged_batch("tri", 9, 8, [20, 20], [0, 1])
+        rv, rf, fo, vo = ragged_cuda(v, f)
+        bad = rf.cpu().clone()
+        bad[3, 1] = int(vo[1]) + 2
+        pipe.submit(rv.cpu().pin_memory(), bad.pin_memory(), fo.cpu(), vo.cpu())
+        with pytest.raises(Exception):
+            pipe.drain()
+        done = pipe.submit(rv.cpu().pin_memory(), rf.cpu().pin_memory(), fo.cpu(), vo.cpu())
+        res = pipe.drain()
+        assert torch.equal(res[-1][1], m.tokenize_ragged(rv, rf, fo, vo).cpu())
+        with pytest.raises(Exception):
+            v, f = synth.ragged_batch("tri", 9, 8, [144] * 4, [0, 1, 2, 3])
+            rv, rf, fo, vo = ragged_cuda(v, f)
+            pipe.submit(rv.cpu(), rf.cpu(), fo.cpu(), vo.cpu())                          # 576 faces > 500
+        pipe.close()
+
+
 _GROUP_SCRIPT = r"""
 import sys, torch
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
