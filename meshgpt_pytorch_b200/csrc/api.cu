@@ -572,6 +572,10 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     const float* x = w.x0;
     int cur = 0;
     bool xp_ready = false;   // the previous layer's launch already computed this layer's relu(lin(x)) (two linears back to back)
+    // relu(lin(x)) of the current layer.  Where the aggregation is fused into the output linear, that launch GATHERS from these rows while
+    // its second phase writes the next layer's - so the two alternate between w.xp and w.agg (free on the tcgen05 path)
+    float* xp_cur = w.xp;
+    float* xp_other = w.agg;
     for (int l = 0; l < L; ++l) {
       const meshtok_sage_layer& ly = m->sage[l];
       const bool first = l == 0, last = l == L - 1;
@@ -584,21 +588,30 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       // xp = relu(lin(x))
       if (!xp_ready) {
         ProfScope ps(PROF_SAGE_LINEAR, s);
-        if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, w.xp, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc;
+        if ((rc = linear(simt, x, w.img_x[cur], ly.dim_in, nullptr, nullptr, 0, ly.lin_w, ly.lin_w_img, ly.lin_b, xp_cur, ly.dim_in, n_faces_dev, max_rows, true, s)) != MESHTOK_OK) return rc;
       }
       xp_ready = false;
       if ((rc = join_edges()) != MESHTOK_OK) return rc;
-      { ProfScope ps(PROF_SAGE_GATHER, s); if ((rc = launch_gather_mean(w.xp, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s)) != MESHTOK_OK) return rc; }
+      // the next layer's lin reads exactly the rows the output linear writes: both run in one launch, tile by tile
+      const bool b2b = fused && !last && ly.cat_w_img != nullptr && m->sage[l + 1].lin_w_img != nullptr && m->sage[l + 1].dim_in == ly.dim_out &&
+                       linear_tc_b2b_ok(ly.dim_out, mode);
+      // ... and the neighbour aggregation in front of it becomes a role of that launch (gather warps write the A tiles): no aggregate image
+      const bool gather_fused = b2b && w.img_agg != nullptr && linear_tc_gather_ok(ly.dim_in, ly.dim_out, mode);
+      if (!gather_fused) {
+        ProfScope ps(PROF_SAGE_GATHER, s);
+        if ((rc = launch_gather_mean(xp_cur, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s)) != MESHTOK_OK) return rc;
+      }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {
         LinearRowEpilogue epi{mode, first ? m->ln_gamma : nullptr, first ? m->ln_beta : nullptr, w.img_x[cur ^ 1], nullptr, nullptr, 0};
         ProfScope ps(PROF_SAGE_LINEAR, s);
-        // the next layer's lin reads exactly the rows this launch writes: run it in the same launch, tile by tile
-        const bool b2b = !last && ly.cat_w_img != nullptr && m->sage[l + 1].lin_w_img != nullptr && m->sage[l + 1].dim_in == ly.dim_out &&
-                         linear_tc_b2b_ok(ly.dim_out, mode);
         if (b2b) {
+          const LinearGather lg{xp_cur, w.indptr, w.src, a->edge_capacity};
+          float* xp_next = gather_fused ? xp_other : xp_cur;
           if ((rc = launch_linear_tc_b2b(w.img_agg, ly.dim_in, w.img_x[cur], ly.dim_in, ly.cat_w_img, ly.lin_l_b, need_fp32 ? w.layer_out[l] : nullptr,
-                                         ly.dim_out, n_faces_dev, max_rows, &epi, m->sage[l + 1].lin_w_img, m->sage[l + 1].lin_b, w.xp, s)) != MESHTOK_OK) return rc;
+                                         ly.dim_out, n_faces_dev, max_rows, &epi, m->sage[l + 1].lin_w_img, m->sage[l + 1].lin_b, xp_next, s,
+                                         gather_fused ? &lg : nullptr)) != MESHTOK_OK) return rc;
+          if (gather_fused) { xp_other = xp_cur; xp_cur = xp_next; }
           xp_ready = true;
         } else if ((rc = linear(false, nullptr, w.img_agg, ly.dim_in, nullptr, w.img_x[cur], ly.dim_in, ly.cat_w, ly.cat_w_img, ly.lin_l_b,
                                 need_fp32 ? w.layer_out[l] : nullptr, ly.dim_out, n_faces_dev, max_rows, false, s, &epi)) != MESHTOK_OK) return rc;

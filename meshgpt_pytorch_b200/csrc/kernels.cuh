@@ -161,9 +161,20 @@ struct LinearRowEpilogue {
   int row_ssq_parts;
 };
 bool linear_tc_b2b_ok(int N, int norm_mode);   // layer output linear + the next layer's `lin` in one launch
+// Neighbour aggregation fused into the output linear (SAGEConv mean aggregation, call sites meshgpt_pytorch.py:764, :769): the A1 operand
+// (the K1 "agg" columns) is not read from an image but produced inside the launch by gather warps - mean over the in-neighbours
+// src[indptr[r] .. indptr[r + 1]) of the fp32 rows x (M, K1), neighbours added in list order, sum * (1 / count) - written as the
+// split-bf16 shared-memory tile the MMA reads.  The aggregate never goes to global memory.
+struct LinearGather {
+  const float* x;        // (M, K1) fp32 rows, NOT written by this launch
+  const int* indptr;     // (M + 1) face CSR by target
+  const int* src;        // source rows
+  long long cap;         // edges stored in src (lists are cut there)
+};
+bool linear_tc_gather_ok(int K1, int N, int norm_mode);   // the fused aggregation is available for this layer shape (MESHTOK_GATHER_FUSED=0: never)
 int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                          int N, const int* m_dev, int m_max, const LinearRowEpilogue* epi, const void* w2_image, const float* bias2,
-                         float* C2, cudaStream_t stream);
+                         float* C2, cudaStream_t stream, const LinearGather* gather = nullptr);
 int linear_tc_read_trace(long long* out, int n);   // timing experiments, see linear_tc.cu
 int linear_tc_ssq_parts(int N);   // (column parts per pass) * passes of an N-wide tcgen05 linear, at most 16
 int linear_tc_fused_norm_ok(int N, int norm_mode);   // MESHTOK_OK when the fused epilogue covers this width

@@ -48,14 +48,17 @@ constexpr int VEC_MAX_N = 1536;   // widest output (the decoder's 9 x 128 coordi
 // of A and HALF of the W chunk, so the bytes pulled from L2 per MMA cycle drop from (128 + NT) to (128 + NT / 2) rows.
 // ncu on the single-CTA kernel (capture r01h, in the git history of profiles/) had the two widest linears at 10.5 TB/s of L2 -> SM traffic, the
 // measured cap of the L2 slices, with the tensor pipe waiting.
-template <bool PAIR, int CPARTS_>
+// GW = gather warps (0 or 4): warps behind the epilogue warps that PRODUCE the A1 operand tiles of a SAGE output linear in shared memory
+// (mean over the in-neighbours of fp32 rows, see the gather role in linear_tc_body) instead of the producer's bulk copy of an image block.
+template <bool PAIR, int CPARTS_, int GW_ = 0>
 struct Cfg {
   static constexpr int MAX_STAGES = 10;
   static constexpr int CPARTS = CPARTS_;                   // column parts of a pass = epilogue warps per TMEM lane quarter
   static constexpr int EPI_WARPS = 4 * CPARTS;
-  static constexpr int NUM_THREADS = (4 + EPI_WARPS) * 32;
+  static constexpr int GW = GW_;
+  static constexpr int NUM_THREADS = (4 + EPI_WARPS + GW) * 32;
   static constexpr uint32_t BAR_OFF = 0;
-  static constexpr uint32_t EPI_OFF = BAR_OFF + 256;
+  static constexpr uint32_t EPI_OFF = BAR_OFF + (GW ? 384 : 256);
   static constexpr uint32_t XCH_OFF = EPI_OFF + EPI_WARPS * 32 * EPI_LD * 4;      // [2 unit parities][3 sums][CPARTS][128 rows] floats
   static constexpr uint32_t VEC_OFF = XCH_OFF + 2 * 3 * CPARTS * 128 * 4;         // bias (N <= 1024), gamma, beta (N <= 64) staged once per CTA
   static constexpr uint32_t RING_OFF = (VEC_OFF + (VEC_MAX_N + 2 * 64) * 4 + 127) / 128 * 128;
@@ -109,6 +112,12 @@ struct LinArgs {
   long long* am_bins;       // the same shape, int64 (0 where row_valid is 0), or null
   int am_B, am_P, am_lead, am_ncoord;
   float am_lo, am_hi;
+  // fused neighbour aggregation (GW > 0 instantiation, phase 0 of a SAGE output linear): when g_x is set the K1 columns of A are the
+  // mean over the in-neighbours of the fp32 rows g_x (M, K1), produced tile by tile by the gather warps; a1_image is not read
+  const float* g_x;
+  const int* g_indptr;
+  const int* g_src;
+  long long g_cap;
 };
 __host__ __device__ inline int lin_chunks(const LinArgs& a) { return (a.conv ? a.taps : 1) * (a.K1 / KC) + a.K2 / KC; }
 
@@ -165,9 +174,9 @@ struct UnitSeq {   // this CTA (pair)'s units in issue order
 
 // TAIL: the instantiation that carries the norm_mode 3 epilogue (decode path); the tokenizer's linears run the one without it
 // (with the extra epilogue in the same kernel they had 4 registers more and were 1 - 2 % slower)
-template <bool PAIR, int CPARTS, bool TAIL = false>
+template <bool PAIR, int CPARTS, bool TAIL = false, int GW = 0>
 __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
-  using G = Cfg<PAIR, CPARTS>;
+  using G = Cfg<PAIR, CPARTS, GW>;
   constexpr int EPI_WARPS = G::EPI_WARPS;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int nphase = g.nphase;
@@ -183,6 +192,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   uint64_t* acc_empty = acc_full + 2;           // [2]       (in a pair the leader's are the ones waited on)
   uint64_t* a_done = acc_empty + 2;             // [4]       phase-0 tile i of this CTA is in global memory (epilogue warps -> producer)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_done + 4);
+  uint64_t* gfull = a_done + 5;                 // [STAGES]  (GW > 0) the gather warps' A tile of the stage is written (both CTAs of a pair -> leader)
 
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
@@ -199,6 +209,8 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       mbar_init(&acc_empty[i], (PAIR ? 2 : 1) * EPI_WARPS);
     }
     for (int i = 0; i < 4; ++i) mbar_init(&a_done[i], 1);
+    if (GW > 0)
+      for (int i = 0; i < STAGES; ++i) mbar_init(&gfull[i], PAIR ? 2 : 1);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -254,10 +266,11 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
       for (int kc = 0, ka = 0, tap = 0; kc < kchunks; ++kc, ++it) {
         mbar_wait(&empty[s], ph ^ 1);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&full[s], (have_a ? a_blk : 0u) + 2 * w_mine);
+          const bool copy_a = have_a && !(GW > 0 && a.g_x != nullptr && ka < kch1);   // (else: the gather warps write the A tile)
+          mbar_arrive_expect_tx(&full[s], (copy_a ? a_blk : 0u) + 2 * w_mine);
           uint8_t* stage = ring + s * stage_bytes;
           const uint8_t* asrc = ka < kch1 ? a1src + (size_t)ka * a_blk : a2src + (size_t)(ka - kch1) * IMG_BLOCK;
-          if (have_a) bulk_g2s(stage, asrc, a_blk, &full[s]);
+          if (copy_a) bulk_g2s(stage, asrc, a_blk, &full[s]);
           const uint8_t* wc = wsrc + (size_t)(a.conv ? tap * kch1 + ka : kc) * (2 * w_part);
           if (PAIR) {
             bulk_g2s(stage + a_slot, wc, w_mine, &full[s]);
@@ -284,11 +297,13 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
     if (leader) {
       const uint32_t s0 = smem_u32(ring);
       uint32_t s = 0, ph = 0;
+      uint32_t gpar = 0;   // bit s: parity of the next completion of gfull[s] (only the gather chunks complete it)
       for (int j = 0; j < n_units; ++j) {
         int phase, grp, pass, ti;
         seq.get(j, phase, grp, pass, ti);
         const LinArgs& a = g.p[phase];
         const int kchunks = lin_chunks(a);
+        const int g_chunks = (GW > 0 && a.g_x != nullptr) ? a.K1 / KC : 0;   // the first g_chunks A tiles come from the gather warps
         const int taps = a.conv ? a.taps : 1;
         const uint32_t rows_h = (uint32_t)(M_TILE + 2 * a.halo);
         const uint32_t a_lbo = a.conv ? rows_h * 16 : 128, a_sbo = a.conv ? 128 : SBO;   // halo image: consecutive rows 16 B apart
@@ -304,6 +319,11 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         const uint32_t d = tmem_base + buf * NT_MAX;
         for (int kc = 0, tap = 0; kc < kchunks; ++kc) {
           mbar_wait(&full[s], ph);
+          if (GW > 0 && kc < g_chunks) {
+            if (PAIR) mbar_wait_cluster(&gfull[s], (gpar >> s) & 1u);
+            else mbar_wait(&gfull[s], (gpar >> s) & 1u);
+            gpar ^= 1u << s;
+          }
           tcgen05_fence_after();
           if (kc == 0 && lane == 0) LT_STAMP(4, j);   // MMA: first stage of the unit has landed
           if (elect_one()) {
@@ -354,7 +374,7 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
         mbar_arrive_cluster_relaxed(remote);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
     // ===== epilogue (both CTAs of a pair, each on its own 128 rows) =====
     const int ew = warp - 4;
     const int q = warp & 3;
@@ -685,6 +705,125 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
     }
   }
 
+  else if (GW > 0 && warp >= 4 + EPI_WARPS) {
+    // ===== gather warps: the aggregated-neighbour half of A, produced in shared memory (SAGEConv mean aggregation) =====
+    // Tile = this CTA's 128 rows; per 32-column chunk a warp takes every GW-th 8-row group: lane = (row & 7) + 8 * (8-column group), so a
+    // warp's 16-byte stores fill 512 contiguous bytes of the canonical K-major tile (no bank conflicts) and a row's four lanes read one
+    // 128-byte line per neighbour.  The CSR entries of a lane's rows (first four sources, count, 1 / count) are read once per tile and
+    // kept in registers for all chunks; neighbours are added in list order, then sum * (1 / count): the same values, bit for bit, as
+    // gather_mean_smem_wide_kernel writes into the aggregate image.  x rows come through L1 (neighbouring rows share their sources).
+    constexpr int STEPS = 16 / (GW > 0 ? GW : 1);
+    const int gw = warp - (4 + EPI_WARPS);
+    const int r8 = lane >> 2, cg = lane & 3;   // a row's four lanes side by side: a quarter warp's 16-byte loads touch two lines, not eight
+    const uint32_t gfull_remote = PAIR ? mapa_shared(smem_u32(&gfull[0]), 0) : 0u;
+    uint32_t s = 0, ph = 0;
+    for (int j = 0; j < n_units; ++j) {
+      int phase, grp, pass, ti;
+      seq.get(j, phase, grp, pass, ti);
+      const LinArgs& a = g.p[phase];
+      const int kchunks = lin_chunks(a);
+      if (a.g_x == nullptr) {
+        // Nothing to gather in this unit, but the ring is still followed stage by stage: a parity wait only tells two consecutive
+        // phases apart, so a warp that skipped a use of stage s could be a whole ring turn ahead of the MMA warp at its next wait on
+        // empty[s] and take the stale phase for the one it needs (seen as wrong tokens at 512 meshes per launch).
+        for (int kc = 0; kc < kchunks; ++kc) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+        }
+        continue;
+      }
+      const int kch1 = a.K1 / KC;
+      const int m_tile = PAIR ? 2 * grp + (int)rank : grp;
+      const long long row0 = (long long)m_tile * M_TILE;
+      int id[STEPS][4], cnt[STEPS], beg[STEPS];
+      float rcp[STEPS];
+#pragma unroll
+      for (int t = 0; t < STEPS; ++t) {
+        const long long row = row0 + (t * GW + gw) * 8 + r8;
+        cnt[t] = -1;   // row beyond M: nothing to read, nothing to write
+        beg[t] = 0; rcp[t] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) id[t][k] = -1;
+        if (row < M) {
+          const int b0 = __ldg(a.g_indptr + row), e_true = __ldg(a.g_indptr + row + 1);
+          const int e = (int)min((long long)e_true, a.g_cap);
+          beg[t] = b0;
+          cnt[t] = max(e - b0, 0);
+          rcp[t] = __frcp_rn(fmaxf((float)(e_true - b0), 1.f));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (k < cnt[t]) {
+              const int v = __ldg(a.g_src + b0 + k);
+              id[t][k] = (unsigned)v < (unsigned)M ? v : -1;   // (a corrupt list contributes nothing)
+            }
+        }
+      }
+      for (int kc = 0; kc < kchunks; ++kc) {
+        mbar_wait(&empty[s], ph ^ 1);   // every stage, also the bulk-copied ones (see above)
+        if (kc < kch1) {
+          uint8_t* stage = ring + s * stage_bytes;
+          const float* xcol = a.g_x + kc * KC + cg * 8;
+#pragma unroll
+          for (int t0 = 0; t0 < STEPS; t0 += 2) {
+            float4 v[2][4][2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[u][k][0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                v[u][k][1] = v[u][k][0];
+                if (id[t0 + u][k] >= 0) {
+                  const float4* p = reinterpret_cast<const float4*>(xcol + (size_t)id[t0 + u][k] * a.K1);
+                  v[u][k][0] = __ldg(p);
+                  v[u][k][1] = __ldg(p + 1);
+                }
+              }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int t = t0 + u;
+              if (cnt[t] < 0) continue;
+              float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (k < cnt[t]) {   // (an invalid source adds the zeros loaded above: x + 0 = x)
+                  a0.x += v[u][k][0].x; a0.y += v[u][k][0].y; a0.z += v[u][k][0].z; a0.w += v[u][k][0].w;
+                  a1.x += v[u][k][1].x; a1.y += v[u][k][1].y; a1.z += v[u][k][1].z; a1.w += v[u][k][1].w;
+                }
+              for (int k = 4; k < cnt[t]; ++k) {   // faces with more than four in-neighbours
+                const int sv = __ldg(a.g_src + beg[t] + k);
+                if ((unsigned)sv < (unsigned)M) {
+                  const float4* p = reinterpret_cast<const float4*>(xcol + (size_t)sv * a.K1);
+                  const float4 w0 = __ldg(p), w1 = __ldg(p + 1);
+                  a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
+                  a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+                }
+              }
+              const float rc = rcp[t];
+              uint4 hi, lo;
+              split2(a0.x * rc, a0.y * rc, hi.x, lo.x);
+              split2(a0.z * rc, a0.w * rc, hi.y, lo.y);
+              split2(a1.x * rc, a1.y * rc, hi.z, lo.z);
+              split2(a1.z * rc, a1.w * rc, hi.w, lo.w);
+              uint8_t* dst = stage + (uint32_t)(t * GW + gw) * 512u + (uint32_t)cg * 128u + (uint32_t)r8 * 16u;
+              *reinterpret_cast<uint4*>(dst) = hi;
+              *reinterpret_cast<uint4*>(dst + A_PART) = lo;
+            }
+          }
+          fence_proxy_async_smem();               // the tile is read by the tensor core (async proxy)
+          named_bar_sync(5, GW * 32);
+          if (gw == 0 && lane == 0) {
+            if (leader) mbar_arrive(&gfull[s]);
+            // relaxed, like the completion forwarder's arrival: the tile is in THIS CTA's shared memory (every writer fenced it for the
+            // async proxy before the barrier above) and only this SM's tensor core reads it; a release.cluster arrival is a full
+            // memory barrier per stage
+            else mbar_arrive_cluster_relaxed(gfull_remote + s * 8u);
+          }
+        }
+        if (++s == (uint32_t)STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  }
+
   pdl_launch_dependents();   // this CTA's work is done: let the next kernel's CTAs start their prologue
   tcgen05_fence_before();
   __syncthreads();
@@ -700,6 +839,8 @@ __global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_kerne
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2>(a); }
 __global__ void __launch_bounds__(Cfg<false, 2>::NUM_THREADS, 1) linear_tc_tail_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<false, 2, true>(a); }
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2>::NUM_THREADS, 1) linear_tc_pair_tail_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2, true>(a); }
+// the SAGE output linears with the neighbour aggregation fused in: four gather warps behind the epilogue warps (512 threads, 128 registers)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Cfg<true, 2, 4>::NUM_THREADS, 1) linear_tc_pair_gather_kernel(const __grid_constant__ LinArgs2 a) { linear_tc_body<true, 2, false, 4>(a); }
 
 // W (N, K) fp32 -> image [pass][kchunk]{hi (NT x 32), lo (NT x 32)} canonical K-major, SBO 512.
 __global__ void __launch_bounds__(256) build_w_image_kernel(const float* __restrict__ W, int N, int K, int NT, uint8_t* __restrict__ image) {
@@ -816,6 +957,7 @@ static int fill_lin_args(LinArgs& a, const void* a1_image, int K1, const void* a
   a.row_valid = nullptr; a.out_halo = 0; a.norm_eps = 0.f;
   a.am_coords = nullptr; a.am_bins = nullptr; a.am_B = a.am_P = a.am_lead = a.am_ncoord = 0; a.am_lo = a.am_hi = 0.f;
   a.ssq_out = nullptr; a.row_ssq = nullptr; a.row_ssq_parts = 0;
+  a.g_x = nullptr; a.g_indptr = nullptr; a.g_src = nullptr; a.g_cap = 0;
   if (epi != nullptr && epi->norm_mode == 0) {
     // plain epilogue with the deferred-normalisation extras
     MT_CHECK_ARG(epi->out_image == nullptr || N % KC == 0, "tcgen05 linear: an output image needs N %% %d == 0 (got %d)", KC, N);
@@ -858,7 +1000,14 @@ static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
   MT_ENSURE_SMEM(linear_tc_pair_tail_kernel, (Cfg<true, 2>::SMEM_TOTAL));
   const int passes = g.nphase == 2 ? 1 : g.p[0].passes;
   const bool tail = g.p[0].norm_mode == 3 || g.p[0].norm_mode == 4;   // decode path: Block tail / arg-max in the epilogue
-  if (linear_tc_pair()) {
+  if (g.p[0].g_x != nullptr) {
+    using PG = Cfg<true, 2, 4>;
+    MT_CHECK_ARG(linear_tc_pair() && !tail, "tcgen05 linear: the fused aggregation exists for the CTA-pair kernel only");
+    MT_ENSURE_SMEM(linear_tc_pair_gather_kernel, (PG::SMEM_TOTAL));
+    const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * passes;
+    const int grid = 2 * min(units, 148 / 2);
+    MT_LAUNCH_PDL(linear_tc_pair_gather_kernel, grid, PG::NUM_THREADS, PG::SMEM_TOTAL, stream, g);
+  } else if (linear_tc_pair()) {
     using P2 = Cfg<true, 2>;
     const int units = ceil_div(ceil_div(m_max, M_TILE), 2) * passes;
     const int grid = 2 * min(units, 148 / 2);
@@ -959,12 +1108,29 @@ bool linear_tc_b2b_ok(int N, int norm_mode) {
   return on == 1 && norm_mode != 0 && N <= NT_MAX && N % KC == 0 && (norm_mode != 2 || N <= 64);
 }
 
+// MESHTOK_GATHER_FUSED=1 turns the fused aggregation on (needs the CTA-pair kernel and K1 a multiple of 32).  It is OFF by default:
+// bit-identical to the separate launches (scripts/gpu_gather_fused_check.py) but measured SLOWER at the bench workload - 4 aggregation
+// launches (95 us) disappear and the four output linears grow from 160 to 350 us, because four gather warps at 128 registers keep only
+// 32 KB of neighbour rows in flight per SM and every 32-column chunk then costs four exposed load round trips (ncu: 54 % of the gather
+// warps' samples in long-scoreboard stalls, tensor pipe active 24 %).
+bool linear_tc_gather_ok(int K1, int N, int norm_mode) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MESHTOK_GATHER_FUSED"); on = (e && atoi(e) == 1) ? 1 : 0; }
+  return on == 1 && linear_tc_pair() && K1 % KC == 0 && linear_tc_b2b_ok(N, norm_mode);
+}
+
 // phase 0: C/out_image = norm([A1 | A2] W^T + bias) (epi: fused row epilogue, out_image required);  phase 1: C2 = relu(out W2^T + bias2)
 int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int K2, const void* w_image, const float* bias, float* C,
                          int N, const int* m_dev, int m_max, const LinearRowEpilogue* epi, const void* w2_image, const float* bias2,
-                         float* C2, cudaStream_t stream) {
+                         float* C2, cudaStream_t stream, const LinearGather* gather) {
   if (m_max == 0) return MESHTOK_OK;
   MT_CHECK_ARG(epi != nullptr && epi->norm_mode != 0 && epi->out_image != nullptr, "tcgen05 linear pair of phases: phase 0 needs the fused row epilogue and an output image");
+  if (gather != nullptr) {
+    MT_CHECK_ARG(linear_tc_gather_ok(K1, N, epi->norm_mode), "tcgen05 linear: fused aggregation not available for K1 %d, N %d", K1, N);
+    MT_CHECK_ARG(gather->x && gather->indptr && gather->src && gather->cap > 0 && gather->x != C2,
+                 "tcgen05 linear: fused aggregation needs x / indptr / src, and x must not be the buffer phase 1 writes");
+    if (a1_image == nullptr) a1_image = a2_image;   // (never read; fill_lin_args wants a pointer)
+  }
   MT_CHECK_ARG(linear_tc_b2b_ok(N, epi->norm_mode), "tcgen05 linear pair of phases: width %d not supported", N);
   LinArgs2 g;
   memset(&g, 0, sizeof(g));
@@ -974,6 +1140,7 @@ int launch_linear_tc_b2b(const void* a1_image, int K1, const void* a2_image, int
   rc = fill_lin_args(g.p[1], epi->out_image, N, nullptr, 0, w2_image, bias2, C2, N, m_dev, m_max, true, nullptr);
   if (rc != MESHTOK_OK) return rc;
   MT_CHECK_ARG(g.p[0].passes == 1 && g.p[1].passes == 1, "tcgen05 linear pair of phases: both must be single pass");
+  if (gather != nullptr) { g.p[0].g_x = gather->x; g.p[0].g_indptr = gather->indptr; g.p[0].g_src = gather->src; g.p[0].g_cap = gather->cap; }
   return launch_lin2(g, m_max, stream);
 }
 
