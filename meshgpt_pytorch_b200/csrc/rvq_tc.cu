@@ -341,12 +341,26 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
       for (int i = 0; i < PER2; ++i) {
         const int c = lane + 32 * i;
         x[i] = c < d2 ? xr[c] : make_float2(0.f, 0.f);
+      }
+      // this row's candidate entries (see RvqPartialLayout): the slots of the clusters whose step range meets the row tile's.  Lane s
+      // holds entry s (n_splits <= 32 is checked by the launcher).  Issued together with the row and its scale, BEFORE the first
+      // reduction: the kernel is bound by the dependent round trips of a row, and these three do not depend on each other.
+      int n_splits = lay.stride;
+      if (lay.mode == 2) {
+        const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;      // first step of the 256-row tile (the launcher checks the range)
+        n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
+      }
+      const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
+      float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
+      if (lane < n_splits) { p0 = prow[lane * RVQ_SLOT_F4]; p1 = prow[lane * RVQ_SLOT_F4 + 1]; }
+      const float rs = rscale[row];
+#pragma unroll
+      for (int i = 0; i < PER2; ++i) {
         x2 = fmaf(x[i].x, x[i].x, x2);
         x2 = fmaf(x[i].y, x[i].y, x2);
       }
       x2 = warp_sum(x2);
       const float xn = sqrtf(x2);
-      const float rs = rscale[row];
       float delta = 0.001953125f * 1.01f * xn * max_norm +
                     5.96e-8f * sqrt_d * (max_norm * __frcp_rn(rs) + xn * inv_escale) + 1e-7f * (x2 + mn2);
       if (c_scale > 0.f) {
@@ -355,16 +369,6 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
         delta += 1e-6f * mn2;
         if (rs * c_scale < 5.9604645e-8f) delta += mn2;
       }
-      // this row's candidate entries (see RvqPartialLayout): the slots of the clusters whose step range meets the row tile's
-      int n_splits = lay.stride;
-      if (lay.mode == 2) {
-        const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;      // first step of the 256-row tile (the launcher checks the range)
-        n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
-      }
-      // lane s holds entry s (n_splits <= 32 is checked by the launcher): one parallel load instead of a serial walk
-      const float4* prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
-      float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
-      if (lane < n_splits) { p0 = prow[lane * RVQ_SLOT_F4]; p1 = prow[lane * RVQ_SLOT_F4 + 1]; }
       float smin = p0.x;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
@@ -386,9 +390,9 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
         for (int which = 0; which < cnt; ++which) {
           const int code0 = __float_as_int(which == 0 ? y0 : which == 1 ? y1 : which == 2 ? y2 : y3) * CHUNK;
           // exact fp32 distance of all CHUNK codes at once (coalesced codebook rows, CHUNK independent dot products)
-          float d[CHUNK];
+          float d[CHUNK], en[CHUNK];
 #pragma unroll
-          for (int j = 0; j < CHUNK; ++j) d[j] = 0.f;
+          for (int j = 0; j < CHUNK; ++j) { d[j] = 0.f; en[j] = __ldg(e2 + code0 + j); }   // |e|^2 travels with the codebook rows
 #pragma unroll
           for (int i = 0; i < PER2; ++i) {
             const int c = lane + 32 * i;
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
             for (int j = 0; j < CHUNK; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
 #pragma unroll
           for (int j = 0; j < CHUNK; ++j) {
-            const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, __ldg(e2 + code0 + j)), __fmul_rn(d[j], -2.f)), 0.f));
+            const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, en[j]), __fmul_rn(d[j], -2.f)), 0.f));
             if (q < bd || (q == bd && code0 + j < bi)) { bd = q; bi = code0 + j; }
           }
         }
