@@ -56,14 +56,17 @@ struct ProfScope {
   ~ProfScope() { prof_end(sec, s); }
 };
 
-// ---- programmatic dependent launch (opt-in experiment) ---------------------------------------------------------------
-// The pipeline is ~34 short kernels in one stream / graph.  Launched with programmatic stream serialization, kernel n+1
+// ---- programmatic dependent launch -------------------------------------------------------------------------------------
+// The pipeline is ~22 short kernels in one stream / graph.  Launched with programmatic stream serialization, kernel n+1
 // may start its CTAs (launch latency, barrier init, TMEM allocation) once kernel n's CTAs have signalled
 // pdl_launch_dependents(), and blocks in pdl_wait() until kernel n has completed and its writes are visible; every kernel
 // launched through launch_pdl() calls pdl_wait() before it touches anything an earlier kernel wrote (device-side counters
-// included).  MEASURED (B200, graph replay of the C2 step): 1.113 ms with the attribute against 1.062 ms without, with the
-// trigger at the start of the kernels as well as at their end - the dependents' parked CTAs cost more than the hidden
-// prologues save.  So the attribute is only set when MESHTOK_PDL=1; without it pdl_wait / pdl_launch_dependents are no-ops.
+// included).  Round 1 measured this SLOWER (1.113 against 1.062 ms per C2 step: ~34 launches then, every wait at the top of
+// its kernel, so only the launch latency could overlap).  Round 2, with 22 launches and the two tcgen05 kernels setting up
+// their barriers / TMEM before the wait (linear_tc.cu, rvq_tc2.cu): 0.829 against 0.837 ms at C2 (e2e 66.8 against 65.5 M
+// faces/s), +1.4 % at C3, +0.7 % at C4, device time unchanged and e2e +2-3 % at 1 024 meshes per launch (A/B on one box each,
+// scripts/gpu_ab.sh "MESHTOK_PDL=0" "MESHTOK_PDL=1"); all GPU tests green with it.  On by default; MESHTOK_PDL=0 turns the
+// attribute off (pdl_wait / pdl_launch_dependents are then no-ops).
 bool pdl_enabled();
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {

@@ -140,6 +140,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 struct LinArgs2 {
   LinArgs p[2];
   int nphase;
+  int pdl;            // launched with programmatic stream serialization: set up barriers / TMEM BEFORE waiting for the previous kernel
   long long* trace;   // timing experiments (MESHTOK_LINEAR_TRACE): clock64 stamps of cluster 0, [2 ranks][8 events][16 units]; else null
 };
 
@@ -200,8 +201,10 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
 
   // Earlier kernels' results are read from here on (the row count first: its load travels while the barriers and TMEM are
   // set up).  With PDL enabled this gives up the overlap of the prologue; PDL is opt-in and measured slower anyway.
-  pdl_wait();
-  const int M = g.p[0].m_dev ? min(__ldg(g.p[0].m_dev), g.p[0].m_max) : g.p[0].m_max;
+  // Without PDL the row count's load travels while the barriers and TMEM are set up (~2.5 us per launch); with it the set-up itself
+  // overlaps the previous kernel's tail and the count is read after the wait.
+  int M = g.p[0].m_max;
+  if (!g.pdl && g.p[0].m_dev) M = min(__ldg(g.p[0].m_dev), g.p[0].m_max);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], PAIR && leader ? 2 : 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -224,6 +227,10 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
   __syncthreads();
   if (PAIR) cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
+  if (g.pdl) {
+    pdl_wait();
+    if (g.p[0].m_dev) M = min(*reinterpret_cast<const volatile int*>(g.p[0].m_dev), g.p[0].m_max);
+  }
   const uint32_t tmem_base = *tmem_slot;
   const int m_tiles = (M + M_TILE - 1) / M_TILE;
   const int m_groups = PAIR ? (m_tiles + 1) / 2 : m_tiles;   // a group = the row tile(s) one MMA covers
@@ -994,6 +1001,7 @@ static int launch_lin2(const LinArgs2& g_in, int m_max, cudaStream_t stream) {
     if (g_lin_trace_k >= 0) { MT_CHECK_CUDA(cudaMalloc(&g_lin_trace, 2 * 8 * 16 * sizeof(long long))); MT_CHECK_CUDA(cudaMemset(g_lin_trace, 0, 2 * 8 * 16 * sizeof(long long))); }
   }
   g.trace = (g_lin_trace_k >= 0 && (g_lin_launches++ % 7) == g_lin_trace_k) ? g_lin_trace : nullptr;
+  g.pdl = pdl_enabled() ? 1 : 0;
   MT_ENSURE_SMEM(linear_tc_kernel, (Cfg<false, 2>::SMEM_TOTAL));
   MT_ENSURE_SMEM(linear_tc_pair_kernel, (Cfg<true, 2>::SMEM_TOTAL));
   MT_ENSURE_SMEM(linear_tc_tail_kernel, (Cfg<false, 2>::SMEM_TOTAL));

@@ -12,7 +12,7 @@ long long g_launch_count = 0;
 
 bool pdl_enabled() {
   static int on = -1;
-  if (on < 0) { const char* e = getenv("MESHTOK_PDL"); on = (e && e[0] == '1') ? 1 : 0; }
+  if (on < 0) { const char* e = getenv("MESHTOK_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
   return on == 1;
 }
 

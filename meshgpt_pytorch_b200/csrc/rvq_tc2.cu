@@ -75,6 +75,7 @@ struct Search2Args {
   const int* n_rows_dev;
   int max_rows, T, max_slots, w_min;   // T = K / 256 code-pair-tiles
   float4* partial;         // (R, CSPLIT * max_slots) entries of RVQ_SLOT_F4 float4 (rvq_screen.cuh)
+  int pdl;                 // launched with programmatic stream serialization: barriers / TMEM are set up before the wait
 };
 
 __host__ __device__ __forceinline__ int w_min_of(int T) { return T / 4 > W_MIN ? T / 4 : W_MIN; }
@@ -103,9 +104,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   const int warp = warp_id(), lane = lane_id();
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  // earlier kernels' results are read from here on; the row count first, so that its load travels during the set-up
-  pdl_wait();
-  const int n_rows = min(__ldg(a.n_rows_dev), a.max_rows);
+  // earlier kernels' results: without PDL the row count is read first, so that its load travels during the set-up; with PDL the
+  // set-up overlaps the previous kernel's tail and everything an earlier kernel wrote is read after the wait below
+  int n_rows = a.max_rows;
+  if (!a.pdl) n_rows = min(__ldg(a.n_rows_dev), a.max_rows);
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; ++i) { mbar_init(&b_full[i], leader ? 2 : 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 2 * EPI_WARPS); }
@@ -118,6 +120,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1) rvq_
   __syncthreads();
   cluster_sync_all();   // both CTAs' barriers and TMEM exist before anything crosses the pair
   tcgen05_fence_after();
+  if (a.pdl) {
+    pdl_wait();
+    n_rows = min(*reinterpret_cast<const volatile int*>(a.n_rows_dev), a.max_rows);
+  }
   const uint32_t tmem_base = *tmem_slot;
   const int G = (n_rows + M_PAIR - 1) / M_PAIR;
   const int T = a.T;
@@ -351,6 +357,7 @@ int launch_rvq_tc2_search(const void* row_image, const float* rscale, int D, con
   Search2Args a;
   a.rimg = static_cast<const uint8_t*>(row_image); a.image = static_cast<const uint8_t*>(codebook_tiles); a.rscale = rscale;
   a.escale = escale; a.n_rows_dev = n_rows_dev; a.max_rows = max_rows; a.T = plan.T; a.max_slots = plan.max_slots; a.w_min = w_min_of(plan.T); a.partial = partial;
+  a.pdl = pdl_enabled() ? 1 : 0;
   // enough clusters for the worst case, never more than the machine has SM pairs
   const long long steps = (long long)ceil_div(max_rows, M_PAIR) * plan.T;
   const int wm = w_min_of(plan.T);
