@@ -483,6 +483,251 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
   pdl_launch_dependents();
 }
 
+// Round 2: the same re-score with FOUR rows per warp (eight lanes per row).  The kernel above executes ~730 warp instructions per row,
+// each once, and most of them are scalar per-row work (error window, step ranges of the partial layout, comparisons, addresses) that
+// all 32 lanes repeat; at 1 024 meshes per launch it is issue bound (0.6 instructions per cycle and scheduler).  Here a lane group of 8
+// owns a row: lane `sub` holds the float4 columns sub, sub + 8, ... (128-byte row pieces per step, coalesced), reductions take three
+// shuffle steps instead of five, and the scalar work of four rows shares one instruction stream.  Same arithmetic per code
+// (fp32 dot product, sqrt(max(|x|^2 + |e|^2 - 2 <x, e>, 0)), lowest index on ties); only the summation order inside a dot product
+// differs (eight partial sums instead of 32), which the parity tests cover like any other fp32 evaluation order.
+template <int NI>   // float4 per lane: D <= 32 * NI
+__global__ void __launch_bounds__(256, 2) rvq_rescore4_kernel(float* __restrict__ rows, int D, const float* __restrict__ cb,
+                                                              const float* __restrict__ e2, int K, float max_norm, float escale, float c_scale,
+                                                              float* __restrict__ rscale, const float4* __restrict__ partial, RvqPartialLayout lay,
+                                                              const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ codes, int Q,
+                                                              int level, int update, uint8_t* __restrict__ row_image, int* __restrict__ stats) {
+  __shared__ float s_x[32 * 4 * NI];
+  __shared__ float s_x2;
+  __shared__ int s_row[32];
+  __shared__ unsigned long long s_best[32];
+  pdl_wait();
+  const int lane = lane_id(), warp = warp_id();
+  const int sub = lane & 7, grp = lane >> 3;
+  const unsigned gmask = 0xffu << (grp * 8);
+  const int rpb = (blockDim.x >> 5) * 4;   // rows per CTA and iteration: 32
+  const int n = min(*n_dev, max_rows);
+  const int d4 = D >> 2;
+  unsigned W = 1u;
+  if (lay.mode == 2) {
+    const long long S = (long long)((n + 255) >> 8) * lay.T;
+    long long w = (S + lay.n_clusters - 1) / lay.n_clusters;
+    if (w < lay.w_min) w = lay.w_min;
+    W = (unsigned)w;
+  }
+  const float sqrt_d = sqrtf((float)D);
+  const float mn2 = max_norm * max_norm;
+  const float inv_escale = 1.f / escale;
+  const int stride = gridDim.x * rpb;
+  const int iters = (n + stride - 1) / stride;   // the same trip count for every warp of the grid: the loop holds CTA barriers
+  for (int it = 0; it < iters; ++it) {
+    const int slot = warp * 4 + grp;             // this row's slot in the CTA's lists
+    const int row = it * stride + blockIdx.x * rpb + slot;
+    const bool active = row < n;
+    float4 x[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) x[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float x2 = 0.f;
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    bool ambiguous = false;
+    int n_splits = 0;
+    const float4* prow = partial;
+    float4 p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f), p1 = p0;
+    float window = -INFINITY;
+    if (active) {
+      const float4* xr = reinterpret_cast<const float4*>(rows + (size_t)row * D);
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int c = sub + 8 * i;
+        x[i] = c < d4 ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      n_splits = lay.stride;
+      if (lay.mode == 2) {
+        const unsigned a = (unsigned)(row >> 8) * (unsigned)lay.T;
+        n_splits = lay.parts * (int)((a + (unsigned)lay.T - 1u) / W - a / W + 1u);
+      }
+      prow = partial + (size_t)row * lay.stride * RVQ_SLOT_F4;
+      if (sub < n_splits) { p0 = prow[sub * RVQ_SLOT_F4]; p1 = prow[sub * RVQ_SLOT_F4 + 1]; }   // entries sub, (sub + 8, ... below)
+    }
+    const float rs = active ? rscale[row] : 1.f;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      x2 = fmaf(x[i].x, x[i].x, x2); x2 = fmaf(x[i].y, x[i].y, x2);
+      x2 = fmaf(x[i].z, x[i].z, x2); x2 = fmaf(x[i].w, x[i].w, x2);
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) x2 += __shfl_xor_sync(0xffffffffu, x2, o);
+    // entries 8 .. 31 of a row with more than eight (wide partial layouts only): their best scores join the minimum
+    float smin = p0.x;
+    for (int e = sub + 8; e < n_splits; e += 8) smin = fminf(smin, prow[e * RVQ_SLOT_F4].x);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, o));
+    if (active) {
+      const float xn = sqrtf(x2);
+      float delta = 0.001953125f * 1.01f * xn * max_norm +
+                    5.96e-8f * sqrt_d * (max_norm * __frcp_rn(rs) + xn * inv_escale) + 1e-7f * (x2 + mn2);
+      if (c_scale > 0.f) {
+        delta += 1e-6f * mn2;
+        if (rs * c_scale < 5.9604645e-8f) delta += mn2;
+      }
+      window = smin + 2.f * delta;
+    }
+    // passes over the row's entries, eight per pass (lane sub holds entry pass * 8 + sub); one pass unless the layout is wide
+    const int n_pass = __reduce_max_sync(0xffffffffu, (n_splits + 7) >> 3);
+    for (int pass = 0; pass < n_pass; ++pass) {
+      if (pass > 0) {
+        p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f); p1 = p0;
+        const int e = pass * 8 + sub;
+        if (e < n_splits) { p0 = prow[e * RVQ_SLOT_F4]; p1 = prow[e * RVQ_SLOT_F4 + 1]; }
+      }
+      // chunks of this lane's entry inside the window (ascending list -> a prefix); a list whose LAST kept chunk is inside may be incomplete
+      const int mine = (p0.x <= window) + (p0.z <= window) + (p1.x <= window) + (p1.z <= window);
+      ambiguous = ambiguous || ((__ballot_sync(0xffffffffu, p1.z <= window) & gmask) != 0u);
+    }
+    // (an ambiguous row is decided by the full scan alone; a NaN row has no chunk inside the window and falls through to code 0)
+    for (int pass = 0; pass < n_pass; ++pass) {
+      if (n_pass > 1) {
+        p0 = make_float4(INFINITY, 0.f, INFINITY, 0.f); p1 = p0;
+        const int e = pass * 8 + sub;
+        if (e < n_splits) { p0 = prow[e * RVQ_SLOT_F4]; p1 = prow[e * RVQ_SLOT_F4 + 1]; }
+      }
+      const int mine = ambiguous ? 0 : (p0.x <= window) + (p0.z <= window) + (p1.x <= window) + (p1.z <= window);
+      unsigned live = (__ballot_sync(0xffffffffu, mine > 0) & gmask) >> (grp * 8);   // this row's entries with candidates
+      int which = 0;   // next chunk of the current owner entry
+      while (__any_sync(0xffffffffu, live != 0u)) {
+        const bool busy = live != 0u;
+        const int owner = grp * 8 + (busy ? __ffs(live) - 1 : 0);
+        const int cnt = __shfl_sync(0xffffffffu, mine, owner);
+        const float y0 = __shfl_sync(0xffffffffu, p0.y, owner), y1 = __shfl_sync(0xffffffffu, p0.w, owner);
+        const float y2 = __shfl_sync(0xffffffffu, p1.y, owner), y3 = __shfl_sync(0xffffffffu, p1.w, owner);
+        const int code0 = __float_as_int(which == 0 ? y0 : which == 1 ? y1 : which == 2 ? y2 : y3) * CHUNK;
+        float d[CHUNK], en[CHUNK];
+#pragma unroll
+        for (int j = 0; j < CHUNK; ++j) { d[j] = 0.f; en[j] = 0.f; }
+        if (busy) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) en[j] = __ldg(e2 + code0 + j);
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const int c = sub + 8 * i;
+            if (c < d4) {
+              float4 e[CHUNK];
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) e[j] = __ldg(reinterpret_cast<const float4*>(cb + (size_t)(code0 + j) * D) + c);
+#pragma unroll
+              for (int j = 0; j < CHUNK; ++j) {
+                d[j] = fmaf(x[i].x, e[j].x, d[j]); d[j] = fmaf(x[i].y, e[j].y, d[j]);
+                d[j] = fmaf(x[i].z, e[j].z, d[j]); d[j] = fmaf(x[i].w, e[j].w, d[j]);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
+        if (busy) {
+#pragma unroll
+          for (int j = 0; j < CHUNK; ++j) {
+            const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(x2, en[j]), __fmul_rn(d[j], -2.f)), 0.f));
+            if (q < bd || (q == bd && code0 + j < bi)) { bd = q; bi = code0 + j; }
+          }
+          if (++which >= cnt) { which = 0; live &= live - 1; }
+        }
+      }
+    }
+    // ---- ambiguous rows of this CTA: exact fp32 scan of the whole codebook by all warps (rare; the barrier is the common-case cost) ----
+    if (__syncthreads_or(ambiguous ? 1 : 0)) {
+      if (sub == 0) { s_row[slot] = ambiguous ? row : -1; s_best[slot] = ~0ull; }
+      __syncthreads();
+      for (int w = 0; w < rpb; ++w) {
+        const int r = s_row[w];
+        if (r < 0) continue;   // (uniform: shared memory)
+        for (int k = threadIdx.x; k < D; k += blockDim.x) s_x[k] = rows[(size_t)r * D + k];
+        if (slot == w && sub == 0) s_x2 = x2;   // the row's owner has |x|^2 (the same value for every code, whatever its rounding)
+        __syncthreads();
+        const float xx = s_x2;
+        float sd = INFINITY;
+        int si = 0x7fffffff;
+        for (int code = threadIdx.x; code < K; code += blockDim.x) {   // ascending per thread: strict < keeps the lowest index
+          const float4* er = reinterpret_cast<const float4*>(cb + (size_t)code * D);
+          float acc = 0.f;
+          for (int k4 = 0; k4 < d4; ++k4) {
+            const float4 e = __ldg(er + k4);
+            const float4 xv = *reinterpret_cast<const float4*>(s_x + 4 * k4);
+            acc = fmaf(xv.x, e.x, acc); acc = fmaf(xv.y, e.y, acc); acc = fmaf(xv.z, e.z, acc); acc = fmaf(xv.w, e.w, acc);
+          }
+          const float q = sqrtf(fmaxf(__fadd_rn(__fadd_rn(xx, __ldg(e2 + code)), __fmul_rn(acc, -2.f)), 0.f));
+          if (q < sd) { sd = q; si = code; }
+        }
+        unsigned long long key = si == 0x7fffffff ? ~0ull : (((unsigned long long)__float_as_uint(sd) << 32) | (unsigned int)si);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+          key = other < key ? other : key;
+        }
+        if (lane == 0) atomicMin(&s_best[w], key);
+        __syncthreads();   // s_best[w] complete; s_x free for the next row
+      }
+      if (ambiguous) {
+        const unsigned long long key = s_best[slot];
+        bd = __uint_as_float((unsigned int)(key >> 32));
+        bi = key == ~0ull ? 0x7fffffff : (int)(unsigned int)(key & 0xffffffffull);
+        if (sub == 0) atomicAdd(stats + 1, 1);
+      }
+    }
+    // ---- decided: code id, residual update, the next level's row scale and image (groups without a row take part in the shuffles) ----
+    if (bi == 0x7fffffff) bi = 0;   // NaN row: no comparison succeeded (torch.argmax of an all-NaN row is 0 as well)
+    if (active && sub == 0) codes[(size_t)row * Q + level] = bi;
+    if (update) {
+      float vmax = 0.f;
+      if (active) {
+        const float4* er = reinterpret_cast<const float4*>(cb + (size_t)bi * D);
+        float4* dst = reinterpret_cast<float4*>(rows + (size_t)row * D);
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int c = sub + 8 * i;
+          if (c < d4) {
+            const float4 e = __ldg(er + c);
+            x[i].x = __fsub_rn(x[i].x, e.x); x[i].y = __fsub_rn(x[i].y, e.y);
+            x[i].z = __fsub_rn(x[i].z, e.z); x[i].w = __fsub_rn(x[i].w, e.w);
+            dst[c] = x[i];
+            vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(x[i].x), fabsf(x[i].y)), fmaxf(fabsf(x[i].z), fabsf(x[i].w))));
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+      if (active) {
+        float sc = rvq_pow2_scale(vmax);
+        if (row_image) sc = fminf(sc, 32768.f / c_scale);   // (see rvq_emit_row_scale_and_image)
+        if (sub == 0 && rscale) rscale[row] = sc;
+        if (row_image) {
+          uint8_t* tile = row_image + (size_t)(row >> 7) * rvq_image_tile_bytes(D);
+          const int r = row & 127;
+#pragma unroll
+          for (int i = 0; i < NI; ++i) {
+            const int c = sub + 8 * i;
+            if (c < d4) {
+              const int k = 4 * c;
+              const __half2 h0 = __floats2half2_rn(x[i].x * sc, x[i].y * sc), h1 = __floats2half2_rn(x[i].z * sc, x[i].w * sc);
+              const uint32_t off = (uint32_t)(k >> 6) * (128u * 128u) + (uint32_t)r * 128u + ((uint32_t)(((k >> 3) ^ r) & 7) << 4) + (uint32_t)(k & 7) * 2u;
+              *reinterpret_cast<uint2*>(tile + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            }
+          }
+          if (sub < 2) {
+            const __half ch = __float2half_rn(sc * c_scale);
+            const __half2 cc = __halves2half2(ch, ch);
+            uint8_t* ex = tile + (size_t)128 * D * 2 + (size_t)(r >> 3) * RVQ_EXTRA_SBO + (size_t)(r & 7) * 16 + (size_t)sub * 128;
+            *reinterpret_cast<uint4*>(ex) = sub == 0 ? make_uint4(*reinterpret_cast<const uint32_t*>(&cc), 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+      }
+    }
+  }
+  pdl_launch_dependents();
+}
+
 // fp32 codebook * escale -> fp16 image in stage order: [128-code tile][64-dim chunk][128 rows x 128 B, SWIZZLE_128B].
 __global__ void __launch_bounds__(256) build_image_kernel(const float* __restrict__ cb, const float* __restrict__ e2, int K, int D, float escale,
                                                           float kappa, uint8_t* __restrict__ image) {
@@ -595,6 +840,15 @@ int launch_rvq_rescore(float* rows, float* rscale, int D, const float* codebook,
                "rvq re-score: %d rows x %d code tiles exceed the 32-bit step range", max_rows, layout.T);
   MT_CHECK_ARG(D % 4 == 0 && D <= 192, "rvq re-score: dim %d must be a multiple of 4 and <= 192", D);
   MT_CHECK_ARG(row_image == nullptr || (D % 64 == 0 && c_scale > 0.f), "rvq: a row image needs dim %% 64 == 0 and c_scale > 0");
+  // four rows per warp (rvq_rescore4_kernel) unless MESHTOK_RESCORE4=0 asks for the one-row-per-warp kernel (A/B runs)
+  static int four = -1;
+  if (four < 0) { const char* e = getenv("MESHTOK_RESCORE4"); four = (e && atoi(e) == 0) ? 0 : 1; }
+  if (four == 1 && D % 4 == 0) {
+    const int blocks = max(1, min(ceil_div(max_rows, 32), 148 * 8));
+    MT_LAUNCH_PDL(rvq_rescore4_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
+                  n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
+    return MESHTOK_OK;
+  }
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
   MT_LAUNCH_PDL(rvq_rescore_kernel<3>, blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
                 n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
