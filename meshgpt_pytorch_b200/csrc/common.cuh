@@ -98,6 +98,16 @@ constexpr int kWarp = 32;
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ int warp_id() { return threadIdx.x >> 5; }
 
+// Packed fp32 add (sm_100: SASS FADD2): acc.{x,y} += v.{x,y} and acc.{z,w} += v.{z,w}, each element rounded like a scalar add.rn -
+// half the issue slots of four FADDs.  The summing kernels (folded embedding tables, neighbour aggregation) are bound by instruction
+// issue and by dependent add chains, not by the fp32 pipe.
+__device__ __forceinline__ void add4(float4& acc, const float4& v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(&acc);
+  const unsigned long long* b = reinterpret_cast<const unsigned long long*>(&v);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a[0]) : "l"(b[0]));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a[1]) : "l"(b[1]));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

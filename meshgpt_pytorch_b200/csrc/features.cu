@@ -126,9 +126,18 @@ __global__ void __launch_bounds__(128) face_bins_kernel(FeatParams p) {
       bins[NVF * 4 + 1 + c] = (unsigned short)discretize_rn(__fdiv_rn(cr[c], cd), p.coor_lo, p.coor_den, (float)p.n_normal, p.n_normal);
     // table row ids (slot offset + bin), 2 per 32-bit store
     uint32_t* dst = reinterpret_cast<uint32_t*>(p.bins_out + (size_t)row * NSLOT);
+    if (p.pair_layout) {   // [even slots | odd slots], ids = shared-memory line numbers (face_sum_pair_kernel)
+      constexpr int H = NSLOT / 2;
 #pragma unroll
-    for (int s = 0; s < NSLOT; s += 2)
-      dst[s / 2] = (uint32_t)(p.slot_off[s] + bins[s]) | ((uint32_t)(p.slot_off[s + 1] + bins[s + 1]) << 16);
+      for (int j = 0; j < H; j += 2) {
+        dst[j / 2] = (uint32_t)(p.pair_off[2 * j] + bins[2 * j]) | ((uint32_t)(p.pair_off[2 * j + 2] + bins[2 * j + 2]) << 16);
+        dst[H / 2 + j / 2] = (uint32_t)(p.pair_off[2 * j + 1] + bins[2 * j + 1]) | ((uint32_t)(p.pair_off[2 * j + 3] + bins[2 * j + 3]) << 16);
+      }
+    } else {
+#pragma unroll
+      for (int s = 0; s < NSLOT; s += 2)
+        dst[s / 2] = (uint32_t)(p.slot_off[s] + bins[s]) | ((uint32_t)(p.slot_off[s + 1] + bins[s + 1]) << 16);
+    }
     if (p.face_coords_out) {
 #pragma unroll
       for (int s = 0; s < NVF * 3; ++s) p.face_coords_out[in_face * (NVF * 3) + s] = bins[s];
@@ -188,17 +197,17 @@ __global__ void __launch_bounds__(256, 4) face_sum_kernel(FeatParams p) {
 // threads take one face (a float4 column each), so a warp reads S * 4-byte pieces of 32 / (S / 4) table rows per slot from
 // shared memory instead of L2, and writes whole 128-byte segments of the activation image.  Same slot order of the
 // additions as face_sum_kernel -> the same bits.
-template <int NVF, int S>
-__global__ void __launch_bounds__(512, 1) face_sum_smem_kernel(FeatParams p, int rows_total, int groups) {
+template <int NVF, int S, int NT>
+__global__ void __launch_bounds__(NT, 1) face_sum_smem_kernel(FeatParams p, int rows_total, int groups) {
   extern __shared__ float4 stab[];   // [rows_total][S / 4]
   constexpr int NSLOT = NVF * 3 + NVF + 1 + 3;
-  constexpr int s4 = S >> 2, ROWS_PER_IT = 512 / s4;
+  constexpr int s4 = S >> 2, ROWS_PER_IT = NT / s4;
   const int D = p.D, nslices = D / S;
   const int slice = blockIdx.x % nslices, g = blockIdx.x / nslices;
   const int tid = threadIdx.x;
   const int c = tid % s4;
   // the tables are model constants: staged before the wait on the preceding kernels
-  for (int i = tid; i < rows_total * s4; i += 512) {
+  for (int i = tid; i < rows_total * s4; i += NT) {
     const int row = i / s4, cc = i % s4;
     stab[i] = __ldg(reinterpret_cast<const float4*>(p.tables + (size_t)row * D + slice * S) + cc);
   }
@@ -238,11 +247,126 @@ __global__ void __launch_bounds__(512, 1) face_sum_smem_kernel(FeatParams p, int
 template <int NVF, int S>
 int launch_face_sum_smem(const FeatParams& p, int rows_total, int max_rows, cudaStream_t stream) {
   const size_t smem = (size_t)rows_total * S * sizeof(float);
-  MT_ENSURE_SMEM((face_sum_smem_kernel<NVF, S>), 200 * 1024);
   const int nslices = p.D / S;
   const int groups = max(1, min(148 / nslices, ceil_div(max_rows, 64)));
-  MT_LAUNCH_PDL((face_sum_smem_kernel<NVF, S>), groups * nslices, 512, smem, stream, p, rows_total, groups);
+  // MESHTOK_FACE_SUM_T=1024: 1 024 threads (64 registers) per CTA - one CTA per SM (the table slice is 128 KB), so the thread count IS
+  // the occupancy; it changed nothing, the kernel runs at the pace of the shared-memory pipe (see face_sum_pair_kernel)
+  static int nt = -1;
+  if (nt < 0) { const char* e = getenv("MESHTOK_FACE_SUM_T"); nt = (e && atoi(e) == 1024) ? 1024 : 512; }   // (1 024 threads measured no faster: 57.4 vs 57.6 us at C2)
+  if (nt == 1024) {
+    MT_ENSURE_SMEM((face_sum_smem_kernel<NVF, S, 1024>), 200 * 1024);
+    MT_LAUNCH_PDL((face_sum_smem_kernel<NVF, S, 1024>), groups * nslices, 1024, smem, stream, p, rows_total, groups);
+  } else {
+    MT_ENSURE_SMEM((face_sum_smem_kernel<NVF, S, 512>), 200 * 1024);
+    MT_LAUNCH_PDL((face_sum_smem_kernel<NVF, S, 512>), groups * nslices, 512, smem, stream, p, rows_total, groups);
+  }
   return MESHTOK_OK;
+}
+
+// Round 2: the same sum without shared-memory bank conflicts.  ncu on the kernel above: 1.4 M bank conflicts per launch - with 16-column
+// slices a table row is 64 bytes, so the two rows a quarter warp reads per instruction (two faces x one slot) share their banks half of
+// the time, and the kernel runs at the shared-memory pipe's pace (1 024 threads instead of 512 changed nothing: 57.4 vs 57.6 us).  Here
+// the slots are split into the even and the odd ones and LINE i of the table (128 bytes) holds row i of the even slots in its first 64
+// bytes and row i of the odd slots in its second 64.  The two faces of a quarter warp walk their slots in opposite order - lanes 0-3
+// even, odd, even, ... and lanes 4-7 odd, even, odd, ... - so every instruction reads one even and one odd row: disjoint banks.  No
+// select is needed for that: the ids are stored [even slots | odd slots] per face, a thread only swaps its two id pointers and its two
+// table-half pointers by lane parity, keeps one accumulator per half (the even slots are summed in the same order whichever half a lane
+// calls "first") and adds the two at the end (a + b = b + a bit for bit), then the bias.  Same instruction count as the kernel above
+// plus four adds.  (A version with EIGHT lanes per face - one half each, joined by shuffles - was conflict free too but executed 2.6 x
+// the instructions and took 65 us.)  The table slice is staged with cp.async, 16 copies per thread in flight.
+template <int NVF, int NT>
+__global__ void __launch_bounds__(NT, 1) face_sum_pair_kernel(FeatParams p, int lines, int groups) {
+  extern __shared__ float4 stab[];   // [lines][8]: even row (4 float4) | odd row (4 float4)
+  constexpr int NSLOT = NVF * 3 + NVF + 1 + 3, H = NSLOT / 2, HW = H / 2;   // slots, slots per half, id words per half
+  constexpr int S = 16, FACES_PER_IT = NT / 4;
+  const int D = p.D, nslices = D / S;
+  const int slice = blockIdx.x % nslices, g = blockIdx.x / nslices;
+  const int tid = threadIdx.x;
+  const int c = tid & 3, par = (tid >> 2) & 1;
+  // the tables are model constants: staged before the wait on the preceding kernels
+  {
+    const uint32_t sbase = tc::smem_u32(stab);
+#pragma unroll
+    for (int s = 0; s < NSLOT; ++s) {
+      const int n_s = (s + 1 < NSLOT ? p.slot_off[s + 1] : p.slot_off[NSLOT - 1] + p.n_normal) - p.slot_off[s];
+      const float* src = p.tables + (size_t)p.slot_off[s] * D + slice * S;
+      const uint32_t dst = sbase + (uint32_t)p.pair_off[s] * 128u + (uint32_t)(s & 1) * 64u;
+      for (int i = tid; i < n_s * 4; i += NT) {
+        const int r = i >> 2, cc = i & 3;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)r * 128u + (uint32_t)cc * 16u), "l"(src + (size_t)r * D + cc * 4) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + slice * S) + c);
+  pdl_wait();
+  const int n_rows = p.counts->n_faces;
+  const int per = (((n_rows + groups - 1) / groups) + 7) & ~7;   // whole 8-row groups of the image per CTA (r_lo is even)
+  const int r_lo = g * per, r_hi = min(n_rows, r_lo + per);
+  int row = r_lo + (tid >> 2);
+  // ids of the half this lane reads first / second: the current face's, the next one's and the one after.  The ids sit behind TWO
+  // dependent global loads (row_face -> bins); ncu on the round-1 kernel, which fetched both one iteration ahead, had 40 % of its stall
+  // samples waiting for them (an iteration is ~300 cycles of work).  Here row_face runs three faces ahead and the ids two.
+  uint32_t wf[HW], ws[HW], nf[HW], ns[HW], mf[HW], ms[HW];
+  auto load_ids = [&](int rf, uint32_t (&d0)[HW], uint32_t (&d1)[HW]) {
+    const uint32_t* bp = reinterpret_cast<const uint32_t*>(p.bins_out + (size_t)rf * NSLOT);
+#pragma unroll
+    for (int j = 0; j < HW; ++j) { d0[j] = __ldg(bp + par * HW + j); d1[j] = __ldg(bp + (par ^ 1) * HW + j); }
+  };
+  auto rf_at = [&](int r) { return r < r_hi ? __ldg(p.row_face + r) : 0; };
+  {
+    const int rf0 = rf_at(row), rf1 = rf_at(row + FACES_PER_IT);
+    if (row < r_hi) load_ids(rf0, wf, ws);
+    if (row + FACES_PER_IT < r_hi) load_ids(rf1, nf, ns);
+  }
+  int rf2 = rf_at(row + 2 * FACES_PER_IT);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  const float4* tf = stab + par * 4 + c;          // the half read first: even rows for lanes 0-3 of a quarter warp, odd rows for lanes 4-7
+  const float4* ts = stab + (par ^ 1) * 4 + c;
+  for (; row < r_hi; row += FACES_PER_IT) {
+    if (row + 2 * FACES_PER_IT < r_hi) load_ids(rf2, mf, ms);
+    rf2 = rf_at(row + 3 * FACES_PER_IT);
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+#pragma unroll
+    for (int j = 0; j < HW; ++j) {
+      const float4 f0 = tf[(wf[j] & 0xffffu) * 8];
+      const float4 s0 = ts[(ws[j] & 0xffffu) * 8];
+      const float4 f1 = tf[(wf[j] >> 16) * 8];
+      const float4 s1 = ts[(ws[j] >> 16) * 8];
+      add4(a0, f0);
+      add4(a1, s0);
+      add4(a0, f1);
+      add4(a1, s1);
+    }
+    add4(a0, a1);
+    add4(a0, b4);
+    const float4 sum = a0;
+    const int col = slice * S + c * 4;
+    if (p.x0) *reinterpret_cast<float4*>(p.x0 + (size_t)row * D + col) = sum;
+    if (p.x0_image) tc::image_store4(p.x0_image, D, row, col, sum);
+#pragma unroll
+    for (int j = 0; j < HW; ++j) { wf[j] = nf[j]; ws[j] = ns[j]; nf[j] = mf[j]; ns[j] = ms[j]; }
+  }
+  pdl_launch_dependents();
+}
+
+// Shared-memory lines of the pair layout and every slot's first line; 0 when the layout does not apply (slice not 16 columns, odd slot
+// count per half, table too large for one SM) or MESHTOK_FACE_SUM_PAIR=0 asks for the round-1 kernel (A/B runs).
+static int face_pair_plan(const FeatParams& p, int* pair_off) {
+  static int on = -1;
+  if (on < 0) { const char* e = getenv("MESHTOK_FACE_SUM_PAIR"); on = (e && atoi(e) == 0) ? 0 : 1; }
+  const int nslot = p.nvf * 4 + 4;
+  if (on == 0 || p.D % 16 != 0 || p.D / 16 > 148 || (nslot / 2) % 2 != 0) return 0;   // (only fields that both launchers see alike)
+  int lines[2] = {0, 0};
+  for (int s = 0; s < nslot; ++s) {
+    const int n = (s + 1 < nslot ? p.slot_off[s + 1] : p.slot_off[nslot - 1] + p.n_normal) - p.slot_off[s];
+    pair_off[s] = lines[s & 1];
+    lines[s & 1] += n;
+  }
+  const int L = max(lines[0], lines[1]);
+  if (L > 65535 || (size_t)L * 128 > (size_t)200 * 1024) return 0;
+  return L;
 }
 
 constexpr int FACE_SUM_SMEM_MAX = 200 * 1024;
@@ -263,8 +387,10 @@ int launch_face_bins(const FeatParams& p, long long max_in_faces, cudaStream_t s
   if (rc != MESHTOK_OK) return rc;
   if (max_in_faces == 0) return MESHTOK_OK;
   const int blocks1 = (int)max(1ll, min((max_in_faces + 127) / 128, 148ll * 16));
-  if (p.nvf == 3) MT_LAUNCH_PDL(face_bins_kernel<3>, blocks1, 128, 0, stream, p);
-  else MT_LAUNCH_PDL(face_bins_kernel<4>, blocks1, 128, 0, stream, p);
+  FeatParams q = p;
+  q.pair_layout = face_pair_plan(p, q.pair_off) > 0 ? 1 : 0;   // the id format follows the kernel launch_face_sum will take
+  if (p.nvf == 3) MT_LAUNCH_PDL(face_bins_kernel<3>, blocks1, 128, 0, stream, q);
+  else MT_LAUNCH_PDL(face_bins_kernel<4>, blocks1, 128, 0, stream, q);
   return MESHTOK_OK;
 }
 
@@ -273,6 +399,24 @@ int launch_face_sum(const FeatParams& p, int max_rows, cudaStream_t stream) {
   int rc = face_embed_check(p);
   if (rc != MESHTOK_OK) return rc;
   if (max_rows == 0) return MESHTOK_OK;
+  {
+    FeatParams q = p;
+    const int L = face_pair_plan(p, q.pair_off);
+    if (L > 0) {
+      q.pair_layout = 1;
+      const int nslices = p.D / 16;
+      const int groups = max(1, min(148 / nslices, ceil_div(max_rows, 64)));
+      const size_t smem = (size_t)L * 128;
+      if (p.nvf == 3) {
+        MT_ENSURE_SMEM((face_sum_pair_kernel<3, 512>), 200 * 1024);
+        MT_LAUNCH_PDL((face_sum_pair_kernel<3, 512>), groups * nslices, 512, smem, stream, q, L, groups);
+      } else {
+        MT_ENSURE_SMEM((face_sum_pair_kernel<4, 512>), 200 * 1024);
+        MT_LAUNCH_PDL((face_sum_pair_kernel<4, 512>), groups * nslices, 512, smem, stream, q, L, groups);
+      }
+      return MESHTOK_OK;
+    }
+  }
   // table slices in shared memory when a slice of >= 8 columns fits; else table rows straight from L2
   const int rows_total = p.n_coor * p.nvf * 3 + p.n_angle * p.nvf + p.n_area + p.n_normal * 3;
   int S = 0;

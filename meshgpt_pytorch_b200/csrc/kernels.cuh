@@ -24,6 +24,11 @@ struct FeatParams {
   uint8_t* x0_image;        // split-bf16 activation image of x0 (tc_common.cuh) or null
   int64_t* face_coords_out; // (B,F,nvf*3) or null
   uint16_t* bins_out;       // (B*F, nvf*4+4) workspace: folded-table row id (slot offset + bin) of every slot of every input face b*F+f
+  // Set by the launchers (features.cu), not by the caller: pair_layout = 1 -> the ids are written for face_sum_pair_kernel: per face
+  // [ids of the even slots | ids of the odd slots], each id = pair_off[slot] + bin = the 128-byte LINE of the shared-memory table that holds
+  // the even slot's row in its first half and the odd slot's row in its second half
+  int pair_layout;
+  int pair_off[20];
 };
 // features + discretisation -> table row ids per INPUT face: needs nothing from the topology kernel (runs next to it on the side stream)
 int launch_face_bins(const FeatParams& p, long long max_in_faces, cudaStream_t stream);

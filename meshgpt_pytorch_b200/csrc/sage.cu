@@ -479,10 +479,10 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
         }
         if (exp == 2) { a0.x += __int_as_float(off); continue; }   // experiment: no neighbour row reads
         const float4 v0 = p0a[off], v1 = p0b[off], v2 = p1a[off], v3 = p1b[off];
-        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
-        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
-        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
-        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+        add4(a0, v0);   // packed fp32 adds (FADD2): the same roundings in half the issue slots
+        add4(a1, v1);
+        add4(a2, v2);
+        add4(a3, v3);
       }
       const float rc = __frcp_rn(fmaxf((float)(e_true - s), 1.f));
       const int row = r0 + lrow;
