@@ -235,7 +235,8 @@ def test_large_batch_aggregation_kernel_gives_the_same_tokens(tmp_path):
     script.write_text(_GROUP_SCRIPT.format(root=root, tests=os.path.join(root, "tests")))
     outs = {}
     for name, env in (("one slice", dict(MESHTOK_GATHER_WIDE_GROUP="1")), ("groups of 2", dict(MESHTOK_GATHER_WIDE_GROUP="2")), ("default", {}),
-                      ("round 1 per slice", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="0")), ("round 1 groups", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="1"))):
+                      ("round 1 per slice", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="0")), ("round 1 groups", dict(MESHTOK_GATHER_WIDE="0", MESHTOK_GATHER_GROUP="1")),
+                      ("fused into the output linears", dict(MESHTOK_GATHER_FUSED="1"))):
         path = tmp_path / f"{name.replace(' ', '_')}.pt"
         r = subprocess.run([sys.executable, str(script), str(path)], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-2000:]
