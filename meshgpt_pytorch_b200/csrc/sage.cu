@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
                                                                            uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
                                                                            const int* __restrict__ edge_off, int rows_cap, int edges_cap, int group,
                                                                            int nbuf, long long* __restrict__ trace, int exp,
-                                                                           const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes) {
+                                                                           const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes, int early) {
   // [nbuf][buf_rows + 1][8] float4 x slices (row buf_rows stays zero: what an invalid source id points at) | [rows_cap + 1] local row
   // pointers | [edges_cap] source row * 8 (u16) | [2] mbarriers.  box_rows > 0: the slices arrive by TMA (n_boxes boxes of box_rows x 32
   // columns, one elected thread, completion on an mbarrier); box_rows == 0: by 16-byte cp.async copies of all threads.
@@ -384,28 +384,28 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   int* sptr = reinterpret_cast<int*>(sx + (size_t)nbuf * buf_stride);
   unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
   uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ssrc + edges_cap + 3) & ~(uintptr_t)7);
-  pdl_wait();
+  // Programmatic dependent launch: this kernel's CTAs become resident while the linear in front of it is still in its last round.  The
+  // CSR of the mesh (face / edge offsets, row pointers, source ids) was written by the topology kernels, which completed before that
+  // linear passed ITS wait, so it is staged BEFORE griddepcontrol.wait (L2 loads, ld.global.cg: no line an earlier launch left in this
+  // SM's L1 can be taken for it); only the x slices - the linear's output - wait.  With TMA the last warp alone waits and issues the
+  // copies (every read of x goes through the mbarrier its copies complete); without, every thread copies, so every thread waits.
+  if (!early) pdl_wait();   // MESHTOK_GATHER_EARLY=0: everything behind the wait, as before (A/B)
   GM_STAMP(0, gtimer()); GM_STAMP(1, clock64()); GM_STAMP(7, smid());
   const int nslices = d / S;
   const int ngroups = (nslices + group - 1) / group;
   const int b = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
   const int slice0 = grp * group, slice1 = min(nslices, slice0 + group);
-  const int r0 = __ldg(face_off + b);
-  const int n_b = min(__ldg(face_off + b + 1) - r0, rows_cap);
-  const int e0 = __ldg(edge_off + b);                       // = indptr[r0]
-  const long long e1_true = __ldg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
+  const int r0 = __ldcg(face_off + b);
+  const int n_b = min(__ldcg(face_off + b + 1) - r0, rows_cap);
+  const int e0 = __ldcg(edge_off + b);                       // = indptr[r0]
+  const long long e1_true = __ldcg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
   const int tid = threadIdx.x;
   const int c = tid % s4;
   const uint32_t sx_addr = tc::smem_u32(sx);
-  if (tma && tid == 0) {
-    for (int k = 0; k < nbuf; ++k) tc::mbar_init(&full[k], 1);
-    tc::fence_barrier_init();
-    tc::fence_proxy_async_smem();
-  }
-  if (tma) __syncthreads();
+  constexpr int issuer = NTHR - 32;   // first lane of the last warp
   auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf
     if (tma) {
-      if (tid == 0) {   // rows beyond the mesh (the next mesh's, or zeros beyond the tensor) land in the buffer too and are never referenced
+      if (tid == issuer) {   // rows beyond the mesh (the next mesh's, or zeros beyond the tensor) land in the buffer too and are never referenced
         tc::mbar_arrive_expect_tx(&full[buf], (uint32_t)n_boxes * (uint32_t)box_rows * 128u);
         for (int i = 0; i < n_boxes; ++i)
           tc::tma_load_2d(sx + (size_t)buf * buf_stride + (size_t)i * box_rows * s4, &tmap, slice * S, r0 + i * box_rows, &full[buf]);
@@ -420,19 +420,28 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  issue(slice0, 0);
+  if (tma && tid >= issuer) {   // the last warp: barriers, wait for the producer of x, first slice on its way - then its share of the CSR
+    if (tid == issuer) {
+      for (int k = 0; k < nbuf; ++k) tc::mbar_init(&full[k], 1);
+      tc::fence_barrier_init();
+      tc::fence_proxy_async_smem();
+    }
+    pdl_wait();
+    issue(slice0, 0);
+    __syncwarp();
+  }
   GM_STAMP(2, 0);
   const int zero_row = tma ? buf_rows : n_b;
   if (tid < s4)
     for (int k = 0; k < nbuf; ++k) sx[(size_t)k * buf_stride + zero_row * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
   const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
   const bool fast = n_e <= edges_cap && e1_true <= cap && (buf_rows + 1) * s4 <= 65536;
-  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldg(indptr + r0 + i) - e0;
+  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldcg(indptr + r0 + i) - e0;
   if (fast) {
     for (int base = tid; base < n_e; base += NTHR * 4) {
       int t[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = base + j * NTHR < n_e ? __ldg(src + e0 + base + j * NTHR) : 0;
+      for (int j = 0; j < 4; ++j) t[j] = base + j * NTHR < n_e ? __ldcg(src + e0 + base + j * NTHR) : 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (base + j * NTHR < n_e) {
@@ -440,6 +449,10 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
           ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4);
         }
     }
+  }
+  if (!tma) {
+    pdl_wait();
+    issue(slice0, 0);
   }
   GM_STAMP(3, clock64());
   const size_t img_tile = (size_t)(d >> 5) * tc::IMG_BLOCK;   // bytes per 128-row tile
@@ -662,6 +675,8 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     }
     static int gexp = -1;
     if (gexp < 0) { const char* e = getenv("MESHTOK_GATHER_EXP"); gexp = e ? atoi(e) : 0; }
+    static int early = -1;   // CSR staged ahead of griddepcontrol.wait (default); 0 = behind it (A/B)
+    if (early < 0) { const char* e = getenv("MESHTOK_GATHER_EARLY"); early = (e && atoi(e) == 0) ? 0 : 1; }
     if (best < 1e30) {
       const int nbuf = group >= 2 ? 2 : 1;
       const size_t smem_w = align_up(nbuf * per_buf + csr, 128);
@@ -670,11 +685,11 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       if (group == 1) {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 113 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early);
       } else {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<1024, 1>), B * ngroups, 1024, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early);
       }
       return MESHTOK_OK;
     }
