@@ -346,6 +346,162 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float4* __restrict
   }
 }
 
+
+// Residual LFQ, round 2: THREAD = ROW.  The warp-per-two-rows kernel above spends its instructions on weight loads (every lane re-reads
+// its 14 x 6 weights from L1 for every pair of rows) and on the butterfly that joins 32 partial sums per dot product: ~210 instructions
+// per row, 35 us for the 55 168 rows of the quad workload.  Here a thread keeps all `bits` dot products of ITS row in registers and walks
+// the row's columns: per 4 columns one 16-byte read of the row and, per projected dimension, one 16-byte BROADCAST read of the weights
+// (shared memory, staged once per CTA before griddepcontrol.wait - they are model constants) + 4 FMAs; no shuffles, no reductions, the
+// sign bits and the residual levels are per-thread scalar code: ~90 instructions per row.  Rows arrive as 128-row x 32-column chunks by
+// cp.async (coalesced 128-byte pieces), double buffered, in rows of 36 floats so that the eight 16-byte reads of a quarter warp cover all
+// 32 banks.  Dot products accumulate in column order (one FMA chain per projected dimension).
+constexpr int LFQ_TR = 128;   // rows per tile = threads per CTA
+constexpr int LFQ_CH = 32;    // columns per staged chunk
+constexpr int LFQ_LD = 36;    // floats per staged row
+
+// DS = 2: two adjacent lanes share a row, each owns every other projected dimension (twice the warps for the same rows: the kernel is
+// bound by the latency of its shared-memory reads at ~3 warps per scheduler, ncu); the weight rows are padded by 4 floats so that the two
+// 16-byte broadcast reads of an instruction fall into different banks.
+template <int NB, bool EXACT, int RPT, int DS>   // NB accumulators per row; EXACT: bits == NB (no guards); RPT rows per thread
+__global__ void __launch_bounds__(LFQ_TR * DS / RPT) lfq_rows_kernel(const float* __restrict__ rows, int D, const float* __restrict__ w_in,
+                                                                     const float* __restrict__ b_in, int bits, int Q,
+                                                                     const float* __restrict__ w_out, const float* __restrict__ b_out,
+                                                                     int32_t* __restrict__ codes, float* __restrict__ quantized_out,
+                                                                     const int* __restrict__ n_rows_dev, int max_rows) {
+  constexpr int NT = LFQ_TR * DS / RPT;   // threads
+  constexpr int RS = LFQ_TR / RPT;        // a thread's rows are RS apart in the tile
+  constexpr int NBT = NB / DS;            // projected dimensions per thread: h, h + DS, ...
+  static_assert(NB % DS == 0, "NB must split evenly");
+  extern __shared__ __align__(16) float lfq_sm[];
+  const int WLD = D + 4;                  // floats per staged weight row
+  float* wsm = lfq_sm;                    // [bits][WLD]
+  float* tile = lfq_sm + bits * WLD;      // [2][LFQ_TR][LFQ_LD]
+  const int tid = threadIdx.x;
+  const int trow = tid / DS, h = tid % DS;
+  {
+    const int d4 = D >> 2;
+    for (int i = tid; i < bits * d4; i += NT) {
+      const int dd = i / d4, c4 = i - dd * d4;
+      *reinterpret_cast<float4*>(wsm + dd * WLD + 4 * c4) = __ldg(reinterpret_cast<const float4*>(w_in + (size_t)dd * D) + c4);
+    }
+  }
+  pdl_wait();
+  const int n = n_rows_dev ? min(*n_rows_dev, max_rows) : max_rows;
+  const int nchunks = D / LFQ_CH;
+  const uint32_t tile_addr = (uint32_t)__cvta_generic_to_shared(tile);
+  for (int tile0 = blockIdx.x * LFQ_TR; tile0 < n; tile0 += gridDim.x * LFQ_TR) {
+    auto issue = [&](int k, int buf) {   // chunk k of this tile's rows -> buffer buf (rows beyond n are left as they are: never used)
+#pragma unroll
+      for (int j = 0; j < LFQ_TR * (LFQ_CH / 4) / NT; ++j) {
+        const int idx = tid + j * NT, r = idx >> 3, c4 = idx & 7;
+        if (tile0 + r < n) {
+          const float* src = rows + (size_t)(tile0 + r) * D + k * LFQ_CH + c4 * 4;
+          const uint32_t dst = tile_addr + (uint32_t)((buf * LFQ_TR + r) * LFQ_LD + c4 * 4) * 4u;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    float p[RPT][NBT];
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr)
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) p[rr][i] = 0.f;
+    issue(0, 0);
+    for (int k = 0; k < nchunks; ++k) {
+      const int buf = k & 1;
+      if (k + 1 < nchunks) {
+        issue(k + 1, buf ^ 1);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+      }
+      __syncthreads();   // chunk k (and, the first time, the weights) visible to every thread
+      const float* tr = tile + (buf * LFQ_TR + trow) * LFQ_LD;
+      const float* wk = wsm + h * WLD + k * LFQ_CH;
+#pragma unroll
+      for (int c4 = 0; c4 < LFQ_CH / 4; ++c4) {
+        float4 r[RPT];
+#pragma unroll
+        for (int rr = 0; rr < RPT; ++rr) r[rr] = *reinterpret_cast<const float4*>(tr + rr * RS * LFQ_LD + 4 * c4);
+#pragma unroll
+        for (int i = 0; i < NBT; ++i) {
+          if (EXACT || h + DS * i < bits) {
+            const float4 w = *reinterpret_cast<const float4*>(wk + i * DS * WLD + 4 * c4);   // one broadcast read serves RPT rows
+#pragma unroll
+            for (int rr = 0; rr < RPT; ++rr)
+              p[rr][i] = fmaf(r[rr].w, w.w, fmaf(r[rr].z, w.z, fmaf(r[rr].y, w.y, fmaf(r[rr].x, w.x, p[rr][i]))));
+          }
+        }
+      }
+      __syncthreads();   // every read of this buffer is done before the iteration after next refills it
+    }
+    float bias[NBT];
+#pragma unroll
+    for (int i = 0; i < NBT; ++i) bias[i] = (EXACT || h + DS * i < bits) ? __ldg(b_in + h + DS * i) : 0.f;
+#pragma unroll
+    for (int rr = 0; rr < RPT; ++rr) {
+      const int row = tile0 + trow + rr * RS;
+      const bool live = row < n;
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) p[rr][i] += bias[i];
+      float qsum[NBT];
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) qsum[i] = 0.f;
+      for (int l = 0; l < Q; ++l) {
+        const float scale = exp2f(-(float)l);
+        unsigned code = 0u;
+#pragma unroll
+        for (int i = 0; i < NBT; ++i) {
+          if (EXACT || h + DS * i < bits) {
+            const bool bit = p[rr][i] > 0.f;   // dimension 0 is the most significant bit
+            code |= bit ? (1u << (bits - 1 - (h + DS * i))) : 0u;
+            const float q = bit ? scale : -scale;
+            p[rr][i] -= q;
+            qsum[i] += q;
+          }
+        }
+        if (DS == 2) code |= __shfl_xor_sync(0xffffffffu, code, 1);
+        if (live && h == 0) codes[(size_t)row * Q + l] = (int32_t)code;
+      }
+#pragma unroll
+      for (int i = 0; i < NBT; ++i) p[rr][i] = qsum[i];   // (kept for project_out below)
+    }
+    if (quantized_out != nullptr) {   // project_out: (D x bits) . qsum + b_out, through the staging tile for coalesced stores
+      for (int k = 0; k < nchunks; ++k) {
+#pragma unroll
+        for (int rr = 0; rr < RPT; ++rr) {
+          float* tw = tile + (trow + rr * RS) * LFQ_LD;
+#pragma unroll
+          for (int c4 = 0; c4 < LFQ_CH / 4; ++c4) {
+            float o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c = k * LFQ_CH + c4 * 4 + j;
+              float t = 0.f;
+#pragma unroll
+              for (int i = 0; i < NBT; ++i)
+                if (EXACT || h + DS * i < bits) t = fmaf(p[rr][i], __ldg(w_out + (size_t)c * bits + h + DS * i), t);
+              if (DS == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
+              o[j] = t + __ldg(b_out + c);
+            }
+            if (h == 0) *reinterpret_cast<float4*>(tw + 4 * c4) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LFQ_TR * (LFQ_CH / 4) / NT; ++j) {
+          const int idx = tid + j * NT, r = idx >> 3, c4 = idx & 7;
+          if (tile0 + r < n)
+            *reinterpret_cast<float4*>(quantized_out + (size_t)(tile0 + r) * D + k * LFQ_CH + c4 * 4) = *reinterpret_cast<const float4*>(tile + r * LFQ_LD + c4 * 4);
+        }
+        __syncthreads();
+      }
+    }
+  }
+  pdl_launch_dependents();
+}
+
 }  // namespace
 
 int launch_scatter_mean(const float* y, int D, const int* vptr, const int* vinc, float* avg, const Counts* counts,
@@ -374,6 +530,40 @@ int launch_lfq(const float* rows, int D, const float* w_in, const float* b_in, i
   MT_CHECK_ARG(D >= 1 && D <= 512, "lfq: dim %d must be <= 512", D);
   if (max_rows == 0) return MESHTOK_OK;
   MT_CHECK_ARG(bits >= 1 && bits <= 16, "lfq: %d bits per level (codebook_size up to 65536 is supported)", bits);
+  // thread = row (lfq_rows_kernel): whole 32-column chunks, 16-byte aligned rows and weights; MESHTOK_LFQ_ROWS=0 keeps the warp kernel (A/B)
+  static int use_rows = -1;
+  if (use_rows < 0) { const char* e = getenv("MESHTOK_LFQ_ROWS"); use_rows = (e && atoi(e) == 0) ? 0 : 1; }
+  const size_t smem_rows = ((size_t)bits * (D + 4) + 2 * (size_t)LFQ_TR * LFQ_LD) * sizeof(float);
+  if (use_rows && D % LFQ_CH == 0 && (reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(w_in) | reinterpret_cast<uintptr_t>(quantized_out)) % 16 == 0 &&
+      smem_rows <= 200 * 1024) {
+    const int blocks_r = max(1, min(ceil_div(max_rows, LFQ_TR), 148 * 4));
+#define LR1(NB, EX, R, S)                                                                                                                 \
+  do {                                                                                                                                    \
+    MT_ENSURE_SMEM((lfq_rows_kernel<NB, EX, R, S>), 200 * 1024);                                                                          \
+    MT_LAUNCH_PDL((lfq_rows_kernel<NB, EX, R, S>), blocks_r, LFQ_TR * S / R, smem_rows, stream, rows, D, w_in, b_in, bits, Q, w_out,      \
+                  b_out, codes, quantized_out, n_rows_dev, max_rows);                                                                     \
+  } while (0)
+#define LR(NB, EX)                                                                                                                        \
+  do {                                                                                                                                    \
+    if (variant == 12) LR1(NB, EX, 1, 2);                                                                                                 \
+    else if (variant == 22) LR1(NB, EX, 2, 2);                                                                                            \
+    else if (variant == 21) LR1(NB, EX, 2, 1);                                                                                            \
+    else LR1(NB, EX, 1, 1);                                                                                                               \
+  } while (0)
+    // variant = 10 * rows per thread + lanes per row (MESHTOK_LFQ_VARIANT=11|21|12|22; measured on C3, B200: see DESIGN)
+    static int variant = -1;
+    if (variant < 0) { const char* e = getenv("MESHTOK_LFQ_VARIANT"); variant = e ? atoi(e) : 12; }
+    if (bits == 14) LR(14, true);
+    else if (bits == 16) LR(16, true);
+    else if (bits == 12) LR(12, true);
+    else if (bits == 10) LR(10, true);
+    else if (bits == 8) LR(8, true);
+    else if (bits < 8) LR(8, false);
+    else LR(16, false);
+#undef LR1
+#undef LR
+    return MESHTOK_OK;
+  }
   const int blocks = max(1, min(ceil_div(max_rows, 16), 148 * 16));
   const int per = ceil_div(D, 32);
 #define LQ(P, V) lfq_kernel<P, V><<<blocks, 256, 0, stream>>>(rows, D, w_in, b_in, bits, Q, w_out, b_out, codes, quantized_out, n_rows_dev, max_rows)
