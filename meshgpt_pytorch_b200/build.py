@@ -52,7 +52,7 @@ def _headers():
     return hs
 
 
-def build_library(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+def build_library(force: bool = False, verbose: bool = False, experiments: bool = False, variant: str = "", defines=()) -> str:
     """experiments: a SECOND library, lib/libmeshtok_exp.so, compiled with -DMESHTOK_EXPERIMENTS - the timing experiments that skip work
     (and so produce wrong results) exist only there; load it with MESHTOK_LIBRARY=.../libmeshtok_exp.so.  The product build has none."""
     global OBJ_DIR, LIB_PATH, COMMON_FLAGS
@@ -60,6 +60,10 @@ def build_library(force: bool = False, verbose: bool = False, experiments: bool 
         OBJ_DIR = os.path.join(HERE, "lib", "obj_exp")
         LIB_PATH = os.path.join(HERE, "lib", "libmeshtok_exp.so")
         COMMON_FLAGS = COMMON_FLAGS + ["-DMESHTOK_EXPERIMENTS"]
+    if variant:   # A/B builds: lib/libmeshtok_<variant>.so with extra -D flags (python build.py --variant early -DMESHTOK_PDL_EARLY=0)
+        OBJ_DIR = os.path.join(HERE, "lib", "obj_" + variant)
+        LIB_PATH = os.path.join(HERE, "lib", f"libmeshtok_{variant}.so")
+        COMMON_FLAGS = COMMON_FLAGS + list(defines)
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
     hdr_digest = _digest(_headers())
@@ -105,4 +109,6 @@ def build_library(force: bool = False, verbose: bool = False, experiments: bool 
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv, variant=_variant,
+                        defines=[a for a in sys.argv if a.startswith("-D")]))

@@ -87,7 +87,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     ++::meshtok::g_launch_count;                                                                           \
     MT_CHECK_CUDA(::meshtok::launch_pdl(kernel, dim3(grid), dim3(block), smem, stream, __VA_ARGS__));      \
   } while (0)
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef MESHTOK_PDL_EARLY
+#define MESHTOK_PDL_EARLY 0
+#endif
+// -DMESHTOK_PDL_EARLY=1 (python build.py --variant early -DMESHTOK_PDL_EARLY=1): pdl_wait() also SIGNALS - once every CTA of a kernel has
+// passed its wait the next kernel's CTAs may become resident in this kernel's tail and run their launch latency and prologue there.
+// (Signalling only AFTER the own wait keeps the invariant every prologue relies on: when kernel n+1 runs anything at all, kernels
+// <= n-1 are complete and visible.)  MEASURED at C2 on one box, two runs each: 0.805 / 0.806 ms against 0.806 / 0.805 ms with the signal
+// at the end of every CTA's work - the ramps of these kernels are pipeline fill and wave tails, not launch latency.  Off.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if MESHTOK_PDL_EARLY
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
