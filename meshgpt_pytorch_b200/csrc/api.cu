@@ -42,6 +42,7 @@ struct Workspace {
   int* mesh_counts;
   int* offs;
   int *deg_out, *deg_in, *face_row, *row_face, *vert_row, *vptr, *vinc, *indptr, *src;
+  uint8_t* lcsr;     // per-mesh local CSR blocks for the aggregation kernel (launch_local_csr)
   int *ecount, *cursor, *etmp;
   float* x0;
   float *xp, *agg;
@@ -188,6 +189,7 @@ int carve_all(const meshtok_model* m, int B, int F, int V, int E, int64_t cap, l
   const size_t BF = total_faces > 0 ? (size_t)min((long long)slots, total_faces) : slots;
   const size_t BV = total_vertices > 0 ? (size_t)min((long long)B * V, total_vertices) : (size_t)B * V;
   carve_topology(c, w, B, F, m->nvf, V, E, cap, BF, BV, t);
+  w->lcsr = c.take<uint8_t>((size_t)B * local_csr_stride(F));
   w->rows_cap = (int)BF;
   w->vrows_cap = (int)BV;
   const int D = m->dim_codebook, Q = m->num_quantizers;
@@ -528,6 +530,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
     if (rc != MESHTOK_OK) return rc;
+    if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, s)) != MESHTOK_OK) return rc;
   } else {
     TopoParams pe = p;
     pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
@@ -536,6 +539,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
     MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
     if ((rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
+    // the aggregation kernels' per-mesh CSR blocks: once per batch, behind the adjacency on the side stream
+    if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, side->stream)) != MESHTOK_OK) return rc;
     MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
     edges_pending = true;
   }
@@ -599,7 +604,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
       const bool gather_fused = b2b && w.img_agg != nullptr && linear_tc_gather_ok(ly.dim_in, ly.dim_out, mode);
       if (!gather_fused) {
         ProfScope ps(PROF_SAGE_GATHER, s);
-        if ((rc = launch_gather_mean(xp_cur, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s)) != MESHTOK_OK) return rc;
+        if ((rc = launch_gather_mean(xp_cur, ly.dim_in, w.indptr, w.src, a->edge_capacity, simt ? w.agg : nullptr, simt ? nullptr : w.img_agg, w.counts, max_rows, w.offs, B, F, s, w.lcsr)) != MESHTOK_OK) return rc;
       }
       // out = lin_l(agg) + lin_r(x)  [-> normalise (-> SiLU -> LayerNorm)]
       if (fused) {

@@ -38,9 +38,16 @@ int launch_face_sum(const FeatParams& p, int max_rows, cudaStream_t stream);
 // ---- K4 ------------------------------------------------------------------------------------------
 // agg[t] = mean over in-edges (s -> t) of x[s]; sum in ascending CSR order / max(count, 1).
 // agg (fp32 rows) and agg_image (split-bf16 activation image) are both optional outputs.
+// lcsr (optional): the per-mesh local CSR blocks of launch_local_csr - a CTA then takes its mesh's row pointers and source ids with ONE
+// bulk copy instead of three dependent global round trips.
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity,
                        float* agg, void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F,
-                       cudaStream_t stream);
+                       cudaStream_t stream, const void* lcsr = nullptr);
+// Per mesh one block of local_csr_stride(F) bytes: {n_e, fast, e0, 0} | row pointers relative to the mesh's first edge (F + 1 ints) |
+// source rows relative to the mesh's first row, pre-multiplied for the aggregation kernel's shared-memory layout (5 F u16).
+// Runs once per batch after the face CSR exists (next to the topology kernels, off the critical path); all five layers read it.
+size_t local_csr_stride(int F);
+int launch_local_csr(const int* indptr, const int* src, long long edge_capacity, const int* face_off, int B, int F, void* lcsr, cudaStream_t stream);
 int gather_mean_read_trace(long long* out, int n);   // timing experiments, see sage.cu
 // in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).
 // image_out (optional): the same rows as a split-bf16 activation image for the next tcgen05 linear.

@@ -363,13 +363,51 @@ __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const f
 // One CTA per (mesh, group of `group` consecutive slices), slices double buffered when group >= 2.  The eight threads of a quarter warp
 // (four faces x two halves) read eight different 16-byte chunks in every instruction whatever rows they come from: a face takes its two
 // 8-column pairs in the order (face & 1) and the two chunks of a pair in the order (face >> 1) & 1 - no bank conflicts.
+// ---- per-mesh local CSR blocks (round 2, last session) -------------------------------------------------------------------------------
+// clock64 trace of the wide kernel at C2: of a CTA's ~23 k cycles, ~6 k went into its prologue - face / edge offsets, then row pointers
+// and source ids (dependent global round trips), then the conversion into shared memory - repeated by every (mesh, slice) CTA of all
+// five layers.  local_csr_kernel does that conversion ONCE per batch and mesh, into a block with the aggregation kernel's shared-memory
+// layout, so the CTA's prologue is one bulk copy (cp.async.bulk, completion on an mbarrier, issued ahead of griddepcontrol.wait).
+__host__ __device__ inline int lcsr_ptr_bytes(int F) { return (((F + 1) * 4) + 15) & ~15; }
+__host__ __device__ inline int lcsr_src_bytes(int F) { return ((5 * F * 2) + 15) & ~15; }
+__host__ __device__ inline int lcsr_stride_bytes(int F) { return 16 + lcsr_ptr_bytes(F) + lcsr_src_bytes(F); }
+static inline void gather_tma_geometry(int F, int* box_rows, int* n_boxes) {   // boxes of at most 256 rows x 32 columns
+  *n_boxes = (F + 255) / 256;
+  *box_rows = (F + *n_boxes - 1) / *n_boxes;
+}
+
+__global__ void __launch_bounds__(256) local_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ src, long long cap,
+                                                        const int* __restrict__ face_off, const int* __restrict__ edge_off, int F,
+                                                        int zero_row, uint8_t* __restrict__ lcsr) {
+  const int b = blockIdx.x;
+  const int edges_cap = 5 * F;
+  uint8_t* blk = lcsr + (size_t)b * lcsr_stride_bytes(F);
+  int* hdr = reinterpret_cast<int*>(blk);
+  int* sptr = reinterpret_cast<int*>(blk + 16);
+  unsigned short* ssrc = reinterpret_cast<unsigned short*>(blk + 16 + lcsr_ptr_bytes(F));
+  const int r0 = face_off[b];
+  const int n_b = min(face_off[b + 1] - r0, F);
+  const int e0 = edge_off[b];
+  const long long e1_true = edge_off[b + 1];
+  const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
+  const bool fast = n_e <= edges_cap && e1_true <= cap && (zero_row + 1) * 8 <= 65536;
+  if (threadIdx.x == 0) { hdr[0] = n_e; hdr[1] = fast ? 1 : 0; hdr[2] = e0; hdr[3] = 0; }
+  for (int i = threadIdx.x; i <= n_b; i += blockDim.x) sptr[i] = indptr[r0 + i] - e0;
+  if (fast)
+    for (int q = threadIdx.x; q < n_e; q += blockDim.x) {
+      const unsigned nb = (unsigned)(src[e0 + q] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
+      ssrc[q] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * 8u);
+    }
+}
+
 template <int NTHR, int CTAS>
 __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const float* __restrict__ x, int d, const int* __restrict__ indptr,
                                                                            const int* __restrict__ src, long long cap, float* __restrict__ agg,
                                                                            uint8_t* __restrict__ agg_image, const int* __restrict__ face_off,
                                                                            const int* __restrict__ edge_off, int rows_cap, int edges_cap, int group,
                                                                            int nbuf, long long* __restrict__ trace, int exp,
-                                                                           const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes, int early) {
+                                                                           const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes, int early,
+                                                                           const uint8_t* __restrict__ lcsr) {
   // [nbuf][buf_rows + 1][8] float4 x slices (row buf_rows stays zero: what an invalid source id points at) | [rows_cap + 1] local row
   // pointers | [edges_cap] source row * 8 (u16) | [2] mbarriers.  box_rows > 0: the slices arrive by TMA (n_boxes boxes of box_rows x 32
   // columns, one elected thread, completion on an mbarrier); box_rows == 0: by 16-byte cp.async copies of all threads.
@@ -381,9 +419,12 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   const bool tma = box_rows > 0;
   const int buf_rows = tma ? box_rows * n_boxes : rows_cap;
   const int buf_stride = (buf_rows + 1) * s4 + ((buf_rows + 1) & 1) * s4;   // float4 per buffer, a multiple of 256 bytes: every box lands 128-byte aligned
-  int* sptr = reinterpret_cast<int*>(sx + (size_t)nbuf * buf_stride);
-  unsigned short* ssrc = reinterpret_cast<unsigned short*>(sptr + rows_cap + 1);
-  uint64_t* full = reinterpret_cast<uint64_t*>(reinterpret_cast<uintptr_t>(ssrc + edges_cap + 3) & ~(uintptr_t)7);
+  // behind the slices: the mesh's local CSR block in the layout of local_csr_kernel (header | row pointers | source ids), the mbarriers
+  uint8_t* blk = reinterpret_cast<uint8_t*>(sx + (size_t)nbuf * buf_stride);
+  int* hdr = reinterpret_cast<int*>(blk);
+  int* sptr = reinterpret_cast<int*>(blk + 16);
+  unsigned short* ssrc = reinterpret_cast<unsigned short*>(blk + 16 + lcsr_ptr_bytes(rows_cap));
+  uint64_t* full = reinterpret_cast<uint64_t*>(blk + lcsr_stride_bytes(rows_cap));   // [nbuf] slices, [2] the CSR block
   // Programmatic dependent launch: this kernel's CTAs become resident while the linear in front of it is still in its last round.  The
   // CSR of the mesh (face / edge offsets, row pointers, source ids) was written by the topology kernels, which completed before that
   // linear passed ITS wait, so it is staged BEFORE griddepcontrol.wait (L2 loads, ld.global.cg: no line an earlier launch left in this
@@ -395,14 +436,23 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   const int ngroups = (nslices + group - 1) / group;
   const int b = blockIdx.x / ngroups, grp = blockIdx.x % ngroups;
   const int slice0 = grp * group, slice1 = min(nslices, slice0 + group);
+  const int tid = threadIdx.x;
+  constexpr int issuer = NTHR - 32;   // first lane of the last warp
+  const bool use_l = tma && lcsr != nullptr;
+  if (tma && tid == issuer) {
+    for (int k = 0; k < nbuf; ++k) tc::mbar_init(&full[k], 1);
+    tc::mbar_init(&full[2], 1);
+    tc::fence_barrier_init();
+    tc::fence_proxy_async_smem();
+    if (use_l) {   // the mesh's CSR block: written once per batch next to the topology kernels - nothing the kernel in front of this one touches
+      tc::mbar_arrive_expect_tx(&full[2], (uint32_t)lcsr_stride_bytes(rows_cap));
+      tc::bulk_g2s(blk, lcsr + (size_t)b * lcsr_stride_bytes(rows_cap), (uint32_t)lcsr_stride_bytes(rows_cap), &full[2]);
+    }
+  }
   const int r0 = __ldcg(face_off + b);
   const int n_b = min(__ldcg(face_off + b + 1) - r0, rows_cap);
-  const int e0 = __ldcg(edge_off + b);                       // = indptr[r0]
-  const long long e1_true = __ldcg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
-  const int tid = threadIdx.x;
   const int c = tid % s4;
   const uint32_t sx_addr = tc::smem_u32(sx);
-  constexpr int issuer = NTHR - 32;   // first lane of the last warp
   auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf
     if (tma) {
       if (tid == issuer) {   // rows beyond the mesh (the next mesh's, or zeros beyond the tensor) land in the buffer too and are never referenced
@@ -420,12 +470,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
-  if (tma && tid >= issuer) {   // the last warp: barriers, wait for the producer of x, first slice on its way - then its share of the CSR
-    if (tid == issuer) {
-      for (int k = 0; k < nbuf; ++k) tc::mbar_init(&full[k], 1);
-      tc::fence_barrier_init();
-      tc::fence_proxy_async_smem();
-    }
+  if (tma && tid >= issuer) {   // the last warp: wait for the producer of x, first slice on its way - then its share of the CSR
     pdl_wait();
     issue(slice0, 0);
     __syncwarp();
@@ -434,20 +479,30 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   const int zero_row = tma ? buf_rows : n_b;
   if (tid < s4)
     for (int k = 0; k < nbuf; ++k) sx[(size_t)k * buf_stride + zero_row * s4 + tid] = make_float4(0.f, 0.f, 0.f, 0.f);   // the row an invalid source id points at
-  const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
-  const bool fast = n_e <= edges_cap && e1_true <= cap && (buf_rows + 1) * s4 <= 65536;
-  for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldcg(indptr + r0 + i) - e0;
-  if (fast) {
-    for (int base = tid; base < n_e; base += NTHR * 4) {
-      int t[4];
+  int e0, n_e;
+  bool fast;
+  if (use_l) {
+    __syncthreads();                 // the barriers exist
+    tc::mbar_wait(&full[2], 0);      // header, row pointers and source ids have landed
+    n_e = hdr[0]; fast = hdr[1] != 0; e0 = hdr[2];
+  } else {
+    e0 = __ldcg(edge_off + b);                                 // = indptr[r0]
+    const long long e1_true = __ldcg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
+    n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
+    fast = n_e <= edges_cap && e1_true <= cap && (buf_rows + 1) * s4 <= 65536;
+    for (int i = tid; i <= n_b; i += NTHR) sptr[i] = __ldcg(indptr + r0 + i) - e0;
+    if (fast) {
+      for (int base = tid; base < n_e; base += NTHR * 4) {
+        int t[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) t[j] = base + j * NTHR < n_e ? __ldcg(src + e0 + base + j * NTHR) : 0;
+        for (int j = 0; j < 4; ++j) t[j] = base + j * NTHR < n_e ? __ldcg(src + e0 + base + j * NTHR) : 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (base + j * NTHR < n_e) {
-          const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
-          ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4);
-        }
+        for (int j = 0; j < 4; ++j)
+          if (base + j * NTHR < n_e) {
+            const unsigned nb = (unsigned)(t[j] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
+            ssrc[base + j * NTHR] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4);
+          }
+      }
     }
   }
   if (!tma) {
@@ -609,8 +664,20 @@ int gather_mean_read_trace(long long* out, int n) {
   return min(n, 1024 * 8);
 }
 
+size_t local_csr_stride(int F) { return (size_t)lcsr_stride_bytes(F); }
+
+int launch_local_csr(const int* indptr, const int* src, long long edge_capacity, const int* face_off, int B, int F, void* lcsr, cudaStream_t stream) {
+  if (B == 0 || lcsr == nullptr) return MESHTOK_OK;
+  int box_rows, n_boxes;
+  gather_tma_geometry(F, &box_rows, &n_boxes);
+  local_csr_kernel<<<B, 256, 0, stream>>>(indptr, src, edge_capacity, face_off, face_off + 2 * (size_t)(B + 1), F, box_rows * n_boxes,
+                                          static_cast<uint8_t*>(lcsr));
+  MT_CHECK_LAUNCH();
+  return MESHTOK_OK;
+}
+
 int launch_gather_mean(const float* x, int d, const int* indptr, const int* src, long long edge_capacity, float* agg,
-                       void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F, cudaStream_t stream) {
+                       void* agg_image, const Counts* counts, int max_rows, const int* face_off, int B, int F, cudaStream_t stream, const void* lcsr) {
   MT_CHECK_ARG(d % 4 == 0 && d <= 1024, "gather_mean: feature width %d must be a multiple of 4 and <= 1024", d);
   if (max_rows == 0) return MESHTOK_OK;
   if (g_gm_trace_k == -2) {   // timing experiments only: MESHTOK_GATHER_TRACE=k stamps the k-th aggregation launch of every step (5 per step)
@@ -644,12 +711,16 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
     if (use_tma < 0) { const char* e = getenv("MESHTOK_GATHER_TMA"); use_tma = (e && atoi(e) == 0) ? 0 : 1; }
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
-    int n_boxes = ceil_div(F, 256), box_rows = ceil_div(F, n_boxes);
+    int n_boxes, box_rows;
+    gather_tma_geometry(F, &box_rows, &n_boxes);
     const bool tma = use_tma && make_tmap_rows_f32(x, d, (long long)max_rows, box_rows, &tmap);
     if (!tma) { box_rows = 0; n_boxes = 0; }
     const int buf_rows = tma ? box_rows * n_boxes : F;
     const size_t per_buf = (size_t)((buf_rows + 1) + ((buf_rows + 1) & 1)) * 32 * sizeof(float);
-    const size_t csr = (size_t)(F + 1) * sizeof(int) + (size_t)(edges_cap + 4) * sizeof(unsigned short) + 2 * sizeof(uint64_t) + 8;
+    const size_t csr = (size_t)lcsr_stride_bytes(F) + 3 * sizeof(uint64_t);
+    static int use_lcsr = -1;   // MESHTOK_GATHER_LCSR=0: every CTA converts its mesh's CSR itself, as before (A/B)
+    if (use_lcsr < 0) { const char* e = getenv("MESHTOK_GATHER_LCSR"); use_lcsr = (e && atoi(e) == 0) ? 0 : 1; }
+    const uint8_t* lc = (tma && use_lcsr) ? static_cast<const uint8_t*>(lcsr) : nullptr;
     // Slices per CTA.  MEASURED (B200, scripts/gpu_ab.sh; 64 and 1 024 meshes per launch): one slice per CTA with 512 threads and two
     // CTAs per SM - each slice arriving by TMA while the other CTA computes - is as fast as or faster than every grouping with
     // double-buffered slices (C2: 126.7 us over the five layers against 132 - 202 us for groups of 2 / 4 / 8; 1 024 meshes: 1.50 ms
@@ -685,11 +756,11 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       if (group == 1) {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 113 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc);
       } else {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<1024, 1>), B * ngroups, 1024, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc);
       }
       return MESHTOK_OK;
     }
