@@ -754,8 +754,16 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       const int ngroups = ceil_div(nslices, group);
       const int* edge_off = face_off + 2 * (size_t)(B + 1);
       if (group == 1) {
-        MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 113 * 1024);
-        MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
+        MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 120 * 1024);
+        // No more CTAs than SMs (the 64-wide layer at 64 meshes: 128): the block scheduler would still put them two to an SM - 65 SMs busy,
+        // 83 idle, two row loops sharing one shared-memory pipe (clock64 trace: 15.9 k cycles against 9.3 k alone).  A request of more
+        // than half an SM's shared memory spreads them one per SM.
+        static int spread = -1;
+        if (spread < 0) { const char* e = getenv("MESHTOK_GATHER_SPREAD"); spread = (e && atoi(e) == 0) ? 0 : 1; }
+        int n_sm = 148;
+        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+        const size_t smem_launch = (spread && (long long)B * ngroups <= n_sm) ? (size_t)max((long long)smem_w, 118ll * 1024) : smem_w;
+        MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_launch, stream, x, d, indptr, src, edge_capacity, agg,
                       static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc);
       } else {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
