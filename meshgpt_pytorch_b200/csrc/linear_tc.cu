@@ -29,6 +29,9 @@
 #include "common.cuh"
 #include "kernels.cuh"
 #include "tc_common.cuh"
+#ifndef MESHTOK_SILU_FAST
+#define MESHTOK_SILU_FAST 0
+#endif
 
 namespace meshtok {
 
@@ -582,8 +585,15 @@ __device__ __forceinline__ void linear_tc_body(const LinArgs2& g) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float t0 = o0[j] * inv, t1 = o1[j] * inv;
+#if MESHTOK_SILU_FAST
+            // |t| <= 1 after the normalisation: ex2.approx and the approximate divide are each within ~2 ulp here, far below the 1e-5 of
+            // the split-bf16 product feeding them; the IEEE divide + expf were two thirds of this epilogue's instructions
+            o0[j] = h0 ? __fdividef(t0, 1.f + __expf(-t0)) : 0.f;
+            o1[j] = h1 ? __fdividef(t1, 1.f + __expf(-t1)) : 0.f;
+#else
             o0[j] = h0 ? __fdiv_rn(t0, 1.f + expf(-t0)) : 0.f;
             o1[j] = h1 ? __fdiv_rn(t1, 1.f + expf(-t1)) : 0.f;
+#endif
             sum += o0[j] + o1[j];
           }
           xs[(CPARTS + cpart) * 128 + rit] = sum;
