@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
                                                                            const int* __restrict__ edge_off, int rows_cap, int edges_cap, int group,
                                                                            int nbuf, long long* __restrict__ trace, int exp,
                                                                            const __grid_constant__ CUtensorMap tmap, int box_rows, int n_boxes, int early,
-                                                                           const uint8_t* __restrict__ lcsr) {
+                                                                           const uint8_t* __restrict__ lcsr, int stagger_ns, int n_sm) {
   // [nbuf][buf_rows + 1][8] float4 x slices (row buf_rows stays zero: what an invalid source id points at) | [rows_cap + 1] local row
   // pointers | [edges_cap] source row * 8 (u16) | [2] mbarriers.  box_rows > 0: the slices arrive by TMA (n_boxes boxes of box_rows x 32
   // columns, one elected thread, completion on an mbarrier); box_rows == 0: by 16-byte cp.async copies of all threads.
@@ -472,6 +472,10 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   };
   if (tma && tid >= issuer) {   // the last warp: wait for the producer of x, first slice on its way - then its share of the CSR
     pdl_wait();
+    // Two CTAs share an SM; started together they load together (each at half the SM's L2 bandwidth) and then loop together (each at
+    // half the shared-memory pipe).  The second CTA of an SM's first wave issues its slice a little later: the first one gets the full
+    // load bandwidth and starts its loop while the second one's slice is still in flight.
+    if (stagger_ns > 0 && ((blockIdx.x / n_sm) & 1) != 0 && blockIdx.x < 2 * n_sm) __nanosleep(stagger_ns);
     issue(slice0, 0);
     __syncwarp();
   }
@@ -753,6 +757,10 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       const size_t smem_w = align_up(nbuf * per_buf + csr, 128);
       const int ngroups = ceil_div(nslices, group);
       const int* edge_off = face_off + 2 * (size_t)(B + 1);
+      static int stagger = -1;   // ns by which the second CTA of an SM's first wave delays its slice (MESHTOK_GATHER_STAGGER, 0 = off)
+      if (stagger < 0) { const char* e = getenv("MESHTOK_GATHER_STAGGER"); stagger = e ? atoi(e) : 0; }
+      int n_sm = 148;
+      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
       if (group == 1) {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 120 * 1024);
         // No more CTAs than SMs (the 64-wide layer at 64 meshes: 128): the block scheduler would still put them two to an SM - 65 SMs busy,
@@ -760,15 +768,13 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
         // than half an SM's shared memory spreads them one per SM.
         static int spread = -1;
         if (spread < 0) { const char* e = getenv("MESHTOK_GATHER_SPREAD"); spread = (e && atoi(e) == 0) ? 0 : 1; }
-        int n_sm = 148;
-        { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
         const size_t smem_launch = (spread && (long long)B * ngroups <= n_sm) ? (size_t)max((long long)smem_w, 118ll * 1024) : smem_w;
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<512, 2>), B * ngroups, 512, smem_launch, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc, stagger, n_sm);
       } else {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<1024, 1>), 226 * 1024);
         MT_LAUNCH_PDL((gather_mean_smem_wide_kernel<1024, 1>), B * ngroups, 1024, smem_w, stream, x, d, indptr, src, edge_capacity, agg,
-                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc);
+                      static_cast<uint8_t*>(agg_image), face_off, edge_off, F, edges_cap, group, nbuf, trace, gexp, tmap, box_rows, n_boxes, early, lc, stagger, n_sm);
       }
       return MESHTOK_OK;
     }
