@@ -490,8 +490,8 @@ __global__ void __launch_bounds__(256) rvq_rescore_kernel(float* __restrict__ ro
 // shuffle steps instead of five, and the scalar work of four rows shares one instruction stream.  Same arithmetic per code
 // (fp32 dot product, sqrt(max(|x|^2 + |e|^2 - 2 <x, e>, 0)), lowest index on ties); only the summation order inside a dot product
 // differs (eight partial sums instead of 32), which the parity tests cover like any other fp32 evaluation order.
-template <int NI>   // float4 per lane: D <= 32 * NI
-__global__ void __launch_bounds__(256, 2) rvq_rescore4_kernel(float* __restrict__ rows, int D, const float* __restrict__ cb,
+template <int NI, int MINB>   // float4 per lane: D <= 32 * NI; MINB CTAs per SM the register allocation is held to
+__global__ void __launch_bounds__(256, MINB) rvq_rescore4_kernel(float* __restrict__ rows, int D, const float* __restrict__ cb,
                                                               const float* __restrict__ e2, int K, float max_norm, float escale, float c_scale,
                                                               float* __restrict__ rscale, const float4* __restrict__ partial, RvqPartialLayout lay,
                                                               const int* __restrict__ n_dev, int max_rows, int32_t* __restrict__ codes, int Q,
@@ -845,8 +845,15 @@ int launch_rvq_rescore(float* rows, float* rscale, int D, const float* codebook,
   if (four < 0) { const char* e = getenv("MESHTOK_RESCORE4"); four = (e && atoi(e) == 0) ? 0 : 1; }
   if (four == 1 && D % 4 == 0) {
     const int blocks = max(1, min(ceil_div(max_rows, 32), 148 * 8));
-    MT_LAUNCH_PDL(rvq_rescore4_kernel<6>, blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
-                  n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
+    // MESHTOK_RESCORE_OCC=3: 80 registers (40 bytes of spills) and three CTAs per SM instead of 128 registers and two (A/B)
+    static int occ = -1;
+    if (occ < 0) { const char* e = getenv("MESHTOK_RESCORE_OCC"); occ = e ? atoi(e) : 2; }
+    if (occ == 3)
+      MT_LAUNCH_PDL((rvq_rescore4_kernel<6, 3>), blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
+                    n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
+    else
+      MT_LAUNCH_PDL((rvq_rescore4_kernel<6, 2>), blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
+                    n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
     return MESHTOK_OK;
   }
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
