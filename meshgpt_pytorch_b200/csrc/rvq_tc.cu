@@ -845,15 +845,9 @@ int launch_rvq_rescore(float* rows, float* rscale, int D, const float* codebook,
   if (four < 0) { const char* e = getenv("MESHTOK_RESCORE4"); four = (e && atoi(e) == 0) ? 0 : 1; }
   if (four == 1 && D % 4 == 0) {
     const int blocks = max(1, min(ceil_div(max_rows, 32), 148 * 8));
-    // MESHTOK_RESCORE_OCC=3: 80 registers (40 bytes of spills) and three CTAs per SM instead of 128 registers and two (A/B)
-    static int occ = -1;
-    if (occ < 0) { const char* e = getenv("MESHTOK_RESCORE_OCC"); occ = e ? atoi(e) : 2; }
-    if (occ == 3)
-      MT_LAUNCH_PDL((rvq_rescore4_kernel<6, 3>), blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
-                    n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
-    else
-      MT_LAUNCH_PDL((rvq_rescore4_kernel<6, 2>), blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
-                    n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
+    // (held to 80 registers for three CTAs per SM - 40 bytes of spills - the kernel measured 58.5 against 43.8 us per step at C2: it stays at 128)
+    MT_LAUNCH_PDL((rvq_rescore4_kernel<6, 2>), blocks, 256, 0, stream, rows, D, codebook, e2, K, max_norm, escale, c_scale, rscale, partial, layout,
+                  n_rows_dev, max_rows, codes, Q, level, update ? 1 : 0, static_cast<uint8_t*>(row_image), stats);
     return MESHTOK_OK;
   }
   const int blocks = max(1, min(ceil_div(max_rows, 8), 148 * 16));
