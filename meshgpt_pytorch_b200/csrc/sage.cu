@@ -376,10 +376,11 @@ static inline void gather_tma_geometry(int F, int* box_rows, int* n_boxes) {   /
   *box_rows = (F + *n_boxes - 1) / *n_boxes;
 }
 
+constexpr int LCSR_PARTS = 4;   // CTAs per mesh
 __global__ void __launch_bounds__(256) local_csr_kernel(const int* __restrict__ indptr, const int* __restrict__ src, long long cap,
                                                         const int* __restrict__ face_off, const int* __restrict__ edge_off, int F,
                                                         int zero_row, uint8_t* __restrict__ lcsr) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / LCSR_PARTS, part = blockIdx.x % LCSR_PARTS;
   const int edges_cap = 5 * F;
   uint8_t* blk = lcsr + (size_t)b * lcsr_stride_bytes(F);
   int* hdr = reinterpret_cast<int*>(blk);
@@ -391,10 +392,11 @@ __global__ void __launch_bounds__(256) local_csr_kernel(const int* __restrict__ 
   const long long e1_true = edge_off[b + 1];
   const int n_e = (int)((e1_true < cap ? e1_true : cap) - e0);
   const bool fast = n_e <= edges_cap && e1_true <= cap && (zero_row + 1) * 8 <= 65536;
-  if (threadIdx.x == 0) { hdr[0] = n_e; hdr[1] = fast ? 1 : 0; hdr[2] = e0; hdr[3] = 0; }
-  for (int i = threadIdx.x; i <= n_b; i += blockDim.x) sptr[i] = indptr[r0 + i] - e0;
+  const int t = part * blockDim.x + threadIdx.x, nt = LCSR_PARTS * blockDim.x;
+  if (t == 0) { hdr[0] = n_e; hdr[1] = fast ? 1 : 0; hdr[2] = e0; hdr[3] = 0; }
+  for (int i = t; i <= n_b; i += nt) sptr[i] = indptr[r0 + i] - e0;
   if (fast)
-    for (int q = threadIdx.x; q < n_e; q += blockDim.x) {
+    for (int q = t; q < n_e; q += nt) {
       const unsigned nb = (unsigned)(src[e0 + q] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
       ssrc[q] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * 8u);
     }
@@ -674,7 +676,7 @@ int launch_local_csr(const int* indptr, const int* src, long long edge_capacity,
   if (B == 0 || lcsr == nullptr) return MESHTOK_OK;
   int box_rows, n_boxes;
   gather_tma_geometry(F, &box_rows, &n_boxes);
-  local_csr_kernel<<<B, 256, 0, stream>>>(indptr, src, edge_capacity, face_off, face_off + 2 * (size_t)(B + 1), F, box_rows * n_boxes,
+  local_csr_kernel<<<B * LCSR_PARTS, 256, 0, stream>>>(indptr, src, edge_capacity, face_off, face_off + 2 * (size_t)(B + 1), F, box_rows * n_boxes,
                                           static_cast<uint8_t*>(lcsr));
   MT_CHECK_LAUNCH();
   return MESHTOK_OK;
