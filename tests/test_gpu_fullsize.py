@@ -102,3 +102,22 @@ def test_fused_aggregation_is_bit_identical_to_the_separate_launches():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "scripts", "gpu_gather_fused_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "bit-identical" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("nxny", [(25, 25), (30, 30)])
+def test_meshes_above_800_faces(nxny):
+    """1 250 and 1 800 faces per mesh: a 32-column slice of such a mesh no longer fits twice per SM, so the aggregation takes the one-CTA-per-SM
+    instantiation with several TMA boxes per slice (1 250) or, beyond the shared memory of an SM, the kernels that read the neighbour rows
+    through L2 (1 800) - the per-mesh CSR blocks, the topology kernel's shared-memory tables and the folded-table sum at sizes no BASELINE
+    workload reaches.  Same bar as every other full-size test."""
+    o, m = make_pair(use_residual_lfq=False)
+    v, f = synth.grid_batch("tri", *nxny, [0, 1, 2])
+    got = m.tokenize(v.cuda(), f.cuda())
+    m.check_last_status()
+    rate, n_bad, in_err = assert_tokens_match_or_attributed(o, m, v, f, got, label=f"{2 * nxny[0] * nxny[1]} faces")
+    print(f"{2 * nxny[0] * nxny[1]} faces per mesh: token agreement {rate:.6f}, {n_bad} attributed, quantizer input within {in_err:.2e}")
+    # and next to small meshes in one -1 padded batch
+    v2, f2 = synth.ragged_batch("tri", *nxny, [2 * nxny[0] * nxny[1], 37, 600], [3, 4, 5])
+    got2 = m.tokenize(v2.cuda(), f2.cuda())
+    m.check_last_status()
+    assert_tokens_match_or_attributed(o, m, v2, f2, got2, label=f"{2 * nxny[0] * nxny[1]} faces, ragged")
