@@ -765,7 +765,9 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       if (stagger < 0) { const char* e = getenv("MESHTOK_GATHER_STAGGER"); stagger = e ? atoi(e) : 1000; }
       int n_sm = 148;
       { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
-      if (group == 1) {
+      // (512 threads, two CTAs per SM) where a single-slice CTA fits twice; else 1 024 threads and the SM to itself - also with ONE slice per
+      // CTA when two buffers of a large mesh do not fit (meshes of ~900 .. 1 700 faces; found by test_meshes_above_800_faces)
+      if (group == 1 && 2 * (smem_w + 1024) <= 226 * 1024) {
         MT_ENSURE_SMEM((gather_mean_smem_wide_kernel<512, 2>), 120 * 1024);
         // No more CTAs than SMs (the 64-wide layer at 64 meshes: 128): the block scheduler would still put them two to an SM - 65 SMs busy,
         // 83 idle, two row loops sharing one shared-memory pipe (clock64 trace: 15.9 k cycles against 9.3 k alone).  A request of more

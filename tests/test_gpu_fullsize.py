@@ -116,8 +116,16 @@ def test_meshes_above_800_faces(nxny):
     m.check_last_status()
     rate, n_bad, in_err = assert_tokens_match_or_attributed(o, m, v, f, got, label=f"{2 * nxny[0] * nxny[1]} faces")
     print(f"{2 * nxny[0] * nxny[1]} faces per mesh: token agreement {rate:.6f}, {n_bad} attributed, quantizer input within {in_err:.2e}")
-    # and next to small meshes in one -1 padded batch
+    # and next to small meshes in one -1 padded batch.  A flipped feature bin (an angle or a normal within an ulp of a rounding boundary,
+    # scripts/gpu_flip_diag.py) reaches every vertex within five hops: the flipped faces are counted directly and the share of
+    # quantizer inputs beyond 2e-3 is bounded by what that many flips can touch
     v2, f2 = synth.ragged_batch("tri", *nxny, [2 * nxny[0] * nxny[1], 37, 600], [3, 4, 5])
+    m.keep_taps = True
     got2 = m.tokenize(v2.cuda(), f2.cuda())
+    m.keep_taps = False
     m.check_last_status()
-    assert_tokens_match_or_attributed(o, m, v2, f2, got2, label=f"{2 * nxny[0] * nxny[1]} faces, ragged")
+    _, st = o.forward_codes(vertices=v2, faces=f2, return_stages=True)
+    flips = int(((m.taps()["x0"].cpu() - st["project_in"]).abs().max(-1).values > 1e-4).sum())
+    print(f"   ragged: {flips} face rows with a flipped feature bin")
+    assert flips <= 3, flips
+    assert_tokens_match_or_attributed(o, m, v2, f2, got2, label=f"{2 * nxny[0] * nxny[1]} faces, ragged", max_bad_input_frac=0.005 + 0.02 * flips)
