@@ -77,6 +77,17 @@ def quads_1250():
     return f"agreement {rate:.6f}, {n_bad} attributed"
 
 
-for name, fn in (("5000-face meshes", big_mesh), ("4096 small meshes", many_small), ("book mesh", book), ("single face", single_face),
+def ragged_1250():
+    from meshgpt_pytorch_b200 import data as Dt
+    v, f = synth.ragged_batch("tri", 25, 25, [1250, 300, 37, 1250], [0, 1, 2, 3])
+    r = Dt.padded_to_ragged(v, f)
+    flat = m.tokenize_ragged(r["vertices"].cuda(), r["faces"].cuda(), r["face_offsets"], r["vertex_offsets"])
+    back = Dt.ragged_to_padded_codes(flat, r["face_offsets"], 3, m.pad_id)
+    padded = m.tokenize(v.cuda(), f.cuda())
+    g = m.graphed(v.cuda(), f.cuda())
+    return f"ragged == padded: {torch.equal(back.cpu(), padded.cpu())}, graph replay == eager: {torch.equal(g().cpu(), padded.cpu())}, " + compare(v, f, "ragged 1250", max_bad_input_frac=0.05)
+
+
+for name, fn in (("ragged + graphed, 1250-face meshes", ragged_1250), ("5000-face meshes", big_mesh), ("4096 small meshes", many_small), ("book mesh", book), ("single face", single_face),
                  ("1250-quad meshes", quads_1250)):
     run(name, fn)
