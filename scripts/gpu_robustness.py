@@ -88,6 +88,30 @@ def ragged_1250():
     return f"ragged == padded: {torch.equal(back.cpu(), padded.cpu())}, graph replay == eager: {torch.equal(g().cpu(), padded.cpu())}, " + compare(v, f, "ragged 1250", max_bad_input_frac=0.05)
 
 
-for name, fn in (("ragged + graphed, 1250-face meshes", ragged_1250), ("5000-face meshes", big_mesh), ("4096 small meshes", many_small), ("book mesh", book), ("single face", single_face),
+def decode_1250():
+    import test_gpu_decode as TD
+    from helpers import SMALL_CFG
+    oo, mm, od, md = TD.make_decoders(dict(SMALL_CFG, use_residual_lfq=False), (32, 32, 64, 64))
+    v, f = synth.ragged_batch("tri", 25, 25, [1250, 300, 37], [0, 1, 2])
+    codes = oo.tokenize(v, f)
+    want_c, want_bins, want_mask = od.decode_from_codes_to_faces(codes, return_discrete_codes=True)
+    got_c, got_bins, got_mask = md.decode_from_codes_to_faces(codes.cuda(), return_discrete_codes=True)
+    same = (got_bins.cpu() == want_bins)[want_mask]
+    return f"mask equal {torch.equal(got_mask.cpu(), want_mask)}, decoded bins equal on {float(same.float().mean()):.4f} of the coordinates"
+
+
+def frontend_long():
+    import test_gpu_frontend as TF
+    kw = dict(codebook_size=16384, num_quantizers=2, quads=False, dim=512, max_seq_len=8190)
+    fo, fm = TF.make_pair(**kw)
+    codes = torch.randint(0, 16385, (2, 8190))
+    codes[1, 5000:] = -1
+    want_g, want_f = fo(codes)
+    got_g, got_f = fm.embed_codes(codes.cuda())
+    err = float((got_f.cpu() - want_f).abs().max() / want_f.abs().max())
+    return f"fine tokens bit-exact {torch.equal(got_g.cpu(), want_g)}, face tokens within {err:.2e}"
+
+
+for name, fn in (("decode, 1250-face meshes", decode_1250), ("front end, 8190-token sequences", frontend_long), ("ragged + graphed, 1250-face meshes", ragged_1250), ("5000-face meshes", big_mesh), ("4096 small meshes", many_small), ("book mesh", book), ("single face", single_face),
                  ("1250-quad meshes", quads_1250)):
     run(name, fn)
