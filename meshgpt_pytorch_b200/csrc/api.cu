@@ -519,6 +519,20 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     MT_CHECK_CUDA(cudaEventRecord(side->bins_done, side->stream));
     bins_pending = true;
   }
+  // The face adjacency reads nothing the maps launch writes (it recomputes the packed rows from the faces and has its own look-back
+  // block), so it does not have to wait for it.  MESHTOK_EDGES_EARLY=1 launches it behind the feature bins on the side stream, BEFORE
+  // the maps launch: it is then out of the folded-table sum's way sooner (that kernel's 144 CTAs otherwise share the SMs with the 64
+  // one-per-SM adjacency CTAs: 54 -> 37 us for the section) and a serial step takes 0.795 instead of 0.804 ms - but host to host, with
+  // two batches in flight, the same change costs 1.4 % (68.4 -> 67.4 M faces/s at C2: three one-CTA-per-SM launches at the head of every
+  // graph get in the way of the other batch's tensor-core kernels).  The headline is the host-to-host number: off by default.
+  static int edges_early_on = -1;
+  if (edges_early_on < 0) { const char* e = getenv("MESHTOK_EDGES_EARLY"); edges_early_on = (e && atoi(e) == 1) ? 1 : 0; }
+  const bool edges_early = edges_early_on && want_features && !a->face_edges;
+  TopoParams pe = p;
+  pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
+  pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
+  pe.ticket = pe.mesh_counts + 8 * (size_t)B;
+  if (edges_early && (rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
   prof_begin(PROF_TOPOLOGY, s);
   // Two launches: the maps (packed face rows, vertex incidence CSR) are all the feature kernel and the first linear
   // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
@@ -532,13 +546,9 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     if (rc != MESHTOK_OK) return rc;
     if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, s)) != MESHTOK_OK) return rc;
   } else {
-    TopoParams pe = p;
-    pe.mesh_counts = w.mesh_counts + (8 * (size_t)B + 4);
-    pe.mesh_prefix = pe.mesh_counts + 4 * (size_t)B;
-    pe.ticket = pe.mesh_counts + 8 * (size_t)B;
     MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
-    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
-    if ((rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
+    MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));   // (the per-mesh CSR blocks below need the maps launch's face offsets)
+    if (!edges_early && (rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
     // the aggregation kernels' per-mesh CSR blocks: once per batch, behind the adjacency on the side stream
     if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, side->stream)) != MESHTOK_OK) return rc;
     MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));

@@ -394,7 +394,8 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     p.face_off[gridDim.x] = nf; p.vert_off[gridDim.x] = nv;
     p.counts->n_faces = nf; p.counts->n_vrows = nv;
     p.vptr[nv] = nf * nvf;
-    if (MODE == MODE_MAPS || !p.do_adjacency) {   // no edges (yet): keep the totals consistent until they are known
+    if (!p.do_adjacency) {   // user-supplied edges follow: keep the totals consistent until they are known.  (With do_adjacency the
+                             // edges launch writes the total - possibly BEFORE this launch ends: the two may run side by side.)
       p.edge_off[gridDim.x] = 0;
     }
   }
