@@ -538,7 +538,15 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   // need; the face adjacency (the expensive part, one CTA per mesh = fewer CTAs than SMs for small batches) runs on a
   // side stream next to them and is joined before the first neighbour aggregation.  Inside a stream capture the side
   // stream becomes a parallel branch of the graph.
-  if ((rc = topo_maps(p, s)) != MESHTOK_OK) return rc;
+  // Maps and adjacency in ONE launch on the caller's stream (topology_kernel<CSR>: the faces are staged and sorted once instead of
+  // twice).  The folded-table sum then waits for the adjacency too (topology section 27 -> 40 us at C2), but it no longer shares the
+  // SMs with the 64 one-per-SM adjacency CTAs of the side stream (its section: 54 -> 38 us), and the step has one launch less:
+  // measured on one box each, two runs per setting: C2 0.7985 -> 0.795 ms (host to host 68.8 -> 69.0 M faces/s), C3 0.5725 -> 0.568 ms,
+  // C4 1.776 -> 1.748 ms, 1 024 meshes per launch 12.50 -> 12.39 ms.  MESHTOK_TOPO_ONE=0: the two launches of before (A/B).
+  static int topo_one_on = -1;
+  if (topo_one_on < 0) { const char* e = getenv("MESHTOK_TOPO_ONE"); topo_one_on = (e && atoi(e) == 0) ? 0 : 1; }
+  const bool topo_one = topo_one_on && !a->face_edges && !edges_early;
+  if ((rc = topo_one ? topo_csr(p, s) : topo_maps(p, s)) != MESHTOK_OK) return rc;
   bool edges_pending = false;
   if (a->face_edges) {
     rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
@@ -548,7 +556,7 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   } else {
     MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
     MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));   // (the per-mesh CSR blocks below need the maps launch's face offsets)
-    if (!edges_early && (rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
+    if (!edges_early && !topo_one && (rc = topo_edges(pe, side->stream)) != MESHTOK_OK) return rc;
     // the aggregation kernels' per-mesh CSR blocks: once per batch, behind the adjacency on the side stream
     if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, side->stream)) != MESHTOK_OK) return rc;
     MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
