@@ -85,6 +85,9 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   int* inc = vcur + (V + 1);      // [FN]   incidence entries face*nvf+slot
   int* scratch = inc + FN;        // [48]
   uint32_t* bits = reinterpret_cast<uint32_t*>(scratch + 48);  // [nwarps][p.words_per_warp]
+  // CSR modes: the first p.ncache in-neighbours of every face, kept by the counting pass so that the emitting pass does not walk the
+  // incidence lists a second time (the k-way merge is most of this kernel's instructions; ncu: issue bound at ~0.55 IPC per scheduler)
+  unsigned short* ncache = reinterpret_cast<unsigned short*>(bits + (size_t)(blockDim.x >> 5) * p.words_per_warp);   // [F][p.ncache]
   const int Wf = (F + 31) >> 5;
   const int Ww = p.words_per_warp;
 
@@ -237,19 +240,31 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   };
   // counting: degrees only (MODE_COUNT: both, to global; CSR modes: in-degree into fptr[]);  else: emit the
   // neighbours in ascending order at fptr[i] (dense list by source / CSR by target).
-  auto adjacency = [&](const bool counting, const int face_off, const int edge_off) {
+  auto adjacency = [&](const bool counting, const int face_off, const int edge_off, const int mesh_edges = 0) {
     const int thr = p.threshold;
     const bool keep3 = p.include_self != 0;
+    const int nc = kLookBack ? p.ncache : 0;
     int total_out = 0;
     for (int i = tid; i < F; i += nt) {
       int dout = 0, din = 0, r = 0;
       if (face_valid(i)) {
         const int mybase = counting ? 0 : fptr[i];
+        if (!counting && nc > 0) {   // the whole list is in the cache: copy it out
+          const int deg = (i + 1 < F ? fptr[i + 1] : mesh_edges) - mybase;
+          if (deg <= nc) {
+            for (int q = 0; q < deg; ++q) {
+              const long long at = (long long)edge_off + mybase + q;
+              if (at < p.edge_capacity) p.src[at] = face_off + frank[ncache[i * nc + q]];
+            }
+            continue;
+          }
+        }
         for_each_candidate(i, [&](const int k, const int n_ik, const int n_ki) {
           const bool eo = !kLookBack && n_ik >= thr && (keep3 || n_ik != 3);
           const bool ei = (MODE != MODE_FILL_DENSE) && n_ki >= thr && (keep3 || n_ki != 3);
           if (counting) {
             dout += eo;
+            if (ei && din < nc) ncache[i * nc + din] = (unsigned short)k;
             din += ei;
           } else if (MODE == MODE_FILL_DENSE) {
             if (eo) {
@@ -349,7 +364,7 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   }
   __syncthreads();
   const int face_off = scratch[42], vert_off = scratch[43], edge_off = scratch[44];
-  if (kEdges && p.do_adjacency) adjacency(false, face_off, edge_off);
+  if (kEdges && p.do_adjacency) adjacency(false, face_off, edge_off, mesh_total);
   __syncthreads();
 
   // ---- 4. outputs: maps + vertex CSR + face CSR row pointers ------------------------------------
@@ -564,8 +579,16 @@ template <int MODE, int NVF>
 static int launch_topology_nvf(TopoParams p, cudaStream_t stream) {
   const int nt = topo_threads(p.F);
   int ww = 0;
-  const size_t smem = topo_smem_bytes(p.F, p.nvf, p.V, nt, &ww);
+  size_t smem = topo_smem_bytes(p.F, p.nvf, p.V, nt, &ww);
   p.words_per_warp = ww;
+  p.ncache = 0;
+  if ((MODE == MODE_CSR || MODE == MODE_EDGES) && p.do_adjacency && p.F <= 65535) {
+    // neighbour cache of the counting pass (8 per face: the derived adjacency has at most nvf + 1 entries on a manifold mesh), where it fits
+    static int cache_on = -1;   // MESHTOK_TOPO_CACHE=0: the emitting pass walks the incidence lists again, as before (A/B)
+    if (cache_on < 0) { const char* e = getenv("MESHTOK_TOPO_CACHE"); cache_on = (e && atoi(e) == 0) ? 0 : 1; }
+    const size_t extra = ((size_t)p.F * 8 * sizeof(unsigned short) + 15) & ~(size_t)15;
+    if (cache_on && smem + extra <= 220 * 1024) { p.ncache = 8; smem += extra; }
+  }
   if (smem > 48 * 1024) MT_ENSURE_SMEM((topology_kernel<MODE, NVF>), 220 * 1024);
   topology_kernel<MODE, NVF><<<p.B, nt, smem, stream>>>(p);
   MT_CHECK_LAUNCH();

@@ -13,6 +13,7 @@ struct TopoParams {
   int include_self;
   int do_adjacency;       // 0 when the caller supplies face_edges
   int words_per_warp;     // filled by the launcher
+  int ncache;             // filled by the launcher: neighbours per face the counting pass keeps for the emitting pass (0: none)
   int* status;
   int* mesh_counts;       // [B][4] nvalid, nref, nedges, ready flag (MODE_CSR look-back descriptor)
   int* mesh_prefix;       // [B][4] inclusive prefixes of the same + ready flag   (MODE_CSR)

@@ -527,7 +527,7 @@ torch.save(out, sys.argv[1])
                                   "MESHTOK_GATHER_WIDE=0", "MESHTOK_GATHER_WIDE_GROUP=3", "MESHTOK_GATHER_WIDE_GROUP=1",
                                   "MESHTOK_RESCORE4=0", "MESHTOK_FACE_SUM_PAIR=0", "MESHTOK_PDL=0", "MESHTOK_GATHER_FUSED=1",
                                   "MESHTOK_GATHER_LCSR=0", "MESHTOK_GATHER_SPREAD=0", "MESHTOK_LFQ_ROWS=0", "MESHTOK_LFQ_VARIANT=21",
-                                  "MESHTOK_TOPO_ONE=0", "MESHTOK_EDGES_EARLY=1"])
+                                  "MESHTOK_TOPO_ONE=0", "MESHTOK_EDGES_EARLY=1", "MESHTOK_TOPO_CACHE=0"])
 def test_fallback_kernels_agree_with_the_default_path(knob, tmp_path):
     """Every kernel that has a fallback (tables / neighbour rows from L2, single-CTA linear and RVQ search, one linear per
     launch) computes the same tokens as the default path.  The switches are read once per process, hence subprocesses."""
