@@ -545,7 +545,12 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
   // C4 1.776 -> 1.748 ms, 1 024 meshes per launch 12.50 -> 12.39 ms.  MESHTOK_TOPO_ONE=0: the two launches of before (A/B).
   static int topo_one_on = -1;
   if (topo_one_on < 0) { const char* e = getenv("MESHTOK_TOPO_ONE"); topo_one_on = (e && atoi(e) == 0) ? 0 : 1; }
-  const bool topo_one = topo_one_on && !a->face_edges && !edges_early;
+  const bool topo_one = topo_one_on && want_features && !a->face_edges && !edges_early;   // (quantize() without an encoder pass keeps the pair)
+  if (topo_one) {   // the one launch also writes the aggregation kernels' per-mesh CSR blocks (no local_csr_kernel, no side-stream join)
+    p.lcsr = w.lcsr;
+    p.lcsr_stride = (int)local_csr_stride(F);
+    local_csr_layout(F, &p.lcsr_ptr_bytes, &p.lcsr_zero_row);
+  }
   if ((rc = topo_one ? topo_csr(p, s) : topo_maps(p, s)) != MESHTOK_OK) return rc;
   bool edges_pending = false;
   if (a->face_edges) {
@@ -553,6 +558,8 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
     if (rc != MESHTOK_OK) return rc;
     if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, s)) != MESHTOK_OK) return rc;
+  } else if (topo_one) {
+    // (everything the aggregation needs came out of the one topology launch)
   } else {
     MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
     MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));   // (the per-mesh CSR blocks below need the maps launch's face offsets)

@@ -47,6 +47,9 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
 // source rows relative to the mesh's first row, pre-multiplied for the aggregation kernel's shared-memory layout (5 F u16).
 // Runs once per batch after the face CSR exists (next to the topology kernels, off the critical path); all five layers read it.
 size_t local_csr_stride(int F);
+// layout constants of a block for a producer other than local_csr_kernel (the one-launch topology kernel): bytes of the row-pointer part,
+// the local row an invalid source id points at
+void local_csr_layout(int F, int* ptr_bytes, int* zero_row);
 int launch_local_csr(const int* indptr, const int* src, long long edge_capacity, const int* face_off, int B, int F, void* lcsr, cudaStream_t stream);
 int gather_mean_read_trace(long long* out, int n);   // timing experiments, see sage.cu
 // in place: x <- x / max(|x|_2, 1e-12); when gamma != null also SiLU then LayerNorm(gamma, beta, eps 1e-5).

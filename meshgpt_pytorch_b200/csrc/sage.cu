@@ -671,6 +671,12 @@ int gather_mean_read_trace(long long* out, int n) {
 }
 
 size_t local_csr_stride(int F) { return (size_t)lcsr_stride_bytes(F); }
+void local_csr_layout(int F, int* ptr_bytes, int* zero_row) {
+  int box_rows, n_boxes;
+  gather_tma_geometry(F, &box_rows, &n_boxes);
+  *ptr_bytes = lcsr_ptr_bytes(F);
+  *zero_row = box_rows * n_boxes;
+}
 
 int launch_local_csr(const int* indptr, const int* src, long long edge_capacity, const int* face_off, int B, int F, void* lcsr, cudaStream_t stream) {
   if (B == 0 || lcsr == nullptr) return MESHTOK_OK;

@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
   };
   // counting: degrees only (MODE_COUNT: both, to global; CSR modes: in-degree into fptr[]);  else: emit the
   // neighbours in ascending order at fptr[i] (dense list by source / CSR by target).
+  // (CSR modes with p.lcsr: the mesh's block of the aggregation kernel's local CSR, see topology.cuh)
+  uint8_t* lblk = (kLookBack && p.lcsr != nullptr) ? p.lcsr + (size_t)b * p.lcsr_stride : nullptr;
+  unsigned short* lsrc = lblk ? reinterpret_cast<unsigned short*>(lblk + 16 + p.lcsr_ptr_bytes) : nullptr;
   auto adjacency = [&](const bool counting, const int face_off, const int edge_off, const int mesh_edges = 0) {
     const int thr = p.threshold;
     const bool keep3 = p.include_self != 0;
@@ -254,7 +257,9 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
           if (deg <= nc) {
             for (int q = 0; q < deg; ++q) {
               const long long at = (long long)edge_off + mybase + q;
-              if (at < p.edge_capacity) p.src[at] = face_off + frank[ncache[i * nc + q]];
+              const int fr = frank[ncache[i * nc + q]];
+              if (at < p.edge_capacity) p.src[at] = face_off + fr;
+              if (lsrc != nullptr && mybase + q < 5 * F) lsrc[mybase + q] = (unsigned short)(fr * 8);
             }
             continue;
           }
@@ -276,6 +281,7 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
           } else if (ei) {
             const long long at = (long long)edge_off + mybase + r;
             if (at < p.edge_capacity) p.src[at] = face_off + frank[k];
+            if (lsrc != nullptr && mybase + r < 5 * F) lsrc[mybase + r] = (unsigned short)(frank[k] * 8);
             ++r;
           }
         });
@@ -373,6 +379,21 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     if (tid == 0) p.edge_off[b] = edge_off;
     for (int f = tid; f < F; f += nt)
       if (face_valid(f)) p.indptr[face_off + frank[f]] = edge_off + fptr[f];
+    if (lblk != nullptr) {   // header and row pointers of the local CSR block (the source ids went out with the edges above)
+      int* lptr = reinterpret_cast<int*>(lblk + 16);
+      for (int f = tid; f < F; f += nt)
+        if (face_valid(f)) lptr[frank[f]] = fptr[f];
+      if (tid == 0) {
+        lptr[nvalid] = mesh_total;
+        const long long e1 = (long long)edge_off + mesh_total;
+        const int n_e = (int)((e1 < p.edge_capacity ? e1 : p.edge_capacity) - edge_off);
+        int* hdr = reinterpret_cast<int*>(lblk);
+        hdr[0] = n_e;
+        hdr[1] = (n_e <= 5 * F && e1 <= p.edge_capacity && (p.lcsr_zero_row + 1) * 8 <= 65536) ? 1 : 0;
+        hdr[2] = edge_off;
+        hdr[3] = 0;
+      }
+    }
     if ((long long)edge_off + mesh_total > p.edge_capacity && tid == 0) atomicOr(p.status, MESHTOK_WS_STATUS_EDGE_OVERFLOW);
     if (last_mesh && tid == 0) {
       const int nf = face_off + nvalid, ne = edge_off + mesh_total;

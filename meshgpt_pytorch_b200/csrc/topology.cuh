@@ -37,6 +37,10 @@ struct TopoParams {
   int* indptr;            // [B*F+1]
   int* src;               // [edge_capacity]
   long long edge_capacity;
+  // CSR mode, optional: the aggregation kernel's per-mesh local CSR blocks (sage.cu, local_csr_kernel's format), written here while the
+  // mesh's row pointers and neighbour lists are still in shared memory: {n_e, fast, e0, 0} | row pointers (F + 1) | source row * 8 (u16)
+  uint8_t* lcsr;
+  int lcsr_stride, lcsr_ptr_bytes, lcsr_zero_row;
 };
 
 int topo_threads(int F);
