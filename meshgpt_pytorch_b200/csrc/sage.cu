@@ -458,8 +458,10 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
   auto issue = [&](int slice, int buf) {   // the x slice of this mesh -> buffer buf
     if (tma) {
       if (tid == issuer) {   // rows beyond the mesh (the next mesh's, or zeros beyond the tensor) land in the buffer too and are never referenced
-        tc::mbar_arrive_expect_tx(&full[buf], (uint32_t)n_boxes * (uint32_t)box_rows * 128u);
-        for (int i = 0; i < n_boxes; ++i)
+        // only the boxes this mesh reaches into: a 100-face mesh of a batch whose largest has 800 loads one box of four
+        const int nb = min(n_boxes, (n_b + box_rows - 1) / box_rows);
+        tc::mbar_arrive_expect_tx(&full[buf], (uint32_t)nb * (uint32_t)box_rows * 128u);
+        for (int i = 0; i < nb; ++i)
           tc::tma_load_2d(sx + (size_t)buf * buf_stride + (size_t)i * box_rows * s4, &tmap, slice * S, r0 + i * box_rows, &full[buf]);
       }
       return;
