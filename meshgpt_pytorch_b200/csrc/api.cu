@@ -557,7 +557,13 @@ int meshtok_tokenize(const meshtok_model* m, const meshtok_tokenize_args* a, voi
     rc = topo_user_edges(a->face_edges, B, E, ragged ? a->edge_offsets : nullptr, a->total_edges, a->pad_id, w.mesh_counts, w.offs, w.counts, w.ecount, w.cursor, w.etmp,
                          w.indptr, w.src, a->edge_capacity, max_rows, w.status, s);
     if (rc != MESHTOK_OK) return rc;
-    if (a->encoded_in == nullptr && (rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, s)) != MESHTOK_OK) return rc;
+    if (a->encoded_in == nullptr) {   // the per-mesh CSR blocks: on the side stream, next to the folded-table sum and the first linear
+      MT_CHECK_CUDA(cudaEventRecord(side->fork, s));
+      MT_CHECK_CUDA(cudaStreamWaitEvent(side->stream, side->fork, 0));
+      if ((rc = launch_local_csr(w.indptr, w.src, a->edge_capacity, w.offs, B, F, w.lcsr, side->stream)) != MESHTOK_OK) return rc;
+      MT_CHECK_CUDA(cudaEventRecord(side->join, side->stream));
+      edges_pending = true;
+    }
   } else if (topo_one) {
     // (everything the aggregation needs came out of the one topology launch)
   } else {
