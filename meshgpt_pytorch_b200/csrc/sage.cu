@@ -363,10 +363,13 @@ __global__ void __launch_bounds__(NTHR, 1) gather_mean_smem_group_kernel(const f
 // One CTA per (mesh, group of `group` consecutive slices), slices double buffered when group >= 2.  The eight threads of a quarter warp
 // (four faces x two halves) read eight different 16-byte chunks in every instruction whatever rows they come from: a face takes its two
 // 8-column pairs in the order (face & 1) and the two chunks of a pair in the order (face >> 1) & 1 - no bank conflicts.
+// (Later finding, same tool: with two threads per face the row loop is no longer issue bound - a loop with half the instructions per
+//  neighbour measured 2 % SLOWER - but bound by the SM's shared-memory / L1 data pipe: a CTA alone on its SM takes 8.3 k cycles for the
+//  loop, two take 16.6 k; 780 16-byte-per-lane reads + bank conflicts + image stores keep that pipe ~58 % busy.  DESIGN section 9.)
 // ---- per-mesh local CSR blocks (round 2, last session) -------------------------------------------------------------------------------
 // clock64 trace of the wide kernel at C2: of a CTA's ~23 k cycles, ~6 k went into its prologue - face / edge offsets, then row pointers
 // and source ids (dependent global round trips), then the conversion into shared memory - repeated by every (mesh, slice) CTA of all
-// five layers.  local_csr_kernel does that conversion ONCE per batch and mesh, into a block with the aggregation kernel's shared-memory
+// five layers.  local_csr_kernel (or, on the default path, the one-launch topology kernel itself) does that conversion ONCE per batch and mesh, into a block with the aggregation kernel's shared-memory
 // layout, so the CTA's prologue is one bulk copy (cp.async.bulk, completion on an mbarrier, issued ahead of griddepcontrol.wait).
 __host__ __device__ inline int lcsr_ptr_bytes(int F) { return (((F + 1) * 4) + 15) & ~15; }
 __host__ __device__ inline int lcsr_src_bytes(int F) { return ((5 * F * 2) + 15) & ~15; }
