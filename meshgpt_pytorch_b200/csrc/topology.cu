@@ -17,7 +17,8 @@
 //      neighbours at the prefix of the degrees - no bitmap, no sort, no warp reductions on this path.
 // The relation is NOT symmetric for degenerate faces (SURVEY hard part 1), hence separate out- and in-degrees.
 //
-// The pipeline uses MODE_MAPS + MODE_EDGES (or ONE launch, MODE_CSR): each CTA takes a mesh by ticket, counts its in-degrees, obtains the
+// The pipeline uses ONE launch, MODE_CSR (MODE_MAPS + MODE_EDGES on two streams is the A/B partner and the form quantize() without an
+// encoder pass and user-supplied edges take): each CTA takes a mesh by ticket, counts its in-degrees, obtains the
 // exclusive prefix of (valid faces, referenced vertices, edges) over the preceding meshes with a warp-wide decoupled
 // look-back over per-mesh descriptors in global memory (aggregate / inclusive-prefix flags, as in single-pass scans),
 // and then emits its slice of the batch-global CSR - no separate count launch, offsets kernel or host sync.  The
