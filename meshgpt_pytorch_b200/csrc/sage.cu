@@ -775,7 +775,15 @@ int launch_gather_mean(const float* x, int d, const int* indptr, const int* src,
       static int stagger = -1;
       if (stagger < 0) { const char* e = getenv("MESHTOK_GATHER_STAGGER"); stagger = e ? atoi(e) : 1000; }
       int n_sm = 148;
-      { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); }
+      {   // SM count of the current device, looked up once per device
+        static int sm_of[64] = {0};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64) {
+          if (sm_of[dev] == 0) { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) sm_of[dev] = v; }
+          if (sm_of[dev] > 0) n_sm = sm_of[dev];
+        }
+      }
       // (512 threads, two CTAs per SM) where a single-slice CTA fits twice; else 1 024 threads and the SM to itself - also with ONE slice per
       // CTA when two buffers of a large mesh do not fit (meshes of ~900 .. 1 700 faces; found by test_meshes_above_800_faces)
       if (group == 1 && 2 * (smem_w + 1024) <= 226 * 1024) {
