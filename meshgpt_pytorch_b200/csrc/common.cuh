@@ -101,6 +101,20 @@ __device__ __forceinline__ void pdl_wait() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #endif
 }
+// -DMESHTOK_BOUNDS=1 (python build.py --variant bounds -DMESHTOK_BOUNDS=1, loaded with MESHTOK_LIBRARY=): device-side index checks that trap
+// with a message.  compute-sanitizer is closed on the GPU pool this was developed on; the GPU test suite run against this build is the
+// memory-safety evidence for the index arithmetic of the kernels that carry the checks.
+#if defined(MESHTOK_BOUNDS) && MESHTOK_BOUNDS
+#define MT_DCHECK(c)                                                                        \
+  do {                                                                                      \
+    if (!(c)) {                                                                             \
+      printf("MT_DCHECK failed: %s (%s:%d, block %d thread %d)\n", #c, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+      __trap();                                                                             \
+    }                                                                                       \
+  } while (0)
+#else
+#define MT_DCHECK(c) do { } while (0)
+#endif
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -394,6 +394,7 @@ __global__ void __launch_bounds__(LFQ_TR * DS / RPT) lfq_rows_kernel(const float
 #pragma unroll
       for (int j = 0; j < LFQ_TR * (LFQ_CH / 4) / NT; ++j) {
         const int idx = tid + j * NT, r = idx >> 3, c4 = idx & 7;
+        MT_DCHECK(r < LFQ_TR && buf >= 0 && buf < 2 && k >= 0 && (k + 1) * LFQ_CH <= D);
         if (tile0 + r < n) {
           const float* src = rows + (size_t)(tile0 + r) * D + k * LFQ_CH + c4 * 4;
           const uint32_t dst = tile_addr + (uint32_t)((buf * LFQ_TR + r) * LFQ_LD + c4 * 4) * 4u;

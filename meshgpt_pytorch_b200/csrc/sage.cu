@@ -397,9 +397,11 @@ __global__ void __launch_bounds__(256) local_csr_kernel(const int* __restrict__ 
   const bool fast = n_e <= edges_cap && e1_true <= cap && (zero_row + 1) * 8 <= 65536;
   const int t = part * blockDim.x + threadIdx.x, nt = LCSR_PARTS * blockDim.x;
   if (t == 0) { hdr[0] = n_e; hdr[1] = fast ? 1 : 0; hdr[2] = e0; hdr[3] = 0; }
-  for (int i = t; i <= n_b; i += nt) sptr[i] = indptr[r0 + i] - e0;
+  MT_DCHECK(n_b >= 0 && n_b <= F && n_e >= 0 && r0 >= 0);
+  for (int i = t; i <= n_b; i += nt) { sptr[i] = indptr[r0 + i] - e0; MT_DCHECK(sptr[i] >= 0 && (long long)e0 + sptr[i] <= e1_true); }
   if (fast)
     for (int q = t; q < n_e; q += nt) {
+      MT_DCHECK(q < edges_cap && (long long)e0 + q < cap);
       const unsigned nb = (unsigned)(src[e0 + q] - r0);   // (always < n_b: edges are intra-mesh; a corrupt list reads the zero row)
       ssrc[q] = (unsigned short)((nb < (unsigned)n_b ? nb : (unsigned)zero_row) * 8u);
     }
@@ -496,6 +498,8 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
     __syncthreads();                 // the barriers exist
     tc::mbar_wait(&full[2], 0);      // header, row pointers and source ids have landed
     n_e = hdr[0]; fast = hdr[1] != 0; e0 = hdr[2];
+    MT_DCHECK(n_e >= 0 && (!fast || n_e <= edges_cap) && n_b >= 0 && n_b <= rows_cap);
+    MT_DCHECK(sptr[0] == 0 && (!fast || sptr[n_b] == n_e));
   } else {
     e0 = __ldcg(edge_off + b);                                 // = indptr[r0]
     const long long e1_true = __ldcg(edge_off + b + 1);        // = indptr[r0 + n_b] (n_b is the whole mesh: rows_cap >= every mesh)
@@ -547,11 +551,13 @@ __global__ void __launch_bounds__(NTHR, CTAS) gather_mean_smem_wide_kernel(const
       const float4* p1b = sxb + 4 * h + 2 * (rot ^ 1) + (sw ^ 1);
       const int s = sptr[lrow];
       const int e_true = sptr[lrow + 1];
+      MT_DCHECK(lrow < n_b && s >= 0 && e_true >= s);
       float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
       const int e = fast ? e_true : min(e_true, n_e);
       for (int q = s; q < e; ++q) {
         int off;
-        if (fast) off = ssrc[q];
+        MT_DCHECK(q >= 0 && (!fast || q < n_e));
+        if (fast) { off = ssrc[q]; MT_DCHECK(off >= 0 && off <= zero_row * s4 && (off & (s4 - 1)) == 0); }
         else {   // a mesh with more edges than the staging area holds, or a list cut by the edge capacity
           const unsigned nb = (unsigned)(__ldg(src + e0 + q) - r0);
           off = (int)(nb < (unsigned)n_b ? nb : (unsigned)zero_row) * s4;

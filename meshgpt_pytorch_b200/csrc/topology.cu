@@ -255,10 +255,13 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
         const int mybase = counting ? 0 : fptr[i];
         if (!counting && nc > 0) {   // the whole list is in the cache: copy it out
           const int deg = (i + 1 < F ? fptr[i + 1] : mesh_edges) - mybase;
+          MT_DCHECK(deg >= 0 && mybase >= 0 && mybase + deg <= mesh_edges);
           if (deg <= nc) {
             for (int q = 0; q < deg; ++q) {
               const long long at = (long long)edge_off + mybase + q;
+              MT_DCHECK(ncache[i * nc + q] < F);
               const int fr = frank[ncache[i * nc + q]];
+              MT_DCHECK(fr >= 0 && fr < nvalid);
               if (at < p.edge_capacity) p.src[at] = face_off + fr;
               if (lsrc != nullptr && mybase + q < 5 * F) lsrc[mybase + q] = (unsigned short)(fr * 8);
             }
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(1024, 1) topology_kernel(TopoParams p) {
     if (lblk != nullptr) {   // header and row pointers of the local CSR block (the source ids went out with the edges above)
       int* lptr = reinterpret_cast<int*>(lblk + 16);
       for (int f = tid; f < F; f += nt)
-        if (face_valid(f)) lptr[frank[f]] = fptr[f];
+        if (face_valid(f)) { MT_DCHECK(frank[f] >= 0 && frank[f] < nvalid && 16 + 4 * (nvalid + 1) <= 16 + p.lcsr_ptr_bytes); lptr[frank[f]] = fptr[f]; }
       if (tid == 0) {
         lptr[nvalid] = mesh_total;
         const long long e1 = (long long)edge_off + mesh_total;
