@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(NT, 1) face_sum_pair_kernel(FeatParams p, int 
     float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
 #pragma unroll
     for (int j = 0; j < HW; ++j) {
+      MT_DCHECK((int)(wf[j] & 0xffffu) < lines && (int)(wf[j] >> 16) < lines && (int)(ws[j] & 0xffffu) < lines && (int)(ws[j] >> 16) < lines);
       const float4 f0 = tf[(wf[j] & 0xffffu) * 8];
       const float4 s0 = ts[(ws[j] & 0xffffu) * 8];
       const float4 f1 = tf[(wf[j] >> 16) * 8];

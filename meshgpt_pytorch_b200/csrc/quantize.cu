@@ -27,10 +27,12 @@ __global__ void __launch_bounds__(256) scatter_mean_kernel(const float* __restri
   const int d2 = D >> 1;
   for (int row = blockIdx.x * wpb + warp_id(); row < n; row += gridDim.x * wpb) {
     const int s = vptr[row], e = vptr[row + 1];
+    MT_DCHECK(s >= 0 && e >= s && e <= counts->n_faces * 4);
     float2 acc[PER2];
 #pragma unroll
     for (int i = 0; i < PER2; ++i) acc[i] = make_float2(0.f, 0.f);
     for (int q = s; q < e; ++q) {
+      MT_DCHECK(vinc[q] >= 0 && vinc[q] < counts->n_faces * 4);
       const float2* yr = reinterpret_cast<const float2*>(y + (size_t)vinc[q] * D);
 #pragma unroll
       for (int i = 0; i < PER2; ++i) {
@@ -239,7 +241,9 @@ __global__ void __launch_bounds__(256) gather_codes_kernel(const int64_t* __rest
   }
   const int b = pf / F;
   const long long v = faces[tok];
+  MT_DCHECK(v >= 0 && v < V);
   const int vr = vert_row[(size_t)b * V + v];
+  MT_DCHECK(vr >= 0 && (long long)vr < (long long)BF / F * V);
   for (int q = 0; q < Q; ++q) {
     dst[q] = vcodes[(size_t)vr * Q + q];
   }
